@@ -1,0 +1,389 @@
+"""TEST INFRASTRUCTURE ONLY — ctypes bindings for the CPU oracle (oracle/libmsm_oracle.so,
+our restatement) and for the compiled reference (oracle/_ref/libref_newresampler.so).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module; the product package newmsm_b200 never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(_HERE, "libmsm_oracle.so")
+REF_SO = os.path.join(_HERE, "_ref", "libref_newresampler.so")
+REFERENCE_ROOT = "/root/reference"
+
+_vp, _i, _d = C.c_void_p, C.c_int, C.c_double
+
+
+def build(ref: bool | None = None) -> None:
+    """Compile the oracle restatement, and the reference build when /root/reference exists."""
+    subprocess.run(["make", "-s", "-C", _HERE, "oracle"], check=True)
+    if ref is None:
+        ref = os.path.isdir(REFERENCE_ROOT)
+    if ref:
+        subprocess.run(["make", "-s", "-C", _HERE, "ref"], check=True)
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_SO)
+
+
+def _p(a):
+    return a.ctypes.data_as(_vp) if a is not None else None
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+# --------------------------------------------------------------------------------------
+# our restatement
+# --------------------------------------------------------------------------------------
+class Oracle:
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            if not os.path.exists(ORACLE_SO):
+                build(ref=False)
+            L = C.CDLL(ORACLE_SO)
+            L.orc_octree_build.restype = _vp
+            L.orc_octree_build.argtypes = [_i, _vp, _i, _vp]
+            L.orc_octree_free.argtypes = [_vp]
+            L.orc_octree_dump.argtypes = [_vp, _vp, _vp, _i, _vp, _i, _vp]
+            L.orc_octree_query.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i]
+            L.orc_bary_weights.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _i]
+            L.orc_vertex_areas.argtypes = [_i, _vp, _i, _vp, _vp]
+            L.orc_adaptive_weights.argtypes = [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i]
+            L.orc_metric_resample.argtypes = [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i]
+            L.orc_bary_resample.argtypes = [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i]
+            L.orc_sphere_project_warp.argtypes = [_i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i]
+            L.orc_surface_resample.argtypes = [_i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i]
+            L.orc_nn_resample.argtypes = [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i]
+            L.orc_rotation_matrix.argtypes = [_vp, _vp, _vp]
+            for f in (L.orc_corr, L.orc_ssd):
+                f.restype = _d
+                f.argtypes = [_i, _vp, _vp, _vp]
+            L.orc_sim_for_min.restype = _d
+            L.orc_sim_for_min.argtypes = [_i, _i, _vp, _vp, _vp]
+            L.orc_patch_membership.argtypes = [_i, _vp, _i, _vp, _vp, _d, _vp, _vp, _i, _i]
+            L.orc_unary_costs.argtypes = [_i, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp,
+                                          _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i]
+            cls._lib = L
+        return cls._lib
+
+
+class OracleOctree:
+    """octree.cpp restated; see oracle/msm_oracle.h."""
+
+    def __init__(self, xyz, tri):
+        self.xyz, self.tri = _f64(xyz), _i32(tri)
+        self.L = Oracle.lib()
+        self.h = self.L.orc_octree_build(len(self.xyz), _p(self.xyz), len(self.tri), _p(self.tri))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_octree_free(self.h)
+            self.h = None
+
+    def dump(self):
+        nt = C.c_int()
+        n = self.L.orc_octree_dump(self.h, None, None, 0, None, 0, C.byref(nt))
+        kinds, counts, tris = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(nt.value, np.int32)
+        self.L.orc_octree_dump(self.h, _p(kinds), _p(counts), n, _p(tris), nt.value, C.byref(nt))
+        return kinds, counts, tris
+
+    def query(self, pts, nthreads=8):
+        pts = _f64(pts)
+        n = len(pts)
+        tri, vtx = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        st, path = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        self.L.orc_octree_query(self.h, n, _p(pts), _p(tri), _p(vtx), _p(st), _p(path), nthreads)
+        return tri, vtx, st, path
+
+    def bary_weights(self, pts, nthreads=8):
+        pts = _f64(pts)
+        n = len(pts)
+        idx, w, ne = np.zeros((n, 3), np.int32), np.zeros((n, 3)), np.zeros(n, np.int32)
+        err = self.L.orc_bary_weights(self.h, n, _p(pts), _p(idx), _p(w), _p(ne), nthreads)
+        return idx, w, ne, err
+
+
+def oracle_vertex_areas(xyz, tri):
+    xyz, tri = _f64(xyz), _i32(tri)
+    out = np.zeros(len(xyz))
+    Oracle.lib().orc_vertex_areas(len(xyz), _p(xyz), len(tri), _p(tri), _p(out))
+    return out
+
+
+def _csr_call(fn, nrows, *args):
+    rowptr = np.zeros(nrows + 1, np.int32)
+    nnz = fn(*args, _p(rowptr), None, None, 0)
+    if nnz < 0:
+        raise RuntimeError("query failed")
+    col, val = np.zeros(nnz, np.int32), np.zeros(nnz)
+    fn(*args, _p(rowptr), _p(col), _p(val), nnz)
+    return rowptr, col, val
+
+
+def oracle_adaptive_weights(xyz_in, tri_in, xyz_low, tri_low):
+    a, b, c, d = _f64(xyz_in), _i32(tri_in), _f64(xyz_low), _i32(tri_low)
+    return _csr_call(Oracle.lib().orc_adaptive_weights, len(c), len(a), _p(a), len(b), _p(b), len(c), _p(c), len(d), _p(d))
+
+
+def oracle_metric_resample(xyz_in, tri_in, xyz_low, tri_low, feat, nthreads=8):
+    a, b, c, d, f = _f64(xyz_in), _i32(tri_in), _f64(xyz_low), _i32(tri_low), _f64(feat)
+    out = np.zeros((f.shape[0], len(c)))
+    e = Oracle.lib().orc_metric_resample(len(a), _p(a), len(b), _p(b), len(c), _p(c), len(d), _p(d),
+                                         f.shape[0], _p(f), _p(out), nthreads)
+    if e:
+        raise RuntimeError(f"oracle metric_resample failed ({e})")
+    return out
+
+
+def oracle_bary_resample(xyz_in, tri_in, xyz_low, feat, nthreads=8):
+    a, b, c, f = _f64(xyz_in), _i32(tri_in), _f64(xyz_low), _f64(feat)
+    out = np.zeros((f.shape[0], len(c)))
+    e = Oracle.lib().orc_bary_resample(len(a), _p(a), len(b), _p(b), len(c), _p(c), f.shape[0], _p(f), _p(out), nthreads)
+    if e:
+        raise RuntimeError(f"oracle bary_resample failed ({e})")
+    return out
+
+
+def oracle_sphere_project_warp(sphere, from_xyz, tri, to_xyz, nthreads=8):
+    s, a, t, b = _f64(sphere), _f64(from_xyz), _i32(tri), _f64(to_xyz)
+    out = np.zeros_like(s)
+    e = Oracle.lib().orc_sphere_project_warp(len(s), _p(s), len(a), _p(a), len(t), _p(t), _p(b), _p(out), nthreads)
+    if e:
+        raise RuntimeError("oracle sphere_project_warp failed")
+    return out
+
+
+def oracle_surface_resample(low, sph, tri, anat, nthreads=8):
+    s, a, t, b = _f64(low), _f64(sph), _i32(tri), _f64(anat)
+    out = np.zeros_like(s)
+    e = Oracle.lib().orc_surface_resample(len(s), _p(s), len(a), _p(a), len(t), _p(t), _p(b), _p(out), nthreads)
+    if e:
+        raise RuntimeError("oracle surface_resample failed")
+    return out
+
+
+def oracle_nn_resample(low, xyz, tri, feat, nthreads=8):
+    s, a, t, f = _f64(low), _f64(xyz), _i32(tri), _f64(feat)
+    out = np.zeros((f.shape[0], len(s)))
+    e = Oracle.lib().orc_nn_resample(len(s), _p(s), len(a), _p(a), len(t), _p(t), f.shape[0], _p(f), _p(out), nthreads)
+    if e:
+        raise RuntimeError("oracle nn_resample failed")
+    return out
+
+
+def oracle_rotation_matrix(ci, index):
+    a, b, R = _f64(ci), _f64(index), np.zeros(9)
+    Oracle.lib().orc_rotation_matrix(_p(a), _p(b), _p(R))
+    return R.reshape(3, 3)
+
+
+def oracle_sim(simmeasure, A, B, w):
+    A, B, w = _f64(A), _f64(B), _f64(w)
+    return Oracle.lib().orc_sim_for_min(simmeasure, len(A), _p(A), _p(B), _p(w))
+
+
+def oracle_patch_membership(cp_xyz, src_xyz, maxsep, rng, nthreads=8):
+    cp, s, ms = _f64(cp_xyz), _f64(src_xyz), _f64(maxsep)
+    rowptr = np.zeros(len(cp) + 1, np.int32)
+    L = Oracle.lib()
+    n = L.orc_patch_membership(len(cp), _p(cp), len(s), _p(s), _p(ms), rng, _p(rowptr), None, 0, nthreads)
+    mem = np.zeros(n, np.int32)
+    L.orc_patch_membership(len(cp), _p(cp), len(s), _p(s), _p(ms), rng, _p(rowptr), _p(mem), n, nthreads)
+    return rowptr, mem
+
+
+def oracle_unary_costs(kind, simmeasure, tree: OracleOctree, cp_xyz, rot, labels, src_xyz, prow, pmem,
+                       src_feat, ref_feat, cfw, absw, want_tri=False, nthreads=8):
+    cp, rot, labels, src = _f64(cp_xyz), _f64(rot), _f64(labels), _f64(src_xyz)
+    prow, pmem = _i32(prow), _i32(pmem)
+    sf, rf, absw = _f64(np.atleast_2d(src_feat)), _f64(np.atleast_2d(ref_feat)), _f64(absw)
+    D = sf.shape[0]
+    cfw_rows = 0 if cfw is None else np.atleast_2d(cfw).shape[0]
+    cfw_a = None if cfw is None else _f64(np.atleast_2d(cfw))
+    Lb = len(labels)
+    out = np.zeros((Lb, len(cp)))
+    tri_out = np.zeros((Lb, int(prow[-1])), np.int32) if want_tri else None
+    e = Oracle.lib().orc_unary_costs(kind, simmeasure, tree.h, len(cp), _p(cp), _p(rot), Lb, _p(labels),
+                                     len(src), _p(src), _p(prow), _p(pmem), D, _p(sf), _p(rf),
+                                     cfw_rows, _p(cfw_a), _p(absw), _p(out), _p(tri_out), nthreads)
+    if e:
+        raise RuntimeError("oracle unary costs: a query failed")
+    return (out, tri_out) if want_tri else out
+
+
+# --------------------------------------------------------------------------------------
+# compiled reference (oracle/_ref)
+# --------------------------------------------------------------------------------------
+class Ref:
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            if not have_ref():
+                raise RuntimeError("oracle/_ref/libref_newresampler.so not built (needs /root/reference; run `make -C oracle ref`)")
+            L = C.CDLL(REF_SO)
+            L.ref_mesh_new.restype = _vp
+            L.ref_mesh_new.argtypes = [_i, _vp, _i, _vp]
+            L.ref_mesh_icosa.restype = _vp
+            L.ref_mesh_icosa.argtypes = [_i, _d]
+            L.ref_mesh_free.argtypes = [_vp]
+            L.ref_mesh_nvertices.argtypes = [_vp]
+            L.ref_mesh_ntriangles.argtypes = [_vp]
+            L.ref_mesh_export.argtypes = [_vp, _vp, _vp]
+            L.ref_mesh_set_pvalues.argtypes = [_vp, _i, _vp]
+            L.ref_vertex_areas.argtypes = [_vp, _vp]
+            L.ref_octree_new.restype = _vp
+            L.ref_octree_new.argtypes = [_vp]
+            L.ref_octree_free.argtypes = [_vp]
+            L.ref_octree_query.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _i]
+            L.ref_octree_dump.argtypes = [_vp, _vp, _vp, _i, _vp, _i, _vp]
+            L.ref_bary_weights.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i]
+            L.ref_adaptive_weights.argtypes = [_vp, _vp, _i, _vp, _vp, _vp, _i]
+            L.ref_metric_resample.restype = _d
+            L.ref_metric_resample.argtypes = [_vp, _vp, _i, _vp]
+            L.ref_bary_resample.restype = _d
+            L.ref_bary_resample.argtypes = [_vp, _vp, _i, _vp]
+            L.ref_sphere_project_warp.argtypes = [_vp, _vp, _vp, _i, _vp]
+            L.ref_surface_resample.argtypes = [_vp, _vp, _vp, _i, _vp]
+            L.ref_nn_resample.argtypes = [_vp, _vp, _i, _vp]
+            L.ref_rotation_matrix.argtypes = [_vp, _vp, _vp]
+            cls._lib = L
+        return cls._lib
+
+
+class RefMesh:
+    def __init__(self, xyz=None, tri=None, icosa=None, radius=100.0, feat=None):
+        self.L = Ref.lib()
+        if icosa is not None:
+            self.h = self.L.ref_mesh_icosa(int(icosa), float(radius))
+        else:
+            xyz, tri = _f64(xyz), _i32(tri)
+            self.h = self.L.ref_mesh_new(len(xyz), _p(xyz), len(tri), _p(tri))
+        self.nv = self.L.ref_mesh_nvertices(self.h)
+        self.nt = self.L.ref_mesh_ntriangles(self.h)
+        if feat is not None:
+            self.set_features(feat)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.ref_mesh_free(self.h)
+            self.h = None
+
+    def export(self):
+        xyz, tri = np.zeros((self.nv, 3)), np.zeros((self.nt, 3), np.int32)
+        self.L.ref_mesh_export(self.h, _p(xyz), _p(tri))
+        return xyz, tri
+
+    def set_features(self, feat):
+        f = _f64(np.atleast_2d(feat))
+        assert f.shape[1] == self.nv
+        self.D = f.shape[0]
+        self.L.ref_mesh_set_pvalues(self.h, f.shape[0], _p(f))
+
+    def vertex_areas(self):
+        out = np.zeros(self.nv)
+        self.L.ref_vertex_areas(self.h, _p(out))
+        return out
+
+
+class RefOctree:
+    def __init__(self, mesh: RefMesh):
+        self.mesh = mesh
+        self.L = Ref.lib()
+        self.h = self.L.ref_octree_new(mesh.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.ref_octree_free(self.h)
+            self.h = None
+
+    def dump(self):
+        nt = C.c_int()
+        n = self.L.ref_octree_dump(self.h, None, None, 0, None, 0, C.byref(nt))
+        kinds, counts, tris = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(nt.value, np.int32)
+        self.L.ref_octree_dump(self.h, _p(kinds), _p(counts), n, _p(tris), nt.value, C.byref(nt))
+        return kinds, counts, tris
+
+    def query(self, pts, nthreads=8):
+        pts = _f64(pts)
+        n = len(pts)
+        tri, vtx, st = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32)
+        self.L.ref_octree_query(self.h, n, _p(pts), _p(tri), _p(vtx), _p(st), nthreads)
+        return tri, vtx, st
+
+    def bary_weights(self, low: RefMesh, nthreads=8):
+        n = low.nv
+        idx, w, ne = np.zeros((n, 3), np.int32), np.zeros((n, 3)), np.zeros(n, np.int32)
+        err = self.L.ref_bary_weights(low.h, self.mesh.h, self.h, _p(idx), _p(w), _p(ne), nthreads)
+        return idx, w, ne, err
+
+
+def ref_adaptive_weights(m_in: RefMesh, m_low: RefMesh, nthreads=1):
+    L = Ref.lib()
+    rowptr = np.zeros(m_low.nv + 1, np.int32)
+    cap = 64 * max(m_low.nv, m_in.nv)
+    col, val = np.zeros(cap, np.int32), np.zeros(cap)
+    nnz = L.ref_adaptive_weights(m_in.h, m_low.h, nthreads, _p(rowptr), _p(col), _p(val), cap)
+    if nnz < 0 or nnz > cap:
+        raise RuntimeError("reference adaptive weights failed")
+    return rowptr, col[:nnz].copy(), val[:nnz].copy()
+
+
+def ref_metric_resample(m_in: RefMesh, m_low: RefMesh, nthreads=1, want_out=True):
+    out = np.zeros((m_in.D, m_low.nv)) if want_out else None
+    secs = Ref.lib().ref_metric_resample(m_in.h, m_low.h, nthreads, _p(out))
+    if secs < 0:
+        raise RuntimeError("reference metric_resample failed")
+    return out, secs
+
+
+def ref_bary_resample(m_in: RefMesh, m_low: RefMesh, nthreads=1, want_out=True):
+    out = np.zeros((m_in.D, m_low.nv)) if want_out else None
+    secs = Ref.lib().ref_bary_resample(m_in.h, m_low.h, nthreads, _p(out))
+    if secs < 0:
+        raise RuntimeError("reference bary_resample failed")
+    return out, secs
+
+
+def ref_sphere_project_warp(sphere: RefMesh, m_from: RefMesh, m_to: RefMesh, nthreads=1):
+    out = np.zeros((sphere.nv, 3))
+    if Ref.lib().ref_sphere_project_warp(sphere.h, m_from.h, m_to.h, nthreads, _p(out)):
+        raise RuntimeError("reference sphere_project_warp failed")
+    return out
+
+
+def ref_surface_resample(anat: RefMesh, sph: RefMesh, low: RefMesh, nthreads=1):
+    out = np.zeros((low.nv, 3))
+    if Ref.lib().ref_surface_resample(anat.h, sph.h, low.h, nthreads, _p(out)):
+        raise RuntimeError("reference surface_resample failed")
+    return out
+
+
+def ref_nn_resample(m_in: RefMesh, m_low: RefMesh, nthreads=1):
+    out = np.zeros((m_in.D, m_low.nv))
+    if Ref.lib().ref_nn_resample(m_in.h, m_low.h, nthreads, _p(out)):
+        raise RuntimeError("reference nn resample failed")
+    return out
+
+
+def ref_rotation_matrix(ci, index):
+    a, b, R = _f64(ci), _f64(index), np.zeros(9)
+    Ref.lib().ref_rotation_matrix(_p(a), _p(b), _p(R))
+    return R.reshape(3, 3)

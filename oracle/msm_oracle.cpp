@@ -1,0 +1,685 @@
+// TEST INFRASTRUCTURE ONLY — see msm_oracle.h. CPU restatement of the reference hot path,
+// written from the reference's behaviour (file:line cited per function), own data structures.
+// Compiled with -O2 -ffp-contract=off (no FMA) so FP64 decisions are IEEE-reproducible.
+#include "msm_oracle.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <numeric>
+#include <vector>
+
+namespace {
+
+constexpr double EPS = 1e-8;   // point.h:31
+constexpr double RAD = 100.0;  // point.h:32
+constexpr int MAX_TRIANGLES = 50; // node.h:33
+constexpr double MESH_BOUNDS = 101.0; // octree.h:37
+constexpr double NOT_IN_TRIANGLE = -1.0; // octree.h:35
+constexpr double DMAX = std::numeric_limits<double>::max();
+
+struct P3 { double X, Y, Z; };
+
+inline P3 sub(const P3& a, const P3& b) { return {a.X - b.X, a.Y - b.Y, a.Z - b.Z}; }      // point.cpp:185
+inline P3 mul(const P3& a, double d) { return {a.X * d, a.Y * d, a.Z * d}; }                // point.cpp:198
+inline double dot(const P3& a, const P3& b) { return a.X * b.X + a.Y * b.Y + a.Z * b.Z; }   // point.cpp:173
+inline P3 cross(const P3& a, const P3& b) {                                                 // point.cpp:177
+    return {a.Y * b.Z - a.Z * b.Y, b.X * a.Z - b.Z * a.X, a.X * b.Y - b.X * a.Y};
+}
+inline double norm(const P3& a) { return std::sqrt(a.X * a.X + a.Y * a.Y + a.Z * a.Z); }     // point.h:44
+inline void normalize(P3& a) {                                                              // point.cpp:26
+    double n = norm(a);
+    if (n > EPS) { a.X /= n; a.Y /= n; a.Z /= n; }
+}
+inline P3 matvec(const double* M, const P3& v) {                                            // point.cpp:202
+    return {M[0] * v.X + M[1] * v.Y + M[2] * v.Z,
+            M[3] * v.X + M[4] * v.Y + M[5] * v.Z,
+            M[6] * v.X + M[7] * v.Y + M[8] * v.Z};
+}
+
+// point.cpp:46-61
+inline P3 project_point(const P3& vb, const P3& v1, const P3& v2, const P3& v3) {
+    P3 s1 = sub(v3, v1); normalize(s1);
+    P3 s2 = sub(v2, v1); normalize(s2);
+    P3 s3 = cross(s1, s2); normalize(s3);
+    double si = dot(s3, v1) / dot(s3, vb);
+    return mul(vb, si);
+}
+// point.cpp:36-44
+inline bool same_side(const P3& p1, const P3& p2, const P3& a, const P3& b) {
+    return dot(cross(sub(b, a), sub(p1, a)), cross(sub(b, a), sub(p2, a))) > -EPS;
+}
+inline bool point_in_triangle(const P3& p, const P3& a, const P3& b, const P3& c) {
+    return same_side(p, a, b, c) && same_side(p, b, c, a) && same_side(p, c, a, b);
+}
+// point.cpp:68-75
+inline double compute_area(const P3& v0, const P3& v1, const P3& v2) {
+    return 0.5 * norm(cross(sub(v1, v0), sub(v2, v0)));
+}
+// triangle.cpp:85-122
+inline double dist_to_point(const P3& x0, const P3& x1, const P3& x2, const P3& x3) {
+    double d, dmin = DMAX;
+    P3 u = sub(x2, x1);
+    if (dot(sub(x0, x1), u) > 0 && dot(sub(x0, x2), u) < 0) {
+        d = norm(cross(sub(x0, x1), sub(x0, x2))) / norm(sub(x2, x1));
+        if (d < dmin) dmin = d;
+    }
+    u = sub(x3, x1);
+    if (dot(sub(x0, x1), u) > 0 && dot(sub(x0, x3), u) < 0) {
+        d = norm(cross(sub(x0, x1), sub(x0, x3))) / norm(sub(x3, x1));
+        if (d < dmin) dmin = d;
+    }
+    u = sub(x3, x2);
+    if (dot(sub(x0, x2), u) > 0 && dot(sub(x0, x3), u) < 0) {
+        d = norm(cross(sub(x0, x2), sub(x0, x3))) / norm(sub(x3, x2));
+        if (d < dmin) dmin = d;
+    }
+    d = norm(sub(x0, x1)); if (d < dmin) dmin = d;
+    d = norm(sub(x0, x2)); if (d < dmin) dmin = d;
+    d = norm(sub(x0, x3)); if (d < dmin) dmin = d;
+    return dmin;
+}
+
+struct ONode {
+    double b[3][3];       // [axis][lo, mid, hi]  (node.h:42)
+    bool leaf = true;
+    ONode* ch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // index = i*4+j*2+k
+    ONode* parent = nullptr;
+    std::vector<int> tris;
+    ~ONode() { for (auto* c : ch) delete c; }
+};
+
+} // namespace
+
+struct orc_octree {
+    ONode* root = nullptr;
+    int nv = 0, nt = 0;
+    std::vector<P3> v;
+    std::vector<int> tri;
+    ~orc_octree() { delete root; }
+    const P3& tv(int t, int k) const { return v[tri[3 * t + k]]; }
+};
+
+namespace {
+
+// node.cpp:67-77 (closed box)
+inline bool contains_point(const ONode* n, const P3& p) {
+    const double q[3] = {p.X, p.Y, p.Z};
+    for (int i = 0; i < 3; ++i) {
+        if (q[i] < n->b[i][0]) return false;
+        if (q[i] > n->b[i][2]) return false;
+    }
+    return true;
+}
+// node.cpp:112-120 (closed AABB overlap)
+inline bool can_contain(const ONode* n, const double* lo, const double* hi) {
+    for (int i = 0; i < 3; ++i)
+        if (hi[i] < n->b[i][0] || lo[i] > n->b[i][2]) return false;
+    return true;
+}
+// node.cpp:91-110
+void make_children(ONode* n) {
+    n->leaf = false;
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j)
+            for (int k = 0; k < 2; ++k) {
+                ONode* c = new ONode();
+                const int o[3] = {i, j, k};
+                for (int a = 0; a < 3; ++a) {
+                    c->b[a][0] = n->b[a][o[a]];
+                    c->b[a][2] = n->b[a][o[a] + 1];
+                    c->b[a][1] = (c->b[a][0] + c->b[a][2]) / 2.0;
+                }
+                c->parent = n;
+                n->ch[i * 4 + j * 2 + k] = c;
+            }
+}
+
+void tri_aabb(const orc_octree* T, int t, double* lo, double* hi) { // octree.cpp:46-59
+    const P3& a = T->tv(t, 0);
+    lo[0] = hi[0] = a.X; lo[1] = hi[1] = a.Y; lo[2] = hi[2] = a.Z;
+    for (int k = 1; k < 3; ++k) {
+        const P3& p = T->tv(t, k);
+        const double q[3] = {p.X, p.Y, p.Z};
+        for (int i = 0; i < 3; ++i) {
+            if (q[i] < lo[i]) lo[i] = q[i];
+            if (q[i] > hi[i]) hi[i] = q[i];
+        }
+    }
+}
+
+// octree.cpp:63-141
+void add_triangle(orc_octree* T, ONode* n, int t, const double* lo, const double* hi) {
+    if (n->leaf) {
+        n->tris.push_back(t);
+        const int num = (int)n->tris.size();
+        if (num >= MAX_TRIANGLES) {
+            int total_size = 0, num_split = 0;
+            double tlo[3], thi[3];
+            for (int i = 0; i < num; ++i) {
+                tri_aabb(T, n->tris[i], tlo, thi);
+                int split_size = 8;
+                for (int d = 0; d < 3; ++d) // node.cpp:79-89: containing_oct uses strict '<' against the midpoint
+                    if ((tlo[d] < n->b[d][1]) == (thi[d] < n->b[d][1])) split_size >>= 1;
+                total_size += split_size;
+                if (split_size != 8) ++num_split;
+            }
+            if (num_split > 0 && total_size < 3 * num) {
+                make_children(n);
+                for (int i = 0; i < num; ++i) {
+                    tri_aabb(T, n->tris[i], tlo, thi);
+                    for (int c = 0; c < 8; ++c)
+                        if (can_contain(n->ch[c], tlo, thi)) add_triangle(T, n->ch[c], n->tris[i], tlo, thi);
+                }
+                n->tris.clear();
+            }
+        }
+    } else {
+        for (int c = 0; c < 8; ++c)
+            if (can_contain(n->ch[c], lo, hi)) add_triangle(T, n->ch[c], t, lo, hi);
+    }
+}
+
+// octree.cpp:143-154
+inline double distance_to_triangle(const orc_octree* T, const P3& pt, int t) {
+    const P3 &v0 = T->tv(t, 0), &v1 = T->tv(t, 1), &v2 = T->tv(t, 2);
+    P3 mP = project_point(pt, v0, v1, v2);
+    if (point_in_triangle(mP, v0, v1, v2)) return dist_to_point(mP, v0, v1, v2);
+    return NOT_IN_TRIANGLE;
+}
+
+// octree.cpp:156-214. Returns triangle id or -1; *status as in the header.
+int closest_triangle(const orc_octree* T, const P3& pt, int* status, int* path) {
+    if (!contains_point(T->root, pt)) { *status = 1; return -1; }
+    int best = -1;
+    double best_d = DMAX;
+    const ONode* cur = T->root;
+    while (!cur->leaf) {
+        // the reference's range-for keeps iterating the ORIGINAL node's children while
+        // reassigning current_oct, so the LAST containing child wins
+        const ONode* next = cur;
+        for (int c = 0; c < 8; ++c)
+            if (contains_point(cur->ch[c], pt)) next = cur->ch[c];
+        cur = next;
+    }
+    for (int t : cur->tris) {
+        double d = distance_to_triangle(T, pt, t);
+        if (d > NOT_IN_TRIANGLE && d < best_d) { best = t; best_d = d; }
+    }
+    int used = 0;
+    if (best < 0) {
+        if (!cur->parent) { *status = 2; return -1; } // reference dereferences nullptr here (App. A.4)
+        used = 1;
+        best_d = DMAX;
+        for (int c = 0; c < 8; ++c)
+            for (int t : cur->parent->ch[c]->tris) {
+                double d = distance_to_triangle(T, pt, t);
+                if (d > NOT_IN_TRIANGLE && d < best_d) { best = t; best_d = d; }
+            }
+    }
+    if (best < 0) {
+        used = 2;
+        best_d = DMAX;
+        for (int c = 0; c < 8; ++c)
+            for (int t : cur->parent->ch[c]->tris)
+                for (int k = 0; k < 3; ++k) {
+                    double d = 2 * RAD * std::asin(norm(sub(T->tv(t, k), pt)) / (2 * RAD));
+                    if (d < best_d) { best = t; best_d = d; }
+                }
+    }
+    if (best < 0) { *status = 2; return -1; }
+    *status = 0;
+    if (path) *path = used;
+    return best;
+}
+
+// octree.cpp:216-233
+int closest_vertex_of(const orc_octree* T, const P3& pt, int t) {
+    double dist = DMAX;
+    int id = 0;
+    for (int k = 0; k < 3; ++k) {
+        double d = norm(sub(pt, T->tv(t, k)));
+        if (d < dist) { id = T->tri[3 * t + k]; dist = d; }
+    }
+    return id;
+}
+
+// triangle.cpp:124-143 -> entries in ascending key order (std::map semantics)
+int bary_weights_of(const orc_octree* T, const P3& p, int t, int* idx, double* w) {
+    const P3 &v1 = T->tv(t, 0), &v2 = T->tv(t, 1), &v3 = T->tv(t, 2);
+    P3 PP = project_point(p, v1, v2, v3);
+    double Aa = compute_area(PP, v2, v3);
+    double Ab = compute_area(PP, v1, v3);
+    double Ac = compute_area(PP, v1, v2);
+    double A = Aa + Ab + Ac;
+    std::map<int, double> m;
+    m[T->tri[3 * t]] = Aa / A;
+    m[T->tri[3 * t + 1]] = Ab / A;
+    m[T->tri[3 * t + 2]] = Ac / A;
+    int j = 0;
+    for (auto& it : m) { idx[j] = it.first; w[j] = it.second; ++j; }
+    int n = j;
+    for (; j < 3; ++j) { idx[j] = -1; w[j] = 0.0; }
+    return n;
+}
+
+// triangle.cpp:145-157 (NO projection of vref)
+inline void bary_interp_weights(const P3& v1, const P3& v2, const P3& v3, const P3& vref, double* w) {
+    double Aa = compute_area(vref, v2, v3);
+    double Ab = compute_area(vref, v1, v3);
+    double Ac = compute_area(vref, v1, v2);
+    double A = Aa + Ab + Ac;
+    w[0] = Aa / A; w[1] = Ab / A; w[2] = Ac / A;
+}
+
+orc_octree* build_tree(int nv, const double* xyz, int nt, const int* tri) {
+    orc_octree* T = new orc_octree();
+    T->nv = nv; T->nt = nt;
+    T->v.resize(nv);
+    for (int i = 0; i < nv; ++i) T->v[i] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+    T->tri.assign(tri, tri + 3 * (size_t)nt);
+    T->root = new ONode();
+    for (int a = 0; a < 3; ++a) { // octree.cpp:31-40, node.cpp:43-57
+        T->root->b[a][0] = -MESH_BOUNDS;
+        T->root->b[a][2] = MESH_BOUNDS;
+        T->root->b[a][1] = (T->root->b[a][0] + T->root->b[a][2]) / 2.0;
+    }
+    double lo[3], hi[3];
+    for (int t = 0; t < nt; ++t) { // octree.cpp:42-61
+        tri_aabb(T, t, lo, hi);
+        add_triangle(T, T->root, t, lo, hi);
+    }
+    return T;
+}
+
+void dump(const ONode* n, std::vector<int>& kinds, std::vector<int>& counts, std::vector<int>& tris) {
+    kinds.push_back(n->leaf ? 1 : 0);
+    counts.push_back((int)n->tris.size());
+    tris.insert(tris.end(), n->tris.begin(), n->tris.end());
+    if (!n->leaf) for (int c = 0; c < 8; ++c) dump(n->ch[c], kinds, counts, tris);
+}
+
+struct Weights { std::vector<std::map<int, double>> rows; };
+
+// resampler.cpp:142-167
+int bary_weight_maps(const orc_octree* T, int n, const double* pts, std::vector<std::map<int, double>>& out) {
+    out.assign(n, {});
+    int err = 0;
+    #pragma omp parallel for
+    for (int k = 0; k < n; ++k) {
+        P3 p{pts[3 * k], pts[3 * k + 1], pts[3 * k + 2]};
+        int st;
+        int t = closest_triangle(T, p, &st, nullptr);
+        if (t < 0) {
+            #pragma omp critical
+            { if (!err) err = st; }
+            continue;
+        }
+        int idx[3]; double w[3];
+        int m = bary_weights_of(T, p, t, idx, w);
+        for (int j = 0; j < m; ++j) out[k][idx[j]] = w[j];
+    }
+    return err;
+}
+
+void vertex_areas(int nv, const double* xyz, int nt, const int* tri, double* out) {
+    // Triangle::calc_area (triangle.cpp:47-50) summed per vertex in push order (= ascending
+    // triangle id, mesh.cpp:112-118), divided by the number of adjacent triangles (mesh.cpp:1275)
+    std::vector<double> sum(nv, 0.0);
+    std::vector<int> cnt(nv, 0);
+    for (int t = 0; t < nt; ++t) {
+        P3 a{xyz[3 * tri[3 * t]], xyz[3 * tri[3 * t] + 1], xyz[3 * tri[3 * t] + 2]};
+        P3 b{xyz[3 * tri[3 * t + 1]], xyz[3 * tri[3 * t + 1] + 1], xyz[3 * tri[3 * t + 1] + 2]};
+        P3 c{xyz[3 * tri[3 * t + 2]], xyz[3 * tri[3 * t + 2] + 1], xyz[3 * tri[3 * t + 2] + 2]};
+        double area = 0.5 * norm(cross(sub(c, a), sub(b, a)));
+        for (int k = 0; k < 3; ++k) { sum[tri[3 * t + k]] += area; cnt[tri[3 * t + k]]++; }
+    }
+    for (int i = 0; i < nv; ++i) out[i] = sum[i] / cnt[i];
+}
+
+// resampler.cpp:72-140 without EXCL, single-thread order
+int adaptive_maps(int nv_in, const double* xyz_in, int nt_in, const int* tri_in,
+                  int nv_low, const double* xyz_low, int nt_low, const int* tri_low,
+                  std::vector<std::map<int, double>>& adapt) {
+    orc_octree* tin = build_tree(nv_in, xyz_in, nt_in, tri_in);
+    std::vector<std::map<int, double>> forward, reverse;
+    int e = bary_weight_maps(tin, nv_low, xyz_low, forward);
+    delete tin;
+    if (e) return e;
+    orc_octree* tlow = build_tree(nv_low, xyz_low, nt_low, tri_low);
+    e = bary_weight_maps(tlow, nv_in, xyz_in, reverse);
+    delete tlow;
+    if (e) return e;
+
+    std::vector<double> newA(nv_low), oldA(nv_in), correction(nv_in, 0.0);
+    vertex_areas(nv_low, xyz_low, nt_low, tri_low, newA.data());
+    vertex_areas(nv_in, xyz_in, nt_in, tri_in, oldA.data());
+    std::vector<std::map<int, double>> rr(nv_low);
+    adapt.assign(nv_low, {});
+    for (int o = 0; o < nv_in; ++o)
+        for (auto& it : reverse[o]) rr[it.first][o] = it.second;
+    for (int n = 0; n < nv_low; ++n) {
+        if (rr[n].size() <= forward[n].size()) adapt[n] = forward[n];
+        else adapt[n] = rr[n];
+        for (auto& it : adapt[n]) { it.second *= newA[n]; correction[it.first] += it.second; }
+    }
+    for (int n = 0; n < nv_low; ++n) {
+        double ws = 0.0;
+        for (auto& it : adapt[n]) { it.second *= oldA[it.first] / correction[it.first]; ws += it.second; }
+        if (ws != 0.0) for (auto& it : adapt[n]) it.second /= ws;
+    }
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+orc_octree* orc_octree_build(int nv, const double* xyz, int nt, const int* tri) { return build_tree(nv, xyz, nt, tri); }
+void orc_octree_free(orc_octree* t) { delete t; }
+
+int orc_octree_dump(const orc_octree* t, int* kinds, int* counts, int node_cap, int* tris, int tri_cap, int* n_tris) {
+    std::vector<int> k, c, tr;
+    dump(t->root, k, c, tr);
+    if ((int)k.size() <= node_cap) {
+        std::memcpy(kinds, k.data(), k.size() * sizeof(int));
+        std::memcpy(counts, c.data(), c.size() * sizeof(int));
+    }
+    if ((int)tr.size() <= tri_cap) std::memcpy(tris, tr.data(), tr.size() * sizeof(int));
+    *n_tris = (int)tr.size();
+    return (int)k.size();
+}
+
+void orc_octree_query(const orc_octree* t, int n, const double* pts, int* out_tri, int* out_vertex,
+                      int* status, int* path, int nthreads) {
+    #pragma omp parallel for num_threads(nthreads > 0 ? nthreads : 1)
+    for (int i = 0; i < n; ++i) {
+        P3 p{pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+        int st = 0, pa = 0;
+        int id = closest_triangle(t, p, &st, &pa);
+        out_tri[i] = id;
+        if (status) status[i] = st;
+        if (path) path[i] = pa;
+        if (out_vertex) out_vertex[i] = id >= 0 ? closest_vertex_of(t, p, id) : -1;
+    }
+}
+
+int orc_bary_weights(const orc_octree* t, int n, const double* pts, int* idx, double* w, int* n_entries, int nthreads) {
+    int err = 0;
+    #pragma omp parallel for num_threads(nthreads > 0 ? nthreads : 1)
+    for (int i = 0; i < n; ++i) {
+        P3 p{pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+        int st;
+        int id = closest_triangle(t, p, &st, nullptr);
+        if (id < 0) {
+            for (int j = 0; j < 3; ++j) { idx[3 * i + j] = -1; w[3 * i + j] = 0.0; }
+            if (n_entries) n_entries[i] = 0;
+            #pragma omp critical
+            { if (!err) err = st; }
+            continue;
+        }
+        int m = bary_weights_of(t, p, id, idx + 3 * i, w + 3 * i);
+        if (n_entries) n_entries[i] = m;
+    }
+    return err;
+}
+
+void orc_vertex_areas(int nv, const double* xyz, int nt, const int* tri, double* out) { vertex_areas(nv, xyz, nt, tri, out); }
+
+int orc_adaptive_weights(int nv_in, const double* xyz_in, int nt_in, const int* tri_in,
+                         int nv_low, const double* xyz_low, int nt_low, const int* tri_low,
+                         int* rowptr, int* col, double* val, int cap) {
+    std::vector<std::map<int, double>> adapt;
+    if (adaptive_maps(nv_in, xyz_in, nt_in, tri_in, nv_low, xyz_low, nt_low, tri_low, adapt)) return -1;
+    int pos = 0;
+    for (int r = 0; r < nv_low; ++r) {
+        rowptr[r] = pos;
+        for (auto& it : adapt[r]) { if (pos < cap) { col[pos] = it.first; val[pos] = it.second; } ++pos; }
+    }
+    rowptr[nv_low] = pos;
+    return pos;
+}
+
+int orc_metric_resample(int nv_in, const double* xyz_in, int nt_in, const int* tri_in,
+                        int nv_low, const double* xyz_low, int nt_low, const int* tri_low,
+                        int D, const double* feat_in, double* feat_out, int nthreads) {
+    std::vector<std::map<int, double>> adapt;
+    if (adaptive_maps(nv_in, xyz_in, nt_in, tri_in, nv_low, xyz_low, nt_low, tri_low, adapt)) return 1;
+    for (int d = 0; d < D; ++d) { // resampler.cpp:40-52
+        #pragma omp parallel for num_threads(nthreads > 0 ? nthreads : 1)
+        for (int k = 0; k < nv_low; ++k) {
+            double val = 0.0;
+            for (auto& it : adapt[k]) val += feat_in[(size_t)d * nv_in + it.first] * it.second;
+            feat_out[(size_t)d * nv_low + k] = val;
+        }
+    }
+    return 0;
+}
+
+int orc_bary_resample(int nv_in, const double* xyz_in, int nt_in, const int* tri_in,
+                      int n_low, const double* xyz_low, int D, const double* feat_in, double* feat_out, int nthreads) {
+    orc_octree* t = build_tree(nv_in, xyz_in, nt_in, tri_in);
+    std::vector<int> idx(3 * (size_t)n_low), ne(n_low);
+    std::vector<double> w(3 * (size_t)n_low);
+    int e = orc_bary_weights(t, n_low, xyz_low, idx.data(), w.data(), ne.data(), nthreads);
+    delete t;
+    if (e) return e;
+    for (int d = 0; d < D; ++d)
+        #pragma omp parallel for num_threads(nthreads > 0 ? nthreads : 1)
+        for (int k = 0; k < n_low; ++k) {
+            double val = 0.0;
+            for (int j = 0; j < ne[k]; ++j) val += feat_in[(size_t)d * nv_in + idx[3 * k + j]] * w[3 * k + j];
+            feat_out[(size_t)d * n_low + k] = val;
+        }
+    return 0;
+}
+
+static int blend_coords(int n, const double* q_xyz, int nv, const double* mesh_xyz, int nt, const int* tri,
+                        const double* payload_xyz, double* out_xyz, bool reproject, int nthreads) {
+    orc_octree* t = build_tree(nv, mesh_xyz, nt, tri);
+    std::vector<int> idx(3 * (size_t)n), ne(n);
+    std::vector<double> w(3 * (size_t)n);
+    int e = orc_bary_weights(t, n, q_xyz, idx.data(), w.data(), ne.data(), nthreads);
+    delete t;
+    if (e) return e;
+    for (int i = 0; i < n; ++i) {
+        P3 np{0, 0, 0};
+        for (int j = 0; j < ne[i]; ++j) { // Point*double then += (point.cpp:198,224)
+            const double* c = payload_xyz + 3 * (size_t)idx[3 * i + j];
+            P3 s = mul(P3{c[0], c[1], c[2]}, w[3 * i + j]);
+            np.X += s.X; np.Y += s.Y; np.Z += s.Z;
+        }
+        if (reproject) { normalize(np); np.X *= 100; np.Y *= 100; np.Z *= 100; } // resampler.cpp:324-325
+        out_xyz[3 * i] = np.X; out_xyz[3 * i + 1] = np.Y; out_xyz[3 * i + 2] = np.Z;
+    }
+    return 0;
+}
+
+int orc_sphere_project_warp(int n, const double* sphere_xyz, int nv, const double* from_xyz, int nt, const int* tri,
+                            const double* to_xyz, double* out_xyz, int nthreads) {
+    return blend_coords(n, sphere_xyz, nv, from_xyz, nt, tri, to_xyz, out_xyz, true, nthreads);
+}
+
+int orc_surface_resample(int n, const double* low_xyz, int nv, const double* sph_xyz, int nt, const int* tri,
+                         const double* anat_xyz, double* out_xyz, int nthreads) {
+    return blend_coords(n, low_xyz, nv, sph_xyz, nt, tri, anat_xyz, out_xyz, false, nthreads);
+}
+
+int orc_nn_resample(int n, const double* low_xyz, int nv, const double* xyz, int nt, const int* tri,
+                    int D, const double* feat_in, double* feat_out, int nthreads) {
+    orc_octree* t = build_tree(nv, xyz, nt, tri);
+    std::vector<int> tr(n), vx(n), st(n);
+    orc_octree_query(t, n, low_xyz, tr.data(), vx.data(), st.data(), nullptr, nthreads);
+    delete t;
+    for (int i = 0; i < n; ++i) if (st[i]) return st[i];
+    for (int d = 0; d < D; ++d)
+        for (int i = 0; i < n; ++i) feat_out[(size_t)d * n + i] = feat_in[(size_t)d * nv + vx[i]];
+    return 0;
+}
+
+// point.cpp:97-152, with the 3x3 algebra spelled out in the same evaluation order as
+// R = I + u*sin(theta) + (1-cos(theta))*(u*u) (left-to-right sums, s = 0 + a + b + c products).
+int orc_rotation_matrix(const double* ci_, const double* index_, double* R) {
+    P3 ci{ci_[0], ci_[1], ci_[2]}, index{index_[0], index_[1], index_[2]};
+    normalize(ci); normalize(index);
+    const double c = dot(ci, index);
+    const double theta = std::acos(c);
+    if (theta > M_PI) return 1;
+    const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    P3 cr = cross(ci, index);
+    normalize(cr);
+    if (std::fabs(1 - c) < EPS) { std::memcpy(R, I, sizeof(I)); return 0; }
+    if (norm(cr) < EPS) { for (int i = 0; i < 9; ++i) R[i] = -I[i]; return 0; }
+    const double u[9] = {0, -cr.Z, cr.Y, cr.Z, 0, -cr.X, -cr.Y, cr.X, 0};
+    if (std::fabs(-1 - c) < EPS) {
+        const double op[9] = {cr.X * cr.X, cr.X * cr.Y, cr.X * cr.Z, cr.Y * cr.X, cr.Y * cr.Y, cr.Y * cr.Z,
+                              cr.Z * cr.X, cr.Z * cr.Y, cr.Z * cr.Z};
+        for (int i = 0; i < 9; ++i) R[i] = 2 * op[i] - I[i];
+        return 0;
+    }
+    const double s = std::sin(theta), omc = 1 - std::cos(theta);
+    double uu[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double a = 0.0;
+            for (int k = 0; k < 3; ++k) a += u[3 * i + k] * u[3 * k + j];
+            uu[3 * i + j] = a;
+        }
+    for (int i = 0; i < 9; ++i) R[i] = (I[i] + u[i] * s) + omc * uu[i];
+    return 0;
+}
+
+// similarities.cpp:129-158
+double orc_corr(int n, const double* A, const double* B, const double* w) {
+    double prod = 0.0, varA = 0.0, varB = 0.0, meanA = 0.0, meanB = 0.0, sum = 0.0;
+    for (int i = 0; i < n; ++i) sum += w[i];
+    for (int i = 0; i < n; ++i) { meanA += w[i] * A[i]; meanB += w[i] * B[i]; }
+    if (sum > 0.0) { meanA /= sum; meanB /= sum; }
+    for (int s = 0; s < n; ++s) {
+        prod += w[s] * (A[s] - meanA) * (B[s] - meanB);
+        varA += w[s] * (A[s] - meanA) * (A[s] - meanA);
+        varB += w[s] * (B[s] - meanB) * (B[s] - meanB);
+    }
+    if (sum > 0.0) { prod /= sum; varA /= sum; varB /= sum; }
+    if (varA == 0.0 || varB == 0.0) return 0.0;
+    return prod / (std::sqrt(varA) * std::sqrt(varB));
+}
+
+// similarities.cpp:179-188
+double orc_ssd(int n, const double* A, const double* B, const double* w) {
+    double prod = 0.0;
+    for (int i = 0; i < n; ++i) prod += w[i] * (A[i] - B[i]) * (A[i] - B[i]);
+    return std::sqrt(prod) / n;
+}
+
+// similarities.h:48-58 (simmeasure 1 = SSD, 2 = correlation)
+double orc_sim_for_min(int simmeasure, int n, const double* A, const double* B, const double* w) {
+    if (simmeasure == 1) return orc_ssd(n, A, B, w);
+    if (simmeasure == 2) return 1 - (1 + orc_corr(n, A, B, w)) * 0.5;
+    return std::numeric_limits<double>::quiet_NaN();
+}
+
+int orc_patch_membership(int ncp, const double* cp, int nsrc, const double* src,
+                         const double* maxsep, double range, int* rowptr, int* members, int cap, int nthreads) {
+    std::vector<std::vector<int>> lists(ncp);
+    #pragma omp parallel for num_threads(nthreads > 0 ? nthreads : 1)
+    for (int k = 0; k < ncp; ++k) {
+        P3 c{cp[3 * k], cp[3 * k + 1], cp[3 * k + 2]};
+        for (int i = 0; i < nsrc; ++i) { // DiscreteCostFunction.cpp:102-107
+            P3 s{src[3 * i], src[3 * i + 1], src[3 * i + 2]};
+            if ((2 * RAD * std::asin(norm(sub(c, s)) / (2 * RAD))) < range * maxsep[k]) lists[k].push_back(i);
+        }
+    }
+    int pos = 0;
+    for (int k = 0; k < ncp; ++k) {
+        rowptr[k] = pos;
+        for (int i : lists[k]) { if (pos < cap) members[pos] = i; ++pos; }
+    }
+    rowptr[ncp] = pos;
+    return pos;
+}
+
+int orc_unary_costs(int kind, int simmeasure, const orc_octree* T,
+                    int ncp, const double* cp_xyz, const double* rot, int L, const double* labels,
+                    int nsrc, const double* src_xyz, const int* prow, const int* pmem,
+                    int D, const double* src_feat, const double* ref_feat,
+                    int cfw_rows, const double* cfw, const double* absw,
+                    double* out, int* tri_out, int nthreads) {
+    const int nvt = T->nv;
+    const int total = prow[ncp];
+    int err = 0;
+    for (int l = 0; l < L; ++l) { // DiscreteCostFunction.cpp:236-243
+        #pragma omp parallel for num_threads(nthreads > 0 ? nthreads : 1)
+        for (int k = 0; k < ncp; ++k) {
+            const P3 lab{labels[3 * l], labels[3 * l + 1], labels[3 * l + 2]};
+            const P3 dest = matvec(rot + 9 * (size_t)k, lab);
+            double R[9];
+            const double ci[3] = {cp_xyz[3 * k], cp_xyz[3 * k + 1], cp_xyz[3 * k + 2]};
+            const double de[3] = {dest.X, dest.Y, dest.Z};
+            orc_rotation_matrix(ci, de, R);
+            const int P = prow[k + 1] - prow[k];
+            std::vector<double> tgt((size_t)P * D), wts(3 * (size_t)P);
+            std::vector<int> ids(3 * (size_t)P);
+            bool bad = false;
+            for (int i = 0; i < P; ++i) { // get_target_data, cpp:353-376 / 410-442 / 652-678
+                const int sv = pmem[prow[k] + i];
+                const P3 tmp = matvec(R, P3{src_xyz[3 * sv], src_xyz[3 * sv + 1], src_xyz[3 * sv + 2]});
+                int st;
+                const int t = closest_triangle(T, tmp, &st, nullptr);
+                if (tri_out) tri_out[(size_t)l * total + prow[k] + i] = t;
+                if (t < 0) { bad = true; break; }
+                double w[3];
+                bary_interp_weights(T->tv(t, 0), T->tv(t, 1), T->tv(t, 2), tmp, w);
+                for (int d = 0; d < D; ++d) { // triangle.cpp:156: Aa*va1 + Ab*va2 + Ac*va3
+                    const double* rf = ref_feat + (size_t)d * nvt;
+                    tgt[(size_t)i * D + d] = w[0] * rf[T->tri[3 * t]] + w[1] * rf[T->tri[3 * t + 1]] + w[2] * rf[T->tri[3 * t + 2]];
+                }
+            }
+            if (bad) {
+                #pragma omp critical
+                err = 2;
+                out[(size_t)l * ncp + k] = std::numeric_limits<double>::quiet_NaN();
+                continue;
+            }
+            double cost = 0.0;
+            std::vector<double> a, b, w;
+            if (kind == 0) { // cpp:378-383
+                a.resize(P); b.resize(P); w.resize(P);
+                for (int i = 0; i < P; ++i) {
+                    const int sv = pmem[prow[k] + i];
+                    a[i] = src_feat[sv]; b[i] = tgt[(size_t)i * D];
+                    w[i] = cfw_rows >= 1 ? cfw[sv] : 1.0;
+                }
+                cost = orc_sim_for_min(simmeasure, P, a.data(), b.data(), w.data());
+            } else if (kind == 1) { // cpp:444-458
+                a.resize(D); b.resize(D); w.resize(D);
+                for (int i = 0; i < P; ++i) {
+                    const int sv = pmem[prow[k] + i];
+                    for (int d = 0; d < D; ++d) {
+                        a[d] = src_feat[(size_t)d * nsrc + sv]; b[d] = tgt[(size_t)i * D + d];
+                        w[d] = cfw_rows >= d + 1 ? cfw[(size_t)d * nsrc + sv] : 1.0;
+                    }
+                    cost += orc_sim_for_min(simmeasure, D, a.data(), b.data(), w.data());
+                }
+                if (P > 0) cost /= P;
+            } else { // cpp:681-692
+                a.resize(P); b.resize(P); w.resize(P);
+                for (int i = 0; i < P; ++i) w[i] = cfw_rows >= 1 ? cfw[pmem[prow[k] + i]] : 1.0;
+                for (int d = 0; d < D; ++d) {
+                    for (int i = 0; i < P; ++i) {
+                        a[i] = src_feat[(size_t)d * nsrc + pmem[prow[k] + i]];
+                        b[i] = tgt[(size_t)i * D + d];
+                    }
+                    cost += orc_sim_for_min(simmeasure, P, a.data(), b.data(), w.data());
+                }
+                cost /= D;
+            }
+            out[(size_t)l * ncp + k] = absw[k] * cost;
+        }
+    }
+    return err;
+}
+
+} // extern "C"

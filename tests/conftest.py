@@ -1,0 +1,26 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def oracle_built():
+    from oracle import bindings
+    bindings.build()
+    return bindings
+
+
+@pytest.fixture(scope="session")
+def ref_built(oracle_built):
+    if not oracle_built.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    return oracle_built

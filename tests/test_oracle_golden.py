@@ -1,0 +1,72 @@
+"""CPU oracle against the committed golden fixtures (outputs of the compiled reference,
+tests/golden/make_golden.py). Runs without /root/reference. Bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(G, name))
+
+
+def test_octree_golden(oracle_built):
+    g = load("octree_ico3.npz")
+    t = oracle_built.OracleOctree(g["xyz"], g["tri"])
+    kinds, counts, leaf_tris = t.dump()
+    assert np.array_equal(kinds, g["kinds"]) and np.array_equal(counts, g["counts"])
+    assert np.array_equal(leaf_tris, g["leaf_tris"])
+    tri, vtx, st, _ = t.query(g["q"])
+    assert np.array_equal(tri, g["tri_id"]) and np.array_equal(st, g["status"])
+    ok = st == 0
+    assert np.array_equal(vtx[ok], g["vertex_id"][ok])
+    idx, w, n, err = t.bary_weights(g["q"][ok])
+    assert err == 0
+    assert np.array_equal(idx, g["w_idx"]) and np.array_equal(w, g["w_val"]) and np.array_equal(n, g["w_n"])
+    assert np.array_equal(oracle_built.oracle_vertex_areas(g["xyz"], g["tri"]), g["vertex_area"])
+
+
+@pytest.mark.parametrize("name", ["down", "up"])
+def test_resample_golden(oracle_built, name):
+    g = load(f"resample_{name}.npz")
+    rowptr, col, val = oracle_built.oracle_adaptive_weights(g["xyz_in"], g["tri_in"], g["xyz_low"], g["tri_low"])
+    assert np.array_equal(rowptr, g["rowptr"]) and np.array_equal(col, g["col"]) and np.array_equal(val, g["val"])
+    out = oracle_built.oracle_metric_resample(g["xyz_in"], g["tri_in"], g["xyz_low"], g["tri_low"], g["feat"])
+    assert np.array_equal(out, g["metric_out"])
+    out = oracle_built.oracle_bary_resample(g["xyz_in"], g["tri_in"], g["xyz_low"], g["feat"])
+    assert np.array_equal(out, g["bary_out"])
+    # rows of the adaptive matrix are normalised (resampler.cpp:130-135)
+    sums = np.add.reduceat(val, rowptr[:-1])
+    assert np.allclose(sums, 1.0, atol=1e-12)
+
+
+def test_blend_golden(oracle_built):
+    g = load("blend.npz")
+    O = oracle_built
+    assert np.array_equal(O.oracle_sphere_project_warp(g["sph"], g["xf"], g["tf"], g["xto"]), g["warp"])
+    assert np.array_equal(O.oracle_surface_resample(g["sph"], g["xf"], g["tf"], g["anat"]), g["surf"])
+    assert np.array_equal(O.oracle_nn_resample(g["sph"], g["xf"], g["tf"], g["feat"]), g["nn"])
+
+
+def test_rotation_golden(oracle_built):
+    g = load("rotation.npz")
+    for ci, ix, R in zip(g["ci"], g["index"], g["R"]):
+        assert np.array_equal(oracle_built.oracle_rotation_matrix(ci, ix), R)
+    assert np.array_equal(g["R"][0], np.eye(3)) and np.array_equal(g["R"][2], np.eye(3))
+
+
+def test_similarity_kats(oracle_built):
+    # analytic known answers: corr(A,A)=1 -> cost 0; corr(A,-A)=-1 -> cost 1;
+    # zero variance -> r=0 -> cost 0.5 (similarities.cpp:157); SSD = sqrt(sum w d^2)/n (cpp:186)
+    rng = np.random.default_rng(0)
+    A = rng.normal(size=65); w = rng.uniform(0.5, 1.5, size=65)
+    assert abs(oracle_built.oracle_sim(2, A, A, w)) < 1e-15
+    assert abs(oracle_built.oracle_sim(2, A, -A, w) - 1.0) < 1e-15
+    assert oracle_built.oracle_sim(2, A, np.ones(65), w) == 0.5
+    B = rng.normal(size=65)
+    assert np.isclose(oracle_built.oracle_sim(1, A, B, w), np.sqrt((w * (A - B) ** 2).sum()) / 65, rtol=1e-14)
+    r = np.cov(A, B, aweights=w, bias=True)
+    r = r[0, 1] / np.sqrt(r[0, 0] * r[1, 1])
+    assert np.isclose(oracle_built.oracle_sim(2, A, B, w), 1 - (1 + r) / 2, rtol=1e-12)

@@ -1,0 +1,139 @@
+"""Pins the CPU oracle (oracle/msm_oracle.cpp, our restatement) against the UNMODIFIED
+reference compiled into oracle/_ref (the reference has no tests of its own).
+Everything here is bit-exact (np.array_equal) — oracle and reference run the same FP64
+operation order on the same host libm. Skipped when oracle/_ref is absent."""
+import numpy as np
+import pytest
+
+from newmsm_b200 import synth
+
+
+def _queries(level, seed=0, n_rand=5000):
+    xyz, tri = synth.icosphere(level)
+    hi = synth.rotate_sphere(synth.icosphere(min(level + 1, 6))[0])
+    rng = np.random.default_rng(seed)
+    r = rng.normal(size=(n_rand, 3))
+    r = r / np.linalg.norm(r, axis=1, keepdims=True) * 100
+    edge_mid = (xyz[tri[:, 0]] + xyz[tri[:, 1]]) / 2          # on an edge (below the sphere)
+    cent = (xyz[tri[:, 0]] + xyz[tri[:, 1]] + xyz[tri[:, 2]]) / 3
+    planes = r.copy(); planes[: n_rand // 3, 0] = 0.0          # exactly on octree mid-planes
+    planes[n_rand // 3: 2 * n_rand // 3, 1] = 50.5
+    return np.concatenate([hi, r, xyz, edge_mid, cent, planes, xyz * 1.005, xyz * 0.97])
+
+
+@pytest.mark.parametrize("level", [0, 1, 2, 3, 4, 5])
+def test_icosphere_generator_matches_reference(ref_built, level):
+    xyz, tri = synth.icosphere(level)
+    rx, rt = ref_built.RefMesh(icosa=level).export()
+    assert np.array_equal(xyz, rx) and np.array_equal(tri, rt)
+
+
+@pytest.mark.parametrize("level", [2, 3, 4, 5])
+def test_octree_topology(ref_built, level):
+    xyz, tri = synth.icosphere(level)
+    a = ref_built.RefOctree(ref_built.RefMesh(xyz, tri)).dump()
+    b = ref_built.OracleOctree(xyz, tri).dump()
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+def test_octree_topology_jittered(ref_built):
+    xyz, tri = synth.icosphere(5)
+    xyz = synth.jitter_sphere(xyz, tri, seed=3)
+    a = ref_built.RefOctree(ref_built.RefMesh(xyz, tri)).dump()
+    b = ref_built.OracleOctree(xyz, tri).dump()
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("level", [2, 3, 4, 5])
+def test_nearest_triangle_and_vertex(ref_built, level, capfd):
+    xyz, tri = synth.icosphere(level)
+    q = _queries(level)
+    rt, rv, rs = ref_built.RefOctree(ref_built.RefMesh(xyz, tri)).query(q)
+    ot, ov, os_, path = ref_built.OracleOctree(xyz, tri).query(q)
+    capfd.readouterr()  # MeshException::what() prints to stdout (meshException.cpp:26)
+    assert np.array_equal(rt, ot)
+    assert np.array_equal(rs, os_)
+    ok = rs == 0
+    assert np.array_equal(rv[ok], ov[ok])
+    assert ok.sum() > 0.8 * len(q)
+
+
+def test_out_of_box_status(ref_built, capfd):
+    xyz, tri = synth.icosphere(3)
+    q = np.array([[101.5, 0, 0], [0, -200, 0], [101.0, 101.0, 101.0], [100.0, 0, 0]])
+    rt, _, rs = ref_built.RefOctree(ref_built.RefMesh(xyz, tri)).query(q)
+    ot, _, os_, _ = ref_built.OracleOctree(xyz, tri).query(q)
+    capfd.readouterr()
+    assert list(rs[:2]) == [1, 1] and np.array_equal(rs, os_) and np.array_equal(rt, ot)
+
+
+@pytest.mark.parametrize("lv_mesh,lv_pts", [(4, 5), (5, 4), (3, 3)])
+def test_bary_weights(ref_built, lv_mesh, lv_pts):
+    xyz, tri = synth.icosphere(lv_mesh)
+    pts = synth.rotate_sphere(synth.icosphere(lv_pts)[0]) if lv_mesh != lv_pts else xyz
+    rm = ref_built.RefMesh(xyz, tri)
+    low = ref_built.RefMesh(pts, synth.icosphere(lv_pts)[1])
+    ri, rw, rn, e = ref_built.RefOctree(rm).bary_weights(low)
+    oi, ow, on, e2 = ref_built.OracleOctree(xyz, tri).bary_weights(pts)
+    assert e == 0 and e2 == 0
+    assert np.array_equal(ri, oi) and np.array_equal(rw, ow) and np.array_equal(rn, on)
+    if lv_mesh == lv_pts:  # identity resample KAT: one weight is 1, the others 0
+        assert np.allclose(np.sort(ow, axis=1), [[0, 0, 1]], atol=1e-12)
+
+
+def test_vertex_areas(ref_built):
+    xyz, tri = synth.icosphere(4)
+    xyz = synth.jitter_sphere(xyz, tri, seed=5)
+    assert np.array_equal(ref_built.RefMesh(xyz, tri).vertex_areas(), ref_built.oracle_vertex_areas(xyz, tri))
+
+
+@pytest.mark.parametrize("lv_in,lv_low", [(5, 4), (4, 5), (4, 4)])
+def test_adaptive_weights_and_metric_resample(ref_built, lv_in, lv_low):
+    xi, ti = synth.icosphere(lv_in)
+    xi = synth.jitter_sphere(xi, ti, seed=11)
+    xl, tl = synth.icosphere(lv_low)
+    xl = synth.rotate_sphere(xl)
+    feat = synth.smooth_fields(xi, 3)
+    mi, ml = ref_built.RefMesh(xi, ti, feat=feat), ref_built.RefMesh(xl, tl)
+    a = ref_built.ref_adaptive_weights(mi, ml, nthreads=1)
+    b = ref_built.oracle_adaptive_weights(xi, ti, xl, tl)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    out_ref, _ = ref_built.ref_metric_resample(mi, ml, nthreads=1)
+    out_orc = ref_built.oracle_metric_resample(xi, ti, xl, tl, feat)
+    assert np.array_equal(out_ref, out_orc)
+    bre, _ = ref_built.ref_bary_resample(mi, ml, nthreads=1)
+    assert np.array_equal(bre, ref_built.oracle_bary_resample(xi, ti, xl, feat))
+
+
+def test_warp_surface_nn(ref_built):
+    xf, tf = synth.icosphere(4)
+    xto = synth.smooth_warp(xf, max_disp=4.0, seed=9)
+    sph = synth.rotate_sphere(synth.icosphere(5)[0])
+    t5 = synth.icosphere(5)[1]
+    R = ref_built
+    got = R.oracle_sphere_project_warp(sph, xf, tf, xto)
+    want = R.ref_sphere_project_warp(R.RefMesh(sph, t5), R.RefMesh(xf, tf), R.RefMesh(xto, tf))
+    assert np.array_equal(got, want)
+    anat = xf * np.array([1.0, 0.8, 0.6])
+    got = R.oracle_surface_resample(sph, xf, tf, anat)
+    want = R.ref_surface_resample(R.RefMesh(anat, tf), R.RefMesh(xf, tf), R.RefMesh(sph, t5))
+    assert np.array_equal(got, want)
+    feat = synth.smooth_fields(xf, 2)
+    got = R.oracle_nn_resample(sph, xf, tf, feat)
+    want = R.ref_nn_resample(R.RefMesh(xf, tf, feat=feat), R.RefMesh(sph, t5))
+    assert np.array_equal(got, want)
+
+
+def test_rotation_matrix(ref_built):
+    rng = np.random.default_rng(1)
+    cases = [(rng.normal(size=3), rng.normal(size=3)) for _ in range(200)]
+    a = rng.normal(size=3)
+    cases += [(a, a), (a, -a), (a, a * 3.0), (np.array([1.0, 0, 0]), np.array([-1.0, 1e-9, 0]))]
+    for ci, ix in cases:
+        assert np.array_equal(ref_built.ref_rotation_matrix(ci, ix), ref_built.oracle_rotation_matrix(ci, ix))
+    R = ref_built.oracle_rotation_matrix(cases[0][0], cases[0][1])
+    u = cases[0][0] / np.linalg.norm(cases[0][0]); v = cases[0][1] / np.linalg.norm(cases[0][1])
+    assert np.allclose(R @ u, v, atol=1e-12)
