@@ -1,0 +1,159 @@
+/* msmgpu.h — C ABI of the B200 (sm_100a) implementation of newMSM's data-parallel hot path.
+ *
+ * The reference (rbesenczi/newMSM) has no FFI: its hot path is C++ classes called in-process.
+ * Each entry point below replaces one reference interface; the citation after "replaces:"
+ * is relative to /root/reference/libraries/. A reference-side adapter keeps
+ * the C++ signatures (newresampler::Octree / Resampler / free functions,
+ * newmeshreg::DiscreteCostFunction) and forwards to these calls.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; `_dev` suffix = pointers are DEVICE pointers and the call
+ *    is asynchronous on the context stream; otherwise pointers are HOST pointers and the call
+ *    copies in/out and synchronises before returning.
+ *  - coordinates: xyz = [n][3] double (AoS, the reference's Point), triangles = [nt][3] int32,
+ *    0-based vertex ids. Sphere radius 100 (point.h:32).
+ *  - features at the host boundary are CHANNEL-major [D][V] like Mesh::pvalues
+ *    (msm-newresampler/src/mesh.h:44); on the device they are VERTEX-major rows [V][D].
+ *  - every function returns msmgpu_status; msmgpu_last_error() gives the message
+ *    (the reference's MeshException texts where one exists). There is no CPU fallback:
+ *    without a CUDA device every compute entry point returns MSMGPU_ERR_CUDA.
+ */
+#ifndef MSMGPU_H
+#define MSMGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    MSMGPU_OK = 0,
+    MSMGPU_ERR_CUDA = 1,          /* CUDA runtime error / no device */
+    MSMGPU_ERR_INVALID = 2,       /* bad argument */
+    MSMGPU_ERR_OUT_OF_BOX = 3,    /* "Point is not in the bounding box of the mesh" (octree.cpp:158) */
+    MSMGPU_ERR_NO_TRIANGLE = 4,   /* "Error in octree. ..." (octree.cpp:211) */
+    MSMGPU_ERR_CAPACITY = 5       /* internal buffer bound exceeded */
+} msmgpu_status;
+
+typedef struct msmgpu_ctx msmgpu_ctx;         /* device + stream + scratch */
+typedef struct msmgpu_mesh msmgpu_mesh;       /* device-resident vertices/faces (+ per-face tables) */
+typedef struct msmgpu_octree msmgpu_octree;   /* flattened octree of one mesh */
+typedef struct msmgpu_weights msmgpu_weights; /* device CSR resampling matrix */
+typedef struct msmgpu_costfn msmgpu_costfn;   /* device state of one DiscreteCostFunction */
+
+const char* msmgpu_last_error(void);
+const char* msmgpu_version(void);
+int msmgpu_device_count(void);
+
+/* stream == NULL -> a private non-blocking stream; otherwise a cudaStream_t owned by the caller */
+msmgpu_status msmgpu_ctx_create(int device, void* stream, msmgpu_ctx** out);
+void msmgpu_ctx_destroy(msmgpu_ctx* ctx);
+msmgpu_status msmgpu_ctx_sync(msmgpu_ctx* ctx);
+void* msmgpu_ctx_stream(msmgpu_ctx* ctx);
+
+/* replaces: newresampler::Mesh as geometry carrier (msm-newresampler/src/mesh.h:37-58) */
+msmgpu_status msmgpu_mesh_create(msmgpu_ctx* ctx, int nv, const double* xyz, int nt, const int32_t* tri, msmgpu_mesh** out);
+msmgpu_status msmgpu_mesh_create_dev(msmgpu_ctx* ctx, int nv, const double* d_xyz, int nt, const int32_t* d_tri, msmgpu_mesh** out);
+msmgpu_status msmgpu_mesh_set_coords(msmgpu_mesh* m, const double* xyz);   /* Mesh::set_coord for all vertices */
+void msmgpu_mesh_destroy(msmgpu_mesh* m);
+/* replaces: compute_vertex_area (msm-newresampler/src/mesh.cpp:1275) for all vertices */
+msmgpu_status msmgpu_mesh_vertex_areas(msmgpu_mesh* m, double* out);
+
+/* replaces: Octree::Octree / initialize_tree / add_triangle (msm-newresampler/src/octree.cpp:31-141).
+ * Built on the device, level by level, with the same leaf sets and leaf order as sequential insertion. */
+msmgpu_status msmgpu_octree_build(msmgpu_mesh* m, msmgpu_octree** out);
+/* same for a batch of meshes in one pass (a forest: every kernel launch covers all meshes) */
+msmgpu_status msmgpu_octree_build_batch(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, msmgpu_octree** out);
+void msmgpu_octree_destroy(msmgpu_octree* t);
+/* sizes: n_nodes, n_leaf_refs (sum of leaf triangle counts), depth */
+msmgpu_status msmgpu_octree_stats(msmgpu_octree* t, int* n_nodes, int* n_leaf_refs, int* depth);
+/* pre-order dump (children in the reference's [i][j][k] order): kinds[n_nodes] (1 leaf / 0 internal),
+ * counts[n_nodes], tris[n_leaf_refs] — for parity tests of the topology */
+msmgpu_status msmgpu_octree_dump(msmgpu_octree* t, int32_t* kinds, int32_t* counts, int32_t* tris);
+
+/* replaces: Octree::get_closest_triangle (octree.cpp:156-214) and get_closest_vertex_ID (216-233) for n points.
+ * out_tri / out_vertex may be NULL. status[i]: 0 ok, MSMGPU_ERR_OUT_OF_BOX, MSMGPU_ERR_NO_TRIANGLE; status may be
+ * NULL, then the first failing point makes the call fail like the reference's throw. */
+msmgpu_status msmgpu_nearest_triangle(msmgpu_octree* t, int n, const double* pts, int32_t* out_tri, int32_t* out_vertex, int32_t* status);
+msmgpu_status msmgpu_nearest_triangle_dev(msmgpu_octree* t, int n, const double* d_pts, int32_t* d_tri, int32_t* d_vertex, int32_t* d_status);
+
+/* replaces: Resampler::get_barycentric_weights (msm-newresampler/src/resampler.cpp:142-167): idx/w are [n][3], entries in
+ * ascending vertex id (std::map order); n_entries[n] (<3 when ids repeat), may be NULL. */
+msmgpu_status msmgpu_bary_weights(msmgpu_octree* t, int n, const double* pts, int32_t* idx, double* w, int32_t* n_entries);
+msmgpu_status msmgpu_bary_weights_dev(msmgpu_octree* t, int n, const double* d_pts, int32_t* d_idx, double* d_w, int32_t* d_n_entries, int32_t* d_status);
+
+/* replaces: Resampler::get_adaptive_barycentric_weights (resampler.cpp:72-140, no exclusion mask).
+ * Result: CSR over target vertices, columns ascending. */
+msmgpu_status msmgpu_adaptive_weights(msmgpu_mesh* in_mesh, msmgpu_mesh* low_mesh, msmgpu_weights** out);
+/* optional pre-built trees (NULL = build): lets a batch share the target tree */
+msmgpu_status msmgpu_adaptive_weights_ex(msmgpu_mesh* in_mesh, msmgpu_octree* in_tree, msmgpu_mesh* low_mesh, msmgpu_octree* low_tree, msmgpu_weights** out);
+msmgpu_status msmgpu_weights_shape(msmgpu_weights* w, int* n_rows, int* n_cols, int64_t* nnz);
+msmgpu_status msmgpu_weights_export(msmgpu_weights* w, int32_t* rowptr, int32_t* col, double* val);
+void msmgpu_weights_destroy(msmgpu_weights* w);
+
+/* replaces: the interpolation loop of Resampler::barycentric_data_interpolation (resampler.cpp:40-52).
+ * d_in: [n_cols][D] float rows, d_out: [n_rows][D] float rows (vertex-major). */
+msmgpu_status msmgpu_weights_apply_f32_dev(msmgpu_weights* w, int D, const float* d_in, float* d_out);
+
+/* replaces: metric_resample(in, low) (resampler.cpp:304): adaptive-barycentric resampling of D channels.
+ * Host buffers, channel-major: feat_in [D][nv_in] double, feat_out [D][nv_low] double. */
+msmgpu_status msmgpu_metric_resample(msmgpu_mesh* in_mesh, msmgpu_mesh* low_mesh, int D, const double* feat_in, double* feat_out);
+/* f32 payload variant (what the reference reads from / writes to GIFTI, mesh.cpp:625): channel-major host floats */
+msmgpu_status msmgpu_metric_resample_f32(msmgpu_mesh* in_mesh, msmgpu_octree* in_tree, msmgpu_mesh* low_mesh, msmgpu_octree* low_tree,
+                                         int D, const float* feat_in, float* feat_out);
+
+/* Plain barycentric resample = Octree(in) + get_barycentric_weights + loop of resampler.cpp:40-52, fused in one
+ * kernel (query -> weights -> 3-row gather). Device rows: d_feat_in [nv_in][D] float, d_feat_out [n][D] float. */
+msmgpu_status msmgpu_bary_resample_f32_dev(msmgpu_octree* t, int n, const double* d_pts, int D, const float* d_feat_in, float* d_feat_out, int32_t* d_status);
+/* batched over subjects (one launch): trees[s], pts shared, d_feat_in[s], d_feat_out[s] */
+msmgpu_status msmgpu_bary_resample_batch_f32_dev(msmgpu_ctx* ctx, int n_subjects, msmgpu_octree* const* trees, int n, const double* d_pts,
+                                                 int D, const float* const* d_feat_in, float* const* d_feat_out, int32_t* d_status);
+/* host-buffer convenience (channel-major double in/out), used by the parity tests */
+msmgpu_status msmgpu_bary_resample(msmgpu_mesh* in_mesh, int n, const double* pts, int D, const double* feat_in, double* feat_out);
+
+/* replaces: sphere_project_warp (resampler.cpp:311-328): out = normalize(sum w*to[idx])*100 for n points located in `from` */
+msmgpu_status msmgpu_sphere_project_warp(msmgpu_mesh* from_mesh, const double* to_xyz, int n, const double* sphere_xyz, double* out_xyz);
+/* replaces: surface_resample (resampler.cpp:284-302) / project_anatomical_mesh (260-282): out = sum w*anat[idx] */
+msmgpu_status msmgpu_surface_resample(msmgpu_mesh* sph_mesh, const double* anat_xyz, int n, const double* low_xyz, double* out_xyz);
+/* replaces: nearest_neighbour_interpolation (resampler.cpp:232-258, no exclusion): channel-major host doubles */
+msmgpu_status msmgpu_nn_resample(msmgpu_mesh* in_mesh, int n, const double* low_xyz, int D, const double* feat_in, double* feat_out);
+
+/* replaces: estimate_rotation_matrix (msm-newresampler/src/point.cpp:97-152) for n (ci,index) pairs -> [n][9] row-major */
+msmgpu_status msmgpu_rotation_matrices(msmgpu_ctx* ctx, int n, const double* ci, const double* index, double* R);
+
+/* ---- discrete-optimisation cost evaluation (msm-newmeshreg/src/DiscreteCostFunction.{h,cpp}) ---- */
+typedef enum {
+    MSMGPU_COST_UNIVARIATE = 0,   /* UnivariateNonLinearSRegDiscreteCostFunction  (cpp:326-383) */
+    MSMGPU_COST_MULTIVARIATE = 1, /* MultivariateNonLinearSRegDiscreteCostFunction (cpp:385-458) */
+    MSMGPU_COST_PATCHWISE = 2     /* PatchwiseMultivariate...                      (cpp:620-692) */
+} msmgpu_cost_kind;
+
+/* replaces: set_meshes + set_featurespace + set_octrees (DiscreteCostFunction.h:173-189).
+ * target: TARGET mesh + its octree; source_xyz [nsrc][3]; features channel-major doubles:
+ * src_feat [D][nsrc] (FEAT input), ref_feat [D][nv_target] (FEAT reference). simmeasure 1 = SSD, 2 = correlation. */
+msmgpu_status msmgpu_costfn_create(msmgpu_octree* target_tree, msmgpu_cost_kind kind, int simmeasure,
+                                   int nsrc, const double* source_xyz, int D, const double* src_feat, const double* ref_feat,
+                                   msmgpu_costfn** out);
+void msmgpu_costfn_destroy(msmgpu_costfn* c);
+/* replaces: reset_source (DiscreteCostFunction.h:190) */
+msmgpu_status msmgpu_costfn_reset_source(msmgpu_costfn* c, const double* source_xyz);
+/* replaces: reset_CPgrid + set_spacings + set_dataaffintyweighting + get_source_data (cpp:334-351: patch membership by
+ * within_controlpt_range, cpp:102-107) + resample_weights (cpp:303-323) inputs.
+ * cp_xyz [ncp][3], maxsep [ncp], range = _controlptrange, cfw [cfw_rows][nsrc] or NULL (weights 1), absw [ncp] AbsoluteWeights. */
+msmgpu_status msmgpu_costfn_set_cpgrid(msmgpu_costfn* c, int ncp, const double* cp_xyz, const double* maxsep, double range,
+                                       int cfw_rows, const double* cfw, const double* absw);
+/* patch lists as computed on the device: rowptr[ncp+1], members[rowptr[ncp]] (ascending source id); members may be NULL */
+msmgpu_status msmgpu_costfn_patches(msmgpu_costfn* c, int32_t* rowptr, int32_t* members);
+/* replaces: set_labels (h:180) + computeUnaryCosts (cpp:236-243): labels [L][3], rotations [ncp][9] row-major.
+ * out [L][ncp] doubles (label-major like unarycosts[l*N+k]); tri_out (optional) [L][n_patch_entries] nearest-triangle ids. */
+msmgpu_status msmgpu_costfn_unary_table(msmgpu_costfn* c, int L, const double* labels, const double* rotations,
+                                        double* out, int32_t* tri_out);
+/* device-resident variant: d_out [L][ncp], asynchronous on the context stream */
+msmgpu_status msmgpu_costfn_unary_table_dev(msmgpu_costfn* c, int L, const double* d_labels, const double* d_rotations, double* d_out, int32_t* d_tri_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSMGPU_H */

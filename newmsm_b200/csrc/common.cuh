@@ -1,0 +1,135 @@
+// Internal declarations shared by the kernels and the C-ABI layer (include/msmgpu.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/msmgpu.h"
+#include "geom.cuh"
+
+namespace msm {
+
+void set_error(const std::string& msg);
+msmgpu_status fail(msmgpu_status st, const std::string& msg);
+
+#define MSM_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return ::msm::fail(MSMGPU_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+#define MSM_TRY(expr)                          \
+    do {                                       \
+        msmgpu_status _s = (expr);             \
+        if (_s != MSMGPU_OK) return _s;        \
+    } while (0)
+
+// Stream-ordered scratch allocation (cudaMallocAsync pool, kept warm by a high release threshold).
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaStream_t s = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { release(); p = o.p; n = o.n; s = o.s; o.p = nullptr; o.n = 0; return *this; }
+    ~DevBuf() { release(); }
+    cudaError_t alloc(size_t count, cudaStream_t stream) {
+        release();
+        s = stream; n = count;
+        if (count == 0) { p = nullptr; return cudaSuccess; }
+        return cudaMallocAsync((void**)&p, count * sizeof(T), stream);
+    }
+    void release() {
+        if (p) cudaFreeAsync(p, s);
+        p = nullptr; n = 0;
+    }
+};
+
+// One int4 per octree node: x = first child (-1 for a leaf; the 8 children are contiguous in the
+// reference's [i][j][k] order), y = start of the triangle list in `pairs`, z = number of triangles
+// (0 for internal nodes, like Node::triangles_size() after clear_triangles(), octree.cpp:129),
+// w = parent (-1 for a root).
+struct Forest {
+    msmgpu_ctx* ctx = nullptr;
+    int n_nodes = 0;
+    int n_pairs = 0;   // used length of `pairs` (all levels)
+    int depth = 0;
+    DevBuf<int4> nodes;
+    DevBuf<int> pairs;
+    DevBuf<unsigned char> node_depth;
+};
+
+struct TreeView {
+    const int4* nodes;
+    const int* pairs;
+    const double* tv;   // [nt][9] triangle corner coordinates
+    const int* tri;     // [nt][3]
+    int root;
+};
+
+} // namespace msm
+
+struct msmgpu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+};
+
+struct msmgpu_mesh {
+    msmgpu_ctx* ctx = nullptr;
+    int nv = 0, nt = 0;
+    msm::DevBuf<double> xyz;   // [nv][3]
+    msm::DevBuf<int> tri;      // [nt][3]
+    msm::DevBuf<double> tv;    // [nt][9] corner coordinates per triangle (gather-free leaf scans)
+    msm::DevBuf<double> aabb;  // [nt][6] lo xyz, hi xyz (octree.cpp:46-59)
+};
+
+struct msmgpu_octree {
+    std::shared_ptr<msm::Forest> forest;
+    int root = 0;
+    msmgpu_mesh* mesh = nullptr;
+    msm::TreeView view() const {
+        return msm::TreeView{forest->nodes.p, forest->pairs.p, mesh->tv.p, mesh->tri.p, root};
+    }
+};
+
+struct msmgpu_weights {
+    msmgpu_ctx* ctx = nullptr;
+    int n_rows = 0, n_cols = 0;
+    int64_t nnz = 0;
+    msm::DevBuf<int> rowptr;
+    msm::DevBuf<int> col;
+    msm::DevBuf<double> val;
+};
+
+namespace msm {
+
+// ---- launchers implemented in the .cu files -------------------------------------------------
+msmgpu_status mesh_refresh_tables(msmgpu_mesh* m);
+msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, std::shared_ptr<Forest>& out, std::vector<int>& roots);
+
+msmgpu_status launch_nearest(const TreeView& t, int n, const double* d_pts, int* d_tri, int* d_vertex, int* d_status, cudaStream_t s);
+msmgpu_status launch_bary_weights(const TreeView& t, int n, const double* d_pts, int* d_idx, double* d_w, int* d_ne, int* d_status, cudaStream_t s);
+msmgpu_status launch_blend_coords(const TreeView& t, int n, const double* d_pts, const double* d_payload_xyz, double* d_out, int reproject, int* d_status, cudaStream_t s);
+
+struct ResampleJob {      // one subject of a batched fused resample
+    TreeView tree;
+    const float* feat_in;   // [nv][D]
+    float* feat_out;        // [n][D]
+};
+msmgpu_status launch_bary_resample_f32(const ResampleJob* d_jobs, int n_jobs, int n, const double* d_pts, int D, int* d_status, cudaStream_t s);
+
+msmgpu_status exclusive_scan_i32(const int* d_in, int* d_out, int n, int* d_total, cudaStream_t s);
+
+// first non-zero entry of d_status[n] -> host (0 if none)
+msmgpu_status first_error(const int* d_status, int n, cudaStream_t s, int* host_code);
+msmgpu_status status_to_error(int code);
+
+} // namespace msm

@@ -1,0 +1,121 @@
+// FP64 geometric primitives for the sm_100a kernels.
+//
+// Every decision the reference makes on the nearest-triangle path is an IEEE-754 double
+// comparison of values built from + - * / sqrt in a fixed order (point.cpp:26-75,
+// triangle.cpp:85-157). These device functions evaluate the same expressions in the same
+// association order; the translation unit is compiled with --fmad=false so nvcc never
+// contracts a*b+c, and CUDA's double / and sqrt are correctly rounded, hence triangle ids
+// and barycentric weights reproduce the CPU path bit for bit.
+#pragma once
+#include <cuda_runtime.h>
+#include <cfloat>
+
+namespace msm {
+
+constexpr double kEps = 1e-8;          // point.h:31 EPSILON
+constexpr double kRad = 100.0;         // point.h:32 RAD
+constexpr double kBounds = 101.0;      // octree.h:37 MESH_BOUNDS
+constexpr int kMaxTriangles = 50;      // node.h:33 MAX_TRIANGLES
+constexpr double kNotInTriangle = -1.0; // octree.h:35
+
+struct V3 { double x, y, z; };
+
+__host__ __device__ __forceinline__ V3 vsub(const V3& a, const V3& b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__host__ __device__ __forceinline__ V3 vscale(const V3& a, double s) { return {a.x * s, a.y * s, a.z * s}; }
+__host__ __device__ __forceinline__ double vdot(const V3& a, const V3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+// point.cpp:177-182 (note the operand order of the middle component)
+__host__ __device__ __forceinline__ V3 vcross(const V3& a, const V3& b) {
+    return {a.y * b.z - a.z * b.y, b.x * a.z - b.z * a.x, a.x * b.y - b.x * a.y};
+}
+__host__ __device__ __forceinline__ double vnorm(const V3& a) { return sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
+// point.cpp:26-34: no-op for |a| <= 1e-8
+__host__ __device__ __forceinline__ V3 vnormalized(V3 a) {
+    const double n = vnorm(a);
+    if (n > kEps) { a.x /= n; a.y /= n; a.z /= n; }
+    return a;
+}
+// 3x3 row-major matrix times point, point.cpp:202-208
+__host__ __device__ __forceinline__ V3 mat_apply(const double* M, const V3& v) {
+    return {M[0] * v.x + M[1] * v.y + M[2] * v.z,
+            M[3] * v.x + M[4] * v.y + M[5] * v.z,
+            M[6] * v.x + M[7] * v.y + M[8] * v.z};
+}
+
+// point.cpp:46-61 — ray origin->vb intersected with the plane of (v1,v2,v3)
+__host__ __device__ __forceinline__ V3 project_to_plane(const V3& vb, const V3& v1, const V3& v2, const V3& v3) {
+    const V3 s1 = vnormalized(vsub(v3, v1));
+    const V3 s2 = vnormalized(vsub(v2, v1));
+    const V3 s3 = vnormalized(vcross(s1, s2));
+    const double si = vdot(s3, v1) / vdot(s3, vb);
+    return vscale(vb, si);
+}
+
+// point.cpp:36-39
+__host__ __device__ __forceinline__ bool same_side(const V3& p1, const V3& p2, const V3& a, const V3& b) {
+    const V3 ba = vsub(b, a);
+    return vdot(vcross(ba, vsub(p1, a)), vcross(ba, vsub(p2, a))) > -kEps;
+}
+// point.cpp:41-44
+__host__ __device__ __forceinline__ bool in_triangle(const V3& p, const V3& a, const V3& b, const V3& c) {
+    return same_side(p, a, b, c) && same_side(p, b, c, a) && same_side(p, c, a, b);
+}
+// point.cpp:68-75
+__host__ __device__ __forceinline__ double tri_area(const V3& v0, const V3& v1, const V3& v2) {
+    return 0.5 * vnorm(vcross(vsub(v1, v0), vsub(v2, v0)));
+}
+// triangle.cpp:47-50 (cached Triangle::area — operands the other way round)
+__host__ __device__ __forceinline__ double tri_area_cached(const V3& v0, const V3& v1, const V3& v2) {
+    return 0.5 * vnorm(vcross(vsub(v2, v0), vsub(v1, v0)));
+}
+
+// triangle.cpp:85-122 — distance from x0 (already in the plane) to the triangle boundary
+__host__ __device__ __forceinline__ double boundary_distance(const V3& x0, const V3& x1, const V3& x2, const V3& x3) {
+    double d, dmin = DBL_MAX;
+    const V3 a1 = vsub(x0, x1), a2 = vsub(x0, x2), a3 = vsub(x0, x3);
+    V3 u = vsub(x2, x1);
+    if (vdot(a1, u) > 0 && vdot(a2, u) < 0) {
+        d = vnorm(vcross(a1, a2)) / vnorm(u);
+        if (d < dmin) dmin = d;
+    }
+    u = vsub(x3, x1);
+    if (vdot(a1, u) > 0 && vdot(a3, u) < 0) {
+        d = vnorm(vcross(a1, a3)) / vnorm(u);
+        if (d < dmin) dmin = d;
+    }
+    u = vsub(x3, x2);
+    if (vdot(a2, u) > 0 && vdot(a3, u) < 0) {
+        d = vnorm(vcross(a2, a3)) / vnorm(u);
+        if (d < dmin) dmin = d;
+    }
+    d = vnorm(a1); if (d < dmin) dmin = d;
+    d = vnorm(a2); if (d < dmin) dmin = d;
+    d = vnorm(a3); if (d < dmin) dmin = d;
+    return dmin;
+}
+
+// octree.cpp:143-154
+__host__ __device__ __forceinline__ double distance_to_triangle(const V3& pt, const V3& v0, const V3& v1, const V3& v2) {
+    const V3 mP = project_to_plane(pt, v0, v1, v2);
+    if (in_triangle(mP, v0, v1, v2)) return boundary_distance(mP, v0, v1, v2);
+    return kNotInTriangle;
+}
+
+// triangle.cpp:124-143: weights for (v1,v2,v3) with the query projected into the plane first
+__host__ __device__ __forceinline__ void bary_weights_projected(const V3& p, const V3& v1, const V3& v2, const V3& v3, double* w) {
+    const V3 PP = project_to_plane(p, v1, v2, v3);
+    const double Aa = tri_area(PP, v2, v3);
+    const double Ab = tri_area(PP, v1, v3);
+    const double Ac = tri_area(PP, v1, v2);
+    const double A = Aa + Ab + Ac;
+    w[0] = Aa / A; w[1] = Ab / A; w[2] = Ac / A;
+}
+// triangle.cpp:145-157: same without the projection (used by the cost functions)
+__host__ __device__ __forceinline__ void bary_weights_raw(const V3& p, const V3& v1, const V3& v2, const V3& v3, double* w) {
+    const double Aa = tri_area(p, v2, v3);
+    const double Ab = tri_area(p, v1, v3);
+    const double Ac = tri_area(p, v1, v2);
+    const double A = Aa + Ab + Ac;
+    w[0] = Aa / A; w[1] = Ab / A; w[2] = Ac / A;
+}
+
+} // namespace msm
