@@ -46,6 +46,13 @@ typedef struct msmgpu_costfn msmgpu_costfn;   /* device state of one DiscreteCos
 const char* msmgpu_last_error(void);
 const char* msmgpu_version(void);
 int msmgpu_device_count(void);
+/* debugging aid: text of a pending CUDA runtime error left by an unchecked call (clears it); "" if none */
+const char* msmgpu_debug_take_cuda_error(void);
+
+/* Tuning knob with no effect on results: how many lanes cooperate on one nearest-triangle query
+ * (1, 2, 4, 8, 16 or 32; default 8 or $MSMGPU_QUERY_GROUP). */
+msmgpu_status msmgpu_set_query_group(int lanes);
+int msmgpu_get_query_group(void);
 
 /* stream == NULL -> a private non-blocking stream; otherwise a cudaStream_t owned by the caller */
 msmgpu_status msmgpu_ctx_create(int device, void* stream, msmgpu_ctx** out);
@@ -58,6 +65,7 @@ msmgpu_status msmgpu_mesh_create(msmgpu_ctx* ctx, int nv, const double* xyz, int
 msmgpu_status msmgpu_mesh_create_dev(msmgpu_ctx* ctx, int nv, const double* d_xyz, int nt, const int32_t* d_tri, msmgpu_mesh** out);
 msmgpu_status msmgpu_mesh_set_coords(msmgpu_mesh* m, const double* xyz);   /* Mesh::set_coord for all vertices */
 void msmgpu_mesh_destroy(msmgpu_mesh* m);
+msmgpu_status msmgpu_mesh_shape(msmgpu_mesh* m, int* nv, int* nt);
 /* replaces: compute_vertex_area (msm-newresampler/src/mesh.cpp:1275) for all vertices */
 msmgpu_status msmgpu_mesh_vertex_areas(msmgpu_mesh* m, double* out);
 
@@ -146,12 +154,14 @@ msmgpu_status msmgpu_costfn_set_cpgrid(msmgpu_costfn* c, int ncp, const double* 
                                        int cfw_rows, const double* cfw, const double* absw);
 /* patch lists as computed on the device: rowptr[ncp+1], members[rowptr[ncp]] (ascending source id); members may be NULL */
 msmgpu_status msmgpu_costfn_patches(msmgpu_costfn* c, int32_t* rowptr, int32_t* members);
-/* replaces: set_labels (h:180) + computeUnaryCosts (cpp:236-243): labels [L][3], rotations [ncp][9] row-major.
- * out [L][ncp] doubles (label-major like unarycosts[l*N+k]); tri_out (optional) [L][n_patch_entries] nearest-triangle ids. */
+/* replaces: set_labels (h:180) + computeUnaryCosts (cpp:236-243): labels [L][3], rotations [ncp][9] row-major (HOST arrays:
+ * the per-(cp,label) matrices estimate_rotation_matrix(CP_k, ROT_k*label_l) are built with the host libm).
+ * out [L][ncp] doubles (label-major like unarycosts[l*N+k]); tri_out (optional) [L][n_patch_entries] nearest-triangle ids.
+ * A failed query makes that entry NaN and the call return MSMGPU_ERR_NO_TRIANGLE (the reference throws, octree.cpp:211). */
 msmgpu_status msmgpu_costfn_unary_table(msmgpu_costfn* c, int L, const double* labels, const double* rotations,
                                         double* out, int32_t* tri_out);
-/* device-resident variant: d_out [L][ncp], asynchronous on the context stream */
-msmgpu_status msmgpu_costfn_unary_table_dev(msmgpu_costfn* c, int L, const double* d_labels, const double* d_rotations, double* d_out, int32_t* d_tri_out);
+/* device-resident result: d_out [L][ncp] (and d_tri_out) stay on the device for a device-side consumer; labels / rotations are host arrays */
+msmgpu_status msmgpu_costfn_unary_table_dev(msmgpu_costfn* c, int L, const double* labels, const double* rotations, double* d_out, int32_t* d_tri_out);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,474 @@
+// C ABI (include/msmgpu.h), part 1: context, meshes, octrees, queries, barycentric resampling,
+// coordinate blends. Host-pointer entry points stage through stream-ordered device buffers and
+// synchronise; `_dev` entry points only enqueue work on the context stream.
+#include "common.cuh"
+
+#include <climits>
+#include <cmath>
+#include <cstring>
+#include <functional>
+
+namespace msm {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+msmgpu_status fail(msmgpu_status st, const std::string& msg) {
+    g_last_error = msg;
+    return st;
+}
+
+msmgpu_status status_to_error(int code) {
+    switch (code) {
+        case MSMGPU_OK: return MSMGPU_OK;
+        case MSMGPU_ERR_OUT_OF_BOX: return fail(MSMGPU_ERR_OUT_OF_BOX, "Point is not in the bounding box of the mesh");   // octree.cpp:158
+        case MSMGPU_ERR_NO_TRIANGLE: return fail(MSMGPU_ERR_NO_TRIANGLE, "Error in octree. No closest triangle found for the point.");   // octree.cpp:211
+        default: return fail((msmgpu_status)code, "query failed");
+    }
+}
+
+__global__ void k_first_error(const int* __restrict__ st, size_t n, unsigned long long* __restrict__ first) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n && st[i] != 0) atomicMin(first, (unsigned long long)i);
+}
+
+msmgpu_status first_error(const int* d_status, size_t n, cudaStream_t s, int* host_code) {
+    *host_code = 0;
+    if (n == 0) { MSM_CUDA(cudaStreamSynchronize(s)); return MSMGPU_OK; }
+    DevBuf<unsigned long long> first;
+    MSM_CUDA(first.alloc(1, s));
+    MSM_CUDA(cudaMemsetAsync(first.p, 0xff, sizeof(unsigned long long), s));
+    k_first_error<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_status, n, first.p);
+    MSM_CUDA(cudaGetLastError());
+    unsigned long long h = 0;
+    MSM_CUDA(cudaMemcpyAsync(&h, first.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    MSM_CUDA(cudaStreamSynchronize(s));
+    if (h != ~0ull) {
+        MSM_CUDA(cudaMemcpyAsync(host_code, d_status + h, sizeof(int), cudaMemcpyDeviceToHost, s));
+        MSM_CUDA(cudaStreamSynchronize(s));
+    }
+    return MSMGPU_OK;
+}
+
+// ---- layout kernels (32x32 shared-memory tiles, coalesced on both sides) ----------------------
+template <typename TI, typename TO>
+__global__ void k_transpose(int rows, int cols, const TI* __restrict__ in, TO* __restrict__ out) {
+    __shared__ TO tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int r = r0 + j, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) tile[j][threadIdx.x] = (TO)in[(size_t)r * cols + c];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int c = c0 + j, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) out[(size_t)c * rows + r] = tile[threadIdx.x][j];
+    }
+}
+
+template <typename TI, typename TO>
+static msmgpu_status transpose(int rows, int cols, const TI* in, TO* out, cudaStream_t s) {
+    if (rows <= 0 || cols <= 0) return MSMGPU_OK;
+    const dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+    k_transpose<TI, TO><<<grid, block, 0, s>>>(rows, cols, in, out);
+    MSM_CUDA(cudaGetLastError());
+    return MSMGPU_OK;
+}
+
+msmgpu_status launch_chmajor_f64_to_rows_f32(int D, int nv, const double* d_in, float* d_out, cudaStream_t s) { return transpose<double, float>(D, nv, d_in, d_out, s); }
+msmgpu_status launch_rows_f32_to_chmajor_f64(int D, int nv, const float* d_in, double* d_out, cudaStream_t s) { return transpose<float, double>(nv, D, d_in, d_out, s); }
+msmgpu_status launch_chmajor_f32_to_rows_f32(int D, int nv, const float* d_in, float* d_out, cudaStream_t s) { return transpose<float, float>(D, nv, d_in, d_out, s); }
+msmgpu_status launch_rows_f32_to_chmajor_f32(int D, int nv, const float* d_in, float* d_out, cudaStream_t s) { return transpose<float, float>(nv, D, d_in, d_out, s); }
+msmgpu_status launch_transpose_f64(int rows, int cols, const double* d_in, double* d_out, cudaStream_t s) { return transpose<double, double>(rows, cols, d_in, d_out, s); }
+
+// estimate_rotation_matrix (point.cpp:97-152). Evaluated on the HOST: its acos/sin/cos are the
+// only operations on the path whose CUDA implementation is not bit-identical to glibc's, the
+// matrices decide nearest-triangle ids downstream, and there are only O(N_cp * L) of them.
+bool host_rotation_matrix(const double* ci_, const double* index_, double* R) {
+    V3 ci{ci_[0], ci_[1], ci_[2]}, index{index_[0], index_[1], index_[2]};
+    ci = vnormalized(ci);
+    index = vnormalized(index);
+    const double c = vdot(ci, index);
+    const double theta = std::acos(c);
+    if (theta > M_PI) return false;
+    const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    const V3 cr = vnormalized(vcross(ci, index));
+    if (std::fabs(1 - c) < kEps) { std::memcpy(R, I, sizeof(I)); return true; }
+    if (vnorm(cr) < kEps) { for (int i = 0; i < 9; ++i) R[i] = -I[i]; return true; }
+    const double u[9] = {0, -cr.z, cr.y, cr.z, 0, -cr.x, -cr.y, cr.x, 0};
+    if (std::fabs(-1 - c) < kEps) {
+        const double o[3] = {cr.x, cr.y, cr.z};
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) R[3 * i + j] = 2 * (o[i] * o[j]) - I[3 * i + j];
+        return true;
+    }
+    const double sn = std::sin(theta), omc = 1 - std::cos(theta);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double a = 0.0;
+            for (int k = 0; k < 3; ++k) a += u[3 * i + k] * u[3 * k + j];
+            R[3 * i + j] = (I[3 * i + j] + u[3 * i + j] * sn) + omc * a;
+        }
+    return true;
+}
+
+static msmgpu_status check_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(MSMGPU_ERR_CUDA, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    }
+    return MSMGPU_OK;
+}
+
+template <typename T>
+static msmgpu_status upload(DevBuf<T>& b, const T* host, size_t n, cudaStream_t s) {
+    MSM_CUDA(b.alloc(n, s));
+    if (n) MSM_CUDA(cudaMemcpyAsync(b.p, host, n * sizeof(T), cudaMemcpyHostToDevice, s));
+    return MSMGPU_OK;
+}
+
+static msmgpu_status finish_queries(const int* d_status, size_t n, int* host_status, cudaStream_t s) {
+    if (host_status) {
+        MSM_CUDA(cudaMemcpyAsync(host_status, d_status, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+        MSM_CUDA(cudaStreamSynchronize(s));
+        return MSMGPU_OK;
+    }
+    int code = 0;
+    MSM_TRY(first_error(d_status, n, s, &code));
+    return status_to_error(code);
+}
+
+} // namespace msm
+
+using namespace msm;
+
+extern "C" {
+
+const char* msmgpu_last_error(void) { return g_last_error.c_str(); }
+const char* msmgpu_version(void) { return "newmsm_b200 0.1 (sm_100a)"; }
+
+/* debugging aid: the CUDA runtime's pending (non-sticky) error, cleared by the call; "" if none */
+const char* msmgpu_debug_take_cuda_error(void) {
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? "" : cudaGetErrorString(e);
+}
+
+int msmgpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+msmgpu_status msmgpu_ctx_create(int device, void* stream, msmgpu_ctx** out) {
+    if (!out) return fail(MSMGPU_ERR_INVALID, "ctx_create: out is NULL");
+    *out = nullptr;
+    MSM_TRY(check_device());
+    MSM_CUDA(cudaSetDevice(device));
+    auto* c = new msmgpu_ctx();
+    c->device = device;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete c; return fail(MSMGPU_ERR_CUDA, cudaGetErrorString(e)); }
+        c->own_stream = true;
+    }
+    // keep freed scratch in the pool: repeated calls (one per registration iteration) reuse it
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    *out = c;
+    return MSMGPU_OK;
+}
+
+void msmgpu_ctx_destroy(msmgpu_ctx* c) {
+    if (!c) return;
+    cudaStreamSynchronize(c->stream);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+msmgpu_status msmgpu_ctx_sync(msmgpu_ctx* c) {
+    if (!c) return fail(MSMGPU_ERR_INVALID, "ctx is NULL");
+    MSM_CUDA(cudaStreamSynchronize(c->stream));
+    return MSMGPU_OK;
+}
+void* msmgpu_ctx_stream(msmgpu_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+static msmgpu_status mesh_create_impl(msmgpu_ctx* ctx, int nv, const double* xyz, int nt, const int32_t* tri, bool dev, msmgpu_mesh** out) {
+    if (!ctx || !out || nv <= 0 || nt < 0 || !xyz || (nt > 0 && !tri)) return fail(MSMGPU_ERR_INVALID, "mesh_create: bad arguments");
+    *out = nullptr;
+    MSM_CUDA(cudaSetDevice(ctx->device));
+    auto m = std::unique_ptr<msmgpu_mesh>(new msmgpu_mesh());
+    m->ctx = ctx; m->nv = nv; m->nt = nt;
+    cudaStream_t s = ctx->stream;
+    const cudaMemcpyKind kind = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    MSM_CUDA(m->xyz.alloc(3 * (size_t)nv, s));
+    MSM_CUDA(m->tri.alloc(3 * (size_t)nt, s));
+    MSM_CUDA(m->rec.alloc((size_t)nt, s));
+    MSM_CUDA(m->aabb.alloc(6 * (size_t)nt, s));
+    MSM_CUDA(cudaMemcpyAsync(m->xyz.p, xyz, 3 * (size_t)nv * sizeof(double), kind, s));
+    if (nt) MSM_CUDA(cudaMemcpyAsync(m->tri.p, tri, 3 * (size_t)nt * sizeof(int), kind, s));
+    MSM_TRY(mesh_refresh_tables(m.get()));
+    if (!dev) MSM_CUDA(cudaStreamSynchronize(s));   // the host buffers may be released by the caller
+    *out = m.release();
+    return MSMGPU_OK;
+}
+
+msmgpu_status msmgpu_mesh_create(msmgpu_ctx* ctx, int nv, const double* xyz, int nt, const int32_t* tri, msmgpu_mesh** out) {
+    return mesh_create_impl(ctx, nv, xyz, nt, tri, false, out);
+}
+msmgpu_status msmgpu_mesh_create_dev(msmgpu_ctx* ctx, int nv, const double* d_xyz, int nt, const int32_t* d_tri, msmgpu_mesh** out) {
+    return mesh_create_impl(ctx, nv, d_xyz, nt, d_tri, true, out);
+}
+
+msmgpu_status msmgpu_mesh_set_coords(msmgpu_mesh* m, const double* xyz) {
+    if (!m || !xyz) return fail(MSMGPU_ERR_INVALID, "mesh_set_coords: bad arguments");
+    MSM_CUDA(cudaSetDevice(m->ctx->device));
+    MSM_CUDA(cudaMemcpyAsync(m->xyz.p, xyz, 3 * (size_t)m->nv * sizeof(double), cudaMemcpyHostToDevice, m->ctx->stream));
+    MSM_TRY(mesh_refresh_tables(m));
+    MSM_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    return MSMGPU_OK;
+}
+
+void msmgpu_mesh_destroy(msmgpu_mesh* m) {
+    if (!m) return;
+    cudaSetDevice(m->ctx->device);
+    delete m;
+}
+
+msmgpu_status msmgpu_mesh_shape(msmgpu_mesh* m, int* nv, int* nt) {
+    if (!m) return fail(MSMGPU_ERR_INVALID, "mesh is NULL");
+    if (nv) *nv = m->nv;
+    if (nt) *nt = m->nt;
+    return MSMGPU_OK;
+}
+
+msmgpu_status msmgpu_octree_build_batch(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, msmgpu_octree** out) {
+    if (!ctx || n <= 0 || !meshes || !out) return fail(MSMGPU_ERR_INVALID, "octree_build_batch: bad arguments");
+    MSM_CUDA(cudaSetDevice(ctx->device));
+    std::shared_ptr<Forest> F;
+    std::vector<int> roots;
+    MSM_TRY(forest_build(ctx, n, meshes, F, roots));
+    for (int i = 0; i < n; ++i) {
+        auto* t = new msmgpu_octree();
+        t->ctx = ctx;
+        t->forest = F;
+        t->root = roots[i];
+        t->mesh = meshes[i];
+        out[i] = t;
+    }
+    return MSMGPU_OK;
+}
+
+msmgpu_status msmgpu_octree_build(msmgpu_mesh* m, msmgpu_octree** out) {
+    if (!m || !out) return fail(MSMGPU_ERR_INVALID, "octree_build: bad arguments");
+    *out = nullptr;
+    return msmgpu_octree_build_batch(m->ctx, 1, &m, out);
+}
+
+void msmgpu_octree_destroy(msmgpu_octree* t) {
+    if (!t) return;
+    cudaSetDevice(t->ctx->device);
+    delete t;
+}
+
+// pre-order walk of one tree of the forest on host copies of the node / pair arrays
+static msmgpu_status tree_walk(msmgpu_octree* t, const std::function<void(const int4&, int depth, const int* pairs)>& visit) {
+    Forest& F = *t->forest;
+    cudaStream_t s = F.ctx->stream;
+    std::vector<int4> nodes(F.n_nodes);
+    std::vector<int> pairs(F.n_pairs);
+    MSM_CUDA(cudaMemcpyAsync(nodes.data(), F.nodes.p, nodes.size() * sizeof(int4), cudaMemcpyDeviceToHost, s));
+    MSM_CUDA(cudaMemcpyAsync(pairs.data(), F.pairs.p, pairs.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
+    MSM_CUDA(cudaStreamSynchronize(s));
+    std::vector<std::pair<int, int>> stack{{t->root, 0}};
+    while (!stack.empty()) {
+        const auto [g, depth] = stack.back();
+        stack.pop_back();
+        const int4& nd = nodes[g];
+        visit(nd, depth, pairs.data());
+        if (nd.x >= 0)
+            for (int c = 7; c >= 0; --c) stack.push_back({nd.x + c, depth + 1});
+    }
+    return MSMGPU_OK;
+}
+
+msmgpu_status msmgpu_octree_stats(msmgpu_octree* t, int* n_nodes, int* n_leaf_refs, int* depth) {
+    if (!t) return fail(MSMGPU_ERR_INVALID, "octree is NULL");
+    int nn = 0, nr = 0, dp = 0;
+    MSM_TRY(tree_walk(t, [&](const int4& nd, int d, const int*) { ++nn; nr += nd.z; dp = d > dp ? d : dp; }));
+    if (n_nodes) *n_nodes = nn;
+    if (n_leaf_refs) *n_leaf_refs = nr;
+    if (depth) *depth = dp;
+    return MSMGPU_OK;
+}
+
+msmgpu_status msmgpu_octree_dump(msmgpu_octree* t, int32_t* kinds, int32_t* counts, int32_t* tris) {
+    if (!t || !kinds || !counts || !tris) return fail(MSMGPU_ERR_INVALID, "octree_dump: bad arguments");
+    int i = 0, j = 0;
+    return tree_walk(t, [&](const int4& nd, int, const int* pairs) {
+        kinds[i] = nd.x < 0 ? 1 : 0;
+        counts[i] = nd.z;
+        ++i;
+        for (int k = 0; k < nd.z; ++k) tris[j++] = pairs[nd.y + k];
+    });
+}
+
+msmgpu_status msmgpu_nearest_triangle_dev(msmgpu_octree* t, int n, const double* d_pts, int32_t* d_tri, int32_t* d_vertex, int32_t* d_status) {
+    if (!t || n < 0 || (n > 0 && !d_pts)) return fail(MSMGPU_ERR_INVALID, "nearest_triangle_dev: bad arguments");
+    MSM_CUDA(cudaSetDevice(t->mesh->ctx->device));
+    return launch_nearest(t->view(), n, d_pts, d_tri, d_vertex, d_status, t->mesh->ctx->stream);
+}
+
+msmgpu_status msmgpu_nearest_triangle(msmgpu_octree* t, int n, const double* pts, int32_t* out_tri, int32_t* out_vertex, int32_t* status) {
+    if (!t || n < 0 || (n > 0 && !pts)) return fail(MSMGPU_ERR_INVALID, "nearest_triangle: bad arguments");
+    if (n == 0) return MSMGPU_OK;
+    MSM_CUDA(cudaSetDevice(t->mesh->ctx->device));
+    cudaStream_t s = t->mesh->ctx->stream;
+    DevBuf<double> d_pts;
+    DevBuf<int> d_tri, d_vtx, d_st;
+    MSM_TRY(upload(d_pts, pts, 3 * (size_t)n, s));
+    MSM_CUDA(d_tri.alloc(n, s));
+    MSM_CUDA(d_vtx.alloc(n, s));
+    MSM_CUDA(d_st.alloc(n, s));
+    MSM_TRY(launch_nearest(t->view(), n, d_pts.p, d_tri.p, d_vtx.p, d_st.p, s));
+    if (out_tri) MSM_CUDA(cudaMemcpyAsync(out_tri, d_tri.p, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (out_vertex) MSM_CUDA(cudaMemcpyAsync(out_vertex, d_vtx.p, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    return finish_queries(d_st.p, n, status, s);
+}
+
+msmgpu_status msmgpu_bary_weights_dev(msmgpu_octree* t, int n, const double* d_pts, int32_t* d_idx, double* d_w, int32_t* d_n_entries, int32_t* d_status) {
+    if (!t || n < 0 || (n > 0 && (!d_pts || !d_idx || !d_w))) return fail(MSMGPU_ERR_INVALID, "bary_weights_dev: bad arguments");
+    MSM_CUDA(cudaSetDevice(t->mesh->ctx->device));
+    return launch_bary_weights(t->view(), n, d_pts, d_idx, d_w, d_n_entries, d_status, t->mesh->ctx->stream);
+}
+
+msmgpu_status msmgpu_bary_weights(msmgpu_octree* t, int n, const double* pts, int32_t* idx, double* w, int32_t* n_entries) {
+    if (!t || n < 0 || (n > 0 && (!pts || !idx || !w))) return fail(MSMGPU_ERR_INVALID, "bary_weights: bad arguments");
+    if (n == 0) return MSMGPU_OK;
+    MSM_CUDA(cudaSetDevice(t->mesh->ctx->device));
+    cudaStream_t s = t->mesh->ctx->stream;
+    DevBuf<double> d_pts, d_w;
+    DevBuf<int> d_idx, d_ne, d_st;
+    MSM_TRY(upload(d_pts, pts, 3 * (size_t)n, s));
+    MSM_CUDA(d_idx.alloc(3 * (size_t)n, s));
+    MSM_CUDA(d_w.alloc(3 * (size_t)n, s));
+    MSM_CUDA(d_ne.alloc(n, s));
+    MSM_CUDA(d_st.alloc(n, s));
+    MSM_TRY(launch_bary_weights(t->view(), n, d_pts.p, d_idx.p, d_w.p, d_ne.p, d_st.p, s));
+    MSM_CUDA(cudaMemcpyAsync(idx, d_idx.p, 3 * (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    MSM_CUDA(cudaMemcpyAsync(w, d_w.p, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (n_entries) MSM_CUDA(cudaMemcpyAsync(n_entries, d_ne.p, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    return finish_queries(d_st.p, n, nullptr, s);
+}
+
+msmgpu_status msmgpu_bary_resample_batch_f32_dev(msmgpu_ctx* ctx, int n_subjects, msmgpu_octree* const* trees, int n, const double* d_pts,
+                                                 int D, const float* const* d_feat_in, float* const* d_feat_out, int32_t* d_status) {
+    if (!ctx || n_subjects <= 0 || !trees || n < 0 || D <= 0 || !d_feat_in || !d_feat_out || (n > 0 && !d_pts))
+        return fail(MSMGPU_ERR_INVALID, "bary_resample_batch: bad arguments");
+    MSM_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    std::vector<ResampleJob> jobs(n_subjects);
+    for (int i = 0; i < n_subjects; ++i) {
+        if (!trees[i] || trees[i]->mesh->ctx != ctx) return fail(MSMGPU_ERR_INVALID, "bary_resample_batch: tree from another context");
+        jobs[i] = ResampleJob{trees[i]->view(), d_feat_in[i], d_feat_out[i]};
+    }
+    DevBuf<ResampleJob> d_jobs;
+    MSM_CUDA(d_jobs.alloc(n_subjects, s));
+    // pageable source: the runtime stages it before returning, so `jobs` may go out of scope
+    MSM_CUDA(cudaMemcpyAsync(d_jobs.p, jobs.data(), jobs.size() * sizeof(ResampleJob), cudaMemcpyHostToDevice, s));
+    return launch_bary_resample_f32(d_jobs.p, n_subjects, n, d_pts, D, d_status, s);
+}
+
+msmgpu_status msmgpu_bary_resample_f32_dev(msmgpu_octree* t, int n, const double* d_pts, int D, const float* d_feat_in, float* d_feat_out, int32_t* d_status) {
+    if (!t) return fail(MSMGPU_ERR_INVALID, "bary_resample_f32_dev: tree is NULL");
+    return msmgpu_bary_resample_batch_f32_dev(t->mesh->ctx, 1, &t, n, d_pts, D, &d_feat_in, &d_feat_out, d_status);
+}
+
+msmgpu_status msmgpu_bary_resample(msmgpu_mesh* in_mesh, int n, const double* pts, int D, const double* feat_in, double* feat_out) {
+    if (!in_mesh || n <= 0 || D <= 0 || !pts || !feat_in || !feat_out) return fail(MSMGPU_ERR_INVALID, "bary_resample: bad arguments");
+    msmgpu_ctx* ctx = in_mesh->ctx;
+    MSM_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    msmgpu_octree* t = nullptr;
+    MSM_TRY(msmgpu_octree_build(in_mesh, &t));
+    std::unique_ptr<msmgpu_octree> guard(t);
+    const int nv = in_mesh->nv;
+    DevBuf<double> d_pts, d_cm_in, d_cm_out;
+    DevBuf<float> d_rows_in, d_rows_out;
+    DevBuf<int> d_st;
+    MSM_TRY(upload(d_pts, pts, 3 * (size_t)n, s));
+    MSM_TRY(upload(d_cm_in, feat_in, (size_t)D * nv, s));
+    MSM_CUDA(d_rows_in.alloc((size_t)D * nv, s));
+    MSM_CUDA(d_rows_out.alloc((size_t)D * n, s));
+    MSM_CUDA(d_cm_out.alloc((size_t)D * n, s));
+    MSM_CUDA(d_st.alloc(n, s));
+    MSM_TRY(launch_chmajor_f64_to_rows_f32(D, nv, d_cm_in.p, d_rows_in.p, s));
+    MSM_TRY(msmgpu_bary_resample_f32_dev(t, n, d_pts.p, D, d_rows_in.p, d_rows_out.p, d_st.p));
+    MSM_TRY(launch_rows_f32_to_chmajor_f64(D, n, d_rows_out.p, d_cm_out.p, s));
+    MSM_CUDA(cudaMemcpyAsync(feat_out, d_cm_out.p, (size_t)D * n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    return finish_queries(d_st.p, n, nullptr, s);
+}
+
+static msmgpu_status blend_impl(msmgpu_mesh* mesh, const double* payload, int n, const double* q, double* out, int reproject) {
+    if (!mesh || !payload || n <= 0 || !q || !out) return fail(MSMGPU_ERR_INVALID, "blend: bad arguments");
+    msmgpu_ctx* ctx = mesh->ctx;
+    MSM_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    msmgpu_octree* t = nullptr;
+    MSM_TRY(msmgpu_octree_build(mesh, &t));
+    std::unique_ptr<msmgpu_octree> guard(t);
+    DevBuf<double> d_q, d_pay, d_out;
+    DevBuf<int> d_st;
+    MSM_TRY(upload(d_q, q, 3 * (size_t)n, s));
+    MSM_TRY(upload(d_pay, payload, 3 * (size_t)mesh->nv, s));
+    MSM_CUDA(d_out.alloc(3 * (size_t)n, s));
+    MSM_CUDA(d_st.alloc(n, s));
+    MSM_TRY(launch_blend_coords(t->view(), n, d_q.p, d_pay.p, d_out.p, reproject, d_st.p, s));
+    MSM_CUDA(cudaMemcpyAsync(out, d_out.p, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    return finish_queries(d_st.p, n, nullptr, s);
+}
+
+msmgpu_status msmgpu_sphere_project_warp(msmgpu_mesh* from_mesh, const double* to_xyz, int n, const double* sphere_xyz, double* out_xyz) {
+    return blend_impl(from_mesh, to_xyz, n, sphere_xyz, out_xyz, 1);
+}
+msmgpu_status msmgpu_surface_resample(msmgpu_mesh* sph_mesh, const double* anat_xyz, int n, const double* low_xyz, double* out_xyz) {
+    return blend_impl(sph_mesh, anat_xyz, n, low_xyz, out_xyz, 0);
+}
+
+msmgpu_status msmgpu_nn_resample(msmgpu_mesh* in_mesh, int n, const double* low_xyz, int D, const double* feat_in, double* feat_out) {
+    if (!in_mesh || n <= 0 || D <= 0 || !low_xyz || !feat_in || !feat_out) return fail(MSMGPU_ERR_INVALID, "nn_resample: bad arguments");
+    msmgpu_ctx* ctx = in_mesh->ctx;
+    MSM_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    msmgpu_octree* t = nullptr;
+    MSM_TRY(msmgpu_octree_build(in_mesh, &t));
+    std::unique_ptr<msmgpu_octree> guard(t);
+    DevBuf<double> d_q, d_in, d_out;
+    DevBuf<int> d_vtx, d_st;
+    MSM_TRY(upload(d_q, low_xyz, 3 * (size_t)n, s));
+    MSM_TRY(upload(d_in, feat_in, (size_t)D * in_mesh->nv, s));
+    MSM_CUDA(d_out.alloc((size_t)D * n, s));
+    MSM_CUDA(d_vtx.alloc(n, s));
+    MSM_CUDA(d_st.alloc(n, s));
+    MSM_TRY(launch_nearest(t->view(), n, d_q.p, nullptr, d_vtx.p, d_st.p, s));
+    MSM_TRY(launch_gather_channels_f64(n, in_mesh->nv, D, d_vtx.p, d_in.p, d_out.p, s));
+    MSM_CUDA(cudaMemcpyAsync(feat_out, d_out.p, (size_t)D * n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    return finish_queries(d_st.p, n, nullptr, s);
+}
+
+msmgpu_status msmgpu_rotation_matrices(msmgpu_ctx*, int n, const double* ci, const double* index, double* R) {
+    if (n < 0 || (n > 0 && (!ci || !index || !R))) return fail(MSMGPU_ERR_INVALID, "rotation_matrices: bad arguments");
+    bool ok = true;
+#pragma omp parallel for reduction(&& : ok)
+    for (int i = 0; i < n; ++i) ok = host_rotation_matrix(ci + 3 * (size_t)i, index + 3 * (size_t)i, R + 9 * (size_t)i) && ok;
+    if (!ok) return fail(MSMGPU_ERR_INVALID, "rotation angle is greater than 90 degrees");   // point.cpp:109-110
+    return MSMGPU_OK;
+}
+
+} // extern "C"

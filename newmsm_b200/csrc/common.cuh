@@ -69,7 +69,7 @@ struct Forest {
 struct TreeView {
     const int4* nodes;
     const int* pairs;
-    const double* tv;   // [nt][9] triangle corner coordinates
+    const TriRec* rec;  // [nt] per-triangle query records (geom.cuh)
     const int* tri;     // [nt][3]
     int root;
 };
@@ -87,16 +87,17 @@ struct msmgpu_mesh {
     int nv = 0, nt = 0;
     msm::DevBuf<double> xyz;   // [nv][3]
     msm::DevBuf<int> tri;      // [nt][3]
-    msm::DevBuf<double> tv;    // [nt][9] corner coordinates per triangle (gather-free leaf scans)
+    msm::DevBuf<msm::TriRec> rec; // [nt] one 128-byte query record per triangle (gather-free leaf scans)
     msm::DevBuf<double> aabb;  // [nt][6] lo xyz, hi xyz (octree.cpp:46-59)
 };
 
 struct msmgpu_octree {
+    msmgpu_ctx* ctx = nullptr;   // kept here so destroy never has to look through `mesh`
     std::shared_ptr<msm::Forest> forest;
     int root = 0;
     msmgpu_mesh* mesh = nullptr;
     msm::TreeView view() const {
-        return msm::TreeView{forest->nodes.p, forest->pairs.p, mesh->tv.p, mesh->tri.p, root};
+        return msm::TreeView{forest->nodes.p, forest->pairs.p, mesh->rec.p, mesh->tri.p, root};
     }
 };
 
@@ -115,9 +116,11 @@ namespace msm {
 msmgpu_status mesh_refresh_tables(msmgpu_mesh* m);
 msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, std::shared_ptr<Forest>& out, std::vector<int>& roots);
 
+int query_group_width();
 msmgpu_status launch_nearest(const TreeView& t, int n, const double* d_pts, int* d_tri, int* d_vertex, int* d_status, cudaStream_t s);
 msmgpu_status launch_bary_weights(const TreeView& t, int n, const double* d_pts, int* d_idx, double* d_w, int* d_ne, int* d_status, cudaStream_t s);
 msmgpu_status launch_blend_coords(const TreeView& t, int n, const double* d_pts, const double* d_payload_xyz, double* d_out, int reproject, int* d_status, cudaStream_t s);
+msmgpu_status launch_gather_channels_f64(int n, int nv, int D, const int* d_vtx, const double* d_in, double* d_out, cudaStream_t s);
 
 struct ResampleJob {      // one subject of a batched fused resample
     TreeView tree;
@@ -128,8 +131,15 @@ msmgpu_status launch_bary_resample_f32(const ResampleJob* d_jobs, int n_jobs, in
 
 msmgpu_status exclusive_scan_i32(const int* d_in, int* d_out, int n, int* d_total, cudaStream_t s);
 
-// first non-zero entry of d_status[n] -> host (0 if none)
-msmgpu_status first_error(const int* d_status, int n, cudaStream_t s, int* host_code);
+// layout changes between the host boundary (channel-major doubles) and device rows
+msmgpu_status launch_chmajor_f64_to_rows_f32(int D, int nv, const double* d_in, float* d_out, cudaStream_t s);
+msmgpu_status launch_rows_f32_to_chmajor_f64(int D, int nv, const float* d_in, double* d_out, cudaStream_t s);
+msmgpu_status launch_chmajor_f32_to_rows_f32(int D, int nv, const float* d_in, float* d_out, cudaStream_t s);
+msmgpu_status launch_rows_f32_to_chmajor_f32(int D, int nv, const float* d_in, float* d_out, cudaStream_t s);
+msmgpu_status launch_transpose_f64(int rows, int cols, const double* d_in, double* d_out, cudaStream_t s);   // [rows][cols] -> [cols][rows]
+
+// first non-zero entry of d_status[n] -> host code (0 if none); synchronises the stream
+msmgpu_status first_error(const int* d_status, size_t n, cudaStream_t s, int* host_code);
 msmgpu_status status_to_error(int code);
 
 } // namespace msm

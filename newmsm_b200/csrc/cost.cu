@@ -1,0 +1,474 @@
+// Discrete-optimisation cost evaluation: patch membership and unary cost tables for the three
+// non-HO cost classes of msm-newmeshreg/src/DiscreteCostFunction.cpp:
+//   Univariate   (cpp:326-383), Multivariate (385-458), PatchwiseMultivariate (620-692),
+// with the similarities of similarities.cpp:129-188 (weighted Pearson, weighted SSD) selected by
+// get_sim_for_min (similarities.h:48-58).
+//
+// Work decomposition: one CTA per (control point, label). Phase 1 — the lanes, in groups of G,
+// rotate the patch's source points by R(cp,label), find their nearest target triangle and the
+// UNPROJECTED barycentric weights (triangle.cpp:145-157) and park (ids, weights) in shared
+// memory. Phase 2 — the similarity. Every floating-point sum of the reference is a sequential
+// FP64 sum over the patch (P ~ 65) or over the channels (D ~ 40); a lane evaluates one such sum in
+// the reference's order, so costs are reproduced to the last bit and the label choices of the host
+// solver cannot flip. The sums are short and independent across the 48 678 (cp,label) CTAs, which
+// is where the parallelism comes from.
+#include "query.cuh"
+
+#include <cmath>
+#include <limits>
+
+namespace msm {
+
+bool host_rotation_matrix(const double* ci, const double* index, double* R);
+
+} // namespace msm
+
+struct msmgpu_costfn {
+    msmgpu_ctx* ctx = nullptr;
+    msmgpu_octree* tree = nullptr;
+    int kind = 0, simmeasure = 2;
+    int nsrc = 0, D = 0, nvt = 0;
+    msm::DevBuf<double> src_xyz;    // [nsrc][3]
+    msm::DevBuf<double> src_feat;   // [nsrc][D] rows
+    msm::DevBuf<double> ref_feat;   // [nvt][D] rows
+    int ncp = 0, cfw_rows = 0;
+    double range = 0;
+    std::vector<double> h_cp;       // host copy: the rotation matrices are built on the host (api.cu)
+    msm::DevBuf<double> cp_xyz, cfw /* [nsrc][cfw_rows] rows */, absw, chord_thr;
+    msm::DevBuf<int> prow, pmem;    // patches: CSR over control points, ascending source id
+    int n_patch = 0, max_patch = 0;
+};
+
+namespace msm {
+
+constexpr unsigned kFullMask = kFull;
+
+// ------------------------------------------------------------------------------------------
+// patch membership (DiscreteCostFunction.cpp:102-107, 334-351)
+//   member <=> 2 R asin(|cp - src| / 2R) < range * MAXSEP(cp)
+// The left side is a non-decreasing function of the chord |cp - src|, so per control point there
+// is one threshold chord x* with  member <=> chord < x*.  x* is found on the host by bisection
+// over the doubles with the host libm (patch_chord_threshold), which keeps asin -- whose CUDA
+// implementation is not bit-identical to glibc's -- out of the N_cp x N_src device loop while
+// reproducing the reference's decision for every representable chord.
+// ------------------------------------------------------------------------------------------
+static double geodesic_of_chord(double chord) { return 2 * kRad * std::asin(chord / (2 * kRad)); }
+
+double patch_chord_threshold(double limit) {
+    // smallest double x in [0, 2R] with geodesic(x) >= limit, or nextafter(2R) if there is none
+    const double hi0 = 2 * kRad;
+    if (!(geodesic_of_chord(0.0) < limit)) return 0.0;
+    if (geodesic_of_chord(hi0) < limit) return std::nextafter(hi0, std::numeric_limits<double>::infinity());
+    uint64_t lo, hi;   // invariant: g(lo) < limit, g(hi) >= limit (positive doubles order like their bit patterns)
+    double dlo = 0.0, dhi = hi0;
+    memcpy(&lo, &dlo, 8);
+    memcpy(&hi, &dhi, 8);
+    while (hi - lo > 1) {
+        const uint64_t mid = lo + (hi - lo) / 2;
+        double dm;
+        memcpy(&dm, &mid, 8);
+        if (geodesic_of_chord(dm) < limit) lo = mid; else hi = mid;
+    }
+    memcpy(&dhi, &hi, 8);
+    return dhi;
+}
+
+__device__ __forceinline__ bool in_patch(const V3& c, const double* __restrict__ src, int i, double thr) {
+    const V3 s{__ldg(src + 3 * (size_t)i), __ldg(src + 3 * (size_t)i + 1), __ldg(src + 3 * (size_t)i + 2)};
+    return vnorm(vsub(c, s)) < thr;
+}
+
+// one CTA per control point; pass 0 counts, pass 1 writes the members in ascending source id
+template <int PASS>
+__global__ void __launch_bounds__(256) k_patch_members(int nsrc, const double* __restrict__ cp, const double* __restrict__ src,
+                                                       const double* __restrict__ thr, int* __restrict__ count,
+                                                       const int* __restrict__ rowptr, int* __restrict__ members) {
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
+    const int k = blockIdx.x;
+    const V3 c{cp[3 * (size_t)k], cp[3 * (size_t)k + 1], cp[3 * (size_t)k + 2]};
+    const double t = thr[k];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_base = PASS ? rowptr[k] : 0;
+    __syncthreads();
+    for (int base = 0; base < nsrc; base += 256) {
+        const int i = base + threadIdx.x;
+        const bool m = i < nsrc && in_patch(c, src, i, t);
+        const unsigned bal = __ballot_sync(kFullMask, m);
+        if (lane == 0) s_warp[warp] = __popc(bal);
+        __syncthreads();
+        int off = s_base;
+        for (int w = 0; w < warp; ++w) off += s_warp[w];
+        if (PASS && m) members[off + __popc(bal & ((1u << lane) - 1u))] = i;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int w = 0; w < 8; ++w) tot += s_warp[w];
+            s_base += tot;
+        }
+        __syncthreads();
+    }
+    if (!PASS && threadIdx.x == 0) count[k] = s_base;
+}
+
+__global__ void k_max_i32(int n, const int* __restrict__ v, int* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicMax(out, v[i]);
+}
+
+// ------------------------------------------------------------------------------------------
+// similarities (sequential FP64, similarities.cpp:129-188), element access through functors
+// ------------------------------------------------------------------------------------------
+template <class FA, class FB, class FW>
+__device__ __forceinline__ double sim_corr(int n, FA A, FB B, FW W) {
+    double prod = 0.0, varA = 0.0, varB = 0.0, meanA = 0.0, meanB = 0.0, sum = 0.0;
+    for (int i = 0; i < n; ++i) sum += W(i);
+    for (int i = 0; i < n; ++i) {
+        const double w = W(i);
+        meanA += w * A(i);
+        meanB += w * B(i);
+    }
+    if (sum > 0.0) { meanA /= sum; meanB /= sum; }
+    for (int i = 0; i < n; ++i) {
+        const double w = W(i), a = A(i) - meanA, b = B(i) - meanB;
+        prod += w * a * b;
+        varA += w * a * a;
+        varB += w * b * b;
+    }
+    if (sum > 0.0) { prod /= sum; varA /= sum; varB /= sum; }
+    if (varA == 0.0 || varB == 0.0) return 0.0;
+    return prod / (sqrt(varA) * sqrt(varB));
+}
+template <class FA, class FB, class FW>
+__device__ __forceinline__ double sim_ssd(int n, FA A, FB B, FW W) {
+    double prod = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const double d = A(i) - B(i);
+        prod += W(i) * d * d;
+    }
+    return sqrt(prod) / n;
+}
+template <class FA, class FB, class FW>
+__device__ __forceinline__ double sim_for_min(int simmeasure, int n, FA A, FB B, FW W) {
+    if (simmeasure == 1) return sim_ssd(n, A, B, W);
+    if (simmeasure == 2) return 1 - (1 + sim_corr(n, A, B, W)) * 0.5;
+    return nan("");
+}
+
+// ------------------------------------------------------------------------------------------
+// unary cost table
+// ------------------------------------------------------------------------------------------
+struct UnaryArgs {
+    TreeView tree;
+    int kind, simmeasure, ncp, L, nsrc, D, nvt, cfw_rows, n_patch;
+    const double* R;          // [L][ncp][9]
+    const double* src_xyz;    // [nsrc][3]
+    const int* prow;          // [ncp+1]
+    const int* pmem;          // [n_patch]
+    const double* src_feat;   // [nsrc][D]
+    const double* ref_feat;   // [nvt][D]
+    const double* cfw;        // [nsrc][cfw_rows]
+    const double* absw;       // [ncp]
+    double* out;              // [L][ncp]
+    int* tri_out;             // [L][n_patch] or NULL
+    int* err;                 // set to 1 when a query finds no triangle
+};
+
+constexpr int kCostThreads = 64;
+
+template <int G>
+__global__ void __launch_bounds__(kCostThreads) k_unary_table(UnaryArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int k = blockIdx.x, l = blockIdx.y;
+    const int p0 = a.prow[k], P = a.prow[k + 1] - p0;
+    // shared: w[P][3] doubles | sims[max(P,D)] doubles | idx[P][3] ints | bad flag
+    double* s_w = reinterpret_cast<double*>(smem_raw);
+    const int n_sims = P > a.D ? P : a.D;
+    double* s_sim = s_w + 3 * (size_t)P;
+    int* s_idx = reinterpret_cast<int*>(s_sim + n_sims);
+    __shared__ int s_bad;
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
+
+    double R[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = __ldg(a.R + ((size_t)l * a.ncp + k) * 9 + i);
+
+    // phase 1 (get_target_data, cpp:353-376 / 410-442 / 652-678): rotate, locate, weights
+    const int gl = threadIdx.x % G;
+    const int rounds = (P + kCostThreads / G - 1) / (kCostThreads / G);
+    for (int r = 0; r < rounds; ++r) {
+        const int i = r * (kCostThreads / G) + threadIdx.x / G;
+        const bool active = i < P;
+        V3 tmp{0, 0, 0};
+        if (active) {
+            const int sv = __ldg(a.pmem + p0 + i);
+            tmp = mat_apply(R, V3{__ldg(a.src_xyz + 3 * (size_t)sv), __ldg(a.src_xyz + 3 * (size_t)sv + 1), __ldg(a.src_xyz + 3 * (size_t)sv + 2)});
+        }
+        int st;
+        const int t = nearest_triangle<G>(a.tree, tmp, active, gl, st);
+        if (active && gl == 0) {
+            if (a.tri_out) a.tri_out[(size_t)l * a.n_patch + p0 + i] = t;
+            if (t < 0) {
+                s_bad = 1;
+            } else {
+                const double* v = a.tree.rec[t].v;
+                double w[3];
+                bary_weights_raw(tmp, V3{v[0], v[1], v[2]}, V3{v[3], v[4], v[5]}, V3{v[6], v[7], v[8]}, w);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    s_w[3 * i + j] = w[j];
+                    s_idx[3 * i + j] = __ldg(a.tree.tri + 3 * (size_t)t + j);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (s_bad) {   // the reference throws here (octree.cpp:211); the table entry is NaN and the call reports the error
+        if (threadIdx.x == 0) { a.out[(size_t)l * a.ncp + k] = nan(""); *a.err = 1; }
+        return;
+    }
+
+    const int D = a.D;
+    const double* __restrict__ rf = a.ref_feat;
+    const double* __restrict__ sf = a.src_feat;
+    // target value of patch point i in channel d (triangle.cpp:156: Aa*va1 + Ab*va2 + Ac*va3)
+    auto tgt = [&](int i, int d) -> double {
+        return s_w[3 * i] * __ldg(rf + (size_t)s_idx[3 * i] * D + d) + s_w[3 * i + 1] * __ldg(rf + (size_t)s_idx[3 * i + 1] * D + d) +
+               s_w[3 * i + 2] * __ldg(rf + (size_t)s_idx[3 * i + 2] * D + d);
+    };
+    auto srcv = [&](int i) -> int { return __ldg(a.pmem + p0 + i); };
+    double cost = 0.0;
+    if (a.kind == MSMGPU_COST_UNIVARIATE) {   // cpp:378-383
+        for (int i = threadIdx.x; i < P; i += kCostThreads) s_sim[i] = tgt(i, 0);   // parallel gather, sequential sums below
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int cr = a.cfw_rows;
+            cost = sim_for_min(a.simmeasure, P,
+                               [&](int i) { return __ldg(sf + (size_t)srcv(i) * D); },
+                               [&](int i) { return s_sim[i]; },
+                               [&](int i) { return cr >= 1 ? __ldg(a.cfw + (size_t)srcv(i) * cr) : 1.0; });
+        }
+    } else if (a.kind == MSMGPU_COST_MULTIVARIATE) {   // cpp:444-458: per-vertex similarity across channels, mean over the patch
+        const int cr = a.cfw_rows;
+        for (int i = threadIdx.x; i < P; i += kCostThreads) {
+            const int sv = srcv(i);
+            s_sim[i] = sim_for_min(a.simmeasure, D,
+                                   [&](int d) { return __ldg(sf + (size_t)sv * D + d); },
+                                   [&](int d) { return tgt(i, d); },
+                                   [&](int d) { return cr >= d + 1 ? __ldg(a.cfw + (size_t)sv * cr + d) : 1.0; });
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < P; ++i) cost += s_sim[i];
+            if (P > 0) cost /= P;
+        }
+    } else {   // cpp:681-692: per-channel similarity across the patch, mean over channels
+        const int cr = a.cfw_rows;
+        for (int d = threadIdx.x; d < D; d += kCostThreads) {
+            s_sim[d] = sim_for_min(a.simmeasure, P,
+                                   [&](int i) { return __ldg(sf + (size_t)srcv(i) * D + d); },
+                                   [&](int i) { return tgt(i, d); },
+                                   [&](int i) { return cr >= 1 ? __ldg(a.cfw + (size_t)srcv(i) * cr) : 1.0; });
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int d = 0; d < D; ++d) cost += s_sim[d];
+            cost /= D;
+        }
+    }
+    if (threadIdx.x == 0) a.out[(size_t)l * a.ncp + k] = __ldg(a.absw + k) * cost;
+}
+
+static size_t unary_smem_bytes(int max_patch, int D) {
+    const size_t n_sims = (size_t)(max_patch > D ? max_patch : D);
+    return 3 * (size_t)max_patch * sizeof(double) + n_sims * sizeof(double) + 3 * (size_t)max_patch * sizeof(int) + 16;
+}
+
+template <int G>
+static msmgpu_status launch_unary_g(const UnaryArgs& a, size_t smem, cudaStream_t s) {
+    if (smem > 48 * 1024) MSM_CUDA(cudaFuncSetAttribute(k_unary_table<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_unary_table<G><<<dim3((unsigned)a.ncp, (unsigned)a.L), kCostThreads, smem, s>>>(a);
+    MSM_CUDA(cudaGetLastError());
+    return MSMGPU_OK;
+}
+
+static msmgpu_status launch_unary(const UnaryArgs& a, int max_patch, cudaStream_t s) {
+    const size_t smem = unary_smem_bytes(max_patch, a.D);
+    if (smem > 200 * 1024) return fail(MSMGPU_ERR_CAPACITY, "unary_table: patch too large for shared memory");
+    switch (query_group_width()) {
+        case 1: return launch_unary_g<1>(a, smem, s);
+        case 2: return launch_unary_g<2>(a, smem, s);
+        case 4: return launch_unary_g<4>(a, smem, s);
+        case 16: return launch_unary_g<16>(a, smem, s);
+        case 32: return launch_unary_g<32>(a, smem, s);
+        default: return launch_unary_g<8>(a, smem, s);
+    }
+}
+
+template <typename T>
+static msmgpu_status upload_vec(DevBuf<T>& b, const T* host, size_t n, cudaStream_t s) {
+    MSM_CUDA(b.alloc(n, s));
+    if (n) MSM_CUDA(cudaMemcpyAsync(b.p, host, n * sizeof(T), cudaMemcpyHostToDevice, s));
+    return MSMGPU_OK;
+}
+
+// host channel-major [D][n] doubles -> device rows [n][D]
+static msmgpu_status upload_rows(DevBuf<double>& rows, const double* host_cm, int D, int n, cudaStream_t s) {
+    DevBuf<double> cm;
+    MSM_TRY(upload_vec(cm, host_cm, (size_t)D * n, s));
+    MSM_CUDA(rows.alloc((size_t)D * n, s));
+    MSM_TRY(launch_transpose_f64(D, n, cm.p, rows.p, s));
+    MSM_CUDA(cudaStreamSynchronize(s));   // `cm` is released after the transpose has consumed it
+    return MSMGPU_OK;
+}
+
+} // namespace msm
+
+using namespace msm;
+
+extern "C" {
+
+msmgpu_status msmgpu_costfn_create(msmgpu_octree* target_tree, msmgpu_cost_kind kind, int simmeasure, int nsrc, const double* source_xyz,
+                                   int D, const double* src_feat, const double* ref_feat, msmgpu_costfn** out) {
+    if (!target_tree || !out || nsrc <= 0 || D <= 0 || !source_xyz || !src_feat || !ref_feat || kind < 0 || kind > 2)
+        return fail(MSMGPU_ERR_INVALID, "costfn_create: bad arguments");
+    if (simmeasure != 1 && simmeasure != 2) return fail(MSMGPU_ERR_INVALID, "costfn_create: simmeasure must be 1 (SSD) or 2 (correlation)");
+    *out = nullptr;
+    msmgpu_ctx* ctx = target_tree->mesh->ctx;
+    MSM_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    auto c = std::unique_ptr<msmgpu_costfn>(new msmgpu_costfn());
+    c->ctx = ctx; c->tree = target_tree; c->kind = kind; c->simmeasure = simmeasure;
+    c->nsrc = nsrc; c->D = D; c->nvt = target_tree->mesh->nv;
+    MSM_TRY(upload_vec(c->src_xyz, source_xyz, 3 * (size_t)nsrc, s));
+    MSM_TRY(upload_rows(c->src_feat, src_feat, D, nsrc, s));
+    MSM_TRY(upload_rows(c->ref_feat, ref_feat, D, c->nvt, s));
+    MSM_CUDA(cudaStreamSynchronize(s));
+    *out = c.release();
+    return MSMGPU_OK;
+}
+
+void msmgpu_costfn_destroy(msmgpu_costfn* c) {
+    if (!c) return;
+    cudaSetDevice(c->ctx->device);
+    delete c;
+}
+
+msmgpu_status msmgpu_costfn_reset_source(msmgpu_costfn* c, const double* source_xyz) {
+    if (!c || !source_xyz) return fail(MSMGPU_ERR_INVALID, "costfn_reset_source: bad arguments");
+    MSM_CUDA(cudaSetDevice(c->ctx->device));
+    MSM_CUDA(cudaMemcpyAsync(c->src_xyz.p, source_xyz, 3 * (size_t)c->nsrc * sizeof(double), cudaMemcpyHostToDevice, c->ctx->stream));
+    MSM_CUDA(cudaStreamSynchronize(c->ctx->stream));
+    return MSMGPU_OK;
+}
+
+msmgpu_status msmgpu_costfn_set_cpgrid(msmgpu_costfn* c, int ncp, const double* cp_xyz, const double* maxsep, double range,
+                                       int cfw_rows, const double* cfw, const double* absw) {
+    if (!c || ncp <= 0 || !cp_xyz || !maxsep || !absw || cfw_rows < 0 || (cfw_rows > 0 && !cfw))
+        return fail(MSMGPU_ERR_INVALID, "costfn_set_cpgrid: bad arguments");
+    MSM_CUDA(cudaSetDevice(c->ctx->device));
+    cudaStream_t s = c->ctx->stream;
+    c->ncp = ncp; c->range = range; c->cfw_rows = cfw_rows;
+    c->h_cp.assign(cp_xyz, cp_xyz + 3 * (size_t)ncp);
+    std::vector<double> thr(ncp);
+#pragma omp parallel for
+    for (int k = 0; k < ncp; ++k) thr[k] = patch_chord_threshold(range * maxsep[k]);   // cpp:104: < _controlptrange * MAXSEP(k+1)
+    MSM_TRY(upload_vec(c->cp_xyz, cp_xyz, 3 * (size_t)ncp, s));
+    MSM_TRY(upload_vec(c->absw, absw, (size_t)ncp, s));
+    MSM_TRY(upload_vec(c->chord_thr, thr.data(), (size_t)ncp, s));
+    if (cfw_rows > 0) MSM_TRY(upload_rows(c->cfw, cfw, cfw_rows, c->nsrc, s));
+    // patch lists
+    DevBuf<int> count, d_tot;
+    MSM_CUDA(count.alloc(ncp, s));
+    MSM_CUDA(d_tot.alloc(2, s));
+    MSM_CUDA(c->prow.alloc((size_t)ncp + 1, s));
+    k_patch_members<0><<<ncp, 256, 0, s>>>(c->nsrc, c->cp_xyz.p, c->src_xyz.p, c->chord_thr.p, count.p, nullptr, nullptr);
+    MSM_CUDA(cudaGetLastError());
+    MSM_TRY(exclusive_scan_i32(count.p, c->prow.p, ncp, d_tot.p, s));
+    MSM_CUDA(cudaMemcpyAsync(c->prow.p + ncp, d_tot.p, sizeof(int), cudaMemcpyDeviceToDevice, s));
+    MSM_CUDA(cudaMemsetAsync(d_tot.p + 1, 0, sizeof(int), s));
+    k_max_i32<<<(ncp + 255) / 256, 256, 0, s>>>(ncp, count.p, d_tot.p + 1);
+    MSM_CUDA(cudaGetLastError());
+    int h[2];
+    MSM_CUDA(cudaMemcpyAsync(h, d_tot.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    MSM_CUDA(cudaStreamSynchronize(s));
+    c->n_patch = h[0];
+    c->max_patch = h[1];
+    MSM_CUDA(c->pmem.alloc((size_t)c->n_patch, s));
+    if (c->n_patch > 0) {
+        k_patch_members<1><<<ncp, 256, 0, s>>>(c->nsrc, c->cp_xyz.p, c->src_xyz.p, c->chord_thr.p, nullptr, c->prow.p, c->pmem.p);
+        MSM_CUDA(cudaGetLastError());
+    }
+    MSM_CUDA(cudaStreamSynchronize(s));
+    return MSMGPU_OK;
+}
+
+msmgpu_status msmgpu_costfn_patches(msmgpu_costfn* c, int32_t* rowptr, int32_t* members) {
+    if (!c || !rowptr || c->ncp <= 0) return fail(MSMGPU_ERR_INVALID, "costfn_patches: set_cpgrid first");
+    MSM_CUDA(cudaSetDevice(c->ctx->device));
+    cudaStream_t s = c->ctx->stream;
+    MSM_CUDA(cudaMemcpyAsync(rowptr, c->prow.p, ((size_t)c->ncp + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (members && c->n_patch) MSM_CUDA(cudaMemcpyAsync(members, c->pmem.p, (size_t)c->n_patch * sizeof(int), cudaMemcpyDeviceToHost, s));
+    MSM_CUDA(cudaStreamSynchronize(s));
+    return MSMGPU_OK;
+}
+
+// d_out [L][ncp]; d_tri_out [L][n_patch] or NULL; labels / rotations are HOST arrays (see host_rotation_matrix)
+msmgpu_status msmgpu_costfn_unary_table_dev(msmgpu_costfn* c, int L, const double* labels, const double* rotations, double* d_out, int32_t* d_tri_out) {
+    if (!c || L <= 0 || !labels || !rotations || !d_out) return fail(MSMGPU_ERR_INVALID, "costfn_unary_table: bad arguments");
+    if (c->ncp <= 0) return fail(MSMGPU_ERR_INVALID, "costfn_unary_table: set_cpgrid first");
+    MSM_CUDA(cudaSetDevice(c->ctx->device));
+    cudaStream_t s = c->ctx->stream;
+    const int ncp = c->ncp;
+    // R(l,k) = estimate_rotation_matrix(CP_k, ROT_k * label_l)  (cpp:379-380, 445-446, 682-683)
+    std::vector<double> R((size_t)L * ncp * 9);
+    bool ok = true;
+#pragma omp parallel for collapse(2) reduction(&& : ok)
+    for (int l = 0; l < L; ++l)
+        for (int k = 0; k < ncp; ++k) {
+            const double* M = rotations + 9 * (size_t)k;
+            const double* lb = labels + 3 * (size_t)l;
+            const V3 dest = mat_apply(M, V3{lb[0], lb[1], lb[2]});
+            const double de[3] = {dest.x, dest.y, dest.z};
+            ok = host_rotation_matrix(c->h_cp.data() + 3 * (size_t)k, de, R.data() + ((size_t)l * ncp + k) * 9) && ok;
+        }
+    if (!ok) return fail(MSMGPU_ERR_INVALID, "rotation angle is greater than 90 degrees");
+    DevBuf<double> d_R;
+    MSM_TRY(upload_vec(d_R, R.data(), R.size(), s));
+    UnaryArgs a;
+    a.tree = c->tree->view();
+    a.kind = c->kind; a.simmeasure = c->simmeasure; a.ncp = ncp; a.L = L; a.nsrc = c->nsrc; a.D = c->D; a.nvt = c->nvt;
+    a.cfw_rows = c->cfw_rows; a.n_patch = c->n_patch;
+    a.R = d_R.p; a.src_xyz = c->src_xyz.p; a.prow = c->prow.p; a.pmem = c->pmem.p;
+    a.src_feat = c->src_feat.p; a.ref_feat = c->ref_feat.p; a.cfw = c->cfw.p; a.absw = c->absw.p;
+    a.out = d_out; a.tri_out = d_tri_out;
+    DevBuf<int> d_err;
+    MSM_CUDA(d_err.alloc(1, s));
+    MSM_CUDA(cudaMemsetAsync(d_err.p, 0, sizeof(int), s));
+    a.err = d_err.p;
+    MSM_TRY(launch_unary(a, c->max_patch, s));
+    int h_err = 0;
+    MSM_CUDA(cudaMemcpyAsync(&h_err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MSM_CUDA(cudaStreamSynchronize(s));   // R (pageable host vector) and d_R are released on return
+    if (h_err) return status_to_error(MSMGPU_ERR_NO_TRIANGLE);   // the reference throws (octree.cpp:211); failed entries are NaN
+    return MSMGPU_OK;
+}
+
+msmgpu_status msmgpu_costfn_unary_table(msmgpu_costfn* c, int L, const double* labels, const double* rotations, double* out, int32_t* tri_out) {
+    if (!c || L <= 0 || !out) return fail(MSMGPU_ERR_INVALID, "costfn_unary_table: bad arguments");
+    MSM_CUDA(cudaSetDevice(c->ctx->device));
+    cudaStream_t s = c->ctx->stream;
+    DevBuf<double> d_out;
+    DevBuf<int> d_tri;
+    MSM_CUDA(d_out.alloc((size_t)L * c->ncp, s));
+    if (tri_out) MSM_CUDA(d_tri.alloc((size_t)L * c->n_patch, s));
+    const msmgpu_status st = msmgpu_costfn_unary_table_dev(c, L, labels, rotations, d_out.p, tri_out ? d_tri.p : nullptr);
+    if (st != MSMGPU_OK && st != MSMGPU_ERR_NO_TRIANGLE) return st;
+    MSM_CUDA(cudaMemcpyAsync(out, d_out.p, (size_t)L * c->ncp * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (tri_out) MSM_CUDA(cudaMemcpyAsync(tri_out, d_tri.p, (size_t)L * c->n_patch * sizeof(int), cudaMemcpyDeviceToHost, s));
+    MSM_CUDA(cudaStreamSynchronize(s));
+    return st;
+}
+
+} // extern "C"

@@ -118,4 +118,77 @@ __host__ __device__ __forceinline__ void bary_weights_raw(const V3& p, const V3&
     w[0] = Aa / A; w[1] = Ab / A; w[2] = Ac / A;
 }
 
+// ------------------------------------------------------------------------------------------
+// Per-triangle query record: one 128-byte line per triangle, so a lane testing a triangle
+// touches exactly one L1/L2 line. Everything in it is a function of the triangle only and is
+// evaluated with the same expressions the reference evaluates per query (point.cpp:48-57,
+// triangle.cpp:91-110), so using the stored values changes no bit of any decision.
+// ------------------------------------------------------------------------------------------
+struct __align__(16) TriRec {
+    double v[9];      // corners v1 v2 v3 (Triangle::vertices order)
+    double s3[3];     // unit plane normal as project_point builds it (point.cpp:48-55)
+    double d;         // s3 . v1 (point.cpp:57)
+    double e12, e13, e23;   // |v2-v1|, |v3-v1|, |v3-v2| (denominators in triangle.cpp:91-110)
+};
+static_assert(sizeof(TriRec) == 128, "TriRec must be one 128-byte line");
+
+__host__ __device__ __forceinline__ void make_trirec(const V3& v1, const V3& v2, const V3& v3, TriRec& r) {
+    r.v[0] = v1.x; r.v[1] = v1.y; r.v[2] = v1.z;
+    r.v[3] = v2.x; r.v[4] = v2.y; r.v[5] = v2.z;
+    r.v[6] = v3.x; r.v[7] = v3.y; r.v[8] = v3.z;
+    const V3 s1 = vnormalized(vsub(v3, v1));
+    const V3 s2 = vnormalized(vsub(v2, v1));
+    const V3 s3 = vnormalized(vcross(s1, s2));
+    r.s3[0] = s3.x; r.s3[1] = s3.y; r.s3[2] = s3.z;
+    r.d = vdot(s3, v1);
+    r.e12 = vnorm(vsub(v2, v1));
+    r.e13 = vnorm(vsub(v3, v1));
+    r.e23 = vnorm(vsub(v3, v2));
+}
+
+// project_point (point.cpp:46-61) with the triangle-only part taken from the record
+__device__ __forceinline__ V3 rec_project(const V3& pt, const V3& s3, double d) {
+    const double si = d / vdot(s3, pt);
+    return vscale(pt, si);
+}
+
+// triangle.cpp:85-122 with the edge lengths taken from the record
+__device__ __forceinline__ double rec_boundary_distance(const V3& x0, const V3& x1, const V3& x2, const V3& x3,
+                                                        double e12, double e13, double e23) {
+    double d, dmin = DBL_MAX;
+    const V3 a1 = vsub(x0, x1), a2 = vsub(x0, x2), a3 = vsub(x0, x3);
+    V3 u = vsub(x2, x1);
+    if (vdot(a1, u) > 0 && vdot(a2, u) < 0) {
+        d = vnorm(vcross(a1, a2)) / e12;
+        if (d < dmin) dmin = d;
+    }
+    u = vsub(x3, x1);
+    if (vdot(a1, u) > 0 && vdot(a3, u) < 0) {
+        d = vnorm(vcross(a1, a3)) / e13;
+        if (d < dmin) dmin = d;
+    }
+    u = vsub(x3, x2);
+    if (vdot(a2, u) > 0 && vdot(a3, u) < 0) {
+        d = vnorm(vcross(a2, a3)) / e23;
+        if (d < dmin) dmin = d;
+    }
+    d = vnorm(a1); if (d < dmin) dmin = d;
+    d = vnorm(a2); if (d < dmin) dmin = d;
+    d = vnorm(a3); if (d < dmin) dmin = d;
+    return dmin;
+}
+
+// octree.cpp:143-154 for one triangle record (loaded as eight 16-byte words)
+__device__ __forceinline__ double rec_distance(const V3& pt, const TriRec* __restrict__ rp) {
+    const double2* q = reinterpret_cast<const double2*>(rp);
+    const double2 a = __ldg(q + 0), b = __ldg(q + 1), c = __ldg(q + 2), d4 = __ldg(q + 3), e = __ldg(q + 4);
+    const double2 f = __ldg(q + 5), g = __ldg(q + 6);
+    const V3 v1{a.x, a.y, b.x}, v2{b.y, c.x, c.y}, v3{d4.x, d4.y, e.x};
+    const V3 s3{e.y, f.x, f.y};
+    const V3 mP = rec_project(pt, s3, g.x);
+    if (!in_triangle(mP, v1, v2, v3)) return kNotInTriangle;
+    const double2 h = __ldg(q + 7);
+    return rec_boundary_distance(mP, v1, v2, v3, g.y, h.x, h.y);
+}
+
 } // namespace msm

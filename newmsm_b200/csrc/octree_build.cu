@@ -116,17 +116,17 @@ msmgpu_status exclusive_scan_i32(const int* d_in, int* d_out, int n, int* d_tota
 // per-triangle tables
 // ------------------------------------------------------------------------------------------
 __global__ void k_mesh_tables(int nt, const double* __restrict__ xyz, const int* __restrict__ tri,
-                              double* __restrict__ tv, double* __restrict__ aabb) {
+                              TriRec* __restrict__ rec, double* __restrict__ aabb) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nt) return;
-    double lo[3], hi[3];
+    double lo[3], hi[3], cv[9];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const int v = tri[3 * t + k];
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             const double c = xyz[3 * (size_t)v + a];
-            tv[9 * (size_t)t + 3 * k + a] = c;
+            cv[3 * k + a] = c;
             if (k == 0) { lo[a] = c; hi[a] = c; }
             else { // octree.cpp:52-58
                 if (c < lo[a]) lo[a] = c;
@@ -136,11 +136,14 @@ __global__ void k_mesh_tables(int nt, const double* __restrict__ xyz, const int*
     }
 #pragma unroll
     for (int a = 0; a < 3; ++a) { aabb[6 * (size_t)t + a] = lo[a]; aabb[6 * (size_t)t + 3 + a] = hi[a]; }
+    TriRec r;
+    make_trirec(V3{cv[0], cv[1], cv[2]}, V3{cv[3], cv[4], cv[5]}, V3{cv[6], cv[7], cv[8]}, r);
+    rec[t] = r;
 }
 
 msmgpu_status mesh_refresh_tables(msmgpu_mesh* m) {
     if (m->nt == 0) return MSMGPU_OK;
-    k_mesh_tables<<<(m->nt + 255) / 256, 256, 0, m->ctx->stream>>>(m->nt, m->xyz.p, m->tri.p, m->tv.p, m->aabb.p);
+    k_mesh_tables<<<(m->nt + 255) / 256, 256, 0, m->ctx->stream>>>(m->nt, m->xyz.p, m->tri.p, m->rec.p, m->aabb.p);
     MSM_CUDA(cudaGetLastError());
     return MSMGPU_OK;
 }

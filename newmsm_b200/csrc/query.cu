@@ -1,0 +1,263 @@
+// Nearest-triangle queries on the flattened octree and the kernels fed by them:
+// barycentric weights, coordinate blends (sphere_project_warp / surface_resample),
+// nearest-vertex gathers and the fused query -> weights -> 128-bit row gather resampler.
+//
+// Reference behaviour reproduced (msm-newresampler/src): Octree::get_closest_triangle
+// (octree.cpp:156-214), get_closest_vertex_ID (216-233), Triangle::calc_barycentric_weights
+// (triangle.cpp:124-143), Resampler::get_barycentric_weights (resampler.cpp:142-167), the
+// interpolation loop of barycentric_data_interpolation (resampler.cpp:40-52),
+// sphere_project_warp (311-328), surface_resample (284-302), nearest_neighbour_interpolation
+// (232-258).
+//
+// Execution model: a query is owned by a GROUP of G lanes (G = 1..32, compile-time). The lanes
+// of a group descend the tree redundantly (same addresses -> one broadcast load), then test
+// the leaf's triangles G at a time, one 128-byte TriRec line per lane, and arg-min over
+// (distance, scan position) with width-G shuffles. The reference keeps the FIRST triangle of
+// the scan with the strictly smallest distance, so ties are broken by scan position, which
+// makes the result independent of G.
+#include "query.cuh"
+
+namespace msm {
+
+// ------------------------------------------------------------------------------------------
+// stand-alone query kernels
+// ------------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(256) k_nearest(TreeView T, int n, const double* __restrict__ pts,
+                                                 int* __restrict__ out_tri, int* __restrict__ out_vtx, int* __restrict__ out_status) {
+    const int gl = threadIdx.x % G;
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const bool active = q < n;
+    const V3 pt = active ? load_pt(pts, q) : V3{0, 0, 0};
+    int st;
+    const int t = nearest_triangle<G>(T, pt, active, gl, st);
+    if (!active || gl != 0) return;
+    if (out_tri) out_tri[q] = t;
+    if (out_status) out_status[q] = st;
+    if (out_vtx) {   // octree.cpp:216-233
+        int id = -1;
+        if (t >= 0) {
+            double dist = DBL_MAX;
+            id = 0;
+            const double* v = T.rec[t].v;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double d = vnorm(vsub(pt, V3{v[3 * k], v[3 * k + 1], v[3 * k + 2]}));
+                if (d < dist) { id = __ldg(T.tri + 3 * (size_t)t + k); dist = d; }
+            }
+        }
+        out_vtx[q] = id;
+    }
+}
+
+template <int G>
+__global__ void __launch_bounds__(256) k_bary_weights(TreeView T, int n, const double* __restrict__ pts, int* __restrict__ out_idx,
+                                                      double* __restrict__ out_w, int* __restrict__ out_ne, int* __restrict__ out_status) {
+    const int gl = threadIdx.x % G;
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const bool active = q < n;
+    const V3 pt = active ? load_pt(pts, q) : V3{0, 0, 0};
+    int st;
+    const int t = nearest_triangle<G>(T, pt, active, gl, st);
+    if (!active || gl != 0) return;
+    int idx[3] = {-1, -1, -1};
+    double w[3] = {0, 0, 0};
+    int ne = 0;
+    if (t >= 0) ne = sorted_weights(T, t, pt, idx, w);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { out_idx[3 * (size_t)q + j] = idx[j]; out_w[3 * (size_t)q + j] = w[j]; }
+    if (out_ne) out_ne[q] = ne;
+    if (out_status) out_status[q] = st;
+}
+
+// sphere_project_warp (resampler.cpp:311-328, reproject = 1) / surface_resample (284-302, reproject = 0):
+// newPt = sum over the weight map (ascending id) of payload[id] * w, optionally normalised * 100.
+template <int G>
+__global__ void __launch_bounds__(256) k_blend_coords(TreeView T, int n, const double* __restrict__ pts, const double* __restrict__ payload,
+                                                      double* __restrict__ out, int reproject, int* __restrict__ out_status) {
+    const int gl = threadIdx.x % G;
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const bool active = q < n;
+    const V3 pt = active ? load_pt(pts, q) : V3{0, 0, 0};
+    int st;
+    const int t = nearest_triangle<G>(T, pt, active, gl, st);
+    if (!active || gl != 0) return;
+    V3 np{0, 0, 0};
+    if (t >= 0) {
+        int idx[3];
+        double w[3];
+        const int ne = sorted_weights(T, t, pt, idx, w);
+        for (int j = 0; j < ne; ++j) {   // Point*double then += (point.cpp:198,224)
+            const V3 c = load_pt(payload, idx[j]);
+            const V3 s = vscale(c, w[j]);
+            np.x += s.x; np.y += s.y; np.z += s.z;
+        }
+        if (reproject) {   // resampler.cpp:324-325
+            np = vnormalized(np);
+            np.x *= kRad; np.y *= kRad; np.z *= kRad;
+        }
+    }
+    out[3 * (size_t)q] = np.x; out[3 * (size_t)q + 1] = np.y; out[3 * (size_t)q + 2] = np.z;
+    if (out_status) out_status[q] = st;
+}
+
+// ------------------------------------------------------------------------------------------
+// fused barycentric resampler: query -> weights (shared memory) -> 3-row gather of D floats
+// ------------------------------------------------------------------------------------------
+constexpr int kResThreads = 256;
+constexpr int kResTile = 128;   // targets per CTA
+
+template <int G>
+__global__ void __launch_bounds__(kResThreads) k_bary_resample_f32(const ResampleJob* __restrict__ jobs, int n, const double* __restrict__ pts,
+                                                                  int D, int* __restrict__ out_status) {
+    __shared__ int s_idx[kResTile * 3];
+    __shared__ double s_w[kResTile * 3];
+    __shared__ int s_ne[kResTile];
+    const ResampleJob job = jobs[blockIdx.y];
+    const int tile0 = blockIdx.x * kResTile;
+    const int gl = threadIdx.x % G;
+    static_assert(kResTile % (kResThreads / G) == 0 || (kResThreads / G) % kResTile == 0, "tile/group mismatch");
+
+    // phase A: one group per target (FP64, L1/L2-resident tree and triangle records)
+    for (int q = threadIdx.x / G; q < kResTile; q += kResThreads / G) {
+        const int k = tile0 + q;
+        const bool active = k < n;
+        const V3 pt = active ? load_pt(pts, k) : V3{0, 0, 0};
+        int st;
+        const int t = nearest_triangle<G>(job.tree, pt, active, gl, st);
+        if (gl == 0) {
+            int idx[3] = {-1, -1, -1};
+            double w[3] = {0, 0, 0};
+            int ne = 0;
+            if (t >= 0) ne = sorted_weights(job.tree, t, pt, idx, w);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) { s_idx[3 * q + j] = idx[j]; s_w[3 * q + j] = w[j]; }
+            s_ne[q] = ne;
+            if (active && out_status) out_status[(size_t)blockIdx.y * n + k] = st;
+        }
+    }
+    __syncthreads();
+
+    // phase B: out[k][:] = sum_j in[idx_j][:] * w_j, accumulated in FP64 in ascending-id order like
+    // resampler.cpp:46-48, rows read and written as 128-bit words. HBM-bound part.
+    const float* __restrict__ fin = job.feat_in;
+    float* __restrict__ fout = job.feat_out;
+    const int rows = min(kResTile, n - tile0);
+    if ((D & 3) == 0 && ((reinterpret_cast<uintptr_t>(fin) | reinterpret_cast<uintptr_t>(fout)) & 15) == 0) {
+        const int D4 = D >> 2;
+        const float4* __restrict__ in4 = reinterpret_cast<const float4*>(fin);
+        float4* __restrict__ out4 = reinterpret_cast<float4*>(fout);
+        const int slots = rows * D4;
+        for (int s = threadIdx.x; s < slots; s += kResThreads) {
+            const int q = s / D4, c = s - q * D4;
+            const int ne = s_ne[q];
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                if (j < ne) {
+                    const float4 f = __ldg(in4 + (size_t)s_idx[3 * q + j] * D4 + c);
+                    const double w = s_w[3 * q + j];
+                    a0 += (double)f.x * w; a1 += (double)f.y * w; a2 += (double)f.z * w; a3 += (double)f.w * w;
+                }
+            }
+            __stcs(out4 + (size_t)(tile0 + q) * D4 + c, make_float4((float)a0, (float)a1, (float)a2, (float)a3));
+        }
+    } else {
+        const int slots = rows * D;
+        for (int s = threadIdx.x; s < slots; s += kResThreads) {
+            const int q = s / D, c = s - q * D;
+            const int ne = s_ne[q];
+            double a = 0.0;
+            for (int j = 0; j < ne; ++j) a += (double)__ldg(fin + (size_t)s_idx[3 * q + j] * D + c) * s_w[3 * q + j];
+            fout[(size_t)(tile0 + q) * D + c] = (float)a;
+        }
+    }
+}
+
+// nearest_neighbour_interpolation (resampler.cpp:232-258): out[d][i] = in[d][vertex_i], channel-major doubles
+__global__ void k_gather_channels_f64(int n, int nv, int D, const int* __restrict__ vtx, const double* __restrict__ in, double* __restrict__ out) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= (size_t)n * D) return;
+    const int d = (int)(i / n), k = (int)(i - (size_t)d * n);
+    const int v = vtx[k];
+    out[i] = v >= 0 ? in[(size_t)d * nv + v] : 0.0;
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers. The group width is a tuning knob (MSMGPU_QUERY_GROUP = 1,2,4,8,16,32; default 8).
+// ------------------------------------------------------------------------------------------
+static int g_query_group = 0;   // 0 = not yet chosen
+
+static bool valid_group(int v) { return v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32; }
+
+int query_group_width() {
+    if (g_query_group == 0) {
+        const char* e = getenv("MSMGPU_QUERY_GROUP");
+        const int v = e ? atoi(e) : 8;
+        g_query_group = valid_group(v) ? v : 8;
+    }
+    return g_query_group;
+}
+
+#define MSM_DISPATCH_G(G_, ...)                          \
+    switch (G_) {                                        \
+        case 1: { constexpr int G = 1; __VA_ARGS__; } break;   \
+        case 2: { constexpr int G = 2; __VA_ARGS__; } break;   \
+        case 4: { constexpr int G = 4; __VA_ARGS__; } break;   \
+        case 16: { constexpr int G = 16; __VA_ARGS__; } break; \
+        case 32: { constexpr int G = 32; __VA_ARGS__; } break; \
+        default: { constexpr int G = 8; __VA_ARGS__; } break;  \
+    }
+
+static inline unsigned query_blocks(int n, int g) { return (unsigned)(((long long)n * g + 255) / 256); }
+
+msmgpu_status launch_nearest(const TreeView& t, int n, const double* d_pts, int* d_tri, int* d_vertex, int* d_status, cudaStream_t s) {
+    if (n <= 0) return MSMGPU_OK;
+    const int g = query_group_width();
+    MSM_DISPATCH_G(g, (k_nearest<G><<<query_blocks(n, G), 256, 0, s>>>(t, n, d_pts, d_tri, d_vertex, d_status)));
+    MSM_CUDA(cudaGetLastError());
+    return MSMGPU_OK;
+}
+
+msmgpu_status launch_bary_weights(const TreeView& t, int n, const double* d_pts, int* d_idx, double* d_w, int* d_ne, int* d_status, cudaStream_t s) {
+    if (n <= 0) return MSMGPU_OK;
+    const int g = query_group_width();
+    MSM_DISPATCH_G(g, (k_bary_weights<G><<<query_blocks(n, G), 256, 0, s>>>(t, n, d_pts, d_idx, d_w, d_ne, d_status)));
+    MSM_CUDA(cudaGetLastError());
+    return MSMGPU_OK;
+}
+
+msmgpu_status launch_blend_coords(const TreeView& t, int n, const double* d_pts, const double* d_payload_xyz, double* d_out, int reproject,
+                                  int* d_status, cudaStream_t s) {
+    if (n <= 0) return MSMGPU_OK;
+    const int g = query_group_width();
+    MSM_DISPATCH_G(g, (k_blend_coords<G><<<query_blocks(n, G), 256, 0, s>>>(t, n, d_pts, d_payload_xyz, d_out, reproject, d_status)));
+    MSM_CUDA(cudaGetLastError());
+    return MSMGPU_OK;
+}
+
+msmgpu_status launch_bary_resample_f32(const ResampleJob* d_jobs, int n_jobs, int n, const double* d_pts, int D, int* d_status, cudaStream_t s) {
+    if (n <= 0 || n_jobs <= 0) return MSMGPU_OK;
+    const int g = query_group_width();
+    const dim3 grid((unsigned)((n + kResTile - 1) / kResTile), (unsigned)n_jobs);
+    MSM_DISPATCH_G(g, (k_bary_resample_f32<G><<<grid, kResThreads, 0, s>>>(d_jobs, n, d_pts, D, d_status)));
+    MSM_CUDA(cudaGetLastError());
+    return MSMGPU_OK;
+}
+
+msmgpu_status launch_gather_channels_f64(int n, int nv, int D, const int* d_vtx, const double* d_in, double* d_out, cudaStream_t s) {
+    const size_t total = (size_t)n * D;
+    if (total == 0) return MSMGPU_OK;
+    k_gather_channels_f64<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(n, nv, D, d_vtx, d_in, d_out);
+    MSM_CUDA(cudaGetLastError());
+    return MSMGPU_OK;
+}
+
+} // namespace msm
+
+extern "C" msmgpu_status msmgpu_set_query_group(int lanes) {
+    if (!msm::valid_group(lanes)) return msm::fail(MSMGPU_ERR_INVALID, "set_query_group: lanes must be 1, 2, 4, 8, 16 or 32");
+    msm::g_query_group = lanes;
+    return MSMGPU_OK;
+}
+extern "C" int msmgpu_get_query_group(void) { return msm::query_group_width(); }

@@ -1,0 +1,139 @@
+// Device-side nearest-triangle query on the flattened octree, shared by query.cu and cost.cu.
+// See query.cu for the execution model (groups of G lanes per query).
+#pragma once
+#include "common.cuh"
+
+#include <climits>
+
+namespace msm {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+template <int G>
+__device__ __forceinline__ void group_argmin(double& d, int& pos, int& t) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(kFull, d, o, G);
+        const int op = __shfl_xor_sync(kFull, pos, o, G);
+        const int ot = __shfl_xor_sync(kFull, t, o, G);
+        if (od < d || (od == d && op < pos)) { d = od; pos = op; t = ot; }
+    }
+}
+
+// All 32 lanes of the warp must call this together (inactive queries pass active = false);
+// the G lanes of a group pass the same point. `gl` = lane index inside the group.
+// Returns the triangle id (same value in all lanes of the group) or -1; status as msmgpu_status.
+template <int G>
+__device__ __forceinline__ int nearest_triangle(const TreeView& T, const V3& pt, bool active, int gl, int& status) {
+    status = MSMGPU_OK;
+    if (active) {   // node.cpp:67-77 on the root cube [-101,101]^3 (octree.cpp:157-158)
+        if (pt.x < -kBounds || pt.x > kBounds || pt.y < -kBounds || pt.y > kBounds || pt.z < -kBounds || pt.z > kBounds) {
+            status = MSMGPU_ERR_OUT_OF_BOX;
+            active = false;
+        }
+    }
+    double best_d = DBL_MAX;
+    int best_pos = INT_MAX, best_t = -1, parent = -1;
+    if (active) {
+        int4 nd = __ldg(T.nodes + T.root);
+        double lox = -kBounds, loy = -kBounds, loz = -kBounds, half = kBounds;
+        // octree.cpp:165-170: the LAST child (i,j,k nesting) whose closed box contains pt wins; child
+        // boxes are products of [lo,mid] / [mid,hi], so that is "upper half iff p >= mid" per axis.
+        while (nd.x >= 0) {
+            int c = 0;
+            const double mx = lox + half, my = loy + half, mz = loz + half;
+            if (pt.x >= mx) { c |= 4; lox = mx; }
+            if (pt.y >= my) { c |= 2; loy = my; }
+            if (pt.z >= mz) { c |= 1; loz = mz; }
+            half *= 0.5;
+            nd = __ldg(T.nodes + nd.x + c);
+        }
+        parent = nd.w;
+        for (int i = gl; i < nd.z; i += G) {   // octree.cpp:172-178
+            const int t = __ldg(T.pairs + nd.y + i);
+            const double d = rec_distance(pt, T.rec + t);
+            if (d > kNotInTriangle && d < best_d) { best_d = d; best_pos = i; best_t = t; }
+        }
+    }
+    group_argmin<G>(best_d, best_pos, best_t);
+    bool need = active && best_t < 0;
+    if (__any_sync(kFull, need)) {
+        if (need && parent < 0) { status = MSMGPU_ERR_NO_TRIANGLE; need = false; }   // root is a leaf
+        int first_child = 0;
+        if (need) {   // fallback 1, octree.cpp:180-192: every leaf child of the parent, children in order
+            first_child = __ldg(T.nodes + parent).x;
+            int base = 0;
+            for (int c = 0; c < 8; ++c) {
+                const int4 ch = __ldg(T.nodes + first_child + c);
+                for (int i = gl; i < ch.z; i += G) {
+                    const int t = __ldg(T.pairs + ch.y + i);
+                    const double d = rec_distance(pt, T.rec + t);
+                    if (d > kNotInTriangle && d < best_d) { best_d = d; best_pos = base + i; best_t = t; }
+                }
+                base += ch.z;
+            }
+        }
+        group_argmin<G>(best_d, best_pos, best_t);
+        const bool need2 = need && best_t < 0;
+        if (__any_sync(kFull, need2)) {
+            if (need2) {   // fallback 2, octree.cpp:194-208: triangle owning the geodesically nearest corner.
+                // 2R asin(c/2R) is increasing in the chord c, so the chord is compared directly.
+                int base = 0;
+                for (int c = 0; c < 8; ++c) {
+                    const int4 ch = __ldg(T.nodes + first_child + c);
+                    for (int i = gl; i < ch.z; i += G) {
+                        const int t = __ldg(T.pairs + ch.y + i);
+                        const double* v = T.rec[t].v;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            const double d = vnorm(vsub(V3{v[3 * k], v[3 * k + 1], v[3 * k + 2]}, pt));
+                            if (d < best_d) { best_d = d; best_pos = 3 * (base + i) + k; best_t = t; }
+                        }
+                    }
+                    base += ch.z;
+                }
+            }
+            group_argmin<G>(best_d, best_pos, best_t);
+        }
+        if (need && best_t < 0) status = MSMGPU_ERR_NO_TRIANGLE;   // octree.cpp:210-211
+    }
+    return best_t;
+}
+
+__device__ __forceinline__ V3 load_pt(const double* __restrict__ pts, int i) {
+    return V3{__ldg(pts + 3 * (size_t)i), __ldg(pts + 3 * (size_t)i + 1), __ldg(pts + 3 * (size_t)i + 2)};
+}
+__device__ __forceinline__ void rec_corners(const TriRec* __restrict__ r, V3& v1, V3& v2, V3& v3) {
+    v1 = V3{r->v[0], r->v[1], r->v[2]};
+    v2 = V3{r->v[3], r->v[4], r->v[5]};
+    v3 = V3{r->v[6], r->v[7], r->v[8]};
+}
+
+// calc_barycentric_weights (triangle.cpp:124-143) -> std::map<int,double> semantics: entries in
+// ascending vertex id, a repeated id keeps the LAST value assigned. Returns the entry count.
+__device__ __forceinline__ int sorted_weights(const TreeView& T, int t, const V3& pt, int* idx, double* w) {
+    const TriRec* r = T.rec + t;
+    V3 v1, v2, v3;
+    rec_corners(r, v1, v2, v3);
+    const V3 PP = rec_project(pt, V3{r->s3[0], r->s3[1], r->s3[2]}, r->d);
+    const double Aa = tri_area(PP, v2, v3);
+    const double Ab = tri_area(PP, v1, v3);
+    const double Ac = tri_area(PP, v1, v2);
+    const double A = Aa + Ab + Ac;
+    int id[3] = {__ldg(T.tri + 3 * (size_t)t), __ldg(T.tri + 3 * (size_t)t + 1), __ldg(T.tri + 3 * (size_t)t + 2)};
+    double ww[3] = {Aa / A, Ab / A, Ac / A};
+    int n = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {   // insert (id[k], ww[k]) into the sorted list
+        int j = 0;
+        while (j < n && idx[j] < id[k]) ++j;
+        if (j < n && idx[j] == id[k]) { w[j] = ww[k]; continue; }
+        for (int m = n; m > j; --m) { idx[m] = idx[m - 1]; w[m] = w[m - 1]; }
+        idx[j] = id[k]; w[j] = ww[k];
+        ++n;
+    }
+    for (int j = n; j < 3; ++j) { idx[j] = -1; w[j] = 0.0; }
+    return n;
+}
+
+} // namespace msm

@@ -1,0 +1,106 @@
+"""Host-side mirror of the reference's unary cost classes (msm-newmeshreg/src/DiscreteCostFunction.h:
+82-244) on top of the C ABI. The class and method names are the reference's; the per-call virtual
+`computeUnaryCost(node, label)` becomes a lookup into the table `computeUnaryCosts()` filled on the
+GPU (label-major `unarycosts[label * N + node]`, DiscreteCostFunction.cpp:242).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import check, f64, ptr
+from .resampler import Mesh, Octree
+
+MeshregException = capi.MsmGpuError   # reg_tools.h:38
+
+UNIVARIATE, MULTIVARIATE, PATCHWISE = 0, 1, 2
+SSD, CORRELATION = 1, 2   # similarities.h:48-58 (_simmeasure)
+
+
+class NonLinearSRegDiscreteCostFunction:
+    """Common state: TARGET mesh + octree, SOURCE mesh, FEAT (input/reference features), CP grid."""
+
+    KIND = UNIVARIATE
+
+    def __init__(self, simmeasure: int = CORRELATION):
+        self.simmeasure = simmeasure
+        self.h = None
+        self.unarycosts = None
+
+    # set_meshes + set_featurespace + set_octrees (DiscreteCostFunction.h:173-189)
+    def set_meshes(self, target: Mesh, source_xyz, src_feat, ref_feat, target_tree: Octree | None = None):
+        self.target = target
+        self.tree = target_tree or Octree(target)
+        self.L = target.L
+        s, a, b = f64(source_xyz), f64(np.atleast_2d(src_feat)), f64(np.atleast_2d(ref_feat))
+        assert a.shape[1] == len(s) and b.shape[1] == target.nvertices() and a.shape[0] == b.shape[0]
+        self.D, self.nsrc = a.shape[0], len(s)
+        self.h = C.c_void_p()
+        check(self.L.msmgpu_costfn_create(self.tree.h, self.KIND, self.simmeasure, len(s), ptr(s), self.D, ptr(a), ptr(b), C.byref(self.h)))
+
+    def reset_source(self, source_xyz):
+        s = f64(source_xyz)
+        check(self.L.msmgpu_costfn_reset_source(self.h, ptr(s)))
+
+    # reset_CPgrid + set_spacings + get_source_data (cpp:334-351)
+    def reset_CPgrid(self, cp_xyz, maxsep, controlptrange: float, HIGHREScfweight=None, AbsoluteWeights=None):
+        cp, ms = f64(cp_xyz), f64(maxsep)
+        self.ncp = len(cp)
+        absw = np.ones(self.ncp) if AbsoluteWeights is None else f64(AbsoluteWeights)
+        cfw = None if HIGHREScfweight is None else f64(np.atleast_2d(HIGHREScfweight))
+        check(self.L.msmgpu_costfn_set_cpgrid(self.h, self.ncp, ptr(cp), ptr(ms), float(controlptrange),
+                                              0 if cfw is None else cfw.shape[0], ptr(cfw), ptr(absw)))
+
+    def get_source_data(self):
+        """patch lists (CSR rowptr, members) as `_sourceinrange` (cpp:334-351)."""
+        rowptr = np.zeros(self.ncp + 1, np.int32)
+        check(self.L.msmgpu_costfn_patches(self.h, ptr(rowptr), None))
+        mem = np.zeros(int(rowptr[-1]), np.int32)
+        check(self.L.msmgpu_costfn_patches(self.h, ptr(rowptr), ptr(mem)))
+        return rowptr, mem
+
+    # set_labels + computeUnaryCosts (h:180, cpp:236-243)
+    def computeUnaryCosts(self, labels, ROTATIONS, want_triangles: bool = False):
+        lab, rot = f64(labels).reshape(-1, 3), f64(ROTATIONS).reshape(-1, 9)
+        assert len(rot) == self.ncp
+        self.nlabels = len(lab)
+        out = np.zeros((self.nlabels, self.ncp))
+        tri = None
+        if want_triangles:
+            rowptr = np.zeros(self.ncp + 1, np.int32)
+            check(self.L.msmgpu_costfn_patches(self.h, ptr(rowptr), None))
+            tri = np.zeros((self.nlabels, int(rowptr[-1])), np.int32)
+        check(self.L.msmgpu_costfn_unary_table(self.h, self.nlabels, ptr(lab), ptr(rot), ptr(out), ptr(tri)))
+        self.unarycosts = out
+        return (out, tri) if want_triangles else out
+
+    def computeUnaryCost(self, node: int, label: int) -> float:
+        return float(self.unarycosts[label, node])
+
+    def getUnaryCosts(self):
+        return self.unarycosts.reshape(-1)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.msmgpu_costfn_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class UnivariateNonLinearSRegDiscreteCostFunction(NonLinearSRegDiscreteCostFunction):
+    KIND = UNIVARIATE
+
+
+class MultivariateNonLinearSRegDiscreteCostFunction(NonLinearSRegDiscreteCostFunction):
+    KIND = MULTIVARIATE
+
+
+class PatchwiseMultivariateNonLinearSRegDiscreteCostFunction(NonLinearSRegDiscreteCostFunction):
+    KIND = PATCHWISE

@@ -1,0 +1,296 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (newmsm_b200.capi / resampler /
+discrete_cost), against the CPU oracle on the same seeded inputs and against the committed golden
+fixtures (outputs of the compiled reference). Indices bit-exact; FP64 outputs bit-exact; FP32
+payloads within 1e-5 relative (BASELINE.json north_star)."""
+import os
+
+import numpy as np
+import pytest
+
+from newmsm_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ST = {0: 0, 1: capi.ERR_OUT_OF_BOX, 2: capi.ERR_NO_TRIANGLE}   # oracle status -> msmgpu_status
+
+
+def load(name):
+    return np.load(os.path.join(G, name))
+
+
+@pytest.fixture(scope="module")
+def R():
+    from newmsm_b200 import build, resampler
+    build.build_library()
+    assert capi.lib().msmgpu_device_count() > 0, "no CUDA device: the GPU tests cannot run on a fallback"
+    return resampler
+
+
+@pytest.fixture(autouse=True)
+def no_pending_cuda_error():
+    yield
+    import gc
+    gc.collect()
+    pending = capi.lib().msmgpu_debug_take_cuda_error()
+    assert not pending, f"a call left a CUDA error behind: {pending.decode()}"
+
+
+@pytest.fixture(scope="module")
+def meshes():
+    out = {k: synth.icosphere(k) for k in (2, 3, 4, 5, 6)}
+    x5, t5 = out[5]
+    out["j5"] = (synth.jitter_sphere(x5, t5, frac=0.3, seed=11), t5)
+    return out
+
+
+def query_points(xyz, seed=0, n_rand=20000):
+    rng = np.random.default_rng(seed)
+    rot = synth.rotate_sphere(xyz)
+    rnd = rng.normal(size=(n_rand, 3))
+    rnd = rnd / np.linalg.norm(rnd, axis=1, keepdims=True) * 100.0
+    off = rnd[: n_rand // 4] * rng.uniform(0.6, 1.009, size=(n_rand // 4, 1))       # off the sphere, inside the cube
+    box = rng.uniform(-101, 101, size=(2000, 3))                                     # anywhere in the root cube
+    out_of_box = np.array([[101.5, 0, 0], [0, -102, 0], [50, 50, 101.0001]])
+    return np.concatenate([xyz, rot, rnd, off, box, out_of_box])
+
+
+def adversarial_points(xyz, tri):
+    mids = (xyz[tri[:, 0]] + xyz[tri[:, 1]]) / 2      # on edges (not re-projected: inside the sphere)
+    cent = xyz[tri].mean(axis=1)
+    on_mid_planes = np.array([[0.0, 0, 100], [0, 100, 0], [100, 0, 0], [0, 0, -100], [50.5, 50.5, 50.5], [-50.5, 25.25, 0]])
+    return np.concatenate([mids, cent, mids / np.linalg.norm(mids, axis=1, keepdims=True) * 100, on_mid_planes])
+
+
+@pytest.mark.parametrize("key", [2, 3, 4, 5, 6, "j5"])
+def test_octree_topology_matches_oracle(R, oracle_built, meshes, key):
+    xyz, tri = meshes[key]
+    ot = oracle_built.OracleOctree(xyz, tri)
+    k0, c0, t0 = ot.dump()
+    m = R.Mesh(xyz, tri)
+    k1, c1, t1 = R.Octree(m).dump()
+    assert np.array_equal(k0, k1) and np.array_equal(c0, c1) and np.array_equal(t0, t1)
+
+
+def test_octree_forest_batch(R, oracle_built, meshes):
+    keys = [4, "j5", 3, 5]
+    ms = [R.Mesh(*meshes[k]) for k in keys]
+    trees = R.Octree.build_batch(ms)
+    for k, t in zip(keys, trees):
+        ref = oracle_built.OracleOctree(*meshes[k]).dump()
+        got = t.dump()
+        assert all(np.array_equal(a, b) for a, b in zip(ref, got))
+        q = synth.rotate_sphere(meshes[k][0])
+        assert np.array_equal(t.get_closest_triangle(q), oracle_built.OracleOctree(*meshes[k]).query(q)[0])
+
+
+def test_octree_golden(R):
+    g = load("octree_ico3.npz")
+    t = R.Octree(R.Mesh(g["xyz"], g["tri"]))
+    kinds, counts, leaf_tris = t.dump()
+    assert np.array_equal(kinds, g["kinds"]) and np.array_equal(counts, g["counts"]) and np.array_equal(leaf_tris, g["leaf_tris"])
+    tri, vtx, st = t.query(g["q"])
+    assert np.array_equal(tri, g["tri_id"])
+    assert np.array_equal(st, np.vectorize(ST.get)(g["status"]))
+    ok = st == 0
+    assert np.array_equal(vtx[ok], g["vertex_id"][ok])
+    idx = np.zeros((ok.sum(), 3), np.int32); w = np.zeros((ok.sum(), 3)); ne = np.zeros(ok.sum(), np.int32)
+    q = np.ascontiguousarray(g["q"][ok])
+    capi.check(t.L.msmgpu_bary_weights(t.h, len(q), capi.ptr(q), capi.ptr(idx), capi.ptr(w), capi.ptr(ne)))
+    assert np.array_equal(idx, g["w_idx"]) and np.array_equal(w, g["w_val"]) and np.array_equal(ne, g["w_n"])
+    assert np.array_equal(t.mesh.vertex_areas(), g["vertex_area"])
+
+
+@pytest.mark.parametrize("group", [1, 2, 4, 8, 16, 32])
+@pytest.mark.parametrize("key", [3, 5, "j5"])
+def test_nearest_triangle_bit_exact(R, oracle_built, meshes, key, group):
+    xyz, tri = meshes[key]
+    capi.check(capi.lib().msmgpu_set_query_group(group))
+    try:
+        q = np.concatenate([query_points(xyz, seed=group), adversarial_points(xyz, tri)])
+        t0, v0, s0, _ = oracle_built.OracleOctree(xyz, tri).query(q)
+        t1, v1, s1 = R.Octree(R.Mesh(xyz, tri)).query(q)
+        assert np.array_equal(s1, np.vectorize(ST.get)(s0))
+        assert np.array_equal(t0, t1)
+        ok = s0 == 0
+        assert np.array_equal(v0[ok], v1[ok])
+        assert (s0 == 1).sum() == 3
+    finally:
+        capi.check(capi.lib().msmgpu_set_query_group(8))
+
+
+def test_query_raises_like_reference(R, meshes):
+    t = R.Octree(R.Mesh(*meshes[3]))
+    with pytest.raises(R.MeshException) as e:
+        t.get_closest_triangle(np.array([[0.0, 0.0, 150.0]]))
+    assert e.value.status == capi.ERR_OUT_OF_BOX and "bounding box" in e.value.message
+    assert len(t.get_closest_triangle(np.zeros((0, 3)))) == 0     # empty input
+
+
+def test_bary_weights_bit_exact(R, oracle_built, meshes):
+    xyz, tri = meshes[6]
+    low = synth.rotate_sphere(meshes[5][0])
+    i0, w0, n0, err = oracle_built.OracleOctree(xyz, tri).bary_weights(low)
+    assert err == 0
+    m = R.Mesh(xyz, tri)
+    i1, w1, n1 = R.Resampler().get_barycentric_weights(R.Mesh(low, meshes[5][1]), m, R.Octree(m))
+    assert np.array_equal(i0, i1) and np.array_equal(n0, n1) and np.array_equal(w0, w1)
+    # resampling a mesh onto itself gives identity weights (SURVEY §4 known answer)
+    i2, w2, n2 = R.Resampler().get_barycentric_weights(m, m, R.Octree(m))
+    hit = np.take_along_axis(w2, np.argmax(w2, axis=1)[:, None], 1)[:, 0]
+    assert np.allclose(hit, 1.0, atol=1e-9)
+    assert np.array_equal(np.take_along_axis(i2, np.argmax(w2, axis=1)[:, None], 1)[:, 0], np.arange(len(xyz)))
+
+
+@pytest.mark.parametrize("D", [1, 4, 7, 40])
+def test_fused_bary_resample(R, oracle_built, meshes, D):
+    xyz, tri = meshes[5]
+    low = synth.rotate_sphere(meshes[4][0], 0.02, -0.01, 0.05)
+    feat = synth.smooth_fields(xyz, D).astype(np.float32).astype(np.float64)     # FP32 payload, exactly representable
+    ref = oracle_built.oracle_bary_resample(xyz, tri, low, feat)
+    got = R.barycentric_resample(R.Mesh(xyz, tri), low, feat)
+    # FP64 accumulation in the reference's order, rounded once to FP32 on output
+    assert np.array_equal(got, ref.astype(np.float32).astype(np.float64))
+    scale = np.abs(ref).max()
+    assert np.abs(got - ref).max() <= 1e-5 * scale
+
+
+def test_fused_bary_resample_linear_field(R, meshes):
+    """A linear field a.x is reproduced exactly (to FP32) inside planar triangles at the projected point."""
+    xyz, tri = meshes[6]
+    low = synth.rotate_sphere(meshes[5][0])
+    a = np.array([[0.3, -0.2, 0.5], [1.0, 0.0, 0.0]])
+    feat = (a @ xyz.T).astype(np.float32).astype(np.float64)
+    got = R.barycentric_resample(R.Mesh(xyz, tri), low, feat)
+    m = R.Mesh(xyz, tri)
+    tri_id = R.Octree(m).get_closest_triangle(low)
+    v = xyz[tri[tri_id]]                                   # project the query into the triangle plane
+    nrm = np.cross(v[:, 1] - v[:, 0], v[:, 2] - v[:, 0])
+    s = (nrm * v[:, 0]).sum(1) / (nrm * low).sum(1)
+    expect = a @ (low * s[:, None]).T
+    assert np.abs(got - expect).max() < 2e-5 * np.abs(expect).max()
+
+
+@pytest.mark.parametrize("name", ["down", "up"])
+def test_adaptive_weights_golden(R, name):
+    g = load(f"resample_{name}.npz")
+    m_in, m_low = R.Mesh(g["xyz_in"], g["tri_in"], g["feat"]), R.Mesh(g["xyz_low"], g["tri_low"])
+    rowptr, col, val = R.Resampler().get_adaptive_barycentric_weights(m_in, m_low).csr()
+    assert np.array_equal(rowptr, g["rowptr"]) and np.array_equal(col, g["col"])
+    assert np.array_equal(val, g["val"])
+    assert np.array_equal(R.metric_resample(m_in, m_low), g["metric_out"])
+    got = R.barycentric_resample(m_in, g["xyz_low"])
+    assert np.abs(got - g["bary_out"]).max() <= 1e-5 * np.abs(g["bary_out"]).max()
+    f32out = R.metric_resample_f32(m_in, m_low, g["feat"].astype(np.float32))
+    assert np.abs(f32out - g["metric_out"]).max() <= 1e-5 * np.abs(g["metric_out"]).max()
+
+
+@pytest.mark.parametrize("pair", [(6, 5), (5, "j5"), ("j5", 4), (4, 5)])
+def test_adaptive_weights_vs_oracle(R, oracle_built, meshes, pair):
+    (xi, ti), (xl, tl) = meshes[pair[0]], meshes[pair[1]]
+    xl = synth.rotate_sphere(xl, 0.05, 0.02, -0.03)
+    r0, c0, v0 = oracle_built.oracle_adaptive_weights(xi, ti, xl, tl)
+    m_in, m_low = R.Mesh(xi, ti), R.Mesh(xl, tl)
+    W = R.Resampler().get_adaptive_barycentric_weights(m_in, m_low)
+    r1, c1, v1 = W.csr()
+    assert np.array_equal(r0, r1) and np.array_equal(c0, c1) and np.array_equal(v0, v1)
+    assert np.array_equal(m_in.vertex_areas(), oracle_built.oracle_vertex_areas(xi, ti))
+    feat = synth.smooth_fields(xi, 3)
+    m_in.pvalues = feat
+    assert np.array_equal(R.metric_resample(m_in, m_low), oracle_built.oracle_metric_resample(xi, ti, xl, tl, feat))
+    rows = W.rows()
+    assert len(rows) == len(xl) and abs(sum(rows[0].values()) - 1.0) < 1e-12
+
+
+def test_blend_golden(R):
+    g = load("blend.npz")
+    m = R.Mesh(g["xf"], g["tf"])
+    assert np.array_equal(R.sphere_project_warp(g["sph"], m, g["xto"]), g["warp"])
+    assert np.array_equal(R.surface_resample(g["anat"], m, g["sph"]), g["surf"])
+    assert np.array_equal(R.nearest_neighbour_interpolation(m, g["sph"], g["feat"]), g["nn"])
+
+
+def test_rotation_golden(R):
+    g = load("rotation.npz")
+    assert np.array_equal(R.estimate_rotation_matrix(g["ci"], g["index"]), g["R"])
+
+
+# ---------------------------------------------------------------------------------------------
+# cost functions
+# ---------------------------------------------------------------------------------------------
+def cost_setup(oracle_built, cp_level, data_level, D, seed=3):
+    cp, _ = synth.icosphere(cp_level)
+    xyz, tri = synth.icosphere(data_level)
+    src = synth.smooth_warp(xyz, max_disp=1.5, seed=seed)                 # SOURCE mesh = warped data grid
+    ref_feat = synth.smooth_fields(xyz, D, seed0=100)
+    src_feat = synth.smooth_fields(src, D, seed0=100, noise=0.05)
+    # MAXSEP: largest distance from a CP to its mesh neighbours ~ CP spacing; any positive vector is a valid input
+    cp_tri = synth.icosphere(cp_level)[1]
+    e = np.zeros(len(cp))
+    for a, b in ((0, 1), (1, 2), (0, 2)):
+        d = np.linalg.norm(cp[cp_tri[:, a]] - cp[cp_tri[:, b]], axis=1)
+        np.maximum.at(e, cp_tri[:, a], d)
+        np.maximum.at(e, cp_tri[:, b], d)
+    rng = np.random.default_rng(seed)
+    # 7 labels: the CP itself plus 6 small displacements, expressed around the north pole like the label grid
+    centre = np.array([0.0, 0.0, 100.0])
+    labels = [centre]
+    for k in range(6):
+        ang = k * np.pi / 3
+        p = centre + 0.4 * e.mean() * np.array([np.cos(ang), np.sin(ang), 0.0])
+        labels.append(p / np.linalg.norm(p) * 100)
+    labels = np.array(labels)
+    rot = np.array([oracle_built.oracle_rotation_matrix(centre, c) for c in cp]).reshape(-1, 9)   # get_rotations (DiscreteModel.cpp:310)
+    absw = rng.uniform(0.5, 1.5, size=len(cp))
+    return dict(cp=cp, xyz=xyz, tri=tri, src=src, ref_feat=ref_feat, src_feat=src_feat, maxsep=e, labels=labels, rot=rot, absw=absw)
+
+
+def test_patch_membership_bit_exact(R, oracle_built):
+    from newmsm_b200 import discrete_cost as DC
+    s = cost_setup(oracle_built, 3, 5, 1)
+    cf = DC.UnivariateNonLinearSRegDiscreteCostFunction()
+    cf.set_meshes(R.Mesh(s["xyz"], s["tri"]), s["src"], s["src_feat"], s["ref_feat"])
+    for rng_ in (1.0, 0.5, 1.7):
+        cf.reset_CPgrid(s["cp"], s["maxsep"], rng_)
+        r1, m1 = cf.get_source_data()
+        r0, m0 = oracle_built.oracle_patch_membership(s["cp"], s["src"], s["maxsep"], rng_)
+        assert np.array_equal(r0, r1) and np.array_equal(m0, m1)
+    # knife edge: thresholds that EQUAL a computed geodesic distance (strict '<' must exclude that vertex)
+    k = np.arange(len(s["cp"]))
+    chord = np.linalg.norm(s["cp"][k] - s["src"][(k * 37) % len(s["src"])], axis=1)
+    chord = np.sqrt(((s["cp"][k] - s["src"][(k * 37) % len(s["src"])]) ** 2) @ np.ones(3))
+    ms = 2 * 100.0 * np.arcsin(np.minimum(chord, 15.0) / (2 * 100.0))
+    cf.reset_CPgrid(s["cp"], ms, 1.0)
+    r1, m1 = cf.get_source_data()
+    r0, m0 = oracle_built.oracle_patch_membership(s["cp"], s["src"], ms, 1.0)
+    assert np.array_equal(r0, r1) and np.array_equal(m0, m1)
+
+
+@pytest.mark.parametrize("kind,D", [(0, 1), (1, 6), (2, 6)])
+@pytest.mark.parametrize("sim", [1, 2])
+def test_unary_costs_bit_exact(R, oracle_built, kind, D, sim):
+    from newmsm_b200 import discrete_cost as DC
+    s = cost_setup(oracle_built, 3, 5, D)
+    cls = [DC.UnivariateNonLinearSRegDiscreteCostFunction, DC.MultivariateNonLinearSRegDiscreteCostFunction,
+           DC.PatchwiseMultivariateNonLinearSRegDiscreteCostFunction][kind]
+    cf = cls(simmeasure=sim)
+    cf.set_meshes(R.Mesh(s["xyz"], s["tri"]), s["src"], s["src_feat"], s["ref_feat"])
+    rng = np.random.default_rng(5)
+    cfw = rng.uniform(0.2, 1.0, size=(D if kind == 1 else 1, len(s["src"])))
+    for weights in (None, cfw):
+        cf.reset_CPgrid(s["cp"], s["maxsep"], 1.0, HIGHREScfweight=weights, AbsoluteWeights=s["absw"])
+        prow, pmem = cf.get_source_data()
+        got, tri_got = cf.computeUnaryCosts(s["labels"], s["rot"], want_triangles=True)
+        ot = oracle_built.OracleOctree(s["xyz"], s["tri"])
+        ref, tri_ref = oracle_built.oracle_unary_costs(kind, sim, ot, s["cp"], s["rot"], s["labels"], s["src"], prow, pmem,
+                                                       s["src_feat"], s["ref_feat"], weights, s["absw"], want_tri=True)
+        assert np.array_equal(tri_got, tri_ref)
+        assert np.array_equal(got, ref)
+        assert cf.computeUnaryCost(5, 2) == ref[2, 5]
+    # corr(A, A) = 1 -> cost 0 when the source is the target and label 0 = "stay" (SURVEY §4 known answer)
+    if sim == 2 and kind == 0:
+        cf2 = cls(simmeasure=2)
+        cf2.set_meshes(R.Mesh(s["xyz"], s["tri"]), s["xyz"], s["ref_feat"], s["ref_feat"])
+        cf2.reset_CPgrid(s["cp"], s["maxsep"], 1.0)
+        c = cf2.computeUnaryCosts(s["labels"][:1], s["rot"])
+        assert np.abs(c).max() < 1e-12
