@@ -46,6 +46,8 @@ typedef struct msmgpu_costfn msmgpu_costfn;   /* device state of one DiscreteCos
 const char* msmgpu_last_error(void);
 const char* msmgpu_version(void);
 int msmgpu_device_count(void);
+/* number of kernels this library has launched since it was loaded (bench.py reports it as gpu_launches) */
+unsigned long long msmgpu_launch_count(void);
 /* debugging aid: text of a pending CUDA runtime error left by an unchecked call (clears it); "" if none */
 const char* msmgpu_debug_take_cuda_error(void);
 
@@ -118,6 +120,8 @@ msmgpu_status msmgpu_bary_resample_f32_dev(msmgpu_octree* t, int n, const double
 /* batched over subjects (one launch): trees[s], pts shared, d_feat_in[s], d_feat_out[s] */
 msmgpu_status msmgpu_bary_resample_batch_f32_dev(msmgpu_ctx* ctx, int n_subjects, msmgpu_octree* const* trees, int n, const double* d_pts,
                                                  int D, const float* const* d_feat_in, float* const* d_feat_out, int32_t* d_status);
+/* host buffers, FP32 payload, channel-major like Mesh::pvalues: feat_in [D][nv] float -> feat_out [D][n] float */
+msmgpu_status msmgpu_bary_resample_f32(msmgpu_octree* t, int n, const double* pts, int D, const float* feat_in, float* feat_out);
 /* host-buffer convenience (channel-major double in/out), used by the parity tests */
 msmgpu_status msmgpu_bary_resample(msmgpu_mesh* in_mesh, int n, const double* pts, int D, const double* feat_in, double* feat_out);
 

@@ -35,6 +35,7 @@ _SIGNATURES = {
     "msmgpu_last_error": (C.c_char_p, []),
     "msmgpu_version": (C.c_char_p, []),
     "msmgpu_device_count": (_i, []),
+    "msmgpu_launch_count": (C.c_ulonglong, []),
     "msmgpu_debug_take_cuda_error": (C.c_char_p, []),
     "msmgpu_set_query_group": (_i, [_i]),
     "msmgpu_get_query_group": (_i, []),
@@ -67,6 +68,7 @@ _SIGNATURES = {
     "msmgpu_metric_resample_f32": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "msmgpu_bary_resample_f32_dev": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp]),
     "msmgpu_bary_resample_batch_f32_dev": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp]),
+    "msmgpu_bary_resample_f32": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
     "msmgpu_bary_resample": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
     "msmgpu_sphere_project_warp": (_i, [_vp, _vp, _i, _vp, _vp]),
     "msmgpu_surface_resample": (_i, [_vp, _vp, _i, _vp, _vp]),

@@ -11,6 +11,7 @@
 namespace msm {
 
 static thread_local std::string g_last_error;
+unsigned long long g_launch_count = 0;
 
 void set_error(const std::string& msg) { g_last_error = msg; }
 msmgpu_status fail(msmgpu_status st, const std::string& msg) {
@@ -39,7 +40,7 @@ msmgpu_status first_error(const int* d_status, size_t n, cudaStream_t s, int* ho
     MSM_CUDA(first.alloc(1, s));
     MSM_CUDA(cudaMemsetAsync(first.p, 0xff, sizeof(unsigned long long), s));
     k_first_error<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_status, n, first.p);
-    MSM_CUDA(cudaGetLastError());
+    MSM_LAUNCH_CHECK();
     unsigned long long h = 0;
     MSM_CUDA(cudaMemcpyAsync(&h, first.p, sizeof(h), cudaMemcpyDeviceToHost, s));
     MSM_CUDA(cudaStreamSynchronize(s));
@@ -71,7 +72,7 @@ static msmgpu_status transpose(int rows, int cols, const TI* in, TO* out, cudaSt
     if (rows <= 0 || cols <= 0) return MSMGPU_OK;
     const dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
     k_transpose<TI, TO><<<grid, block, 0, s>>>(rows, cols, in, out);
-    MSM_CUDA(cudaGetLastError());
+    MSM_LAUNCH_CHECK();
     return MSMGPU_OK;
 }
 
@@ -154,6 +155,8 @@ const char* msmgpu_debug_take_cuda_error(void) {
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? "" : cudaGetErrorString(e);
 }
+
+unsigned long long msmgpu_launch_count(void) { return g_launch_count; }
 
 int msmgpu_device_count(void) {
     int n = 0;
@@ -412,6 +415,29 @@ msmgpu_status msmgpu_bary_resample(msmgpu_mesh* in_mesh, int n, const double* pt
     MSM_TRY(msmgpu_bary_resample_f32_dev(t, n, d_pts.p, D, d_rows_in.p, d_rows_out.p, d_st.p));
     MSM_TRY(launch_rows_f32_to_chmajor_f64(D, n, d_rows_out.p, d_cm_out.p, s));
     MSM_CUDA(cudaMemcpyAsync(feat_out, d_cm_out.p, (size_t)D * n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    return finish_queries(d_st.p, n, nullptr, s);
+}
+
+// FP32 payload on host buffers (channel-major floats, what GIFTI stores): Octree(in) is supplied by the caller
+msmgpu_status msmgpu_bary_resample_f32(msmgpu_octree* t, int n, const double* pts, int D, const float* feat_in, float* feat_out) {
+    if (!t || n <= 0 || D <= 0 || !pts || !feat_in || !feat_out) return fail(MSMGPU_ERR_INVALID, "bary_resample_f32: bad arguments");
+    msmgpu_ctx* ctx = t->ctx;
+    MSM_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const int nv = t->mesh->nv;
+    DevBuf<double> d_pts;
+    DevBuf<float> d_cm_in, d_rows_in, d_rows_out, d_cm_out;
+    DevBuf<int> d_st;
+    MSM_TRY(upload(d_pts, pts, 3 * (size_t)n, s));
+    MSM_TRY(upload(d_cm_in, feat_in, (size_t)D * nv, s));
+    MSM_CUDA(d_rows_in.alloc((size_t)D * nv, s));
+    MSM_CUDA(d_rows_out.alloc((size_t)D * n, s));
+    MSM_CUDA(d_cm_out.alloc((size_t)D * n, s));
+    MSM_CUDA(d_st.alloc(n, s));
+    MSM_TRY(launch_chmajor_f32_to_rows_f32(D, nv, d_cm_in.p, d_rows_in.p, s));
+    MSM_TRY(msmgpu_bary_resample_f32_dev(t, n, d_pts.p, D, d_rows_in.p, d_rows_out.p, d_st.p));
+    MSM_TRY(launch_rows_f32_to_chmajor_f32(D, n, d_rows_out.p, d_cm_out.p, s));
+    MSM_CUDA(cudaMemcpyAsync(feat_out, d_cm_out.p, (size_t)D * n * sizeof(float), cudaMemcpyDeviceToHost, s));
     return finish_queries(d_st.p, n, nullptr, s);
 }
 

@@ -22,6 +22,14 @@ msmgpu_status fail(msmgpu_status st, const std::string& msg);
             return ::msm::fail(MSMGPU_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
     } while (0)
 
+// after every kernel launch: count it (msmgpu_launch_count) and pick up launch errors
+extern unsigned long long g_launch_count;
+#define MSM_LAUNCH_CHECK()                 \
+    do {                                   \
+        ++::msm::g_launch_count;           \
+        MSM_CUDA(cudaGetLastError());      \
+    } while (0)
+
 #define MSM_TRY(expr)                          \
     do {                                       \
         msmgpu_status _s = (expr);             \

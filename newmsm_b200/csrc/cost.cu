@@ -289,7 +289,7 @@ template <int G>
 static msmgpu_status launch_unary_g(const UnaryArgs& a, size_t smem, cudaStream_t s) {
     if (smem > 48 * 1024) MSM_CUDA(cudaFuncSetAttribute(k_unary_table<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_unary_table<G><<<dim3((unsigned)a.ncp, (unsigned)a.L), kCostThreads, smem, s>>>(a);
-    MSM_CUDA(cudaGetLastError());
+    MSM_LAUNCH_CHECK();
     return MSMGPU_OK;
 }
 
@@ -384,12 +384,12 @@ msmgpu_status msmgpu_costfn_set_cpgrid(msmgpu_costfn* c, int ncp, const double* 
     MSM_CUDA(d_tot.alloc(2, s));
     MSM_CUDA(c->prow.alloc((size_t)ncp + 1, s));
     k_patch_members<0><<<ncp, 256, 0, s>>>(c->nsrc, c->cp_xyz.p, c->src_xyz.p, c->chord_thr.p, count.p, nullptr, nullptr);
-    MSM_CUDA(cudaGetLastError());
+    MSM_LAUNCH_CHECK();
     MSM_TRY(exclusive_scan_i32(count.p, c->prow.p, ncp, d_tot.p, s));
     MSM_CUDA(cudaMemcpyAsync(c->prow.p + ncp, d_tot.p, sizeof(int), cudaMemcpyDeviceToDevice, s));
     MSM_CUDA(cudaMemsetAsync(d_tot.p + 1, 0, sizeof(int), s));
     k_max_i32<<<(ncp + 255) / 256, 256, 0, s>>>(ncp, count.p, d_tot.p + 1);
-    MSM_CUDA(cudaGetLastError());
+    MSM_LAUNCH_CHECK();
     int h[2];
     MSM_CUDA(cudaMemcpyAsync(h, d_tot.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
     MSM_CUDA(cudaStreamSynchronize(s));
@@ -398,7 +398,7 @@ msmgpu_status msmgpu_costfn_set_cpgrid(msmgpu_costfn* c, int ncp, const double* 
     MSM_CUDA(c->pmem.alloc((size_t)c->n_patch, s));
     if (c->n_patch > 0) {
         k_patch_members<1><<<ncp, 256, 0, s>>>(c->nsrc, c->cp_xyz.p, c->src_xyz.p, c->chord_thr.p, nullptr, c->prow.p, c->pmem.p);
-        MSM_CUDA(cudaGetLastError());
+        MSM_LAUNCH_CHECK();
     }
     MSM_CUDA(cudaStreamSynchronize(s));
     return MSMGPU_OK;

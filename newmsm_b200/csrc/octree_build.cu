@@ -98,17 +98,17 @@ msmgpu_status exclusive_scan_i32(const int* d_in, int* d_out, int n, int* d_tota
     const int tiles = (n + kScanTile - 1) / kScanTile;
     if (tiles == 1) {
         k_scan_tiles<<<1, kScanThreads, 0, s>>>(d_in, d_out, n, nullptr, d_total);
-        MSM_CUDA(cudaGetLastError());
+        MSM_LAUNCH_CHECK();
         return MSMGPU_OK;
     }
     DevBuf<int> sums, offs;
     MSM_CUDA(sums.alloc(tiles, s));
     MSM_CUDA(offs.alloc(tiles, s));
     k_scan_tile_sums<<<tiles, kScanThreads, 0, s>>>(d_in, n, sums.p);
-    MSM_CUDA(cudaGetLastError());
+    MSM_LAUNCH_CHECK();
     MSM_TRY(exclusive_scan_i32(sums.p, offs.p, tiles, nullptr, s));
     k_scan_tiles<<<tiles, kScanThreads, 0, s>>>(d_in, d_out, n, offs.p, d_total);
-    MSM_CUDA(cudaGetLastError());
+    MSM_LAUNCH_CHECK();
     return MSMGPU_OK;
 }
 
@@ -144,7 +144,7 @@ __global__ void k_mesh_tables(int nt, const double* __restrict__ xyz, const int*
 msmgpu_status mesh_refresh_tables(msmgpu_mesh* m) {
     if (m->nt == 0) return MSMGPU_OK;
     k_mesh_tables<<<(m->nt + 255) / 256, 256, 0, m->ctx->stream>>>(m->nt, m->xyz.p, m->tri.p, m->rec.p, m->aabb.p);
-    MSM_CUDA(cudaGetLastError());
+    MSM_LAUNCH_CHECK();
     return MSMGPU_OK;
 }
 
@@ -384,7 +384,7 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
             for (int v : h_nt) max_nt = v > max_nt ? v : max_nt;
             dim3 grid((unsigned)std::min((max_nt + 255) / 256, 1024), (unsigned)n);
             k_init_roots<<<grid, 256, 0, s>>>(n, F->nodes.p, bn.p, F->node_depth.p, F->pairs.p, d_off.p, d_nt.p);
-            MSM_CUDA(cudaGetLastError());
+            MSM_LAUNCH_CHECK();
         }
         int node_begin = 0, n_level = n;
         int n_nodes = n;
@@ -405,7 +405,7 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
             (void)avg;
             const int tb = depth <= 2 ? 1024 : (depth <= 4 ? 256 : 128);
             k_decide_count<<<n_level, tb, 0, s>>>(node_begin, F->nodes.p, bn.p, F->pairs.p, d_aabb.p, root_half, split_flag.p, child_cnt.p);
-            MSM_CUDA(cudaGetLastError());
+            MSM_LAUNCH_CHECK();
             MSM_TRY(exclusive_scan_i32(split_flag.p, split_rank.p, n_level, totals.p, s));
             MSM_TRY(exclusive_scan_i32(child_cnt.p, child_off.p, n_level * 8, totals.p + 1, s));
             int h_tot[2];
@@ -416,14 +416,14 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
             if (n_split == 0) break;
             if ((long long)n_nodes + 8ll * n_split > node_cap || n_pairs + new_pairs > pair_cap) { overflow = true; break; }
             k_save_lists<<<(n_level + 255) / 256, 256, 0, s>>>(node_begin, n_level, F->nodes.p, list_start.p, list_count.p);
-            MSM_CUDA(cudaGetLastError());
+            MSM_LAUNCH_CHECK();
             k_make_children<<<(n_level + 255) / 256, 256, 0, s>>>(node_begin, n_level, F->nodes.p, bn.p, F->node_depth.p, split_flag.p,
                                                                  split_rank.p, child_cnt.p, child_off.p, n_nodes, (int)n_pairs, root_half,
                                                                  (int)node_cap);
-            MSM_CUDA(cudaGetLastError());
+            MSM_LAUNCH_CHECK();
             k_scatter<<<n_level, tb, 0, s>>>(node_begin, F->nodes.p, bn.p, F->pairs.p, d_aabb.p, root_half, split_flag.p, list_start.p,
                                              list_count.p, child_off.p, (int)n_pairs);
-            MSM_CUDA(cudaGetLastError());
+            MSM_LAUNCH_CHECK();
             node_begin = n_nodes;
             n_level = 8 * n_split;
             n_nodes += n_level;

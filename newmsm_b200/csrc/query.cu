@@ -215,7 +215,7 @@ msmgpu_status launch_nearest(const TreeView& t, int n, const double* d_pts, int*
     if (n <= 0) return MSMGPU_OK;
     const int g = query_group_width();
     MSM_DISPATCH_G(g, (k_nearest<G><<<query_blocks(n, G), 256, 0, s>>>(t, n, d_pts, d_tri, d_vertex, d_status)));
-    MSM_CUDA(cudaGetLastError());
+    MSM_LAUNCH_CHECK();
     return MSMGPU_OK;
 }
 
@@ -223,7 +223,7 @@ msmgpu_status launch_bary_weights(const TreeView& t, int n, const double* d_pts,
     if (n <= 0) return MSMGPU_OK;
     const int g = query_group_width();
     MSM_DISPATCH_G(g, (k_bary_weights<G><<<query_blocks(n, G), 256, 0, s>>>(t, n, d_pts, d_idx, d_w, d_ne, d_status)));
-    MSM_CUDA(cudaGetLastError());
+    MSM_LAUNCH_CHECK();
     return MSMGPU_OK;
 }
 
@@ -232,7 +232,7 @@ msmgpu_status launch_blend_coords(const TreeView& t, int n, const double* d_pts,
     if (n <= 0) return MSMGPU_OK;
     const int g = query_group_width();
     MSM_DISPATCH_G(g, (k_blend_coords<G><<<query_blocks(n, G), 256, 0, s>>>(t, n, d_pts, d_payload_xyz, d_out, reproject, d_status)));
-    MSM_CUDA(cudaGetLastError());
+    MSM_LAUNCH_CHECK();
     return MSMGPU_OK;
 }
 
@@ -241,7 +241,7 @@ msmgpu_status launch_bary_resample_f32(const ResampleJob* d_jobs, int n_jobs, in
     const int g = query_group_width();
     const dim3 grid((unsigned)((n + kResTile - 1) / kResTile), (unsigned)n_jobs);
     MSM_DISPATCH_G(g, (k_bary_resample_f32<G><<<grid, kResThreads, 0, s>>>(d_jobs, n, d_pts, D, d_status)));
-    MSM_CUDA(cudaGetLastError());
+    MSM_LAUNCH_CHECK();
     return MSMGPU_OK;
 }
 
@@ -249,7 +249,7 @@ msmgpu_status launch_gather_channels_f64(int n, int nv, int D, const int* d_vtx,
     const size_t total = (size_t)n * D;
     if (total == 0) return MSMGPU_OK;
     k_gather_channels_f64<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(n, nv, D, d_vtx, d_in, d_out);
-    MSM_CUDA(cudaGetLastError());
+    MSM_LAUNCH_CHECK();
     return MSMGPU_OK;
 }
 

@@ -97,7 +97,7 @@ static msmgpu_status bucketize(const E& e, int n_src, int nkeys, Buckets& B, cud
     MSM_CUDA(cudaMemsetAsync(cursor.p, 0, nkeys * sizeof(int), s));
     const unsigned gs = (unsigned)((n_src + 255) / 256), gk = (unsigned)((nkeys + 255) / 256);
     if (n_src > 0) k_bucket_count<E><<<gs, 256, 0, s>>>(e, cnt.p);
-    MSM_CUDA(cudaGetLastError());
+    MSM_LAUNCH_CHECK();
     MSM_TRY(exclusive_scan_i32(cnt.p, B.ptr.p, nkeys, d_total.p, s));
     MSM_CUDA(cudaMemcpyAsync(B.ptr.p + nkeys, d_total.p, sizeof(int), cudaMemcpyDeviceToDevice, s));
     MSM_CUDA(cudaMemcpyAsync(&B.total, d_total.p, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -106,9 +106,9 @@ static msmgpu_status bucketize(const E& e, int n_src, int nkeys, Buckets& B, cud
     MSM_CUDA(B.val.alloc((size_t)B.total, s));
     if (B.total > 0) {
         k_bucket_fill<E><<<gs, 256, 0, s>>>(e, B.ptr.p, cursor.p, B.id.p, B.val.p);
-        MSM_CUDA(cudaGetLastError());
+        MSM_LAUNCH_CHECK();
         k_bucket_sort<<<gk, 256, 0, s>>>(nkeys, B.ptr.p, B.id.p, B.val.p);
-        MSM_CUDA(cudaGetLastError());
+        MSM_LAUNCH_CHECK();
     }
     return MSMGPU_OK;
 }
@@ -138,7 +138,7 @@ msmgpu_status vertex_areas_dev(msmgpu_mesh* m, double* d_out) {
     Buckets B;
     MSM_TRY(bucketize(EmitVertexTriangles{m->tri.p, m->rec.p, m->nt}, m->nt, m->nv, B, s));
     k_bucket_mean<<<(m->nv + 255) / 256, 256, 0, s>>>(m->nv, B.ptr.p, B.val.p, d_out);
-    MSM_CUDA(cudaGetLastError());
+    MSM_LAUNCH_CHECK();
     return MSMGPU_OK;
 }
 
@@ -221,7 +221,7 @@ msmgpu_status adaptive_weights_build(msmgpu_mesh* in_mesh, msmgpu_octree* in_tre
     MSM_CUDA(W->rowptr.alloc((size_t)nv_low + 1, s));
     const unsigned gl = (unsigned)((nv_low + 255) / 256);
     k_row_lengths<<<gl, 256, 0, s>>>(nv_low, fne.p, rr.ptr.p, len.p);
-    MSM_CUDA(cudaGetLastError());
+    MSM_LAUNCH_CHECK();
     MSM_TRY(exclusive_scan_i32(len.p, W->rowptr.p, nv_low, d_nnz.p, s));
     MSM_CUDA(cudaMemcpyAsync(W->rowptr.p + nv_low, d_nnz.p, sizeof(int), cudaMemcpyDeviceToDevice, s));
     int nnz = 0;
@@ -230,15 +230,15 @@ msmgpu_status adaptive_weights_build(msmgpu_mesh* in_mesh, msmgpu_octree* in_tre
     MSM_CUDA(W->col.alloc((size_t)nnz, s));
     MSM_CUDA(W->val.alloc((size_t)nnz, s));
     k_fill_rows<<<gl, 256, 0, s>>>(nv_low, W->rowptr.p, fidx.p, fw.p, fne.p, rr.ptr.p, rr.id.p, rr.val.p, new_area.p, W->col.p, W->val.p);
-    MSM_CUDA(cudaGetLastError());
+    MSM_LAUNCH_CHECK();
 
     // correction[src] = sum over targets (ascending) of the area-scaled weights (resampler.cpp:114-116)
     Buckets cols;
     MSM_TRY(bucketize(EmitCsrColumns{W->rowptr.p, W->col.p, W->val.p, nv_low}, nv_low, nv_in, cols, s));
     k_bucket_sum<<<(nv_in + 255) / 256, 256, 0, s>>>(nv_in, cols.ptr.p, cols.val.p, correction.p);
-    MSM_CUDA(cudaGetLastError());
+    MSM_LAUNCH_CHECK();
     k_finish_rows<<<gl, 256, 0, s>>>(nv_low, W->rowptr.p, W->col.p, W->val.p, old_area.p, correction.p);
-    MSM_CUDA(cudaGetLastError());
+    MSM_LAUNCH_CHECK();
     W->ctx = ctx;
     W->n_rows = nv_low;
     W->n_cols = nv_in;
@@ -292,7 +292,7 @@ msmgpu_status csr_apply_f32(const msmgpu_weights* W, int D, const float* d_in, f
         const long long slots = (long long)W->n_rows * D;
         k_csr_apply<float><<<(unsigned)((slots + 255) / 256), 256, 0, s>>>(W->n_rows, W->rowptr.p, W->col.p, W->val.p, D, d_in, d_out);
     }
-    MSM_CUDA(cudaGetLastError());
+    MSM_LAUNCH_CHECK();
     return MSMGPU_OK;
 }
 
@@ -300,7 +300,7 @@ msmgpu_status csr_apply_f64(const msmgpu_weights* W, int D, const double* d_in, 
     if (W->n_rows == 0 || D == 0) return MSMGPU_OK;
     const long long slots = (long long)W->n_rows * D;
     k_csr_apply<double><<<(unsigned)((slots + 255) / 256), 256, 0, s>>>(W->n_rows, W->rowptr.p, W->col.p, W->val.p, D, d_in, d_out);
-    MSM_CUDA(cudaGetLastError());
+    MSM_LAUNCH_CHECK();
     return MSMGPU_OK;
 }
 
