@@ -110,6 +110,15 @@ class ClockSampler:
         except Exception:
             self.p = None
 
+    def mark(self):
+        """Only samples taken after this call count (the sampler itself is started before the warm-up, because
+        nvidia-smi's start-up can stall CUDA calls for tens of ms)."""
+        self.f.flush()
+        try:
+            self.skip = len(open(self.f.name).read().splitlines())
+        except Exception:
+            self.skip = 0
+
     def stop(self):
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -120,7 +129,7 @@ class ClockSampler:
         except Exception:
             self.p.kill()
         self.f.flush()
-        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines()[getattr(self, "skip", 0):] if r.strip()]
         os.unlink(self.f.name)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -241,6 +250,7 @@ def run_ours(a):
     d_status = torch.zeros(S, n_low, dtype=torch.int32, device=dev)
     feat_ptrs = (capi.C.c_void_p * S)(*[t.data_ptr() for t in d_feat])
     outb_ptrs = (capi.C.c_void_p * S)(*[t.data_ptr() for t in d_out_b])
+    outa_ptrs = (capi.C.c_void_p * S)(*[t.data_ptr() for t in d_out_a])
     torch.cuda.synchronize()
 
     stage_ms = {"mesh_tables+octree_forest": [], "bary_fused_batch": [], "adaptive_weights": [], "adaptive_apply": []}
@@ -258,14 +268,12 @@ def run_ours(a):
             capi.check(L.msmgpu_bary_resample_batch_f32_dev(ctx.h, S, tree_ptrs, n_low, capi.ptr(d_low_xyz), D, feat_ptrs, outb_ptrs,
                                                            capi.ptr(d_status)))
             if ev: ev[2].record(stream)
-            ws = []
-            for s in range(S):
-                h = capi.C.c_void_p()
-                capi.check(L.msmgpu_adaptive_weights_ex(meshes[s].h, trees[s].h, low.h, low_tree.h, capi.C.byref(h)))
-                ws.append(R.Weights(L, h))
+            mesh_ptrs = (capi.C.c_void_p * S)(*[m.h.value for m in meshes])
+            w_ptrs = (capi.C.c_void_p * S)()
+            capi.check(L.msmgpu_adaptive_weights_batch(ctx.h, S, mesh_ptrs, tree_ptrs, low.h, low_tree.h, w_ptrs))
+            ws = [R.Weights(L, capi.C.c_void_p(w_ptrs[s])) for s in range(S)]
             if ev: ev[3].record(stream)
-            for s in range(S):
-                ws[s].apply_f32_dev(D, d_feat[s], d_out_a[s])
+            capi.check(L.msmgpu_weights_apply_batch_f32_dev(ctx.h, S, w_ptrs, D, feat_ptrs, outa_ptrs))
             if ev: ev[4].record(stream)
             for w in ws: w.close()
             for t in trees: t.close()
@@ -282,12 +290,24 @@ def run_ours(a):
         if world > 1:
             dist.barrier()
 
+    clocks = ClockSampler(local)
     for _ in range(max(a.warmup, 3)):
         device_step()
     sync_all()
+    if os.environ.get("BENCH_DEBUG"):
+        for mode in ("sync each step", "no sync"):
+            ts = []
+            for _ in range(6):
+                t0 = time.perf_counter()
+                device_step()
+                if mode.startswith("sync"):
+                    stream.synchronize()
+                ts.append(1e3 * (time.perf_counter() - t0))
+            stream.synchronize()
+            print(f"[debug] {mode}: host ms per step {[round(t, 1) for t in ts]}", file=sys.stderr, flush=True)
     assert int(d_status.abs().max().item()) == 0, "a nearest-triangle query failed"
     launches0 = L.msmgpu_launch_count()
-    clocks = ClockSampler(local)
+    clocks.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     e0.record(stream)
@@ -322,21 +342,20 @@ def run_ours(a):
         evs[reps].record(stream)
         stream.synchronize()
         k_ms = float(np.mean([evs[i].elapsed_time(evs[i + 1]) for i in range(reps)]))
-        # adaptive apply alone
-        h = capi.C.c_void_p()
-        capi.check(L.msmgpu_adaptive_weights_ex(meshes[0].h, trees[0].h, low.h, trees[-1].h, capi.C.byref(h)))
-        W = R.Weights(L, h)
-        nnz = W.shape()[2]
-        ea = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        for s in range(min(S, 3)):
-            W.apply_f32_dev(D, d_feat[s], d_out_a[s])
-        ea[0].record(stream)
-        for s in range(S):
-            W.apply_f32_dev(D, d_feat[s], d_out_a[s])     # same matrix, different (cold) feature blocks
-        ea[1].record(stream)
+        # adaptive apply alone (one launch for the batch)
+        mesh_ptrs = (capi.C.c_void_p * S)(*[m.h.value for m in meshes])
+        w_ptrs = (capi.C.c_void_p * S)()
+        capi.check(L.msmgpu_adaptive_weights_batch(ctx.h, S, mesh_ptrs, tree_ptrs, low.h, trees[-1].h, w_ptrs))
+        Ws = [R.Weights(L, capi.C.c_void_p(w_ptrs[s])) for s in range(S)]
+        nnz = sum(w.shape()[2] for w in Ws)
+        ea = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+        for i in range(reps + 2):
+            if i >= 2: ea[i - 2].record(stream)
+            capi.check(L.msmgpu_weights_apply_batch_f32_dev(ctx.h, S, w_ptrs, D, feat_ptrs, outa_ptrs))
+        ea[reps].record(stream)
         stream.synchronize()
-        apply_ms = ea[0].elapsed_time(ea[1]) / S
-        W.close()
+        apply_ms = float(np.mean([ea[i].elapsed_time(ea[i + 1]) for i in range(reps)]))
+        for W in Ws: W.close()
         for t_ in trees: t_.close()
         for m in meshes: m.close()
         low.close()
@@ -350,7 +369,7 @@ def run_ours(a):
     # B_bary = 24 N_t + 24 V_s + 12 T_s + 4 D min(3 N_t, V_s) + 4 D N_t  per subject
     bytes_bary = 24 * n_low + 24 * nv + 12 * nt + 4 * D * min(3 * n_low, nv) + 4 * D * n_low
     achieved = S * bytes_bary / (k_ms * 1e-3) / 1e9
-    bytes_apply = 4 * D * nv + 4 * D * n_low + 12 * nnz + 4 * (n_low + 1)
+    bytes_apply = S * (4 * D * nv + 4 * D * n_low + 4 * (n_low + 1)) + 12 * nnz
     roofline = {"kernel": "k_bary_resample_f32 (fused query + weights + 3-row gather, one launch for the batch)", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "launch_ms": k_ms, "algorithmic_bytes_per_launch": S * bytes_bary,

@@ -52,7 +52,7 @@ unsigned long long msmgpu_launch_count(void);
 const char* msmgpu_debug_take_cuda_error(void);
 
 /* Tuning knob with no effect on results: how many lanes cooperate on one nearest-triangle query
- * (1, 2, 4, 8, 16 or 32; default 8 or $MSMGPU_QUERY_GROUP). */
+ * (1, 2, 4, 8, 16 or 32; default 2 or $MSMGPU_QUERY_GROUP). */
 msmgpu_status msmgpu_set_query_group(int lanes);
 int msmgpu_get_query_group(void);
 
@@ -99,6 +99,10 @@ msmgpu_status msmgpu_bary_weights_dev(msmgpu_octree* t, int n, const double* d_p
 msmgpu_status msmgpu_adaptive_weights(msmgpu_mesh* in_mesh, msmgpu_mesh* low_mesh, msmgpu_weights** out);
 /* optional pre-built trees (NULL = build): lets a batch share the target tree */
 msmgpu_status msmgpu_adaptive_weights_ex(msmgpu_mesh* in_mesh, msmgpu_octree* in_tree, msmgpu_mesh* low_mesh, msmgpu_octree* low_tree, msmgpu_weights** out);
+/* batch of n subjects onto one target mesh: one set of kernel launches for all of them. in_trees may be NULL or hold
+ * NULL entries (built here, as one forest), low_tree may be NULL. out[n] share one device store. */
+msmgpu_status msmgpu_adaptive_weights_batch(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* in_meshes, msmgpu_octree* const* in_trees,
+                                            msmgpu_mesh* low_mesh, msmgpu_octree* low_tree, msmgpu_weights** out);
 msmgpu_status msmgpu_weights_shape(msmgpu_weights* w, int* n_rows, int* n_cols, int64_t* nnz);
 msmgpu_status msmgpu_weights_export(msmgpu_weights* w, int32_t* rowptr, int32_t* col, double* val);
 void msmgpu_weights_destroy(msmgpu_weights* w);
@@ -106,6 +110,8 @@ void msmgpu_weights_destroy(msmgpu_weights* w);
 /* replaces: the interpolation loop of Resampler::barycentric_data_interpolation (resampler.cpp:40-52).
  * d_in: [n_cols][D] float rows, d_out: [n_rows][D] float rows (vertex-major). */
 msmgpu_status msmgpu_weights_apply_f32_dev(msmgpu_weights* w, int D, const float* d_in, float* d_out);
+/* one launch for the n matrices of one msmgpu_adaptive_weights_batch call: d_in[i] / d_out[i] row pointers per subject */
+msmgpu_status msmgpu_weights_apply_batch_f32_dev(msmgpu_ctx* ctx, int n, msmgpu_weights* const* ws, int D, const float* const* d_in, float* const* d_out);
 
 /* replaces: metric_resample(in, low) (resampler.cpp:304): adaptive-barycentric resampling of D channels.
  * Host buffers, channel-major: feat_in [D][nv_in] double, feat_out [D][nv_low] double. */

@@ -60,6 +60,8 @@ _SIGNATURES = {
     "msmgpu_bary_weights_dev": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "msmgpu_adaptive_weights": (_i, [_vp, _vp, _pp]),
     "msmgpu_adaptive_weights_ex": (_i, [_vp, _vp, _vp, _vp, _pp]),
+    "msmgpu_adaptive_weights_batch": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "msmgpu_weights_apply_batch_f32_dev": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
     "msmgpu_weights_shape": (_i, [_vp, _vp, _vp, _vp]),
     "msmgpu_weights_export": (_i, [_vp, _vp, _vp, _vp]),
     "msmgpu_weights_destroy": (None, [_vp]),

@@ -78,6 +78,7 @@ struct TreeView {
     const int4* nodes;
     const int* pairs;
     const TriRec* rec;  // [nt] per-triangle query records (geom.cuh)
+    const double* cull; // [nt][4] conservative bounding spheres (geom.cuh make_cull)
     const int* tri;     // [nt][3]
     int root;
 };
@@ -97,6 +98,7 @@ struct msmgpu_mesh {
     msm::DevBuf<int> tri;      // [nt][3]
     msm::DevBuf<msm::TriRec> rec; // [nt] one 128-byte query record per triangle (gather-free leaf scans)
     msm::DevBuf<double> aabb;  // [nt][6] lo xyz, hi xyz (octree.cpp:46-59)
+    msm::DevBuf<double> cull;  // [nt][4] centre + r^2 of the conservative cull sphere
 };
 
 struct msmgpu_octree {
@@ -105,17 +107,24 @@ struct msmgpu_octree {
     int root = 0;
     msmgpu_mesh* mesh = nullptr;
     msm::TreeView view() const {
-        return msm::TreeView{forest->nodes.p, forest->pairs.p, mesh->rec.p, mesh->tri.p, root};
+        return msm::TreeView{forest->nodes.p, forest->pairs.p, mesh->rec.p, mesh->cull.p, mesh->tri.p, root};
     }
+};
+
+// CSR storage shared by the weight matrices of one batch (one allocation, one set of launches)
+struct WeightsStore {
+    msm::DevBuf<int> rowptr;   // [batch * n_rows + 1], offsets into col / val
+    msm::DevBuf<int> col;      // column = source vertex id, local to its subject
+    msm::DevBuf<double> val;
 };
 
 struct msmgpu_weights {
     msmgpu_ctx* ctx = nullptr;
     int n_rows = 0, n_cols = 0;
     int64_t nnz = 0;
-    msm::DevBuf<int> rowptr;
-    msm::DevBuf<int> col;
-    msm::DevBuf<double> val;
+    std::shared_ptr<WeightsStore> store;
+    const int* rowptr = nullptr;   // n_rows + 1 entries (absolute offsets into store->col / val)
+    int first = 0;                 // rowptr[0], cached on the host
 };
 
 namespace msm {
@@ -129,6 +138,14 @@ msmgpu_status launch_nearest(const TreeView& t, int n, const double* d_pts, int*
 msmgpu_status launch_bary_weights(const TreeView& t, int n, const double* d_pts, int* d_idx, double* d_w, int* d_ne, int* d_status, cudaStream_t s);
 msmgpu_status launch_blend_coords(const TreeView& t, int n, const double* d_pts, const double* d_payload_xyz, double* d_out, int reproject, int* d_status, cudaStream_t s);
 msmgpu_status launch_gather_channels_f64(int n, int nv, int D, const int* d_vtx, const double* d_in, double* d_out, cudaStream_t s);
+
+struct QueryJob {         // one subject of a batched barycentric-weights launch
+    TreeView tree;
+    const double* pts;      // [n][3]
+    int n;
+    int out_off;            // first output slot of this job in the concatenated outputs
+};
+msmgpu_status launch_bary_weights_batch(const QueryJob* d_jobs, int n_jobs, int max_n, int* d_idx, double* d_w, int* d_ne, int* d_status, cudaStream_t s);
 
 struct ResampleJob {      // one subject of a batched fused resample
     TreeView tree;

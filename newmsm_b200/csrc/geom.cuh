@@ -191,4 +191,54 @@ __device__ __forceinline__ double rec_distance(const V3& pt, const TriRec* __res
     return rec_boundary_distance(mP, v1, v2, v3, g.y, h.x, h.y);
 }
 
+// ------------------------------------------------------------------------------------------
+// Conservative cull record per triangle: a sphere (C, r) that contains every point the reference's
+// point_in_triangle (point.cpp:36-44) can accept for this triangle, so a query whose line
+// {t * pt} misses the sphere can skip the triangle without evaluating it -- the skipped test would
+// have returned NOT_IN_TRIANGLE, hence no decision changes.
+//
+// same_side accepts p iff  dot(cross(e, p - P), n2) > -1e-8  with n2 = cross(e, O - P) normal to the
+// plane; the left side equals |e| |n2| h, h = signed in-plane distance of p from the edge line
+// (positive towards the opposite corner O). The accepted set is therefore the prism over the
+// triangle grown by h_k = 1e-8 / (|e_k| |n2_k|) across each edge. The grown triangle lies inside the
+// triangle scaled about its incentre I by (rho + h) / rho (rho = inradius, h = max h_k), and the
+// projected query lies in the plane up to rounding, so r = lambda * max |V_i - I| (inflated for the
+// rounding of the reference's own evaluation and of the cull test) bounds it. Degenerate
+// triangles (n2 = 0, accepted everywhere) get r = +inf and are never culled.
+// ------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ void make_cull(const V3& a, const V3& b, const V3& c, double* out4) {
+    const double la = vnorm(vsub(b, c)), lb = vnorm(vsub(c, a)), lc = vnorm(vsub(a, b));
+    const double per = la + lb + lc;
+    const double n2a = vnorm(vcross(vsub(c, b), vsub(a, b)));   // side (b,c), opposite a
+    const double n2b = vnorm(vcross(vsub(a, c), vsub(b, c)));   // side (c,a), opposite b
+    const double n2c = vnorm(vcross(vsub(b, a), vsub(c, a)));   // side (a,b), opposite c
+    const double lmax = fmax(la, fmax(lb, lc));
+    const double inf = 1.0 / 0.0;
+    double r2 = inf;
+    V3 I{0, 0, 0};
+    const double pa = la * n2a, pb = lb * n2b, pc = lc * n2c;
+    if (per > 0 && pa > 0 && pb > 0 && pc > 0) {
+        I = V3{(la * a.x + lb * b.x + lc * c.x) / per, (la * a.y + lb * b.y + lc * c.y) / per, (la * a.z + lb * b.z + lc * c.z) / per};
+        const double rho = n2c / per;                            // 2 * area / perimeter
+        const double h = (1e-8 / fmin(pa, fmin(pb, pc)) + 1e-12 * (1.0 + lmax)) * 1.000001;
+        const double lambda = 1.0 + h / rho;
+        const double reach = fmax(vnorm(vsub(a, I)), fmax(vnorm(vsub(b, I)), vnorm(vsub(c, I))));
+        const double r = lambda * reach * (1.0 + 1e-7) + 1e-7;
+        r2 = r * r;
+        if (!(r2 == r2)) r2 = inf;                               // NaN from 0/0 -> never cull
+    }
+    out4[0] = I.x; out4[1] = I.y; out4[2] = I.z; out4[3] = r2;
+}
+
+// keep the triangle iff the line through the origin and pt may touch the sphere:  |C x pt|^2 <= r^2 |pt|^2
+__device__ __forceinline__ bool cull_keep(const double* __restrict__ cull4, const V3& pt, double pp) {
+    const double2 c01 = __ldg(reinterpret_cast<const double2*>(cull4));
+    const double2 c23 = __ldg(reinterpret_cast<const double2*>(cull4) + 1);
+    const double x = __fma_rn(c01.y, pt.z, -(c23.x * pt.y));
+    const double y = __fma_rn(c23.x, pt.x, -(c01.x * pt.z));
+    const double z = __fma_rn(c01.x, pt.y, -(c01.y * pt.x));
+    const double d2 = __fma_rn(x, x, __fma_rn(y, y, z * z));
+    return !(d2 > c23.y * pp);     // written so that NaN keeps the triangle
+}
+
 } // namespace msm

@@ -116,7 +116,7 @@ msmgpu_status exclusive_scan_i32(const int* d_in, int* d_out, int n, int* d_tota
 // per-triangle tables
 // ------------------------------------------------------------------------------------------
 __global__ void k_mesh_tables(int nt, const double* __restrict__ xyz, const int* __restrict__ tri,
-                              TriRec* __restrict__ rec, double* __restrict__ aabb) {
+                              TriRec* __restrict__ rec, double* __restrict__ aabb, double* __restrict__ cull) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nt) return;
     double lo[3], hi[3], cv[9];
@@ -139,11 +139,15 @@ __global__ void k_mesh_tables(int nt, const double* __restrict__ xyz, const int*
     TriRec r;
     make_trirec(V3{cv[0], cv[1], cv[2]}, V3{cv[3], cv[4], cv[5]}, V3{cv[6], cv[7], cv[8]}, r);
     rec[t] = r;
+    double c4[4];
+    make_cull(V3{cv[0], cv[1], cv[2]}, V3{cv[3], cv[4], cv[5]}, V3{cv[6], cv[7], cv[8]}, c4);
+    reinterpret_cast<double2*>(cull)[2 * (size_t)t] = make_double2(c4[0], c4[1]);
+    reinterpret_cast<double2*>(cull)[2 * (size_t)t + 1] = make_double2(c4[2], c4[3]);
 }
 
 msmgpu_status mesh_refresh_tables(msmgpu_mesh* m) {
     if (m->nt == 0) return MSMGPU_OK;
-    k_mesh_tables<<<(m->nt + 255) / 256, 256, 0, m->ctx->stream>>>(m->nt, m->xyz.p, m->tri.p, m->rec.p, m->aabb.p);
+    k_mesh_tables<<<(m->nt + 255) / 256, 256, 0, m->ctx->stream>>>(m->nt, m->xyz.p, m->tri.p, m->rec.p, m->aabb.p, m->cull.p);
     MSM_LAUNCH_CHECK();
     return MSMGPU_OK;
 }

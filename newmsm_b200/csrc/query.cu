@@ -70,6 +70,30 @@ __global__ void __launch_bounds__(256) k_bary_weights(TreeView T, int n, const d
     if (out_status) out_status[q] = st;
 }
 
+// the same for a batch of jobs (blockIdx.y = job): different trees and/or different point sets, outputs concatenated
+template <int G>
+__global__ void __launch_bounds__(256) k_bary_weights_batch(const QueryJob* __restrict__ jobs, int* __restrict__ out_idx, double* __restrict__ out_w,
+                                                            int* __restrict__ out_ne, int* __restrict__ out_status) {
+    const QueryJob job = jobs[blockIdx.y];
+    const int gl = threadIdx.x % G;
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    if ((blockIdx.x * blockDim.x) / G >= job.n) return;     // whole CTA beyond this job's points
+    const bool active = q < job.n;
+    const V3 pt = active ? load_pt(job.pts, q) : V3{0, 0, 0};
+    int st;
+    const int t = nearest_triangle<G>(job.tree, pt, active, gl, st);
+    if (!active || gl != 0) return;
+    int idx[3] = {-1, -1, -1};
+    double w[3] = {0, 0, 0};
+    int ne = 0;
+    if (t >= 0) ne = sorted_weights(job.tree, t, pt, idx, w);
+    const size_t o = (size_t)job.out_off + q;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { out_idx[3 * o + j] = idx[j]; out_w[3 * o + j] = w[j]; }
+    out_ne[o] = ne;
+    out_status[o] = st;
+}
+
 // sphere_project_warp (resampler.cpp:311-328, reproject = 1) / surface_resample (284-302, reproject = 0):
 // newPt = sum over the weight map (ascending id) of payload[id] * w, optionally normalised * 100.
 template <int G>
@@ -193,8 +217,8 @@ static bool valid_group(int v) { return v == 1 || v == 2 || v == 4 || v == 8 || 
 int query_group_width() {
     if (g_query_group == 0) {
         const char* e = getenv("MSMGPU_QUERY_GROUP");
-        const int v = e ? atoi(e) : 8;
-        g_query_group = valid_group(v) ? v : 8;
+        const int v = e ? atoi(e) : 2;
+        g_query_group = valid_group(v) ? v : 2;
     }
     return g_query_group;
 }
@@ -223,6 +247,14 @@ msmgpu_status launch_bary_weights(const TreeView& t, int n, const double* d_pts,
     if (n <= 0) return MSMGPU_OK;
     const int g = query_group_width();
     MSM_DISPATCH_G(g, (k_bary_weights<G><<<query_blocks(n, G), 256, 0, s>>>(t, n, d_pts, d_idx, d_w, d_ne, d_status)));
+    MSM_LAUNCH_CHECK();
+    return MSMGPU_OK;
+}
+
+msmgpu_status launch_bary_weights_batch(const QueryJob* d_jobs, int n_jobs, int max_n, int* d_idx, double* d_w, int* d_ne, int* d_status, cudaStream_t s) {
+    if (n_jobs <= 0 || max_n <= 0) return MSMGPU_OK;
+    const int g = query_group_width();
+    MSM_DISPATCH_G(g, (k_bary_weights_batch<G><<<dim3(query_blocks(max_n, G), (unsigned)n_jobs), 256, 0, s>>>(d_jobs, d_idx, d_w, d_ne, d_status)));
     MSM_LAUNCH_CHECK();
     return MSMGPU_OK;
 }

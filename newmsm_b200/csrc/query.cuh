@@ -49,8 +49,32 @@ __device__ __forceinline__ int nearest_triangle(const TreeView& T, const V3& pt,
             nd = __ldg(T.nodes + nd.x + c);
         }
         parent = nd.w;
-        for (int i = gl; i < nd.z; i += G) {   // octree.cpp:172-178
-            const int t = __ldg(T.pairs + nd.y + i);
+        // octree.cpp:172-178, in two phases so that the expensive test runs on few, well-packed lanes:
+        // (1) cull: one 32-byte sphere test per candidate, survivors recorded in a bit mask
+        //     (bit j = this lane's j-th candidate, i = gl + j*G);
+        // (2) the reference's full test (projection, 3 same-side tests, boundary distance) for survivors, in
+        //     ascending scan position, so "first strictly smaller distance wins" is preserved.
+        const double pp = vdot(pt, pt);
+        const int* __restrict__ list = T.pairs + nd.y;
+        unsigned long long keep = 0ull;
+        const int mine = (nd.z - gl + G - 1) / G;             // candidates owned by this lane (may be <= 0)
+        const int fast = mine < 64 ? mine : 64;
+        for (int j = 0; j < fast; ++j) {
+            const int t = __ldg(list + gl + j * G);
+            if (cull_keep(T.cull + 4 * (size_t)t, pt, pp)) keep |= 1ull << j;
+        }
+        while (keep) {
+            const int j = __ffsll((long long)keep) - 1;
+            keep &= keep - 1;
+            const int i = gl + j * G;
+            const int t = __ldg(list + i);
+            const double d = rec_distance(pt, T.rec + t);
+            if (d > kNotInTriangle && d < best_d) { best_d = d; best_pos = i; best_t = t; }
+        }
+        for (int j = 64; j < mine; ++j) {                     // oversized leaves (split refused, octree.cpp:102): no mask
+            const int i = gl + j * G;
+            const int t = __ldg(list + i);
+            if (!cull_keep(T.cull + 4 * (size_t)t, pt, pp)) continue;
             const double d = rec_distance(pt, T.rec + t);
             if (d > kNotInTriangle && d < best_d) { best_d = d; best_pos = i; best_t = t; }
         }
@@ -67,6 +91,7 @@ __device__ __forceinline__ int nearest_triangle(const TreeView& T, const V3& pt,
                 const int4 ch = __ldg(T.nodes + first_child + c);
                 for (int i = gl; i < ch.z; i += G) {
                     const int t = __ldg(T.pairs + ch.y + i);
+                    if (!cull_keep(T.cull + 4 * (size_t)t, pt, vdot(pt, pt))) continue;
                     const double d = rec_distance(pt, T.rec + t);
                     if (d > kNotInTriangle && d < best_d) { best_d = d; best_pos = base + i; best_t = t; }
                 }

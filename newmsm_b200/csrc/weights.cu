@@ -11,6 +11,9 @@
 // single-threaded reference (whose own OpenMP version races on `correction`).
 #include "common.cuh"
 
+#include <algorithm>
+#include <type_traits>
+
 namespace msm {
 
 // ------------------------------------------------------------------------------------------
@@ -23,31 +26,45 @@ struct Buckets {
     int total = 0;
 };
 
-// emitters: n_src() sources, each emitting count(i) triples (key, id, val)
+// segment s with off[s] <= i < off[s+1]  (off has n_seg + 1 entries)
+__device__ __forceinline__ int find_segment(const int* __restrict__ off, int n_seg, int i) {
+    int lo = 0, hi = n_seg;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(off + mid) <= i) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// Emitters: n_src() sources, each emitting count(i) triples (key, id, val). All of them cover a BATCH of
+// subjects: vertex keys of subject s are shifted by in_off[s], target keys by s * n_low.
 struct EmitVertexTriangles {   // key = vertex, id = triangle, val = cached triangle area (triangle.cpp:47-50)
-    const int* tri; const TriRec* rec; int nt;
-    __device__ int n_src() const { return nt; }
+    const int* const* tri; const TriRec* const* rec; const int* tri_off; const int* key_off; int S; int total;
+    __device__ int n_src() const { return total; }
     __device__ int count(int) const { return 3; }
-    __device__ int key(int t, int j) const { return tri[3 * (size_t)t + j]; }
-    __device__ int id(int t, int) const { return t; }
-    __device__ double val(int t, int) const {
-        const double* v = rec[t].v;
+    __device__ int seg(int i) const { return S == 1 ? 0 : find_segment(tri_off, S, i); }
+    __device__ int key(int i, int j) const { const int s = seg(i); return key_off[s] + tri[s][3 * (size_t)(i - tri_off[s]) + j]; }
+    __device__ int id(int i, int) const { return i - tri_off[seg(i)]; }
+    __device__ double val(int i, int) const {
+        const int s = seg(i);
+        const double* v = rec[s][i - tri_off[s]].v;
         return tri_area_cached(V3{v[0], v[1], v[2]}, V3{v[3], v[4], v[5]}, V3{v[6], v[7], v[8]});
     }
 };
 struct EmitReverse {   // resampler.cpp:91-95: reverse_reorder[target][source] = weight
-    const int* ridx; const double* rw; const int* rne; int n;
-    __device__ int n_src() const { return n; }
+    const int* ridx; const double* rw; const int* rne; const int* in_off; int S; int n_low; int total;
+    __device__ int n_src() const { return total; }
     __device__ int count(int o) const { return rne[o]; }
-    __device__ int key(int o, int j) const { return ridx[3 * (size_t)o + j]; }
-    __device__ int id(int o, int) const { return o; }
+    __device__ int seg(int o) const { return S == 1 ? 0 : find_segment(in_off, S, o); }
+    __device__ int key(int o, int j) const { return seg(o) * n_low + ridx[3 * (size_t)o + j]; }
+    __device__ int id(int o, int) const { return o - in_off[seg(o)]; }
     __device__ double val(int o, int j) const { return rw[3 * (size_t)o + j]; }
 };
 struct EmitCsrColumns {   // key = column (source vertex), id = row (target), val = stored value
-    const int* rowptr; const int* col; const double* v; int n_rows;
-    __device__ int n_src() const { return n_rows; }
+    const int* rowptr; const int* col; const double* v; const int* in_off; int n_low; int total;
+    __device__ int n_src() const { return total; }
     __device__ int count(int r) const { return rowptr[r + 1] - rowptr[r]; }
-    __device__ int key(int r, int j) const { return col[rowptr[r] + j]; }
+    __device__ int key(int r, int j) const { return in_off[r / n_low] + col[rowptr[r] + j]; }
     __device__ int id(int r, int) const { return r; }
     __device__ double val(int r, int j) const { return v[rowptr[r] + j]; }
 };
@@ -86,30 +103,29 @@ __global__ void k_bucket_sort(int nkeys, const int* __restrict__ ptr, int* __res
     }
 }
 
+// `capacity` >= the number of triples that will be emitted (an upper bound avoids a host round trip)
 template <class E>
-static msmgpu_status bucketize(const E& e, int n_src, int nkeys, Buckets& B, cudaStream_t s) {
-    DevBuf<int> cnt, cursor, d_total;
+static msmgpu_status bucketize(const E& e, int n_src, int nkeys, size_t capacity, Buckets& B, cudaStream_t s) {
+    DevBuf<int> cnt, cursor;
     MSM_CUDA(cnt.alloc(nkeys, s));
     MSM_CUDA(cursor.alloc(nkeys, s));
-    MSM_CUDA(d_total.alloc(1, s));
     MSM_CUDA(B.ptr.alloc((size_t)nkeys + 1, s));
+    MSM_CUDA(B.id.alloc(capacity, s));
+    MSM_CUDA(B.val.alloc(capacity, s));
     MSM_CUDA(cudaMemsetAsync(cnt.p, 0, nkeys * sizeof(int), s));
     MSM_CUDA(cudaMemsetAsync(cursor.p, 0, nkeys * sizeof(int), s));
-    const unsigned gs = (unsigned)((n_src + 255) / 256), gk = (unsigned)((nkeys + 255) / 256);
-    if (n_src > 0) k_bucket_count<E><<<gs, 256, 0, s>>>(e, cnt.p);
-    MSM_LAUNCH_CHECK();
-    MSM_TRY(exclusive_scan_i32(cnt.p, B.ptr.p, nkeys, d_total.p, s));
-    MSM_CUDA(cudaMemcpyAsync(B.ptr.p + nkeys, d_total.p, sizeof(int), cudaMemcpyDeviceToDevice, s));
-    MSM_CUDA(cudaMemcpyAsync(&B.total, d_total.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-    MSM_CUDA(cudaStreamSynchronize(s));
-    MSM_CUDA(B.id.alloc((size_t)B.total, s));
-    MSM_CUDA(B.val.alloc((size_t)B.total, s));
-    if (B.total > 0) {
-        k_bucket_fill<E><<<gs, 256, 0, s>>>(e, B.ptr.p, cursor.p, B.id.p, B.val.p);
-        MSM_LAUNCH_CHECK();
-        k_bucket_sort<<<gk, 256, 0, s>>>(nkeys, B.ptr.p, B.id.p, B.val.p);
-        MSM_LAUNCH_CHECK();
+    if (n_src <= 0 || nkeys <= 0) {
+        MSM_CUDA(cudaMemsetAsync(B.ptr.p, 0, ((size_t)nkeys + 1) * sizeof(int), s));
+        return MSMGPU_OK;
     }
+    const unsigned gs = (unsigned)((n_src + 255) / 256), gk = (unsigned)((nkeys + 255) / 256);
+    k_bucket_count<E><<<gs, 256, 0, s>>>(e, cnt.p);
+    MSM_LAUNCH_CHECK();
+    MSM_TRY(exclusive_scan_i32(cnt.p, B.ptr.p, nkeys, B.ptr.p + nkeys, s));
+    k_bucket_fill<E><<<gs, 256, 0, s>>>(e, B.ptr.p, cursor.p, B.id.p, B.val.p);
+    MSM_LAUNCH_CHECK();
+    k_bucket_sort<<<gk, 256, 0, s>>>(nkeys, B.ptr.p, B.id.p, B.val.p);
+    MSM_LAUNCH_CHECK();
     return MSMGPU_OK;
 }
 
@@ -133,34 +149,59 @@ __global__ void k_bucket_sum(int nkeys, const int* __restrict__ ptr, const doubl
     out[k] = sum;
 }
 
-msmgpu_status vertex_areas_dev(msmgpu_mesh* m, double* d_out) {
-    cudaStream_t s = m->ctx->stream;
+// vertex areas of a batch of meshes, concatenated: d_out[key_off[s] + v]
+static msmgpu_status vertex_areas_batch(msmgpu_ctx* ctx, int S, msmgpu_mesh* const* meshes, const std::vector<int>& key_off, double* d_out) {
+    cudaStream_t s = ctx->stream;
+    std::vector<const int*> h_tri(S);
+    std::vector<const TriRec*> h_rec(S);
+    std::vector<int> h_toff(S + 1, 0);
+    for (int i = 0; i < S; ++i) {
+        h_tri[i] = meshes[i]->tri.p;
+        h_rec[i] = meshes[i]->rec.p;
+        h_toff[i + 1] = h_toff[i] + meshes[i]->nt;
+    }
+    DevBuf<const int*> d_tri;
+    DevBuf<const TriRec*> d_rec;
+    DevBuf<int> d_toff, d_koff;
+    MSM_CUDA(d_tri.alloc(S, s));
+    MSM_CUDA(d_rec.alloc(S, s));
+    MSM_CUDA(d_toff.alloc(S + 1, s));
+    MSM_CUDA(d_koff.alloc(S + 1, s));
+    MSM_CUDA(cudaMemcpyAsync(d_tri.p, h_tri.data(), S * sizeof(int*), cudaMemcpyHostToDevice, s));
+    MSM_CUDA(cudaMemcpyAsync(d_rec.p, h_rec.data(), S * sizeof(TriRec*), cudaMemcpyHostToDevice, s));
+    MSM_CUDA(cudaMemcpyAsync(d_toff.p, h_toff.data(), (S + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
+    MSM_CUDA(cudaMemcpyAsync(d_koff.p, key_off.data(), (S + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
+    const int total_t = h_toff[S], nkeys = key_off[S];
     Buckets B;
-    MSM_TRY(bucketize(EmitVertexTriangles{m->tri.p, m->rec.p, m->nt}, m->nt, m->nv, B, s));
-    k_bucket_mean<<<(m->nv + 255) / 256, 256, 0, s>>>(m->nv, B.ptr.p, B.val.p, d_out);
+    MSM_TRY(bucketize(EmitVertexTriangles{d_tri.p, d_rec.p, d_toff.p, d_koff.p, S, total_t}, total_t, nkeys, 3 * (size_t)total_t, B, s));
+    k_bucket_mean<<<(nkeys + 255) / 256, 256, 0, s>>>(nkeys, B.ptr.p, B.val.p, d_out);
     MSM_LAUNCH_CHECK();
-    return MSMGPU_OK;
+    return MSMGPU_OK;   // (pageable H2D copies are staged before cudaMemcpyAsync returns, the host tables may go)
+}
+
+msmgpu_status vertex_areas_dev(msmgpu_mesh* m, double* d_out) {
+    return vertex_areas_batch(m->ctx, 1, &m, std::vector<int>{0, m->nv}, d_out);
 }
 
 // ------------------------------------------------------------------------------------------
-// adaptive weights
+// adaptive weights (batched over subjects; rows are global: r = s * n_low + target)
 // ------------------------------------------------------------------------------------------
 // resampler.cpp:105-109: keep the forward list unless the transposed reverse list has MORE entries
-__global__ void k_row_lengths(int n_low, const int* __restrict__ fne, const int* __restrict__ rr_ptr, int* __restrict__ len) {
+__global__ void k_row_lengths(int n_rows, const int* __restrict__ fne, const int* __restrict__ rr_ptr, int* __restrict__ len) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= n_low) return;
+    if (n >= n_rows) return;
     const int r = rr_ptr[n + 1] - rr_ptr[n];
     len[n] = r <= fne[n] ? fne[n] : r;
 }
 // rows in ascending column order, multiplied by the target vertex area (resampler.cpp:111-113)
-__global__ void k_fill_rows(int n_low, const int* __restrict__ rowptr, const int* __restrict__ fidx, const double* __restrict__ fw,
+__global__ void k_fill_rows(int n_rows, int n_low, const int* __restrict__ rowptr, const int* __restrict__ fidx, const double* __restrict__ fw,
                             const int* __restrict__ fne, const int* __restrict__ rr_ptr, const int* __restrict__ rr_id,
                             const double* __restrict__ rr_val, const double* __restrict__ new_area, int* __restrict__ col, double* __restrict__ val) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= n_low) return;
+    if (n >= n_rows) return;
     const int rb = rr_ptr[n], r = rr_ptr[n + 1] - rb;
     const int o = rowptr[n];
-    const double a = new_area[n];
+    const double a = new_area[n % n_low];
     if (r <= fne[n]) {
         for (int j = 0; j < fne[n]; ++j) { col[o + j] = fidx[3 * (size_t)n + j]; val[o + j] = fw[3 * (size_t)n + j] * a; }
     } else {
@@ -168,14 +209,15 @@ __global__ void k_fill_rows(int n_low, const int* __restrict__ rowptr, const int
     }
 }
 // resampler.cpp:120-137: w *= oldArea[src] / correction[src]; then each row normalised to sum 1
-__global__ void k_finish_rows(int n_low, const int* __restrict__ rowptr, const int* __restrict__ col, double* __restrict__ val,
-                              const double* __restrict__ old_area, const double* __restrict__ correction) {
+__global__ void k_finish_rows(int n_rows, int n_low, const int* __restrict__ rowptr, const int* __restrict__ col, double* __restrict__ val,
+                              const int* __restrict__ in_off, const double* __restrict__ old_area, const double* __restrict__ correction) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= n_low) return;
+    if (n >= n_rows) return;
     const int b = rowptr[n], e = rowptr[n + 1];
+    const int koff = in_off[n / n_low];
     double ws = 0.0;
     for (int i = b; i < e; ++i) {
-        const int c = col[i];
+        const int c = koff + col[i];
         const double v = val[i] * (old_area[c] / correction[c]);
         val[i] = v;
         ws += v;
@@ -184,65 +226,96 @@ __global__ void k_finish_rows(int n_low, const int* __restrict__ rowptr, const i
         for (int i = b; i < e; ++i) val[i] /= ws;
 }
 
-msmgpu_status adaptive_weights_build(msmgpu_mesh* in_mesh, msmgpu_octree* in_tree, msmgpu_mesh* low_mesh, msmgpu_octree* low_tree,
-                                     msmgpu_weights* W) {
-    msmgpu_ctx* ctx = in_mesh->ctx;
+// Builds the S matrices into one shared store; out[s] become views of it.
+msmgpu_status adaptive_weights_build_batch(msmgpu_ctx* ctx, int S, msmgpu_mesh* const* in_meshes, msmgpu_octree* const* in_trees,
+                                           msmgpu_mesh* low_mesh, msmgpu_octree* low_tree, msmgpu_weights** out) {
     cudaStream_t s = ctx->stream;
-    const int nv_in = in_mesh->nv, nv_low = low_mesh->nv;
-    // forward: targets located in the input mesh; reverse: input vertices located in the target mesh (resampler.cpp:74-78)
+    const int n_low = low_mesh->nv;
+    std::vector<int> in_off(S + 1, 0);
+    int max_nv = 0;
+    for (int i = 0; i < S; ++i) {
+        in_off[i + 1] = in_off[i] + in_meshes[i]->nv;
+        max_nv = std::max(max_nv, in_meshes[i]->nv);
+    }
+    const long long NV = in_off[S], NL = (long long)S * n_low;
+    if (3 * (NV + NL) > 0x7fffffffll) return fail(MSMGPU_ERR_CAPACITY, "adaptive_weights: batch too large for 32-bit offsets");
+
+    // forward: targets located in each input mesh; reverse: input vertices located in the target mesh (resampler.cpp:74-78)
+    std::vector<QueryJob> jobs(2 * (size_t)S);
+    for (int i = 0; i < S; ++i) {
+        jobs[i] = QueryJob{in_trees[i]->view(), low_mesh->xyz.p, n_low, i * n_low};
+        jobs[S + i] = QueryJob{low_tree->view(), in_meshes[i]->xyz.p, in_meshes[i]->nv, in_off[i]};
+    }
+    DevBuf<QueryJob> d_jobs;
+    DevBuf<int> d_in_off;
+    MSM_CUDA(d_jobs.alloc(jobs.size(), s));
+    MSM_CUDA(d_in_off.alloc(S + 1, s));
+    MSM_CUDA(cudaMemcpyAsync(d_jobs.p, jobs.data(), jobs.size() * sizeof(QueryJob), cudaMemcpyHostToDevice, s));
+    MSM_CUDA(cudaMemcpyAsync(d_in_off.p, in_off.data(), (S + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
     DevBuf<int> fidx, fne, ridx, rne, st;
     DevBuf<double> fw, rw;
-    MSM_CUDA(fidx.alloc(3 * (size_t)nv_low, s));
-    MSM_CUDA(fw.alloc(3 * (size_t)nv_low, s));
-    MSM_CUDA(fne.alloc(nv_low, s));
-    MSM_CUDA(ridx.alloc(3 * (size_t)nv_in, s));
-    MSM_CUDA(rw.alloc(3 * (size_t)nv_in, s));
-    MSM_CUDA(rne.alloc(nv_in, s));
-    MSM_CUDA(st.alloc((size_t)nv_low + nv_in, s));
-    MSM_TRY(launch_bary_weights(in_tree->view(), nv_low, low_mesh->xyz.p, fidx.p, fw.p, fne.p, st.p, s));
-    MSM_TRY(launch_bary_weights(low_tree->view(), nv_in, in_mesh->xyz.p, ridx.p, rw.p, rne.p, st.p + nv_low, s));
+    MSM_CUDA(fidx.alloc(3 * (size_t)NL, s));
+    MSM_CUDA(fw.alloc(3 * (size_t)NL, s));
+    MSM_CUDA(fne.alloc((size_t)NL, s));
+    MSM_CUDA(ridx.alloc(3 * (size_t)NV, s));
+    MSM_CUDA(rw.alloc(3 * (size_t)NV, s));
+    MSM_CUDA(rne.alloc((size_t)NV, s));
+    MSM_CUDA(st.alloc((size_t)(NL + NV), s));
+    MSM_TRY(launch_bary_weights_batch(d_jobs.p, S, n_low, fidx.p, fw.p, fne.p, st.p, s));
+    MSM_TRY(launch_bary_weights_batch(d_jobs.p + S, S, max_nv, ridx.p, rw.p, rne.p, st.p + NL, s));
     int code = 0;
-    MSM_TRY(first_error(st.p, (size_t)nv_low + nv_in, s, &code));
+    MSM_TRY(first_error(st.p, (size_t)(NL + NV), s, &code));   // synchronises: `jobs` / `in_off` may now go
     if (code) return status_to_error(code);
 
     DevBuf<double> new_area, old_area, correction;
-    MSM_CUDA(new_area.alloc(nv_low, s));
-    MSM_CUDA(old_area.alloc(nv_in, s));
-    MSM_CUDA(correction.alloc(nv_in, s));
+    MSM_CUDA(new_area.alloc(n_low, s));
+    MSM_CUDA(old_area.alloc((size_t)NV, s));
+    MSM_CUDA(correction.alloc((size_t)NV, s));
     MSM_TRY(vertex_areas_dev(low_mesh, new_area.p));
-    MSM_TRY(vertex_areas_dev(in_mesh, old_area.p));
+    MSM_TRY(vertex_areas_batch(ctx, S, in_meshes, in_off, old_area.p));
 
-    Buckets rr;   // reverse weights regrouped by target
-    MSM_TRY(bucketize(EmitReverse{ridx.p, rw.p, rne.p, nv_in}, nv_in, nv_low, rr, s));
+    Buckets rr;   // reverse weights regrouped by (subject, target)
+    MSM_TRY(bucketize(EmitReverse{ridx.p, rw.p, rne.p, d_in_off.p, S, n_low, (int)NV}, (int)NV, (int)NL, 3 * (size_t)NV, rr, s));
 
-    DevBuf<int> len, d_nnz;
-    MSM_CUDA(len.alloc(nv_low, s));
-    MSM_CUDA(d_nnz.alloc(1, s));
-    MSM_CUDA(W->rowptr.alloc((size_t)nv_low + 1, s));
-    const unsigned gl = (unsigned)((nv_low + 255) / 256);
-    k_row_lengths<<<gl, 256, 0, s>>>(nv_low, fne.p, rr.ptr.p, len.p);
+    auto store = std::make_shared<WeightsStore>();
+    DevBuf<int> len;
+    MSM_CUDA(len.alloc((size_t)NL, s));
+    MSM_CUDA(store->rowptr.alloc((size_t)NL + 1, s));
+    const unsigned gl = (unsigned)((NL + 255) / 256);
+    k_row_lengths<<<gl, 256, 0, s>>>((int)NL, fne.p, rr.ptr.p, len.p);
     MSM_LAUNCH_CHECK();
-    MSM_TRY(exclusive_scan_i32(len.p, W->rowptr.p, nv_low, d_nnz.p, s));
-    MSM_CUDA(cudaMemcpyAsync(W->rowptr.p + nv_low, d_nnz.p, sizeof(int), cudaMemcpyDeviceToDevice, s));
-    int nnz = 0;
-    MSM_CUDA(cudaMemcpyAsync(&nnz, d_nnz.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-    MSM_CUDA(cudaStreamSynchronize(s));
-    MSM_CUDA(W->col.alloc((size_t)nnz, s));
-    MSM_CUDA(W->val.alloc((size_t)nnz, s));
-    k_fill_rows<<<gl, 256, 0, s>>>(nv_low, W->rowptr.p, fidx.p, fw.p, fne.p, rr.ptr.p, rr.id.p, rr.val.p, new_area.p, W->col.p, W->val.p);
+    MSM_TRY(exclusive_scan_i32(len.p, store->rowptr.p, (int)NL, store->rowptr.p + NL, s));
+    // nnz <= 3 NL + 3 NV (each row is either its <= 3 forward entries or its share of the <= 3 NV reverse entries)
+    const size_t cap = 3 * (size_t)(NL + NV);
+    MSM_CUDA(store->col.alloc(cap, s));
+    MSM_CUDA(store->val.alloc(cap, s));
+    k_fill_rows<<<gl, 256, 0, s>>>((int)NL, n_low, store->rowptr.p, fidx.p, fw.p, fne.p, rr.ptr.p, rr.id.p, rr.val.p, new_area.p, store->col.p,
+                                   store->val.p);
     MSM_LAUNCH_CHECK();
 
     // correction[src] = sum over targets (ascending) of the area-scaled weights (resampler.cpp:114-116)
     Buckets cols;
-    MSM_TRY(bucketize(EmitCsrColumns{W->rowptr.p, W->col.p, W->val.p, nv_low}, nv_low, nv_in, cols, s));
-    k_bucket_sum<<<(nv_in + 255) / 256, 256, 0, s>>>(nv_in, cols.ptr.p, cols.val.p, correction.p);
+    MSM_TRY(bucketize(EmitCsrColumns{store->rowptr.p, store->col.p, store->val.p, d_in_off.p, n_low, (int)NL}, (int)NL, (int)NV, cap, cols, s));
+    k_bucket_sum<<<(unsigned)((NV + 255) / 256), 256, 0, s>>>((int)NV, cols.ptr.p, cols.val.p, correction.p);
     MSM_LAUNCH_CHECK();
-    k_finish_rows<<<gl, 256, 0, s>>>(nv_low, W->rowptr.p, W->col.p, W->val.p, old_area.p, correction.p);
+    k_finish_rows<<<gl, 256, 0, s>>>((int)NL, n_low, store->rowptr.p, store->col.p, store->val.p, d_in_off.p, old_area.p, correction.p);
     MSM_LAUNCH_CHECK();
-    W->ctx = ctx;
-    W->n_rows = nv_low;
-    W->n_cols = nv_in;
-    W->nnz = nnz;
+
+    // per-subject views: rowptr offsets of the subject boundaries
+    std::vector<int> bounds(S + 1);
+    MSM_CUDA(cudaMemcpy2DAsync(bounds.data(), sizeof(int), store->rowptr.p, (size_t)n_low * sizeof(int), sizeof(int), S + 1, cudaMemcpyDeviceToHost, s));
+    MSM_CUDA(cudaStreamSynchronize(s));
+    for (int i = 0; i < S; ++i) {
+        auto* W = new msmgpu_weights();
+        W->ctx = ctx;
+        W->n_rows = n_low;
+        W->n_cols = in_meshes[i]->nv;
+        W->store = store;
+        W->rowptr = store->rowptr.p + (size_t)i * n_low;
+        W->first = bounds[i];
+        W->nnz = bounds[i + 1] - bounds[i];
+        out[i] = W;
+    }
     return MSMGPU_OK;
 }
 
@@ -250,59 +323,78 @@ msmgpu_status adaptive_weights_build(msmgpu_mesh* in_mesh, msmgpu_octree* in_tre
 // CSR apply: out[r][:] = sum over row r (ascending column) of in[col][:] * val, FP64 accumulation in
 // the reference's order (resampler.cpp:46-48). One thread per (row, 16-byte chunk): the threads of a
 // row read consecutive chunks of the same source rows (coalesced 128-bit loads), col/val are
-// broadcast loads.
+// broadcast loads. The batched form covers all subjects of a store in one launch.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_csr_apply_f32x4(int n_rows, const int* __restrict__ rowptr, const int* __restrict__ col,
-                                                         const double* __restrict__ val, int D4, const float4* __restrict__ in,
-                                                         float4* __restrict__ out) {
+struct ApplyJob {
+    const int* rowptr;   // n_rows + 1 absolute offsets
+    const void* in;      // [n_cols][D]
+    void* out;           // [n_rows][D]
+};
+
+__global__ void __launch_bounds__(256) k_csr_apply_f32x4(const ApplyJob* __restrict__ jobs, int n_rows, const int* __restrict__ col,
+                                                         const double* __restrict__ val, int D4) {
+    const ApplyJob job = jobs[blockIdx.y];
     const long long slot = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const int r = (int)(slot / D4);
     if (r >= n_rows) return;
     const int c = (int)(slot - (long long)r * D4);
-    const int b = __ldg(rowptr + r), e = __ldg(rowptr + r + 1);
+    const float4* __restrict__ in = static_cast<const float4*>(job.in);
+    const int b = __ldg(job.rowptr + r), e = __ldg(job.rowptr + r + 1);
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     for (int i = b; i < e; ++i) {
         const float4 f = __ldg(in + (size_t)__ldg(col + i) * D4 + c);
         const double w = __ldg(val + i);
         a0 += (double)f.x * w; a1 += (double)f.y * w; a2 += (double)f.z * w; a3 += (double)f.w * w;
     }
-    __stcs(out + (size_t)r * D4 + c, make_float4((float)a0, (float)a1, (float)a2, (float)a3));
+    __stcs(static_cast<float4*>(job.out) + (size_t)r * D4 + c, make_float4((float)a0, (float)a1, (float)a2, (float)a3));
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) k_csr_apply(int n_rows, const int* __restrict__ rowptr, const int* __restrict__ col,
-                                                   const double* __restrict__ val, int D, const T* __restrict__ in, T* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_csr_apply(const ApplyJob* __restrict__ jobs, int n_rows, const int* __restrict__ col,
+                                                   const double* __restrict__ val, int D) {
+    const ApplyJob job = jobs[blockIdx.y];
     const long long slot = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const int r = (int)(slot / D);
     if (r >= n_rows) return;
     const int c = (int)(slot - (long long)r * D);
+    const T* __restrict__ in = static_cast<const T*>(job.in);
     double a = 0.0;
-    for (int i = __ldg(rowptr + r); i < __ldg(rowptr + r + 1); ++i) a += (double)__ldg(in + (size_t)__ldg(col + i) * D + c) * __ldg(val + i);
-    out[(size_t)r * D + c] = (T)a;
+    for (int i = __ldg(job.rowptr + r); i < __ldg(job.rowptr + r + 1); ++i) a += (double)__ldg(in + (size_t)__ldg(col + i) * D + c) * __ldg(val + i);
+    static_cast<T*>(job.out)[(size_t)r * D + c] = (T)a;
 }
 
-msmgpu_status csr_apply_f32(const msmgpu_weights* W, int D, const float* d_in, float* d_out, cudaStream_t s) {
-    if (W->n_rows == 0 || D == 0) return MSMGPU_OK;
-    if ((D & 3) == 0 && ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) & 15) == 0) {
+// all weights must share one store (one batch) and have the same n_rows
+template <typename T>
+static msmgpu_status csr_apply_batch(msmgpu_ctx* ctx, int n, msmgpu_weights* const* Ws, int D, const T* const* d_in, T* const* d_out) {
+    cudaStream_t s = ctx->stream;
+    if (n <= 0 || D <= 0) return MSMGPU_OK;
+    const WeightsStore* store = Ws[0]->store.get();
+    const int n_rows = Ws[0]->n_rows;
+    bool vec = std::is_same<T, float>::value && (D & 3) == 0;
+    std::vector<ApplyJob> jobs(n);
+    for (int i = 0; i < n; ++i) {
+        if (Ws[i]->store.get() != store || Ws[i]->n_rows != n_rows) return fail(MSMGPU_ERR_INVALID, "weights_apply_batch: weights from different batches");
+        jobs[i] = ApplyJob{Ws[i]->rowptr, d_in[i], d_out[i]};
+        vec = vec && ((reinterpret_cast<uintptr_t>(d_in[i]) | reinterpret_cast<uintptr_t>(d_out[i])) & 15) == 0;
+    }
+    if (n_rows == 0) return MSMGPU_OK;
+    DevBuf<ApplyJob> d_jobs;
+    MSM_CUDA(d_jobs.alloc(n, s));
+    MSM_CUDA(cudaMemcpyAsync(d_jobs.p, jobs.data(), n * sizeof(ApplyJob), cudaMemcpyHostToDevice, s));   // pageable: staged before return
+    if (vec) {
         const int D4 = D >> 2;
-        const long long slots = (long long)W->n_rows * D4;
-        k_csr_apply_f32x4<<<(unsigned)((slots + 255) / 256), 256, 0, s>>>(W->n_rows, W->rowptr.p, W->col.p, W->val.p, D4,
-                                                                         reinterpret_cast<const float4*>(d_in), reinterpret_cast<float4*>(d_out));
+        const long long slots = (long long)n_rows * D4;
+        k_csr_apply_f32x4<<<dim3((unsigned)((slots + 255) / 256), (unsigned)n), 256, 0, s>>>(d_jobs.p, n_rows, store->col.p, store->val.p, D4);
     } else {
-        const long long slots = (long long)W->n_rows * D;
-        k_csr_apply<float><<<(unsigned)((slots + 255) / 256), 256, 0, s>>>(W->n_rows, W->rowptr.p, W->col.p, W->val.p, D, d_in, d_out);
+        const long long slots = (long long)n_rows * D;
+        k_csr_apply<T><<<dim3((unsigned)((slots + 255) / 256), (unsigned)n), 256, 0, s>>>(d_jobs.p, n_rows, store->col.p, store->val.p, D);
     }
     MSM_LAUNCH_CHECK();
     return MSMGPU_OK;
 }
 
-msmgpu_status csr_apply_f64(const msmgpu_weights* W, int D, const double* d_in, double* d_out, cudaStream_t s) {
-    if (W->n_rows == 0 || D == 0) return MSMGPU_OK;
-    const long long slots = (long long)W->n_rows * D;
-    k_csr_apply<double><<<(unsigned)((slots + 255) / 256), 256, 0, s>>>(W->n_rows, W->rowptr.p, W->col.p, W->val.p, D, d_in, d_out);
-    MSM_LAUNCH_CHECK();
-    return MSMGPU_OK;
-}
+msmgpu_status csr_apply_f32(msmgpu_weights* W, int D, const float* d_in, float* d_out) { return csr_apply_batch<float>(W->ctx, 1, &W, D, &d_in, &d_out); }
+msmgpu_status csr_apply_f64(msmgpu_weights* W, int D, const double* d_in, double* d_out) { return csr_apply_batch<double>(W->ctx, 1, &W, D, &d_in, &d_out); }
 
 } // namespace msm
 
@@ -322,29 +414,37 @@ msmgpu_status msmgpu_mesh_vertex_areas(msmgpu_mesh* m, double* out) {
     return MSMGPU_OK;
 }
 
+msmgpu_status msmgpu_adaptive_weights_batch(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* in_meshes, msmgpu_octree* const* in_trees,
+                                            msmgpu_mesh* low_mesh, msmgpu_octree* low_tree, msmgpu_weights** out) {
+    if (!ctx || n <= 0 || !in_meshes || !low_mesh || !out || low_mesh->ctx != ctx) return fail(MSMGPU_ERR_INVALID, "adaptive_weights_batch: bad arguments");
+    MSM_CUDA(cudaSetDevice(ctx->device));
+    for (int i = 0; i < n; ++i) out[i] = nullptr;
+    // missing trees are built as one forest
+    std::vector<msmgpu_mesh*> need;
+    for (int i = 0; i < n; ++i) {
+        if (!in_meshes[i] || in_meshes[i]->ctx != ctx) return fail(MSMGPU_ERR_INVALID, "adaptive_weights_batch: mesh from another context");
+        if (!in_trees || !in_trees[i]) need.push_back(in_meshes[i]);
+        else if (in_trees[i]->mesh != in_meshes[i]) return fail(MSMGPU_ERR_INVALID, "adaptive_weights: tree/mesh mismatch");
+    }
+    if (!low_tree) need.push_back(low_mesh);
+    else if (low_tree->mesh != low_mesh) return fail(MSMGPU_ERR_INVALID, "adaptive_weights: tree/mesh mismatch");
+    std::vector<msmgpu_octree*> built(need.size(), nullptr);
+    std::vector<std::unique_ptr<msmgpu_octree>> owned;
+    if (!need.empty()) {
+        MSM_TRY(msmgpu_octree_build_batch(ctx, (int)need.size(), need.data(), built.data()));
+        for (auto* t : built) owned.emplace_back(t);
+    }
+    std::vector<msmgpu_octree*> trees(n);
+    size_t k = 0;
+    for (int i = 0; i < n; ++i) trees[i] = (in_trees && in_trees[i]) ? in_trees[i] : built[k++];
+    if (!low_tree) low_tree = built[k++];
+    return adaptive_weights_build_batch(ctx, n, in_meshes, trees.data(), low_mesh, low_tree, out);
+}
+
 msmgpu_status msmgpu_adaptive_weights_ex(msmgpu_mesh* in_mesh, msmgpu_octree* in_tree, msmgpu_mesh* low_mesh, msmgpu_octree* low_tree,
                                          msmgpu_weights** out) {
     if (!in_mesh || !low_mesh || !out || in_mesh->ctx != low_mesh->ctx) return fail(MSMGPU_ERR_INVALID, "adaptive_weights: bad arguments");
-    *out = nullptr;
-    MSM_CUDA(cudaSetDevice(in_mesh->ctx->device));
-    std::unique_ptr<msmgpu_octree> own_in, own_low;
-    if (!in_tree || !low_tree) {   // both missing trees are built as one forest
-        msmgpu_mesh* ms[2];
-        msmgpu_octree* ts[2];
-        int k = 0;
-        if (!in_tree) ms[k++] = in_mesh;
-        if (!low_tree) ms[k++] = low_mesh;
-        MSM_TRY(msmgpu_octree_build_batch(in_mesh->ctx, k, ms, ts));
-        k = 0;
-        if (!in_tree) { own_in.reset(ts[k++]); in_tree = own_in.get(); }
-        if (!low_tree) { own_low.reset(ts[k++]); low_tree = own_low.get(); }
-    }
-    if (in_tree->mesh != in_mesh || low_tree->mesh != low_mesh) return fail(MSMGPU_ERR_INVALID, "adaptive_weights: tree/mesh mismatch");
-    auto W = std::unique_ptr<msmgpu_weights>(new msmgpu_weights());
-    MSM_TRY(adaptive_weights_build(in_mesh, in_tree, low_mesh, low_tree, W.get()));
-    MSM_CUDA(cudaStreamSynchronize(in_mesh->ctx->stream));
-    *out = W.release();
-    return MSMGPU_OK;
+    return msmgpu_adaptive_weights_batch(in_mesh->ctx, 1, &in_mesh, &in_tree, low_mesh, low_tree, out);
 }
 
 msmgpu_status msmgpu_adaptive_weights(msmgpu_mesh* in_mesh, msmgpu_mesh* low_mesh, msmgpu_weights** out) {
@@ -363,10 +463,12 @@ msmgpu_status msmgpu_weights_export(msmgpu_weights* w, int32_t* rowptr, int32_t*
     if (!w) return fail(MSMGPU_ERR_INVALID, "weights is NULL");
     MSM_CUDA(cudaSetDevice(w->ctx->device));
     cudaStream_t s = w->ctx->stream;
-    if (rowptr) MSM_CUDA(cudaMemcpyAsync(rowptr, w->rowptr.p, ((size_t)w->n_rows + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
-    if (col && w->nnz) MSM_CUDA(cudaMemcpyAsync(col, w->col.p, (size_t)w->nnz * sizeof(int), cudaMemcpyDeviceToHost, s));
-    if (val && w->nnz) MSM_CUDA(cudaMemcpyAsync(val, w->val.p, (size_t)w->nnz * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (rowptr) MSM_CUDA(cudaMemcpyAsync(rowptr, w->rowptr, ((size_t)w->n_rows + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (col && w->nnz) MSM_CUDA(cudaMemcpyAsync(col, w->store->col.p + w->first, (size_t)w->nnz * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (val && w->nnz) MSM_CUDA(cudaMemcpyAsync(val, w->store->val.p + w->first, (size_t)w->nnz * sizeof(double), cudaMemcpyDeviceToHost, s));
     MSM_CUDA(cudaStreamSynchronize(s));
+    if (rowptr)   // offsets are absolute inside the batch store: make them local to this matrix
+        for (int i = 0; i <= w->n_rows; ++i) rowptr[i] -= w->first;
     return MSMGPU_OK;
 }
 
@@ -379,7 +481,15 @@ void msmgpu_weights_destroy(msmgpu_weights* w) {
 msmgpu_status msmgpu_weights_apply_f32_dev(msmgpu_weights* w, int D, const float* d_in, float* d_out) {
     if (!w || D <= 0 || !d_in || !d_out) return fail(MSMGPU_ERR_INVALID, "weights_apply: bad arguments");
     MSM_CUDA(cudaSetDevice(w->ctx->device));
-    return csr_apply_f32(w, D, d_in, d_out, w->ctx->stream);
+    return csr_apply_f32(w, D, d_in, d_out);
+}
+
+msmgpu_status msmgpu_weights_apply_batch_f32_dev(msmgpu_ctx* ctx, int n, msmgpu_weights* const* ws, int D, const float* const* d_in, float* const* d_out) {
+    if (!ctx || n <= 0 || !ws || D <= 0 || !d_in || !d_out) return fail(MSMGPU_ERR_INVALID, "weights_apply_batch: bad arguments");
+    for (int i = 0; i < n; ++i)
+        if (!ws[i] || !d_in[i] || !d_out[i]) return fail(MSMGPU_ERR_INVALID, "weights_apply_batch: NULL entry");
+    MSM_CUDA(cudaSetDevice(ctx->device));
+    return csr_apply_batch<float>(ctx, n, ws, D, d_in, d_out);
 }
 
 // metric_resample (resampler.cpp:304-309) on host buffers, FP64 payload: channel-major in/out like Mesh::pvalues
@@ -397,7 +507,7 @@ msmgpu_status msmgpu_metric_resample(msmgpu_mesh* in_mesh, msmgpu_mesh* low_mesh
     MSM_CUDA(cm_out.alloc((size_t)D * nl, s));
     MSM_CUDA(cudaMemcpyAsync(cm_in.p, feat_in, (size_t)D * nv * sizeof(double), cudaMemcpyHostToDevice, s));
     MSM_TRY(launch_transpose_f64(D, nv, cm_in.p, rows_in.p, s));
-    MSM_TRY(csr_apply_f64(W, D, rows_in.p, rows_out.p, s));
+    MSM_TRY(csr_apply_f64(W, D, rows_in.p, rows_out.p));
     MSM_TRY(launch_transpose_f64(nl, D, rows_out.p, cm_out.p, s));
     MSM_CUDA(cudaMemcpyAsync(feat_out, cm_out.p, (size_t)D * nl * sizeof(double), cudaMemcpyDeviceToHost, s));
     MSM_CUDA(cudaStreamSynchronize(s));
@@ -420,7 +530,7 @@ msmgpu_status msmgpu_metric_resample_f32(msmgpu_mesh* in_mesh, msmgpu_octree* in
     MSM_CUDA(cm_out.alloc((size_t)D * nl, s));
     MSM_CUDA(cudaMemcpyAsync(cm_in.p, feat_in, (size_t)D * nv * sizeof(float), cudaMemcpyHostToDevice, s));
     MSM_TRY(launch_chmajor_f32_to_rows_f32(D, nv, cm_in.p, rows_in.p, s));
-    MSM_TRY(csr_apply_f32(W, D, rows_in.p, rows_out.p, s));
+    MSM_TRY(csr_apply_f32(W, D, rows_in.p, rows_out.p));
     MSM_TRY(launch_rows_f32_to_chmajor_f32(D, nl, rows_out.p, cm_out.p, s));
     MSM_CUDA(cudaMemcpyAsync(feat_out, cm_out.p, (size_t)D * nl * sizeof(float), cudaMemcpyDeviceToHost, s));
     MSM_CUDA(cudaStreamSynchronize(s));

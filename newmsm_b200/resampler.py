@@ -224,6 +224,16 @@ class Resampler:
         check(in_mesh.L.msmgpu_adaptive_weights(in_mesh.h, sphLow.h, C.byref(h)))
         return Weights(in_mesh.L, h)
 
+    def get_adaptive_barycentric_weights_batch(self, in_meshes, sphLow: Mesh, in_trees=None, low_tree: Octree | None = None):
+        """The same for a batch of subjects resampled onto one target: one set of launches (msmgpu_adaptive_weights_batch)."""
+        n = len(in_meshes)
+        ctx = sphLow.ctx
+        mh = (C.c_void_p * n)(*[m.h.value for m in in_meshes])
+        th = (C.c_void_p * n)(*[(t.h.value if t is not None else None) for t in in_trees]) if in_trees else None
+        out = (C.c_void_p * n)()
+        check(ctx.L.msmgpu_adaptive_weights_batch(ctx.h, n, mh, th, sphLow.h, low_tree.h if low_tree else None, out))
+        return [Weights(ctx.L, C.c_void_p(out[i])) for i in range(n)]
+
     def barycentric_data_interpolation(self, metric_in: Mesh, sphLow: Mesh, nthreads: int = 1, EXCL=None):
         """resampler.cpp:30-70: adaptive-barycentric resampling of metric_in.pvalues -> [D, n_low]."""
         if EXCL is not None:
