@@ -104,6 +104,8 @@ class ClockSampler:
     def __init__(self, index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        if os.environ.get("BENCH_NO_CLOCKS"):
+            return
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
@@ -291,9 +293,15 @@ def run_ours(a):
             dist.barrier()
 
     clocks = ClockSampler(local)
+    dbg = []
     for _ in range(max(a.warmup, 3)):
+        t0 = time.perf_counter()
         device_step()
+        stream.synchronize()
+        dbg.append(round(1e3 * (time.perf_counter() - t0), 1))
     sync_all()
+    if os.environ.get("BENCH_DEBUG"):
+        print(f"[debug] warm-up steps, host ms: {dbg}", file=sys.stderr, flush=True)
     if os.environ.get("BENCH_DEBUG"):
         for mode in ("sync each step", "no sync"):
             ts = []
@@ -313,6 +321,7 @@ def run_ours(a):
     e0.record(stream)
     for _ in range(a.steps):
         device_step()
+        stream.synchronize()   # a step's results are complete when it returns (and the stream-ordered pool reuses its blocks)
     e1.record(stream)
     sync_all()
     ms_total = e0.elapsed_time(e1)

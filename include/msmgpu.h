@@ -52,7 +52,7 @@ unsigned long long msmgpu_launch_count(void);
 const char* msmgpu_debug_take_cuda_error(void);
 
 /* Tuning knob with no effect on results: how many lanes cooperate on one nearest-triangle query
- * (1, 2, 4, 8, 16 or 32; default 2 or $MSMGPU_QUERY_GROUP). */
+ * (1, 2, 4, 8, 16 or 32; default 1 or $MSMGPU_QUERY_GROUP). */
 msmgpu_status msmgpu_set_query_group(int lanes);
 int msmgpu_get_query_group(void);
 

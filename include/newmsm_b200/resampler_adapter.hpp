@@ -1,0 +1,217 @@
+// resampler_adapter.hpp — the reference-side binding of include/msmgpu.h for msm-newresampler.
+//
+// Header-only. It keeps the reference's C++ interface (msm-newresampler/src/resampler.h:38-53,
+// octree.h:39-59): same class / function names, argument meaning and error behaviour
+// (newresampler::MeshException with the reference's messages), in namespace newresampler_gpu,
+// and forwards to the C ABI. A maintainer switches a call site by changing the namespace (or with
+// `namespace newresampler = newresampler_gpu;`-style aliases per function) and linking
+// libmsmgpu.so; see INTEGRATION.md. `nthreads` arguments are accepted and ignored.
+//
+// Checked in-process against the reference's own CPU functions by integration/adapter_check.cpp.
+#pragma once
+
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#ifndef NEWMSM_B200_RESAMPLER_HEADER
+#define NEWMSM_B200_RESAMPLER_HEADER "newresampler/resampler.h"
+#endif
+#include NEWMSM_B200_RESAMPLER_HEADER   // the reference's Mesh / Point / Triangle / MeshException
+
+#include "../msmgpu.h"
+
+namespace newresampler_gpu {
+
+using newresampler::Mesh;
+using newresampler::MeshException;
+using newresampler::Point;
+using newresampler::Triangle;
+
+namespace detail {
+
+inline void check(msmgpu_status st) {
+    if (st != MSMGPU_OK) {
+        static thread_local std::string msg;   // MeshException keeps the pointer (meshException.h:31)
+        msg = msmgpu_last_error();
+        throw MeshException(msg.c_str());
+    }
+}
+
+inline msmgpu_ctx* context() {   // one context per process on $MSMGPU_DEVICE (default 0)
+    static msmgpu_ctx* ctx = [] {
+        const char* e = std::getenv("MSMGPU_DEVICE");
+        msmgpu_ctx* c = nullptr;
+        check(msmgpu_ctx_create(e ? std::atoi(e) : 0, nullptr, &c));
+        return c;
+    }();
+    return ctx;
+}
+
+inline std::vector<double> coords_of(const Mesh& m) {
+    std::vector<double> xyz(3 * (size_t)m.nvertices());
+    for (int i = 0; i < m.nvertices(); ++i) {
+        const Point& p = m.get_coord(i);
+        xyz[3 * (size_t)i] = p.X; xyz[3 * (size_t)i + 1] = p.Y; xyz[3 * (size_t)i + 2] = p.Z;
+    }
+    return xyz;
+}
+
+inline std::vector<double> pvalues_of(const Mesh& m) {   // channel-major [D][V] like Mesh::pvalues (mesh.h:44)
+    const int D = m.get_dimension(), V = m.nvertices();
+    std::vector<double> f((size_t)D * V);
+    for (int d = 0; d < D; ++d)
+        for (int v = 0; v < V; ++v) f[(size_t)d * V + v] = m.get_pvalue(v, d);
+    return f;
+}
+
+// device copy of a reference Mesh (geometry only)
+class DeviceMesh {
+public:
+    explicit DeviceMesh(const Mesh& m) : nv(m.nvertices()), nt(m.ntriangles()) {
+        const std::vector<double> xyz = coords_of(m);
+        tri.resize(3 * (size_t)nt);
+        for (int t = 0; t < nt; ++t)
+            for (int k = 0; k < 3; ++k) tri[3 * (size_t)t + k] = m.get_triangle_vertexID(t, k);
+        check(msmgpu_mesh_create(context(), nv, xyz.data(), nt, tri.data(), &h));
+    }
+    ~DeviceMesh() { msmgpu_mesh_destroy(h); }
+    DeviceMesh(const DeviceMesh&) = delete;
+    DeviceMesh& operator=(const DeviceMesh&) = delete;
+    msmgpu_mesh* h = nullptr;
+    int nv, nt;
+    std::vector<int32_t> tri;
+};
+
+inline Mesh with_pvalues(const Mesh& geometry, int D, const std::vector<double>& cm) {   // like resampler.cpp:37-38, 54-57
+    Mesh out = geometry;
+    out.initialize_pvalues(D);
+    const int V = out.nvertices();
+    for (int d = 0; d < D; ++d)
+        for (int v = 0; v < V; ++v) out.set_pvalue(v, cm[(size_t)d * V + v], d);
+    return out;
+}
+
+}  // namespace detail
+
+// octree.h:39-59. Besides the reference's per-point calls there are batched ones: a GPU launch per point
+// would be absurd, so hot callers pass all their points at once.
+class Octree {
+    std::unique_ptr<detail::DeviceMesh> dm;
+    msmgpu_octree* h = nullptr;
+    const Mesh* target;
+
+public:
+    explicit Octree(const Mesh& t) : dm(new detail::DeviceMesh(t)), target(&t) { detail::check(msmgpu_octree_build(dm->h, &h)); }
+    ~Octree() { msmgpu_octree_destroy(h); }
+    Octree(const Octree&) = delete;
+    Octree& operator=(const Octree&) = delete;
+
+    msmgpu_octree* handle() const { return h; }
+
+    std::vector<int> get_closest_triangle_ids(const std::vector<Point>& pts) const {
+        std::vector<double> q(3 * pts.size());
+        for (size_t i = 0; i < pts.size(); ++i) { q[3 * i] = pts[i].X; q[3 * i + 1] = pts[i].Y; q[3 * i + 2] = pts[i].Z; }
+        std::vector<int32_t> ids(pts.size());
+        detail::check(msmgpu_nearest_triangle(h, (int)pts.size(), q.data(), ids.data(), nullptr, nullptr));   // throws like octree.cpp:158 / 211
+        return std::vector<int>(ids.begin(), ids.end());
+    }
+    Triangle get_closest_triangle(const Point& pt) const { return target->get_triangle(get_closest_triangle_ids({pt})[0]); }
+
+    std::vector<int> get_closest_vertex_IDs(const std::vector<Point>& pts) const {
+        std::vector<double> q(3 * pts.size());
+        for (size_t i = 0; i < pts.size(); ++i) { q[3 * i] = pts[i].X; q[3 * i + 1] = pts[i].Y; q[3 * i + 2] = pts[i].Z; }
+        std::vector<int32_t> ids(pts.size());
+        detail::check(msmgpu_nearest_triangle(h, (int)pts.size(), q.data(), nullptr, ids.data(), nullptr));
+        return std::vector<int>(ids.begin(), ids.end());
+    }
+    int get_closest_vertex_ID(const Point& pt) const { return get_closest_vertex_IDs({pt})[0]; }
+};
+
+// resampler.h:38-44
+class Resampler {
+public:
+    std::vector<std::map<int, double>> get_barycentric_weights(const Mesh& low, const Mesh& /*orig*/, const Octree& oct, int /*nthreads*/ = 1) {
+        const int n = low.nvertices();
+        const std::vector<double> q = detail::coords_of(low);
+        std::vector<int32_t> idx(3 * (size_t)n), ne(n);
+        std::vector<double> w(3 * (size_t)n);
+        detail::check(msmgpu_bary_weights(oct.handle(), n, q.data(), idx.data(), w.data(), ne.data()));
+        std::vector<std::map<int, double>> out(n);
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < ne[i]; ++j) out[i].emplace_hint(out[i].end(), idx[3 * (size_t)i + j], w[3 * (size_t)i + j]);
+        return out;
+    }
+
+    std::vector<std::map<int, double>> get_adaptive_barycentric_weights(const Mesh& in_mesh, const Mesh& sphLow, int /*nthreads*/ = 1,
+                                                                        std::shared_ptr<Mesh> EXCL = std::shared_ptr<Mesh>()) {
+        if (EXCL) return newresampler::Resampler().get_adaptive_barycentric_weights(in_mesh, sphLow, 1, EXCL);   // masks: host path, out of scope
+        detail::DeviceMesh a(in_mesh), b(sphLow);
+        msmgpu_weights* W = nullptr;
+        detail::check(msmgpu_adaptive_weights(a.h, b.h, &W));
+        int n_rows = 0;
+        int64_t nnz = 0;
+        msmgpu_weights_shape(W, &n_rows, nullptr, &nnz);
+        std::vector<int32_t> rowptr((size_t)n_rows + 1), col((size_t)nnz);
+        std::vector<double> val((size_t)nnz);
+        const msmgpu_status st = msmgpu_weights_export(W, rowptr.data(), col.data(), val.data());
+        msmgpu_weights_destroy(W);
+        detail::check(st);
+        std::vector<std::map<int, double>> out(n_rows);
+        for (int r = 0; r < n_rows; ++r)
+            for (int e = rowptr[r]; e < rowptr[r + 1]; ++e) out[r].emplace_hint(out[r].end(), col[e], val[e]);
+        return out;
+    }
+
+    Mesh barycentric_data_interpolation(const Mesh& metric_in, const Mesh& sphLow, int nthreads = 1,
+                                        std::shared_ptr<Mesh> EXCL = std::shared_ptr<Mesh>()) {
+        if (EXCL) return newresampler::Resampler().barycentric_data_interpolation(metric_in, sphLow, nthreads, EXCL);
+        detail::DeviceMesh a(metric_in), b(sphLow);
+        const int D = metric_in.get_dimension();
+        const std::vector<double> fin = detail::pvalues_of(metric_in);
+        std::vector<double> fout((size_t)D * sphLow.nvertices());
+        detail::check(msmgpu_metric_resample(a.h, b.h, D, fin.data(), fout.data()));
+        return detail::with_pvalues(sphLow, D, fout);
+    }
+};
+
+// resampler.h:46-53
+inline Mesh metric_resample(const Mesh& in, const Mesh& target, int nthreads = 1, std::shared_ptr<Mesh> EXCL = std::shared_ptr<Mesh>()) {
+    return Resampler().barycentric_data_interpolation(in, target, nthreads, EXCL);
+}
+
+inline Mesh surface_resample(const Mesh& anat_orig, const Mesh& sphere_orig, const Mesh& sphere_low, int /*nthreads*/ = 1) {
+    // resampler.cpp:284-302: new coordinates of sphere_low's vertices = blend of anat_orig over sphere_orig's triangles
+    detail::DeviceMesh s(sphere_orig);
+    const std::vector<double> anat = detail::coords_of(anat_orig), low = detail::coords_of(sphere_low);
+    std::vector<double> out(low.size());
+    detail::check(msmgpu_surface_resample(s.h, anat.data(), sphere_low.nvertices(), low.data(), out.data()));
+    Mesh res = sphere_low;
+    for (int i = 0; i < res.nvertices(); ++i) res.set_coord(i, Point(out[3 * (size_t)i], out[3 * (size_t)i + 1], out[3 * (size_t)i + 2]));
+    return res;
+}
+
+inline Mesh project_anatomical_mesh(const Mesh& orig, const Mesh& target, const Mesh& anat, int nthreads = 1) {   // resampler.cpp:260-282
+    return newresampler_gpu::surface_resample(anat, orig, target, nthreads);
+}
+
+inline void sphere_project_warp(Mesh& sphere, const Mesh& from, const Mesh& to, int /*nthreads*/ = 1) {   // resampler.cpp:311-328
+    detail::DeviceMesh f(from);
+    const std::vector<double> t = detail::coords_of(to), q = detail::coords_of(sphere);
+    std::vector<double> out(q.size());
+    detail::check(msmgpu_sphere_project_warp(f.h, t.data(), sphere.nvertices(), q.data(), out.data()));
+    for (int i = 0; i < sphere.nvertices(); ++i) sphere.set_coord(i, Point(out[3 * (size_t)i], out[3 * (size_t)i + 1], out[3 * (size_t)i + 2]));
+}
+
+inline Mesh nearest_neighbour_interpolation(Mesh& orig, const Mesh& sphLow, int nthreads = 1, std::shared_ptr<Mesh> EXCL = std::shared_ptr<Mesh>()) {
+    if (EXCL) return newresampler::nearest_neighbour_interpolation(orig, sphLow, nthreads, EXCL);   // resampler.cpp:232-258
+    detail::DeviceMesh a(orig);
+    const int D = orig.get_dimension();
+    const std::vector<double> fin = detail::pvalues_of(orig), low = detail::coords_of(sphLow);
+    std::vector<double> fout((size_t)D * sphLow.nvertices());
+    detail::check(msmgpu_nn_resample(a.h, sphLow.nvertices(), low.data(), D, fin.data(), fout.data()));
+    return detail::with_pvalues(sphLow, D, fout);
+}
+
+}  // namespace newresampler_gpu

@@ -1,0 +1,108 @@
+// In-process drop-in check (TEST INFRASTRUCTURE, built by `make -C oracle adapter_check` into oracle/_ref/):
+// the reference's own Mesh objects go through include/newmsm_b200/resampler_adapter.hpp to the GPU and
+// the results are compared, bit for bit, with the reference's own CPU functions called on the same objects.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "newmsm_b200/resampler_adapter.hpp"
+
+using namespace newresampler;
+
+static int failures = 0;
+#define EXPECT(cond, what)                                   \
+    do {                                                     \
+        if (!(cond)) { std::printf("FAIL: %s\n", what); ++failures; } \
+        else std::printf("ok:   %s\n", what);                \
+    } while (0)
+
+static Mesh sphere(int level, double rx, double ry, double rz) {
+    Mesh m = make_mesh_from_icosa(level);
+    true_rescale(m, RAD);
+    if (rx != 0 || ry != 0 || rz != 0) {
+        for (int i = 0; i < m.nvertices(); ++i) {
+            Point p = m.get_coord(i);
+            Point q(p.X * std::cos(rz) - p.Y * std::sin(rz), p.X * std::sin(rz) + p.Y * std::cos(rz), p.Z);
+            Point r(q.X * std::cos(ry) + q.Z * std::sin(ry), q.Y, -q.X * std::sin(ry) + q.Z * std::cos(ry));
+            Point s(r.X, r.Y * std::cos(rx) - r.Z * std::sin(rx), r.Y * std::sin(rx) + r.Z * std::cos(rx));
+            s.normalize();
+            m.set_coord(i, s * RAD);
+        }
+    }
+    return Mesh(m);   // copy => triangles rebuilt, cached areas refreshed (mesh.cpp:37-53)
+}
+
+static bool same_pvalues(const Mesh& a, const Mesh& b) {
+    if (a.get_dimension() != b.get_dimension() || a.nvertices() != b.nvertices()) return false;
+    for (int d = 0; d < a.get_dimension(); ++d)
+        for (int v = 0; v < a.nvertices(); ++v) {
+            const double x = a.get_pvalue(v, d), y = b.get_pvalue(v, d);
+            if (std::memcmp(&x, &y, sizeof(double)) != 0) return false;
+        }
+    return true;
+}
+static bool same_coords(const Mesh& a, const Mesh& b) {
+    for (int v = 0; v < a.nvertices(); ++v) {
+        const Point &p = a.get_coord(v), &q = b.get_coord(v);
+        if (p.X != q.X || p.Y != q.Y || p.Z != q.Z) return false;
+    }
+    return true;
+}
+
+int main() {
+    try {
+        Mesh in = sphere(5, 0, 0, 0), low = sphere(4, 0.013, 0.021, 0.034);
+        in.initialize_pvalues(3);
+        for (int d = 0; d < 3; ++d)
+            for (int v = 0; v < in.nvertices(); ++v) {
+                const Point& p = in.get_coord(v);
+                in.set_pvalue(v, std::cos(0.05 * p.X * (d + 1) + 0.3) + std::sin(0.04 * p.Y - 0.02 * p.Z * d), d);
+            }
+
+        // metric_resample (adaptive barycentric), resampler.cpp:304
+        Mesh cpu = metric_resample(in, low, 1);
+        Mesh gpu = newresampler_gpu::metric_resample(in, low, 1);
+        EXPECT(same_pvalues(cpu, gpu), "metric_resample: GPU == reference CPU, bit for bit");
+
+        // adaptive weights as vector<map<int,double>>
+        Resampler rc;
+        newresampler_gpu::Resampler rg;
+        EXPECT(rc.get_adaptive_barycentric_weights(in, low, 1) == rg.get_adaptive_barycentric_weights(in, low, 1),
+               "get_adaptive_barycentric_weights: identical maps");
+
+        // octree queries + barycentric weights
+        Octree oc(in);
+        newresampler_gpu::Octree og(in);
+        std::vector<Point> pts;
+        for (int v = 0; v < low.nvertices(); ++v) pts.push_back(low.get_coord(v));
+        const std::vector<int> ids = og.get_closest_triangle_ids(pts);
+        bool ok = true;
+        for (size_t i = 0; i < pts.size(); ++i) ok = ok && oc.get_closest_triangle(pts[i]).get_no() == ids[i];
+        EXPECT(ok, "get_closest_triangle: identical triangle ids");
+        EXPECT(oc.get_closest_triangle(pts[7]).get_no() == og.get_closest_triangle(pts[7]).get_no(), "get_closest_triangle(Point): same Triangle");
+        EXPECT(oc.get_closest_vertex_ID(pts[11]) == og.get_closest_vertex_ID(pts[11]), "get_closest_vertex_ID");
+        EXPECT(rc.get_barycentric_weights(low, in, oc, 1) == rg.get_barycentric_weights(low, in, og, 1), "get_barycentric_weights: identical maps");
+
+        // sphere_project_warp, resampler.cpp:311
+        Mesh to = sphere(5, 0.0, 0.01, -0.02);
+        Mesh s1 = low, s2 = low;
+        sphere_project_warp(s1, in, to, 1);
+        newresampler_gpu::sphere_project_warp(s2, in, to, 1);
+        EXPECT(same_coords(s1, s2), "sphere_project_warp: identical coordinates");
+
+        // surface_resample / nearest neighbour
+        EXPECT(same_coords(surface_resample(to, in, low, 1), newresampler_gpu::surface_resample(to, in, low, 1)), "surface_resample: identical coordinates");
+        EXPECT(same_pvalues(nearest_neighbour_interpolation(in, low, 1), newresampler_gpu::nearest_neighbour_interpolation(in, low, 1)),
+               "nearest_neighbour_interpolation: identical values");
+
+        // error behaviour: the reference's exception with the reference's message (octree.cpp:158)
+        bool threw = false;
+        try { og.get_closest_triangle(Point(0, 0, 150)); } catch (MeshException& e) { threw = std::strstr(e.what(), "bounding box") != nullptr; }
+        EXPECT(threw, "out-of-box query throws MeshException(\"Point is not in the bounding box of the mesh\")");
+    } catch (std::exception& e) {
+        std::printf("FAIL: unexpected exception\n");
+        return 2;
+    }
+    std::printf(failures ? "ADAPTER CHECK FAILED (%d)\n" : "ADAPTER CHECK PASSED\n", failures);
+    return failures ? 1 : 0;
+}

@@ -27,6 +27,8 @@ def build(ref: bool | None = None) -> None:
         ref = os.path.isdir(REFERENCE_ROOT)
     if ref:
         subprocess.run(["make", "-s", "-C", _HERE, "ref"], check=True)
+        if os.path.exists(os.path.join(os.path.dirname(_HERE), "newmsm_b200", "lib", "libmsmgpu.so")):
+            subprocess.run(["make", "-s", "-C", _HERE, "adapter_check"], check=True)   # in-process drop-in check (C++ adapter)
 
 
 def have_ref() -> bool:

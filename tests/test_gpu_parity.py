@@ -116,7 +116,7 @@ def test_nearest_triangle_bit_exact(R, oracle_built, meshes, key, group):
         assert np.array_equal(v0[ok], v1[ok])
         assert (s0 == 1).sum() == 3
     finally:
-        capi.check(capi.lib().msmgpu_set_query_group(2))
+        capi.check(capi.lib().msmgpu_set_query_group(1))
 
 
 def test_query_raises_like_reference(R, meshes):
@@ -244,6 +244,17 @@ def test_blend_golden(R):
 def test_rotation_golden(R):
     g = load("rotation.npz")
     assert np.array_equal(R.estimate_rotation_matrix(g["ci"], g["index"]), g["R"])
+
+
+def test_cpp_adapter_drop_in(R):
+    """The reference's own Mesh objects through include/newmsm_b200/resampler_adapter.hpp, compared in-process with
+    the reference's CPU functions (integration/adapter_check.cpp, built here into oracle/_ref/ where /root/reference is)."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "adapter_check")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/adapter_check not built (needs /root/reference: make -C oracle adapter_check)")
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "ADAPTER CHECK PASSED" in res.stdout, res.stdout + res.stderr
 
 
 # ---------------------------------------------------------------------------------------------
