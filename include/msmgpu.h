@@ -68,6 +68,9 @@ msmgpu_status msmgpu_mesh_create_dev(msmgpu_ctx* ctx, int nv, const double* d_xy
 msmgpu_status msmgpu_mesh_set_coords(msmgpu_mesh* m, const double* xyz);   /* Mesh::set_coord for all vertices */
 void msmgpu_mesh_destroy(msmgpu_mesh* m);
 msmgpu_status msmgpu_mesh_shape(msmgpu_mesh* m, int* nv, int* nt);
+/* replaces: Mesh::pvalues / set_pvalues (mesh.h:44, mesh.cpp:206) as a device-resident FP32 payload: channel-major host floats
+ * [D][nv] uploaded ONCE and reused by msmgpu_mesh_bary_resample_f32 / msmgpu_mesh_metric_resample_f32 */
+msmgpu_status msmgpu_mesh_set_features_f32(msmgpu_mesh* m, int D, const float* feat_cm);
 /* replaces: compute_vertex_area (msm-newresampler/src/mesh.cpp:1275) for all vertices */
 msmgpu_status msmgpu_mesh_vertex_areas(msmgpu_mesh* m, double* out);
 
@@ -128,6 +131,9 @@ msmgpu_status msmgpu_bary_resample_batch_f32_dev(msmgpu_ctx* ctx, int n_subjects
                                                  int D, const float* const* d_feat_in, float* const* d_feat_out, int32_t* d_status);
 /* host buffers, FP32 payload, channel-major like Mesh::pvalues: feat_in [D][nv] float -> feat_out [D][n] float */
 msmgpu_status msmgpu_bary_resample_f32(msmgpu_octree* t, int n, const double* pts, int D, const float* feat_in, float* feat_out);
+/* the same two resamplers on the mesh's resident features: only the result crosses PCIe. feat_out channel-major [D][n] floats */
+msmgpu_status msmgpu_mesh_bary_resample_f32(msmgpu_octree* t, int n, const double* pts, float* feat_out);
+msmgpu_status msmgpu_mesh_metric_resample_f32(msmgpu_mesh* in_mesh, msmgpu_octree* in_tree, msmgpu_mesh* low_mesh, msmgpu_octree* low_tree, float* feat_out);
 /* host-buffer convenience (channel-major double in/out), used by the parity tests */
 msmgpu_status msmgpu_bary_resample(msmgpu_mesh* in_mesh, int n, const double* pts, int D, const double* feat_in, double* feat_out);
 
@@ -145,8 +151,20 @@ msmgpu_status msmgpu_rotation_matrices(msmgpu_ctx* ctx, int n, const double* ci,
 typedef enum {
     MSMGPU_COST_UNIVARIATE = 0,   /* UnivariateNonLinearSRegDiscreteCostFunction  (cpp:326-383) */
     MSMGPU_COST_MULTIVARIATE = 1, /* MultivariateNonLinearSRegDiscreteCostFunction (cpp:385-458) */
-    MSMGPU_COST_PATCHWISE = 2     /* PatchwiseMultivariate...                      (cpp:620-692) */
+    MSMGPU_COST_PATCHWISE = 2,    /* PatchwiseMultivariate...                      (cpp:620-692) */
+    MSMGPU_COST_HO_UNIVARIATE = 3,   /* HOUnivariateNonLinearSRegDiscreteCostFunction   (cpp:460-531): triplet likelihood */
+    MSMGPU_COST_HO_MULTIVARIATE = 4  /* HOMultivariateNonLinearSRegDiscreteCostFunction (cpp:533-618) */
 } msmgpu_cost_kind;
+
+/* regulariser parameters of NonLinearSRegDiscreteCostFunction::set_parameters (cpp:119-133) */
+typedef struct {
+    double lambda;          /* "lambda"        _reglambda */
+    double shear_modulus;   /* "shearmodulus"  _mu     (default 0.4) */
+    double bulk_modulus;    /* "bulkmodulus"   _kappa  (default 1.6) */
+    double k_exponent;      /* "kexponent"     _k_exp  (default 2) */
+    double exponent;        /* "exponent"      _rexp   (default 2) */
+    int rmode;              /* "regularisermode": 2 or 3 = spherical strain (4/5 need anatomical meshes: not accelerated) */
+} msmgpu_reg_params;
 
 /* replaces: set_meshes + set_featurespace + set_octrees (DiscreteCostFunction.h:173-189).
  * target: TARGET mesh + its octree; source_xyz [nsrc][3]; features channel-major doubles:
@@ -172,6 +190,21 @@ msmgpu_status msmgpu_costfn_unary_table(msmgpu_costfn* c, int L, const double* l
                                         double* out, int32_t* tri_out);
 /* device-resident result: d_out [L][ncp] (and d_tri_out) stay on the device for a device-side consumer; labels / rotations are host arrays */
 msmgpu_status msmgpu_costfn_unary_table_dev(msmgpu_costfn* c, int L, const double* labels, const double* rotations, double* d_out, int32_t* d_tri_out);
+
+/* replaces: HO*::get_source_data (cpp:468-485, 541-563): patches = source vertices grouped by their nearest CP-GRID triangle
+ * (cp_tri [ntri][3]); msmgpu_costfn_patches then returns rowptr[ntri+1] / members. HO kinds only. */
+msmgpu_status msmgpu_costfn_set_cpgrid_ho(msmgpu_costfn* c, int ncp, const double* cp_xyz, int ntri, const int32_t* cp_tri,
+                                          int cfw_rows, const double* cfw, const double* absw);
+/* replaces: computeTripletCost (cpp:135-188) = HO likelihood (cpp:487-531, 565-618; 0 for the non-HO kinds) + lambda * strain^exponent
+ * (reg_tools.cpp:551-743) for n requests (triplet, la, lb, lc). triplets [ntrip][3] node ids (ascending, DiscreteModel.cpp:303),
+ * rotations [ncp][9], labels [L][3], orig_cp_xyz [ncp][3] = _ORIG. Folded triangles cost FOLDING * lambda = 1e7 * lambda. */
+msmgpu_status msmgpu_costfn_triplet_costs(msmgpu_costfn* c, int ntrip, const int32_t* triplets, int L, const double* labels, const double* rotations,
+                                          const double* orig_cp_xyz, const msmgpu_reg_params* prm, int n, const int32_t* req_triplet,
+                                          const int32_t* req_la, const int32_t* req_lb, const int32_t* req_lc, double* out);
+/* the 8 combinations Fusion::optimize asks per triplet for one candidate label (Fusion.h:181-196): out [ntrip][8],
+ * out[t][b] = cost(t, b&4 ? label : labeling[A], b&2 ? label : labeling[B], b&1 ? label : labeling[C]) */
+msmgpu_status msmgpu_costfn_triplet_batch(msmgpu_costfn* c, int ntrip, const int32_t* triplets, int L, const double* labels, const double* rotations,
+                                          const double* orig_cp_xyz, const msmgpu_reg_params* prm, const int32_t* labeling, int label, double* out);
 
 #ifdef __cplusplus
 }

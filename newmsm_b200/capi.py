@@ -48,6 +48,9 @@ _SIGNATURES = {
     "msmgpu_mesh_set_coords": (_i, [_vp, _vp]),
     "msmgpu_mesh_destroy": (None, [_vp]),
     "msmgpu_mesh_shape": (_i, [_vp, _vp, _vp]),
+    "msmgpu_mesh_set_features_f32": (_i, [_vp, _i, _vp]),
+    "msmgpu_mesh_bary_resample_f32": (_i, [_vp, _i, _vp, _vp]),
+    "msmgpu_mesh_metric_resample_f32": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "msmgpu_mesh_vertex_areas": (_i, [_vp, _vp]),
     "msmgpu_octree_build": (_i, [_vp, _pp]),
     "msmgpu_octree_build_batch": (_i, [_vp, _i, _vp, _vp]),
@@ -83,7 +86,17 @@ _SIGNATURES = {
     "msmgpu_costfn_patches": (_i, [_vp, _vp, _vp]),
     "msmgpu_costfn_unary_table": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     "msmgpu_costfn_unary_table_dev": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
+    "msmgpu_costfn_set_cpgrid_ho": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp]),
+    "msmgpu_costfn_triplet_costs": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "msmgpu_costfn_triplet_batch": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
 }
+
+
+class RegParams(C.Structure):
+    """msmgpu_reg_params (include/msmgpu.h)"""
+    _fields_ = [("lambda_", C.c_double), ("shear_modulus", C.c_double), ("bulk_modulus", C.c_double),
+                ("k_exponent", C.c_double), ("exponent", C.c_double), ("rmode", C.c_int)]
+
 
 _lib = None
 

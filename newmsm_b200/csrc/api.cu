@@ -442,6 +442,40 @@ msmgpu_status msmgpu_bary_resample_f32(msmgpu_octree* t, int n, const double* pt
     return finish_queries(d_st.p, n, nullptr, s);
 }
 
+// Mesh::pvalues as a device-resident payload (mesh.h:44; set_pvalues, mesh.cpp:206): one upload serves every later resample
+msmgpu_status msmgpu_mesh_set_features_f32(msmgpu_mesh* m, int D, const float* feat_cm) {
+    if (!m || D <= 0 || !feat_cm) return fail(MSMGPU_ERR_INVALID, "mesh_set_features_f32: bad arguments");
+    MSM_CUDA(cudaSetDevice(m->ctx->device));
+    cudaStream_t s = m->ctx->stream;
+    DevBuf<float> cm;
+    MSM_TRY(upload(cm, feat_cm, (size_t)D * m->nv, s));
+    MSM_CUDA(m->feat.alloc((size_t)D * m->nv, s));
+    MSM_TRY(launch_chmajor_f32_to_rows_f32(D, m->nv, cm.p, m->feat.p, s));
+    m->feat_D = D;
+    MSM_CUDA(cudaStreamSynchronize(s));
+    return MSMGPU_OK;
+}
+
+msmgpu_status msmgpu_mesh_bary_resample_f32(msmgpu_octree* t, int n, const double* pts, float* feat_out) {
+    if (!t || n <= 0 || !pts || !feat_out) return fail(MSMGPU_ERR_INVALID, "mesh_bary_resample_f32: bad arguments");
+    if (t->mesh->feat_D <= 0) return fail(MSMGPU_ERR_INVALID, "mesh_bary_resample_f32: the mesh has no resident features (msmgpu_mesh_set_features_f32)");
+    msmgpu_ctx* ctx = t->ctx;
+    MSM_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const int D = t->mesh->feat_D;
+    DevBuf<double> d_pts;
+    DevBuf<float> d_rows_out, d_cm_out;
+    DevBuf<int> d_st;
+    MSM_TRY(upload(d_pts, pts, 3 * (size_t)n, s));
+    MSM_CUDA(d_rows_out.alloc((size_t)D * n, s));
+    MSM_CUDA(d_cm_out.alloc((size_t)D * n, s));
+    MSM_CUDA(d_st.alloc(n, s));
+    MSM_TRY(msmgpu_bary_resample_f32_dev(t, n, d_pts.p, D, t->mesh->feat.p, d_rows_out.p, d_st.p));
+    MSM_TRY(launch_rows_f32_to_chmajor_f32(D, n, d_rows_out.p, d_cm_out.p, s));
+    MSM_CUDA(cudaMemcpyAsync(feat_out, d_cm_out.p, (size_t)D * n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    return finish_queries(d_st.p, n, nullptr, s);
+}
+
 static msmgpu_status blend_impl(msmgpu_mesh* mesh, const double* payload, int n, const double* q, double* out, int reproject) {
     if (!mesh || !payload || n <= 0 || !q || !out) return fail(MSMGPU_ERR_INVALID, "blend: bad arguments");
     msmgpu_ctx* ctx = mesh->ctx;

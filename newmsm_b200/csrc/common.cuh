@@ -99,6 +99,8 @@ struct msmgpu_mesh {
     msm::DevBuf<msm::TriRec> rec; // [nt] one 128-byte query record per triangle (gather-free leaf scans)
     msm::DevBuf<double> aabb;  // [nt][6] lo xyz, hi xyz (octree.cpp:46-59)
     msm::DevBuf<double> cull;  // [nt][4] centre + r^2 of the conservative cull sphere
+    msm::DevBuf<float> feat;   // optional resident payload, vertex-major rows [nv][feat_D] (Mesh::pvalues, mesh.h:44)
+    int feat_D = 0;
 };
 
 struct msmgpu_octree {

@@ -12,7 +12,7 @@
 // the reference's order, so costs are reproduced to the last bit and the label choices of the host
 // solver cannot flip. The sums are short and independent across the 48 678 (cp,label) CTAs, which
 // is where the parallelism comes from.
-#include "query.cuh"
+#include "cost.cuh"
 
 #include <cmath>
 #include <limits>
@@ -22,22 +22,6 @@ namespace msm {
 bool host_rotation_matrix(const double* ci, const double* index, double* R);
 
 } // namespace msm
-
-struct msmgpu_costfn {
-    msmgpu_ctx* ctx = nullptr;
-    msmgpu_octree* tree = nullptr;
-    int kind = 0, simmeasure = 2;
-    int nsrc = 0, D = 0, nvt = 0;
-    msm::DevBuf<double> src_xyz;    // [nsrc][3]
-    msm::DevBuf<double> src_feat;   // [nsrc][D] rows
-    msm::DevBuf<double> ref_feat;   // [nvt][D] rows
-    int ncp = 0, cfw_rows = 0;
-    double range = 0;
-    std::vector<double> h_cp;       // host copy: the rotation matrices are built on the host (api.cu)
-    msm::DevBuf<double> cp_xyz, cfw /* [nsrc][cfw_rows] rows */, absw, chord_thr;
-    msm::DevBuf<int> prow, pmem;    // patches: CSR over control points, ascending source id
-    int n_patch = 0, max_patch = 0;
-};
 
 namespace msm {
 
@@ -114,45 +98,6 @@ __global__ void __launch_bounds__(256) k_patch_members(int nsrc, const double* _
 __global__ void k_max_i32(int n, const int* __restrict__ v, int* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) atomicMax(out, v[i]);
-}
-
-// ------------------------------------------------------------------------------------------
-// similarities (sequential FP64, similarities.cpp:129-188), element access through functors
-// ------------------------------------------------------------------------------------------
-template <class FA, class FB, class FW>
-__device__ __forceinline__ double sim_corr(int n, FA A, FB B, FW W) {
-    double prod = 0.0, varA = 0.0, varB = 0.0, meanA = 0.0, meanB = 0.0, sum = 0.0;
-    for (int i = 0; i < n; ++i) sum += W(i);
-    for (int i = 0; i < n; ++i) {
-        const double w = W(i);
-        meanA += w * A(i);
-        meanB += w * B(i);
-    }
-    if (sum > 0.0) { meanA /= sum; meanB /= sum; }
-    for (int i = 0; i < n; ++i) {
-        const double w = W(i), a = A(i) - meanA, b = B(i) - meanB;
-        prod += w * a * b;
-        varA += w * a * a;
-        varB += w * b * b;
-    }
-    if (sum > 0.0) { prod /= sum; varA /= sum; varB /= sum; }
-    if (varA == 0.0 || varB == 0.0) return 0.0;
-    return prod / (sqrt(varA) * sqrt(varB));
-}
-template <class FA, class FB, class FW>
-__device__ __forceinline__ double sim_ssd(int n, FA A, FB B, FW W) {
-    double prod = 0.0;
-    for (int i = 0; i < n; ++i) {
-        const double d = A(i) - B(i);
-        prod += W(i) * d * d;
-    }
-    return sqrt(prod) / n;
-}
-template <class FA, class FB, class FW>
-__device__ __forceinline__ double sim_for_min(int simmeasure, int n, FA A, FB B, FW W) {
-    if (simmeasure == 1) return sim_ssd(n, A, B, W);
-    if (simmeasure == 2) return 1 - (1 + sim_corr(n, A, B, W)) * 0.5;
-    return nan("");
 }
 
 // ------------------------------------------------------------------------------------------
@@ -331,7 +276,7 @@ extern "C" {
 
 msmgpu_status msmgpu_costfn_create(msmgpu_octree* target_tree, msmgpu_cost_kind kind, int simmeasure, int nsrc, const double* source_xyz,
                                    int D, const double* src_feat, const double* ref_feat, msmgpu_costfn** out) {
-    if (!target_tree || !out || nsrc <= 0 || D <= 0 || !source_xyz || !src_feat || !ref_feat || kind < 0 || kind > 2)
+    if (!target_tree || !out || nsrc <= 0 || D <= 0 || !source_xyz || !src_feat || !ref_feat || kind < 0 || kind > MSMGPU_COST_HO_MULTIVARIATE)
         return fail(MSMGPU_ERR_INVALID, "costfn_create: bad arguments");
     if (simmeasure != 1 && simmeasure != 2) return fail(MSMGPU_ERR_INVALID, "costfn_create: simmeasure must be 1 (SSD) or 2 (correlation)");
     *out = nullptr;
@@ -367,6 +312,7 @@ msmgpu_status msmgpu_costfn_set_cpgrid(msmgpu_costfn* c, int ncp, const double* 
                                        int cfw_rows, const double* cfw, const double* absw) {
     if (!c || ncp <= 0 || !cp_xyz || !maxsep || !absw || cfw_rows < 0 || (cfw_rows > 0 && !cfw))
         return fail(MSMGPU_ERR_INVALID, "costfn_set_cpgrid: bad arguments");
+    if (c->kind >= MSMGPU_COST_HO_UNIVARIATE) return fail(MSMGPU_ERR_INVALID, "costfn_set_cpgrid: HO cost functions take msmgpu_costfn_set_cpgrid_ho");
     MSM_CUDA(cudaSetDevice(c->ctx->device));
     cudaStream_t s = c->ctx->stream;
     c->ncp = ncp; c->range = range; c->cfw_rows = cfw_rows;
@@ -395,6 +341,7 @@ msmgpu_status msmgpu_costfn_set_cpgrid(msmgpu_costfn* c, int ncp, const double* 
     MSM_CUDA(cudaStreamSynchronize(s));
     c->n_patch = h[0];
     c->max_patch = h[1];
+    c->n_patch_rows = ncp;
     MSM_CUDA(c->pmem.alloc((size_t)c->n_patch, s));
     if (c->n_patch > 0) {
         k_patch_members<1><<<ncp, 256, 0, s>>>(c->nsrc, c->cp_xyz.p, c->src_xyz.p, c->chord_thr.p, nullptr, c->prow.p, c->pmem.p);
@@ -405,10 +352,10 @@ msmgpu_status msmgpu_costfn_set_cpgrid(msmgpu_costfn* c, int ncp, const double* 
 }
 
 msmgpu_status msmgpu_costfn_patches(msmgpu_costfn* c, int32_t* rowptr, int32_t* members) {
-    if (!c || !rowptr || c->ncp <= 0) return fail(MSMGPU_ERR_INVALID, "costfn_patches: set_cpgrid first");
+    if (!c || !rowptr || c->n_patch_rows <= 0) return fail(MSMGPU_ERR_INVALID, "costfn_patches: set_cpgrid first");
     MSM_CUDA(cudaSetDevice(c->ctx->device));
     cudaStream_t s = c->ctx->stream;
-    MSM_CUDA(cudaMemcpyAsync(rowptr, c->prow.p, ((size_t)c->ncp + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
+    MSM_CUDA(cudaMemcpyAsync(rowptr, c->prow.p, ((size_t)c->n_patch_rows + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
     if (members && c->n_patch) MSM_CUDA(cudaMemcpyAsync(members, c->pmem.p, (size_t)c->n_patch * sizeof(int), cudaMemcpyDeviceToHost, s));
     MSM_CUDA(cudaStreamSynchronize(s));
     return MSMGPU_OK;
@@ -418,6 +365,7 @@ msmgpu_status msmgpu_costfn_patches(msmgpu_costfn* c, int32_t* rowptr, int32_t* 
 msmgpu_status msmgpu_costfn_unary_table_dev(msmgpu_costfn* c, int L, const double* labels, const double* rotations, double* d_out, int32_t* d_tri_out) {
     if (!c || L <= 0 || !labels || !rotations || !d_out) return fail(MSMGPU_ERR_INVALID, "costfn_unary_table: bad arguments");
     if (c->ncp <= 0) return fail(MSMGPU_ERR_INVALID, "costfn_unary_table: set_cpgrid first");
+    if (c->kind >= MSMGPU_COST_HO_UNIVARIATE) return fail(MSMGPU_ERR_INVALID, "costfn_unary_table: the HO classes have no unary term (DiscreteCostFunction.h:46 returns 0)");
     MSM_CUDA(cudaSetDevice(c->ctx->device));
     cudaStream_t s = c->ctx->stream;
     const int ncp = c->ncp;

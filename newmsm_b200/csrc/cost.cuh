@@ -1,0 +1,65 @@
+// Shared by cost.cu (unary tables) and triplet.cu (HO patches, triplet costs): the device state of one
+// DiscreteCostFunction and the sequential FP64 similarities.
+#pragma once
+#include "query.cuh"
+
+struct msmgpu_costfn {
+    msmgpu_ctx* ctx = nullptr;
+    msmgpu_octree* tree = nullptr;
+    int kind = 0, simmeasure = 2;
+    int nsrc = 0, D = 0, nvt = 0;
+    msm::DevBuf<double> src_xyz;    // [nsrc][3]
+    msm::DevBuf<double> src_feat;   // [nsrc][D] rows
+    msm::DevBuf<double> ref_feat;   // [nvt][D] rows
+    int ncp = 0, cfw_rows = 0;
+    double range = 0;
+    std::vector<double> h_cp;       // host copy: the rotation matrices are built on the host (api.cu)
+    msm::DevBuf<double> cp_xyz, cfw /* [nsrc][cfw_rows] rows */, absw, chord_thr;
+    msm::DevBuf<int> prow, pmem;    // patches: CSR over control points (or CP-grid triangles for the HO kinds), ascending source id
+    int n_patch = 0, max_patch = 0, n_patch_rows = 0;
+    // HO (triclique) state: the CP-grid triangles the patches hang on (DiscreteCostFunction.cpp:468-485)
+    int n_cp_tri = 0;
+};
+
+namespace msm {
+
+// ------------------------------------------------------------------------------------------
+// similarities (sequential FP64, similarities.cpp:129-188), element access through functors
+// ------------------------------------------------------------------------------------------
+template <class FA, class FB, class FW>
+__device__ __forceinline__ double sim_corr(int n, FA A, FB B, FW W) {
+    double prod = 0.0, varA = 0.0, varB = 0.0, meanA = 0.0, meanB = 0.0, sum = 0.0;
+    for (int i = 0; i < n; ++i) sum += W(i);
+    for (int i = 0; i < n; ++i) {
+        const double w = W(i);
+        meanA += w * A(i);
+        meanB += w * B(i);
+    }
+    if (sum > 0.0) { meanA /= sum; meanB /= sum; }
+    for (int i = 0; i < n; ++i) {
+        const double w = W(i), a = A(i) - meanA, b = B(i) - meanB;
+        prod += w * a * b;
+        varA += w * a * a;
+        varB += w * b * b;
+    }
+    if (sum > 0.0) { prod /= sum; varA /= sum; varB /= sum; }
+    if (varA == 0.0 || varB == 0.0) return 0.0;
+    return prod / (sqrt(varA) * sqrt(varB));
+}
+template <class FA, class FB, class FW>
+__device__ __forceinline__ double sim_ssd(int n, FA A, FB B, FW W) {
+    double prod = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const double d = A(i) - B(i);
+        prod += W(i) * d * d;
+    }
+    return sqrt(prod) / n;
+}
+template <class FA, class FB, class FW>
+__device__ __forceinline__ double sim_for_min(int simmeasure, int n, FA A, FB B, FW W) {
+    if (simmeasure == 1) return sim_ssd(n, A, B, W);
+    if (simmeasure == 2) return 1 - (1 + sim_corr(n, A, B, W)) * 0.5;
+    return nan("");
+}
+
+} // namespace msm

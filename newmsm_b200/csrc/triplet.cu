@@ -1,0 +1,419 @@
+// Triplet (higher-order clique) costs: the strain regulariser and the HO likelihoods.
+//
+// Reference behaviour restated (msm-newmeshreg/src):
+//   NonLinearSRegDiscreteCostFunction::computeTripletCost       DiscreteCostFunction.cpp:135-188 (regoption 2/3: spherical strain)
+//   HOUnivariate / HOMultivariate get_source_data                cpp:468-485, 541-563  (patch = sources whose nearest CP-grid triangle it is)
+//   HOUnivariate / HOMultivariate get_target_data + likelihood   cpp:487-531, 565-618
+//   calculate_triangular_strain / triangle_strain / calculate_tri reg_tools.cpp:698-743, 551-646, 267-313
+// called by Fusion::optimize with 8 label combinations per triplet and candidate label (Fusion.h:181-196).
+//
+// The 2x2 / 3x3 NEWMAT algebra of the regulariser is written out (2x2 inverse by adjugate over determinant,
+// 3x3 determinant by first-row cofactors, products summed left to right). FSL's NEWMAT is not part of the
+// reference tree, so parity for this part is against the CPU restatement of the test suite ("parity unpinned").
+//
+// Work decomposition: one warp per request (triplet, la, lb, lc). HO kinds: the lanes, in groups of G, move
+// the triangle's source points with the barycentric blend of the three displaced control points, locate them
+// on the target (query.cuh) and park (ids, weights) in the warp's shared-memory slice; similarity sums are the
+// reference's sequential FP64 sums (cost.cuh). Lane 0 evaluates the strain energy.
+#include "cost.cuh"
+
+#include <algorithm>
+
+namespace msm {
+
+// ------------------------------------------------------------------------------------------
+// strain energy
+// ------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ V3 tri_normal(const V3& v0, const V3& v1, const V3& v2) {   // triangle.cpp:42-47
+    return vnormalized(vcross(vsub(v2, v0), vsub(v1, v0)));
+}
+
+__host__ __device__ __forceinline__ void tangents(const V3& a, V3& e1, V3& e2) {   // reg_tools.cpp:267-313
+    V3 b{1.0, 0.0, 0.0};
+    V3 c = vcross(a, b);
+    double len = c.x * c.x + c.y * c.y + c.z * c.z;
+    if (len == 0.0) {
+        b = V3{0.0, 1.0, 0.0};
+        c = vcross(a, b);
+        len = c.x * c.x + c.y * c.y + c.z * c.z;
+    }
+    len = sqrt(len);
+    if (len == 0.0) len = 1;
+    e1 = V3{c.x / len, c.y / len, c.z / len};
+    b = vcross(a, c);
+    len = sqrt(b.x * b.x + b.y * b.y + b.z * b.z);
+    if (len == 0) len = 1;
+    e2 = V3{b.x / len, b.y / len, b.z / len};
+}
+
+__host__ __device__ __forceinline__ double det3(const double* m) {
+    return m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+}
+
+// x^e; the two exponents every shipped config uses (2 and 1) are exact products, so they match a correctly
+// rounded pow() bit for bit; other exponents use CUDA's pow (<= 2 ulp from glibc's)
+__device__ __forceinline__ double pow_cfg(double x, double e) {
+    if (e == 2.0) return x * x;
+    if (e == 1.0) return x;
+    return pow(x, e);
+}
+
+__device__ double triangle_strain_dev(const double* AA, const double* BB, double MU, double KAPPA, double k_exp) {   // reg_tools.cpp:551-646
+    const double c0 = AA[3] - AA[0], c1 = AA[4] - AA[1], c4 = AA[6] - AA[0], c5 = AA[7] - AA[1];
+    const double c0c = BB[3] - BB[0], c1c = BB[4] - BB[1], c4c = BB[6] - BB[0], c5c = BB[7] - BB[1];
+    const double det = c0 * c5 - c4 * c1;
+    const double i11 = c5 / det, i12 = -c4 / det, i21 = -c1 / det, i22 = c0 / det;
+    const double F11 = c0c * i11 + c4c * i21, F12 = c0c * i12 + c4c * i22;
+    const double F21 = c1c * i11 + c5c * i21, F22 = c1c * i12 + c5c * i22;
+    const double G11 = F11 * F11 + F21 * F21 + 0.0 * 0.0, G12 = F11 * F12 + F21 * F22 + 0.0 * 0.0;
+    const double G21 = F12 * F11 + F22 * F21 + 0.0 * 0.0, G22 = F12 * F12 + F22 * F22 + 0.0 * 0.0;
+    const double G33 = 0.0 * 0.0 + 0.0 * 0.0 + 1.0 * 1.0;
+    const double I1 = G11 + G22 + G33;
+    const double g[9] = {G11, G12, 0.0, G21, G22, 0.0, 0.0, 0.0, G33};
+    const double I3 = det3(g);
+    const double J = sqrt(I3);
+    const double I1st_new = (I1 - 1.0) / J;
+    double R;
+    if (I1st_new <= 2) R = 1.0;
+    else R = 0.5 * (I1st_new + sqrt(I1st_new * I1st_new - 4));
+    const double Rshared = pow_cfg(R, k_exp), Jshared = pow_cfg(J, k_exp);
+    return 0.5 * (MU * (Rshared + 1.0 / Rshared - 2) + KAPPA * (Jshared + 1.0 / Jshared - 2));
+}
+
+__device__ double triangular_strain_dev(const V3* O, const V3* F, double mu, double kappa, double k_exp) {   // reg_tools.cpp:698-743
+    const V3 NO = tri_normal(O[0], O[1], O[2]), NF = tri_normal(F[0], F[1], F[2]);
+    V3 e1, e2, f1, f2;
+    tangents(NO, e1, e2);
+    tangents(NF, f1, f2);
+    double TR[9] = {e1.x, e2.x, NO.x, e1.y, e2.y, NO.y, e1.z, e2.z, NO.z};     // form_matrix_from_points, point.cpp:77-95
+    double TR2[9] = {f1.x, f2.x, NF.x, f1.y, f2.y, NF.y, f1.z, f2.z, NF.z};
+    if (det3(TR) < 0) {
+        double t;
+        t = TR[0]; TR[0] = TR[1]; TR[1] = t; t = TR[3]; TR[3] = TR[4]; TR[4] = t; t = TR[6]; TR[6] = TR[7]; TR[7] = t;
+    }
+    if (det3(TR) < 0) {   // sic: the reference tests TRANS a second time (reg_tools.cpp:722)
+        double t;
+        t = TR2[0]; TR2[0] = TR2[1]; TR2[1] = t; t = TR2[3]; TR2[3] = TR2[4]; TR2[4] = t; t = TR2[6]; TR2[6] = TR2[7]; TR2[7] = t;
+    }
+    double A[9], B[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            A[3 * i + j] = O[i].x * TR[j] + O[i].y * TR[3 + j] + O[i].z * TR[6 + j];
+            B[3 * i + j] = F[i].x * TR2[j] + F[i].y * TR2[3 + j] + F[i].z * TR2[6 + j];
+        }
+    return triangle_strain_dev(A, B, mu, kappa, k_exp);
+}
+
+// ------------------------------------------------------------------------------------------
+// HO patches: group the source vertices by their nearest CP-grid triangle, ascending source id
+// ------------------------------------------------------------------------------------------
+__global__ void k_count_keys(int n, const int* __restrict__ key, int* __restrict__ cnt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && key[i] >= 0) atomicAdd(cnt + key[i], 1);
+}
+__global__ void k_fill_keys(int n, const int* __restrict__ key, const int* __restrict__ ptr, int* __restrict__ cursor, int* __restrict__ ids) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && key[i] >= 0) ids[ptr[key[i]] + atomicAdd(cursor + key[i], 1)] = i;
+}
+__global__ void k_sort_segments(int nkeys, const int* __restrict__ ptr, int* __restrict__ ids, int* __restrict__ max_len) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nkeys) return;
+    const int b = ptr[k], e = ptr[k + 1];
+    for (int i = b + 1; i < e; ++i) {
+        const int v = ids[i];
+        int j = i - 1;
+        while (j >= b && ids[j] > v) { ids[j + 1] = ids[j]; --j; }
+        ids[j + 1] = v;
+    }
+    atomicMax(max_len, e - b);
+}
+
+// ------------------------------------------------------------------------------------------
+// triplet cost kernel
+// ------------------------------------------------------------------------------------------
+struct TripletArgs {
+    TreeView tree;
+    int kind, simmeasure, ncp, nsrc, D, cfw_rows, n, max_patch;
+    const int* triplets;      // [ntrip][3]
+    const int* req_t;         // [n] or NULL (then request r = 8 * triplet + combo, Fusion.h:181-196)
+    const int* req_la; const int* req_lb; const int* req_lc;
+    const int* labeling;      // [ncp] (combo mode)
+    int label;                // candidate label (combo mode)
+    const double* labels;     // [L][3]
+    const double* rot;        // [ncp][9]
+    const double* cp_xyz;     // [ncp][3] current control points (_CPgrid)
+    const double* orig_xyz;   // [ncp][3] _ORIG
+    const double* src_xyz; const int* prow; const int* pmem;
+    const double* src_feat; const double* ref_feat; const double* cfw; const double* absw;
+    double lambda, mu, kappa, k_exp, rexp;
+    double* out;              // [n]
+    int* err;
+};
+
+constexpr int kTripWarps = 4;
+
+template <int G>
+__global__ void __launch_bounds__(kTripWarps * 32) k_triplet_costs(TripletArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * kTripWarps + warp;
+    if (r >= a.n) return;
+    // per-warp slice: w[max_patch][3] doubles | sim[max_patch] doubles | idx[max_patch][3] ints
+    const size_t slice = (size_t)a.max_patch * (4 * sizeof(double) + 3 * sizeof(int));
+    unsigned char* base = smem_raw + (size_t)warp * ((slice + 15) & ~(size_t)15);
+    double* s_w = reinterpret_cast<double*>(base);
+    double* s_sim = s_w + 3 * (size_t)a.max_patch;
+    int* s_idx = reinterpret_cast<int*>(s_sim + a.max_patch);
+
+    int t, lab[3];
+    if (a.req_t) {
+        t = a.req_t[r];
+        lab[0] = a.req_la[r]; lab[1] = a.req_lb[r]; lab[2] = a.req_lc[r];
+    } else {
+        t = r >> 3;
+        const int combo = r & 7;
+        for (int k = 0; k < 3; ++k) lab[k] = (combo >> (2 - k)) & 1 ? a.label : a.labeling[a.triplets[3 * (size_t)t + k]];
+    }
+    V3 def[3], cur[3], org[3];
+    int ids[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        ids[k] = a.triplets[3 * (size_t)t + k];
+        const double* lb = a.labels + 3 * (size_t)lab[k];
+        def[k] = mat_apply(a.rot + 9 * (size_t)ids[k], V3{lb[0], lb[1], lb[2]});        // (*ROTATIONS)[node] * _labels[label], cpp:140-142
+        cur[k] = load_pt(a.cp_xyz, ids[k]);
+        org[k] = load_pt(a.orig_xyz, ids[k]);
+    }
+    // only estimate the cost if it does not cause folding (cpp:152)
+    if (vdot(tri_normal(def[0], def[1], def[2]), tri_normal(cur[0], cur[1], cur[2])) < 0.0) {
+        if (lane == 0) a.out[r] = 1e7 * a.lambda;
+        return;
+    }
+    double likelihood = 0.0;
+    if (a.kind >= MSMGPU_COST_HO_UNIVARIATE) {   // warp-uniform
+        const int p0 = a.prow[t], P = a.prow[t + 1] - p0;
+        const int gl = lane % G;
+        int bad = 0;
+        for (int i0 = 0; i0 < P; i0 += 32 / G) {
+            const int i = i0 + lane / G;
+            const bool active = i < P;
+            V3 tmp{0, 0, 0};
+            if (active) {   // cpp:503-506: project onto the CP triangle, blend with the displaced CPs, back to the sphere
+                const int sv = __ldg(a.pmem + p0 + i);
+                const V3 SP = project_to_plane(load_pt(a.src_xyz, sv), cur[0], cur[1], cur[2]);
+                double w[3];
+                bary_weights_raw(SP, cur[0], cur[1], cur[2], w);
+                const V3 x = vscale(def[0], w[0]), y = vscale(def[1], w[1]), z = vscale(def[2], w[2]);   // triangle.cpp:169
+                tmp = V3{x.x + y.x + z.x, x.y + y.y + z.y, x.z + y.z + z.z};
+                tmp = vnormalized(tmp);
+                tmp = vscale(tmp, kRad);
+            }
+            int st;
+            const int tt = nearest_triangle<G>(a.tree, tmp, active, gl, st);
+            if (active && gl == 0) {
+                if (tt < 0) {
+                    bad = 1;
+                } else {
+                    const double* v = a.tree.rec[tt].v;
+                    double w[3];
+                    bary_weights_raw(tmp, V3{v[0], v[1], v[2]}, V3{v[3], v[4], v[5]}, V3{v[6], v[7], v[8]}, w);
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        s_w[3 * i + j] = w[j];
+                        s_idx[3 * i + j] = __ldg(a.tree.tri + 3 * (size_t)tt + j);
+                    }
+                }
+            }
+        }
+        if (__any_sync(kFull, bad)) {
+            if (lane == 0) { a.out[r] = nan(""); *a.err = 1; }
+            return;
+        }
+        __syncwarp();
+        const int D = a.D;
+        const double* __restrict__ rf = a.ref_feat;
+        const double* __restrict__ sf = a.src_feat;
+        auto tgt = [&](int i, int d) -> double {
+            return s_w[3 * i] * __ldg(rf + (size_t)s_idx[3 * i] * D + d) + s_w[3 * i + 1] * __ldg(rf + (size_t)s_idx[3 * i + 1] * D + d) +
+                   s_w[3 * i + 2] * __ldg(rf + (size_t)s_idx[3 * i + 2] * D + d);
+        };
+        auto srcv = [&](int i) -> int { return __ldg(a.pmem + p0 + i); };
+        const int cr = a.cfw_rows;
+        double cost = 0.0;
+        if (a.kind == MSMGPU_COST_HO_UNIVARIATE) {   // cpp:522-531
+            for (int i = lane; i < P; i += 32) s_sim[i] = tgt(i, 0);
+            __syncwarp();
+            if (lane == 0)
+                cost = sim_for_min(a.simmeasure, P, [&](int i) { return __ldg(sf + (size_t)srcv(i) * D); }, [&](int i) { return s_sim[i]; },
+                                   [&](int i) { return cr >= 1 ? __ldg(a.cfw + (size_t)srcv(i) * cr) : 1.0; });
+        } else {   // cpp:601-618
+            for (int i = lane; i < P; i += 32) {
+                const int sv = srcv(i);
+                s_sim[i] = sim_for_min(a.simmeasure, D, [&](int d) { return __ldg(sf + (size_t)sv * D + d); }, [&](int d) { return tgt(i, d); },
+                                       [&](int d) { return cr >= d + 1 ? __ldg(a.cfw + (size_t)sv * cr + d) : 1.0; });
+            }
+            __syncwarp();
+            if (lane == 0) {
+                for (int i = 0; i < P; ++i) cost += s_sim[i];
+                if (P > 0) cost /= P;
+            }
+        }
+        if (lane == 0) likelihood = (__ldg(a.absw + ids[0]) + __ldg(a.absw + ids[1]) + __ldg(a.absw + ids[2])) / 3.0 * cost;
+    }
+    if (lane == 0) {   // regoption 2/3 (cpp:158-166), then cpp:187
+        const double W = triangular_strain_dev(org, def, a.mu, a.kappa, a.k_exp);
+        a.out[r] = likelihood + a.lambda * pow_cfg(W, a.rexp);
+    }
+}
+
+template <int G>
+static msmgpu_status launch_triplet_g(const TripletArgs& a, size_t smem, cudaStream_t s) {
+    if (smem > 48 * 1024) MSM_CUDA(cudaFuncSetAttribute(k_triplet_costs<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_triplet_costs<G><<<(unsigned)((a.n + kTripWarps - 1) / kTripWarps), kTripWarps * 32, smem, s>>>(a);
+    MSM_LAUNCH_CHECK();
+    return MSMGPU_OK;
+}
+
+template <typename T>
+static msmgpu_status up(DevBuf<T>& b, const T* host, size_t n, cudaStream_t s) {
+    MSM_CUDA(b.alloc(n, s));
+    if (n) MSM_CUDA(cudaMemcpyAsync(b.p, host, n * sizeof(T), cudaMemcpyHostToDevice, s));
+    return MSMGPU_OK;
+}
+
+static msmgpu_status triplet_run(msmgpu_costfn* c, int ntrip, const int32_t* triplets, int L, const double* labels, const double* rotations,
+                                 const double* orig_cp_xyz, const msmgpu_reg_params* prm, int n, const int32_t* req_t, const int32_t* req_la,
+                                 const int32_t* req_lb, const int32_t* req_lc, const int32_t* labeling, int label, double* out) {
+    if (!c || ntrip <= 0 || !triplets || L <= 0 || !labels || !rotations || !orig_cp_xyz || !prm || n <= 0 || !out)
+        return fail(MSMGPU_ERR_INVALID, "costfn_triplet: bad arguments");
+    if (c->ncp <= 0) return fail(MSMGPU_ERR_INVALID, "costfn_triplet: set the control-point grid first");
+    if (prm->rmode != 2 && prm->rmode != 3)
+        return fail(MSMGPU_ERR_INVALID, "DiscreteModel computeTripletCost regoption does not exist");   // cpp:183 (4/5 need anatomical meshes: not accelerated)
+    const bool ho = c->kind >= MSMGPU_COST_HO_UNIVARIATE;
+    if (ho && c->n_patch_rows != ntrip) return fail(MSMGPU_ERR_INVALID, "costfn_triplet: HO patches were built for a different CP-grid triangle count");
+    MSM_CUDA(cudaSetDevice(c->ctx->device));
+    cudaStream_t s = c->ctx->stream;
+    DevBuf<int> d_trip, d_rt, d_la, d_lb, d_lc, d_labeling, d_err;
+    DevBuf<double> d_labels, d_rot, d_orig, d_out;
+    MSM_TRY(up(d_trip, triplets, 3 * (size_t)ntrip, s));
+    MSM_TRY(up(d_labels, labels, 3 * (size_t)L, s));
+    MSM_TRY(up(d_rot, rotations, 9 * (size_t)c->ncp, s));
+    MSM_TRY(up(d_orig, orig_cp_xyz, 3 * (size_t)c->ncp, s));
+    if (req_t) {
+        MSM_TRY(up(d_rt, req_t, (size_t)n, s));
+        MSM_TRY(up(d_la, req_la, (size_t)n, s));
+        MSM_TRY(up(d_lb, req_lb, (size_t)n, s));
+        MSM_TRY(up(d_lc, req_lc, (size_t)n, s));
+    } else {
+        MSM_TRY(up(d_labeling, labeling, (size_t)c->ncp, s));
+    }
+    MSM_CUDA(d_out.alloc((size_t)n, s));
+    MSM_CUDA(d_err.alloc(1, s));
+    MSM_CUDA(cudaMemsetAsync(d_err.p, 0, sizeof(int), s));
+    TripletArgs a;
+    a.tree = c->tree->view();
+    a.kind = c->kind; a.simmeasure = c->simmeasure; a.ncp = c->ncp; a.nsrc = c->nsrc; a.D = c->D; a.cfw_rows = c->cfw_rows; a.n = n;
+    a.max_patch = ho ? std::max(c->max_patch, 1) : 1;
+    a.triplets = d_trip.p; a.req_t = req_t ? d_rt.p : nullptr; a.req_la = d_la.p; a.req_lb = d_lb.p; a.req_lc = d_lc.p;
+    a.labeling = d_labeling.p; a.label = label; a.labels = d_labels.p; a.rot = d_rot.p; a.cp_xyz = c->cp_xyz.p; a.orig_xyz = d_orig.p;
+    a.src_xyz = c->src_xyz.p; a.prow = c->prow.p; a.pmem = c->pmem.p; a.src_feat = c->src_feat.p; a.ref_feat = c->ref_feat.p;
+    a.cfw = c->cfw.p; a.absw = c->absw.p;
+    a.lambda = prm->lambda; a.mu = prm->shear_modulus; a.kappa = prm->bulk_modulus; a.k_exp = prm->k_exponent; a.rexp = prm->exponent;
+    a.out = d_out.p; a.err = d_err.p;
+    const size_t slice = ((size_t)a.max_patch * (4 * sizeof(double) + 3 * sizeof(int)) + 15) & ~(size_t)15;
+    const size_t smem = slice * kTripWarps;
+    if (smem > 200 * 1024) return fail(MSMGPU_ERR_CAPACITY, "costfn_triplet: patch too large for shared memory");
+    switch (query_group_width()) {
+        case 2: MSM_TRY(launch_triplet_g<2>(a, smem, s)); break;
+        case 4: MSM_TRY(launch_triplet_g<4>(a, smem, s)); break;
+        case 8: MSM_TRY(launch_triplet_g<8>(a, smem, s)); break;
+        case 16: MSM_TRY(launch_triplet_g<16>(a, smem, s)); break;
+        case 32: MSM_TRY(launch_triplet_g<32>(a, smem, s)); break;
+        default: MSM_TRY(launch_triplet_g<1>(a, smem, s)); break;
+    }
+    int h_err = 0;
+    MSM_CUDA(cudaMemcpyAsync(out, d_out.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    MSM_CUDA(cudaMemcpyAsync(&h_err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MSM_CUDA(cudaStreamSynchronize(s));
+    if (h_err) return status_to_error(MSMGPU_ERR_NO_TRIANGLE);
+    return MSMGPU_OK;
+}
+
+} // namespace msm
+
+using namespace msm;
+
+extern "C" {
+
+msmgpu_status msmgpu_costfn_set_cpgrid_ho(msmgpu_costfn* c, int ncp, const double* cp_xyz, int ntri, const int32_t* cp_tri,
+                                          int cfw_rows, const double* cfw, const double* absw) {
+    if (!c || ncp <= 0 || !cp_xyz || ntri <= 0 || !cp_tri || !absw || cfw_rows < 0 || (cfw_rows > 0 && !cfw))
+        return fail(MSMGPU_ERR_INVALID, "costfn_set_cpgrid_ho: bad arguments");
+    if (c->kind < MSMGPU_COST_HO_UNIVARIATE) return fail(MSMGPU_ERR_INVALID, "costfn_set_cpgrid_ho: not an HO cost function");
+    MSM_CUDA(cudaSetDevice(c->ctx->device));
+    cudaStream_t s = c->ctx->stream;
+    c->ncp = ncp; c->cfw_rows = cfw_rows;
+    c->h_cp.assign(cp_xyz, cp_xyz + 3 * (size_t)ncp);
+    MSM_TRY(up(c->cp_xyz, cp_xyz, 3 * (size_t)ncp, s));
+    MSM_TRY(up(c->absw, absw, (size_t)ncp, s));
+    if (cfw_rows > 0) {
+        DevBuf<double> cm;
+        MSM_TRY(up(cm, cfw, (size_t)cfw_rows * c->nsrc, s));
+        MSM_CUDA(c->cfw.alloc((size_t)cfw_rows * c->nsrc, s));
+        MSM_TRY(launch_transpose_f64(cfw_rows, c->nsrc, cm.p, c->cfw.p, s));
+        MSM_CUDA(cudaStreamSynchronize(s));
+    }
+    // newresampler::Octree cp_tree(_CPgrid); closest triangle of every source vertex (cpp:472-476)
+    msmgpu_mesh* cpm = nullptr;
+    MSM_TRY(msmgpu_mesh_create(c->ctx, ncp, cp_xyz, ntri, cp_tri, &cpm));
+    std::unique_ptr<msmgpu_mesh, void (*)(msmgpu_mesh*)> mg(cpm, msmgpu_mesh_destroy);
+    msmgpu_octree* cpt = nullptr;
+    MSM_TRY(msmgpu_octree_build(cpm, &cpt));
+    std::unique_ptr<msmgpu_octree, void (*)(msmgpu_octree*)> tg(cpt, msmgpu_octree_destroy);
+    DevBuf<int> key, st, cnt, cursor, d_max;
+    MSM_CUDA(key.alloc(c->nsrc, s));
+    MSM_CUDA(st.alloc(c->nsrc, s));
+    MSM_CUDA(cnt.alloc(ntri, s));
+    MSM_CUDA(cursor.alloc(ntri, s));
+    MSM_CUDA(d_max.alloc(1, s));
+    MSM_TRY(launch_nearest(cpt->view(), c->nsrc, c->src_xyz.p, key.p, nullptr, st.p, s));
+    int code = 0;
+    MSM_TRY(first_error(st.p, c->nsrc, s, &code));
+    if (code) return status_to_error(code);
+    MSM_CUDA(cudaMemsetAsync(cnt.p, 0, ntri * sizeof(int), s));
+    MSM_CUDA(cudaMemsetAsync(cursor.p, 0, ntri * sizeof(int), s));
+    MSM_CUDA(cudaMemsetAsync(d_max.p, 0, sizeof(int), s));
+    MSM_CUDA(c->prow.alloc((size_t)ntri + 1, s));
+    MSM_CUDA(c->pmem.alloc((size_t)c->nsrc, s));
+    const unsigned gs = (unsigned)((c->nsrc + 255) / 256), gk = (unsigned)((ntri + 255) / 256);
+    k_count_keys<<<gs, 256, 0, s>>>(c->nsrc, key.p, cnt.p);
+    MSM_LAUNCH_CHECK();
+    MSM_TRY(exclusive_scan_i32(cnt.p, c->prow.p, ntri, c->prow.p + ntri, s));
+    k_fill_keys<<<gs, 256, 0, s>>>(c->nsrc, key.p, c->prow.p, cursor.p, c->pmem.p);
+    MSM_LAUNCH_CHECK();
+    k_sort_segments<<<gk, 256, 0, s>>>(ntri, c->prow.p, c->pmem.p, d_max.p);
+    MSM_LAUNCH_CHECK();
+    MSM_CUDA(cudaMemcpyAsync(&c->max_patch, d_max.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MSM_CUDA(cudaStreamSynchronize(s));
+    c->n_patch = c->nsrc;
+    c->n_patch_rows = ntri;
+    c->n_cp_tri = ntri;
+    return MSMGPU_OK;
+}
+
+msmgpu_status msmgpu_costfn_triplet_costs(msmgpu_costfn* c, int ntrip, const int32_t* triplets, int L, const double* labels, const double* rotations,
+                                          const double* orig_cp_xyz, const msmgpu_reg_params* prm, int n, const int32_t* req_triplet,
+                                          const int32_t* req_la, const int32_t* req_lb, const int32_t* req_lc, double* out) {
+    if (!req_triplet || !req_la || !req_lb || !req_lc) return fail(MSMGPU_ERR_INVALID, "costfn_triplet_costs: bad arguments");
+    return triplet_run(c, ntrip, triplets, L, labels, rotations, orig_cp_xyz, prm, n, req_triplet, req_la, req_lb, req_lc, nullptr, 0, out);
+}
+
+msmgpu_status msmgpu_costfn_triplet_batch(msmgpu_costfn* c, int ntrip, const int32_t* triplets, int L, const double* labels, const double* rotations,
+                                          const double* orig_cp_xyz, const msmgpu_reg_params* prm, const int32_t* labeling, int label, double* out) {
+    if (!labeling || label < 0 || label >= L) return fail(MSMGPU_ERR_INVALID, "costfn_triplet_batch: bad arguments");
+    return triplet_run(c, ntrip, triplets, L, labels, rotations, orig_cp_xyz, prm, 8 * ntrip, nullptr, nullptr, nullptr, nullptr, labeling, label, out);
+}
+
+} // extern "C"

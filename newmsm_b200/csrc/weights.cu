@@ -514,6 +514,25 @@ msmgpu_status msmgpu_metric_resample(msmgpu_mesh* in_mesh, msmgpu_mesh* low_mesh
     return MSMGPU_OK;
 }
 
+// metric_resample of the mesh's RESIDENT features (msmgpu_mesh_set_features_f32): no feature upload
+msmgpu_status msmgpu_mesh_metric_resample_f32(msmgpu_mesh* in_mesh, msmgpu_octree* in_tree, msmgpu_mesh* low_mesh, msmgpu_octree* low_tree, float* feat_out) {
+    if (!in_mesh || !low_mesh || !feat_out) return fail(MSMGPU_ERR_INVALID, "mesh_metric_resample_f32: bad arguments");
+    if (in_mesh->feat_D <= 0) return fail(MSMGPU_ERR_INVALID, "mesh_metric_resample_f32: the mesh has no resident features (msmgpu_mesh_set_features_f32)");
+    msmgpu_weights* W = nullptr;
+    MSM_TRY(msmgpu_adaptive_weights_ex(in_mesh, in_tree, low_mesh, low_tree, &W));
+    std::unique_ptr<msmgpu_weights> guard(W);
+    cudaStream_t s = in_mesh->ctx->stream;
+    const int D = in_mesh->feat_D, nl = low_mesh->nv;
+    DevBuf<float> rows_out, cm_out;
+    MSM_CUDA(rows_out.alloc((size_t)D * nl, s));
+    MSM_CUDA(cm_out.alloc((size_t)D * nl, s));
+    MSM_TRY(csr_apply_f32(W, D, in_mesh->feat.p, rows_out.p));
+    MSM_TRY(launch_rows_f32_to_chmajor_f32(D, nl, rows_out.p, cm_out.p, s));
+    MSM_CUDA(cudaMemcpyAsync(feat_out, cm_out.p, (size_t)D * nl * sizeof(float), cudaMemcpyDeviceToHost, s));
+    MSM_CUDA(cudaStreamSynchronize(s));
+    return MSMGPU_OK;
+}
+
 // FP32 payload (what GIFTI stores, mesh.cpp:625): channel-major host floats, optional pre-built trees
 msmgpu_status msmgpu_metric_resample_f32(msmgpu_mesh* in_mesh, msmgpu_octree* in_tree, msmgpu_mesh* low_mesh, msmgpu_octree* low_tree,
                                          int D, const float* feat_in, float* feat_out) {

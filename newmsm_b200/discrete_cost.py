@@ -15,7 +15,7 @@ from .resampler import Mesh, Octree
 
 MeshregException = capi.MsmGpuError   # reg_tools.h:38
 
-UNIVARIATE, MULTIVARIATE, PATCHWISE = 0, 1, 2
+UNIVARIATE, MULTIVARIATE, PATCHWISE, HO_UNIVARIATE, HO_MULTIVARIATE = 0, 1, 2, 3, 4
 SSD, CORRELATION = 1, 2   # similarities.h:48-58 (_simmeasure)
 
 
@@ -79,6 +79,37 @@ class NonLinearSRegDiscreteCostFunction:
     def computeUnaryCost(self, node: int, label: int) -> float:
         return float(self.unarycosts[label, node])
 
+    # set_parameters (cpp:119-133): the regulariser part
+    def set_parameters(self, lambda_: float, shearmodulus: float = 0.4, bulkmodulus: float = 1.6, kexponent: float = 2.0,
+                       exponent: float = 2.0, regularisermode: int = 3):
+        self.reg = capi.RegParams(lambda_, shearmodulus, bulkmodulus, kexponent, exponent, regularisermode)
+
+    # setTriplets (h:57) + the state computeTripletCost reads: ROTATIONS, _labels, _ORIG
+    def setTriplets(self, triplets, labels, ROTATIONS, ORIG_xyz):
+        self.triplets = capi.i32(triplets).reshape(-1, 3)
+        self._labels = f64(labels).reshape(-1, 3)
+        self._rot = f64(ROTATIONS).reshape(-1, 9)
+        self._orig = f64(ORIG_xyz).reshape(-1, 3)
+
+    def computeTripletCostList(self, triplet, la, lb, lc):
+        """computeTripletCost (cpp:135-188) for arrays of requests."""
+        t, a, b, c_ = (capi.i32(x) for x in (triplet, la, lb, lc))
+        out = np.zeros(len(t))
+        check(self.L.msmgpu_costfn_triplet_costs(self.h, len(self.triplets), ptr(self.triplets), len(self._labels), ptr(self._labels), ptr(self._rot),
+                                                 ptr(self._orig), C.byref(self.reg), len(t), ptr(t), ptr(a), ptr(b), ptr(c_), ptr(out)))
+        return out
+
+    def computeTripletCost(self, triplet: int, labelA: int, labelB: int, labelC: int) -> float:
+        return float(self.computeTripletCostList([triplet], [labelA], [labelB], [labelC])[0])
+
+    def computeTripletCostsForLabel(self, labeling, label: int):
+        """The 8 combinations per triplet Fusion::optimize evaluates for one candidate label (Fusion.h:181-196) -> [T, 8]."""
+        lab = capi.i32(labeling)
+        out = np.zeros((len(self.triplets), 8))
+        check(self.L.msmgpu_costfn_triplet_batch(self.h, len(self.triplets), ptr(self.triplets), len(self._labels), ptr(self._labels), ptr(self._rot),
+                                                 ptr(self._orig), C.byref(self.reg), ptr(lab), int(label), ptr(out)))
+        return out
+
     def getUnaryCosts(self):
         return self.unarycosts.reshape(-1)
 
@@ -92,6 +123,33 @@ class NonLinearSRegDiscreteCostFunction:
             self.close()
         except Exception:
             pass
+
+
+class _HOMixin:
+    """HO (triclique) classes: patches hang on CP-grid triangles (cpp:468-485, 541-563)."""
+
+    def reset_CPgrid(self, cp_xyz, cp_tri, HIGHREScfweight=None, AbsoluteWeights=None):   # noqa: N803
+        cp, tri = f64(cp_xyz), capi.i32(cp_tri)
+        self.ncp = len(cp)
+        self.n_cp_tri = len(tri)
+        absw = np.ones(self.ncp) if AbsoluteWeights is None else f64(AbsoluteWeights)
+        cfw = None if HIGHREScfweight is None else f64(np.atleast_2d(HIGHREScfweight))
+        check(self.L.msmgpu_costfn_set_cpgrid_ho(self.h, self.ncp, ptr(cp), len(tri), ptr(tri), 0 if cfw is None else cfw.shape[0], ptr(cfw), ptr(absw)))
+
+    def get_source_data(self):
+        rowptr = np.zeros(self.n_cp_tri + 1, np.int32)
+        check(self.L.msmgpu_costfn_patches(self.h, ptr(rowptr), None))
+        mem = np.zeros(int(rowptr[-1]), np.int32)
+        check(self.L.msmgpu_costfn_patches(self.h, ptr(rowptr), ptr(mem)))
+        return rowptr, mem
+
+
+class HOUnivariateNonLinearSRegDiscreteCostFunction(_HOMixin, NonLinearSRegDiscreteCostFunction):
+    KIND = HO_UNIVARIATE
+
+
+class HOMultivariateNonLinearSRegDiscreteCostFunction(_HOMixin, NonLinearSRegDiscreteCostFunction):
+    KIND = HO_MULTIVARIATE
 
 
 class UnivariateNonLinearSRegDiscreteCostFunction(NonLinearSRegDiscreteCostFunction):

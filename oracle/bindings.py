@@ -81,6 +81,9 @@ class Oracle:
             L.orc_patch_membership.argtypes = [_i, _vp, _i, _vp, _vp, _d, _vp, _vp, _i, _i]
             L.orc_unary_costs.argtypes = [_i, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp,
                                           _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i]
+            L.orc_ho_patches.argtypes = [_i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i]
+            L.orc_triplet_costs.argtypes = [_i, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp,
+                                            _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _d, _d, _d, _d, _d, _vp, _i]
             cls._lib = L
         return cls._lib
 
@@ -227,6 +230,35 @@ def oracle_unary_costs(kind, simmeasure, tree: OracleOctree, cp_xyz, rot, labels
     if e:
         raise RuntimeError("oracle unary costs: a query failed")
     return (out, tri_out) if want_tri else out
+
+
+def oracle_ho_patches(cp_xyz, cp_tri, src_xyz):
+    cp, tri, s = _f64(cp_xyz), _i32(cp_tri), _f64(src_xyz)
+    rowptr, mem = np.zeros(len(tri) + 1, np.int32), np.zeros(len(s), np.int32)
+    n = Oracle.lib().orc_ho_patches(len(cp), _p(cp), len(tri), _p(tri), len(s), _p(s), _p(rowptr), _p(mem), len(s))
+    if n < 0:
+        raise RuntimeError("oracle HO patches: a query failed")
+    return rowptr, mem[:n].copy()
+
+
+def oracle_triplet_costs(kind, simmeasure, tree, cp_xyz, orig_cp_xyz, rot, labels, triplets, req_t, req_la, req_lb, req_lc,
+                         src_xyz, prow, pmem, src_feat, ref_feat, cfw, absw, lambda_, mu=0.4, kappa=1.6, k_exp=2.0, rexp=2.0, nthreads=8):
+    cp, org, rot, labels = _f64(cp_xyz), _f64(orig_cp_xyz), _f64(rot), _f64(labels)
+    trip = _i32(triplets)
+    rt, la, lb, lc = _i32(req_t), _i32(req_la), _i32(req_lb), _i32(req_lc)
+    src = _f64(src_xyz)
+    prow = _i32(prow) if prow is not None else np.zeros(len(trip) + 1, np.int32)
+    pmem = _i32(pmem) if pmem is not None else np.zeros(1, np.int32)
+    sf, rf, absw = _f64(np.atleast_2d(src_feat)), _f64(np.atleast_2d(ref_feat)), _f64(absw)
+    cfw_rows = 0 if cfw is None else np.atleast_2d(cfw).shape[0]
+    cfw_a = None if cfw is None else _f64(np.atleast_2d(cfw))
+    out = np.zeros(len(rt))
+    e = Oracle.lib().orc_triplet_costs(kind, simmeasure, tree.h if tree is not None else None, len(cp), _p(cp), _p(org), _p(rot), len(labels), _p(labels),
+                                       len(trip), _p(trip), len(rt), _p(rt), _p(la), _p(lb), _p(lc), len(src), _p(src), _p(prow), _p(pmem),
+                                       sf.shape[0], _p(sf), _p(rf), cfw_rows, _p(cfw_a), _p(absw), lambda_, mu, kappa, k_exp, rexp, _p(out), nthreads)
+    if e:
+        raise RuntimeError("oracle triplet costs: a query failed")
+    return out
 
 
 # --------------------------------------------------------------------------------------

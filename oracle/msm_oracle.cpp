@@ -683,3 +683,202 @@ int orc_unary_costs(int kind, int simmeasure, const orc_octree* T,
 }
 
 } // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Triplet costs: regulariser (strain) + HO likelihood. PARITY UNPINNED: the reference's meshreg
+// library cannot be compiled here (FSL NEWMAT/armawrap `.i()`, `Determinant()` and the FSL
+// BFMatrix/OptionParser stack are absent), so this is a restatement of
+// DiscreteCostFunction.cpp:135-188, 468-618 and reg_tools.cpp:267-313, 551-743 with the small
+// dense-matrix algebra written out (2x2 inverse by adjugate / determinant, 3x3 determinant by
+// first-row cofactors, products summed left to right).
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+inline P3 tri_normal(const P3& v0, const P3& v1, const P3& v2) { // triangle.cpp:42-47
+    P3 r = cross(sub(v2, v0), sub(v1, v0));
+    normalize(r);
+    return r;
+}
+
+struct Tangs { P3 e1, e2; };
+Tangs calculate_tri(const P3& a) { // reg_tools.cpp:267-313
+    Tangs T;
+    P3 b{1.0, 0.0, 0.0};
+    P3 c = cross(a, b);
+    double len = c.X * c.X + c.Y * c.Y + c.Z * c.Z;
+    if (len == 0.0) {
+        b = P3{0.0, 1.0, 0.0};
+        c = cross(a, b);
+        len = c.X * c.X + c.Y * c.Y + c.Z * c.Z;
+    }
+    len = std::sqrt(len);
+    if (len == 0.0) len = 1;
+    T.e1 = P3{c.X / len, c.Y / len, c.Z / len};
+    b = cross(a, c);
+    len = std::sqrt(b.X * b.X + b.Y * b.Y + b.Z * b.Z);
+    if (len == 0) len = 1;
+    T.e2 = P3{b.X / len, b.Y / len, b.Z / len};
+    return T;
+}
+
+inline double det3(const double* m) { // row-major 3x3, first-row cofactors
+    return m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+}
+
+// reg_tools.cpp:551-646 without the optional principal-strain output
+double triangle_strain(const double* AA, const double* BB, double MU, double KAPPA, double k_exp) { // AA, BB row-major 3x3, columns 1,2 used
+    const double c0 = AA[3] - AA[0], c1 = AA[4] - AA[1], c4 = AA[6] - AA[0], c5 = AA[7] - AA[1];
+    const double c0c = BB[3] - BB[0], c1c = BB[4] - BB[1], c4c = BB[6] - BB[0], c5c = BB[7] - BB[1];
+    // Edges = [c0 c4; c1 c5], edges = [c0c c4c; c1c c5c]; F = edges * Edges^-1
+    const double det = c0 * c5 - c4 * c1;
+    const double i11 = c5 / det, i12 = -c4 / det, i21 = -c1 / det, i22 = c0 / det;
+    const double F11 = c0c * i11 + c4c * i21, F12 = c0c * i12 + c4c * i22;
+    const double F21 = c1c * i11 + c5c * i21, F22 = c1c * i12 + c5c * i22;
+    // F3D = [F 0; 0 0 1]; F3D_2 = F3D^T F3D
+    const double G11 = F11 * F11 + F21 * F21 + 0.0 * 0.0, G12 = F11 * F12 + F21 * F22 + 0.0 * 0.0;
+    const double G21 = F12 * F11 + F22 * F21 + 0.0 * 0.0, G22 = F12 * F12 + F22 * F22 + 0.0 * 0.0;
+    const double G33 = 0.0 * 0.0 + 0.0 * 0.0 + 1.0 * 1.0;
+    const double I1 = G11 + G22 + G33;
+    const double g[9] = {G11, G12, 0.0, G21, G22, 0.0, 0.0, 0.0, G33};
+    const double I3 = det3(g);
+    const double J = std::sqrt(I3);
+    const double I1st_new = (I1 - 1.0) / J;
+    double R;
+    if (I1st_new <= 2) R = 1.0;
+    else R = 0.5 * (I1st_new + std::sqrt(I1st_new * I1st_new - 4));
+    const double Rshared = std::pow(R, k_exp), Jshared = std::pow(J, k_exp);
+    return 0.5 * (MU * (Rshared + 1.0 / Rshared - 2) + KAPPA * (Jshared + 1.0 / Jshared - 2));
+}
+
+// reg_tools.cpp:698-743 (Triangle overload)
+double triangular_strain(const P3* O, const P3* Fv, double mu, double kappa, double k_exp) {
+    const P3 NO = tri_normal(O[0], O[1], O[2]), NF = tri_normal(Fv[0], Fv[1], Fv[2]);
+    const Tangs T = calculate_tri(NO), T2 = calculate_tri(NF);
+    double TR[9] = {T.e1.X, T.e2.X, NO.X, T.e1.Y, T.e2.Y, NO.Y, T.e1.Z, T.e2.Z, NO.Z};     // point.cpp:77-95
+    double TR2[9] = {T2.e1.X, T2.e2.X, NF.X, T2.e1.Y, T2.e2.Y, NF.Y, T2.e1.Z, T2.e2.Z, NF.Z};
+    if (det3(TR) < 0) { std::swap(TR[0], TR[1]); std::swap(TR[3], TR[4]); std::swap(TR[6], TR[7]); }
+    if (det3(TR) < 0) { std::swap(TR2[0], TR2[1]); std::swap(TR2[3], TR2[4]); std::swap(TR2[6], TR2[7]); } // sic: tests TRANS again (reg_tools.cpp:722)
+    double A[9], B[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            A[3 * i + j] = O[i].X * TR[j] + O[i].Y * TR[3 + j] + O[i].Z * TR[6 + j];
+            B[3 * i + j] = Fv[i].X * TR2[j] + Fv[i].Y * TR2[3 + j] + Fv[i].Z * TR2[6 + j];
+        }
+    return triangle_strain(A, B, mu, kappa, k_exp);
+}
+
+inline P3 bary_blend(const P3& v1, const P3& v2, const P3& v3, const P3& vref, const P3& a1, const P3& a2, const P3& a3) { // triangle.cpp:159-170
+    double w[3];
+    bary_interp_weights(v1, v2, v3, vref, w);
+    const P3 x = mul(a1, w[0]), y = mul(a2, w[1]), z = mul(a3, w[2]);
+    return P3{x.X + y.X + z.X, x.Y + y.Y + z.Y, x.Z + y.Z + z.Z};
+}
+
+} // namespace
+
+extern "C" {
+
+// HO*::get_source_data (DiscreteCostFunction.cpp:468-485, 541-563): sources grouped by their nearest CP-grid triangle
+int orc_ho_patches(int ncp, const double* cp_xyz, int ntri, const int* cp_tri, int nsrc, const double* src_xyz,
+                   int* rowptr, int* members, int cap) {
+    orc_octree* T = build_tree(ncp, cp_xyz, ntri, cp_tri);
+    std::vector<std::vector<int>> lists(ntri);
+    int bad = 0;
+    for (int i = 0; i < nsrc; ++i) {
+        int st;
+        const int t = closest_triangle(T, P3{src_xyz[3 * i], src_xyz[3 * i + 1], src_xyz[3 * i + 2]}, &st, nullptr);
+        if (t < 0) { bad = 1; continue; }
+        lists[t].push_back(i);
+    }
+    delete T;
+    if (bad) return -1;
+    int pos = 0;
+    for (int k = 0; k < ntri; ++k) {
+        rowptr[k] = pos;
+        for (int i : lists[k]) { if (pos < cap) members[pos] = i; ++pos; }
+    }
+    rowptr[ntri] = pos;
+    return pos;
+}
+
+// computeTripletCost (DiscreteCostFunction.cpp:135-188) for n requests (triplet, la, lb, lc).
+// kind: 0..2 = non-HO classes (likelihood 0), 3 = HOUnivariate (cpp:487-531), 4 = HOMultivariate (cpp:565-618).
+// triplets [T][3] node ids; patches (HO kinds) CSR over triplets. rmode 2/3 only (spherical strain). Returns 0 or 2 (a query failed).
+int orc_triplet_costs(int kind, int simmeasure, const orc_octree* T, int ncp, const double* cp_xyz, const double* orig_cp_xyz,
+                      const double* rot, int L, const double* labels, int ntrip, const int* triplets,
+                      int n, const int* req_triplet, const int* req_la, const int* req_lb, const int* req_lc,
+                      int nsrc, const double* src_xyz, const int* prow, const int* pmem, int D, const double* src_feat,
+                      const double* ref_feat, int cfw_rows, const double* cfw, const double* absw,
+                      double lambda, double mu, double kappa, double k_exp, double rexp, double* out, int nthreads) {
+    int err = 0;
+    const int nvt = T ? T->nv : 0;
+    #pragma omp parallel for num_threads(nthreads > 0 ? nthreads : 1)
+    for (int r = 0; r < n; ++r) {
+        const int t = req_triplet[r];
+        const int ids[3] = {triplets[3 * t], triplets[3 * t + 1], triplets[3 * t + 2]};
+        const int lab[3] = {req_la[r], req_lb[r], req_lc[r]};
+        P3 def[3], cur[3], org[3];
+        for (int k = 0; k < 3; ++k) {
+            def[k] = matvec(rot + 9 * (size_t)ids[k], P3{labels[3 * lab[k]], labels[3 * lab[k] + 1], labels[3 * lab[k] + 2]});
+            cur[k] = P3{cp_xyz[3 * ids[k]], cp_xyz[3 * ids[k] + 1], cp_xyz[3 * ids[k] + 2]};
+            org[k] = P3{orig_cp_xyz[3 * ids[k]], orig_cp_xyz[3 * ids[k] + 1], orig_cp_xyz[3 * ids[k] + 2]};
+        }
+        if (dot(tri_normal(def[0], def[1], def[2]), tri_normal(cur[0], cur[1], cur[2])) < 0.0) { out[r] = 1e7 * lambda; continue; } // FOLDING
+        double likelihood = 0.0;
+        if (kind >= 3) {
+            const int P = prow[t + 1] - prow[t];
+            std::vector<double> tgt((size_t)P * D);
+            bool bad = false;
+            for (int i = 0; i < P && !bad; ++i) {
+                const int sv = pmem[prow[t] + i];
+                const P3 SP = project_point(P3{src_xyz[3 * sv], src_xyz[3 * sv + 1], src_xyz[3 * sv + 2]}, cur[0], cur[1], cur[2]);
+                P3 tmp = bary_blend(cur[0], cur[1], cur[2], SP, def[0], def[1], def[2]);
+                normalize(tmp);
+                tmp = mul(tmp, RAD);
+                int st;
+                const int tt = closest_triangle(T, tmp, &st, nullptr);
+                if (tt < 0) { bad = true; break; }
+                double w[3];
+                bary_interp_weights(T->tv(tt, 0), T->tv(tt, 1), T->tv(tt, 2), tmp, w);
+                for (int d = 0; d < D; ++d) {
+                    const double* rf = ref_feat + (size_t)d * nvt;
+                    tgt[(size_t)i * D + d] = w[0] * rf[T->tri[3 * tt]] + w[1] * rf[T->tri[3 * tt + 1]] + w[2] * rf[T->tri[3 * tt + 2]];
+                }
+            }
+            if (bad) {
+                #pragma omp critical
+                err = 2;
+                out[r] = std::numeric_limits<double>::quiet_NaN();
+                continue;
+            }
+            double cost = 0.0;
+            std::vector<double> a, b, w;
+            if (kind == 3) { // cpp:522-531
+                a.resize(P); b.resize(P); w.resize(P);
+                for (int i = 0; i < P; ++i) {
+                    const int sv = pmem[prow[t] + i];
+                    a[i] = src_feat[sv]; b[i] = tgt[(size_t)i * D];
+                    w[i] = cfw_rows >= 1 ? cfw[sv] : 1.0;
+                }
+                cost = orc_sim_for_min(simmeasure, P, a.data(), b.data(), w.data());
+            } else { // cpp:601-618
+                a.resize(D); b.resize(D); w.resize(D);
+                for (int i = 0; i < P; ++i) {
+                    const int sv = pmem[prow[t] + i];
+                    for (int d = 0; d < D; ++d) {
+                        a[d] = src_feat[(size_t)d * nsrc + sv]; b[d] = tgt[(size_t)i * D + d];
+                        w[d] = cfw_rows >= d + 1 ? cfw[(size_t)d * nsrc + sv] : 1.0;
+                    }
+                    cost += orc_sim_for_min(simmeasure, D, a.data(), b.data(), w.data());
+                }
+                if (P > 0) cost /= P;
+            }
+            likelihood = (absw[ids[0]] + absw[ids[1]] + absw[ids[2]]) / 3.0 * cost;
+        }
+        const double W = triangular_strain(org, def, mu, kappa, k_exp); // rmode 2/3, cpp:158-166
+        out[r] = likelihood + lambda * std::pow(W, rexp);
+    }
+    return err;
+}
+
+} // extern "C"

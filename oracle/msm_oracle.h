@@ -89,6 +89,19 @@ int orc_unary_costs(int kind, int simmeasure, const orc_octree* target_tree,
                     int cfw_rows, const double* cfw, const double* absw,
                     double* out, int* tri_out, int nthreads);
 
+/* HO*::get_source_data (DiscreteCostFunction.cpp:468-485, 541-563): CSR over CP-grid triangles. Returns entries or -1. */
+int orc_ho_patches(int ncp, const double* cp_xyz, int ntri, const int* cp_tri, int nsrc, const double* src_xyz,
+                   int* rowptr, int* members, int cap);
+
+/* computeTripletCost (DiscreteCostFunction.cpp:135-188) for n requests; PARITY UNPINNED (see msm_oracle.cpp).
+ * kind 0..2: likelihood 0; 3: HOUnivariate; 4: HOMultivariate. rmode 2/3 (spherical strain) only. */
+int orc_triplet_costs(int kind, int simmeasure, const orc_octree* T, int ncp, const double* cp_xyz, const double* orig_cp_xyz,
+                      const double* rot, int L, const double* labels, int ntrip, const int* triplets,
+                      int n, const int* req_triplet, const int* req_la, const int* req_lb, const int* req_lc,
+                      int nsrc, const double* src_xyz, const int* prow, const int* pmem, int D, const double* src_feat,
+                      const double* ref_feat, int cfw_rows, const double* cfw, const double* absw,
+                      double lambda, double mu, double kappa, double k_exp, double rexp, double* out, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif
