@@ -217,8 +217,12 @@ static msmgpu_status mesh_create_impl(msmgpu_ctx* ctx, int nv, const double* xyz
     MSM_CUDA(m->cull.alloc(4 * (size_t)nt, s));
     MSM_CUDA(cudaMemcpyAsync(m->xyz.p, xyz, 3 * (size_t)nv * sizeof(double), kind, s));
     if (nt) MSM_CUDA(cudaMemcpyAsync(m->tri.p, tri, 3 * (size_t)nt * sizeof(int), kind, s));
-    MSM_TRY(mesh_refresh_tables(m.get()));
-    if (!dev) MSM_CUDA(cudaStreamSynchronize(s));   // the host buffers may be released by the caller
+    if (dev) {
+        m->tables_dirty = true;   // computed with the first octree build, one launch for a whole batch of meshes
+    } else {
+        MSM_TRY(mesh_refresh_tables(m.get()));
+        MSM_CUDA(cudaStreamSynchronize(s));   // the host buffers may be released by the caller
+    }
     *out = m.release();
     return MSMGPU_OK;
 }

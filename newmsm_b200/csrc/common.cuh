@@ -101,6 +101,7 @@ struct msmgpu_mesh {
     msm::DevBuf<double> cull;  // [nt][4] centre + r^2 of the conservative cull sphere
     msm::DevBuf<float> feat;   // optional resident payload, vertex-major rows [nv][feat_D] (Mesh::pvalues, mesh.h:44)
     int feat_D = 0;
+    bool tables_dirty = false;   // rec / aabb / cull not yet computed from xyz (msm::ensure_tables batches that work)
 };
 
 struct msmgpu_octree {
@@ -133,6 +134,7 @@ namespace msm {
 
 // ---- launchers implemented in the .cu files -------------------------------------------------
 msmgpu_status mesh_refresh_tables(msmgpu_mesh* m);
+msmgpu_status ensure_tables(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes);   // one launch for every dirty mesh
 msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, std::shared_ptr<Forest>& out, std::vector<int>& roots);
 
 int query_group_width();

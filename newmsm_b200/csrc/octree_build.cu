@@ -18,6 +18,9 @@
 // reference's (lo+hi)/2 bit for bit.
 #include "common.cuh"
 
+#include <algorithm>
+#include <climits>
+
 namespace msm {
 
 // ------------------------------------------------------------------------------------------
@@ -115,17 +118,21 @@ msmgpu_status exclusive_scan_i32(const int* d_in, int* d_out, int n, int* d_tota
 // ------------------------------------------------------------------------------------------
 // per-triangle tables
 // ------------------------------------------------------------------------------------------
-__global__ void k_mesh_tables(int nt, const double* __restrict__ xyz, const int* __restrict__ tri,
-                              TriRec* __restrict__ rec, double* __restrict__ aabb, double* __restrict__ cull) {
+struct TableJob {
+    const double* xyz; const int* tri; TriRec* rec; double* aabb; double* cull; int nt;
+};
+
+__global__ void __launch_bounds__(256) k_mesh_tables(const TableJob* __restrict__ jobs) {
+    const TableJob job = jobs[blockIdx.y];
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nt) return;
+    if (t >= job.nt) return;
     double lo[3], hi[3], cv[9];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const int v = tri[3 * t + k];
+        const int v = job.tri[3 * (size_t)t + k];
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            const double c = xyz[3 * (size_t)v + a];
+            const double c = job.xyz[3 * (size_t)v + a];
             cv[3 * k + a] = c;
             if (k == 0) { lo[a] = c; hi[a] = c; }
             else { // octree.cpp:52-58
@@ -135,21 +142,40 @@ __global__ void k_mesh_tables(int nt, const double* __restrict__ xyz, const int*
         }
     }
 #pragma unroll
-    for (int a = 0; a < 3; ++a) { aabb[6 * (size_t)t + a] = lo[a]; aabb[6 * (size_t)t + 3 + a] = hi[a]; }
+    for (int a = 0; a < 3; ++a) { job.aabb[6 * (size_t)t + a] = lo[a]; job.aabb[6 * (size_t)t + 3 + a] = hi[a]; }
     TriRec r;
     make_trirec(V3{cv[0], cv[1], cv[2]}, V3{cv[3], cv[4], cv[5]}, V3{cv[6], cv[7], cv[8]}, r);
-    rec[t] = r;
+    job.rec[t] = r;
     double c4[4];
     make_cull(V3{cv[0], cv[1], cv[2]}, V3{cv[3], cv[4], cv[5]}, V3{cv[6], cv[7], cv[8]}, c4);
-    reinterpret_cast<double2*>(cull)[2 * (size_t)t] = make_double2(c4[0], c4[1]);
-    reinterpret_cast<double2*>(cull)[2 * (size_t)t + 1] = make_double2(c4[2], c4[3]);
+    reinterpret_cast<double2*>(job.cull)[2 * (size_t)t] = make_double2(c4[0], c4[1]);
+    reinterpret_cast<double2*>(job.cull)[2 * (size_t)t + 1] = make_double2(c4[2], c4[3]);
+}
+
+// per-triangle tables of every mesh whose coordinates changed since they were last computed, in ONE launch
+msmgpu_status ensure_tables(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes) {
+    std::vector<TableJob> jobs;
+    int max_nt = 0;
+    for (int i = 0; i < n; ++i) {
+        msmgpu_mesh* m = meshes[i];
+        if (!m->tables_dirty || m->nt == 0) { m->tables_dirty = false; continue; }
+        jobs.push_back(TableJob{m->xyz.p, m->tri.p, m->rec.p, m->aabb.p, m->cull.p, m->nt});
+        max_nt = std::max(max_nt, m->nt);
+        m->tables_dirty = false;
+    }
+    if (jobs.empty()) return MSMGPU_OK;
+    cudaStream_t s = ctx->stream;
+    DevBuf<TableJob> d_jobs;
+    MSM_CUDA(d_jobs.alloc(jobs.size(), s));
+    MSM_CUDA(cudaMemcpyAsync(d_jobs.p, jobs.data(), jobs.size() * sizeof(TableJob), cudaMemcpyHostToDevice, s));   // pageable: staged before return
+    k_mesh_tables<<<dim3((unsigned)((max_nt + 255) / 256), (unsigned)jobs.size()), 256, 0, s>>>(d_jobs.p);
+    MSM_LAUNCH_CHECK();
+    return MSMGPU_OK;
 }
 
 msmgpu_status mesh_refresh_tables(msmgpu_mesh* m) {
-    if (m->nt == 0) return MSMGPU_OK;
-    k_mesh_tables<<<(m->nt + 255) / 256, 256, 0, m->ctx->stream>>>(m->nt, m->xyz.p, m->tri.p, m->rec.p, m->aabb.p, m->cull.p);
-    MSM_LAUNCH_CHECK();
-    return MSMGPU_OK;
+    m->tables_dirty = true;
+    return ensure_tables(m->ctx, 1, &m);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -188,58 +214,162 @@ __device__ __forceinline__ void classify(const double* __restrict__ bb, const do
     child_mask = m;
 }
 
-// One CTA per node of the current level: split decision + per-child triangle counts.
-__global__ void k_decide_count(int node_begin, const int4* __restrict__ nodes, const BuildNode* __restrict__ bn,
-                               const int* __restrict__ pairs, const double* const* __restrict__ mesh_aabb,
-                               double root_half, int* __restrict__ split_flag, int* __restrict__ child_cnt) {
-    __shared__ int sw[33];
-    __shared__ int s_cnt[8];
-    __shared__ int s_found;
-    const int li = blockIdx.x;
-    const int g = node_begin + li;
-    const int4 nd = nodes[g];
-    const int cnt = nd.z;
-    if (cnt < kMaxTriangles) {       // octree.cpp:69: the test only runs once a leaf holds >= 50
-        if (threadIdx.x == 0) split_flag[li] = 0;
-        if (threadIdx.x < 8) child_cnt[li * 8 + threadIdx.x] = 0;
-        return;
+// ------------------------------------------------------------------------------------------
+// Chunked level pass. A node's list is cut into chunks of K = TPC * IPT triangles; one TEAM of TPC threads
+// (a warp, or a whole CTA) owns one (node, chunk), every thread IPT consecutive list positions. That keeps the
+// top levels (few nodes, 10^5-triangle lists) and the bottom levels (10^5 nodes, short lists) equally busy.
+//   k_chunk_stats   per chunk: sum of a = split_size - 3, the smallest inclusive prefix of a over the chunk's
+//                   positions p with p + 1 >= 50 (chunk-relative), and the 8 child counts
+//   k_node_combine  per node: walks its chunks in order -> split decision (some prefix of length >= 50 has a
+//                   negative running sum), child totals, and each chunk's exclusive child offsets
+//   k_scatter_chunk per chunk: stable scatter (list order preserved) into the children's lists
+// ------------------------------------------------------------------------------------------
+constexpr int kStatInts = 10;   // sum_a, min_prefix, cnt[8]
+
+template <int TPC>
+__device__ __forceinline__ int team_lane() { return TPC == 32 ? (threadIdx.x & 31) : threadIdx.x; }
+
+// exclusive scan + total over a team (warp shuffles for TPC = 32, shared memory otherwise)
+template <int TPC, typename T>
+__device__ __forceinline__ T team_exclusive_scan(T v, T* smem /* >= 33 entries when TPC > 32 */, T& total) {
+    const int lane = threadIdx.x & 31;
+    T inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const T t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
     }
-    const BuildNode b = bn[g];
+    if (TPC == 32) {
+        total = __shfl_sync(0xffffffffu, inc, 31);
+        return inc - v;
+    } else {
+        const int warp = threadIdx.x >> 5, nwarp = TPC >> 5;
+        if (lane == 31) smem[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const T w = lane < nwarp ? smem[lane] : T(0);
+            T winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const T t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            if (lane < nwarp) smem[lane] = winc - w;
+            if (lane == 31) smem[32] = winc;
+        }
+        __syncthreads();
+        const T res = inc - v + smem[warp];
+        total = smem[32];
+        __syncthreads();
+        return res;
+    }
+}
+
+template <int TPC>
+__device__ __forceinline__ int team_min(int v, int* smem) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (TPC == 32) return v;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = TPC >> 5;
+    if (lane == 0) smem[warp] = v;
+    __syncthreads();
+    int r = smem[0];
+    for (int w = 1; w < nwarp; ++w) r = min(r, smem[w]);
+    __syncthreads();
+    return r;
+}
+
+template <int TPC, int IPT>
+__global__ void __launch_bounds__(TPC == 32 ? 256 : TPC) k_chunk_stats(int node_begin, int n_level, int max_chunks, const int4* __restrict__ nodes,
+                                                                        const BuildNode* __restrict__ bn, const int* __restrict__ pairs,
+                                                                        const double* const* __restrict__ mesh_aabb, double root_half,
+                                                                        int* __restrict__ stats) {
+    constexpr int K = TPC * IPT;
+    constexpr int TEAMS = TPC == 32 ? 8 : 1;
+    __shared__ int s_scan[TPC == 32 ? 1 : 33];
+    __shared__ int s_red[TPC == 32 ? 1 : 32];
+    const int li = blockIdx.x * TEAMS + (TPC == 32 ? (threadIdx.x >> 5) : 0);   // nodes on grid.x (no 65535 limit)
+    const int chunk = blockIdx.y;
+    const bool node_ok = li < n_level;
+    int4 nd = make_int4(0, 0, 0, 0);
+    if (node_ok) nd = nodes[node_begin + li];
+    const int cnt = nd.z;
+    const bool live = node_ok && cnt >= kMaxTriangles && chunk * K < cnt;   // octree.cpp:69: the test only runs from 50 triangles on
+    if (TPC == 32) { if (!live) return; }                                  // warp-uniform
+    else if (!live) return;                                                // CTA-uniform
+    const BuildNode b = bn[node_begin + li];
     const double half = ldexp(root_half, -b.depth);
     const double* __restrict__ aabb = mesh_aabb[b.mesh];
-    if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
-    if (threadIdx.x == 0) s_found = 0;
-    __syncthreads();
-    int carry = 0, found = 0;
-    int my_cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int base = 0; base < cnt; base += blockDim.x) {
-        const int i = base + threadIdx.x;
-        int a = 0; unsigned mask = 0;
-        if (i < cnt) {
-            const int t = pairs[nd.y + i];
-            classify(aabb + 6 * (size_t)t, b.lo, half, a, mask);
-        }
-        int total;
-        const int excl = block_exclusive_scan(a, sw, total);
-        const int incl = carry + excl + a;          // running sum over the first (i+1) triangles
-        if (i < cnt && i + 1 >= kMaxTriangles && incl < 0) found = 1;
-        carry += total;
+    const int tl = team_lane<TPC>();
+    const int p0 = chunk * K + tl * IPT;
+    int a[IPT];
+    int local_sum = 0;
+    int c8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-        for (int c = 0; c < 8; ++c) my_cnt[c] += (mask >> c) & 1u;
+    for (int k = 0; k < IPT; ++k) {
+        a[k] = 0;
+        const int p = p0 + k;
+        if (p < cnt) {
+            unsigned mask;
+            classify(aabb + 6 * (size_t)__ldg(pairs + nd.y + p), b.lo, half, a[k], mask);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) c8[c] += (mask >> c) & 1u;
+        }
+        local_sum += a[k];
     }
-    // reduce child counts and the decision
+    int total;
+    const int excl = team_exclusive_scan<TPC, int>(local_sum, s_scan, total);
+    int run = excl, mn = INT_MAX;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        run += a[k];
+        const int p = p0 + k;
+        if (p < cnt && p + 1 >= kMaxTriangles) mn = min(mn, run);
+    }
+    mn = team_min<TPC>(mn, s_red);
+    int* out = stats + ((size_t)li * max_chunks + chunk) * kStatInts;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-        int v = my_cnt[c];
+        int v = c8[c];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_cnt[c], v);
+        if (TPC == 32) {
+            if (tl == 0) out[2 + c] = v;
+        } else {
+            __shared__ int s_c[8];
+            if (threadIdx.x < 8) s_c[threadIdx.x] = 0;
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_c[c], v);
+            __syncthreads();
+            if (threadIdx.x == 0) out[2 + c] = s_c[c];
+            __syncthreads();
+        }
     }
-    if (__any_sync(0xffffffffu, found) && (threadIdx.x & 31) == 0) s_found = 1;
-    __syncthreads();
-    const int split = s_found;
-    if (threadIdx.x == 0) split_flag[li] = split;
-    if (threadIdx.x < 8) child_cnt[li * 8 + threadIdx.x] = split ? s_cnt[threadIdx.x] : 0;
+    if (tl == 0) { out[0] = total; out[1] = mn; }
+}
+
+// one thread per node of the level
+__global__ void k_node_combine(int node_begin, int n_level, int max_chunks, int K, const int4* __restrict__ nodes, int* __restrict__ stats,
+                               int* __restrict__ split_flag, int* __restrict__ child_cnt) {
+    const int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= n_level) return;
+    const int cnt = nodes[node_begin + li].z;
+    int tot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int split = 0;
+    if (cnt >= kMaxTriangles) {
+        const int nch = (cnt + K - 1) / K;
+        long long run = 0;
+        for (int ch = 0; ch < nch; ++ch) {
+            int* st = stats + ((size_t)li * max_chunks + ch) * kStatInts;
+            if (st[1] != INT_MAX && run + st[1] < 0) split = 1;
+            run += st[0];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { const int v = st[2 + c]; st[2 + c] = tot[c]; tot[c] += v; }   // counts -> exclusive offsets
+        }
+    }
+    split_flag[li] = split;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) child_cnt[li * 8 + c] = split ? tot[c] : 0;
 }
 
 // One thread per node of the level: create the 8 children of every splitting node.
@@ -274,51 +404,68 @@ __global__ void k_make_children(int node_begin, int n_level, int4* __restrict__ 
     }
 }
 
-// One CTA per node: stable scatter of the triangle ids into the children's lists.
-__global__ void k_scatter(int node_begin, const int4* __restrict__ nodes, const BuildNode* __restrict__ bn,
-                          int* __restrict__ pairs, const double* const* __restrict__ mesh_aabb, double root_half,
-                          const int* __restrict__ split_flag, const int* __restrict__ list_start,
-                          const int* __restrict__ list_count, const int* __restrict__ child_off, int next_pair_base) {
-    __shared__ int s_warp[32][8];
-    __shared__ int s_carry[8];
-    const int li = blockIdx.x;
-    if (!split_flag[li]) return;
-    const int g = node_begin + li;
-    const BuildNode b = bn[g];
+template <int TPC, int IPT>
+__global__ void __launch_bounds__(TPC == 32 ? 256 : TPC) k_scatter_chunk(int node_begin, int n_level, int max_chunks, const BuildNode* __restrict__ bn,
+                                                                          int* __restrict__ pairs, const double* const* __restrict__ mesh_aabb,
+                                                                          double root_half, const int* __restrict__ split_flag,
+                                                                          const int* __restrict__ list_start, const int* __restrict__ list_count,
+                                                                          const int* __restrict__ child_off, const int* __restrict__ stats,
+                                                                          int next_pair_base) {
+    constexpr int K = TPC * IPT;
+    constexpr int TEAMS = TPC == 32 ? 8 : 1;
+    __shared__ unsigned long long s_scan[TPC == 32 ? 1 : 33];
+    const int li = blockIdx.x * TEAMS + (TPC == 32 ? (threadIdx.x >> 5) : 0);   // nodes on grid.x (no 65535 limit)
+    const int chunk = blockIdx.y;
+    if (li >= n_level || !split_flag[li]) return;
+    const int cnt = list_count[li];
+    if (chunk * K >= cnt) return;
+    const int start = list_start[li];
+    const BuildNode b = bn[node_begin + li];
     const double half = ldexp(root_half, -b.depth);
     const double* __restrict__ aabb = mesh_aabb[b.mesh];
-    const int start = list_start[li], cnt = list_count[li];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    if (threadIdx.x < 8) s_carry[threadIdx.x] = next_pair_base + child_off[li * 8 + threadIdx.x];
-    __syncthreads();
-    for (int base = 0; base < cnt; base += blockDim.x) {
-        const int i = base + threadIdx.x;
-        int a; unsigned mask = 0; int t = -1;
-        if (i < cnt) {
-            t = pairs[start + i];
-            classify(aabb + 6 * (size_t)t, b.lo, half, a, mask);
-        }
-        int rank[8];
+    const int tl = team_lane<TPC>();
+    const int p0 = chunk * K + tl * IPT;
+    int tri[IPT];
+    unsigned mask[IPT];
+    unsigned long long lo4 = 0, hi4 = 0;   // per-thread child counts, 16 bits per child (K <= 8192 < 2^16)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const unsigned bal = __ballot_sync(0xffffffffu, (mask >> c) & 1u);
-            rank[c] = __popc(bal & ((1u << lane) - 1u));
-            if (lane == 0) s_warp[warp][c] = __popc(bal);
-        }
-        __syncthreads();
-        if (threadIdx.x < 8) {          // exclusive prefix over warps for child threadIdx.x, then advance the carry
-            int run = s_carry[threadIdx.x];
-            for (int w = 0; w < nwarp; ++w) { const int v = s_warp[w][threadIdx.x]; s_warp[w][threadIdx.x] = run; run += v; }
-            s_carry[threadIdx.x] = run;
-        }
-        __syncthreads();
-        if (t >= 0) {
+    for (int k = 0; k < IPT; ++k) {
+        mask[k] = 0;
+        tri[k] = -1;
+        const int p = p0 + k;
+        if (p < cnt) {
+            int a;
+            tri[k] = pairs[start + p];
+            classify(aabb + 6 * (size_t)tri[k], b.lo, half, a, mask[k]);
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-                if ((mask >> c) & 1u) pairs[s_warp[warp][c] + rank[c]] = t;
+            for (int c = 0; c < 4; ++c) {
+                lo4 += (unsigned long long)((mask[k] >> c) & 1u) << (16 * c);
+                hi4 += (unsigned long long)((mask[k] >> (4 + c)) & 1u) << (16 * c);
+            }
         }
-        __syncthreads();
     }
+    unsigned long long tot;
+    const unsigned long long elo = team_exclusive_scan<TPC, unsigned long long>(lo4, s_scan, tot);
+    const unsigned long long ehi = team_exclusive_scan<TPC, unsigned long long>(hi4, s_scan, tot);
+    const int* st = stats + ((size_t)li * max_chunks + chunk) * kStatInts;
+    int pos[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const unsigned long long e = c < 4 ? elo : ehi;
+        pos[c] = next_pair_base + child_off[li * 8 + c] + st[2 + c] + (int)((e >> (16 * (c & 3))) & 0xffffull);
+    }
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        if (tri[k] < 0) continue;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            if ((mask[k] >> c) & 1u) pairs[pos[c]++] = tri[k];
+    }
+}
+
+__global__ void k_max_i32_build(int n, const int* __restrict__ v, int* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && v[i] > 0) atomicMax(out, v[i]);
 }
 
 __global__ void k_save_lists(int node_begin, int n_level, const int4* __restrict__ nodes, int* __restrict__ list_start, int* __restrict__ list_count) {
@@ -350,6 +497,9 @@ __global__ void k_init_roots(int n, int4* nodes, BuildNode* bn, unsigned char* n
 msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, std::shared_ptr<Forest>& out, std::vector<int>& roots) {
     cudaStream_t s = ctx->stream;
     if (n <= 0) return fail(MSMGPU_ERR_INVALID, "forest_build: no meshes");
+    for (int i = 0; i < n; ++i)
+        if (!meshes[i] || meshes[i]->ctx != ctx) return fail(MSMGPU_ERR_INVALID, "forest_build: mesh from another context");
+    MSM_TRY(ensure_tables(ctx, n, meshes));
     long long total_t = 0;
     std::vector<int> h_nt(n), h_off(n);
     std::vector<const double*> h_aabb(n);
@@ -395,8 +545,10 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
         long long n_pairs = total_t;
         int depth = 0;
         bool overflow = false;
-        DevBuf<int> split_flag, split_rank, child_cnt, child_off, list_start, list_count, totals;
-        MSM_CUDA(totals.alloc(2, s));
+        DevBuf<int> split_flag, split_rank, child_cnt, child_off, list_start, list_count, totals, stats;
+        MSM_CUDA(totals.alloc(3, s));
+        int level_max_cnt = 1;
+        for (int v : h_nt) level_max_cnt = std::max(level_max_cnt, v);
         while (n_level > 0) {
             MSM_CUDA(split_flag.alloc(n_level, s));
             MSM_CUDA(split_rank.alloc(n_level, s));
@@ -404,16 +556,30 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
             MSM_CUDA(child_off.alloc((size_t)n_level * 8, s));
             MSM_CUDA(list_start.alloc(n_level, s));
             MSM_CUDA(list_count.alloc(n_level, s));
-            // wide CTAs while lists are long (top levels), narrow ones for the many small deep nodes
-            const long long avg = (n_pairs - (long long)F->n_pairs) / std::max(n_level, 1);
-            (void)avg;
-            const int tb = depth <= 2 ? 1024 : (depth <= 4 ? 256 : 128);
-            k_decide_count<<<n_level, tb, 0, s>>>(node_begin, F->nodes.p, bn.p, F->pairs.p, d_aabb.p, root_half, split_flag.p, child_cnt.p);
+            // team width by the longest list of the level: whole CTAs at the top, warps at the bottom
+            const int max_cnt = level_max_cnt;
+            int K, max_chunks;
+            if (max_cnt > 16384) K = 1024 * 8; else if (max_cnt > 512) K = 256 * 4; else K = 32 * 4;
+            max_chunks = std::max(1, (max_cnt + K - 1) / K);
+            MSM_CUDA(stats.alloc((size_t)n_level * max_chunks * kStatInts, s));
+            if (max_chunks > 65535) return fail(MSMGPU_ERR_CAPACITY, "forest_build: list too long for the chunk grid");
+            const dim3 g_cta((unsigned)n_level, (unsigned)max_chunks), g_warp((unsigned)((n_level + 7) / 8), (unsigned)max_chunks);
+            if (K == 8192)
+                k_chunk_stats<1024, 8><<<g_cta, 1024, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_aabb.p, root_half, stats.p);
+            else if (K == 1024)
+                k_chunk_stats<256, 4><<<g_cta, 256, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_aabb.p, root_half, stats.p);
+            else
+                k_chunk_stats<32, 4><<<g_warp, 256, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_aabb.p, root_half, stats.p);
+            MSM_LAUNCH_CHECK();
+            k_node_combine<<<(n_level + 255) / 256, 256, 0, s>>>(node_begin, n_level, max_chunks, K, F->nodes.p, stats.p, split_flag.p, child_cnt.p);
             MSM_LAUNCH_CHECK();
             MSM_TRY(exclusive_scan_i32(split_flag.p, split_rank.p, n_level, totals.p, s));
             MSM_TRY(exclusive_scan_i32(child_cnt.p, child_off.p, n_level * 8, totals.p + 1, s));
-            int h_tot[2];
-            MSM_CUDA(cudaMemcpyAsync(h_tot, totals.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+            MSM_CUDA(cudaMemsetAsync(totals.p + 2, 0, sizeof(int), s));
+            k_max_i32_build<<<(n_level * 8 + 255) / 256, 256, 0, s>>>(n_level * 8, child_cnt.p, totals.p + 2);
+            MSM_LAUNCH_CHECK();
+            int h_tot[3];
+            MSM_CUDA(cudaMemcpyAsync(h_tot, totals.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, s));
             MSM_CUDA(cudaStreamSynchronize(s));
             const int n_split = h_tot[0];
             const int new_pairs = h_tot[1];
@@ -425,9 +591,17 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
                                                                  split_rank.p, child_cnt.p, child_off.p, n_nodes, (int)n_pairs, root_half,
                                                                  (int)node_cap);
             MSM_LAUNCH_CHECK();
-            k_scatter<<<n_level, tb, 0, s>>>(node_begin, F->nodes.p, bn.p, F->pairs.p, d_aabb.p, root_half, split_flag.p, list_start.p,
-                                             list_count.p, child_off.p, (int)n_pairs);
+            if (K == 8192)
+                k_scatter_chunk<1024, 8><<<g_cta, 1024, 0, s>>>(node_begin, n_level, max_chunks, bn.p, F->pairs.p, d_aabb.p, root_half, split_flag.p,
+                                                               list_start.p, list_count.p, child_off.p, stats.p, (int)n_pairs);
+            else if (K == 1024)
+                k_scatter_chunk<256, 4><<<g_cta, 256, 0, s>>>(node_begin, n_level, max_chunks, bn.p, F->pairs.p, d_aabb.p, root_half, split_flag.p,
+                                                             list_start.p, list_count.p, child_off.p, stats.p, (int)n_pairs);
+            else
+                k_scatter_chunk<32, 4><<<g_warp, 256, 0, s>>>(node_begin, n_level, max_chunks, bn.p, F->pairs.p, d_aabb.p, root_half, split_flag.p,
+                                                             list_start.p, list_count.p, child_off.p, stats.p, (int)n_pairs);
             MSM_LAUNCH_CHECK();
+            level_max_cnt = h_tot[2];
             node_begin = n_nodes;
             n_level = 8 * n_split;
             n_nodes += n_level;

@@ -136,10 +136,10 @@ __global__ void __launch_bounds__(256) k_blend_coords(TreeView T, int n, const d
 constexpr int kResThreads = 256;
 constexpr int kResWarpTile = 32;                                   // targets per warp
 constexpr int kResTile = kResWarpTile * (kResThreads / 32);        // targets per CTA
-constexpr int kResUnroll = 4;
 
-template <int G>
-__global__ void __launch_bounds__(kResThreads) k_bary_resample_f32(const ResampleJob* __restrict__ jobs, int n, const double* __restrict__ pts,
+// U = gather slots in flight per thread, MINB = CTAs per SM the register allocation must allow
+template <int G, int kResUnroll, int MINB>
+__global__ void __launch_bounds__(kResThreads, MINB) k_bary_resample_f32(const ResampleJob* __restrict__ jobs, int n, const double* __restrict__ pts,
                                                                   int D, int* __restrict__ out_status) {
     __shared__ int s_idx_all[kResTile * 3];
     __shared__ double s_w_all[kResTile * 3];
@@ -300,7 +300,13 @@ msmgpu_status launch_bary_resample_f32(const ResampleJob* d_jobs, int n_jobs, in
     if (n <= 0 || n_jobs <= 0) return MSMGPU_OK;
     const int g = query_group_width();
     const dim3 grid((unsigned)((n + kResTile - 1) / kResTile), (unsigned)n_jobs);
-    MSM_DISPATCH_G(g, (k_bary_resample_f32<G><<<grid, kResThreads, 0, s>>>(d_jobs, n, d_pts, D, d_status)));
+    static const int variant = [] { const char* e = getenv("MSMGPU_RESAMPLE_VARIANT"); return e ? atoi(e) : 2; }();
+    switch (variant) {   // tuning knob (profiles/): registers per thread vs loads in flight
+        case 1: MSM_DISPATCH_G(g, (k_bary_resample_f32<G, 2, 3><<<grid, kResThreads, 0, s>>>(d_jobs, n, d_pts, D, d_status))); break;
+        case 2: MSM_DISPATCH_G(g, (k_bary_resample_f32<G, 2, 4><<<grid, kResThreads, 0, s>>>(d_jobs, n, d_pts, D, d_status))); break;
+        case 3: MSM_DISPATCH_G(g, (k_bary_resample_f32<G, 4, 3><<<grid, kResThreads, 0, s>>>(d_jobs, n, d_pts, D, d_status))); break;
+        default: MSM_DISPATCH_G(g, (k_bary_resample_f32<G, 4, 2><<<grid, kResThreads, 0, s>>>(d_jobs, n, d_pts, D, d_status))); break;
+    }
     MSM_LAUNCH_CHECK();
     return MSMGPU_OK;
 }

@@ -12,6 +12,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <climits>
 #include <type_traits>
 
 namespace msm {
@@ -36,64 +37,99 @@ __device__ __forceinline__ int find_segment(const int* __restrict__ off, int n_s
     return lo;
 }
 
-// Emitters: n_src() sources, each emitting count(i) triples (key, id, val). All of them cover a BATCH of
-// subjects: vertex keys of subject s are shifted by in_off[s], target keys by s * n_low.
+// Emitters: n_src() sources; load(i) gathers what the source's triples share, then count / key / id / val per triple.
+// All of them cover a BATCH of subjects: vertex keys of subject s are shifted by in_off[s], target keys by s * n_low.
 struct EmitVertexTriangles {   // key = vertex, id = triangle, val = cached triangle area (triangle.cpp:47-50)
     const int* const* tri; const TriRec* const* rec; const int* tri_off; const int* key_off; int S; int total;
+    struct Src { int t, koff; const int* tri; double area; };
     __device__ int n_src() const { return total; }
-    __device__ int count(int) const { return 3; }
-    __device__ int seg(int i) const { return S == 1 ? 0 : find_segment(tri_off, S, i); }
-    __device__ int key(int i, int j) const { const int s = seg(i); return key_off[s] + tri[s][3 * (size_t)(i - tri_off[s]) + j]; }
-    __device__ int id(int i, int) const { return i - tri_off[seg(i)]; }
-    __device__ double val(int i, int) const {
-        const int s = seg(i);
-        const double* v = rec[s][i - tri_off[s]].v;
-        return tri_area_cached(V3{v[0], v[1], v[2]}, V3{v[3], v[4], v[5]}, V3{v[6], v[7], v[8]});
+    __device__ Src load(int i) const {
+        const int s = S == 1 ? 0 : find_segment(tri_off, S, i);
+        const int t = i - tri_off[s];
+        const double* v = rec[s][t].v;
+        return Src{t, key_off[s], tri[s] + 3 * (size_t)t, tri_area_cached(V3{v[0], v[1], v[2]}, V3{v[3], v[4], v[5]}, V3{v[6], v[7], v[8]})};
     }
+    __device__ int count(const Src&) const { return 3; }
+    __device__ int key(const Src& x, int j) const { return x.koff + x.tri[j]; }
+    __device__ int id(const Src& x, int) const { return x.t; }
+    __device__ double val(const Src& x, int) const { return x.area; }
 };
 struct EmitReverse {   // resampler.cpp:91-95: reverse_reorder[target][source] = weight
     const int* ridx; const double* rw; const int* rne; const int* in_off; int S; int n_low; int total;
+    struct Src { int o, local, kbase; };
     __device__ int n_src() const { return total; }
-    __device__ int count(int o) const { return rne[o]; }
-    __device__ int seg(int o) const { return S == 1 ? 0 : find_segment(in_off, S, o); }
-    __device__ int key(int o, int j) const { return seg(o) * n_low + ridx[3 * (size_t)o + j]; }
-    __device__ int id(int o, int) const { return o - in_off[seg(o)]; }
-    __device__ double val(int o, int j) const { return rw[3 * (size_t)o + j]; }
+    __device__ Src load(int o) const {
+        const int s = S == 1 ? 0 : find_segment(in_off, S, o);
+        return Src{o, o - in_off[s], s * n_low};
+    }
+    __device__ int count(const Src& x) const { return rne[x.o]; }
+    __device__ int key(const Src& x, int j) const { return x.kbase + ridx[3 * (size_t)x.o + j]; }
+    __device__ int id(const Src& x, int) const { return x.local; }
+    __device__ double val(const Src& x, int j) const { return rw[3 * (size_t)x.o + j]; }
 };
 struct EmitCsrColumns {   // key = column (source vertex), id = row (target), val = stored value
     const int* rowptr; const int* col; const double* v; const int* in_off; int n_low; int total;
+    struct Src { int r, b, e, koff; };
     __device__ int n_src() const { return total; }
-    __device__ int count(int r) const { return rowptr[r + 1] - rowptr[r]; }
-    __device__ int key(int r, int j) const { return in_off[r / n_low] + col[rowptr[r] + j]; }
-    __device__ int id(int r, int) const { return r; }
-    __device__ double val(int r, int j) const { return v[rowptr[r] + j]; }
+    __device__ Src load(int r) const { return Src{r, rowptr[r], rowptr[r + 1], in_off[r / n_low]}; }
+    __device__ int count(const Src& x) const { return x.e - x.b; }
+    __device__ int key(const Src& x, int j) const { return x.koff + col[x.b + j]; }
+    __device__ int id(const Src& x, int) const { return x.r; }
+    __device__ double val(const Src& x, int j) const { return v[x.b + j]; }
 };
 
 template <class E>
 __global__ void k_bucket_count(E e, int* __restrict__ cnt) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= e.n_src()) return;
-    const int c = e.count(i);
-    for (int j = 0; j < c; ++j) atomicAdd(cnt + e.key(i, j), 1);
+    const typename E::Src x = e.load(i);
+    const int c = e.count(x);
+    for (int j = 0; j < c; ++j) atomicAdd(cnt + e.key(x, j), 1);
 }
 template <class E>
 __global__ void k_bucket_fill(E e, const int* __restrict__ ptr, int* __restrict__ cursor, int* __restrict__ id, double* __restrict__ val) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= e.n_src()) return;
-    const int c = e.count(i);
+    const typename E::Src x = e.load(i);
+    const int c = e.count(x);
     for (int j = 0; j < c; ++j) {
-        const int k = e.key(i, j);
+        const int k = e.key(x, j);
         const int pos = ptr[k] + atomicAdd(cursor + k, 1);
-        id[pos] = e.id(i, j);
-        val[pos] = e.val(i, j);
+        id[pos] = e.id(x, j);
+        val[pos] = e.val(x, j);
     }
 }
-// insertion sort of each bucket by id (buckets hold a handful of entries: vertex valence, or the
-// ~3 N_s / N_t sources that fall into one target's triangles)
+// Sort each bucket by id. Buckets hold a handful of entries (vertex valence, or the ~3 N_s / N_t sources that fall
+// into one target's triangles): up to 8 entries are sorted in registers (odd-even transposition network), longer
+// ones by insertion in place.
 __global__ void k_bucket_sort(int nkeys, const int* __restrict__ ptr, int* __restrict__ id, double* __restrict__ val) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nkeys) return;
-    const int b = ptr[k], e = ptr[k + 1];
+    const int b = ptr[k], e = ptr[k + 1], len = e - b;
+    if (len <= 1) return;
+    if (len <= 8) {
+        int ki[8];
+        double vi[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            ki[i] = i < len ? id[b + i] : INT_MAX;
+            vi[i] = i < len ? val[b + i] : 0.0;
+        }
+#pragma unroll
+        for (int round = 0; round < 8; ++round) {
+#pragma unroll
+            for (int i = round & 1; i + 1 < 8; i += 2) {
+                if (ki[i] > ki[i + 1]) {
+                    const int tk = ki[i]; ki[i] = ki[i + 1]; ki[i + 1] = tk;
+                    const double tv = vi[i]; vi[i] = vi[i + 1]; vi[i + 1] = tv;
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i < len) { id[b + i] = ki[i]; val[b + i] = vi[i]; }
+        return;
+    }
     for (int i = b + 1; i < e; ++i) {
         const int ki = id[i];
         const double vi = val[i];
@@ -152,6 +188,7 @@ __global__ void k_bucket_sum(int nkeys, const int* __restrict__ ptr, const doubl
 // vertex areas of a batch of meshes, concatenated: d_out[key_off[s] + v]
 static msmgpu_status vertex_areas_batch(msmgpu_ctx* ctx, int S, msmgpu_mesh* const* meshes, const std::vector<int>& key_off, double* d_out) {
     cudaStream_t s = ctx->stream;
+    MSM_TRY(ensure_tables(ctx, S, meshes));
     std::vector<const int*> h_tri(S);
     std::vector<const TriRec*> h_rec(S);
     std::vector<int> h_toff(S + 1, 0);
@@ -208,22 +245,38 @@ __global__ void k_fill_rows(int n_rows, int n_low, const int* __restrict__ rowpt
         for (int j = 0; j < r; ++j) { col[o + j] = rr_id[rb + j]; val[o + j] = rr_val[rb + j] * a; }
     }
 }
-// resampler.cpp:120-137: w *= oldArea[src] / correction[src]; then each row normalised to sum 1
-__global__ void k_finish_rows(int n_rows, int n_low, const int* __restrict__ rowptr, const int* __restrict__ col, double* __restrict__ val,
-                              const int* __restrict__ in_off, const double* __restrict__ old_area, const double* __restrict__ correction) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+// correction[src] = sum of its bucket (ascending target); ratio[src] = oldArea[src] / correction[src] (resampler.cpp:114-123)
+__global__ void k_area_ratio(int nkeys, const int* __restrict__ ptr, const double* __restrict__ val, const double* __restrict__ old_area,
+                             double* __restrict__ ratio) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nkeys) return;
+    double sum = 0.0;
+    for (int i = ptr[k]; i < ptr[k + 1]; ++i) sum += val[i];
+    ratio[k] = old_area[k] / sum;
+}
+// resampler.cpp:120-137: w *= oldArea[src] / correction[src]; then each row normalised to sum 1.
+// One warp per row: the lanes fetch the row's entries (the random ratio[] loads overlap), the row sum is taken in
+// column order by lane-ordered broadcasts, i.e. the reference's sequential sum.
+__global__ void __launch_bounds__(256) k_finish_rows(int n_rows, int n_low, const int* __restrict__ rowptr, const int* __restrict__ col,
+                                                     double* __restrict__ val, const int* __restrict__ in_off, const double* __restrict__ ratio) {
+    const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (n >= n_rows) return;
     const int b = rowptr[n], e = rowptr[n + 1];
     const int koff = in_off[n / n_low];
     double ws = 0.0;
-    for (int i = b; i < e; ++i) {
-        const int c = koff + col[i];
-        const double v = val[i] * (old_area[c] / correction[c]);
-        val[i] = v;
-        ws += v;
+    for (int i0 = b; i0 < e; i0 += 32) {
+        const int i = i0 + lane;
+        double v = 0.0;
+        if (i < e) {
+            v = val[i] * __ldg(ratio + koff + col[i]);
+            val[i] = v;
+        }
+        const int m = min(32, e - i0);
+        for (int k = 0; k < m; ++k) ws += __shfl_sync(0xffffffffu, v, k);
     }
     if (ws != 0.0)
-        for (int i = b; i < e; ++i) val[i] /= ws;
+        for (int i = b + lane; i < e; i += 32) val[i] /= ws;
 }
 
 // Builds the S matrices into one shared store; out[s] become views of it.
@@ -296,9 +349,9 @@ msmgpu_status adaptive_weights_build_batch(msmgpu_ctx* ctx, int S, msmgpu_mesh* 
     // correction[src] = sum over targets (ascending) of the area-scaled weights (resampler.cpp:114-116)
     Buckets cols;
     MSM_TRY(bucketize(EmitCsrColumns{store->rowptr.p, store->col.p, store->val.p, d_in_off.p, n_low, (int)NL}, (int)NL, (int)NV, cap, cols, s));
-    k_bucket_sum<<<(unsigned)((NV + 255) / 256), 256, 0, s>>>((int)NV, cols.ptr.p, cols.val.p, correction.p);
+    k_area_ratio<<<(unsigned)((NV + 255) / 256), 256, 0, s>>>((int)NV, cols.ptr.p, cols.val.p, old_area.p, correction.p);   // correction := ratio
     MSM_LAUNCH_CHECK();
-    k_finish_rows<<<gl, 256, 0, s>>>((int)NL, n_low, store->rowptr.p, store->col.p, store->val.p, d_in_off.p, old_area.p, correction.p);
+    k_finish_rows<<<(unsigned)((NL * 32 + 255) / 256), 256, 0, s>>>((int)NL, n_low, store->rowptr.p, store->col.p, store->val.p, d_in_off.p, correction.p);
     MSM_LAUNCH_CHECK();
 
     // per-subject views: rowptr offsets of the subject boundaries
