@@ -116,6 +116,9 @@ msmgpu_status msmgpu_weights_apply_f32_dev(msmgpu_weights* w, int D, const float
 /* one launch for the n matrices of one msmgpu_adaptive_weights_batch call: d_in[i] / d_out[i] row pointers per subject */
 msmgpu_status msmgpu_weights_apply_batch_f32_dev(msmgpu_ctx* ctx, int n, msmgpu_weights* const* ws, int D, const float* const* d_in, float* const* d_out);
 
+/* FP64 payload (bit-exact with the reference's double features; used by the groupwise fields) */
+msmgpu_status msmgpu_weights_apply_batch_f64_dev(msmgpu_ctx* ctx, int n, msmgpu_weights* const* ws, int D, const double* const* d_in, double* const* d_out);
+
 /* replaces: metric_resample(in, low) (resampler.cpp:304): adaptive-barycentric resampling of D channels.
  * Host buffers, channel-major: feat_in [D][nv_in] double, feat_out [D][nv_low] double. */
 msmgpu_status msmgpu_metric_resample(msmgpu_mesh* in_mesh, msmgpu_mesh* low_mesh, int D, const double* feat_in, double* feat_out);
@@ -205,6 +208,29 @@ msmgpu_status msmgpu_costfn_triplet_costs(msmgpu_costfn* c, int ntrip, const int
  * out[t][b] = cost(t, b&4 ? label : labeling[A], b&2 ? label : labeling[B], b&1 ? label : labeling[C]) */
 msmgpu_status msmgpu_costfn_triplet_batch(msmgpu_costfn* c, int ntrip, const int32_t* triplets, int L, const double* labels, const double* rotations,
                                           const double* orig_cp_xyz, const msmgpu_reg_params* prm, const int32_t* labeling, int label, double* out);
+
+/* ---- groupwise registration (gMSM): msm-newmeshreg/src/DiscreteGroupModel.cpp, DiscreteGroupCostFunction.cpp ---- */
+typedef struct msmgpu_group msmgpu_group;
+
+/* replaces: the per-(subject,label) part of DiscreteGroupModel::get_patch_data (DiscreteGroupModel.cpp:92-106): every data mesh
+ * is "rotated" by every label (estimate_rotation_matrix(centre, vertex) * label, label 0 = identity) and metric_resampled onto the
+ * template. Host in: data_xyz [n][nv][3], tri [nt][3], feat_cm [n][D][nv] doubles. Device out: d_fields [n][L][n_tpl][D] doubles.
+ * A rank calls it for ITS shard of subjects; the shards are all-gathered by the host side (one collective per iteration). */
+msmgpu_status msmgpu_group_fields(msmgpu_ctx* ctx, int n_subjects, int nv, const double* data_xyz, int nt, const int32_t* tri, int D,
+                                  const double* feat_cm, int L, const double* labels, const double* centre, msmgpu_mesh* tpl,
+                                  msmgpu_octree* tpl_tree, double* d_fields);
+/* per-iteration state for the pair costs: rotated control points ROT[node]*label (rotations [S*ncp][9] = m_ROT,
+ * DiscreteGroupModel.cpp:77-86), patch radii range*spacings[S*ncp] (cpp:111), and d_fields [S][L][n_tpl][D] for ALL S subjects */
+msmgpu_status msmgpu_group_create(msmgpu_ctx* ctx, int simmeasure, int S, int ncp, int L, int D, msmgpu_mesh* tpl, const double* d_fields,
+                                  const double* rotations, const double* labels, const double* spacings, double range, msmgpu_group** out);
+void msmgpu_group_destroy(msmgpu_group* g);
+/* replaces: DiscreteGroupCostFunction::computePairwiseCost (DiscreteGroupCostFunction.cpp:54-97) for n requests (pair, la, lb);
+ * pairs [P][2] global node ids (subject*ncp + vertex, DiscreteGroupModel.cpp:37-55). Any sub-array of pairs may be passed (sharding). */
+msmgpu_status msmgpu_group_pair_costs(msmgpu_group* g, int P, const int32_t* pairs, int n, const int32_t* req_pair, const int32_t* req_la,
+                                      const int32_t* req_lb, double* out);
+/* the 4 combinations Fusion::optimize asks per pair for one candidate label (Fusion.h:164-174): out [P][4] =
+ * (cur,cur), (cur,label), (label,cur), (label,label) */
+msmgpu_status msmgpu_group_pair_batch(msmgpu_group* g, int P, const int32_t* pairs, const int32_t* labeling, int label, double* out);
 
 #ifdef __cplusplus
 }

@@ -86,6 +86,12 @@ _SIGNATURES = {
     "msmgpu_costfn_patches": (_i, [_vp, _vp, _vp]),
     "msmgpu_costfn_unary_table": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     "msmgpu_costfn_unary_table_dev": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
+    "msmgpu_weights_apply_batch_f64_dev": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
+    "msmgpu_group_fields": (_i, [_vp, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "msmgpu_group_create": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _d, _pp]),
+    "msmgpu_group_destroy": (None, [_vp]),
+    "msmgpu_group_pair_costs": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
+    "msmgpu_group_pair_batch": (_i, [_vp, _i, _vp, _vp, _i, _vp]),
     "msmgpu_costfn_set_cpgrid_ho": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp]),
     "msmgpu_costfn_triplet_costs": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "msmgpu_costfn_triplet_batch": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),

@@ -225,6 +225,34 @@ __global__ void __launch_bounds__(kCostThreads) k_unary_table(UnaryArgs a) {
     if (threadIdx.x == 0) a.out[(size_t)l * a.ncp + k] = __ldg(a.absw + k) * cost;
 }
 
+// CSR lists {i : |cp_k - src_i| < thr_k}, ascending i, for n_cp centres (count pass, scan, write pass); synchronises
+msmgpu_status build_patch_lists(int n_cp, const double* d_cp, int n_src, const double* d_src, const double* d_thr, DevBuf<int>& prow,
+                                DevBuf<int>& pmem, int& total, int& max_len, cudaStream_t s) {
+    DevBuf<int> count, d_tot;
+    MSM_CUDA(count.alloc(n_cp, s));
+    MSM_CUDA(d_tot.alloc(2, s));
+    MSM_CUDA(prow.alloc((size_t)n_cp + 1, s));
+    k_patch_members<0><<<n_cp, 256, 0, s>>>(n_src, d_cp, d_src, d_thr, count.p, nullptr, nullptr);
+    MSM_LAUNCH_CHECK();
+    MSM_TRY(exclusive_scan_i32(count.p, prow.p, n_cp, d_tot.p, s));
+    MSM_CUDA(cudaMemcpyAsync(prow.p + n_cp, d_tot.p, sizeof(int), cudaMemcpyDeviceToDevice, s));
+    MSM_CUDA(cudaMemsetAsync(d_tot.p + 1, 0, sizeof(int), s));
+    k_max_i32<<<(n_cp + 255) / 256, 256, 0, s>>>(n_cp, count.p, d_tot.p + 1);
+    MSM_LAUNCH_CHECK();
+    int h[2];
+    MSM_CUDA(cudaMemcpyAsync(h, d_tot.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    MSM_CUDA(cudaStreamSynchronize(s));
+    total = h[0];
+    max_len = h[1];
+    MSM_CUDA(pmem.alloc((size_t)total, s));
+    if (total > 0) {
+        k_patch_members<1><<<n_cp, 256, 0, s>>>(n_src, d_cp, d_src, d_thr, nullptr, prow.p, pmem.p);
+        MSM_LAUNCH_CHECK();
+    }
+    MSM_CUDA(cudaStreamSynchronize(s));
+    return MSMGPU_OK;
+}
+
 static size_t unary_smem_bytes(int max_patch, int D) {
     const size_t n_sims = (size_t)(max_patch > D ? max_patch : D);
     return 3 * (size_t)max_patch * sizeof(double) + n_sims * sizeof(double) + 3 * (size_t)max_patch * sizeof(int) + 16;
@@ -324,30 +352,8 @@ msmgpu_status msmgpu_costfn_set_cpgrid(msmgpu_costfn* c, int ncp, const double* 
     MSM_TRY(upload_vec(c->absw, absw, (size_t)ncp, s));
     MSM_TRY(upload_vec(c->chord_thr, thr.data(), (size_t)ncp, s));
     if (cfw_rows > 0) MSM_TRY(upload_rows(c->cfw, cfw, cfw_rows, c->nsrc, s));
-    // patch lists
-    DevBuf<int> count, d_tot;
-    MSM_CUDA(count.alloc(ncp, s));
-    MSM_CUDA(d_tot.alloc(2, s));
-    MSM_CUDA(c->prow.alloc((size_t)ncp + 1, s));
-    k_patch_members<0><<<ncp, 256, 0, s>>>(c->nsrc, c->cp_xyz.p, c->src_xyz.p, c->chord_thr.p, count.p, nullptr, nullptr);
-    MSM_LAUNCH_CHECK();
-    MSM_TRY(exclusive_scan_i32(count.p, c->prow.p, ncp, d_tot.p, s));
-    MSM_CUDA(cudaMemcpyAsync(c->prow.p + ncp, d_tot.p, sizeof(int), cudaMemcpyDeviceToDevice, s));
-    MSM_CUDA(cudaMemsetAsync(d_tot.p + 1, 0, sizeof(int), s));
-    k_max_i32<<<(ncp + 255) / 256, 256, 0, s>>>(ncp, count.p, d_tot.p + 1);
-    MSM_LAUNCH_CHECK();
-    int h[2];
-    MSM_CUDA(cudaMemcpyAsync(h, d_tot.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
-    MSM_CUDA(cudaStreamSynchronize(s));
-    c->n_patch = h[0];
-    c->max_patch = h[1];
+    MSM_TRY(build_patch_lists(ncp, c->cp_xyz.p, c->nsrc, c->src_xyz.p, c->chord_thr.p, c->prow, c->pmem, c->n_patch, c->max_patch, s));
     c->n_patch_rows = ncp;
-    MSM_CUDA(c->pmem.alloc((size_t)c->n_patch, s));
-    if (c->n_patch > 0) {
-        k_patch_members<1><<<ncp, 256, 0, s>>>(c->nsrc, c->cp_xyz.p, c->src_xyz.p, c->chord_thr.p, nullptr, c->prow.p, c->pmem.p);
-        MSM_LAUNCH_CHECK();
-    }
-    MSM_CUDA(cudaStreamSynchronize(s));
     return MSMGPU_OK;
 }
 

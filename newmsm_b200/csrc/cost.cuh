@@ -23,6 +23,11 @@ struct msmgpu_costfn {
 
 namespace msm {
 
+double patch_chord_threshold(double limit);   // cost.cu: host bisection, member <=> chord < threshold
+bool host_rotation_matrix(const double* ci, const double* index, double* R);   // api.cu
+msmgpu_status build_patch_lists(int n_cp, const double* d_cp, int n_src, const double* d_src, const double* d_thr, DevBuf<int>& prow,
+                                DevBuf<int>& pmem, int& total, int& max_len, cudaStream_t s);
+
 // ------------------------------------------------------------------------------------------
 // similarities (sequential FP64, similarities.cpp:129-188), element access through functors
 // ------------------------------------------------------------------------------------------

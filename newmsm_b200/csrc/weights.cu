@@ -545,6 +545,14 @@ msmgpu_status msmgpu_weights_apply_batch_f32_dev(msmgpu_ctx* ctx, int n, msmgpu_
     return csr_apply_batch<float>(ctx, n, ws, D, d_in, d_out);
 }
 
+msmgpu_status msmgpu_weights_apply_batch_f64_dev(msmgpu_ctx* ctx, int n, msmgpu_weights* const* ws, int D, const double* const* d_in, double* const* d_out) {
+    if (!ctx || n <= 0 || !ws || D <= 0 || !d_in || !d_out) return fail(MSMGPU_ERR_INVALID, "weights_apply_batch_f64: bad arguments");
+    for (int i = 0; i < n; ++i)
+        if (!ws[i] || !d_in[i] || !d_out[i]) return fail(MSMGPU_ERR_INVALID, "weights_apply_batch_f64: NULL entry");
+    MSM_CUDA(cudaSetDevice(ctx->device));
+    return csr_apply_batch<double>(ctx, n, ws, D, d_in, d_out);
+}
+
 // metric_resample (resampler.cpp:304-309) on host buffers, FP64 payload: channel-major in/out like Mesh::pvalues
 msmgpu_status msmgpu_metric_resample(msmgpu_mesh* in_mesh, msmgpu_mesh* low_mesh, int D, const double* feat_in, double* feat_out) {
     if (!in_mesh || !low_mesh || D <= 0 || !feat_in || !feat_out) return fail(MSMGPU_ERR_INVALID, "metric_resample: bad arguments");

@@ -81,6 +81,8 @@ class Oracle:
             L.orc_patch_membership.argtypes = [_i, _vp, _i, _vp, _vp, _d, _vp, _vp, _i, _i]
             L.orc_unary_costs.argtypes = [_i, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp,
                                           _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i]
+            L.orc_group_fields.argtypes = [_i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i]
+            L.orc_group_pair_costs.argtypes = [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _d, _vp, _i, _vp, _vp, _vp, _vp, _i]
             L.orc_ho_patches.argtypes = [_i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i]
             L.orc_triplet_costs.argtypes = [_i, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp,
                                             _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _d, _d, _d, _d, _d, _vp, _i]
@@ -258,6 +260,29 @@ def oracle_triplet_costs(kind, simmeasure, tree, cp_xyz, orig_cp_xyz, rot, label
                                        sf.shape[0], _p(sf), _p(rf), cfw_rows, _p(cfw_a), _p(absw), lambda_, mu, kappa, k_exp, rexp, _p(out), nthreads)
     if e:
         raise RuntimeError("oracle triplet costs: a query failed")
+    return out
+
+
+def oracle_group_fields(data_xyz, tri, feat, labels, centre, tpl_xyz, tpl_tri, nthreads=8):
+    """-> [S][L][D][n_tpl] (channel-major per (subject,label))"""
+    xyz, tri, feat, labels, centre = _f64(data_xyz), _i32(tri), _f64(feat), _f64(labels), _f64(centre)
+    tx, tt = _f64(tpl_xyz), _i32(tpl_tri)
+    S, nv, D, L = xyz.shape[0], xyz.shape[1], feat.shape[1], len(labels)
+    out = np.zeros((S, L, D, len(tx)))
+    e = Oracle.lib().orc_group_fields(S, nv, _p(xyz), len(tri), _p(tri), D, _p(feat), L, _p(labels), _p(centre), len(tx), _p(tx), len(tt), _p(tt),
+                                      _p(out), nthreads)
+    if e:
+        raise RuntimeError("oracle group fields: a query failed")
+    return out
+
+
+def oracle_group_pair_costs(simmeasure, ncp, tpl_xyz, fields, rot, labels, spacings, range_, pairs, req_pair, req_la, req_lb, nthreads=8):
+    tx, fields, rot, labels, sp = _f64(tpl_xyz), _f64(fields), _f64(rot), _f64(labels), _f64(spacings).reshape(-1)
+    pairs, rp, la, lb = _i32(pairs), _i32(req_pair), _i32(req_la), _i32(req_lb)
+    S, L, D = fields.shape[0], fields.shape[1], fields.shape[2]
+    out = np.zeros(len(rp))
+    Oracle.lib().orc_group_pair_costs(simmeasure, S, ncp, L, D, len(tx), _p(tx), _p(fields), _p(rot), _p(labels), _p(sp), float(range_), _p(pairs),
+                                      len(rp), _p(rp), _p(la), _p(lb), _p(out), nthreads)
     return out
 
 

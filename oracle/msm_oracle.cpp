@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <iterator>
 #include <limits>
 #include <map>
 #include <numeric>
@@ -879,6 +880,77 @@ int orc_triplet_costs(int kind, int simmeasure, const orc_octree* T, int ncp, co
         out[r] = likelihood + lambda * std::pow(W, rexp);
     }
     return err;
+}
+
+} // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Groupwise (gMSM): DiscreteGroupModel::get_patch_data (DiscreteGroupModel.cpp:88-121) and
+// DiscreteGroupCostFunction::computePairwiseCost (DiscreteGroupCostFunction.cpp:54-97).
+// PARITY UNPINNED for the same reason as the triplet costs (meshreg library not buildable here);
+// the resampling inside is the pinned adaptive-barycentric path.
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+// fields[s][l][d][p] (channel-major per (s,l), like Mesh::pvalues): subject s's data mesh rigidly "rotated" by label l
+// (estimate_rotation_matrix(centre, vertex) * label per vertex; label 0 = no rotation) and metric_resampled onto the template.
+int orc_group_fields(int S, int nv, const double* data_xyz /*[S][nv][3]*/, int nt, const int* tri, int D, const double* feat /*[S][D][nv]*/,
+                     int L, const double* labels, const double* centre, int n_tpl, const double* tpl_xyz, int nt_tpl, const int* tpl_tri,
+                     double* fields /*[S][L][D][n_tpl]*/, int nthreads) {
+    int err = 0;
+    #pragma omp parallel for collapse(2) num_threads(nthreads > 0 ? nthreads : 1)
+    for (int s = 0; s < S; ++s)
+        for (int l = 0; l < L; ++l) {
+            std::vector<double> xyz(data_xyz + (size_t)s * nv * 3, data_xyz + (size_t)(s + 1) * nv * 3);
+            if (l > 0)
+                for (int p = 0; p < nv; ++p) {
+                    double R[9];
+                    orc_rotation_matrix(centre, &xyz[3 * (size_t)p], R);
+                    const P3 q = matvec(R, P3{labels[3 * l], labels[3 * l + 1], labels[3 * l + 2]});
+                    xyz[3 * (size_t)p] = q.X; xyz[3 * (size_t)p + 1] = q.Y; xyz[3 * (size_t)p + 2] = q.Z;
+                }
+            if (orc_metric_resample(nv, xyz.data(), nt, tri, n_tpl, tpl_xyz, nt_tpl, tpl_tri, D, feat + (size_t)s * D * nv,
+                                    fields + ((size_t)s * L + l) * D * n_tpl, 1)) {
+                #pragma omp critical
+                err = 1;
+            }
+        }
+    return err;
+}
+
+// pair cost for n requests (pair, la, lb). pairs [P][2] global node ids (subject * ncp + vertex); rot [S*ncp][9];
+// spacings [S*ncp]; patch(s,v,l) = template vertices p with 2R asin(|rot*label_l - tpl_p| / 2R) < range * spacing.
+int orc_group_pair_costs(int simmeasure, int S, int ncp, int L, int D, int n_tpl, const double* tpl_xyz, const double* fields,
+                         const double* rot, const double* labels, const double* spacings, double range, const int* pairs,
+                         int n, const int* req_pair, const int* req_la, const int* req_lb, double* out, int nthreads) {
+    #pragma omp parallel for num_threads(nthreads > 0 ? nthreads : 1)
+    for (int r = 0; r < n; ++r) {
+        const int nodes[2] = {pairs[2 * req_pair[r]], pairs[2 * req_pair[r] + 1]};
+        const int lab[2] = {req_la[r], req_lb[r]};
+        std::vector<int> patch[2];
+        for (int k = 0; k < 2; ++k) {
+            const P3 rcp = matvec(rot + 9 * (size_t)nodes[k], P3{labels[3 * lab[k]], labels[3 * lab[k] + 1], labels[3 * lab[k] + 2]});
+            for (int p = 0; p < n_tpl; ++p) {
+                const P3 t{tpl_xyz[3 * p], tpl_xyz[3 * p + 1], tpl_xyz[3 * p + 2]};
+                if ((2 * RAD * std::asin(norm(sub(rcp, t)) / (2 * RAD))) < range * spacings[nodes[k]]) patch[k].push_back(p);
+            }
+        }
+        std::vector<int> common;
+        std::set_intersection(patch[0].begin(), patch[0].end(), patch[1].begin(), patch[1].end(), std::back_inserter(common));
+        const int n_c = (int)common.size();
+        if (n_c == 0) { out[r] = std::numeric_limits<double>::quiet_NaN(); continue; }   // the reference dereferences an empty vector here
+        const int sa = nodes[0] / ncp, sb = nodes[1] / ncp;
+        std::vector<double> a(n_c), b(n_c), w(n_c, 1.0);
+        double cost = 0.0;
+        for (int d = 0; d < D; ++d) {
+            const double* fa = fields + (((size_t)sa * L + lab[0]) * D + d) * n_tpl;
+            const double* fb = fields + (((size_t)sb * L + lab[1]) * D + d) * n_tpl;
+            for (int i = 0; i < n_c; ++i) { a[i] = fa[common[i]]; b[i] = fb[common[i]]; }
+            cost += orc_sim_for_min(simmeasure, n_c, a.data(), b.data(), w.data());
+        }
+        out[r] = cost / D;
+    }
+    return 0;
 }
 
 } // extern "C"

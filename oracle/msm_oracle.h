@@ -102,6 +102,14 @@ int orc_triplet_costs(int kind, int simmeasure, const orc_octree* T, int ncp, co
                       const double* ref_feat, int cfw_rows, const double* cfw, const double* absw,
                       double lambda, double mu, double kappa, double k_exp, double rexp, double* out, int nthreads);
 
+/* gMSM, PARITY UNPINNED: DiscreteGroupModel::get_patch_data (DiscreteGroupModel.cpp:88-121) as resampled fields
+ * [S][L][D][n_tpl], and DiscreteGroupCostFunction::computePairwiseCost (DiscreteGroupCostFunction.cpp:54-97). */
+int orc_group_fields(int S, int nv, const double* data_xyz, int nt, const int* tri, int D, const double* feat, int L, const double* labels,
+                     const double* centre, int n_tpl, const double* tpl_xyz, int nt_tpl, const int* tpl_tri, double* fields, int nthreads);
+int orc_group_pair_costs(int simmeasure, int S, int ncp, int L, int D, int n_tpl, const double* tpl_xyz, const double* fields,
+                         const double* rot, const double* labels, const double* spacings, double range, const int* pairs,
+                         int n, const int* req_pair, const int* req_la, const int* req_lb, double* out, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -442,3 +442,64 @@ def test_ho_triplet_likelihood(R, oracle_built, kind, D, sim):
                                             s["src"], prow, pmem, s["src_feat"], s["ref_feat"], cfw, s["absw"], 0.05)
     assert rel_close(got, ref, 4e-16)
     assert (got == ref).mean() > 0.99
+
+
+# ---------------------------------------------------------------------------------------------
+# groupwise (gMSM): resampled fields per (subject,label) and pair costs (parity unpinned: against our restatement)
+# ---------------------------------------------------------------------------------------------
+def group_setup(S=3, cp_level=2, data_level=4, tpl_level=4, D=2):
+    cp0, cp_tri = synth.icosphere(cp_level)
+    dxyz0, dtri = synth.icosphere(data_level)
+    tpl, tpl_tri = synth.icosphere(tpl_level)
+    tpl = synth.rotate_sphere(tpl, 0.004, -0.003, 0.002)
+    data = np.stack([synth.smooth_warp(dxyz0, max_disp=2.0, seed=40 + s) for s in range(S)])
+    cps = np.stack([synth.smooth_warp(cp0, max_disp=1.5, seed=60 + s) for s in range(S)])
+    feat = np.stack([synth.smooth_fields(data[s], D, seed0=100, noise=0.1, noise_seed=7 + s) for s in range(S)])
+    centre = np.array([0.0, 0.0, 100.0])
+    labels = [centre]
+    for k in range(6):
+        p = centre + 6.0 * np.array([np.cos(k * np.pi / 3), np.sin(k * np.pi / 3), 0.0])
+        labels.append(p / np.linalg.norm(p) * 100)
+    return dict(cp_tri=cp_tri, dtri=dtri, tpl=tpl, tpl_tri=tpl_tri, data=data, cps=cps, feat=feat, centre=centre, labels=np.array(labels))
+
+
+@pytest.mark.parametrize("sim", [2, 1])
+def test_group_fields_and_pair_costs(R, oracle_built, sim):
+    from newmsm_b200 import group_cost as GC
+    g = group_setup()
+    S, ncp = g["cps"].shape[0], g["cps"].shape[1]
+    M = GC.DiscreteGroupModel(R.Mesh(g["tpl"], g["tpl_tri"]), simmeasure=sim)
+    spacings = M.get_spacings(g["cps"], g["cp_tri"])
+    rot = M.get_rotations(g["centre"], g["cps"])
+    pairs = M.estimate_pairs(g["cps"], g["cp_tri"])
+    assert len(pairs) == S * (S - 1) // 2 * ncp
+    # pair partner = nearest control point of subject B (DiscreteGroupModel.cpp:51)
+    a0, b0 = pairs[5]
+    sb = b0 // ncp
+    d = np.linalg.norm(g["cps"][sb] - g["cps"][a0 // ncp][a0 % ncp], axis=1)
+    assert d[b0 % ncp] <= d.min() * 1.5
+    fields = M.get_patch_data(g["data"], g["dtri"], g["feat"], g["labels"], g["centre"], rot, spacings, 1.0)
+    ref_fields = oracle_built.oracle_group_fields(g["data"], g["dtri"], g["feat"], g["labels"], g["centre"], g["tpl"], g["tpl_tri"])
+    got_fields = fields.cpu().numpy().transpose(0, 1, 3, 2)            # [S][L][D][n_tpl]
+    assert np.array_equal(got_fields, ref_fields)                      # FP64 adaptive resampling: bit-exact
+    rng = np.random.default_rng(9)
+    n, L = 3000, len(g["labels"])
+    rp, la, lb = rng.integers(0, len(pairs), n), rng.integers(0, L, n), rng.integers(0, L, n)
+    got = M.computePairwiseCostList(pairs, rp, la, lb)
+    ref = oracle_built.oracle_group_pair_costs(sim, ncp, g["tpl"], ref_fields, rot, g["labels"], spacings, 1.0, pairs, rp, la, lb)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    assert ok.mean() > 0.9
+    assert np.array_equal(got[ok], ref[ok])
+    # Fusion's 4 combinations == the list form
+    labeling = rng.integers(0, L, S * ncp).astype(np.int32)
+    batch = M.computePairwiseCostsForLabel(pairs, labeling, 3)
+    P = len(pairs)
+    pp = np.repeat(np.arange(P), 4); combo = np.tile(np.arange(4), P)
+    la4 = np.where(combo & 2, 3, labeling[pairs[pp, 0]]); lb4 = np.where(combo & 1, 3, labeling[pairs[pp, 1]])
+    lst = M.computePairwiseCostList(pairs, pp, la4, lb4)
+    assert np.array_equal(np.nan_to_num(batch.reshape(-1), nan=-1.0), np.nan_to_num(lst, nan=-1.0))
+    # a subject compared with itself under the same label has perfectly correlated patches: cost 0 (corr) / 0 (SSD)
+    self_pairs = np.array([[v, v] for v in range(ncp)], dtype=np.int32)
+    z = M.computePairwiseCostList(self_pairs, np.arange(ncp), np.full(ncp, 2), np.full(ncp, 2))
+    assert np.nanmax(np.abs(z)) < 1e-12
