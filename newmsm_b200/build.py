@@ -38,41 +38,59 @@ def _flags(extra=()):
             "-ccbin", _host_cxx(), "-Xcompiler", "-fPIC,-fopenmp,-O2,-ffp-contract=off", *extra]
 
 
-def _stale(target: str, deps) -> bool:
-    if not os.path.exists(target):
-        return True
-    t = os.path.getmtime(target)
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+def _digest(paths) -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for p in sorted(paths):
+        if os.path.exists(p):
+            h.update(os.path.basename(p).encode())
+            h.update(open(p, "rb").read())
+    h.update(" ".join(_flags()).encode())
+    return h.hexdigest()
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu into lib/libmsmgpu.so when the sources changed (content hash, not mtime: the GPU box receives a
+    copy of the tree with fresh timestamps and must use the library built here)."""
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     hdrs = [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS]
+    stamp = os.path.join(LIBDIR, "libmsmgpu.sha256")
+    want = _digest(srcs + hdrs)
+    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == want:
+        return LIB
+    try:
+        nvcc = _nvcc()
+    except RuntimeError:
+        if os.path.exists(LIB):   # no compiler here: trust the shipped library
+            return LIB
+        raise
     os.makedirs(OBJDIR, exist_ok=True)
     os.makedirs(LIBDIR, exist_ok=True)
-    nvcc = _nvcc()
-    jobs = []
-    objs = []
+    jobs, objs = [], []
     for s in srcs:
         o = os.path.join(OBJDIR, os.path.basename(s)[:-3] + ".o")
+        ostamp = o + ".sha256"
         objs.append(o)
-        if force or _stale(o, [s, *hdrs, __file__]):
+        d = _digest([s] + hdrs)
+        if force or not os.path.exists(o) or not os.path.exists(ostamp) or open(ostamp).read().strip() != d:
             extra = ["-Xptxas", "-v"] if verbose else []
-            jobs.append([nvcc, *_flags(extra), "-c", s, "-o", o])
+            jobs.append(([nvcc, *_flags(extra), "-c", s, "-o", o], ostamp, d))
     if jobs:
         with cf.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
-            for cmd, res in zip(jobs, ex.map(lambda c: subprocess.run(c, capture_output=True, text=True), jobs)):
-                if verbose or res.returncode:
-                    sys.stderr.write(res.stdout + res.stderr)
-                if res.returncode:
-                    raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    if jobs or force or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-ccbin", _host_cxx(), "-gencode", "arch=compute_100a,code=sm_100a",
-               "-Xcompiler", "-fPIC,-fopenmp", "-o", LIB, *objs, "-lgomp"]
-        res = subprocess.run(cmd, capture_output=True, text=True)
-        if res.returncode:
-            sys.stderr.write(res.stdout + res.stderr)
-            raise RuntimeError("link failed: " + " ".join(cmd))
+            results = list(ex.map(lambda j: subprocess.run(j[0], capture_output=True, text=True), jobs))
+        for (cmd, ostamp, d), res in zip(jobs, results):
+            if verbose or res.returncode:
+                sys.stderr.write(res.stdout + res.stderr)
+            if res.returncode:
+                raise RuntimeError("nvcc failed: " + " ".join(cmd))
+            open(ostamp, "w").write(d)
+    cmd = [nvcc, "-shared", "-ccbin", _host_cxx(), "-gencode", "arch=compute_100a,code=sm_100a",
+           "-Xcompiler", "-fPIC,-fopenmp", "-o", LIB, *objs, "-lgomp"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("link failed: " + " ".join(cmd))
+    open(stamp, "w").write(want)
     return LIB
 
 
