@@ -71,6 +71,13 @@ msmgpu_status msmgpu_mesh_shape(msmgpu_mesh* m, int* nv, int* nt);
 /* replaces: Mesh::pvalues / set_pvalues (mesh.h:44, mesh.cpp:206) as a device-resident FP32 payload: channel-major host floats
  * [D][nv] uploaded ONCE and reused by msmgpu_mesh_bary_resample_f32 / msmgpu_mesh_metric_resample_f32 */
 msmgpu_status msmgpu_mesh_set_features_f32(msmgpu_mesh* m, int D, const float* feat_cm);
+/* Triangle::area is cached when a Triangle is constructed (triangle.cpp:31,39) and NOT refreshed by Mesh::set_coord; only a Mesh
+ * copy/assignment recomputes it (mesh.cpp:37-53). compute_vertex_area (mesh.cpp:1275) reads the cached value, so a reference
+ * Mesh that was copied from A and then moved still has A's vertex areas (e.g. DiscreteGroupModel.cpp:94-103). Mirror of that
+ * state: vertex areas of `m` (msmgpu_mesh_vertex_areas, the adaptive weights) are taken from `area_mesh`'s geometry.
+ * area_mesh = NULL (or m) restores "freshly copied" semantics. Same context, same nv/nt; area_mesh must outlive its use. */
+msmgpu_status msmgpu_mesh_set_area_source(msmgpu_mesh* m, msmgpu_mesh* area_mesh);
+
 /* replaces: compute_vertex_area (msm-newresampler/src/mesh.cpp:1275) for all vertices */
 msmgpu_status msmgpu_mesh_vertex_areas(msmgpu_mesh* m, double* out);
 

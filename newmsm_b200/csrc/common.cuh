@@ -102,6 +102,7 @@ struct msmgpu_mesh {
     msm::DevBuf<float> feat;   // optional resident payload, vertex-major rows [nv][feat_D] (Mesh::pvalues, mesh.h:44)
     int feat_D = 0;
     bool tables_dirty = false;   // rec / aabb / cull not yet computed from xyz (msm::ensure_tables batches that work)
+    msmgpu_mesh* area_source = nullptr;   // mesh whose geometry the cached Triangle areas belong to (msmgpu_mesh_set_area_source)
 };
 
 struct msmgpu_octree {

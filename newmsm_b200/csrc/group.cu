@@ -281,6 +281,9 @@ msmgpu_status msmgpu_group_fields(msmgpu_ctx* ctx, int n_subjects, int nv, const
         std::vector<msmgpu_weights*> ws(L, nullptr);
         msmgpu_status st = MSMGPU_OK;
         for (int l = 0; l < L && st == MSMGPU_OK; ++l) st = msmgpu_mesh_create_dev(ctx, nv, d_rot.p + 3 * (size_t)l * nv, nt, d_tri.p, &meshes[l]);
+        // `rotated_mesh` is a COPY of the data mesh that is then moved with set_coord (DiscreteGroupModel.cpp:94-103): its cached
+        // triangle areas, hence the source vertex areas metric_resample uses, are those of the un-moved mesh = meshes[0]
+        for (int l = 1; l < L && st == MSMGPU_OK; ++l) st = msmgpu_mesh_set_area_source(meshes[l], meshes[0]);
         if (st == MSMGPU_OK) st = msmgpu_adaptive_weights_batch(ctx, L, meshes.data(), nullptr, tpl, tpl_tree, ws.data());
         if (st == MSMGPU_OK) {
             std::vector<const double*> in(L, d_feat_rows.p);

@@ -188,6 +188,11 @@ __global__ void k_bucket_sum(int nkeys, const int* __restrict__ ptr, const doubl
 // vertex areas of a batch of meshes, concatenated: d_out[key_off[s] + v]
 static msmgpu_status vertex_areas_batch(msmgpu_ctx* ctx, int S, msmgpu_mesh* const* meshes, const std::vector<int>& key_off, double* d_out) {
     cudaStream_t s = ctx->stream;
+    // Triangle::area is cached when a Triangle is constructed and survives Mesh::set_coord (triangle.cpp:31,39): a mesh that was
+    // copied and then moved keeps the areas of the geometry it was copied from -> read the records of that mesh instead
+    std::vector<msmgpu_mesh*> src(S);
+    for (int i = 0; i < S; ++i) src[i] = meshes[i]->area_source ? meshes[i]->area_source : meshes[i];
+    meshes = src.data();
     MSM_TRY(ensure_tables(ctx, S, meshes));
     std::vector<const int*> h_tri(S);
     std::vector<const TriRec*> h_rec(S);
@@ -454,6 +459,13 @@ msmgpu_status csr_apply_f64(msmgpu_weights* W, int D, const double* d_in, double
 using namespace msm;
 
 extern "C" {
+
+msmgpu_status msmgpu_mesh_set_area_source(msmgpu_mesh* m, msmgpu_mesh* area_mesh) {
+    if (!m || (area_mesh && (area_mesh->ctx != m->ctx || area_mesh->nv != m->nv || area_mesh->nt != m->nt || area_mesh->area_source)))
+        return fail(MSMGPU_ERR_INVALID, "mesh_set_area_source: meshes must share the context and the topology");
+    m->area_source = area_mesh == m ? nullptr : area_mesh;
+    return MSMGPU_OK;
+}
 
 msmgpu_status msmgpu_mesh_vertex_areas(msmgpu_mesh* m, double* out) {
     if (!m || !out) return fail(MSMGPU_ERR_INVALID, "mesh_vertex_areas: bad arguments");

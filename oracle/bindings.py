@@ -15,6 +15,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(_HERE, "libmsm_oracle.so")
 REF_SO = os.path.join(_HERE, "_ref", "libref_newresampler.so")
+REFMR_SO = os.path.join(_HERE, "_ref", "libref_newmeshreg.so")
+NEWMSM_REF = os.path.join(_HERE, "_ref", "newmsm_ref")
 REFERENCE_ROOT = "/root/reference"
 
 _vp, _i, _d = C.c_void_p, C.c_int, C.c_double
@@ -26,13 +28,17 @@ def build(ref: bool | None = None) -> None:
     if ref is None:
         ref = os.path.isdir(REFERENCE_ROOT)
     if ref:
-        subprocess.run(["make", "-s", "-C", _HERE, "ref"], check=True)
+        subprocess.run(["make", "-s", "-j8", "-C", _HERE, "ref", "refmr"], check=True)
         if os.path.exists(os.path.join(os.path.dirname(_HERE), "newmsm_b200", "lib", "libmsmgpu.so")):
             subprocess.run(["make", "-s", "-C", _HERE, "adapter_check"], check=True)   # in-process drop-in check (C++ adapter)
 
 
 def have_ref() -> bool:
     return os.path.exists(REF_SO)
+
+
+def have_refmr() -> bool:
+    return os.path.exists(REFMR_SO)
 
 
 def _p(a):
@@ -446,3 +452,118 @@ def ref_rotation_matrix(ci, index):
     a, b, R = _f64(ci), _f64(index), np.zeros(9)
     Ref.lib().ref_rotation_matrix(_p(a), _p(b), _p(R))
     return R.reshape(3, 3)
+
+
+# --------------------------------------------------------------------------------------
+# compiled reference, registration library (oracle/_ref/libref_newmeshreg.so, oracle/ref_meshreg_driver.cpp)
+# --------------------------------------------------------------------------------------
+class RefMR:
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            if not have_refmr():
+                raise RuntimeError("oracle/_ref/libref_newmeshreg.so not built (needs /root/reference; run `make -C oracle refmr`)")
+            L = C.CDLL(REFMR_SO)
+            for fn in ("refmr_unary", "refmr_triplet", "refmr_pairwise_reg", "refmr_group_pair_costs", "refmr_group_triplet_costs", "refmr_label_sets"):
+                getattr(L, fn).restype = _i
+            L.refmr_unary.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp,
+                                      _i, _vp, _vp, _vp, _d, _vp, _vp, _vp, _i, _vp, _i]
+            L.refmr_triplet.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp,
+                                        _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp,
+                                        _d, _d, _d, _d, _d, _i, _vp, _vp, _vp, _i, _i]
+            L.refmr_pairwise_reg.argtypes = [_i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _d, _d, _d, _i, _vp, _vp, _vp, _vp]
+            L.refmr_group_pair_costs.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _d, _i, _vp,
+                                                 _i, _vp, _vp, _vp, _vp, _vp, _i]
+            L.refmr_group_triplet_costs.argtypes = [_i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _d, _d, _d, _d, _d, _i, _vp, _vp, _vp, _vp, _vp]
+            L.refmr_label_sets.argtypes = [_i, _d, _vp, _vp, _i, _vp, _vp]
+            cls._lib = L
+        return cls._lib
+
+
+def refmr_unary(kind, simmeasure, tgt_xyz, tgt_tri, cp_xyz, cp_tri, rot, labels, src_xyz, src_tri, src_feat, ref_feat, cfw, absw, maxsep, range_,
+                want_costs=True, nthreads=1):
+    """The reference's get_source_data() + computeUnaryCosts(). -> (costs [L][ncp] | None, rowptr, members, AbsoluteWeights used)"""
+    tx, tt, cp, ct, rot, labels = _f64(tgt_xyz), _i32(tgt_tri), _f64(cp_xyz), _i32(cp_tri), _f64(rot), _f64(labels)
+    sx, st = _f64(src_xyz), _i32(src_tri)
+    sf, rf = _f64(np.atleast_2d(src_feat)), _f64(np.atleast_2d(ref_feat))
+    cfw_rows = 0 if cfw is None else np.atleast_2d(cfw).shape[0]
+    cfw_a = None if cfw is None else _f64(np.atleast_2d(cfw))
+    absw_a = None if absw is None else _f64(absw)
+    ms = _f64(maxsep)
+    out = np.zeros((len(labels), len(cp))) if want_costs else None
+    rowptr = np.zeros(len(cp) + 1, np.int32)
+    cap = 64 * len(sx)
+    mem = np.zeros(cap, np.int32)
+    absw_out = np.zeros(len(cp))
+    n = RefMR.lib().refmr_unary(kind, simmeasure, len(tx), _p(tx), len(tt), _p(tt), len(cp), _p(cp), len(ct), _p(ct), _p(rot), len(labels), _p(labels),
+                                len(sx), _p(sx), len(st), _p(st), sf.shape[0], _p(sf), _p(rf), cfw_rows, _p(cfw_a), _p(absw_a), _p(ms), float(range_),
+                                _p(out), _p(rowptr), _p(mem), cap, _p(absw_out), nthreads)
+    if n < 0 or n > cap:
+        raise RuntimeError("reference unary costs failed")
+    return out, rowptr, mem[:n].copy(), absw_out
+
+
+def refmr_triplet(kind, simmeasure, tgt_xyz, tgt_tri, cp_xyz, cp_tri, orig_cp_xyz, rot, labels, triplets, req_t, req_la, req_lb, req_lc,
+                  src_xyz, src_tri, src_feat, ref_feat, cfw, absw, lambda_, mu=0.4, kappa=1.6, k_exp=2.0, rexp=2.0, rmode=3, nthreads=8):
+    """The reference's computeTripletCost for a request list. -> (costs [n], HO patch rowptr, members)"""
+    tx, tt, cp, ct, org, rot, labels = _f64(tgt_xyz), _i32(tgt_tri), _f64(cp_xyz), _i32(cp_tri), _f64(orig_cp_xyz), _f64(rot), _f64(labels)
+    trip, rt, la, lb, lc = _i32(triplets), _i32(req_t), _i32(req_la), _i32(req_lb), _i32(req_lc)
+    sx, st = _f64(src_xyz), _i32(src_tri)
+    sf, rf = _f64(np.atleast_2d(src_feat)), _f64(np.atleast_2d(ref_feat))
+    cfw_rows = 0 if cfw is None else np.atleast_2d(cfw).shape[0]
+    cfw_a = None if cfw is None else _f64(np.atleast_2d(cfw))
+    absw_a = None if absw is None else _f64(absw)
+    out = np.zeros(len(rt))
+    rowptr, mem = np.zeros(len(ct) + 1, np.int32), np.zeros(len(sx), np.int32)
+    n = RefMR.lib().refmr_triplet(kind, simmeasure, len(tx), _p(tx), len(tt), _p(tt), len(cp), _p(cp), len(ct), _p(ct), _p(org), _p(rot), len(labels), _p(labels),
+                                  len(trip), _p(trip), len(rt), _p(rt), _p(la), _p(lb), _p(lc), len(sx), _p(sx), len(st), _p(st), sf.shape[0], _p(sf), _p(rf),
+                                  cfw_rows, _p(cfw_a), _p(absw_a), lambda_, mu, kappa, k_exp, rexp, rmode, _p(out), _p(rowptr), _p(mem), len(sx), nthreads)
+    if n < 0:
+        raise RuntimeError("reference triplet costs failed")
+    return out, rowptr, mem[:n].copy()
+
+
+def refmr_pairwise_reg(cp_xyz, cp_tri, rot, labels, pairs, lambda_, rexp, mvdmax, req_pair, req_la, req_lb):
+    cp, ct, rot, labels, pairs = _f64(cp_xyz), _i32(cp_tri), _f64(rot), _f64(labels), _i32(pairs)
+    rp, la, lb = _i32(req_pair), _i32(req_la), _i32(req_lb)
+    out = np.zeros(len(rp))
+    if RefMR.lib().refmr_pairwise_reg(len(cp), _p(cp), len(ct), _p(ct), _p(rot), len(labels), _p(labels), len(pairs), _p(pairs), lambda_, rexp, mvdmax,
+                                      len(rp), _p(rp), _p(la), _p(lb), _p(out)):
+        raise RuntimeError("reference pairwise regulariser failed")
+    return out
+
+
+def refmr_group_pair_costs(simmeasure, data_xyz, tri, feat, labels, centre, tpl_xyz, tpl_tri, ncp, rot, spacings, range_, pairs, req_pair, req_la, req_lb,
+                           want_fields=False, nthreads=8):
+    xyz, tri, feat, labels, centre = _f64(data_xyz), _i32(tri), _f64(feat), _f64(labels), _f64(centre)
+    tx, tt, rot, sp, pairs = _f64(tpl_xyz), _i32(tpl_tri), _f64(rot), _f64(spacings).reshape(-1), _i32(pairs)
+    rp, la, lb = _i32(req_pair), _i32(req_la), _i32(req_lb)
+    S, nv, D, L = xyz.shape[0], xyz.shape[1], feat.shape[1], len(labels)
+    out = np.zeros(len(rp))
+    fields = np.full((S, L, D, len(tx)), np.nan) if want_fields else None
+    if RefMR.lib().refmr_group_pair_costs(simmeasure, S, nv, _p(xyz), len(tri), _p(tri), D, _p(feat), L, _p(labels), _p(centre), len(tx), _p(tx), len(tt), _p(tt),
+                                          ncp, _p(rot), _p(sp), float(range_), len(pairs), _p(pairs), len(rp), _p(rp), _p(la), _p(lb), _p(out), _p(fields), nthreads):
+        raise RuntimeError("reference group pair costs failed")
+    return (out, fields) if want_fields else out
+
+
+def refmr_group_triplet_costs(cp_xyz, orig_xyz, cp_tri, rot, labels, triplets, lambda_, mu, kappa, k_exp, rexp, req_t, req_la, req_lb, req_lc):
+    cp, org, ct, rot, labels, trip = _f64(cp_xyz), _f64(orig_xyz), _i32(cp_tri), _f64(rot), _f64(labels), _i32(triplets)
+    rt, la, lb, lc = _i32(req_t), _i32(req_la), _i32(req_lb), _i32(req_lc)
+    out = np.zeros(len(rt))
+    if RefMR.lib().refmr_group_triplet_costs(cp.shape[0], cp.shape[1], _p(cp), _p(org), len(ct), _p(ct), _p(rot), len(labels), _p(labels), len(trip), _p(trip),
+                                             lambda_, mu, kappa, k_exp, rexp, len(rt), _p(rt), _p(la), _p(lb), _p(lc), _p(out)):
+        raise RuntimeError("reference group triplet costs failed")
+    return out
+
+
+def refmr_label_sets(sgres, maxvd, cap=64):
+    """label_sampling_grid: -> (vertex labels [n][3], barycentre labels [m][3], centre [3])"""
+    s, b, c = np.zeros((cap, 3)), np.zeros((cap, 3)), np.zeros(3)
+    nb = C.c_int(0)
+    n = RefMR.lib().refmr_label_sets(sgres, float(maxvd), _p(s), _p(b), cap, C.byref(nb), _p(c))
+    if n < 0:
+        raise RuntimeError("reference label sets failed")
+    return s[:n].copy(), b[:nb.value].copy(), c

@@ -343,7 +343,10 @@ void vertex_areas(int nv, const double* xyz, int nt, const int* tri, double* out
 // resampler.cpp:72-140 without EXCL, single-thread order
 int adaptive_maps(int nv_in, const double* xyz_in, int nt_in, const int* tri_in,
                   int nv_low, const double* xyz_low, int nt_low, const int* tri_low,
-                  std::vector<std::map<int, double>>& adapt) {
+                  std::vector<std::map<int, double>>& adapt, const double* area_xyz_in = nullptr) {
+    // area_xyz_in: coordinates the source mesh had when its Triangle objects were last (re)created. Triangle::area is
+    // cached at construction and NOT refreshed by Mesh::set_coord (triangle.cpp:31,39), so a mesh that was
+    // copied and then moved (DiscreteGroupModel.cpp:94-103) keeps the vertex areas of its pre-move geometry.
     orc_octree* tin = build_tree(nv_in, xyz_in, nt_in, tri_in);
     std::vector<std::map<int, double>> forward, reverse;
     int e = bary_weight_maps(tin, nv_low, xyz_low, forward);
@@ -356,7 +359,7 @@ int adaptive_maps(int nv_in, const double* xyz_in, int nt_in, const int* tri_in,
 
     std::vector<double> newA(nv_low), oldA(nv_in), correction(nv_in, 0.0);
     vertex_areas(nv_low, xyz_low, nt_low, tri_low, newA.data());
-    vertex_areas(nv_in, xyz_in, nt_in, tri_in, oldA.data());
+    vertex_areas(nv_in, area_xyz_in ? area_xyz_in : xyz_in, nt_in, tri_in, oldA.data());
     std::vector<std::map<int, double>> rr(nv_low);
     adapt.assign(nv_low, {});
     for (int o = 0; o < nv_in; ++o)
@@ -909,11 +912,21 @@ int orc_group_fields(int S, int nv, const double* data_xyz /*[S][nv][3]*/, int n
                     const P3 q = matvec(R, P3{labels[3 * l], labels[3 * l + 1], labels[3 * l + 2]});
                     xyz[3 * (size_t)p] = q.X; xyz[3 * (size_t)p + 1] = q.Y; xyz[3 * (size_t)p + 2] = q.Z;
                 }
-            if (orc_metric_resample(nv, xyz.data(), nt, tri, n_tpl, tpl_xyz, nt_tpl, tpl_tri, D, feat + (size_t)s * D * nv,
-                                    fields + ((size_t)s * L + l) * D * n_tpl, 1)) {
+            // metric_resample of the moved copy: source vertex areas are still those of the un-moved data mesh (see adaptive_maps)
+            std::vector<std::map<int, double>> adapt;
+            if (adaptive_maps(nv, xyz.data(), nt, tri, n_tpl, tpl_xyz, nt_tpl, tpl_tri, adapt, data_xyz + (size_t)s * nv * 3)) {
                 #pragma omp critical
                 err = 1;
+                continue;
             }
+            const double* fin = feat + (size_t)s * D * nv;
+            double* fout = fields + ((size_t)s * L + l) * D * n_tpl;
+            for (int d = 0; d < D; ++d)
+                for (int k = 0; k < n_tpl; ++k) {
+                    double val = 0.0;
+                    for (auto& it : adapt[k]) val += fin[(size_t)d * nv + it.first] * it.second;
+                    fout[(size_t)d * n_tpl + k] = val;
+                }
         }
     return err;
 }

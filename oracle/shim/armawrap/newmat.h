@@ -15,6 +15,7 @@
 #include <map>
 #include <memory>
 #include <numeric>
+#include <random>
 #include <sstream>
 #include <string>
 #include <cmath>
@@ -215,14 +216,48 @@ public:
     explicit IdentityMatrix(int n) : Matrix(n, n) { for (int i = 1; i <= n; ++i) (*this)(i, i) = 1.0; }
 };
 
-// Off-hot-path (affine initialisation only): declared so the reference compiles; any call
-// is a test-infrastructure error.
-inline void SVD(const Matrix&, DiagonalMatrix&, Matrix&, Matrix&) {
-    throw std::runtime_error("shim NEWMAT: SVD is not provided (off the hot path)");
+// Off the hot path (post-hoc strain maps, reg_tools.cpp:406,443). One-sided Jacobi SVD, singular values
+// in descending order like NEWMAT's: A (m x n, m >= n) = U * D * V.t(), U m x n, D n x n, V n x n.
+inline void SVD(const Matrix& A, DiagonalMatrix& D, Matrix& U, Matrix& V) {
+    const int m = A.Nrows(), n = A.Ncols();
+    if (m < n) throw std::runtime_error("shim NEWMAT: SVD needs rows >= cols");
+    Matrix W = A;
+    V = Matrix(n, n);
+    for (int i = 1; i <= n; ++i) V(i, i) = 1.0;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0;
+        for (int p = 1; p < n; ++p)
+            for (int q = p + 1; q <= n; ++q) {
+                double a = 0, b = 0, c = 0;
+                for (int i = 1; i <= m; ++i) { a += W(i, p) * W(i, p); b += W(i, q) * W(i, q); c += W(i, p) * W(i, q); }
+                if (std::fabs(c) <= 1e-300 || std::fabs(c) <= 1e-15 * std::sqrt(a * b)) continue;
+                off += std::fabs(c);
+                double zeta = (b - a) / (2.0 * c);
+                double t = (zeta >= 0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+                double cs = 1.0 / std::sqrt(1.0 + t * t), sn = cs * t;
+                for (int i = 1; i <= m; ++i) { double x = W(i, p), y = W(i, q); W(i, p) = cs * x - sn * y; W(i, q) = sn * x + cs * y; }
+                for (int i = 1; i <= n; ++i) { double x = V(i, p), y = V(i, q); V(i, p) = cs * x - sn * y; V(i, q) = sn * x + cs * y; }
+            }
+        if (off == 0.0) break;
+    }
+    std::vector<double> sv(n);
+    for (int j = 1; j <= n; ++j) { double s = 0; for (int i = 1; i <= m; ++i) s += W(i, j) * W(i, j); sv[j - 1] = std::sqrt(s); }
+    std::vector<int> ord(n);
+    for (int j = 0; j < n; ++j) ord[j] = j;
+    std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return sv[x] > sv[y]; });
+    D.ReSize(n);
+    U = Matrix(m, n);
+    Matrix V2(n, n);
+    for (int j = 1; j <= n; ++j) {
+        int o = ord[j - 1] + 1;
+        D(j) = sv[o - 1];
+        for (int i = 1; i <= m; ++i) U(i, j) = sv[o - 1] > 0 ? W(i, o) / sv[o - 1] : 0.0;
+        for (int i = 1; i <= n; ++i) V2(i, j) = V(i, o);
+    }
+    V = V2;
 }
-inline void SVD(const Matrix&, DiagonalMatrix&) {
-    throw std::runtime_error("shim NEWMAT: SVD is not provided (off the hot path)");
-}
+inline void SVD(const Matrix& A, DiagonalMatrix& D, Matrix& U) { Matrix V; SVD(A, D, U, V); }
+inline void SVD(const Matrix& A, DiagonalMatrix& D) { Matrix U, V; SVD(A, D, U, V); }
 
 inline std::ostream& operator<<(std::ostream& os, const Matrix& m) {
     for (int i = 1; i <= m.Nrows(); ++i) {

@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from newmsm_b200 import capi, synth
+from cost_cases import cost_setup, triplet_setup, group_setup
 
 pytestmark = pytest.mark.gpu
 
@@ -278,33 +279,6 @@ def test_cpp_adapter_drop_in(R):
 # ---------------------------------------------------------------------------------------------
 # cost functions
 # ---------------------------------------------------------------------------------------------
-def cost_setup(oracle_built, cp_level, data_level, D, seed=3):
-    cp, _ = synth.icosphere(cp_level)
-    xyz, tri = synth.icosphere(data_level)
-    src = synth.smooth_warp(xyz, max_disp=1.5, seed=seed)                 # SOURCE mesh = warped data grid
-    ref_feat = synth.smooth_fields(xyz, D, seed0=100)
-    src_feat = synth.smooth_fields(src, D, seed0=100, noise=0.05)
-    # MAXSEP: largest distance from a CP to its mesh neighbours ~ CP spacing; any positive vector is a valid input
-    cp_tri = synth.icosphere(cp_level)[1]
-    e = np.zeros(len(cp))
-    for a, b in ((0, 1), (1, 2), (0, 2)):
-        d = np.linalg.norm(cp[cp_tri[:, a]] - cp[cp_tri[:, b]], axis=1)
-        np.maximum.at(e, cp_tri[:, a], d)
-        np.maximum.at(e, cp_tri[:, b], d)
-    rng = np.random.default_rng(seed)
-    # 7 labels: the CP itself plus 6 small displacements, expressed around the north pole like the label grid
-    centre = np.array([0.0, 0.0, 100.0])
-    labels = [centre]
-    for k in range(6):
-        ang = k * np.pi / 3
-        p = centre + 0.4 * e.mean() * np.array([np.cos(ang), np.sin(ang), 0.0])
-        labels.append(p / np.linalg.norm(p) * 100)
-    labels = np.array(labels)
-    rot = np.array([oracle_built.oracle_rotation_matrix(centre, c) for c in cp]).reshape(-1, 9)   # get_rotations (DiscreteModel.cpp:310)
-    absw = rng.uniform(0.5, 1.5, size=len(cp))
-    return dict(cp=cp, xyz=xyz, tri=tri, src=src, ref_feat=ref_feat, src_feat=src_feat, maxsep=e, labels=labels, rot=rot, absw=absw)
-
-
 def test_patch_membership_bit_exact(R, oracle_built):
     from newmsm_b200 import discrete_cost as DC
     s = cost_setup(oracle_built, 3, 5, 1)
@@ -359,24 +333,6 @@ def test_unary_costs_bit_exact(R, oracle_built, kind, D, sim):
 # ---------------------------------------------------------------------------------------------
 # triplet costs: strain regulariser + HO likelihood (parity unpinned: against our restatement)
 # ---------------------------------------------------------------------------------------------
-def triplet_setup(oracle_built, cp_level, data_level, D):
-    s = cost_setup(oracle_built, cp_level, data_level, D)
-    cp_tri = synth.icosphere(cp_level)[1]
-    s["cp_tri"] = cp_tri
-    s["triplets"] = np.sort(cp_tri, axis=1).astype(np.int32)          # DiscreteModel.cpp:293-303: node ids ascending
-    s["orig"] = s["cp"].copy()
-    s["cp_now"] = synth.smooth_warp(s["cp"], max_disp=0.3 * s["maxsep"].mean(), seed=17)   # a CP grid that has already moved
-    rng = np.random.default_rng(23)
-    T, L = len(cp_tri), len(s["labels"])
-    n = 4000
-    s["req"] = (rng.integers(0, T, n).astype(np.int32), rng.integers(0, L, n).astype(np.int32),
-                rng.integers(0, L, n).astype(np.int32), rng.integers(0, L, n).astype(np.int32))
-    # rotations map the label-grid centre onto the CURRENT control points (get_rotations, DiscreteModel.cpp:310)
-    centre = np.array([0.0, 0.0, 100.0])
-    s["rot_now"] = np.array([oracle_built.oracle_rotation_matrix(centre, c) for c in s["cp_now"]]).reshape(-1, 9)
-    return s
-
-
 def rel_close(a, b, tol):
     return np.all(np.abs(a - b) <= tol * np.maximum(np.abs(b), 1e-300))
 
@@ -447,22 +403,6 @@ def test_ho_triplet_likelihood(R, oracle_built, kind, D, sim):
 # ---------------------------------------------------------------------------------------------
 # groupwise (gMSM): resampled fields per (subject,label) and pair costs (parity unpinned: against our restatement)
 # ---------------------------------------------------------------------------------------------
-def group_setup(S=3, cp_level=2, data_level=4, tpl_level=4, D=2):
-    cp0, cp_tri = synth.icosphere(cp_level)
-    dxyz0, dtri = synth.icosphere(data_level)
-    tpl, tpl_tri = synth.icosphere(tpl_level)
-    tpl = synth.rotate_sphere(tpl, 0.004, -0.003, 0.002)
-    data = np.stack([synth.smooth_warp(dxyz0, max_disp=2.0, seed=40 + s) for s in range(S)])
-    cps = np.stack([synth.smooth_warp(cp0, max_disp=1.5, seed=60 + s) for s in range(S)])
-    feat = np.stack([synth.smooth_fields(data[s], D, seed0=100, noise=0.1, noise_seed=7 + s) for s in range(S)])
-    centre = np.array([0.0, 0.0, 100.0])
-    labels = [centre]
-    for k in range(6):
-        p = centre + 6.0 * np.array([np.cos(k * np.pi / 3), np.sin(k * np.pi / 3), 0.0])
-        labels.append(p / np.linalg.norm(p) * 100)
-    return dict(cp_tri=cp_tri, dtri=dtri, tpl=tpl, tpl_tri=tpl_tri, data=data, cps=cps, feat=feat, centre=centre, labels=np.array(labels))
-
-
 @pytest.mark.parametrize("sim", [2, 1])
 def test_group_fields_and_pair_costs(R, oracle_built, sim):
     from newmsm_b200 import group_cost as GC
@@ -503,3 +443,72 @@ def test_group_fields_and_pair_costs(R, oracle_built, sim):
     self_pairs = np.array([[v, v] for v in range(ncp)], dtype=np.int32)
     z = M.computePairwiseCostList(self_pairs, np.arange(ncp), np.full(ncp, 2), np.full(ncp, 2))
     assert np.nanmax(np.abs(z)) < 1e-12
+
+
+# ---------------------------------------------------------------------------------------------
+# CUDA path against the outputs of the reference's OWN cost-function classes (tests/golden/costs.npz,
+# generated by tests/golden/make_golden_costs.py from oracle/_ref/libref_newmeshreg.so)
+# ---------------------------------------------------------------------------------------------
+def test_unary_costs_vs_reference_golden(R, oracle_built):
+    from newmsm_b200 import discrete_cost as DC
+    from cost_cases import GOLDEN_CP, GOLDEN_DATA, golden_digest
+    g = load("costs.npz")
+    for kind, D in ((0, 1), (1, 4), (2, 4)):
+        s = cost_setup(oracle_built, GOLDEN_CP, GOLDEN_DATA, D)
+        assert np.array_equal(golden_digest(s), g[f"unary_k{kind}_digest"]), "seeded inputs drifted: regenerate the fixture"
+        cls = [DC.UnivariateNonLinearSRegDiscreteCostFunction, DC.MultivariateNonLinearSRegDiscreteCostFunction,
+               DC.PatchwiseMultivariateNonLinearSRegDiscreteCostFunction][kind]
+        cfw = np.random.default_rng(5).uniform(0.2, 1.0, size=(D if kind == 1 else 1, len(s["src"])))
+        for sim in (1, 2):
+            cf = cls(simmeasure=sim)
+            cf.set_meshes(R.Mesh(s["xyz"], s["tri"]), s["src"], s["src_feat"], s["ref_feat"])
+            cf.reset_CPgrid(s["cp"], s["maxsep"], 1.0, HIGHREScfweight=cfw, AbsoluteWeights=s["absw"])
+            prow, pmem = cf.get_source_data()
+            assert np.array_equal(prow, g[f"unary_k{kind}_prow"]) and np.array_equal(pmem, g[f"unary_k{kind}_pmem"])
+            assert np.array_equal(cf.computeUnaryCosts(s["labels"], s["rot"]), g[f"unary_k{kind}_s{sim}"])
+
+
+def test_triplet_costs_vs_reference_golden(R, oracle_built):
+    from newmsm_b200 import discrete_cost as DC
+    from cost_cases import GOLDEN_CP, GOLDEN_DATA, golden_digest
+    g = load("costs.npz")
+    for kind, D in ((0, 1), (3, 1), (4, 3)):
+        s = triplet_setup(oracle_built, GOLDEN_CP, GOLDEN_DATA, D)
+        assert np.array_equal(golden_digest(s), g[f"triplet_k{kind}_digest"]), "seeded inputs drifted: regenerate the fixture"
+        rt, la, lb, lc = s["req"]
+        cfw = np.random.default_rng(5).uniform(0.2, 1.0, size=(D, len(s["src"])))
+        cls = {0: DC.UnivariateNonLinearSRegDiscreteCostFunction, 3: DC.HOUnivariateNonLinearSRegDiscreteCostFunction,
+               4: DC.HOMultivariateNonLinearSRegDiscreteCostFunction}[kind]
+        cf = cls(simmeasure=2)
+        cf.set_meshes(R.Mesh(s["xyz"], s["tri"]), s["src"], s["src_feat"], s["ref_feat"])
+        if kind >= 3:
+            cf.reset_CPgrid(s["cp_now"], s["cp_tri"], HIGHREScfweight=cfw, AbsoluteWeights=s["absw"])
+            prow, pmem = cf.get_source_data()
+            assert np.array_equal(prow, g[f"triplet_k{kind}_prow"]) and np.array_equal(pmem, g[f"triplet_k{kind}_pmem"])
+        else:
+            cf.reset_CPgrid(s["cp_now"], s["maxsep"], 1.0)
+        cf.set_parameters(0.05)
+        cf.setTriplets(s["triplets"], s["labels"], s["rot_now"], s["orig"])
+        got = cf.computeTripletCostList(rt, la, lb, lc)
+        ref = g[f"triplet_k{kind}"]
+        # strain energy: the device squares with x*x where the host's pow(x, 2) is 1 ulp off in ~0.1 % of the cases
+        assert rel_close(got, ref, 1e-11)
+        assert (got == ref).mean() > 0.95
+
+
+def test_group_costs_vs_reference_golden(R, oracle_built):
+    from newmsm_b200 import group_cost as GC
+    from cost_cases import golden_digest, golden_group_glue
+    g = load("costs.npz")
+    c = group_setup(S=2, cp_level=1, data_level=3, tpl_level=3, D=2)
+    assert np.array_equal(golden_digest(c), g["group_digest"]), "seeded inputs drifted: regenerate the fixture"
+    rot, spacings, pairs, (rp, la, lb) = golden_group_glue(oracle_built, c)
+    for sim in (1, 2):
+        M = GC.DiscreteGroupModel(R.Mesh(c["tpl"], c["tpl_tri"]), simmeasure=sim)
+        fields = M.get_patch_data(c["data"], c["dtri"], c["feat"], c["labels"], c["centre"], rot, spacings, 1.0)
+        got_fields = fields.cpu().numpy().transpose(0, 1, 3, 2)
+        seen = ~np.isnan(g["group_fields"])
+        assert np.array_equal(got_fields[seen], g["group_fields"][seen])
+        got = M.computePairwiseCostList(pairs, rp, la, lb)
+        ok = ~np.isnan(got)
+        assert ok.mean() > 0.9 and np.array_equal(got[ok], g[f"group_pair_s{sim}"][ok])

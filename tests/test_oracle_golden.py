@@ -70,3 +70,55 @@ def test_similarity_kats(oracle_built):
     r = np.cov(A, B, aweights=w, bias=True)
     r = r[0, 1] / np.sqrt(r[0, 0] * r[1, 1])
     assert np.isclose(oracle_built.oracle_sim(2, A, B, w), 1 - (1 + r) / 2, rtol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------
+# cost functions: outputs of the reference's own classes (tests/golden/make_golden_costs.py)
+# ---------------------------------------------------------------------------------------------
+def test_unary_costs_golden(oracle_built):
+    from cost_cases import GOLDEN_CP, GOLDEN_DATA, cost_setup, golden_digest
+    g = load("costs.npz")
+    for kind, D in ((0, 1), (1, 4), (2, 4)):
+        s = cost_setup(oracle_built, GOLDEN_CP, GOLDEN_DATA, D)
+        assert np.array_equal(golden_digest(s), g[f"unary_k{kind}_digest"]), "seeded inputs drifted: regenerate the fixture"
+        prow, pmem = oracle_built.oracle_patch_membership(s["cp"], s["src"], s["maxsep"], 1.0)
+        assert np.array_equal(prow, g[f"unary_k{kind}_prow"]) and np.array_equal(pmem, g[f"unary_k{kind}_pmem"])
+        cfw = np.random.default_rng(5).uniform(0.2, 1.0, size=(D if kind == 1 else 1, len(s["src"])))
+        ot = oracle_built.OracleOctree(s["xyz"], s["tri"])
+        for sim in (1, 2):
+            got = oracle_built.oracle_unary_costs(kind, sim, ot, s["cp"], s["rot"], s["labels"], s["src"], prow, pmem,
+                                                  s["src_feat"], s["ref_feat"], cfw, s["absw"])
+            assert np.array_equal(got, g[f"unary_k{kind}_s{sim}"])
+
+
+def test_triplet_costs_golden(oracle_built):
+    from cost_cases import GOLDEN_CP, GOLDEN_DATA, golden_digest, triplet_setup
+    g = load("costs.npz")
+    for kind, D in ((0, 1), (3, 1), (4, 3)):
+        s = triplet_setup(oracle_built, GOLDEN_CP, GOLDEN_DATA, D)
+        assert np.array_equal(golden_digest(s), g[f"triplet_k{kind}_digest"]), "seeded inputs drifted: regenerate the fixture"
+        rt, la, lb, lc = s["req"]
+        cfw = np.random.default_rng(5).uniform(0.2, 1.0, size=(D, len(s["src"])))
+        prow = pmem = ot = None
+        if kind >= 3:
+            prow, pmem = oracle_built.oracle_ho_patches(s["cp_now"], s["cp_tri"], s["src"])
+            assert np.array_equal(prow, g[f"triplet_k{kind}_prow"]) and np.array_equal(pmem, g[f"triplet_k{kind}_pmem"])
+            ot = oracle_built.OracleOctree(s["xyz"], s["tri"])
+        got = oracle_built.oracle_triplet_costs(kind, 2, ot, s["cp_now"], s["orig"], s["rot_now"], s["labels"], s["triplets"], rt, la, lb, lc,
+                                                s["src"], prow, pmem, s["src_feat"], s["ref_feat"], cfw, s["absw"], 0.05)
+        assert np.array_equal(got, g[f"triplet_k{kind}"])
+
+
+def test_group_costs_golden(oracle_built):
+    from cost_cases import golden_digest, golden_group_glue, group_setup
+    g = load("costs.npz")
+    c = group_setup(S=2, cp_level=1, data_level=3, tpl_level=3, D=2)
+    assert np.array_equal(golden_digest(c), g["group_digest"]), "seeded inputs drifted: regenerate the fixture"
+    rot, spacings, pairs, (rp, la, lb) = golden_group_glue(oracle_built, c)
+    fields = oracle_built.oracle_group_fields(c["data"], c["dtri"], c["feat"], c["labels"], c["centre"], c["tpl"], c["tpl_tri"])
+    seen = ~np.isnan(g["group_fields"])
+    assert np.array_equal(fields[seen], g["group_fields"][seen])
+    for sim in (1, 2):
+        got = oracle_built.oracle_group_pair_costs(sim, c["cps"].shape[1], c["tpl"], fields, rot, c["labels"], spacings, 1.0, pairs, rp, la, lb)
+        ok = ~np.isnan(got)          # empty intersections: undefined behaviour in the reference, not compared
+        assert ok.mean() > 0.9 and np.array_equal(got[ok], g[f"group_pair_s{sim}"][ok])
