@@ -77,6 +77,10 @@ msmgpu_status msmgpu_mesh_set_features_f32(msmgpu_mesh* m, int D, const float* f
  * state: vertex areas of `m` (msmgpu_mesh_vertex_areas, the adaptive weights) are taken from `area_mesh`'s geometry.
  * area_mesh = NULL (or m) restores "freshly copied" semantics. Same context, same nv/nt; area_mesh must outlive its use. */
 msmgpu_status msmgpu_mesh_set_area_source(msmgpu_mesh* m, msmgpu_mesh* area_mesh);
+/* Same purpose with explicit values: areas[nt] = Mesh::get_triangle_area(t) (mesh.cpp:793) of the reference object being mirrored,
+ * whatever its history of copies and set_coord calls. NULL returns to areas computed from the current coordinates. Takes precedence
+ * over the mesh's own geometry (an area source's explicit areas are honoured too). */
+msmgpu_status msmgpu_mesh_set_triangle_areas(msmgpu_mesh* m, const double* areas);
 
 /* replaces: compute_vertex_area (msm-newresampler/src/mesh.cpp:1275) for all vertices */
 msmgpu_status msmgpu_mesh_vertex_areas(msmgpu_mesh* m, double* out);

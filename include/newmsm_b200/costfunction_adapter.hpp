@@ -1,0 +1,346 @@
+// costfunction_adapter.hpp — the reference-side binding of include/msmgpu.h for msm-newmeshreg's cost functions.
+//
+// Header-only. GpuCostFunction<Base, KIND> derives from the reference's own cost-function class
+// (msm-newmeshreg/src/DiscreteCostFunction.h:205-244) and overrides exactly the virtuals that do the data-parallel work
+// (DiscreteCostFunction.h:41-59: get_source_data, computeUnaryCosts, computeUnaryCost, computeTripletCost,
+// computePairwiseCosts); everything else (parameters, meshes, labels, the cost tables the solvers read, ownership)
+// is inherited unchanged, so NonLinearSRegDiscreteModel, FPD::FastPD and Fusion::optimize (Fusion.h:118-246)
+// use it through the same pointers and the same call order (DiscreteModel.cpp:216-262).
+//
+//   * get_source_data()          -> msmgpu_costfn_set_cpgrid[_ho]   (patch membership, cpp:102-107, 334-351, 468-485)
+//   * computeUnaryCosts()        -> msmgpu_costfn_unary_table        (cpp:236-243)
+//   * computeUnaryCost(n, l)     -> entry of that table, built once per iteration (Fusion asks per call, Fusion.h:148-155)
+//   * computeTripletCost(t,a,b,c)-> Fusion asks 8 combinations per triplet for one candidate label, from OpenMP workers
+//                                   (Fusion.h:181-196). The first request of a (labeling, label) phase evaluates ALL triplets x 8
+//                                   combinations in one msmgpu_costfn_triplet_batch launch; the others are table look-ups.
+//   * computePairwiseCosts(p)    -> the rotation regulariser table (cpp:190-243) evaluated in parallel on the host (it is
+//                                   libm-bound: estimate_rotation_matrix + acos per entry), identical values.
+//
+// There is no CPU fallback for the device paths: a failing msmgpu call throws MeshregException with msmgpu_last_error().
+// regoption 4/5 (anatomical strain) are not accelerated: install_gpu_costfunction() leaves the reference's object in place.
+#pragma once
+
+#include <atomic>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <omp.h>
+
+#ifndef NEWMSM_B200_DISCRETEMODEL_HEADER
+#define NEWMSM_B200_DISCRETEMODEL_HEADER "NewMeshReg/DiscreteModel.h"
+#endif
+#include NEWMSM_B200_DISCRETEMODEL_HEADER   // the reference's DiscreteModel / cost-function classes
+
+#include "../msmgpu.h"
+
+namespace newmeshreg_gpu {
+
+using newmeshreg::MeshregException;
+using newresampler::Mesh;
+using newresampler::Point;
+
+namespace detail {
+
+inline void check(msmgpu_status st) {
+    if (st != MSMGPU_OK) {
+        static thread_local std::string msg;
+        msg = std::string("msmgpu: ") + msmgpu_last_error();
+        throw MeshregException(msg.c_str());
+    }
+}
+
+inline msmgpu_ctx* context() {   // one context per process on $MSMGPU_DEVICE (default 0)
+    static msmgpu_ctx* ctx = [] {
+        const char* e = std::getenv("MSMGPU_DEVICE");
+        msmgpu_ctx* c = nullptr;
+        check(msmgpu_ctx_create(e ? std::atoi(e) : 0, nullptr, &c));
+        return c;
+    }();
+    return ctx;
+}
+
+inline std::vector<double> coords_of(const Mesh& m, int n = -1) {
+    if (n < 0) n = m.nvertices();
+    std::vector<double> xyz(3 * (size_t)n);
+    for (int i = 0; i < n; ++i) {
+        const Point& p = m.get_coord(i);
+        xyz[3 * (size_t)i] = p.X; xyz[3 * (size_t)i + 1] = p.Y; xyz[3 * (size_t)i + 2] = p.Z;
+    }
+    return xyz;
+}
+
+inline std::vector<int32_t> triangles_of(const Mesh& m) {
+    std::vector<int32_t> tri(3 * (size_t)m.ntriangles());
+    for (int t = 0; t < m.ntriangles(); ++t)
+        for (int k = 0; k < 3; ++k) tri[3 * (size_t)t + k] = m.get_triangle_vertexID(t, k);
+    return tri;
+}
+
+// the protected state NonLinearSRegDiscreteCostFunction::computePairwiseCost reads (cpp:190-233), cloned into per-thread workers
+struct PairState {
+    Mesh cp, ocp;
+    std::vector<Point> labels;
+    std::shared_ptr<std::vector<NEWMAT::Matrix>> rot;
+    int* pairs;
+    double mvdmax, lambda, rexp;
+};
+struct PairWorker : newmeshreg::NonLinearSRegDiscreteCostFunction {
+    explicit PairWorker(const PairState& s) {
+        _CPgrid = s.cp; _oCPgrid = s.ocp; _labels = s.labels; ROTATIONS = s.rot; _pairs = s.pairs;
+        MVDmax = s.mvdmax; _reglambda = s.lambda; _rexp = s.rexp;
+    }
+};
+
+struct Timers {   // wall-clock split printed by the integration binary (seconds)
+    double source = 0, unary = 0, triplet = 0, pairwise = 0;
+    long unary_tables = 0, triplet_batches = 0;
+};
+inline Timers& timers() { static Timers t; return t; }
+
+}  // namespace detail
+
+template <class Base, msmgpu_cost_kind KIND>
+class GpuCostFunction : public Base {
+    static constexpr bool kHO = KIND == MSMGPU_COST_HO_UNIVARIATE || KIND == MSMGPU_COST_HO_MULTIVARIATE;
+
+    newmeshreg::DiscreteModel* model_;   // owner of labeling[] (DiscreteModel.h:46)
+    msmgpu_mesh* d_target_ = nullptr;
+    msmgpu_octree* d_tree_ = nullptr;
+    msmgpu_costfn* d_cf_ = nullptr;
+
+    // per-iteration host copies handed to the C ABI
+    std::vector<double> labels_, rot_, orig_cp_;
+    std::vector<int32_t> trip_;
+    bool iter_arrays_ready_ = false;
+
+    std::mutex mu_;
+    std::atomic<bool> unary_ready_{false};
+
+    // triplet caches (double-buffered: readers keep using the old table while a new phase is being computed)
+    struct Table {
+        std::vector<int32_t> snap;    // labeling snapshot the table was computed for
+        std::vector<double> val;      // [T] (current labels) or [T][8] (Fusion's combinations)
+        int label = -1;
+    };
+    std::shared_ptr<Table> cur_, fus_;
+
+    void release() {
+        if (d_cf_) msmgpu_costfn_destroy(d_cf_);
+        if (d_tree_) msmgpu_octree_destroy(d_tree_);
+        if (d_target_) msmgpu_mesh_destroy(d_target_);
+        d_cf_ = nullptr; d_tree_ = nullptr; d_target_ = nullptr;
+    }
+
+    void ensure_device() {
+        if (d_cf_) return;
+        msmgpu_ctx* ctx = detail::context();
+        const Mesh& T = this->_TARGET;
+        const std::vector<double> txyz = detail::coords_of(T);
+        const std::vector<int32_t> ttri = detail::triangles_of(T);
+        detail::check(msmgpu_mesh_create(ctx, T.nvertices(), txyz.data(), T.ntriangles(), ttri.data(), &d_target_));
+        detail::check(msmgpu_octree_build(d_target_, &d_tree_));
+        const int D = (int)this->FEAT->get_dim(), ns = this->_SOURCE.nvertices(), nt = T.nvertices();
+        std::vector<double> sf((size_t)D * ns), rf((size_t)D * nt);
+        for (int d = 0; d < D; ++d) {
+            for (int i = 0; i < ns; ++i) sf[(size_t)d * ns + i] = this->FEAT->get_input_val(d + 1, i + 1);
+            for (int i = 0; i < nt; ++i) rf[(size_t)d * nt + i] = this->FEAT->get_ref_val(d + 1, i + 1);
+        }
+        const std::vector<double> sxyz = detail::coords_of(this->_SOURCE);
+        detail::check(msmgpu_costfn_create(d_tree_, KIND, this->_simmeasure, ns, sxyz.data(), D, sf.data(), rf.data(), &d_cf_));
+    }
+
+    // labels / rotations / triplets / undeformed control points of the current iteration (set_labels, setTriplets)
+    void ensure_iter_arrays() {
+        if (iter_arrays_ready_) return;
+        const int L = (int)this->_labels.size(), N = this->_CPgrid.nvertices();
+        labels_.resize(3 * (size_t)L);
+        for (int l = 0; l < L; ++l) { labels_[3 * l] = this->_labels[l].X; labels_[3 * l + 1] = this->_labels[l].Y; labels_[3 * l + 2] = this->_labels[l].Z; }
+        rot_.resize(9 * (size_t)N);
+        for (int k = 0; k < N; ++k)
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) rot_[9 * (size_t)k + 3 * r + c] = (*this->ROTATIONS)[k](r + 1, c + 1);
+        if (this->_triplets && this->m_num_triplets > 0) {
+            trip_.assign(this->_triplets, this->_triplets + 3 * (size_t)this->m_num_triplets);
+            orig_cp_ = detail::coords_of(this->_ORIG, N);   // _ORIG.get_coord(node) (cpp:166-168): the nested icosphere's first N vertices
+        }
+        iter_arrays_ready_ = true;
+    }
+
+    msmgpu_reg_params reg_params() const {
+        msmgpu_reg_params p;
+        p.lambda = this->_reglambda; p.shear_modulus = this->_mu; p.bulk_modulus = this->_kappa;
+        p.k_exponent = this->_k_exp; p.exponent = this->_rexp; p.rmode = this->_rmode;
+        return p;
+    }
+
+    void build_unary_table() {
+        const double t0 = omp_get_wtime();
+        ensure_iter_arrays();
+        detail::check(msmgpu_costfn_unary_table(d_cf_, this->m_num_labels, labels_.data(), rot_.data(), this->unarycosts, nullptr));
+        detail::timers().unary += omp_get_wtime() - t0;
+        detail::timers().unary_tables++;
+    }
+
+    std::shared_ptr<Table> make_table(int label) {
+        const double t0 = omp_get_wtime();
+        ensure_iter_arrays();
+        const int T = this->m_num_triplets, N = this->m_num_nodes;
+        auto tb = std::make_shared<Table>();
+        const int* lab = model_->getLabeling();
+        tb->snap.assign(lab, lab + N);
+        tb->label = label;
+        const msmgpu_reg_params prm = reg_params();
+        if (label < 0) {   // costs at the current labeling
+            std::vector<int32_t> rt(T), la(T), lb(T), lc(T);
+            for (int t = 0; t < T; ++t) { rt[t] = t; la[t] = lab[trip_[3 * t]]; lb[t] = lab[trip_[3 * t + 1]]; lc[t] = lab[trip_[3 * t + 2]]; }
+            tb->val.resize(T);
+            detail::check(msmgpu_costfn_triplet_costs(d_cf_, T, trip_.data(), this->m_num_labels, labels_.data(), rot_.data(), orig_cp_.data(), &prm,
+                                                      T, rt.data(), la.data(), lb.data(), lc.data(), tb->val.data()));
+        } else {           // Fusion.h:181-196: combination c = (A?4:0)|(B?2:0)|(C?1:0), bit set = candidate label
+            tb->val.resize(8 * (size_t)T);
+            detail::check(msmgpu_costfn_triplet_batch(d_cf_, T, trip_.data(), this->m_num_labels, labels_.data(), rot_.data(), orig_cp_.data(), &prm,
+                                                      tb->snap.data(), label, tb->val.data()));
+        }
+        detail::timers().triplet += omp_get_wtime() - t0;
+        detail::timers().triplet_batches++;
+        return tb;
+    }
+
+    static bool fresh(const std::shared_ptr<Table>& tb, const int* lab, int a, int b, int c, int label) {
+        return tb && tb->label == label && tb->snap[a] == lab[a] && tb->snap[b] == lab[b] && tb->snap[c] == lab[c];
+    }
+
+public:
+    explicit GpuCostFunction(newmeshreg::DiscreteModel* model) : model_(model) {}
+    ~GpuCostFunction() override { release(); }
+
+    void initialize(int numNodes, int numLabels, int numPairs, int numTriplets) override {
+        Base::initialize(numNodes, numLabels, numPairs, numTriplets);
+        iter_arrays_ready_ = false;
+        unary_ready_.store(false);
+        std::atomic_store(&cur_, std::shared_ptr<Table>());
+        std::atomic_store(&fus_, std::shared_ptr<Table>());
+    }
+
+    // once per discrete iteration (DiscreteModel.cpp:254): patches of the current source / control-point grid
+    void get_source_data() override {
+        const double t0 = omp_get_wtime();
+        ensure_device();
+        const std::vector<double> sxyz = detail::coords_of(this->_SOURCE);
+        detail::check(msmgpu_costfn_reset_source(d_cf_, sxyz.data()));
+        this->resample_weights();   // AbsoluteWeights (cpp:303-322): newresampler::metric_resample, itself bound to the GPU by the resampler adapter
+        const int N = this->_CPgrid.nvertices(), ns = this->_SOURCE.nvertices();
+        const std::vector<double> cp = detail::coords_of(this->_CPgrid);
+        const int cfw_rows = this->_HIGHREScfweight.Nrows();
+        std::vector<double> cfw((size_t)cfw_rows * ns), absw(N);
+        for (int r = 0; r < cfw_rows; ++r)
+            for (int i = 0; i < ns; ++i) cfw[(size_t)r * ns + i] = this->_HIGHREScfweight(r + 1, i + 1);
+        for (int k = 0; k < N; ++k) absw[k] = this->AbsoluteWeights(k + 1);
+        if (kHO) {
+            const std::vector<int32_t> ctri = detail::triangles_of(this->_CPgrid);
+            detail::check(msmgpu_costfn_set_cpgrid_ho(d_cf_, N, cp.data(), this->_CPgrid.ntriangles(), ctri.data(), cfw_rows, cfw.data(), absw.data()));
+        } else {
+            std::vector<double> sep(N);
+            for (int k = 0; k < N; ++k) sep[k] = this->MAXSEP(k + 1);
+            detail::check(msmgpu_costfn_set_cpgrid(d_cf_, N, cp.data(), sep.data(), this->_controlptrange, cfw_rows, cfw.data(), absw.data()));
+        }
+        detail::timers().source += omp_get_wtime() - t0;
+    }
+
+    void computeUnaryCosts() override {
+        if (kHO) { Base::computeUnaryCosts(); return; }   // HO kinds: computeUnaryCost is the constant 0 (DiscreteCostFunction.h:222)
+        std::lock_guard<std::mutex> g(mu_);
+        build_unary_table();
+        unary_ready_.store(true);
+    }
+
+    double computeUnaryCost(int node, int label) override {
+        if (kHO) return 0;
+        if (!unary_ready_.load(std::memory_order_acquire)) {
+            std::lock_guard<std::mutex> g(mu_);
+            if (!unary_ready_.load()) { build_unary_table(); unary_ready_.store(true, std::memory_order_release); }
+        }
+        return this->unarycosts[label * this->m_num_nodes + node];
+    }
+
+    double computeTripletCost(int triplet, int labelA, int labelB, int labelC) override {
+        if (this->_rmode != 2 && this->_rmode != 3) return Base::computeTripletCost(triplet, labelA, labelB, labelC);
+        const int* lab = model_->getLabeling();
+        const int a = this->_triplets[3 * triplet], b = this->_triplets[3 * triplet + 1], c = this->_triplets[3 * triplet + 2];
+        const bool da = labelA != lab[a], db = labelB != lab[b], dc = labelC != lab[c];
+        if (!da && !db && !dc) {
+            std::shared_ptr<Table> tb = std::atomic_load(&cur_);
+            if (!fresh(tb, lab, a, b, c, -1)) {
+                std::lock_guard<std::mutex> g(mu_);
+                tb = std::atomic_load(&cur_);
+                if (!fresh(tb, lab, a, b, c, -1)) { tb = make_table(-1); std::atomic_store(&cur_, tb); }
+            }
+            return tb->val[triplet];
+        }
+        const int label = da ? labelA : (db ? labelB : labelC);
+        if ((da && labelA != label) || (db && labelB != label) || (dc && labelC != label)) {
+            // not one of Fusion's combinations (two different non-current labels): evaluate this request on its own
+            ensure_iter_arrays();
+            const msmgpu_reg_params prm = reg_params();
+            const int32_t rt = triplet, la = labelA, lb = labelB, lc = labelC;
+            double out = 0;
+            std::lock_guard<std::mutex> g(mu_);
+            detail::check(msmgpu_costfn_triplet_costs(d_cf_, this->m_num_triplets, trip_.data(), this->m_num_labels, labels_.data(), rot_.data(), orig_cp_.data(),
+                                                      &prm, 1, &rt, &la, &lb, &lc, &out));
+            return out;
+        }
+        std::shared_ptr<Table> tb = std::atomic_load(&fus_);
+        if (!fresh(tb, lab, a, b, c, label)) {
+            std::lock_guard<std::mutex> g(mu_);
+            tb = std::atomic_load(&fus_);
+            if (!fresh(tb, lab, a, b, c, label)) { tb = make_table(label); std::atomic_store(&fus_, tb); }
+        }
+        return tb->val[8 * (size_t)triplet + ((da ? 4 : 0) | (db ? 2 : 0) | (dc ? 1 : 0))];
+    }
+
+    // cpp:236-243 runs computePairwiseCost serially because it moves and restores two vertices of the member mesh _CPgrid
+    // (cpp:204-205, 228-229). Each worker here owns a private copy of the cost function's geometry, so the same member function
+    // runs concurrently; every entry is the value the serial loop produces.
+    void computePairwiseCosts(const int* pairs) override {
+        const double t0 = omp_get_wtime();
+        const int P = this->m_num_pairs, L = (int)this->_labels.size(), LL = this->m_num_labels;
+        int nthreads = omp_get_max_threads();
+        if (const char* e = std::getenv("MSMGPU_HOST_THREADS")) nthreads = std::max(1, std::atoi(e));
+        detail::PairState st{this->_CPgrid, this->_oCPgrid, this->_labels, this->ROTATIONS, this->_pairs, this->MVDmax, this->_reglambda, this->_rexp};
+        #pragma omp parallel num_threads(nthreads)
+        {
+            detail::PairWorker w(st);
+            #pragma omp for schedule(dynamic, 8)
+            for (int i = 0; i < P; ++i)
+                for (int j = 0; j < L; ++j)
+                    for (int k = 0; k < L; ++k) this->paircosts[i * LL * LL + k * LL + j] = w.computePairwiseCost(i, j, k);
+        }
+        (void)pairs;
+        detail::timers().pairwise += omp_get_wtime() - t0;
+    }
+
+};
+
+using GpuUnivariate = GpuCostFunction<newmeshreg::UnivariateNonLinearSRegDiscreteCostFunction, MSMGPU_COST_UNIVARIATE>;
+using GpuMultivariate = GpuCostFunction<newmeshreg::MultivariateNonLinearSRegDiscreteCostFunction, MSMGPU_COST_MULTIVARIATE>;
+using GpuPatchwise = GpuCostFunction<newmeshreg::PatchwiseMultivariateNonLinearSRegDiscreteCostFunction, MSMGPU_COST_PATCHWISE>;
+using GpuHOUnivariate = GpuCostFunction<newmeshreg::HOUnivariateNonLinearSRegDiscreteCostFunction, MSMGPU_COST_HO_UNIVARIATE>;
+using GpuHOMultivariate = GpuCostFunction<newmeshreg::HOMultivariateNonLinearSRegDiscreteCostFunction, MSMGPU_COST_HO_MULTIVARIATE>;
+
+// The selection NonLinearSRegDiscreteModel::initialize_cost_function makes (DiscreteModel.cpp:44-60), returning the GPU-backed
+// class of the same kind. `model` owns labeling[]; the result still needs set_parameters(P) like the original.
+inline std::shared_ptr<newmeshreg::NonLinearSRegDiscreteCostFunction> make_gpu_costfunction(newmeshreg::DiscreteModel* model, bool multivariate,
+                                                                                           bool patchwise, bool triclique) {
+    if (multivariate) {
+        if (patchwise) return std::make_shared<GpuPatchwise>(model);
+        if (triclique) return std::make_shared<GpuHOMultivariate>(model);
+        return std::make_shared<GpuMultivariate>(model);
+    }
+    if (triclique) return std::make_shared<GpuHOUnivariate>(model);
+    return std::make_shared<GpuUnivariate>(model);
+}
+
+}  // namespace newmeshreg_gpu

@@ -75,6 +75,11 @@ public:
         for (int t = 0; t < nt; ++t)
             for (int k = 0; k < 3; ++k) tri[3 * (size_t)t + k] = m.get_triangle_vertexID(t, k);
         check(msmgpu_mesh_create(context(), nv, xyz.data(), nt, tri.data(), &h));
+        // Triangle::area is cached at construction and survives set_coord (triangle.cpp:31,39): hand over the values this Mesh
+        // object actually holds, so compute_vertex_area (mesh.cpp:1275) is reproduced whatever the object's history
+        std::vector<double> area((size_t)nt);
+        for (int t = 0; t < nt; ++t) area[t] = m.get_triangle_area(t);
+        if (nt > 0) check(msmgpu_mesh_set_triangle_areas(h, area.data()));
     }
     ~DeviceMesh() { msmgpu_mesh_destroy(h); }
     DeviceMesh(const DeviceMesh&) = delete;

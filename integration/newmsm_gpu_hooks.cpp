@@ -1,0 +1,142 @@
+// newmsm_gpu_hooks.cpp — link-time binding of the GPU library into the UNMODIFIED reference `newmsm` program.
+//
+// `make -C oracle newmsm_gpu` links the reference's own objects (src/newmsm.cpp, msm-newmeshreg, msm-newresampler, compiled
+// where they lie) with this file and libmsmgpu.so, using the linker's --wrap so that no reference source is edited:
+//
+//   NonLinearSRegDiscreteModel::initialize_cost_function (DiscreteModel.cpp:44-60)
+//        -> runs the original, then replaces `costfct` by the GPU-backed class of the same kind
+//           (include/newmsm_b200/costfunction_adapter.hpp)
+//   newresampler::metric_resample / sphere_project_warp (resampler.cpp:304, 311), as called from msm-newmeshreg
+//        -> include/newmsm_b200/resampler_adapter.hpp
+//
+//   newmeshreg::unfold (reg_tools.cpp:118-177), called on the transformed control grid and the warped source every iteration
+//        -> unchanged, but with MSMGPU_TRACE=<file> the labeling chosen by the solver and the control-point grid are appended to
+//           <file> first (exact hex doubles), so a GPU run and a CPU run can be compared label by label, iteration by iteration.
+//           Built with -DMSMGPU_TRACE_ONLY this is the only hook: the reference's CPU path, instrumented (oracle/_ref/newmsm_ref_trace).
+//
+// What a maintainer would write instead of --wrap is the three-line patch shown in INTEGRATION.md. MSMGPU_DISABLE=cost,resample
+// switches individual hooks off (A/B timing); MSMGPU_TIMING=1 prints the wall-clock split at exit.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#ifndef MSMGPU_TRACE_ONLY
+#include "newmsm_b200/costfunction_adapter.hpp"
+#include "newmsm_b200/resampler_adapter.hpp"
+#else
+#include "NewMeshReg/DiscreteModel.h"
+#endif
+
+using newmeshreg::myparam;
+using newmeshreg::NonLinearSRegDiscreteModel;
+using newresampler::Mesh;
+
+#define SYM_METRIC "_ZN12newresampler15metric_resampleERKNS_4MeshES2_iSt10shared_ptrIS0_E"
+#define SYM_WARP "_ZN12newresampler19sphere_project_warpERNS_4MeshERKS0_S3_i"
+
+#define SYM_UNFOLD "_ZN10newmeshreg6unfoldERN12newresampler4MeshEb"
+#define SYM_INIT_CF "_ZN10newmeshreg26NonLinearSRegDiscreteModel24initialize_cost_functionEbRSt3mapINSt7__cxx1112basic_stringIcSt11char_traitsIcESaIcEEESt7variantIJiS7_dbEESt4lessIS7_ESaISt4pairIKS7_S9_EEE"
+void real_unfold(Mesh& m, bool verbose) asm("__real_" SYM_UNFOLD);
+void wrap_unfold(Mesh& m, bool verbose) asm("__wrap_" SYM_UNFOLD);
+void real_initialize_cost_function(NonLinearSRegDiscreteModel* self, bool MV, myparam& P) asm("__real_" SYM_INIT_CF);
+void wrap_initialize_cost_function(NonLinearSRegDiscreteModel* self, bool MV, myparam& P) asm("__wrap_" SYM_INIT_CF);
+
+static NonLinearSRegDiscreteModel* g_model = nullptr;   // the model of the current resolution level
+
+// newmeshreg::unfold (reg_tools.cpp:118) is called on the transformed control-point grid right after applyLabeling and on the
+// warped source mesh (mesh_registration.cpp:225-229): every call is logged (FNV-1a of the coordinates); a mesh of the control
+// grid's size also gets the solver's labeling and its exact coordinates.
+void wrap_unfold(Mesh& m, bool verbose) {
+    if (const char* path = std::getenv("MSMGPU_TRACE")) {
+        static int call = 0;
+        if (FILE* f = std::fopen(path, call == 0 ? "w" : "a")) {
+            unsigned long long h = 1469598103934665603ull;
+            for (int i = 0; i < m.nvertices(); ++i) {
+                const double c[3] = {m.get_coord(i).X, m.get_coord(i).Y, m.get_coord(i).Z};
+                const unsigned char* b = reinterpret_cast<const unsigned char*>(c);
+                for (size_t k = 0; k < sizeof(c); ++k) { h ^= b[k]; h *= 1099511628211ull; }
+            }
+            std::fprintf(f, "U %d nv %d hash %016llx\n", call, m.nvertices(), h);
+            if (g_model && g_model->getNumNodes() == m.nvertices() && g_model->getLabeling()) {
+                std::fprintf(f, "L");
+                for (int i = 0; i < m.nvertices(); ++i) std::fprintf(f, " %d", g_model->getLabeling()[i]);
+                std::fprintf(f, "\nG");
+                for (int i = 0; i < m.nvertices(); ++i) std::fprintf(f, " %a %a %a", m.get_coord(i).X, m.get_coord(i).Y, m.get_coord(i).Z);
+                std::fprintf(f, "\n");
+            }
+            std::fclose(f);
+        }
+        ++call;
+    }
+    real_unfold(m, verbose);
+}
+
+#ifdef MSMGPU_TRACE_ONLY
+void wrap_initialize_cost_function(NonLinearSRegDiscreteModel* self, bool MV, myparam& P) {
+    real_initialize_cost_function(self, MV, P);
+    g_model = self;
+}
+#endif
+
+#ifndef MSMGPU_TRACE_ONLY
+Mesh real_metric_resample(const Mesh& in, const Mesh& target, int nthreads, std::shared_ptr<Mesh> EXCL) asm("__real_" SYM_METRIC);
+Mesh wrap_metric_resample(const Mesh& in, const Mesh& target, int nthreads, std::shared_ptr<Mesh> EXCL) asm("__wrap_" SYM_METRIC);
+void real_sphere_project_warp(Mesh& sphere, const Mesh& from, const Mesh& to, int nthreads) asm("__real_" SYM_WARP);
+void wrap_sphere_project_warp(Mesh& sphere, const Mesh& from, const Mesh& to, int nthreads) asm("__wrap_" SYM_WARP);
+
+namespace {
+
+bool disabled(const char* what) {
+    const char* e = std::getenv("MSMGPU_DISABLE");
+    return e && std::strstr(e, what);
+}
+
+struct Stats {
+    double resample = 0, warp = 0;
+    long n_resample = 0, n_warp = 0;
+    ~Stats() {
+        if (!std::getenv("MSMGPU_TIMING")) return;
+        const auto& t = newmeshreg_gpu::detail::timers();
+        std::fprintf(stderr,
+                     "[msmgpu] get_source_data %.3f s | unary tables %ld in %.3f s | triplet batches %ld in %.3f s | pairwise tables %.3f s | "
+                     "metric_resample %ld in %.3f s | sphere_project_warp %ld in %.3f s | kernel launches %llu\n",
+                     t.source, t.unary_tables, t.unary, t.triplet_batches, t.triplet, t.pairwise, n_resample, resample, n_warp, warp,
+                     msmgpu_launch_count());
+    }
+} stats;
+
+// the model's protected wiring, reachable from a derived view (no reference header is changed)
+struct ModelView : NonLinearSRegDiscreteModel {
+    static void install(NonLinearSRegDiscreteModel* m, myparam& P) {
+        ModelView* v = static_cast<ModelView*>(m);
+        if (v->m_regoption == 4 || v->m_regoption == 5) return;   // anatomical strain: not accelerated, the reference object stays
+        v->costfct = newmeshreg_gpu::make_gpu_costfunction(m, v->m_multivariate, v->m_patchwise, v->m_triclique);
+        v->costfct->set_parameters(P);
+    }
+};
+
+}  // namespace
+
+void wrap_initialize_cost_function(NonLinearSRegDiscreteModel* self, bool MV, myparam& P) {
+    real_initialize_cost_function(self, MV, P);
+    g_model = self;
+    if (!disabled("cost")) ModelView::install(self, P);
+}
+
+Mesh wrap_metric_resample(const Mesh& in, const Mesh& target, int nthreads, std::shared_ptr<Mesh> EXCL) {
+    if (EXCL || disabled("resample")) return real_metric_resample(in, target, nthreads, EXCL);   // exclusion masks: host-side filtering, out of scope
+    const double t0 = omp_get_wtime();
+    Mesh out = newresampler_gpu::metric_resample(in, target, nthreads);
+    stats.resample += omp_get_wtime() - t0;
+    stats.n_resample++;
+    return out;
+}
+
+void wrap_sphere_project_warp(Mesh& sphere, const Mesh& from, const Mesh& to, int nthreads) {
+    if (disabled("resample")) return real_sphere_project_warp(sphere, from, to, nthreads);
+    const double t0 = omp_get_wtime();
+    newresampler_gpu::sphere_project_warp(sphere, from, to, nthreads);
+    stats.warp += omp_get_wtime() - t0;
+    stats.n_warp++;
+}
+#endif  // MSMGPU_TRACE_ONLY

@@ -53,6 +53,7 @@ _SIGNATURES = {
     "msmgpu_mesh_metric_resample_f32": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "msmgpu_mesh_vertex_areas": (_i, [_vp, _vp]),
     "msmgpu_mesh_set_area_source": (_i, [_vp, _vp]),
+    "msmgpu_mesh_set_triangle_areas": (_i, [_vp, _vp]),
     "msmgpu_octree_build": (_i, [_vp, _pp]),
     "msmgpu_octree_build_batch": (_i, [_vp, _i, _vp, _vp]),
     "msmgpu_octree_destroy": (None, [_vp]),

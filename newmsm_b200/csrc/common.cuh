@@ -103,6 +103,7 @@ struct msmgpu_mesh {
     int feat_D = 0;
     bool tables_dirty = false;   // rec / aabb / cull not yet computed from xyz (msm::ensure_tables batches that work)
     msmgpu_mesh* area_source = nullptr;   // mesh whose geometry the cached Triangle areas belong to (msmgpu_mesh_set_area_source)
+    msm::DevBuf<double> tri_area;         // optional explicit cached Triangle::area values [nt] (msmgpu_mesh_set_triangle_areas)
 };
 
 struct msmgpu_octree {

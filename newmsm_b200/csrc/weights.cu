@@ -40,12 +40,13 @@ __device__ __forceinline__ int find_segment(const int* __restrict__ off, int n_s
 // Emitters: n_src() sources; load(i) gathers what the source's triples share, then count / key / id / val per triple.
 // All of them cover a BATCH of subjects: vertex keys of subject s are shifted by in_off[s], target keys by s * n_low.
 struct EmitVertexTriangles {   // key = vertex, id = triangle, val = cached triangle area (triangle.cpp:47-50)
-    const int* const* tri; const TriRec* const* rec; const int* tri_off; const int* key_off; int S; int total;
+    const int* const* tri; const TriRec* const* rec; const double* const* area; const int* tri_off; const int* key_off; int S; int total;
     struct Src { int t, koff; const int* tri; double area; };
     __device__ int n_src() const { return total; }
     __device__ Src load(int i) const {
         const int s = S == 1 ? 0 : find_segment(tri_off, S, i);
         const int t = i - tri_off[s];
+        if (area[s]) return Src{t, key_off[s], tri[s] + 3 * (size_t)t, area[s][t]};   // the caller's cached values
         const double* v = rec[s][t].v;
         return Src{t, key_off[s], tri[s] + 3 * (size_t)t, tri_area_cached(V3{v[0], v[1], v[2]}, V3{v[3], v[4], v[5]}, V3{v[6], v[7], v[8]})};
     }
@@ -196,17 +197,22 @@ static msmgpu_status vertex_areas_batch(msmgpu_ctx* ctx, int S, msmgpu_mesh* con
     MSM_TRY(ensure_tables(ctx, S, meshes));
     std::vector<const int*> h_tri(S);
     std::vector<const TriRec*> h_rec(S);
+    std::vector<const double*> h_area(S);
     std::vector<int> h_toff(S + 1, 0);
     for (int i = 0; i < S; ++i) {
         h_tri[i] = meshes[i]->tri.p;
         h_rec[i] = meshes[i]->rec.p;
+        h_area[i] = meshes[i]->tri_area.p;
         h_toff[i + 1] = h_toff[i] + meshes[i]->nt;
     }
     DevBuf<const int*> d_tri;
     DevBuf<const TriRec*> d_rec;
+    DevBuf<const double*> d_area;
     DevBuf<int> d_toff, d_koff;
     MSM_CUDA(d_tri.alloc(S, s));
     MSM_CUDA(d_rec.alloc(S, s));
+    MSM_CUDA(d_area.alloc(S, s));
+    MSM_CUDA(cudaMemcpyAsync(d_area.p, h_area.data(), S * sizeof(double*), cudaMemcpyHostToDevice, s));
     MSM_CUDA(d_toff.alloc(S + 1, s));
     MSM_CUDA(d_koff.alloc(S + 1, s));
     MSM_CUDA(cudaMemcpyAsync(d_tri.p, h_tri.data(), S * sizeof(int*), cudaMemcpyHostToDevice, s));
@@ -215,7 +221,7 @@ static msmgpu_status vertex_areas_batch(msmgpu_ctx* ctx, int S, msmgpu_mesh* con
     MSM_CUDA(cudaMemcpyAsync(d_koff.p, key_off.data(), (S + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
     const int total_t = h_toff[S], nkeys = key_off[S];
     Buckets B;
-    MSM_TRY(bucketize(EmitVertexTriangles{d_tri.p, d_rec.p, d_toff.p, d_koff.p, S, total_t}, total_t, nkeys, 3 * (size_t)total_t, B, s));
+    MSM_TRY(bucketize(EmitVertexTriangles{d_tri.p, d_rec.p, d_area.p, d_toff.p, d_koff.p, S, total_t}, total_t, nkeys, 3 * (size_t)total_t, B, s));
     k_bucket_mean<<<(nkeys + 255) / 256, 256, 0, s>>>(nkeys, B.ptr.p, B.val.p, d_out);
     MSM_LAUNCH_CHECK();
     return MSMGPU_OK;   // (pageable H2D copies are staged before cudaMemcpyAsync returns, the host tables may go)
@@ -464,6 +470,16 @@ msmgpu_status msmgpu_mesh_set_area_source(msmgpu_mesh* m, msmgpu_mesh* area_mesh
     if (!m || (area_mesh && (area_mesh->ctx != m->ctx || area_mesh->nv != m->nv || area_mesh->nt != m->nt || area_mesh->area_source)))
         return fail(MSMGPU_ERR_INVALID, "mesh_set_area_source: meshes must share the context and the topology");
     m->area_source = area_mesh == m ? nullptr : area_mesh;
+    return MSMGPU_OK;
+}
+
+msmgpu_status msmgpu_mesh_set_triangle_areas(msmgpu_mesh* m, const double* areas) {
+    if (!m) return fail(MSMGPU_ERR_INVALID, "mesh_set_triangle_areas: mesh is NULL");
+    MSM_CUDA(cudaSetDevice(m->ctx->device));
+    if (!areas) { m->tri_area.release(); return MSMGPU_OK; }
+    MSM_CUDA(m->tri_area.alloc((size_t)m->nt, m->ctx->stream));
+    MSM_CUDA(cudaMemcpyAsync(m->tri_area.p, areas, (size_t)m->nt * sizeof(double), cudaMemcpyHostToDevice, m->ctx->stream));
+    MSM_CUDA(cudaStreamSynchronize(m->ctx->stream));
     return MSMGPU_OK;
 }
 

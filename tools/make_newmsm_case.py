@@ -1,0 +1,77 @@
+"""Writes a synthetic pairwise-registration case for the newmsm CLI (docs/guide.md "Example B"):
+--inmesh = --refmesh = an icosphere of the given level (R = 100, FreeSurfer ASCII, mesh.cpp:455), the misalignment lives in
+the data: refdata(x) = f(x) + 5 % noise, indata(x) = f(warp(x)) with a smooth random tangential warp. Data as ASCII matrices
+([V][D] text, mesh.cpp:517). Also writes the reference's own configs with the AFFINE level removed (config/README:3).
+
+    python tools/make_newmsm_case.py --out /tmp/case --level 6 --D 1
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from newmsm_b200 import synth  # noqa: E402
+
+CONFIGS = {
+    # config/basic_configs/config_standard_MSMpair without the AFFINE level (FastPD, pairwise regulariser)
+    "MSMpair": ["--sigma_in=6,4,2", "--sigma_ref=6,4,2", "--lambda=0.1,0.2,0.3", "--it=5,10,10", "--opt=DISCRETE,DISCRETE,DISCRETE",
+                "--CPgrid=2,3,4", "--SGgrid=4,5,6", "--datagrid=5,5,6", "--regoption=1", "--dopt=FastPD"],
+    # config/HCP_multimodal_alignment/MSMAllStrainFinalconf1to1_1to3_2 (HOCR, triclique likelihood, strain regulariser)
+    "MSMAllStrain": ["--simval=2,2,2", "--sigma_in=0,0,0", "--sigma_ref=0,0,0", "--lambda=0.00001,0.0075,0.01", "--it=10,15,15",
+                     "--opt=DISCRETE,DISCRETE,DISCRETE", "--CPgrid=2,3,4", "--SGgrid=4,5,6", "--datagrid=4,5,6", "--regoption=3", "--regexp=2",
+                     "--dopt=HOCR", "--VN", "--rescaleL", "--triclique", "--k_exponent=2", "--bulkmod=1.6", "--shearmod=0.4"],
+}
+
+
+def write_asc(path, xyz, tri):
+    with open(path, "w") as f:
+        f.write("#!ascii version of synthetic sphere\n%d %d\n" % (len(xyz), len(tri)))
+        for p in xyz:
+            f.write("%.17g %.17g %.17g 0\n" % tuple(p))
+        for t in tri:
+            f.write("%d %d %d 0\n" % tuple(t))
+
+
+def scaled(cfg_lines, levels_drop, it_scale):
+    """drop the finest `levels_drop` levels / shrink the iteration counts (for quick smoke cases)"""
+    out = []
+    for ln in cfg_lines:
+        if "=" in ln and "," in ln:
+            k, v = ln.split("=")
+            vals = v.split(",")
+            if levels_drop:
+                vals = vals[:-levels_drop]
+            if k == "--it":
+                vals = [str(max(1, int(round(int(x) * it_scale)))) for x in vals]
+            ln = k + "=" + ",".join(vals)
+        out.append(ln)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", required=True)
+    ap.add_argument("--level", type=int, default=6)
+    ap.add_argument("--D", type=int, default=1)
+    ap.add_argument("--levels-drop", type=int, default=0)
+    ap.add_argument("--it-scale", type=float, default=1.0)
+    ap.add_argument("--max-disp", type=float, default=8.26)
+    a = ap.parse_args()
+    os.makedirs(a.out, exist_ok=True)
+    xyz, tri = synth.icosphere(a.level)
+    write_asc(os.path.join(a.out, "sphere.asc"), xyz, tri)
+    warped = synth.smooth_warp(xyz, max_disp=a.max_disp, seed=2024)
+    ref = synth.smooth_fields(xyz, a.D, seed0=100, noise=0.05, noise_seed=7)        # [D][V]
+    mov = synth.smooth_fields(warped, a.D, seed0=100)
+    np.savetxt(os.path.join(a.out, "refdata.txt"), ref.T, fmt="%.9g")
+    np.savetxt(os.path.join(a.out, "indata.txt"), mov.T, fmt="%.9g")
+    for name, lines in CONFIGS.items():
+        with open(os.path.join(a.out, "conf_" + name), "w") as f:
+            f.write("\n".join(scaled(lines, a.levels_drop, a.it_scale)) + "\n")
+    print("wrote", a.out)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,110 @@
+"""End-to-end `newmsm` on a synthetic case: the UNMODIFIED reference CLI on the host cores (oracle/_ref/newmsm_ref_trace) against
+the same CLI with libmsmgpu.so bound in at link time (oracle/_ref/newmsm_gpu, integration/newmsm_gpu_hooks.cpp).
+Compares the solver's labeling and the control-point grid after every discrete iteration (exact) and the final sphere.reg,
+and reports the wall-clock of both. BASELINE.json metric (iii): "newmsm wall-time vs CPU cores".
+
+    python tools/newmsm_e2e.py --level 6 --config MSMAllStrain --D 40 --threads 16 --out gpurun_out/e2e_cfg3.json
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref", "newmsm_ref_trace")
+GPU = os.path.join(ROOT, "oracle", "_ref", "newmsm_gpu")
+
+
+def parse_trace(path):
+    calls = []
+    with open(path) as f:
+        for line in f:
+            if line.startswith("U "):
+                p = line.split()
+                calls.append({"nv": int(p[3]), "hash": p[5]})
+            elif line.startswith("L "):
+                calls[-1]["labels"] = np.array(line.split()[1:], dtype=np.int32)
+            elif line.startswith("G "):
+                calls[-1]["grid"] = np.array([float.fromhex(x) for x in line.split()[1:]])
+    return calls
+
+
+def read_asc(path):
+    with open(path) as f:
+        f.readline()
+        nv, nt = map(int, f.readline().split())
+        return np.loadtxt(f, max_rows=nv)[:, :3]
+
+
+def run(binary, case, conf, out, threads, trace, extra_env=None):
+    os.makedirs(out, exist_ok=True)
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads), MSMGPU_TRACE=trace, MSMGPU_TIMING="1")
+    env.update(extra_env or {})
+    cmd = [binary, "--inmesh=" + os.path.join(case, "sphere.asc"), "--refmesh=" + os.path.join(case, "sphere.asc"),
+           "--indata=" + os.path.join(case, "indata.txt"), "--refdata=" + os.path.join(case, "refdata.txt"),
+           "--conf=" + conf, "--out=" + out + "/", "-f", "ASCII"]
+    t0 = time.perf_counter()
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True)
+    dt = time.perf_counter() - t0
+    if r.returncode != 0:
+        raise RuntimeError(f"{binary} failed ({r.returncode}):\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")
+    return dt, r.stderr.strip().splitlines()[-1:] if r.stderr.strip() else []
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--level", type=int, default=6)
+    ap.add_argument("--D", type=int, default=1)
+    ap.add_argument("--config", default="MSMpair", choices=["MSMpair", "MSMAllStrain"])
+    ap.add_argument("--levels-drop", type=int, default=0)
+    ap.add_argument("--it-scale", type=float, default=1.0)
+    ap.add_argument("--threads", type=int, default=os.cpu_count())
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--gpu-runs", type=int, default=1)
+    ap.add_argument("--out", default="")
+    a = ap.parse_args()
+    work = tempfile.mkdtemp(prefix="newmsm_case_")
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_newmsm_case.py"), "--out", work, "--level", str(a.level), "--D", str(a.D),
+                    "--levels-drop", str(a.levels_drop), "--it-scale", str(a.it_scale)], check=True, stdout=subprocess.DEVNULL)
+    conf = os.path.join(work, "conf_" + a.config)
+    with open(conf, "a") as f:
+        f.write("--numthreads=%d\n" % a.threads)
+    res = {"config": a.config, "level": a.level, "D": a.D, "levels_drop": a.levels_drop, "it_scale": a.it_scale, "host_threads": a.threads,
+           "verts": 10 * 4 ** a.level + 2}
+    gpu_times = []
+    for k in range(a.gpu_runs):
+        dt, note = run(GPU, work, conf, os.path.join(work, "out_gpu"), a.threads, os.path.join(work, "trace_gpu.txt"))
+        gpu_times.append(dt)
+        res["gpu_split"] = note
+    res["gpu_wall_s"] = min(gpu_times)
+    res["gpu_wall_all_s"] = gpu_times
+    tg = parse_trace(os.path.join(work, "trace_gpu.txt"))
+    res["discrete_iterations"] = sum(1 for c in tg if "labels" in c)
+    if not a.skip_cpu:
+        dt, _ = run(REF, work, conf, os.path.join(work, "out_cpu"), a.threads, os.path.join(work, "trace_cpu.txt"))
+        res["cpu_wall_s"] = dt
+        res["speedup"] = dt / res["gpu_wall_s"]
+        tc = parse_trace(os.path.join(work, "trace_cpu.txt"))
+        res["trace_calls"] = [len(tc), len(tg)]
+        n = min(len(tc), len(tg))
+        res["hashes_equal"] = sum(1 for i in range(n) if tc[i]["hash"] == tg[i]["hash"])
+        lab = [(x["labels"], y["labels"]) for x, y in zip(tc, tg) if "labels" in x and "labels" in y]
+        res["label_iterations"] = len(lab)
+        res["label_mismatch_per_iteration"] = [int((x != y).sum()) if len(x) == len(y) else -1 for x, y in lab]
+        res["labels_bit_exact"] = len(tc) == len(tg) and all(m == 0 for m in res["label_mismatch_per_iteration"])
+        res["all_meshes_bit_exact"] = len(tc) == len(tg) and res["hashes_equal"] == n
+        a_, b_ = read_asc(os.path.join(work, "out_cpu", "sphere.reg.asc")), read_asc(os.path.join(work, "out_gpu", "sphere.reg.asc"))
+        res["final_sphere_max_abs_diff"] = float(np.abs(a_ - b_).max())
+    print(json.dumps(res))
+    if a.out:
+        with open(a.out, "w") as f:
+            json.dump(res, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
