@@ -20,7 +20,10 @@
 // regoption 4/5 (anatomical strain) are not accelerated: install_gpu_costfunction() leaves the reference's object in place.
 #pragma once
 
+#include <algorithm>
 #include <atomic>
+#include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -99,6 +102,17 @@ struct Timers {   // wall-clock split printed by the integration binary (seconds
     long unary_tables = 0, triplet_batches = 0;
 };
 inline Timers& timers() { static Timers t; return t; }
+
+// MSMGPU_VERIFY=1: diagnostic mode. The reference's own CPU implementation of every overridden virtual runs side by side,
+// in-process, on the same object state, and the results are compared bit for bit (report on stderr).
+inline bool verify() { static const bool v = std::getenv("MSMGPU_VERIFY") != nullptr; return v; }
+inline long count_diff(const double* a, const double* b, size_t n, double* worst) {
+    long bad = 0;
+    *worst = 0;
+    for (size_t i = 0; i < n; ++i)
+        if (std::memcmp(a + i, b + i, sizeof(double)) != 0) { ++bad; *worst = std::max(*worst, std::fabs(a[i] - b[i])); }
+    return bad;
+}
 
 }  // namespace detail
 
@@ -206,6 +220,19 @@ class GpuCostFunction : public Base {
         }
         detail::timers().triplet += omp_get_wtime() - t0;
         detail::timers().triplet_batches++;
+        if (detail::verify()) {
+            long bad = 0, n = 0;
+            double worst = 0;
+            for (int t = 0; t < T; t += 5) {
+                const int a = trip_[3 * t], b = trip_[3 * t + 1], c = trip_[3 * t + 2];
+                for (int combo = 0; combo < (label < 0 ? 1 : 8); ++combo, ++n) {
+                    const int la = (combo & 4) ? label : tb->snap[a], lb = (combo & 2) ? label : tb->snap[b], lc = (combo & 1) ? label : tb->snap[c];
+                    const double r = Base::computeTripletCost(t, la, lb, lc), g = label < 0 ? tb->val[t] : tb->val[8 * (size_t)t + combo];
+                    if (std::memcmp(&r, &g, sizeof(double)) != 0) { ++bad; worst = std::max(worst, std::fabs(r - g) / std::max(std::fabs(r), 1e-300)); }
+                }
+            }
+            std::fprintf(stderr, "[msmgpu verify] triplet batch (label %d): %ld of %ld sampled costs differ (max rel %.3g)\n", label, bad, n, worst);
+        }
         return tb;
     }
 
@@ -248,6 +275,21 @@ public:
             detail::check(msmgpu_costfn_set_cpgrid(d_cf_, N, cp.data(), sep.data(), this->_controlptrange, cfw_rows, cfw.data(), absw.data()));
         }
         detail::timers().source += omp_get_wtime() - t0;
+        if (detail::verify()) {
+            Base::get_source_data();   // the reference's patches (and AbsoluteWeights again) for the side-by-side evaluation
+            const int rows = kHO ? this->_CPgrid.ntriangles() : N;
+            std::vector<int32_t> rowptr((size_t)rows + 1), mem((size_t)64 * ns + 1024);
+            detail::check(msmgpu_costfn_patches(d_cf_, rowptr.data(), nullptr));
+            if ((size_t)rowptr[rows] > mem.size()) mem.resize(rowptr[rows]);
+            detail::check(msmgpu_costfn_patches(d_cf_, rowptr.data(), mem.data()));
+            long bad = 0;
+            for (int k = 0; k < rows; ++k) {
+                const std::vector<int>& ref = this->_sourceinrange[k];
+                const bool same = (int)ref.size() == rowptr[k + 1] - rowptr[k] && std::equal(ref.begin(), ref.end(), mem.begin() + rowptr[k]);
+                bad += !same;
+            }
+            std::fprintf(stderr, "[msmgpu verify] get_source_data: %d patches, %d entries, %ld patches differ\n", rows, rowptr[rows], bad);
+        }
     }
 
     void computeUnaryCosts() override {
@@ -255,6 +297,15 @@ public:
         std::lock_guard<std::mutex> g(mu_);
         build_unary_table();
         unary_ready_.store(true);
+        if (detail::verify()) {
+            const int N = this->m_num_nodes, L = this->m_num_labels;
+            std::vector<double> ref((size_t)N * L);
+            for (int j = 0; j < L; ++j)
+                for (int k = 0; k < N; ++k) ref[(size_t)j * N + k] = Base::computeUnaryCost(k, j);   // single thread: see the races noted in tests/
+            double worst;
+            const long bad = detail::count_diff(ref.data(), this->unarycosts, ref.size(), &worst);
+            std::fprintf(stderr, "[msmgpu verify] unary table %d x %d: %ld entries differ (max |diff| %.3g)\n", L, N, bad, worst);
+        }
     }
 
     double computeUnaryCost(int node, int label) override {
@@ -320,6 +371,16 @@ public:
         }
         (void)pairs;
         detail::timers().pairwise += omp_get_wtime() - t0;
+        if (detail::verify()) {
+            long bad = 0, n = 0;
+            for (int i = 0; i < P; i += 7)
+                for (int j = 0; j < L; ++j)
+                    for (int k = 0; k < L; ++k, ++n) {
+                        const double r = Base::computePairwiseCost(i, j, k), g = this->paircosts[i * LL * LL + k * LL + j];
+                        bad += std::memcmp(&r, &g, sizeof(double)) != 0;
+                    }
+            std::fprintf(stderr, "[msmgpu verify] pairwise table: %ld of %ld sampled entries differ\n", bad, n);
+        }
     }
 
 };

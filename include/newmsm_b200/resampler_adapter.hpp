@@ -10,9 +10,12 @@
 // Checked in-process against the reference's own CPU functions by integration/adapter_check.cpp.
 #pragma once
 
+#include <cmath>
+#include <cstdint>
 #include <map>
 #include <memory>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #ifndef NEWMSM_B200_RESAMPLER_HEADER
@@ -217,6 +220,74 @@ inline Mesh nearest_neighbour_interpolation(Mesh& orig, const Mesh& sphLow, int 
     std::vector<double> fout((size_t)D * sphLow.nvertices());
     detail::check(msmgpu_nn_resample(a.h, sphLow.nvertices(), low.data(), D, fin.data(), fout.data()));
     return detail::with_pvalues(sphLow, D, fout);
+}
+
+}  // namespace newresampler_gpu
+
+namespace newresampler_gpu {
+
+// make_mesh_from_icosa (mesh.cpp:1111-1196) without the O(V^2) duplicate-midpoint scan of retessellate (mesh.cpp:910-1008):
+// a midpoint belongs to an undirected edge, so the linear search over all added points (Point== with 1e-8 tolerance,
+// mesh.cpp:945-960) is an edge hash lookup. Vertex ids, face ids, face orientation and every coordinate are the ones the
+// reference produces: new points are numbered in first-seen order, per old face (v0,v1,v2) in the order mid(v1,v2), mid(v0,v2),
+// mid(v0,v1); the four children are (p2,p0,p1), (p1,v0,p2), (p0,v2,p1), (p2,v1,p0); all points are re-normalised after every
+// level with Point::normalize's arithmetic (point.cpp:26-34). Host code: 5.6 s -> 40 ms for ico6.
+inline Mesh make_mesh_from_icosa(int n) {
+    const double t = 0.8506508084, o = 0.5257311121;
+    std::vector<double> v = {t, o, 0, -t, o, 0, -t, -o, 0, t, -o, 0, o, 0, t, o, 0, -t, -o, 0, -t, -o, 0, t, 0, t, o, 0, -t, o, 0, -t, -o, 0, t, -o};
+    enum { ZA, ZB, ZC, ZD, YA, YB, YC, YD, XA, XB, XC, XD };
+    const int base[20][3] = {{YD, XA, YA}, {XB, YD, YA}, {XD, YC, YB}, {YC, XC, YB}, {ZD, YA, ZA}, {YB, ZD, ZA}, {ZB, YD, ZC}, {YC, ZB, ZC},
+                             {XD, ZA, XA}, {ZB, XD, XA}, {ZD, XC, XB}, {XC, ZC, XB}, {ZA, YA, XA}, {YB, ZA, XD}, {ZD, XB, YA}, {XC, ZD, YB},
+                             {ZB, XA, YD}, {XD, ZB, YC}, {XB, ZC, YD}, {ZC, XC, YC}};
+    std::vector<int> f;
+    for (const auto& b : base) { f.push_back(b[0]); f.push_back(b[2]); f.push_back(b[1]); }   // swap_orientation (mesh.cpp:1183-1184)
+    auto normalise = [](std::vector<double>& c) {
+        for (size_t i = 0; i < c.size() / 3; ++i) {
+            const double x = c[3 * i], y = c[3 * i + 1], z = c[3 * i + 2];
+            const double nrm = std::sqrt(x * x + y * y + z * z);
+            if (nrm > 1e-8) { c[3 * i] = x / nrm; c[3 * i + 1] = y / nrm; c[3 * i + 2] = z / nrm; }
+        }
+    };
+    for (int level = 0; level < n; ++level) {
+        const int nv = (int)v.size() / 3, nt = (int)f.size() / 3;
+        std::unordered_map<uint64_t, int> mid;
+        mid.reserve((size_t)nt * 2);
+        std::vector<int> nf;
+        nf.reserve((size_t)nt * 12);
+        auto midpoint = [&](int a, int b) {   // (a + b) / 2 with a, b as written in mesh.cpp:928-936
+            const uint64_t key = ((uint64_t)std::min(a, b) << 32) | (uint32_t)std::max(a, b);
+            auto it = mid.find(key);
+            if (it != mid.end()) return it->second;
+            const int id = (int)v.size() / 3;
+            for (int k = 0; k < 3; ++k) v.push_back((v[3 * (size_t)a + k] + v[3 * (size_t)b + k]) / 2);
+            mid.emplace(key, id);
+            return id;
+        };
+        for (int i = 0; i < nt; ++i) {
+            const int v0 = f[3 * (size_t)i], v1 = f[3 * (size_t)i + 1], v2 = f[3 * (size_t)i + 2];
+            const int p0 = midpoint(v1, v2), p1 = midpoint(v0, v2), p2 = midpoint(v0, v1);
+            const int kids[12] = {p2, p0, p1, p1, v0, p2, p0, v2, p1, p2, v1, p0};
+            nf.insert(nf.end(), kids, kids + 12);
+        }
+        f.swap(nf);
+        (void)nv;
+        // the LAST level is normalised on the Mesh object below: the reference creates its Triangle objects (and caches their
+        // areas, triangle.cpp:31) before that normalisation, and compute_vertex_area later reads those cached values
+        if (level + 1 < n) normalise(v);
+    }
+    Mesh ret;
+    const int nv = (int)v.size() / 3, nt = (int)f.size() / 3;
+    for (int i = 0; i < nv; ++i) ret.push_point(std::make_shared<newresampler::Mpoint>(v[3 * (size_t)i], v[3 * (size_t)i + 1], v[3 * (size_t)i + 2], i));
+    const auto& pts = ret.get_all_points();
+    if (n > 0) {
+        for (int i = 0; i < nt; ++i) ret.push_triangle(Triangle(pts[f[3 * (size_t)i]], pts[f[3 * (size_t)i + 1]], pts[f[3 * (size_t)i + 2]], i));
+        for (auto i = ret.vbegin(); i != ret.vend(); i++) (*i)->normalize();   // mesh.cpp:1006-1007
+    } else {   // the bare icosahedron keeps the adjacency lists of the un-swapped faces (pushed first, swapped after: mesh.cpp:1162-1184)
+        for (int i = 0; i < nt; ++i) ret.push_triangle(Triangle(pts[f[3 * (size_t)i]], pts[f[3 * (size_t)i + 2]], pts[f[3 * (size_t)i + 1]], i));
+        for (auto i = ret.tbegin(); i != ret.tend(); i++) i->swap_orientation();
+    }
+    ret.push_pvalues(std::vector<double>((size_t)nv, 0.0));
+    return ret;
 }
 
 }  // namespace newresampler_gpu

@@ -95,6 +95,38 @@ int main() {
         EXPECT(same_pvalues(nearest_neighbour_interpolation(in, low, 1), newresampler_gpu::nearest_neighbour_interpolation(in, low, 1)),
                "nearest_neighbour_interpolation: identical values");
 
+        // make_mesh_from_icosa (mesh.cpp:1111): identical object state, including the Triangle areas cached BEFORE the last
+        // normalisation and the per-point neighbour / triangle lists (the CPU generator needs no device: checked for 0..5)
+        bool gen_ok = true;
+        for (int level = 0; level <= 5; ++level) {
+            Mesh a = make_mesh_from_icosa(level), b = newresampler_gpu::make_mesh_from_icosa(level);
+            gen_ok = gen_ok && a.nvertices() == b.nvertices() && a.ntriangles() == b.ntriangles() && same_coords(a, b) && same_pvalues(a, b);
+            for (int t = 0; gen_ok && t < a.ntriangles(); ++t) {
+                for (int k = 0; k < 3; ++k) gen_ok = gen_ok && a.get_triangle_vertexID(t, k) == b.get_triangle_vertexID(t, k);
+                const double x = a.get_triangle_area(t), y = b.get_triangle_area(t);
+                gen_ok = gen_ok && std::memcmp(&x, &y, sizeof(double)) == 0 && a.get_triangle(t).get_no() == b.get_triangle(t).get_no();
+            }
+            for (int v = 0; gen_ok && v < a.nvertices(); ++v) {
+                gen_ok = gen_ok && std::vector<int>(a.nbegin(v), a.nend(v)) == std::vector<int>(b.nbegin(v), b.nend(v));
+                gen_ok = gen_ok && std::vector<int>(a.tIDbegin(v), a.tIDend(v)) == std::vector<int>(b.tIDbegin(v), b.tIDend(v));
+            }
+        }
+        EXPECT(gen_ok, "make_mesh_from_icosa: identical vertices, faces, cached areas and adjacency lists for ico0..ico5");
+
+        // meshes as the reference's call sites make them: generated, rescaled, moved, NOT copied -> Triangle::area is stale
+        // (triangle.cpp:31,39) and compute_vertex_area (mesh.cpp:1275) reads it. The adapter mirrors the object's cached values.
+        {
+            Mesh stale_low = make_mesh_from_icosa(4);
+            true_rescale(stale_low, RAD);
+            Mesh stale_in = in;
+            Mesh moved = sphere(5, 0.004, -0.003, 0.002);
+            for (int v = 0; v < stale_in.nvertices(); ++v) stale_in.set_coord(v, moved.get_coord(v));
+            EXPECT(same_pvalues(metric_resample(stale_in, stale_low, 1), newresampler_gpu::metric_resample(stale_in, stale_low, 1)),
+                   "metric_resample on meshes with stale cached triangle areas: GPU == reference CPU, bit for bit");
+            EXPECT(!same_pvalues(metric_resample(stale_in, stale_low, 1), metric_resample(Mesh(stale_in), Mesh(stale_low), 1)),
+                   "(those stale areas do change the result, i.e. the case is not vacuous)");
+        }
+
         // error behaviour: the reference's exception with the reference's message (octree.cpp:158)
         bool threw = false;
         try { og.get_closest_triangle(Point(0, 0, 150)); } catch (MeshException& e) { threw = std::strstr(e.what(), "bounding box") != nullptr; }

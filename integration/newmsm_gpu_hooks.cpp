@@ -18,6 +18,7 @@
 // switches individual hooks off (A/B timing); MSMGPU_TIMING=1 prints the wall-clock split at exit.
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 
 #ifndef MSMGPU_TRACE_ONLY
@@ -123,20 +124,49 @@ void wrap_initialize_cost_function(NonLinearSRegDiscreteModel* self, bool MV, my
     if (!disabled("cost")) ModelView::install(self, P);
 }
 
+// MSMGPU_VERIFY=1: every hooked call ALSO runs the reference's CPU implementation in-process and the two results are compared
+// bit for bit (diagnostic mode; timings are meaningless with it).
+static bool verify() { static const bool v = std::getenv("MSMGPU_VERIFY") != nullptr; return v; }
+
 Mesh wrap_metric_resample(const Mesh& in, const Mesh& target, int nthreads, std::shared_ptr<Mesh> EXCL) {
     if (EXCL || disabled("resample")) return real_metric_resample(in, target, nthreads, EXCL);   // exclusion masks: host-side filtering, out of scope
     const double t0 = omp_get_wtime();
     Mesh out = newresampler_gpu::metric_resample(in, target, nthreads);
     stats.resample += omp_get_wtime() - t0;
     stats.n_resample++;
+    if (verify()) {
+        const Mesh ref = real_metric_resample(in, target, nthreads, EXCL);
+        long bad = 0;
+        double worst = 0;
+        for (int d = 0; d < ref.get_dimension(); ++d)
+            for (int v = 0; v < ref.nvertices(); ++v) {
+                const double a = ref.get_pvalue(v, d), b = out.get_pvalue(v, d);
+                if (std::memcmp(&a, &b, sizeof(double)) != 0) { ++bad; worst = std::max(worst, std::fabs(a - b)); }
+            }
+        std::fprintf(stderr, "[msmgpu verify] metric_resample #%ld  %d -> %d vertices, D=%d: %ld values differ (max |diff| %.3g)\n", stats.n_resample,
+                     in.nvertices(), target.nvertices(), ref.get_dimension(), bad, worst);
+    }
     return out;
 }
 
 void wrap_sphere_project_warp(Mesh& sphere, const Mesh& from, const Mesh& to, int nthreads) {
     if (disabled("resample")) return real_sphere_project_warp(sphere, from, to, nthreads);
+    Mesh before;
+    if (verify()) before = sphere;
     const double t0 = omp_get_wtime();
     newresampler_gpu::sphere_project_warp(sphere, from, to, nthreads);
     stats.warp += omp_get_wtime() - t0;
     stats.n_warp++;
+    if (verify()) {
+        real_sphere_project_warp(before, from, to, nthreads);
+        long bad = 0;
+        int first = -1;
+        for (int v = 0; v < before.nvertices(); ++v) {
+            const newresampler::Point &a = before.get_coord(v), &b = sphere.get_coord(v);
+            if (a.X != b.X || a.Y != b.Y || a.Z != b.Z) { if (first < 0) first = v; ++bad; }
+        }
+        std::fprintf(stderr, "[msmgpu verify] sphere_project_warp #%ld  %d points in a %d-vertex mesh: %ld points differ (first %d)\n", stats.n_warp,
+                     before.nvertices(), from.nvertices(), bad, first);
+    }
 }
 #endif  // MSMGPU_TRACE_ONLY

@@ -53,7 +53,8 @@ def run(binary, case, conf, out, threads, trace, extra_env=None):
     dt = time.perf_counter() - t0
     if r.returncode != 0:
         raise RuntimeError(f"{binary} failed ({r.returncode}):\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")
-    return dt, r.stderr.strip().splitlines()[-1:] if r.stderr.strip() else []
+    lines = r.stderr.strip().splitlines()
+    return dt, [ln for ln in lines if ln.startswith("[msmgpu")]
 
 
 def main():
@@ -65,7 +66,13 @@ def main():
     ap.add_argument("--it-scale", type=float, default=1.0)
     ap.add_argument("--threads", type=int, default=os.cpu_count())
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--parity-threads", type=int, default=1,
+                    help="threads of the CPU run the labels are compared with. The reference is only deterministic single-threaded: "
+                         "get_adaptive_barycentric_weights accumulates `correction[]` in an omp loop without atomics (resampler.cpp:99-118)")
+    ap.add_argument("--skip-timing-cpu", action="store_true", help="do not run the all-threads CPU arm (timing)")
     ap.add_argument("--gpu-runs", type=int, default=1)
+    ap.add_argument("--disable", default="", help="MSMGPU_DISABLE value for the GPU run (cost, resample): A/B isolation of the hooks")
+    ap.add_argument("--verify", action="store_true", help="MSMGPU_VERIFY=1: the hooks also run the reference CPU code in-process and compare")
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     work = tempfile.mkdtemp(prefix="newmsm_case_")
@@ -78,17 +85,31 @@ def main():
            "verts": 10 * 4 ** a.level + 2}
     gpu_times = []
     for k in range(a.gpu_runs):
-        dt, note = run(GPU, work, conf, os.path.join(work, "out_gpu"), a.threads, os.path.join(work, "trace_gpu.txt"))
+        dt, note = run(GPU, work, conf, os.path.join(work, "out_gpu"), a.threads, os.path.join(work, "trace_gpu.txt"),
+                       dict(({"MSMGPU_DISABLE": a.disable} if a.disable else {}), **({"MSMGPU_VERIFY": "1"} if a.verify else {})))
         gpu_times.append(dt)
         res["gpu_split"] = note
     res["gpu_wall_s"] = min(gpu_times)
     res["gpu_wall_all_s"] = gpu_times
     tg = parse_trace(os.path.join(work, "trace_gpu.txt"))
     res["discrete_iterations"] = sum(1 for c in tg if "labels" in c)
-    if not a.skip_cpu:
-        dt, _ = run(REF, work, conf, os.path.join(work, "out_cpu"), a.threads, os.path.join(work, "trace_cpu.txt"))
+    if not a.skip_cpu and not a.skip_timing_cpu:
+        dt, _ = run(REF, work, conf, os.path.join(work, "out_cpu_mt"), a.threads, os.path.join(work, "trace_cpu_mt.txt"))
         res["cpu_wall_s"] = dt
+        res["cpu_threads"] = a.threads
         res["speedup"] = dt / res["gpu_wall_s"]
+        tm = parse_trace(os.path.join(work, "trace_cpu_mt.txt"))
+        lab = [(x["labels"], y["labels"]) for x, y in zip(tm, tg) if "labels" in x and "labels" in y]
+        res["label_mismatch_vs_multithreaded_cpu"] = [int((x != y).sum()) if len(x) == len(y) else -1 for x, y in lab]
+    if not a.skip_cpu:
+        conf1 = conf + "_parity"
+        with open(conf) as f:
+            lines = [ln for ln in f.read().splitlines() if not ln.startswith("--numthreads")]
+        with open(conf1, "w") as f:
+            f.write("\n".join(lines + ["--numthreads=%d" % a.parity_threads]) + "\n")
+        dt, _ = run(REF, work, conf1, os.path.join(work, "out_cpu"), a.parity_threads, os.path.join(work, "trace_cpu.txt"))
+        res["cpu_parity_wall_s"] = dt
+        res["cpu_parity_threads"] = a.parity_threads
         tc = parse_trace(os.path.join(work, "trace_cpu.txt"))
         res["trace_calls"] = [len(tc), len(tg)]
         n = min(len(tc), len(tg))
