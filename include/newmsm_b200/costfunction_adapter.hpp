@@ -100,6 +100,7 @@ struct PairWorker : newmeshreg::NonLinearSRegDiscreteCostFunction {
 struct Timers {   // wall-clock split printed by the integration binary (seconds)
     double source = 0, unary = 0, triplet = 0, pairwise = 0;
     long unary_tables = 0, triplet_batches = 0;
+    double source_done_at = 0;   // omp_get_wtime() when the last get_source_data returned (the optimiser runs next)
 };
 inline Timers& timers() { static Timers t; return t; }
 
@@ -275,6 +276,7 @@ public:
             detail::check(msmgpu_costfn_set_cpgrid(d_cf_, N, cp.data(), sep.data(), this->_controlptrange, cfw_rows, cfw.data(), absw.data()));
         }
         detail::timers().source += omp_get_wtime() - t0;
+        detail::timers().source_done_at = omp_get_wtime();
         if (detail::verify()) {
             Base::get_source_data();   // the reference's patches (and AbsoluteWeights again) for the side-by-side evaluation
             const int rows = kHO ? this->_CPgrid.ntriangles() : N;

@@ -34,6 +34,8 @@ using newresampler::Mesh;
 
 #define SYM_METRIC "_ZN12newresampler15metric_resampleERKNS_4MeshES2_iSt10shared_ptrIS0_E"
 #define SYM_WARP "_ZN12newresampler19sphere_project_warpERNS_4MeshERKS0_S3_i"
+#define SYM_ICOSA "_ZN12newresampler20make_mesh_from_icosaEi"
+#define SYM_FEATINIT "_ZN10newmeshreg12featurespace10initialiseEiRSt6vectorIN12newresampler4MeshESaIS3_EEb"
 
 #define SYM_UNFOLD "_ZN10newmeshreg6unfoldERN12newresampler4MeshEb"
 #define SYM_INIT_CF "_ZN10newmeshreg26NonLinearSRegDiscreteModel24initialize_cost_functionEbRSt3mapINSt7__cxx1112basic_stringIcSt11char_traitsIcESaIcEEESt7variantIJiS7_dbEESt4lessIS7_ESaISt4pairIKS7_S9_EEE"
@@ -85,6 +87,11 @@ Mesh wrap_metric_resample(const Mesh& in, const Mesh& target, int nthreads, std:
 void real_sphere_project_warp(Mesh& sphere, const Mesh& from, const Mesh& to, int nthreads) asm("__real_" SYM_WARP);
 void wrap_sphere_project_warp(Mesh& sphere, const Mesh& from, const Mesh& to, int nthreads) asm("__wrap_" SYM_WARP);
 
+Mesh real_make_mesh_from_icosa(int n) asm("__real_" SYM_ICOSA);
+Mesh wrap_make_mesh_from_icosa(int n) asm("__wrap_" SYM_ICOSA);
+Mesh real_featurespace_initialise(newmeshreg::featurespace* self, int ico, std::vector<Mesh>& IN, bool exclude) asm("__real_" SYM_FEATINIT);
+Mesh wrap_featurespace_initialise(newmeshreg::featurespace* self, int ico, std::vector<Mesh>& IN, bool exclude) asm("__wrap_" SYM_FEATINIT);
+
 namespace {
 
 bool disabled(const char* what) {
@@ -93,16 +100,19 @@ bool disabled(const char* what) {
 }
 
 struct Stats {
-    double resample = 0, warp = 0;
-    long n_resample = 0, n_warp = 0;
+    double resample = 0, warp = 0, icosa = 0, featinit = 0, optimise = 0;
+    long n_resample = 0, n_warp = 0, n_icosa = 0;
+    const double t_start = omp_get_wtime();
     ~Stats() {
         if (!std::getenv("MSMGPU_TIMING")) return;
         const auto& t = newmeshreg_gpu::detail::timers();
         std::fprintf(stderr,
                      "[msmgpu] get_source_data %.3f s | unary tables %ld in %.3f s | triplet batches %ld in %.3f s | pairwise tables %.3f s | "
-                     "metric_resample %ld in %.3f s | sphere_project_warp %ld in %.3f s | kernel launches %llu\n",
-                     t.source, t.unary_tables, t.unary, t.triplet_batches, t.triplet, t.pairwise, n_resample, resample, n_warp, warp,
-                     msmgpu_launch_count());
+                     "metric_resample %ld in %.3f s | sphere_project_warp %ld in %.3f s | make_mesh_from_icosa %ld in %.3f s | "
+                     "featurespace::initialise %.3f s (incl. its resamples) | optimiser phases (solver + cost calls) %.3f s | process %.3f s | "
+                     "kernel launches %llu\n",
+                     t.source, t.unary_tables, t.unary, t.triplet_batches, t.triplet, t.pairwise, n_resample, resample, n_warp, warp, n_icosa, icosa,
+                     featinit, optimise, omp_get_wtime() - t_start, msmgpu_launch_count());
     }
 } stats;
 
@@ -151,6 +161,9 @@ Mesh wrap_metric_resample(const Mesh& in, const Mesh& target, int nthreads, std:
 
 void wrap_sphere_project_warp(Mesh& sphere, const Mesh& from, const Mesh& to, int nthreads) {
     if (disabled("resample")) return real_sphere_project_warp(sphere, from, to, nthreads);
+    // the first warp after get_source_data closes the optimiser phase of a discrete iteration (mesh_registration.cpp:170-222)
+    double& mark = newmeshreg_gpu::detail::timers().source_done_at;
+    if (mark > 0) { stats.optimise += omp_get_wtime() - mark; mark = 0; }
     Mesh before;
     if (verify()) before = sphere;
     const double t0 = omp_get_wtime();
@@ -170,3 +183,22 @@ void wrap_sphere_project_warp(Mesh& sphere, const Mesh& from, const Mesh& to, in
     }
 }
 #endif  // MSMGPU_TRACE_ONLY
+
+#ifndef MSMGPU_TRACE_ONLY
+// mesh.cpp:1111-1196 -> the edge-hash generator of the resampler adapter (identical object, 80x faster at ico6)
+Mesh wrap_make_mesh_from_icosa(int n) {
+    if (disabled("icosa")) return real_make_mesh_from_icosa(n);
+    const double t0 = omp_get_wtime();
+    Mesh m = newresampler_gpu::make_mesh_from_icosa(n);
+    stats.icosa += omp_get_wtime() - t0;
+    stats.n_icosa++;
+    return m;
+}
+
+Mesh wrap_featurespace_initialise(newmeshreg::featurespace* self, int ico, std::vector<Mesh>& IN, bool exclude) {   // timing only
+    const double t0 = omp_get_wtime();
+    Mesh m = real_featurespace_initialise(self, ico, IN, exclude);
+    stats.featinit += omp_get_wtime() - t0;
+    return m;
+}
+#endif

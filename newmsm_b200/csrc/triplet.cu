@@ -50,15 +50,12 @@ __host__ __device__ __forceinline__ double det3(const double* m) {
     return m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
 }
 
-// x^e; the two exponents every shipped config uses (2 and 1) are exact products, so they match a correctly
-// rounded pow() bit for bit; other exponents use CUDA's pow (<= 2 ulp from glibc's)
-__device__ __forceinline__ double pow_cfg(double x, double e) {
-    if (e == 2.0) return x * x;
-    if (e == 1.0) return x;
-    return pow(x, e);
-}
+// The three pow() calls of the path (reg_tools.cpp:596, DiscreteCostFunction.cpp:187) are evaluated with the HOST libm, like
+// estimate_rotation_matrix: glibc's pow(x, 2.0) is not always the correctly rounded x*x and CUDA's pow is not
+// glibc's, while the costs feed a discrete optimiser. The kernel stops at the pow arguments (R = major/minor stretch ratio,
+// J = area ratio); triplet_run() finishes W and the cost on the host with the reference's own expression order.
 
-__device__ double triangle_strain_dev(const double* AA, const double* BB, double MU, double KAPPA, double k_exp) {   // reg_tools.cpp:551-646
+__device__ void triangle_strain_dev(const double* AA, const double* BB, double& R_out, double& J_out) {   // reg_tools.cpp:551-594
     const double c0 = AA[3] - AA[0], c1 = AA[4] - AA[1], c4 = AA[6] - AA[0], c5 = AA[7] - AA[1];
     const double c0c = BB[3] - BB[0], c1c = BB[4] - BB[1], c4c = BB[6] - BB[0], c5c = BB[7] - BB[1];
     const double det = c0 * c5 - c4 * c1;
@@ -76,11 +73,11 @@ __device__ double triangle_strain_dev(const double* AA, const double* BB, double
     double R;
     if (I1st_new <= 2) R = 1.0;
     else R = 0.5 * (I1st_new + sqrt(I1st_new * I1st_new - 4));
-    const double Rshared = pow_cfg(R, k_exp), Jshared = pow_cfg(J, k_exp);
-    return 0.5 * (MU * (Rshared + 1.0 / Rshared - 2) + KAPPA * (Jshared + 1.0 / Jshared - 2));
+    R_out = R;
+    J_out = J;
 }
 
-__device__ double triangular_strain_dev(const V3* O, const V3* F, double mu, double kappa, double k_exp) {   // reg_tools.cpp:698-743
+__device__ void triangular_strain_dev(const V3* O, const V3* F, double& R_out, double& J_out) {   // reg_tools.cpp:698-743
     const V3 NO = tri_normal(O[0], O[1], O[2]), NF = tri_normal(F[0], F[1], F[2]);
     V3 e1, e2, f1, f2;
     tangents(NO, e1, e2);
@@ -103,7 +100,7 @@ __device__ double triangular_strain_dev(const V3* O, const V3* F, double mu, dou
             A[3 * i + j] = O[i].x * TR[j] + O[i].y * TR[3 + j] + O[i].z * TR[6 + j];
             B[3 * i + j] = F[i].x * TR2[j] + F[i].y * TR2[3 + j] + F[i].z * TR2[6 + j];
         }
-    return triangle_strain_dev(A, B, mu, kappa, k_exp);
+    triangle_strain_dev(A, B, R_out, J_out);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -148,6 +145,7 @@ struct TripletArgs {
     const double* src_xyz; const int* prow; const int* pmem;
     const double* src_feat; const double* ref_feat; const double* cfw; const double* absw;
     double lambda, mu, kappa, k_exp, rexp;
+    double* aux;              // [n][2]: R, J of the strain energy (R = NaN: out[r] is already final)
     double* out;              // [n]
     int* err;
 };
@@ -188,7 +186,7 @@ __global__ void __launch_bounds__(kTripWarps * 32) k_triplet_costs(TripletArgs a
     }
     // only estimate the cost if it does not cause folding (cpp:152)
     if (vdot(tri_normal(def[0], def[1], def[2]), tri_normal(cur[0], cur[1], cur[2])) < 0.0) {
-        if (lane == 0) a.out[r] = 1e7 * a.lambda;
+        if (lane == 0) { a.out[r] = 1e7 * a.lambda; a.aux[2 * (size_t)r] = nan(""); a.aux[2 * (size_t)r + 1] = 0.0; }   // final as is
         return;
     }
     double likelihood = 0.0;
@@ -228,7 +226,7 @@ __global__ void __launch_bounds__(kTripWarps * 32) k_triplet_costs(TripletArgs a
             }
         }
         if (__any_sync(kFull, bad)) {
-            if (lane == 0) { a.out[r] = nan(""); *a.err = 1; }
+            if (lane == 0) { a.out[r] = nan(""); a.aux[2 * (size_t)r] = nan(""); a.aux[2 * (size_t)r + 1] = 0.0; *a.err = 1; }
             return;
         }
         __syncwarp();
@@ -263,8 +261,11 @@ __global__ void __launch_bounds__(kTripWarps * 32) k_triplet_costs(TripletArgs a
         if (lane == 0) likelihood = (__ldg(a.absw + ids[0]) + __ldg(a.absw + ids[1]) + __ldg(a.absw + ids[2])) / 3.0 * cost;
     }
     if (lane == 0) {   // regoption 2/3 (cpp:158-166), then cpp:187
-        const double W = triangular_strain_dev(org, def, a.mu, a.kappa, a.k_exp);
-        a.out[r] = likelihood + a.lambda * pow_cfg(W, a.rexp);
+        double R, J;
+        triangular_strain_dev(org, def, R, J);
+        a.out[r] = likelihood;             // + lambda * pow(W(R, J), rexp), added by the host (see the note on pow above)
+        a.aux[2 * (size_t)r] = R;
+        a.aux[2 * (size_t)r + 1] = J;
     }
 }
 
@@ -309,7 +310,9 @@ static msmgpu_status triplet_run(msmgpu_costfn* c, int ntrip, const int32_t* tri
     } else {
         MSM_TRY(up(d_labeling, labeling, (size_t)c->ncp, s));
     }
+    DevBuf<double> d_aux;
     MSM_CUDA(d_out.alloc((size_t)n, s));
+    MSM_CUDA(d_aux.alloc(2 * (size_t)n, s));
     MSM_CUDA(d_err.alloc(1, s));
     MSM_CUDA(cudaMemsetAsync(d_err.p, 0, sizeof(int), s));
     TripletArgs a;
@@ -321,7 +324,7 @@ static msmgpu_status triplet_run(msmgpu_costfn* c, int ntrip, const int32_t* tri
     a.src_xyz = c->src_xyz.p; a.prow = c->prow.p; a.pmem = c->pmem.p; a.src_feat = c->src_feat.p; a.ref_feat = c->ref_feat.p;
     a.cfw = c->cfw.p; a.absw = c->absw.p;
     a.lambda = prm->lambda; a.mu = prm->shear_modulus; a.kappa = prm->bulk_modulus; a.k_exp = prm->k_exponent; a.rexp = prm->exponent;
-    a.out = d_out.p; a.err = d_err.p;
+    a.out = d_out.p; a.aux = d_aux.p; a.err = d_err.p;
     const size_t slice = ((size_t)a.max_patch * (4 * sizeof(double) + 3 * sizeof(int)) + 15) & ~(size_t)15;
     const size_t smem = slice * kTripWarps;
     if (smem > 200 * 1024) return fail(MSMGPU_ERR_CAPACITY, "costfn_triplet: patch too large for shared memory");
@@ -334,10 +337,22 @@ static msmgpu_status triplet_run(msmgpu_costfn* c, int ntrip, const int32_t* tri
         default: MSM_TRY(launch_triplet_g<1>(a, smem, s)); break;
     }
     int h_err = 0;
+    std::vector<double> aux(2 * (size_t)n);
     MSM_CUDA(cudaMemcpyAsync(out, d_out.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    MSM_CUDA(cudaMemcpyAsync(aux.data(), d_aux.p, aux.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
     MSM_CUDA(cudaMemcpyAsync(&h_err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     MSM_CUDA(cudaStreamSynchronize(s));
     if (h_err) return status_to_error(MSMGPU_ERR_NO_TRIANGLE);
+    // reg_tools.cpp:596-597 and DiscreteCostFunction.cpp:187 with the host libm (this translation unit is built with -ffp-contract=off)
+    const double MU = prm->shear_modulus, KAPPA = prm->bulk_modulus, k_exp = prm->k_exponent, rexp = prm->exponent, lambda = prm->lambda;
+#pragma omp parallel for schedule(static) if (n > 4096)
+    for (int r = 0; r < n; ++r) {
+        const double R = aux[2 * (size_t)r], J = aux[2 * (size_t)r + 1];
+        if (R != R) continue;
+        const double Rshared = std::pow(R, k_exp), Jshared = std::pow(J, k_exp);
+        const double W = 0.5 * (MU * (Rshared + 1.0 / Rshared - 2) + KAPPA * (Jshared + 1.0 / Jshared - 2));
+        out[r] = out[r] + lambda * std::pow(W, rexp);
+    }
     return MSMGPU_OK;
 }
 

@@ -70,6 +70,8 @@ def main():
                     help="threads of the CPU run the labels are compared with. The reference is only deterministic single-threaded: "
                          "get_adaptive_barycentric_weights accumulates `correction[]` in an omp loop without atomics (resampler.cpp:99-118)")
     ap.add_argument("--skip-timing-cpu", action="store_true", help="do not run the all-threads CPU arm (timing)")
+    ap.add_argument("--skip-parity-cpu", action="store_true", help="do not run the single-thread CPU arm (labels are then only compared with the "
+                                                                     "all-threads run, which the reference's own data race can perturb)")
     ap.add_argument("--gpu-runs", type=int, default=1)
     ap.add_argument("--disable", default="", help="MSMGPU_DISABLE value for the GPU run (cost, resample): A/B isolation of the hooks")
     ap.add_argument("--verify", action="store_true", help="MSMGPU_VERIFY=1: the hooks also run the reference CPU code in-process and compare")
@@ -101,7 +103,7 @@ def main():
         tm = parse_trace(os.path.join(work, "trace_cpu_mt.txt"))
         lab = [(x["labels"], y["labels"]) for x, y in zip(tm, tg) if "labels" in x and "labels" in y]
         res["label_mismatch_vs_multithreaded_cpu"] = [int((x != y).sum()) if len(x) == len(y) else -1 for x, y in lab]
-    if not a.skip_cpu:
+    if not a.skip_cpu and not a.skip_parity_cpu:
         conf1 = conf + "_parity"
         with open(conf) as f:
             lines = [ln for ln in f.read().splitlines() if not ln.startswith("--numthreads")]
