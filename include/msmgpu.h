@@ -159,6 +159,14 @@ msmgpu_status msmgpu_surface_resample(msmgpu_mesh* sph_mesh, const double* anat_
 msmgpu_status msmgpu_nn_resample(msmgpu_mesh* in_mesh, int n, const double* low_xyz, int D, const double* feat_in, double* feat_out);
 
 /* replaces: estimate_rotation_matrix (msm-newresampler/src/point.cpp:97-152) for n (ci,index) pairs -> [n][9] row-major */
+/* replaces: the O(V^2) neighbourhood search of newresampler::smooth_data (resampler.cpp:186-200), the IEEE-only part of the Gaussian
+ * smoothing. For target i: ref = unit(low_xyz[closest[i]]) (closest = get_closest_vertex_ID of the target in `orig`); the list holds,
+ * in ascending n, every vertex n with unit(low_xyz[n]) . ref >= cos_ang, and chords[] = |ref - unit(low_xyz[n])|. CSR output:
+ * rowptr[n+1] is always written; members / chords only when non-NULL and cap >= rowptr[n] (call once with NULL to size them).
+ * The Gaussian weights (asin, exp: resampler.cpp:204-205) are the caller's, on the host libm. */
+msmgpu_status msmgpu_smooth_neighbourhoods(msmgpu_ctx* ctx, int n, const double* low_xyz, const int32_t* closest, double cos_ang,
+                                           int32_t* rowptr, int64_t cap, int32_t* members, double* chords);
+
 msmgpu_status msmgpu_rotation_matrices(msmgpu_ctx* ctx, int n, const double* ci, const double* index, double* R);
 
 /* ---- discrete-optimisation cost evaluation (msm-newmeshreg/src/DiscreteCostFunction.{h,cpp}) ---- */

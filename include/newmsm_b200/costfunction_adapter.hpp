@@ -134,13 +134,16 @@ class GpuCostFunction : public Base {
     std::mutex mu_;
     std::atomic<bool> unary_ready_{false};
 
-    // triplet caches (double-buffered: readers keep using the old table while a new phase is being computed)
+    // triplet caches. Readers (OpenMP workers inside Fusion::optimize) only do an acquire-load of a raw pointer; a table is
+    // never modified after publication and retired tables stay alive until the next initialize() (a serial point), so a
+    // reader that still holds the previous pointer keeps reading valid memory.
     struct Table {
         std::vector<int32_t> snap;    // labeling snapshot the table was computed for
         std::vector<double> val;      // [T] (current labels) or [T][8] (Fusion's combinations)
         int label = -1;
     };
-    std::shared_ptr<Table> cur_, fus_;
+    std::atomic<const Table*> cur_{nullptr}, fus_{nullptr};
+    std::vector<std::unique_ptr<Table>> tables_;
 
     void release() {
         if (d_cf_) msmgpu_costfn_destroy(d_cf_);
@@ -199,11 +202,12 @@ class GpuCostFunction : public Base {
         detail::timers().unary_tables++;
     }
 
-    std::shared_ptr<Table> make_table(int label) {
+    const Table* make_table(int label) {
         const double t0 = omp_get_wtime();
         ensure_iter_arrays();
         const int T = this->m_num_triplets, N = this->m_num_nodes;
-        auto tb = std::make_shared<Table>();
+        tables_.emplace_back(new Table());
+        Table* tb = tables_.back().get();
         const int* lab = model_->getLabeling();
         tb->snap.assign(lab, lab + N);
         tb->label = label;
@@ -237,7 +241,7 @@ class GpuCostFunction : public Base {
         return tb;
     }
 
-    static bool fresh(const std::shared_ptr<Table>& tb, const int* lab, int a, int b, int c, int label) {
+    static bool fresh(const Table* tb, const int* lab, int a, int b, int c, int label) {
         return tb && tb->label == label && tb->snap[a] == lab[a] && tb->snap[b] == lab[b] && tb->snap[c] == lab[c];
     }
 
@@ -249,8 +253,9 @@ public:
         Base::initialize(numNodes, numLabels, numPairs, numTriplets);
         iter_arrays_ready_ = false;
         unary_ready_.store(false);
-        std::atomic_store(&cur_, std::shared_ptr<Table>());
-        std::atomic_store(&fus_, std::shared_ptr<Table>());
+        cur_.store(nullptr);
+        fus_.store(nullptr);
+        tables_.clear();
     }
 
     // once per discrete iteration (DiscreteModel.cpp:254): patches of the current source / control-point grid
@@ -325,31 +330,31 @@ public:
         const int a = this->_triplets[3 * triplet], b = this->_triplets[3 * triplet + 1], c = this->_triplets[3 * triplet + 2];
         const bool da = labelA != lab[a], db = labelB != lab[b], dc = labelC != lab[c];
         if (!da && !db && !dc) {
-            std::shared_ptr<Table> tb = std::atomic_load(&cur_);
+            const Table* tb = cur_.load(std::memory_order_acquire);
             if (!fresh(tb, lab, a, b, c, -1)) {
                 std::lock_guard<std::mutex> g(mu_);
-                tb = std::atomic_load(&cur_);
-                if (!fresh(tb, lab, a, b, c, -1)) { tb = make_table(-1); std::atomic_store(&cur_, tb); }
+                tb = cur_.load(std::memory_order_acquire);
+                if (!fresh(tb, lab, a, b, c, -1)) { tb = make_table(-1); cur_.store(tb, std::memory_order_release); }
             }
             return tb->val[triplet];
         }
         const int label = da ? labelA : (db ? labelB : labelC);
         if ((da && labelA != label) || (db && labelB != label) || (dc && labelC != label)) {
             // not one of Fusion's combinations (two different non-current labels): evaluate this request on its own
-            ensure_iter_arrays();
             const msmgpu_reg_params prm = reg_params();
             const int32_t rt = triplet, la = labelA, lb = labelB, lc = labelC;
             double out = 0;
             std::lock_guard<std::mutex> g(mu_);
+            ensure_iter_arrays();
             detail::check(msmgpu_costfn_triplet_costs(d_cf_, this->m_num_triplets, trip_.data(), this->m_num_labels, labels_.data(), rot_.data(), orig_cp_.data(),
                                                       &prm, 1, &rt, &la, &lb, &lc, &out));
             return out;
         }
-        std::shared_ptr<Table> tb = std::atomic_load(&fus_);
+        const Table* tb = fus_.load(std::memory_order_acquire);
         if (!fresh(tb, lab, a, b, c, label)) {
             std::lock_guard<std::mutex> g(mu_);
-            tb = std::atomic_load(&fus_);
-            if (!fresh(tb, lab, a, b, c, label)) { tb = make_table(label); std::atomic_store(&fus_, tb); }
+            tb = fus_.load(std::memory_order_acquire);
+            if (!fresh(tb, lab, a, b, c, label)) { tb = make_table(label); fus_.store(tb, std::memory_order_release); }
         }
         return tb->val[8 * (size_t)triplet + ((da ? 4 : 0) | (db ? 2 : 0) | (dc ? 1 : 0))];
     }

@@ -127,6 +127,16 @@ int main() {
                    "(those stale areas do change the result, i.e. the case is not vacuous)");
         }
 
+        // smooth_data (resampler.cpp:169): device neighbourhood scan + host-libm Gaussian weights
+        {
+            Mesh a = in, b = in;
+            EXPECT(same_pvalues(smooth_data(a, a, 4.0, 1), newresampler_gpu::smooth_data(b, b, 4.0, 1)), "smooth_data (sigma 4, D = 3): identical values");
+            Mesh c = low, d = low;
+            c.initialize_pvalues(1); d.initialize_pvalues(1);
+            for (int v = 0; v < c.nvertices(); ++v) { c.set_pvalue(v, std::sin(0.07 * c.get_coord(v).Z), 0); d.set_pvalue(v, std::sin(0.07 * d.get_coord(v).Z), 0); }
+            EXPECT(same_pvalues(smooth_data(c, c, 2.0, 1), newresampler_gpu::smooth_data(d, d, 2.0, 1)), "smooth_data (sigma 2, rotated ico4): identical values");
+        }
+
         // error behaviour: the reference's exception with the reference's message (octree.cpp:158)
         bool threw = false;
         try { og.get_closest_triangle(Point(0, 0, 150)); } catch (MeshException& e) { threw = std::strstr(e.what(), "bounding box") != nullptr; }

@@ -35,6 +35,7 @@ using newresampler::Mesh;
 #define SYM_METRIC "_ZN12newresampler15metric_resampleERKNS_4MeshES2_iSt10shared_ptrIS0_E"
 #define SYM_WARP "_ZN12newresampler19sphere_project_warpERNS_4MeshERKS0_S3_i"
 #define SYM_ICOSA "_ZN12newresampler20make_mesh_from_icosaEi"
+#define SYM_SMOOTH "_ZN12newresampler11smooth_dataERNS_4MeshERKS0_diSt10shared_ptrIS0_E"
 #define SYM_FEATINIT "_ZN10newmeshreg12featurespace10initialiseEiRSt6vectorIN12newresampler4MeshESaIS3_EEb"
 
 #define SYM_UNFOLD "_ZN10newmeshreg6unfoldERN12newresampler4MeshEb"
@@ -89,6 +90,8 @@ void wrap_sphere_project_warp(Mesh& sphere, const Mesh& from, const Mesh& to, in
 
 Mesh real_make_mesh_from_icosa(int n) asm("__real_" SYM_ICOSA);
 Mesh wrap_make_mesh_from_icosa(int n) asm("__wrap_" SYM_ICOSA);
+Mesh real_smooth_data(Mesh& orig, const Mesh& sphLow, double sigma, int nthreads, std::shared_ptr<Mesh> EXCL) asm("__real_" SYM_SMOOTH);
+Mesh wrap_smooth_data(Mesh& orig, const Mesh& sphLow, double sigma, int nthreads, std::shared_ptr<Mesh> EXCL) asm("__wrap_" SYM_SMOOTH);
 Mesh real_featurespace_initialise(newmeshreg::featurespace* self, int ico, std::vector<Mesh>& IN, bool exclude) asm("__real_" SYM_FEATINIT);
 Mesh wrap_featurespace_initialise(newmeshreg::featurespace* self, int ico, std::vector<Mesh>& IN, bool exclude) asm("__wrap_" SYM_FEATINIT);
 
@@ -100,19 +103,19 @@ bool disabled(const char* what) {
 }
 
 struct Stats {
-    double resample = 0, warp = 0, icosa = 0, featinit = 0, optimise = 0;
-    long n_resample = 0, n_warp = 0, n_icosa = 0;
+    double resample = 0, warp = 0, icosa = 0, featinit = 0, optimise = 0, smooth = 0;
+    long n_resample = 0, n_warp = 0, n_icosa = 0, n_smooth = 0;
     const double t_start = omp_get_wtime();
     ~Stats() {
         if (!std::getenv("MSMGPU_TIMING")) return;
         const auto& t = newmeshreg_gpu::detail::timers();
         std::fprintf(stderr,
                      "[msmgpu] get_source_data %.3f s | unary tables %ld in %.3f s | triplet batches %ld in %.3f s | pairwise tables %.3f s | "
-                     "metric_resample %ld in %.3f s | sphere_project_warp %ld in %.3f s | make_mesh_from_icosa %ld in %.3f s | "
+                     "metric_resample %ld in %.3f s | sphere_project_warp %ld in %.3f s | make_mesh_from_icosa %ld in %.3f s | smooth_data %ld in %.3f s | "
                      "featurespace::initialise %.3f s (incl. its resamples) | optimiser phases (solver + cost calls) %.3f s | process %.3f s | "
                      "kernel launches %llu\n",
                      t.source, t.unary_tables, t.unary, t.triplet_batches, t.triplet, t.pairwise, n_resample, resample, n_warp, warp, n_icosa, icosa,
-                     featinit, optimise, omp_get_wtime() - t_start, msmgpu_launch_count());
+                     n_smooth, smooth, featinit, optimise, omp_get_wtime() - t_start, msmgpu_launch_count());
     }
 } stats;
 
@@ -193,6 +196,29 @@ Mesh wrap_make_mesh_from_icosa(int n) {
     stats.icosa += omp_get_wtime() - t0;
     stats.n_icosa++;
     return m;
+}
+
+// resampler.cpp:169-230 -> device neighbourhood scan + host-libm weights (resampler adapter)
+Mesh wrap_smooth_data(Mesh& orig, const Mesh& sphLow, double sigma, int nthreads, std::shared_ptr<Mesh> EXCL) {
+    if (EXCL || disabled("smooth")) return real_smooth_data(orig, sphLow, sigma, nthreads, EXCL);
+    Mesh keep;
+    if (verify()) keep = orig;
+    const double t0 = omp_get_wtime();
+    Mesh out = newresampler_gpu::smooth_data(orig, sphLow, sigma, nthreads, EXCL);
+    stats.smooth += omp_get_wtime() - t0;
+    stats.n_smooth++;
+    if (verify()) {
+        const Mesh ref = real_smooth_data(keep, sphLow, sigma, nthreads, EXCL);
+        long bad = 0;
+        for (int d = 0; d < ref.get_dimension(); ++d)
+            for (int v = 0; v < ref.nvertices(); ++v) {
+                const double a = ref.get_pvalue(v, d), b = out.get_pvalue(v, d);
+                bad += std::memcmp(&a, &b, sizeof(double)) != 0;
+            }
+        std::fprintf(stderr, "[msmgpu verify] smooth_data #%ld  %d vertices, D=%d, sigma %g: %ld values differ\n", stats.n_smooth, ref.nvertices(),
+                     ref.get_dimension(), sigma, bad);
+    }
+    return out;
 }
 
 Mesh wrap_featurespace_initialise(newmeshreg::featurespace* self, int ico, std::vector<Mesh>& IN, bool exclude) {   // timing only

@@ -1,0 +1,95 @@
+// Neighbourhood search of newresampler::smooth_data (msm-newresampler/src/resampler.cpp:169-230) on the device.
+//
+// For every target i the reference scans ALL vertices n of sphLow (O(V^2), 1.7e9 pair tests at ico6) and keeps those with
+//     unit(sphLow[n]) . ref_i >= cos(ang),   ref_i = unit(sphLow[closest_vertex_i]),   ang = 4 asin(sigma / 2R)
+// together with the chord |ref_i - unit(sphLow[n])| (resampler.cpp:186-200). Both are +, -, *, /, sqrt on doubles in a fixed order, so
+// they are bit-identical on the device (--fmad=false); the Gaussian weights that follow need asin / exp and stay on the host libm,
+// on the short lists only (DESIGN.md §4.3 policy). One warp per target: 32 candidates per step, ballot-ordered output = ascending n.
+#include "common.cuh"
+#include "query.cuh"
+
+namespace msm {
+
+__global__ void k_unit_points(int n, const double* __restrict__ xyz, double* __restrict__ unit) {   // Point::normalize, point.cpp:26-34
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const V3 p = vnormalized(load_pt(xyz, i));
+    unit[3 * (size_t)i] = p.x; unit[3 * (size_t)i + 1] = p.y; unit[3 * (size_t)i + 2] = p.z;
+}
+
+constexpr int kSmoothWarps = 8;
+
+// FILL = false: count[i] = list length. FILL = true: members / chords written at rowptr[i] in ascending n.
+template <bool FILL>
+__global__ void __launch_bounds__(kSmoothWarps * 32) k_smooth_neighbours(int n, const double* __restrict__ unit, const int* __restrict__ closest,
+                                                                         double cos_ang, int* __restrict__ count, const int* __restrict__ rowptr,
+                                                                         int* __restrict__ members, double* __restrict__ chords) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * kSmoothWarps + warp;
+    if (i >= n) return;
+    const V3 ref = load_pt(unit, closest[i]);
+    int total = 0;
+    int base = FILL ? rowptr[i] : 0;
+    for (int n0 = 0; n0 < n; n0 += 32) {
+        const int c = n0 + lane;
+        bool in = false;
+        V3 a{0, 0, 0};
+        if (c < n) {
+            a = load_pt(unit, c);
+            in = vdot(a, ref) >= cos_ang;                       // (actual | ref) >= cos(ang)
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, in);
+        if (FILL) {
+            if (in) {
+                const int pos = base + __popc(m & ((1u << lane) - 1u));
+                members[pos] = c;
+                chords[pos] = vnorm(vsub(ref, a));              // (ref - actual).norm()
+            }
+            base += __popc(m);
+        } else {
+            total += __popc(m);
+        }
+    }
+    if (!FILL && lane == 0) count[i] = total;
+}
+
+}  // namespace msm
+
+using namespace msm;
+
+extern "C" msmgpu_status msmgpu_smooth_neighbourhoods(msmgpu_ctx* ctx, int n, const double* low_xyz, const int32_t* closest, double cos_ang,
+                                                      int32_t* rowptr, int64_t cap, int32_t* members, double* chords) {
+    if (!ctx || n <= 0 || !low_xyz || !closest || !rowptr) return fail(MSMGPU_ERR_INVALID, "smooth_neighbourhoods: bad arguments");
+    MSM_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    DevBuf<double> d_xyz, d_unit, d_ch;
+    DevBuf<int> d_closest, d_cnt, d_mem;
+    MSM_CUDA(d_xyz.alloc(3 * (size_t)n, s));
+    MSM_CUDA(d_unit.alloc(3 * (size_t)n, s));
+    MSM_CUDA(d_closest.alloc((size_t)n, s));
+    MSM_CUDA(d_cnt.alloc((size_t)n + 1, s));
+    MSM_CUDA(cudaMemcpyAsync(d_xyz.p, low_xyz, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+    MSM_CUDA(cudaMemcpyAsync(d_closest.p, closest, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s));
+    k_unit_points<<<(n + 255) / 256, 256, 0, s>>>(n, d_xyz.p, d_unit.p);
+    MSM_LAUNCH_CHECK();
+    const unsigned grid = (unsigned)((n + kSmoothWarps - 1) / kSmoothWarps);
+    k_smooth_neighbours<false><<<grid, kSmoothWarps * 32, 0, s>>>(n, d_unit.p, d_closest.p, cos_ang, d_cnt.p, nullptr, nullptr, nullptr);
+    MSM_LAUNCH_CHECK();
+    std::vector<int> cnt((size_t)n);
+    MSM_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    MSM_CUDA(cudaStreamSynchronize(s));
+    int64_t total = 0;
+    for (int i = 0; i < n; ++i) { rowptr[i] = (int32_t)total; total += cnt[i]; }
+    if (total > 0x7fffffffll) return fail(MSMGPU_ERR_CAPACITY, "smooth_neighbourhoods: more than 2^31 neighbour pairs");
+    rowptr[n] = (int32_t)total;
+    if (!members || !chords || cap < total) return MSMGPU_OK;   // sizing call: rowptr[n] tells the caller what to allocate
+    MSM_CUDA(d_mem.alloc((size_t)total, s));
+    MSM_CUDA(d_ch.alloc((size_t)total, s));
+    MSM_CUDA(cudaMemcpyAsync(d_cnt.p, rowptr, ((size_t)n + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
+    k_smooth_neighbours<true><<<grid, kSmoothWarps * 32, 0, s>>>(n, d_unit.p, d_closest.p, cos_ang, nullptr, d_cnt.p, d_mem.p, d_ch.p);
+    MSM_LAUNCH_CHECK();
+    MSM_CUDA(cudaMemcpyAsync(members, d_mem.p, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, s));
+    MSM_CUDA(cudaMemcpyAsync(chords, d_ch.p, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, s));
+    MSM_CUDA(cudaStreamSynchronize(s));
+    return MSMGPU_OK;
+}
