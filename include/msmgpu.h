@@ -251,6 +251,18 @@ msmgpu_status msmgpu_group_pair_costs(msmgpu_group* g, int P, const int32_t* pai
  * (cur,cur), (cur,label), (label,cur), (label,label) */
 msmgpu_status msmgpu_group_pair_batch(msmgpu_group* g, int P, const int32_t* pairs, const int32_t* labeling, int label, double* out);
 
+/* replaces: DiscreteGroupCostFunction::computeTripletCost (msm-newmeshreg/src/DiscreteGroupCostFunction.cpp:26-52): the strain energy
+ * of a control-grid triangle of one subject under three candidate labels, `subcorr * lambda * W^rexp` with subcorr = 0.1 * S
+ * (DiscreteGroupCostFunction.h:45); a folded triangle costs FOLDING = 1e7, a NaN energy FIX_NAN = 1e7 when fixnan != 0.
+ * cp_xyz / orig_xyz / rotations are the per-subject control grids concatenated ([S*ncp]), triplets hold global node ids
+ * (DiscreteGroupModel.cpp:57-74). _costs: request list; _batch: Fusion's 8 combinations per triplet (Fusion.h:181-196), out[T][8]. */
+msmgpu_status msmgpu_group_triplet_costs(msmgpu_ctx* ctx, int n_nodes, const double* cp_xyz, const double* orig_xyz, const double* rotations, int L,
+                                         const double* labels, int ntrip, const int32_t* triplets, const msmgpu_reg_params* prm, double subcorr, int fixnan,
+                                         int n, const int32_t* req_triplet, const int32_t* req_la, const int32_t* req_lb, const int32_t* req_lc, double* out);
+msmgpu_status msmgpu_group_triplet_batch(msmgpu_ctx* ctx, int n_nodes, const double* cp_xyz, const double* orig_xyz, const double* rotations, int L,
+                                         const double* labels, int ntrip, const int32_t* triplets, const msmgpu_reg_params* prm, double subcorr, int fixnan,
+                                         const int32_t* labeling, int label, double* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -98,6 +98,8 @@ _SIGNATURES = {
     "msmgpu_costfn_set_cpgrid_ho": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp]),
     "msmgpu_costfn_triplet_costs": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "msmgpu_costfn_triplet_batch": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "msmgpu_group_triplet_costs": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _d, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "msmgpu_group_triplet_batch": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _d, _i, _vp, _i, _vp]),
 }
 
 

@@ -191,6 +191,25 @@ __device__ __forceinline__ double rec_distance(const V3& pt, const TriRec* __res
     return rec_boundary_distance(mP, v1, v2, v3, g.y, h.x, h.y);
 }
 
+// The two halves of rec_distance, for callers that first collect the containing triangles of all their candidates and only then
+// evaluate the (expensive: 6 sqrt, 3 div) boundary distance of those few: same expressions, same bits.
+__device__ __forceinline__ bool rec_inside(const V3& pt, const TriRec* __restrict__ rp) {
+    const double2* q = reinterpret_cast<const double2*>(rp);
+    const double2 a = __ldg(q + 0), b = __ldg(q + 1), c = __ldg(q + 2), d4 = __ldg(q + 3), e = __ldg(q + 4);
+    const double2 f = __ldg(q + 5), g = __ldg(q + 6);
+    const V3 v1{a.x, a.y, b.x}, v2{b.y, c.x, c.y}, v3{d4.x, d4.y, e.x};
+    const V3 mP = rec_project(pt, V3{e.y, f.x, f.y}, g.x);
+    return in_triangle(mP, v1, v2, v3);
+}
+__device__ __forceinline__ double rec_distance_inside(const V3& pt, const TriRec* __restrict__ rp) {
+    const double2* q = reinterpret_cast<const double2*>(rp);
+    const double2 a = __ldg(q + 0), b = __ldg(q + 1), c = __ldg(q + 2), d4 = __ldg(q + 3), e = __ldg(q + 4);
+    const double2 f = __ldg(q + 5), g = __ldg(q + 6), h = __ldg(q + 7);
+    const V3 v1{a.x, a.y, b.x}, v2{b.y, c.x, c.y}, v3{d4.x, d4.y, e.x};
+    const V3 mP = rec_project(pt, V3{e.y, f.x, f.y}, g.x);
+    return rec_boundary_distance(mP, v1, v2, v3, g.y, h.x, h.y);
+}
+
 // ------------------------------------------------------------------------------------------
 // Conservative cull record per triangle: a sphere (C, r) that contains every point the reference's
 // point_in_triangle (point.cpp:36-44) can accept for this triangle, so a query whose line
@@ -231,6 +250,13 @@ __host__ __device__ __forceinline__ void make_cull(const V3& a, const V3& b, con
 }
 
 // keep the triangle iff the line through the origin and pt may touch the sphere:  |C x pt|^2 <= r^2 |pt|^2
+__device__ __forceinline__ bool cull_keep_loaded(const double2& c01, const double2& c23, const V3& pt, double pp) {
+    const double x = __fma_rn(c01.y, pt.z, -(c23.x * pt.y));
+    const double y = __fma_rn(c23.x, pt.x, -(c01.x * pt.z));
+    const double z = __fma_rn(c01.x, pt.y, -(c01.y * pt.x));
+    const double d2 = __fma_rn(x, x, __fma_rn(y, y, z * z));
+    return !(d2 > c23.y * pp);     // written so that NaN keeps the triangle
+}
 __device__ __forceinline__ bool cull_keep(const double* __restrict__ cull4, const V3& pt, double pp) {
     const double2 c01 = __ldg(reinterpret_cast<const double2*>(cull4));
     const double2 c23 = __ldg(reinterpret_cast<const double2*>(cull4) + 1);

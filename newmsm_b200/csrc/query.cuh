@@ -59,16 +59,45 @@ __device__ __forceinline__ int nearest_triangle(const TreeView& T, const V3& pt,
         unsigned long long keep = 0ull;
         const int mine = (nd.z - gl + G - 1) / G;             // candidates owned by this lane (may be <= 0)
         const int fast = mine < 64 ? mine : 64;
-        for (int j = 0; j < fast; ++j) {
-            const int t = __ldg(list + gl + j * G);
-            if (cull_keep(T.cull + 4 * (size_t)t, pt, pp)) keep |= 1ull << j;
+        // the scan is a chain of dependent loads (id -> cull sphere): batches of 4 candidates, with the ids of the NEXT batch
+        // requested before the spheres of the current one are tested, so one load latency per batch is exposed instead of two
+        {
+            int tn[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) tn[u] = u < fast ? __ldg(list + gl + u * G) : 0;
+            for (int j0 = 0; j0 < fast; j0 += 4) {
+                int t[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) t[u] = tn[u];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) tn[u] = j0 + 4 + u < fast ? __ldg(list + gl + (j0 + 4 + u) * G) : 0;
+                double2 c01[4], c23[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const double2* cp = reinterpret_cast<const double2*>(T.cull + 4 * (size_t)t[u]);
+                    c01[u] = __ldg(cp);
+                    c23[u] = __ldg(cp + 1);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (j0 + u < fast && cull_keep_loaded(c01[u], c23[u], pt, pp)) keep |= 1ull << (j0 + u);
+            }
         }
+        // (2a) containment (projection + 3 same-side tests) for the survivors; (2b) the boundary distance only for the triangles
+        // that contain the projection (one, rarely two or three on an edge / at a vertex). Splitting the loop keeps the lanes of a
+        // warp converged in the expensive part instead of dragging ~6 active lanes through it once per survivor.
+        unsigned long long inside = 0ull;
         while (keep) {
             const int j = __ffsll((long long)keep) - 1;
             keep &= keep - 1;
+            if (rec_inside(pt, T.rec + __ldg(list + gl + j * G))) inside |= 1ull << j;
+        }
+        while (inside) {
+            const int j = __ffsll((long long)inside) - 1;
+            inside &= inside - 1;
             const int i = gl + j * G;
             const int t = __ldg(list + i);
-            const double d = rec_distance(pt, T.rec + t);
+            const double d = rec_distance_inside(pt, T.rec + t);
             if (d > kNotInTriangle && d < best_d) { best_d = d; best_pos = i; best_t = t; }
         }
         for (int j = 64; j < mine; ++j) {                     // oversized leaves (split refused, octree.cpp:102): no mask

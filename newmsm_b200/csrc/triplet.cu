@@ -146,6 +146,7 @@ struct TripletArgs {
     const double* src_feat; const double* ref_feat; const double* cfw; const double* absw;
     double lambda, mu, kappa, k_exp, rexp;
     double* aux;              // [n][2]: R, J of the strain energy (R = NaN: out[r] is already final)
+    double fold_value;        // cost of a folded triangle: FOLDING * lambda (cpp:152) or FOLDING (DiscreteGroupCostFunction.cpp:40)
     double* out;              // [n]
     int* err;
 };
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(kTripWarps * 32) k_triplet_costs(TripletArgs a
     }
     // only estimate the cost if it does not cause folding (cpp:152)
     if (vdot(tri_normal(def[0], def[1], def[2]), tri_normal(cur[0], cur[1], cur[2])) < 0.0) {
-        if (lane == 0) { a.out[r] = 1e7 * a.lambda; a.aux[2 * (size_t)r] = nan(""); a.aux[2 * (size_t)r + 1] = 0.0; }   // final as is
+        if (lane == 0) { a.out[r] = a.fold_value; a.aux[2 * (size_t)r] = nan(""); a.aux[2 * (size_t)r + 1] = 0.0; }   // final as is
         return;
     }
     double likelihood = 0.0;
@@ -324,7 +325,7 @@ static msmgpu_status triplet_run(msmgpu_costfn* c, int ntrip, const int32_t* tri
     a.src_xyz = c->src_xyz.p; a.prow = c->prow.p; a.pmem = c->pmem.p; a.src_feat = c->src_feat.p; a.ref_feat = c->ref_feat.p;
     a.cfw = c->cfw.p; a.absw = c->absw.p;
     a.lambda = prm->lambda; a.mu = prm->shear_modulus; a.kappa = prm->bulk_modulus; a.k_exp = prm->k_exponent; a.rexp = prm->exponent;
-    a.out = d_out.p; a.aux = d_aux.p; a.err = d_err.p;
+    a.out = d_out.p; a.aux = d_aux.p; a.err = d_err.p; a.fold_value = 1e7 * prm->lambda;
     const size_t slice = ((size_t)a.max_patch * (4 * sizeof(double) + 3 * sizeof(int)) + 15) & ~(size_t)15;
     const size_t smem = slice * kTripWarps;
     if (smem > 200 * 1024) return fail(MSMGPU_ERR_CAPACITY, "costfn_triplet: patch too large for shared memory");
@@ -356,11 +357,82 @@ static msmgpu_status triplet_run(msmgpu_costfn* c, int ntrip, const int32_t* tri
     return MSMGPU_OK;
 }
 
+// gMSM triplet term (DiscreteGroupCostFunction.cpp:26-52): the same strain energy on the per-subject control grids, no likelihood,
+// scaled by subcorr = 0.1 * S; a folded triangle costs FOLDING (not FOLDING * lambda), a NaN energy costs FIX_NAN when --fixnan.
+// Node ids in `triplets` are global (subject * ncp + vertex), so the per-subject grids are simply concatenated.
+static msmgpu_status group_triplet_run(msmgpu_ctx* ctx, int n_nodes, const double* cp_xyz, const double* orig_xyz, const double* rotations, int L,
+                                       const double* labels, int ntrip, const int32_t* triplets, const msmgpu_reg_params* prm, double subcorr,
+                                       int fixnan, int n, const int32_t* req_t, const int32_t* req_la, const int32_t* req_lb, const int32_t* req_lc,
+                                       const int32_t* labeling, int label, double* out) {
+    if (!ctx || n_nodes <= 0 || !cp_xyz || !orig_xyz || !rotations || L <= 0 || !labels || ntrip <= 0 || !triplets || !prm || n <= 0 || !out)
+        return fail(MSMGPU_ERR_INVALID, "group_triplet: bad arguments");
+    MSM_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    DevBuf<int> d_trip, d_rt, d_la, d_lb, d_lc, d_labeling, d_err;
+    DevBuf<double> d_labels, d_rot, d_orig, d_cp, d_out, d_aux;
+    MSM_TRY(up(d_trip, triplets, 3 * (size_t)ntrip, s));
+    MSM_TRY(up(d_labels, labels, 3 * (size_t)L, s));
+    MSM_TRY(up(d_rot, rotations, 9 * (size_t)n_nodes, s));
+    MSM_TRY(up(d_orig, orig_xyz, 3 * (size_t)n_nodes, s));
+    MSM_TRY(up(d_cp, cp_xyz, 3 * (size_t)n_nodes, s));
+    if (req_t) {
+        MSM_TRY(up(d_rt, req_t, (size_t)n, s));
+        MSM_TRY(up(d_la, req_la, (size_t)n, s));
+        MSM_TRY(up(d_lb, req_lb, (size_t)n, s));
+        MSM_TRY(up(d_lc, req_lc, (size_t)n, s));
+    } else {
+        MSM_TRY(up(d_labeling, labeling, (size_t)n_nodes, s));
+    }
+    MSM_CUDA(d_out.alloc((size_t)n, s));
+    MSM_CUDA(d_aux.alloc(2 * (size_t)n, s));
+    MSM_CUDA(d_err.alloc(1, s));
+    MSM_CUDA(cudaMemsetAsync(d_err.p, 0, sizeof(int), s));
+    TripletArgs a{};
+    a.kind = MSMGPU_COST_UNIVARIATE; a.simmeasure = 2; a.ncp = n_nodes; a.n = n; a.max_patch = 1;
+    a.triplets = d_trip.p; a.req_t = req_t ? d_rt.p : nullptr; a.req_la = d_la.p; a.req_lb = d_lb.p; a.req_lc = d_lc.p;
+    a.labeling = d_labeling.p; a.label = label; a.labels = d_labels.p; a.rot = d_rot.p; a.cp_xyz = d_cp.p; a.orig_xyz = d_orig.p;
+    a.lambda = prm->lambda; a.mu = prm->shear_modulus; a.kappa = prm->bulk_modulus; a.k_exp = prm->k_exponent; a.rexp = prm->exponent;
+    a.out = d_out.p; a.aux = d_aux.p; a.err = d_err.p; a.fold_value = 1e7;
+    const size_t smem = (((size_t)(4 * sizeof(double) + 3 * sizeof(int)) + 15) & ~(size_t)15) * kTripWarps;
+    MSM_TRY(launch_triplet_g<1>(a, smem, s));
+    std::vector<double> aux(2 * (size_t)n);
+    MSM_CUDA(cudaMemcpyAsync(out, d_out.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    MSM_CUDA(cudaMemcpyAsync(aux.data(), d_aux.p, aux.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    MSM_CUDA(cudaStreamSynchronize(s));
+    const double MU = prm->shear_modulus, KAPPA = prm->bulk_modulus, k_exp = prm->k_exponent, rexp = prm->exponent, lambda = prm->lambda;
+#pragma omp parallel for schedule(static) if (n > 4096)
+    for (int r = 0; r < n; ++r) {
+        const double R = aux[2 * (size_t)r], J = aux[2 * (size_t)r + 1];
+        if (R != R) continue;                                   // folded: FOLDING, already written
+        const double Rshared = std::pow(R, k_exp), Jshared = std::pow(J, k_exp);
+        const double W = 0.5 * (MU * (Rshared + 1.0 / Rshared - 2) + KAPPA * (Jshared + 1.0 / Jshared - 2));
+        if (fixnan && W != W) { out[r] = 1e7; continue; }       // FIX_NAN
+        out[r] = subcorr * lambda * std::pow(W, rexp);
+    }
+    return MSMGPU_OK;
+}
+
 } // namespace msm
 
 using namespace msm;
 
 extern "C" {
+
+msmgpu_status msmgpu_group_triplet_costs(msmgpu_ctx* ctx, int n_nodes, const double* cp_xyz, const double* orig_xyz, const double* rotations, int L,
+                                         const double* labels, int ntrip, const int32_t* triplets, const msmgpu_reg_params* prm, double subcorr, int fixnan,
+                                         int n, const int32_t* req_triplet, const int32_t* req_la, const int32_t* req_lb, const int32_t* req_lc, double* out) {
+    if (!req_triplet || !req_la || !req_lb || !req_lc) return fail(MSMGPU_ERR_INVALID, "group_triplet_costs: bad arguments");
+    return group_triplet_run(ctx, n_nodes, cp_xyz, orig_xyz, rotations, L, labels, ntrip, triplets, prm, subcorr, fixnan, n, req_triplet, req_la, req_lb,
+                             req_lc, nullptr, 0, out);
+}
+
+msmgpu_status msmgpu_group_triplet_batch(msmgpu_ctx* ctx, int n_nodes, const double* cp_xyz, const double* orig_xyz, const double* rotations, int L,
+                                         const double* labels, int ntrip, const int32_t* triplets, const msmgpu_reg_params* prm, double subcorr, int fixnan,
+                                         const int32_t* labeling, int label, double* out) {
+    if (!labeling || label < 0 || label >= L) return fail(MSMGPU_ERR_INVALID, "group_triplet_batch: bad arguments");
+    return group_triplet_run(ctx, n_nodes, cp_xyz, orig_xyz, rotations, L, labels, ntrip, triplets, prm, subcorr, fixnan, 8 * ntrip, nullptr, nullptr,
+                             nullptr, nullptr, labeling, label, out);
+}
 
 msmgpu_status msmgpu_costfn_set_cpgrid_ho(msmgpu_costfn* c, int ncp, const double* cp_xyz, int ntri, const int32_t* cp_tri,
                                           int cfw_rows, const double* cfw, const double* absw) {

@@ -169,6 +169,32 @@ class DiscreteGroupModel:
         dev = torch.device("cuda", self.ctx.device)
         return self.coll.all_gather_blocks(torch.from_numpy(local).to(dev), P).cpu().numpy()
 
+    # DiscreteGroupCostFunction::computeTripletCost (cpp:26-52): strain of a control-grid triangle of one subject, scaled by subcorr = 0.1 * S
+    def computeTripletCostList(self, cps, orig_cps, rotations, labels, triplets, triplet, la, lb, lc, lambda_, shearmodulus=0.4, bulkmodulus=1.6,
+                               kexponent=2.0, exponent=2.0, fixnan=False):
+        """cps / orig_cps [S][ncp][3] current and undeformed control grids; triplets [T][3] GLOBAL node ids (estimate_triplets, cpp:57-74)."""
+        cp, org = f64(cps).reshape(-1, 3), f64(orig_cps).reshape(-1, 3)
+        S = f64(cps).shape[0]
+        rot, labels, trip = f64(rotations).reshape(-1, 9), f64(labels), i32(triplets).reshape(-1, 3)
+        t, a, b, c = i32(triplet), i32(la), i32(lb), i32(lc)
+        reg = capi.RegParams(lambda_, shearmodulus, bulkmodulus, kexponent, exponent, 3)
+        out = np.zeros(len(t))
+        check(self.L_.msmgpu_group_triplet_costs(self.ctx.h, len(cp), ptr(cp), ptr(org), ptr(rot), len(labels), ptr(labels), len(trip), ptr(trip),
+                                                 C.byref(reg), 0.1 * S, int(fixnan), len(t), ptr(t), ptr(a), ptr(b), ptr(c), ptr(out)))
+        return out
+
+    def computeTripletCostsForLabel(self, cps, orig_cps, rotations, labels, triplets, labeling, label, lambda_, shearmodulus=0.4, bulkmodulus=1.6,
+                                    kexponent=2.0, exponent=2.0, fixnan=False):
+        """The 8 combinations per triplet of Fusion::optimize (Fusion.h:181-196) -> [T, 8]."""
+        cp, org = f64(cps).reshape(-1, 3), f64(orig_cps).reshape(-1, 3)
+        S = f64(cps).shape[0]
+        rot, labels, trip, lab = f64(rotations).reshape(-1, 9), f64(labels), i32(triplets).reshape(-1, 3), i32(labeling)
+        reg = capi.RegParams(lambda_, shearmodulus, bulkmodulus, kexponent, exponent, 3)
+        out = np.zeros((len(trip), 8))
+        check(self.L_.msmgpu_group_triplet_batch(self.ctx.h, len(cp), ptr(cp), ptr(org), ptr(rot), len(labels), ptr(labels), len(trip), ptr(trip),
+                                                 C.byref(reg), 0.1 * S, int(fixnan), ptr(lab), int(label), ptr(out)))
+        return out
+
     def close(self):
         if self.g is not None:
             self.L_.msmgpu_group_destroy(self.g)

@@ -292,6 +292,20 @@ def oracle_group_pair_costs(simmeasure, ncp, tpl_xyz, fields, rot, labels, spaci
     return out
 
 
+def oracle_group_triplet_costs(cps, orig_cps, rot, labels, triplets, req_t, req_la, req_lb, req_lc, lambda_, mu=0.4, kappa=1.6, k_exp=2.0, rexp=2.0):
+    """DiscreteGroupCostFunction::computeTripletCost (cpp:26-52) from the pairwise-model restatement: no likelihood, lambda' = subcorr * lambda
+    (the reference multiplies left to right: (subcorr * lambda) * W^rexp), FOLDING instead of FOLDING * lambda."""
+    cp, org = _f64(cps), _f64(orig_cps)
+    S = cp.shape[0]
+    lam = (0.1 * S) * lambda_
+    n_nodes = cp.shape[0] * cp.shape[1]
+    dummy = np.zeros((1, n_nodes))
+    out = oracle_triplet_costs(0, 2, None, cp.reshape(-1, 3), org.reshape(-1, 3), rot, labels, triplets, req_t, req_la, req_lb, req_lc,
+                               cp.reshape(-1, 3), None, None, dummy, dummy, None, np.ones(n_nodes), lam, mu, kappa, k_exp, rexp)
+    out[out == 1e7 * lam] = 1e7
+    return out
+
+
 # --------------------------------------------------------------------------------------
 # compiled reference (oracle/_ref)
 # --------------------------------------------------------------------------------------

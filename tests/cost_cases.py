@@ -102,3 +102,20 @@ def golden_digest(d):
             v = np.concatenate([np.asarray(x).ravel() for x in v])
         h.update(np.ascontiguousarray(v).tobytes())
     return np.frombuffer(h.digest(), dtype=np.uint8)
+
+
+def group_triplet_case(O, g, n=3000):
+    """Inputs of DiscreteGroupCostFunction::computeTripletCost for a group case: global triplets (estimate_triplets, DiscreteGroupModel.cpp:57-74),
+    undeformed grids = the shared icosphere, current grids = g["cps"], a seeded request list."""
+    from newmsm_b200 import synth
+    S, ncp = g["cps"].shape[0], g["cps"].shape[1]
+    level = {12: 0, 42: 1, 162: 2, 642: 3, 2562: 4}[ncp]
+    cp0, _ = synth.icosphere(level)
+    orig = np.stack([cp0] * S)
+    trip = np.concatenate([np.sort(g["cp_tri"] + s_ * ncp, axis=1) for s_ in range(S)]).astype(np.int32)
+    rot = np.array([O.oracle_rotation_matrix(g["centre"], c) for c in g["cps"].reshape(-1, 3)]).reshape(-1, 9)
+    rng = np.random.default_rng(31)
+    L = len(g["labels"])
+    req = (rng.integers(0, len(trip), n).astype(np.int32), rng.integers(0, L, n).astype(np.int32),
+           rng.integers(0, L, n).astype(np.int32), rng.integers(0, L, n).astype(np.int32))
+    return orig, trip, rot, req

@@ -492,9 +492,19 @@ def test_triplet_costs_vs_reference_golden(R, oracle_built):
 
 def test_group_costs_vs_reference_golden(R, oracle_built):
     from newmsm_b200 import group_cost as GC
-    from cost_cases import golden_digest, golden_group_glue
+    from cost_cases import golden_digest, golden_group_glue, group_triplet_case
     g = load("costs.npz")
     c = group_setup(S=2, cp_level=1, data_level=3, tpl_level=3, D=2)
+    # group triplet term (DiscreteGroupCostFunction.cpp:26-52): list form vs the reference's outputs, and Fusion's 8-combination batch
+    orig, trip, rot_t, (rt, ta, tb, tc) = group_triplet_case(oracle_built, c)
+    Mt = GC.DiscreteGroupModel(R.Mesh(c["tpl"], c["tpl_tri"]))
+    assert np.array_equal(Mt.computeTripletCostList(c["cps"], orig, rot_t, c["labels"], trip, rt, ta, tb, tc, 0.05), g["group_triplet"])
+    labeling = np.random.default_rng(3).integers(0, len(c["labels"]), len(rot_t)).astype(np.int32)
+    batch = Mt.computeTripletCostsForLabel(c["cps"], orig, rot_t, c["labels"], trip, labeling, 2, 0.05)
+    T = len(trip)
+    tt = np.repeat(np.arange(T, dtype=np.int32), 8); combo = np.tile(np.arange(8), T)
+    pick = lambda k, bit: np.where((combo >> bit) & 1, 2, labeling[trip[tt, k]]).astype(np.int32)
+    assert np.array_equal(batch.reshape(-1), Mt.computeTripletCostList(c["cps"], orig, rot_t, c["labels"], trip, tt, pick(0, 2), pick(1, 1), pick(2, 0), 0.05))
     assert np.array_equal(golden_digest(c), g["group_digest"]), "seeded inputs drifted: regenerate the fixture"
     rot, spacings, pairs, (rp, la, lb) = golden_group_glue(oracle_built, c)
     for sim in (1, 2):

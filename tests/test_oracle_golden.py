@@ -110,9 +110,11 @@ def test_triplet_costs_golden(oracle_built):
 
 
 def test_group_costs_golden(oracle_built):
-    from cost_cases import golden_digest, golden_group_glue, group_setup
+    from cost_cases import golden_digest, golden_group_glue, group_setup, group_triplet_case
     g = load("costs.npz")
     c = group_setup(S=2, cp_level=1, data_level=3, tpl_level=3, D=2)
+    orig, trip, rot_t, (rt, ta, tb, tc) = group_triplet_case(oracle_built, c)
+    assert np.array_equal(oracle_built.oracle_group_triplet_costs(c["cps"], orig, rot_t, c["labels"], trip, rt, ta, tb, tc, 0.05), g["group_triplet"])
     assert np.array_equal(golden_digest(c), g["group_digest"]), "seeded inputs drifted: regenerate the fixture"
     rot, spacings, pairs, (rp, la, lb) = golden_group_glue(oracle_built, c)
     fields = oracle_built.oracle_group_fields(c["data"], c["dtri"], c["feat"], c["labels"], c["centre"], c["tpl"], c["tpl_tri"])

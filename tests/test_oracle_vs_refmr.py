@@ -6,7 +6,7 @@ Bit-exact unless a tolerance is written next to the assert. Skipped when oracle/
 import numpy as np
 import pytest
 
-from cost_cases import cost_setup, group_setup, triplet_setup
+from cost_cases import cost_setup, group_setup, group_triplet_case, triplet_setup
 
 
 @pytest.fixture(scope="module")
@@ -125,3 +125,13 @@ def test_group_patch_data_and_pair_costs(O, sim):
     ok = ~np.isnan(got)
     assert ok.mean() > 0.9
     assert np.array_equal(got[ok], ref[ok])
+
+
+@pytest.mark.parametrize("kexp,rexp", [(2.0, 2.0), (1.5, 1.3)])
+def test_group_triplet_costs(O, kexp, rexp):
+    g = group_setup()
+    orig, trip, rot, (rt, la, lb, lc) = group_triplet_case(O, g)
+    ref = O.refmr_group_triplet_costs(g["cps"], orig, g["cp_tri"], rot, g["labels"], trip, 0.05, 0.4, 1.6, kexp, rexp, rt, la, lb, lc)
+    got = O.oracle_group_triplet_costs(g["cps"], orig, rot, g["labels"], trip, rt, la, lb, lc, 0.05, 0.4, 1.6, kexp, rexp)
+    assert np.all(np.isfinite(ref)) and np.ptp(ref) > 0
+    assert np.array_equal(got, ref)
