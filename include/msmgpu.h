@@ -196,6 +196,8 @@ msmgpu_status msmgpu_costfn_create(msmgpu_octree* target_tree, msmgpu_cost_kind 
                                    msmgpu_costfn** out);
 void msmgpu_costfn_destroy(msmgpu_costfn* c);
 /* replaces: reset_source (DiscreteCostFunction.h:190) */
+/* sparsesimkernel::set_percentile (similarities.h:40, "--percentile"): threshold of the DICE measures (simmeasure 4 / 5), default 0.75 */
+msmgpu_status msmgpu_costfn_set_percentile(msmgpu_costfn* c, double percentile);
 msmgpu_status msmgpu_costfn_reset_source(msmgpu_costfn* c, const double* source_xyz);
 /* replaces: reset_CPgrid + set_spacings + set_dataaffintyweighting + get_source_data (cpp:334-351: patch membership by
  * within_controlpt_range, cpp:102-107) + resample_weights (cpp:303-323) inputs.

@@ -122,6 +122,7 @@ class GpuCostFunction : public Base {
     static constexpr bool kHO = KIND == MSMGPU_COST_HO_UNIVARIATE || KIND == MSMGPU_COST_HO_MULTIVARIATE;
 
     newmeshreg::DiscreteModel* model_;   // owner of labeling[] (DiscreteModel.h:46)
+    double percentile_ = 0.75;           // "percentile" parameter (DICE measures)
     msmgpu_mesh* d_target_ = nullptr;
     msmgpu_octree* d_tree_ = nullptr;
     msmgpu_costfn* d_cf_ = nullptr;
@@ -168,6 +169,7 @@ class GpuCostFunction : public Base {
         }
         const std::vector<double> sxyz = detail::coords_of(this->_SOURCE);
         detail::check(msmgpu_costfn_create(d_tree_, KIND, this->_simmeasure, ns, sxyz.data(), D, sf.data(), rf.data(), &d_cf_));
+        detail::check(msmgpu_costfn_set_percentile(d_cf_, percentile_));
     }
 
     // labels / rotations / triplets / undeformed control points of the current iteration (set_labels, setTriplets)
@@ -247,6 +249,12 @@ class GpuCostFunction : public Base {
 
 public:
     explicit GpuCostFunction(newmeshreg::DiscreteModel* model) : model_(model) {}
+
+    void set_parameters(newmeshreg::myparam& P) override {   // cpp:119-133; `sim` keeps the percentile private, so it is read here too
+        Base::set_parameters(P);
+        auto it = P.find("percentile");
+        if (it != P.end()) percentile_ = std::get<double>(it->second);
+    }
     ~GpuCostFunction() override { release(); }
 
     void initialize(int numNodes, int numLabels, int numPairs, int numTriplets) override {

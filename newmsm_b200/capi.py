@@ -85,6 +85,7 @@ _SIGNATURES = {
     "msmgpu_costfn_create": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _pp]),
     "msmgpu_costfn_destroy": (None, [_vp]),
     "msmgpu_costfn_reset_source": (_i, [_vp, _vp]),
+    "msmgpu_costfn_set_percentile": (_i, [_vp, _d]),
     "msmgpu_costfn_set_cpgrid": (_i, [_vp, _i, _vp, _vp, _d, _i, _vp, _vp]),
     "msmgpu_costfn_patches": (_i, [_vp, _vp, _vp]),
     "msmgpu_costfn_unary_table": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),

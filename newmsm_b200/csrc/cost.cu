@@ -106,6 +106,7 @@ __global__ void k_max_i32(int n, const int* __restrict__ v, int* __restrict__ ou
 struct UnaryArgs {
     TreeView tree;
     int kind, simmeasure, ncp, L, nsrc, D, nvt, cfw_rows, n_patch;
+    double percentile;
     const double* R;          // [L][ncp][9]
     const double* src_xyz;    // [nsrc][3]
     const int* prow;          // [ncp+1]
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(kCostThreads) k_unary_table(UnaryArgs a) {
             cost = sim_for_min(a.simmeasure, P,
                                [&](int i) { return __ldg(sf + (size_t)srcv(i) * D); },
                                [&](int i) { return s_sim[i]; },
-                               [&](int i) { return cr >= 1 ? __ldg(a.cfw + (size_t)srcv(i) * cr) : 1.0; });
+                               [&](int i) { return cr >= 1 ? __ldg(a.cfw + (size_t)srcv(i) * cr) : 1.0; }, a.percentile);
         }
     } else if (a.kind == MSMGPU_COST_MULTIVARIATE) {   // cpp:444-458: per-vertex similarity across channels, mean over the patch
         const int cr = a.cfw_rows;
@@ -201,7 +202,7 @@ __global__ void __launch_bounds__(kCostThreads) k_unary_table(UnaryArgs a) {
             s_sim[i] = sim_for_min(a.simmeasure, D,
                                    [&](int d) { return __ldg(sf + (size_t)sv * D + d); },
                                    [&](int d) { return tgt(i, d); },
-                                   [&](int d) { return cr >= d + 1 ? __ldg(a.cfw + (size_t)sv * cr + d) : 1.0; });
+                                   [&](int d) { return cr >= d + 1 ? __ldg(a.cfw + (size_t)sv * cr + d) : 1.0; }, a.percentile);
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(kCostThreads) k_unary_table(UnaryArgs a) {
             s_sim[d] = sim_for_min(a.simmeasure, P,
                                    [&](int i) { return __ldg(sf + (size_t)srcv(i) * D + d); },
                                    [&](int i) { return tgt(i, d); },
-                                   [&](int i) { return cr >= 1 ? __ldg(a.cfw + (size_t)srcv(i) * cr) : 1.0; });
+                                   [&](int i) { return cr >= 1 ? __ldg(a.cfw + (size_t)srcv(i) * cr) : 1.0; }, a.percentile);
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -306,7 +307,8 @@ msmgpu_status msmgpu_costfn_create(msmgpu_octree* target_tree, msmgpu_cost_kind 
                                    int D, const double* src_feat, const double* ref_feat, msmgpu_costfn** out) {
     if (!target_tree || !out || nsrc <= 0 || D <= 0 || !source_xyz || !src_feat || !ref_feat || kind < 0 || kind > MSMGPU_COST_HO_MULTIVARIATE)
         return fail(MSMGPU_ERR_INVALID, "costfn_create: bad arguments");
-    if (simmeasure != 1 && simmeasure != 2) return fail(MSMGPU_ERR_INVALID, "costfn_create: simmeasure must be 1 (SSD) or 2 (correlation)");
+    if (simmeasure != 1 && simmeasure != 2 && simmeasure != 4 && simmeasure != 5)
+        return fail(MSMGPU_ERR_INVALID, "Unknown similarity metric");   // similarities.h:57 (1 SSD, 2 correlation, 4 DICE, 5 genDICE)
     *out = nullptr;
     msmgpu_ctx* ctx = target_tree->mesh->ctx;
     MSM_CUDA(cudaSetDevice(ctx->device));
@@ -357,6 +359,12 @@ msmgpu_status msmgpu_costfn_set_cpgrid(msmgpu_costfn* c, int ncp, const double* 
     return MSMGPU_OK;
 }
 
+msmgpu_status msmgpu_costfn_set_percentile(msmgpu_costfn* c, double percentile) {
+    if (!c || !(percentile >= 0.0 && percentile <= 1.0)) return fail(MSMGPU_ERR_INVALID, "costfn_set_percentile: percentile must be in [0, 1]");
+    c->percentile = percentile;
+    return MSMGPU_OK;
+}
+
 msmgpu_status msmgpu_costfn_patches(msmgpu_costfn* c, int32_t* rowptr, int32_t* members) {
     if (!c || !rowptr || c->n_patch_rows <= 0) return fail(MSMGPU_ERR_INVALID, "costfn_patches: set_cpgrid first");
     MSM_CUDA(cudaSetDevice(c->ctx->device));
@@ -392,7 +400,7 @@ msmgpu_status msmgpu_costfn_unary_table_dev(msmgpu_costfn* c, int L, const doubl
     MSM_TRY(upload_vec(d_R, R.data(), R.size(), s));
     UnaryArgs a;
     a.tree = c->tree->view();
-    a.kind = c->kind; a.simmeasure = c->simmeasure; a.ncp = ncp; a.L = L; a.nsrc = c->nsrc; a.D = c->D; a.nvt = c->nvt;
+    a.kind = c->kind; a.simmeasure = c->simmeasure; a.percentile = c->percentile; a.ncp = ncp; a.L = L; a.nsrc = c->nsrc; a.D = c->D; a.nvt = c->nvt;
     a.cfw_rows = c->cfw_rows; a.n_patch = c->n_patch;
     a.R = d_R.p; a.src_xyz = c->src_xyz.p; a.prow = c->prow.p; a.pmem = c->pmem.p;
     a.src_feat = c->src_feat.p; a.ref_feat = c->ref_feat.p; a.cfw = c->cfw.p; a.absw = c->absw.p;

@@ -7,6 +7,7 @@ struct msmgpu_costfn {
     msmgpu_ctx* ctx = nullptr;
     msmgpu_octree* tree = nullptr;
     int kind = 0, simmeasure = 2;
+    double percentile = 0.75;       // sparsesimkernel::percentile (similarities.h:68), DICE only
     int nsrc = 0, D = 0, nvt = 0;
     msm::DevBuf<double> src_xyz;    // [nsrc][3]
     msm::DevBuf<double> src_feat;   // [nsrc][D] rows
@@ -60,10 +61,44 @@ __device__ __forceinline__ double sim_ssd(int n, FA A, FB B, FW W) {
     }
     return sqrt(prod) / n;
 }
+// DICE / genDICE (similarities.cpp:201-253): the reference sorts copies of A and B and thresholds both at the order statistic
+// idx = floor(percentile * n). Only that one order statistic is needed: v = X(i) is it iff #(X < v) <= idx < #(X <= v). O(n^2)
+// compares in one lane (n = patch size or channel count; an "experimental" measure in the reference, mesh_registration.cpp:471).
+template <class F>
+__device__ __forceinline__ double order_statistic(int n, int idx, F X) {
+    for (int i = 0; i < n; ++i) {
+        const double v = X(i);
+        int lt = 0, le = 0;
+        for (int j = 0; j < n; ++j) {
+            const double x = X(j);
+            lt += x < v;
+            le += x <= v;
+        }
+        if (lt <= idx && idx < le) return v;
+    }
+    return nan("");   // idx >= n (percentile = 1): the reference reads past the end of its sorted copy
+}
+template <class FA, class FB>
+__device__ __forceinline__ double sim_dice(int n, FA A, FB B, double percentile, bool general) {
+    const int idx = (int)floor(percentile * n);
+    const double ta = order_statistic(n, idx, A), tb = order_statistic(n, idx, B);
+    int size_A = n, size_B = n, common = 0;
+    for (int i = 0; i < n; ++i) {
+        const bool la = A(i) < ta, lb = B(i) < tb;
+        size_A -= la;
+        size_B -= lb;
+        common += !(la || lb);
+    }
+    if (!general) return 1.0 - ((2.0 * common) / (size_A + size_B));
+    const double b2 = (double)size_B * (double)size_B;   // pow(size_B, 2): exact for these integers
+    return 1.0 - (2.0 * (((common / b2)) / ((size_A + size_B) / b2)));
+}
 template <class FA, class FB, class FW>
-__device__ __forceinline__ double sim_for_min(int simmeasure, int n, FA A, FB B, FW W) {
+__device__ __forceinline__ double sim_for_min(int simmeasure, int n, FA A, FB B, FW W, double percentile = 0.75) {
     if (simmeasure == 1) return sim_ssd(n, A, B, W);
     if (simmeasure == 2) return 1 - (1 + sim_corr(n, A, B, W)) * 0.5;
+    if (simmeasure == 4) return sim_dice(n, A, B, percentile, false);
+    if (simmeasure == 5) return sim_dice(n, A, B, percentile, true);
     return nan("");
 }
 

@@ -283,7 +283,7 @@ template <int TPC, int IPT>
 __global__ void __launch_bounds__(TPC == 32 ? 256 : TPC) k_chunk_stats(int node_begin, int n_level, int max_chunks, const int4* __restrict__ nodes,
                                                                         const BuildNode* __restrict__ bn, const int* __restrict__ pairs,
                                                                         const double* const* __restrict__ mesh_aabb, double root_half,
-                                                                        int* __restrict__ stats) {
+                                                                        int* __restrict__ stats, unsigned char* __restrict__ pmask) {
     constexpr int K = TPC * IPT;
     constexpr int TEAMS = TPC == 32 ? 8 : 1;
     __shared__ int s_scan[TPC == 32 ? 1 : 33];
@@ -312,6 +312,7 @@ __global__ void __launch_bounds__(TPC == 32 ? 256 : TPC) k_chunk_stats(int node_
         if (p < cnt) {
             unsigned mask;
             classify(aabb + 6 * (size_t)__ldg(pairs + nd.y + p), b.lo, half, a[k], mask);
+            pmask[(size_t)nd.y + p] = (unsigned char)mask;   // kept for k_scatter_chunk: the 48-byte AABB is gathered once per level, not twice
 #pragma unroll
             for (int c = 0; c < 8; ++c) c8[c] += (mask >> c) & 1u;
         }
@@ -406,8 +407,8 @@ __global__ void k_make_children(int node_begin, int n_level, int4* __restrict__ 
 
 template <int TPC, int IPT>
 __global__ void __launch_bounds__(TPC == 32 ? 256 : TPC) k_scatter_chunk(int node_begin, int n_level, int max_chunks, const BuildNode* __restrict__ bn,
-                                                                          int* __restrict__ pairs, const double* const* __restrict__ mesh_aabb,
-                                                                          double root_half, const int* __restrict__ split_flag,
+                                                                          int* __restrict__ pairs, const unsigned char* __restrict__ pmask,
+                                                                          const int* __restrict__ split_flag,
                                                                           const int* __restrict__ list_start, const int* __restrict__ list_count,
                                                                           const int* __restrict__ child_off, const int* __restrict__ stats,
                                                                           int next_pair_base) {
@@ -420,9 +421,6 @@ __global__ void __launch_bounds__(TPC == 32 ? 256 : TPC) k_scatter_chunk(int nod
     const int cnt = list_count[li];
     if (chunk * K >= cnt) return;
     const int start = list_start[li];
-    const BuildNode b = bn[node_begin + li];
-    const double half = ldexp(root_half, -b.depth);
-    const double* __restrict__ aabb = mesh_aabb[b.mesh];
     const int tl = team_lane<TPC>();
     const int p0 = chunk * K + tl * IPT;
     int tri[IPT];
@@ -434,9 +432,8 @@ __global__ void __launch_bounds__(TPC == 32 ? 256 : TPC) k_scatter_chunk(int nod
         tri[k] = -1;
         const int p = p0 + k;
         if (p < cnt) {
-            int a;
             tri[k] = pairs[start + p];
-            classify(aabb + 6 * (size_t)tri[k], b.lo, half, a, mask[k]);
+            mask[k] = pmask[(size_t)start + p];   // child-overlap mask computed by k_chunk_stats for this list position
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 lo4 += (unsigned long long)((mask[k] >> c) & 1u) << (16 * c);
@@ -525,6 +522,8 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
         DevBuf<int> d_nt, d_off;
         MSM_CUDA(F->nodes.alloc(node_cap, s));
         MSM_CUDA(F->pairs.alloc(pair_cap, s));
+        DevBuf<unsigned char> pmask;   // per list position: which of the 8 children the triangle goes to (this level only)
+        MSM_CUDA(pmask.alloc(pair_cap, s));
         MSM_CUDA(F->node_depth.alloc(node_cap, s));
         MSM_CUDA(bn.alloc(node_cap, s));
         MSM_CUDA(d_aabb.alloc(n, s));
@@ -565,11 +564,11 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
             if (max_chunks > 65535) return fail(MSMGPU_ERR_CAPACITY, "forest_build: list too long for the chunk grid");
             const dim3 g_cta((unsigned)n_level, (unsigned)max_chunks), g_warp((unsigned)((n_level + 7) / 8), (unsigned)max_chunks);
             if (K == 8192)
-                k_chunk_stats<1024, 8><<<g_cta, 1024, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_aabb.p, root_half, stats.p);
+                k_chunk_stats<1024, 8><<<g_cta, 1024, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_aabb.p, root_half, stats.p, pmask.p);
             else if (K == 1024)
-                k_chunk_stats<256, 4><<<g_cta, 256, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_aabb.p, root_half, stats.p);
+                k_chunk_stats<256, 4><<<g_cta, 256, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_aabb.p, root_half, stats.p, pmask.p);
             else
-                k_chunk_stats<32, 4><<<g_warp, 256, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_aabb.p, root_half, stats.p);
+                k_chunk_stats<32, 4><<<g_warp, 256, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_aabb.p, root_half, stats.p, pmask.p);
             MSM_LAUNCH_CHECK();
             k_node_combine<<<(n_level + 255) / 256, 256, 0, s>>>(node_begin, n_level, max_chunks, K, F->nodes.p, stats.p, split_flag.p, child_cnt.p);
             MSM_LAUNCH_CHECK();
@@ -592,13 +591,13 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
                                                                  (int)node_cap);
             MSM_LAUNCH_CHECK();
             if (K == 8192)
-                k_scatter_chunk<1024, 8><<<g_cta, 1024, 0, s>>>(node_begin, n_level, max_chunks, bn.p, F->pairs.p, d_aabb.p, root_half, split_flag.p,
+                k_scatter_chunk<1024, 8><<<g_cta, 1024, 0, s>>>(node_begin, n_level, max_chunks, bn.p, F->pairs.p, pmask.p, split_flag.p,
                                                                list_start.p, list_count.p, child_off.p, stats.p, (int)n_pairs);
             else if (K == 1024)
-                k_scatter_chunk<256, 4><<<g_cta, 256, 0, s>>>(node_begin, n_level, max_chunks, bn.p, F->pairs.p, d_aabb.p, root_half, split_flag.p,
+                k_scatter_chunk<256, 4><<<g_cta, 256, 0, s>>>(node_begin, n_level, max_chunks, bn.p, F->pairs.p, pmask.p, split_flag.p,
                                                              list_start.p, list_count.p, child_off.p, stats.p, (int)n_pairs);
             else
-                k_scatter_chunk<32, 4><<<g_warp, 256, 0, s>>>(node_begin, n_level, max_chunks, bn.p, F->pairs.p, d_aabb.p, root_half, split_flag.p,
+                k_scatter_chunk<32, 4><<<g_warp, 256, 0, s>>>(node_begin, n_level, max_chunks, bn.p, F->pairs.p, pmask.p, split_flag.p,
                                                              list_start.p, list_count.p, child_off.p, stats.p, (int)n_pairs);
             MSM_LAUNCH_CHECK();
             level_max_cnt = h_tot[2];

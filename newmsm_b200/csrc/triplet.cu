@@ -133,6 +133,7 @@ __global__ void k_sort_segments(int nkeys, const int* __restrict__ ptr, int* __r
 struct TripletArgs {
     TreeView tree;
     int kind, simmeasure, ncp, nsrc, D, cfw_rows, n, max_patch;
+    double percentile;
     const int* triplets;      // [ntrip][3]
     const int* req_t;         // [n] or NULL (then request r = 8 * triplet + combo, Fusion.h:181-196)
     const int* req_la; const int* req_lb; const int* req_lc;
@@ -246,12 +247,12 @@ __global__ void __launch_bounds__(kTripWarps * 32) k_triplet_costs(TripletArgs a
             __syncwarp();
             if (lane == 0)
                 cost = sim_for_min(a.simmeasure, P, [&](int i) { return __ldg(sf + (size_t)srcv(i) * D); }, [&](int i) { return s_sim[i]; },
-                                   [&](int i) { return cr >= 1 ? __ldg(a.cfw + (size_t)srcv(i) * cr) : 1.0; });
+                                   [&](int i) { return cr >= 1 ? __ldg(a.cfw + (size_t)srcv(i) * cr) : 1.0; }, a.percentile);
         } else {   // cpp:601-618
             for (int i = lane; i < P; i += 32) {
                 const int sv = srcv(i);
                 s_sim[i] = sim_for_min(a.simmeasure, D, [&](int d) { return __ldg(sf + (size_t)sv * D + d); }, [&](int d) { return tgt(i, d); },
-                                       [&](int d) { return cr >= d + 1 ? __ldg(a.cfw + (size_t)sv * cr + d) : 1.0; });
+                                       [&](int d) { return cr >= d + 1 ? __ldg(a.cfw + (size_t)sv * cr + d) : 1.0; }, a.percentile);
             }
             __syncwarp();
             if (lane == 0) {
@@ -318,7 +319,7 @@ static msmgpu_status triplet_run(msmgpu_costfn* c, int ntrip, const int32_t* tri
     MSM_CUDA(cudaMemsetAsync(d_err.p, 0, sizeof(int), s));
     TripletArgs a;
     a.tree = c->tree->view();
-    a.kind = c->kind; a.simmeasure = c->simmeasure; a.ncp = c->ncp; a.nsrc = c->nsrc; a.D = c->D; a.cfw_rows = c->cfw_rows; a.n = n;
+    a.kind = c->kind; a.simmeasure = c->simmeasure; a.percentile = c->percentile; a.ncp = c->ncp; a.nsrc = c->nsrc; a.D = c->D; a.cfw_rows = c->cfw_rows; a.n = n;
     a.max_patch = ho ? std::max(c->max_patch, 1) : 1;
     a.triplets = d_trip.p; a.req_t = req_t ? d_rt.p : nullptr; a.req_la = d_la.p; a.req_lb = d_lb.p; a.req_lc = d_lc.p;
     a.labeling = d_labeling.p; a.label = label; a.labels = d_labels.p; a.rot = d_rot.p; a.cp_xyz = c->cp_xyz.p; a.orig_xyz = d_orig.p;

@@ -24,8 +24,9 @@ class NonLinearSRegDiscreteCostFunction:
 
     KIND = UNIVARIATE
 
-    def __init__(self, simmeasure: int = CORRELATION):
-        self.simmeasure = simmeasure
+    def __init__(self, simmeasure: int = CORRELATION, percentile: float = 0.75):
+        self.simmeasure = simmeasure      # 1 SSD, 2 correlation, 4 DICE, 5 genDICE (similarities.h:48-58)
+        self.percentile = percentile      # sparsesimkernel::set_percentile (DICE measures)
         self.h = None
         self.unarycosts = None
 
@@ -39,6 +40,7 @@ class NonLinearSRegDiscreteCostFunction:
         self.D, self.nsrc = a.shape[0], len(s)
         self.h = C.c_void_p()
         check(self.L.msmgpu_costfn_create(self.tree.h, self.KIND, self.simmeasure, len(s), ptr(s), self.D, ptr(a), ptr(b), C.byref(self.h)))
+        check(self.L.msmgpu_costfn_set_percentile(self.h, float(self.percentile)))
 
     def reset_source(self, source_xyz):
         s = f64(source_xyz)

@@ -211,6 +211,10 @@ def oracle_sim(simmeasure, A, B, w):
     return Oracle.lib().orc_sim_for_min(simmeasure, len(A), _p(A), _p(B), _p(w))
 
 
+def oracle_set_percentile(p):
+    Oracle.lib().orc_set_percentile(C.c_double(p))
+
+
 def oracle_patch_membership(cp_xyz, src_xyz, maxsep, rng, nthreads=8):
     cp, s, ms = _f64(cp_xyz), _f64(src_xyz), _f64(maxsep)
     rowptr = np.zeros(len(cp) + 1, np.int32)
@@ -494,6 +498,10 @@ class RefMR:
             L.refmr_label_sets.argtypes = [_i, _d, _vp, _vp, _i, _vp, _vp]
             cls._lib = L
         return cls._lib
+
+
+def refmr_set_percentile(p):
+    RefMR.lib().refmr_set_percentile(C.c_double(p))
 
 
 def refmr_unary(kind, simmeasure, tgt_xyz, tgt_tri, cp_xyz, cp_tri, rot, labels, src_xyz, src_tri, src_feat, ref_feat, cfw, absw, maxsep, range_,

@@ -578,10 +578,32 @@ double orc_ssd(int n, const double* A, const double* B, const double* w) {
     return std::sqrt(prod) / n;
 }
 
-// similarities.h:48-58 (simmeasure 1 = SSD, 2 = correlation)
+// similarities.cpp:201-253: DICE / genDICE on the samples thresholded at the order statistic floor(percentile * n) of each vector
+static double g_percentile = 0.75;   // sparsesimkernel::percentile (similarities.h:68)
+void orc_set_percentile(double p) { g_percentile = p; }
+double orc_dice(int n, const double* A, const double* B, int general) {
+    const int idx = (int)std::floor(g_percentile * n);
+    if (idx >= n) return std::numeric_limits<double>::quiet_NaN();   // the reference indexes past the end here
+    std::vector<double> As(A, A + n), Bs(B, B + n);
+    std::sort(As.begin(), As.end());
+    std::sort(Bs.begin(), Bs.end());
+    int size_A = n, size_B = n, common = 0;
+    for (int i = 0; i < n; ++i) {
+        int keep = 1;
+        if (A[i] < As[idx]) { size_A--; keep = 0; }
+        if (B[i] < Bs[idx]) { size_B--; keep = 0; }
+        common += keep;
+    }
+    if (!general) return 1.0 - ((2.0 * common) / (size_A + size_B));
+    return 1.0 - (2.0 * (((common / std::pow(size_B, 2))) / ((size_A + size_B) / std::pow(size_B, 2))));
+}
+
+// similarities.h:48-58 (simmeasure 1 = SSD, 2 = correlation, 4 = DICE, 5 = genDICE)
 double orc_sim_for_min(int simmeasure, int n, const double* A, const double* B, const double* w) {
     if (simmeasure == 1) return orc_ssd(n, A, B, w);
     if (simmeasure == 2) return 1 - (1 + orc_corr(n, A, B, w)) * 0.5;
+    if (simmeasure == 4) return orc_dice(n, A, B, 0);
+    if (simmeasure == 5) return orc_dice(n, A, B, 1);
     return std::numeric_limits<double>::quiet_NaN();
 }
 

@@ -71,6 +71,9 @@ int orc_rotation_matrix(const double* ci, const double* index, double* R);
 double orc_corr(int n, const double* A, const double* B, const double* w);
 double orc_ssd(int n, const double* A, const double* B, const double* w);
 double orc_sim_for_min(int simmeasure, int n, const double* A, const double* B, const double* w);
+/* similarities.cpp:201-253 DICE (general = 0) / genDICE (1); threshold percentile set process-wide like sparsesimkernel::set_percentile */
+void orc_set_percentile(double p);
+double orc_dice(int n, const double* A, const double* B, int general);
 
 /* DiscreteCostFunction.cpp:102-107 + 334-351: patch membership lists (CSR over CPs, ascending
  * source id). Returns total entries, writes up to cap. */

@@ -88,6 +88,8 @@ int flatten_lists(const std::vector<std::vector<int>>& lists, int* rowptr, int* 
     return pos;
 }
 
+double g_percentile = 0.75;   // refmr_set_percentile -> sparsesimkernel::set_percentile (similarities.h:40)
+
 struct Setup {
     std::shared_ptr<NonLinearSRegDiscreteCostFunction> cf;
     std::shared_ptr<Octree> tree;
@@ -108,6 +110,7 @@ Setup wire(int kind, int simmeasure, int nv_t, const double* tgt_xyz, int nt_t, 
     cf.set_featurespace(make_feat(D, nsrc, src_feat, nv_t, ref_feat));
     cf._simmeasure = simmeasure;
     cf.sim.set_simval(simmeasure);
+    cf.sim.set_percentile(g_percentile);
     cf._controlptrange = range;
     cf._threads = nthreads;
     NEWMAT::ColumnVector sep(ncp);
@@ -124,6 +127,8 @@ Setup wire(int kind, int simmeasure, int nv_t, const double* tgt_xyz, int nt_t, 
 }  // namespace
 
 extern "C" {
+
+void refmr_set_percentile(double p) { g_percentile = p; }
 
 // get_source_data() + computeUnaryCosts() of kinds 0 (Univariate, cpp:326-383), 1 (Multivariate, 385-458),
 // 2 (Patchwise, 620-692). out[L][ncp] label-major like unarycosts (cpp:242). absw_in != NULL replaces the

@@ -28,6 +28,12 @@ def main():
             c, prow, pmem, _ = B.refmr_unary(kind, sim, s["xyz"], s["tri"], s["cp"], cp_tri, s["rot"], s["labels"], s["src"], s["tri"],
                                             s["src_feat"], s["ref_feat"], cfw, s["absw"], s["maxsep"], 1.0, nthreads=1)
             out[f"unary_k{kind}_s{sim}"] = c
+        for sim, pct in ((4, 0.75), (5, 0.6)):     # DICE / genDICE (similarities.cpp:201-253)
+            B.refmr_set_percentile(pct)
+            c, _, _, _ = B.refmr_unary(kind, sim, s["xyz"], s["tri"], s["cp"], cp_tri, s["rot"], s["labels"], s["src"], s["tri"],
+                                       s["src_feat"], s["ref_feat"], cfw, s["absw"], s["maxsep"], 1.0, nthreads=1)
+            B.refmr_set_percentile(0.75)
+            out[f"unary_k{kind}_s{sim}"] = c
         out[f"unary_k{kind}_prow"], out[f"unary_k{kind}_pmem"] = prow, pmem
         out[f"unary_k{kind}_digest"] = digest(s)
     for kind, D in ((0, 1), (3, 1), (4, 3)):

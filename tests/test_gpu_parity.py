@@ -462,6 +462,12 @@ def test_unary_costs_vs_reference_golden(R, oracle_built):
             prow, pmem = cf.get_source_data()
             assert np.array_equal(prow, g[f"unary_k{kind}_prow"]) and np.array_equal(pmem, g[f"unary_k{kind}_pmem"])
             assert np.array_equal(cf.computeUnaryCosts(s["labels"], s["rot"]), g[f"unary_k{kind}_s{sim}"])
+        for sim, pct in ((4, 0.75), (5, 0.6)):     # DICE / genDICE (similarities.cpp:201-253)
+            cf = cls(simmeasure=sim, percentile=pct)
+            cf.set_meshes(R.Mesh(s["xyz"], s["tri"]), s["src"], s["src_feat"], s["ref_feat"])
+            cf.reset_CPgrid(s["cp"], s["maxsep"], 1.0, HIGHREScfweight=cfw, AbsoluteWeights=s["absw"])
+            cf.get_source_data()
+            assert np.array_equal(cf.computeUnaryCosts(s["labels"], s["rot"]), g[f"unary_k{kind}_s{sim}"])
 
 
 def test_triplet_costs_vs_reference_golden(R, oracle_built):

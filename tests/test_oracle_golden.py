@@ -89,6 +89,12 @@ def test_unary_costs_golden(oracle_built):
             got = oracle_built.oracle_unary_costs(kind, sim, ot, s["cp"], s["rot"], s["labels"], s["src"], prow, pmem,
                                                   s["src_feat"], s["ref_feat"], cfw, s["absw"])
             assert np.array_equal(got, g[f"unary_k{kind}_s{sim}"])
+        for sim, pct in ((4, 0.75), (5, 0.6)):
+            oracle_built.oracle_set_percentile(pct)
+            got = oracle_built.oracle_unary_costs(kind, sim, ot, s["cp"], s["rot"], s["labels"], s["src"], prow, pmem,
+                                                  s["src_feat"], s["ref_feat"], cfw, s["absw"])
+            oracle_built.oracle_set_percentile(0.75)
+            assert np.array_equal(got, g[f"unary_k{kind}_s{sim}"])
 
 
 def test_triplet_costs_golden(oracle_built):

@@ -135,3 +135,24 @@ def test_group_triplet_costs(O, kexp, rexp):
     got = O.oracle_group_triplet_costs(g["cps"], orig, rot, g["labels"], trip, rt, la, lb, lc, 0.05, 0.4, 1.6, kexp, rexp)
     assert np.all(np.isfinite(ref)) and np.ptp(ref) > 0
     assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("kind,D", [(0, 1), (1, 9), (2, 4)])
+@pytest.mark.parametrize("sim,pct", [(4, 0.75), (4, 0.4), (5, 0.75)])
+def test_unary_costs_dice(O, kind, D, sim, pct):
+    """simmeasure 4 / 5: DICE / genDICE at a percentile threshold (similarities.cpp:201-253), the reference's "experimental" measures."""
+    from newmsm_b200 import synth
+    s = cost_setup(O, 2, 4, D)
+    cp_tri = synth.icosphere(2)[1]
+    ot = O.OracleOctree(s["xyz"], s["tri"])
+    O.refmr_set_percentile(pct)
+    O.oracle_set_percentile(pct)
+    try:
+        ref, prow, pmem, _ = O.refmr_unary(kind, sim, s["xyz"], s["tri"], s["cp"], cp_tri, s["rot"], s["labels"], s["src"], s["tri"],
+                                           s["src_feat"], s["ref_feat"], None, s["absw"], s["maxsep"], 1.0, nthreads=1)
+        got = O.oracle_unary_costs(kind, sim, ot, s["cp"], s["rot"], s["labels"], s["src"], prow, pmem, s["src_feat"], s["ref_feat"], None, s["absw"])
+    finally:
+        O.refmr_set_percentile(0.75)
+        O.oracle_set_percentile(0.75)
+    assert np.array_equal(got, ref)
+    assert np.ptp(ref) > 0
