@@ -283,7 +283,7 @@ template <int TPC, int IPT>
 __global__ void __launch_bounds__(TPC == 32 ? 256 : TPC) k_chunk_stats(int node_begin, int n_level, int max_chunks, const int4* __restrict__ nodes,
                                                                         const BuildNode* __restrict__ bn, const int* __restrict__ pairs,
                                                                         const double* const* __restrict__ mesh_aabb, double root_half,
-                                                                        int* __restrict__ stats, unsigned char* __restrict__ pmask) {
+                                                                        int* __restrict__ stats, unsigned char* __restrict__ pmask, int level_base) {
     constexpr int K = TPC * IPT;
     constexpr int TEAMS = TPC == 32 ? 8 : 1;
     __shared__ int s_scan[TPC == 32 ? 1 : 33];
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(TPC == 32 ? 256 : TPC) k_chunk_stats(int node_
         if (p < cnt) {
             unsigned mask;
             classify(aabb + 6 * (size_t)__ldg(pairs + nd.y + p), b.lo, half, a[k], mask);
-            pmask[(size_t)nd.y + p] = (unsigned char)mask;   // kept for k_scatter_chunk: the 48-byte AABB is gathered once per level, not twice
+            pmask[(size_t)(nd.y - level_base) + p] = (unsigned char)mask;   // kept for k_scatter_chunk: the 48-byte AABB is gathered once per level, not twice
 #pragma unroll
             for (int c = 0; c < 8; ++c) c8[c] += (mask >> c) & 1u;
         }
@@ -407,7 +407,7 @@ __global__ void k_make_children(int node_begin, int n_level, int4* __restrict__ 
 
 template <int TPC, int IPT>
 __global__ void __launch_bounds__(TPC == 32 ? 256 : TPC) k_scatter_chunk(int node_begin, int n_level, int max_chunks, const BuildNode* __restrict__ bn,
-                                                                          int* __restrict__ pairs, const unsigned char* __restrict__ pmask,
+                                                                          int* __restrict__ pairs, const unsigned char* __restrict__ pmask, int level_base,
                                                                           const int* __restrict__ split_flag,
                                                                           const int* __restrict__ list_start, const int* __restrict__ list_count,
                                                                           const int* __restrict__ child_off, const int* __restrict__ stats,
@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(TPC == 32 ? 256 : TPC) k_scatter_chunk(int nod
         const int p = p0 + k;
         if (p < cnt) {
             tri[k] = pairs[start + p];
-            mask[k] = pmask[(size_t)start + p];   // child-overlap mask computed by k_chunk_stats for this list position
+            mask[k] = pmask[(size_t)(start - level_base) + p];   // child-overlap mask computed by k_chunk_stats for this list position
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 lo4 += (unsigned long long)((mask[k] >> c) & 1u) << (16 * c);
@@ -522,8 +522,11 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
         DevBuf<int> d_nt, d_off;
         MSM_CUDA(F->nodes.alloc(node_cap, s));
         MSM_CUDA(F->pairs.alloc(pair_cap, s));
-        DevBuf<unsigned char> pmask;   // per list position: which of the 8 children the triangle goes to (this level only)
-        MSM_CUDA(pmask.alloc(pair_cap, s));
+        DevBuf<unsigned char> pmask;   // per list position of the CURRENT level: which of the 8 children the triangle goes to
+        long long pmask_cap = 3 * total_t + 4096;
+        MSM_CUDA(pmask.alloc((size_t)pmask_cap, s));
+        int level_base = 0;            // the current level's lists occupy pairs[level_base, level_base + level_entries)
+        long long level_entries = total_t;
         MSM_CUDA(F->node_depth.alloc(node_cap, s));
         MSM_CUDA(bn.alloc(node_cap, s));
         MSM_CUDA(d_aabb.alloc(n, s));
@@ -556,6 +559,10 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
             MSM_CUDA(list_start.alloc(n_level, s));
             MSM_CUDA(list_count.alloc(n_level, s));
             // team width by the longest list of the level: whole CTAs at the top, warps at the bottom
+            if (level_entries > pmask_cap) {
+                pmask_cap = level_entries + level_entries / 4;
+                MSM_CUDA(pmask.alloc((size_t)pmask_cap, s));
+            }
             const int max_cnt = level_max_cnt;
             int K, max_chunks;
             if (max_cnt > 16384) K = 1024 * 8; else if (max_cnt > 512) K = 256 * 4; else K = 32 * 4;
@@ -564,11 +571,11 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
             if (max_chunks > 65535) return fail(MSMGPU_ERR_CAPACITY, "forest_build: list too long for the chunk grid");
             const dim3 g_cta((unsigned)n_level, (unsigned)max_chunks), g_warp((unsigned)((n_level + 7) / 8), (unsigned)max_chunks);
             if (K == 8192)
-                k_chunk_stats<1024, 8><<<g_cta, 1024, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_aabb.p, root_half, stats.p, pmask.p);
+                k_chunk_stats<1024, 8><<<g_cta, 1024, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_aabb.p, root_half, stats.p, pmask.p, level_base);
             else if (K == 1024)
-                k_chunk_stats<256, 4><<<g_cta, 256, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_aabb.p, root_half, stats.p, pmask.p);
+                k_chunk_stats<256, 4><<<g_cta, 256, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_aabb.p, root_half, stats.p, pmask.p, level_base);
             else
-                k_chunk_stats<32, 4><<<g_warp, 256, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_aabb.p, root_half, stats.p, pmask.p);
+                k_chunk_stats<32, 4><<<g_warp, 256, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_aabb.p, root_half, stats.p, pmask.p, level_base);
             MSM_LAUNCH_CHECK();
             k_node_combine<<<(n_level + 255) / 256, 256, 0, s>>>(node_begin, n_level, max_chunks, K, F->nodes.p, stats.p, split_flag.p, child_cnt.p);
             MSM_LAUNCH_CHECK();
@@ -591,16 +598,18 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
                                                                  (int)node_cap);
             MSM_LAUNCH_CHECK();
             if (K == 8192)
-                k_scatter_chunk<1024, 8><<<g_cta, 1024, 0, s>>>(node_begin, n_level, max_chunks, bn.p, F->pairs.p, pmask.p, split_flag.p,
+                k_scatter_chunk<1024, 8><<<g_cta, 1024, 0, s>>>(node_begin, n_level, max_chunks, bn.p, F->pairs.p, pmask.p, level_base, split_flag.p,
                                                                list_start.p, list_count.p, child_off.p, stats.p, (int)n_pairs);
             else if (K == 1024)
-                k_scatter_chunk<256, 4><<<g_cta, 256, 0, s>>>(node_begin, n_level, max_chunks, bn.p, F->pairs.p, pmask.p, split_flag.p,
+                k_scatter_chunk<256, 4><<<g_cta, 256, 0, s>>>(node_begin, n_level, max_chunks, bn.p, F->pairs.p, pmask.p, level_base, split_flag.p,
                                                              list_start.p, list_count.p, child_off.p, stats.p, (int)n_pairs);
             else
-                k_scatter_chunk<32, 4><<<g_warp, 256, 0, s>>>(node_begin, n_level, max_chunks, bn.p, F->pairs.p, pmask.p, split_flag.p,
+                k_scatter_chunk<32, 4><<<g_warp, 256, 0, s>>>(node_begin, n_level, max_chunks, bn.p, F->pairs.p, pmask.p, level_base, split_flag.p,
                                                              list_start.p, list_count.p, child_off.p, stats.p, (int)n_pairs);
             MSM_LAUNCH_CHECK();
             level_max_cnt = h_tot[2];
+            level_base = (int)n_pairs;        // the children's lists were appended at the old end of `pairs`
+            level_entries = new_pairs;
             node_begin = n_nodes;
             n_level = 8 * n_split;
             n_nodes += n_level;
