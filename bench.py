@@ -411,8 +411,17 @@ def run_ours(a):
     bytes_bary = 24 * n_low + 24 * nv + 12 * nt + 4 * D * min(3 * n_low, nv) + 4 * D * n_low
     achieved = S * bytes_bary / (k_ms * 1e-3) / 1e9
     bytes_apply = S * (4 * D * nv + 4 * D * n_low + 4 * (n_low + 1)) + 12 * nnz
+    # DRAM traffic of that kernel per launch from the committed `ncu --set full` capture (bytes per subject x subjects in this launch)
+    traffic, traffic_src = None, None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1m_fused_traffic.json")))
+        traffic = float(tr["dram_bytes_per_subject"]) * S
+        traffic_src = "profiles/r1m_fused_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of an 8-subject launch, scaled to %d subjects)" % S
+    except Exception:
+        pass
     roofline = {"kernel": "k_bary_resample_f32 (fused query + weights + 3-row gather, one launch for the batch)", "bound": "hbm",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src,
                 "launch_ms": k_ms, "algorithmic_bytes_per_launch": S * bytes_bary,
                 "adaptive_apply": {"kernel": "k_csr_apply_f32x4", "launch_ms": apply_ms, "algorithmic_bytes_per_launch": bytes_apply,
                                    "achieved": bytes_apply / (apply_ms * 1e-3) / 1e9, "frac": bytes_apply / (apply_ms * 1e-3) / 1e9 / peak}}

@@ -78,7 +78,7 @@ struct TreeView {
     const int4* nodes;
     const int* pairs;
     const TriRec* rec;  // [nt] per-triangle query records (geom.cuh)
-    const double* cull; // [nt][4] conservative bounding spheres (geom.cuh make_cull)
+    const float4* cull; // [nt] conservative bounding spheres, single-precision record (geom.cuh make_cull / pack_cull)
     const int* tri;     // [nt][3]
     int root;
 };
@@ -98,7 +98,7 @@ struct msmgpu_mesh {
     msm::DevBuf<int> tri;      // [nt][3]
     msm::DevBuf<msm::TriRec> rec; // [nt] one 128-byte query record per triangle (gather-free leaf scans)
     msm::DevBuf<double> aabb;  // [nt][6] lo xyz, hi xyz (octree.cpp:46-59)
-    msm::DevBuf<double> cull;  // [nt][4] centre + r^2 of the conservative cull sphere
+    msm::DevBuf<float4> cull;  // [nt] centre + r^2 of the conservative cull sphere (pack_cull)
     msm::DevBuf<float> feat;   // optional resident payload, vertex-major rows [nv][feat_D] (Mesh::pvalues, mesh.h:44)
     int feat_D = 0;
     bool tables_dirty = false;   // rec / aabb / cull not yet computed from xyz (msm::ensure_tables batches that work)

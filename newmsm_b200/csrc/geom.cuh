@@ -249,6 +249,28 @@ __host__ __device__ __forceinline__ void make_cull(const V3& a, const V3& b, con
     out4[0] = I.x; out4[1] = I.y; out4[2] = I.z; out4[3] = r2;
 }
 
+// The record is STORED in single precision (16 bytes: one 128-bit load per candidate, twice as many spheres per cache line):
+// centre rounded to float, radius grown by the ACTUAL rounding error of the centre |C - Cf| (evaluated in double, padded) and r^2
+// rounded up, so the stored sphere contains the double-precision one: still conservative.
+// The test itself stays in double.
+__host__ __device__ __forceinline__ float4 pack_cull(const double* c4) {
+    const float cx = (float)c4[0], cy = (float)c4[1], cz = (float)c4[2];
+    const double ex = c4[0] - (double)cx, ey = c4[1] - (double)cy, ez = c4[2] - (double)cz;
+    const double r = sqrt(c4[3]) + sqrt(ex * ex + ey * ey + ez * ez) * (1.0 + 1e-9) + 1e-9;   // +inf stays +inf (degenerate: never culled)
+    const double r2 = r * r * (1.0 + 1e-6);
+    float r2f = (float)r2;
+    if ((double)r2f < r2) r2f = nextafterf(r2f, INFINITY);
+    return make_float4(cx, cy, cz, r2f);
+}
+__device__ __forceinline__ bool cull_keep_f4(const float4& c, const V3& pt, double pp) {
+    const double cx = (double)c.x, cy = (double)c.y, cz = (double)c.z;
+    const double x = __fma_rn(cy, pt.z, -(cz * pt.y));
+    const double y = __fma_rn(cz, pt.x, -(cx * pt.z));
+    const double z = __fma_rn(cx, pt.y, -(cy * pt.x));
+    const double d2 = __fma_rn(x, x, __fma_rn(y, y, z * z));
+    return !(d2 > (double)c.w * pp);     // written so that NaN keeps the triangle
+}
+
 // keep the triangle iff the line through the origin and pt may touch the sphere:  |C x pt|^2 <= r^2 |pt|^2
 __device__ __forceinline__ bool cull_keep_loaded(const double2& c01, const double2& c23, const V3& pt, double pp) {
     const double x = __fma_rn(c01.y, pt.z, -(c23.x * pt.y));

@@ -119,7 +119,7 @@ msmgpu_status exclusive_scan_i32(const int* d_in, int* d_out, int n, int* d_tota
 // per-triangle tables
 // ------------------------------------------------------------------------------------------
 struct TableJob {
-    const double* xyz; const int* tri; TriRec* rec; double* aabb; double* cull; int nt;
+    const double* xyz; const int* tri; TriRec* rec; double* aabb; float4* cull; int nt;
 };
 
 __global__ void __launch_bounds__(256) k_mesh_tables(const TableJob* __restrict__ jobs) {
@@ -148,8 +148,7 @@ __global__ void __launch_bounds__(256) k_mesh_tables(const TableJob* __restrict_
     job.rec[t] = r;
     double c4[4];
     make_cull(V3{cv[0], cv[1], cv[2]}, V3{cv[3], cv[4], cv[5]}, V3{cv[6], cv[7], cv[8]}, c4);
-    reinterpret_cast<double2*>(job.cull)[2 * (size_t)t] = make_double2(c4[0], c4[1]);
-    reinterpret_cast<double2*>(job.cull)[2 * (size_t)t + 1] = make_double2(c4[2], c4[3]);
+    job.cull[t] = pack_cull(c4);
 }
 
 // per-triangle tables of every mesh whose coordinates changed since they were last computed, in ONE launch

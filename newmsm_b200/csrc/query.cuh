@@ -50,7 +50,7 @@ __device__ __forceinline__ int nearest_triangle(const TreeView& T, const V3& pt,
         }
         parent = nd.w;
         // octree.cpp:172-178, in two phases so that the expensive test runs on few, well-packed lanes:
-        // (1) cull: one 32-byte sphere test per candidate, survivors recorded in a bit mask
+        // (1) cull: one 16-byte sphere test per candidate, survivors recorded in a bit mask
         //     (bit j = this lane's j-th candidate, i = gl + j*G);
         // (2) the reference's full test (projection, 3 same-side tests, boundary distance) for survivors, in
         //     ascending scan position, so "first strictly smaller distance wins" is preserved.
@@ -71,16 +71,12 @@ __device__ __forceinline__ int nearest_triangle(const TreeView& T, const V3& pt,
                 for (int u = 0; u < 4; ++u) t[u] = tn[u];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) tn[u] = j0 + 4 + u < fast ? __ldg(list + gl + (j0 + 4 + u) * G) : 0;
-                double2 c01[4], c23[4];
+                float4 cs[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const double2* cp = reinterpret_cast<const double2*>(T.cull + 4 * (size_t)t[u]);
-                    c01[u] = __ldg(cp);
-                    c23[u] = __ldg(cp + 1);
-                }
+                for (int u = 0; u < 4; ++u) cs[u] = __ldg(T.cull + t[u]);
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
-                    if (j0 + u < fast && cull_keep_loaded(c01[u], c23[u], pt, pp)) keep |= 1ull << (j0 + u);
+                    if (j0 + u < fast && cull_keep_f4(cs[u], pt, pp)) keep |= 1ull << (j0 + u);
             }
         }
         // (2a) containment (projection + 3 same-side tests) for the survivors; (2b) the boundary distance only for the triangles
@@ -103,7 +99,7 @@ __device__ __forceinline__ int nearest_triangle(const TreeView& T, const V3& pt,
         for (int j = 64; j < mine; ++j) {                     // oversized leaves (split refused, octree.cpp:102): no mask
             const int i = gl + j * G;
             const int t = __ldg(list + i);
-            if (!cull_keep(T.cull + 4 * (size_t)t, pt, pp)) continue;
+            if (!cull_keep_f4(__ldg(T.cull + t), pt, pp)) continue;
             const double d = rec_distance(pt, T.rec + t);
             if (d > kNotInTriangle && d < best_d) { best_d = d; best_pos = i; best_t = t; }
         }
@@ -120,7 +116,7 @@ __device__ __forceinline__ int nearest_triangle(const TreeView& T, const V3& pt,
                 const int4 ch = __ldg(T.nodes + first_child + c);
                 for (int i = gl; i < ch.z; i += G) {
                     const int t = __ldg(T.pairs + ch.y + i);
-                    if (!cull_keep(T.cull + 4 * (size_t)t, pt, vdot(pt, pt))) continue;
+                    if (!cull_keep_f4(__ldg(T.cull + t), pt, vdot(pt, pt))) continue;
                     const double d = rec_distance(pt, T.rec + t);
                     if (d > kNotInTriangle && d < best_d) { best_d = d; best_pos = base + i; best_t = t; }
                 }
