@@ -30,7 +30,8 @@ def build(ref: bool | None = None) -> None:
     if ref:
         subprocess.run(["make", "-s", "-j8", "-C", _HERE, "ref", "refmr"], check=True)
         if os.path.exists(os.path.join(os.path.dirname(_HERE), "newmsm_b200", "lib", "libmsmgpu.so")):
-            subprocess.run(["make", "-s", "-C", _HERE, "adapter_check"], check=True)   # in-process drop-in check (C++ adapter)
+            # in-process drop-in check (C++ adapter) and the reference program linked with the GPU library (integration/_build/)
+            subprocess.run(["make", "-s", "-j8", "-C", _HERE, "adapter_check", "newmsm_gpu"], check=True)
 
 
 def have_ref() -> bool:

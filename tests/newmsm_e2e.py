@@ -1,9 +1,10 @@
 """End-to-end `newmsm` on a synthetic case: the UNMODIFIED reference CLI on the host cores (oracle/_ref/newmsm_ref_trace) against
-the same CLI with libmsmgpu.so bound in at link time (oracle/_ref/newmsm_gpu, integration/newmsm_gpu_hooks.cpp).
+the same CLI with libmsmgpu.so bound in at link time (integration/_build/newmsm_gpu, integration/newmsm_gpu_hooks.cpp).
+TEST / MEASUREMENT INFRASTRUCTURE: it executes the compiled reference under oracle/_ref as the checker and CPU baseline.
 Compares the solver's labeling and the control-point grid after every discrete iteration (exact) and the final sphere.reg,
 and reports the wall-clock of both. BASELINE.json metric (iii): "newmsm wall-time vs CPU cores".
 
-    python tools/newmsm_e2e.py --level 6 --config MSMAllStrain --D 40 --threads 16 --out gpurun_out/e2e_cfg3.json
+    python tests/newmsm_e2e.py --level 6 --config MSMAllStrain --D 40 --threads 16 --out gpurun_out/e2e_cfg3.json
 """
 import argparse
 import json
@@ -17,7 +18,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.path.join(ROOT, "oracle", "_ref", "newmsm_ref_trace")
-GPU = os.path.join(ROOT, "oracle", "_ref", "newmsm_gpu")
+GPU = os.path.join(ROOT, "integration", "_build", "newmsm_gpu")
 
 
 def parse_trace(path):
@@ -61,7 +62,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--level", type=int, default=6)
     ap.add_argument("--D", type=int, default=1)
-    ap.add_argument("--config", default="MSMpair", choices=["MSMpair", "MSMAllStrain"])
+    ap.add_argument("--config", default="MSMpair", choices=["MSMpair", "MSMAllStrain", "MSMstrain", "sMSMSTRcp5"])
     ap.add_argument("--levels-drop", type=int, default=0)
     ap.add_argument("--it-scale", type=float, default=1.0)
     ap.add_argument("--threads", type=int, default=os.cpu_count())

@@ -22,6 +22,15 @@ CONFIGS = {
     "MSMAllStrain": ["--simval=2,2,2", "--sigma_in=0,0,0", "--sigma_ref=0,0,0", "--lambda=0.00001,0.0075,0.01", "--it=10,15,15",
                      "--opt=DISCRETE,DISCRETE,DISCRETE", "--CPgrid=2,3,4", "--SGgrid=4,5,6", "--datagrid=4,5,6", "--regoption=3", "--regexp=2",
                      "--dopt=HOCR", "--VN", "--rescaleL", "--triclique", "--k_exponent=2", "--bulkmod=1.6", "--shearmod=0.4"],
+    # config/basic_configs/config_standard_MSM_strain without the AFFINE level (HOCR, univariate unary costs + strain triplets)
+    "MSMstrain": ["--simval=2,2,2", "--sigma_in=4,2,1", "--sigma_ref=4,2,1", "--lambda=0.2,0.2,0.2", "--it=20,25,25", "--opt=DISCRETE,DISCRETE,DISCRETE",
+                  "--CPgrid=2,3,4", "--SGgrid=4,5,6", "--datagrid=5,5,6", "--regoption=3", "--regexp=2", "--dopt=HOCR", "--VN", "--k_exponent=2",
+                  "--bulkmod=1.6", "--shearmod=0.4", "--rescaleL"],
+    # BASELINE configs[3]: NeuroImage2017 sMSM_STR semantics on ONE level with an ico5 control grid, ico6 data, ico7 sampling grid
+    # (SURVEY §8d cfg4): 10 242 control points, 20 480 triplets
+    "sMSMSTRcp5": ["--simval=2", "--sigma_in=2", "--sigma_ref=2", "--lambda=0.025", "--it=40", "--opt=DISCRETE", "--CPgrid=5", "--SGgrid=7",
+                   "--datagrid=6", "--regoption=3", "--regexp=2", "--dopt=HOCR", "--VN", "--rescaleL", "--triclique", "--k_exponent=2",
+                   "--bulkmod=1.6", "--shearmod=0.4"],
 }
 
 
@@ -38,10 +47,10 @@ def scaled(cfg_lines, levels_drop, it_scale):
     """drop the finest `levels_drop` levels / shrink the iteration counts (for quick smoke cases)"""
     out = []
     for ln in cfg_lines:
-        if "=" in ln and "," in ln:
+        if "=" in ln and ("," in ln or ln.startswith("--it=")):
             k, v = ln.split("=")
             vals = v.split(",")
-            if levels_drop:
+            if levels_drop and len(vals) > levels_drop:
                 vals = vals[:-levels_drop]
             if k == "--it":
                 vals = [str(max(1, int(round(int(x) * it_scale)))) for x in vals]
