@@ -283,11 +283,16 @@ def run_ours(a):
             fp = (capi.C.c_void_p * n)(*[d_feat[s_].data_ptr() for s_ in g])
             ob = (capi.C.c_void_p * n)(*[d_out_b[s_].data_ptr() for s_ in g])
             oa = (capi.C.c_void_p * n)(*[d_out_a[s_].data_ptr() for s_ in g])
-            capi.check(L.msmgpu_bary_resample_batch_f32_dev(cx.h, n, tree_ptrs, n_low, capi.ptr(d_low_xyz), D, fp, ob, d_status_g[w].data_ptr()))
+            # both methods need get_barycentric_weights(targets, subject): the fused resample keeps its weight maps and the adaptive
+            # weights consume them (msmgpu.h: msmgpu_fwd) instead of querying the same points in the same trees again
+            fwd = capi.C.c_void_p()
+            capi.check(L.msmgpu_fwd_create(cx.h, n, n_low, capi.C.byref(fwd)))
+            capi.check(L.msmgpu_bary_resample_batch_f32_dev_keep(cx.h, n, tree_ptrs, n_low, capi.ptr(d_low_xyz), D, fp, ob, d_status_g[w].data_ptr(), fwd))
             if ev: ev[2].record(st)
             mesh_ptrs = (capi.C.c_void_p * n)(*[m.h.value for m in meshes])
             w_ptrs = (capi.C.c_void_p * n)()
-            capi.check(L.msmgpu_adaptive_weights_batch(cx.h, n, mesh_ptrs, tree_ptrs, low.h, low_tree.h, w_ptrs))
+            capi.check(L.msmgpu_adaptive_weights_batch_fwd(cx.h, n, mesh_ptrs, tree_ptrs, low.h, low_tree.h, fwd, w_ptrs))
+            L.msmgpu_fwd_destroy(fwd)
             ws = [R.Weights(L, capi.C.c_void_p(w_ptrs[i])) for i in range(n)]
             if ev: ev[3].record(st)
             capi.check(L.msmgpu_weights_apply_batch_f32_dev(cx.h, n, w_ptrs, D, fp, oa))

@@ -42,6 +42,7 @@ typedef struct msmgpu_mesh msmgpu_mesh;       /* device-resident vertices/faces 
 typedef struct msmgpu_octree msmgpu_octree;   /* flattened octree of one mesh */
 typedef struct msmgpu_weights msmgpu_weights; /* device CSR resampling matrix */
 typedef struct msmgpu_costfn msmgpu_costfn;   /* device state of one DiscreteCostFunction */
+typedef struct msmgpu_fwd msmgpu_fwd;         /* barycentric weight maps of a batch of subjects, kept on the device */
 
 const char* msmgpu_last_error(void);
 const char* msmgpu_version(void);
@@ -144,6 +145,18 @@ msmgpu_status msmgpu_bary_resample_f32_dev(msmgpu_octree* t, int n, const double
 msmgpu_status msmgpu_bary_resample_batch_f32_dev(msmgpu_ctx* ctx, int n_subjects, msmgpu_octree* const* trees, int n, const double* d_pts,
                                                  int D, const float* const* d_feat_in, float* const* d_feat_out, int32_t* d_status);
 /* host buffers, FP32 payload, channel-major like Mesh::pvalues: feat_in [D][nv] float -> feat_out [D][n] float */
+/* A batch job that runs BOTH resampling methods on the same (subjects, targets) computes get_barycentric_weights(targets, subject)
+ * twice in the reference: once for the barycentric resample (resampler.cpp:142) and once as the `forward` half of
+ * get_adaptive_barycentric_weights (resampler.cpp:74-75). The _keep variant of the fused resample stores those maps (3 ids, 3 weights,
+ * entry count per target) and msmgpu_adaptive_weights_batch_fwd consumes them instead of querying again: same values, one query pass.
+ * The store must have been filled for exactly these trees and for targets = the vertices of low_mesh (shape and trees are checked). */
+msmgpu_status msmgpu_fwd_create(msmgpu_ctx* ctx, int n_subjects, int n, msmgpu_fwd** out);
+void msmgpu_fwd_destroy(msmgpu_fwd* f);
+msmgpu_status msmgpu_bary_resample_batch_f32_dev_keep(msmgpu_ctx* ctx, int n_subjects, msmgpu_octree* const* trees, int n, const double* d_pts,
+                                                      int D, const float* const* d_feat_in, float* const* d_feat_out, int32_t* d_status,
+                                                      msmgpu_fwd* keep);
+msmgpu_status msmgpu_adaptive_weights_batch_fwd(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* in_meshes, msmgpu_octree* const* in_trees,
+                                                msmgpu_mesh* low_mesh, msmgpu_octree* low_tree, const msmgpu_fwd* fwd, msmgpu_weights** out);
 msmgpu_status msmgpu_bary_resample_f32(msmgpu_octree* t, int n, const double* pts, int D, const float* feat_in, float* feat_out);
 /* the same two resamplers on the mesh's resident features: only the result crosses PCIe. feat_out channel-major [D][n] floats */
 msmgpu_status msmgpu_mesh_bary_resample_f32(msmgpu_octree* t, int n, const double* pts, float* feat_out);

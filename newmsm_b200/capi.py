@@ -86,6 +86,10 @@ _SIGNATURES = {
     "msmgpu_costfn_destroy": (None, [_vp]),
     "msmgpu_costfn_reset_source": (_i, [_vp, _vp]),
     "msmgpu_costfn_set_percentile": (_i, [_vp, _d]),
+    "msmgpu_fwd_create": (_i, [_vp, _i, _i, _pp]),
+    "msmgpu_fwd_destroy": (None, [_vp]),
+    "msmgpu_bary_resample_batch_f32_dev_keep": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
+    "msmgpu_adaptive_weights_batch_fwd": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "msmgpu_costfn_set_cpgrid": (_i, [_vp, _i, _vp, _vp, _d, _i, _vp, _vp]),
     "msmgpu_costfn_patches": (_i, [_vp, _vp, _vp]),
     "msmgpu_costfn_unary_table": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),

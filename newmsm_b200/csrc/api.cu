@@ -375,16 +375,43 @@ msmgpu_status msmgpu_bary_weights(msmgpu_octree* t, int n, const double* pts, in
     return finish_queries(d_st.p, n, nullptr, s);
 }
 
+msmgpu_status msmgpu_fwd_create(msmgpu_ctx* ctx, int n_subjects, int n, msmgpu_fwd** out) {
+    if (!ctx || n_subjects <= 0 || n <= 0 || !out) return fail(MSMGPU_ERR_INVALID, "fwd_create: bad arguments");
+    MSM_CUDA(cudaSetDevice(ctx->device));
+    std::unique_ptr<msmgpu_fwd> f(new msmgpu_fwd());
+    f->ctx = ctx; f->S = n_subjects; f->n = n;
+    MSM_CUDA(f->idx.alloc(3 * (size_t)n_subjects * n, ctx->stream));
+    MSM_CUDA(f->w.alloc(3 * (size_t)n_subjects * n, ctx->stream));
+    MSM_CUDA(f->ne.alloc((size_t)n_subjects * n, ctx->stream));
+    *out = f.release();
+    return MSMGPU_OK;
+}
+
+void msmgpu_fwd_destroy(msmgpu_fwd* f) {
+    if (!f) return;
+    cudaSetDevice(f->ctx->device);
+    delete f;
+}
+
 msmgpu_status msmgpu_bary_resample_batch_f32_dev(msmgpu_ctx* ctx, int n_subjects, msmgpu_octree* const* trees, int n, const double* d_pts,
                                                  int D, const float* const* d_feat_in, float* const* d_feat_out, int32_t* d_status) {
+    return msmgpu_bary_resample_batch_f32_dev_keep(ctx, n_subjects, trees, n, d_pts, D, d_feat_in, d_feat_out, d_status, nullptr);
+}
+
+msmgpu_status msmgpu_bary_resample_batch_f32_dev_keep(msmgpu_ctx* ctx, int n_subjects, msmgpu_octree* const* trees, int n, const double* d_pts,
+                                                      int D, const float* const* d_feat_in, float* const* d_feat_out, int32_t* d_status,
+                                                      msmgpu_fwd* keep) {
     if (!ctx || n_subjects <= 0 || !trees || n < 0 || D <= 0 || !d_feat_in || !d_feat_out || (n > 0 && !d_pts))
         return fail(MSMGPU_ERR_INVALID, "bary_resample_batch: bad arguments");
+    if (keep && (keep->ctx != ctx || keep->S != n_subjects || keep->n != n)) return fail(MSMGPU_ERR_INVALID, "bary_resample_batch: weight store of another shape");
     MSM_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     std::vector<ResampleJob> jobs(n_subjects);
+    if (keep) { keep->trees.assign(trees, trees + n_subjects); keep->filled = true; }
     for (int i = 0; i < n_subjects; ++i) {
         if (!trees[i] || trees[i]->mesh->ctx != ctx) return fail(MSMGPU_ERR_INVALID, "bary_resample_batch: tree from another context");
-        jobs[i] = ResampleJob{trees[i]->view(), d_feat_in[i], d_feat_out[i]};
+        jobs[i] = ResampleJob{trees[i]->view(), d_feat_in[i], d_feat_out[i], keep ? keep->idx.p + 3 * (size_t)i * n : nullptr,
+                              keep ? keep->w.p + 3 * (size_t)i * n : nullptr, keep ? keep->ne.p + (size_t)i * n : nullptr};
     }
     DevBuf<ResampleJob> d_jobs;
     MSM_CUDA(d_jobs.alloc(n_subjects, s));

@@ -113,7 +113,18 @@ struct msmgpu_octree {
     msmgpu_mesh* mesh = nullptr;
     msm::TreeView view() const {
         return msm::TreeView{forest->nodes.p, forest->pairs.p, mesh->rec.p, mesh->cull.p, mesh->tri.p, root};
+
     }
+};
+
+// forward barycentric weights of a batch, produced by the fused resample and consumed by the adaptive weights
+struct msmgpu_fwd {
+    msmgpu_ctx* ctx = nullptr;
+    int S = 0, n = 0;
+    bool filled = false;
+    msm::DevBuf<int> idx, ne;     // [S][n][3], [S][n]
+    msm::DevBuf<double> w;        // [S][n][3]
+    std::vector<const msmgpu_octree*> trees;   // the trees the weights were computed in (checked by the consumer)
 };
 
 // CSR storage shared by the weight matrices of one batch (one allocation, one set of launches)
@@ -157,7 +168,11 @@ struct ResampleJob {      // one subject of a batched fused resample
     TreeView tree;
     const float* feat_in;   // [nv][D]
     float* feat_out;        // [n][D]
+    int* keep_idx;          // optional [n][3] / [n][3] / [n]: the barycentric weight maps of this subject's targets, kept for
+    double* keep_w;         // msmgpu_adaptive_weights_batch_fwd (same values get_barycentric_weights would recompute)
+    int* keep_ne;
 };
+
 msmgpu_status launch_bary_resample_f32(const ResampleJob* d_jobs, int n_jobs, int n, const double* d_pts, int D, int* d_status, cudaStream_t s);
 
 msmgpu_status exclusive_scan_i32(const int* d_in, int* d_out, int n, int* d_total, cudaStream_t s);

@@ -170,6 +170,11 @@ __global__ void __launch_bounds__(kResThreads, MINB) k_bary_resample_f32(const R
             for (int j = 0; j < 3; ++j) { s_idx[3 * q + j] = idx[j]; s_w[3 * q + j] = w[j]; }
             s_ne[q] = ne;
             if (active && out_status) out_status[(size_t)blockIdx.y * n + k] = st;
+            if (active && job.keep_idx) {   // hand the weight map to the adaptive-weights pass of the same batch
+#pragma unroll
+                for (int j = 0; j < 3; ++j) { job.keep_idx[3 * (size_t)k + j] = idx[j]; job.keep_w[3 * (size_t)k + j] = w[j]; }
+                job.keep_ne[k] = ne;
+            }
         }
     }
     __syncwarp();

@@ -170,19 +170,25 @@ __device__ __forceinline__ int sorted_weights(const TreeView& T, int t, const V3
     const double Ab = tri_area(PP, v1, v3);
     const double Ac = tri_area(PP, v1, v2);
     const double A = Aa + Ab + Ac;
-    int id[3] = {__ldg(T.tri + 3 * (size_t)t), __ldg(T.tri + 3 * (size_t)t + 1), __ldg(T.tri + 3 * (size_t)t + 2)};
-    double ww[3] = {Aa / A, Ab / A, Ac / A};
-    int n = 0;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {   // insert (id[k], ww[k]) into the sorted list
-        int j = 0;
-        while (j < n && idx[j] < id[k]) ++j;
-        if (j < n && idx[j] == id[k]) { w[j] = ww[k]; continue; }
-        for (int m = n; m > j; --m) { idx[m] = idx[m - 1]; w[m] = w[m - 1]; }
-        idx[j] = id[k]; w[j] = ww[k];
-        ++n;
-    }
-    for (int j = n; j < 3; ++j) { idx[j] = -1; w[j] = 0.0; }
+    const int i0 = __ldg(T.tri + 3 * (size_t)t), i1 = __ldg(T.tri + 3 * (size_t)t + 1), i2 = __ldg(T.tri + 3 * (size_t)t + 2);
+    const double w0 = Aa / A, w1 = Ab / A, w2 = Ac / A;
+    // std::map semantics without indexed local arrays (they would live in local memory): assignments in the order 0, 1, 2, a
+    // repeated key keeps the LAST value; then a 3-element sorting network on (key, value), absent entries carry key INT_MAX
+    int ka = i0, kb = INT_MAX, kc = INT_MAX;
+    double va = w0, vb = 0.0, vc = 0.0;
+    if (i1 == ka) va = w1; else { kb = i1; vb = w1; }
+    if (i2 == ka) va = w2; else if (i2 == kb) vb = w2; else { kc = i2; vc = w2; }
+    if (kb == INT_MAX && kc != INT_MAX) { kb = kc; vb = vc; kc = INT_MAX; vc = 0.0; }   // entries are packed: a, b, c
+    auto cswap = [](int& k1, double& v1, int& k2, double& v2) {
+        if (k2 < k1) { const int tk = k1; k1 = k2; k2 = tk; const double tv = v1; v1 = v2; v2 = tv; }
+    };
+    cswap(ka, va, kb, vb);
+    cswap(kb, vb, kc, vc);
+    cswap(ka, va, kb, vb);
+    const int n = 1 + (kb != INT_MAX) + (kc != INT_MAX);
+    idx[0] = ka; w[0] = va;
+    idx[1] = kb != INT_MAX ? kb : -1; w[1] = kb != INT_MAX ? vb : 0.0;
+    idx[2] = kc != INT_MAX ? kc : -1; w[2] = kc != INT_MAX ? vc : 0.0;
     return n;
 }
 

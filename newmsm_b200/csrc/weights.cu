@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(256) k_finish_rows(int n_rows, int n_low, cons
 
 // Builds the S matrices into one shared store; out[s] become views of it.
 msmgpu_status adaptive_weights_build_batch(msmgpu_ctx* ctx, int S, msmgpu_mesh* const* in_meshes, msmgpu_octree* const* in_trees,
-                                           msmgpu_mesh* low_mesh, msmgpu_octree* low_tree, msmgpu_weights** out) {
+                                           msmgpu_mesh* low_mesh, msmgpu_octree* low_tree, msmgpu_weights** out, const msmgpu_fwd* fwd) {
     cudaStream_t s = ctx->stream;
     const int n_low = low_mesh->nv;
     std::vector<int> in_off(S + 1, 0);
@@ -316,16 +316,25 @@ msmgpu_status adaptive_weights_build_batch(msmgpu_ctx* ctx, int S, msmgpu_mesh* 
     MSM_CUDA(d_in_off.alloc(S + 1, s));
     MSM_CUDA(cudaMemcpyAsync(d_jobs.p, jobs.data(), jobs.size() * sizeof(QueryJob), cudaMemcpyHostToDevice, s));
     MSM_CUDA(cudaMemcpyAsync(d_in_off.p, in_off.data(), (S + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
-    DevBuf<int> fidx, fne, ridx, rne, st;
-    DevBuf<double> fw, rw;
-    MSM_CUDA(fidx.alloc(3 * (size_t)NL, s));
-    MSM_CUDA(fw.alloc(3 * (size_t)NL, s));
-    MSM_CUDA(fne.alloc((size_t)NL, s));
+    // forward weights: computed here, or taken from the fused barycentric resample of the same batch (identical values)
+    DevBuf<int> fidx_own, fne_own, ridx, rne, st;
+    DevBuf<double> fw_own, rw;
+    struct { const int* p; } fidx, fne;
+    struct { const double* p; } fw;
+    if (fwd) {
+        fidx.p = fwd->idx.p; fw.p = fwd->w.p; fne.p = fwd->ne.p;
+    } else {
+        MSM_CUDA(fidx_own.alloc(3 * (size_t)NL, s));
+        MSM_CUDA(fw_own.alloc(3 * (size_t)NL, s));
+        MSM_CUDA(fne_own.alloc((size_t)NL, s));
+        fidx.p = fidx_own.p; fw.p = fw_own.p; fne.p = fne_own.p;
+    }
     MSM_CUDA(ridx.alloc(3 * (size_t)NV, s));
     MSM_CUDA(rw.alloc(3 * (size_t)NV, s));
     MSM_CUDA(rne.alloc((size_t)NV, s));
     MSM_CUDA(st.alloc((size_t)(NL + NV), s));
-    MSM_TRY(launch_bary_weights_batch(d_jobs.p, S, n_low, fidx.p, fw.p, fne.p, st.p, s));
+    if (fwd) MSM_CUDA(cudaMemsetAsync(st.p, 0, (size_t)NL * sizeof(int), s));   // the fused kernel already reported the forward statuses
+    else MSM_TRY(launch_bary_weights_batch(d_jobs.p, S, n_low, fidx_own.p, fw_own.p, fne_own.p, st.p, s));
     MSM_TRY(launch_bary_weights_batch(d_jobs.p + S, S, max_nv, ridx.p, rw.p, rne.p, st.p + NL, s));
     int code = 0;
     MSM_TRY(first_error(st.p, (size_t)(NL + NV), s, &code));   // synchronises: `jobs` / `in_off` may now go
@@ -495,8 +504,8 @@ msmgpu_status msmgpu_mesh_vertex_areas(msmgpu_mesh* m, double* out) {
     return MSMGPU_OK;
 }
 
-msmgpu_status msmgpu_adaptive_weights_batch(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* in_meshes, msmgpu_octree* const* in_trees,
-                                            msmgpu_mesh* low_mesh, msmgpu_octree* low_tree, msmgpu_weights** out) {
+msmgpu_status msmgpu_adaptive_weights_batch_fwd(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* in_meshes, msmgpu_octree* const* in_trees,
+                                                msmgpu_mesh* low_mesh, msmgpu_octree* low_tree, const msmgpu_fwd* fwd, msmgpu_weights** out) {
     if (!ctx || n <= 0 || !in_meshes || !low_mesh || !out || low_mesh->ctx != ctx) return fail(MSMGPU_ERR_INVALID, "adaptive_weights_batch: bad arguments");
     MSM_CUDA(cudaSetDevice(ctx->device));
     for (int i = 0; i < n; ++i) out[i] = nullptr;
@@ -519,7 +528,17 @@ msmgpu_status msmgpu_adaptive_weights_batch(msmgpu_ctx* ctx, int n, msmgpu_mesh*
     size_t k = 0;
     for (int i = 0; i < n; ++i) trees[i] = (in_trees && in_trees[i]) ? in_trees[i] : built[k++];
     if (!low_tree) low_tree = built[k++];
-    return adaptive_weights_build_batch(ctx, n, in_meshes, trees.data(), low_mesh, low_tree, out);
+    if (fwd) {
+        if (fwd->ctx != ctx || !fwd->filled || fwd->S != n || fwd->n != low_mesh->nv) return fail(MSMGPU_ERR_INVALID, "adaptive_weights_batch_fwd: weight store does not match the batch");
+        for (int i = 0; i < n; ++i)
+            if (fwd->trees[i] != trees[i]) return fail(MSMGPU_ERR_INVALID, "adaptive_weights_batch_fwd: weights were computed in other trees");
+    }
+    return adaptive_weights_build_batch(ctx, n, in_meshes, trees.data(), low_mesh, low_tree, out, fwd);
+}
+
+msmgpu_status msmgpu_adaptive_weights_batch(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* in_meshes, msmgpu_octree* const* in_trees,
+                                            msmgpu_mesh* low_mesh, msmgpu_octree* low_tree, msmgpu_weights** out) {
+    return msmgpu_adaptive_weights_batch_fwd(ctx, n, in_meshes, in_trees, low_mesh, low_tree, nullptr, out);
 }
 
 msmgpu_status msmgpu_adaptive_weights_ex(msmgpu_mesh* in_mesh, msmgpu_octree* in_tree, msmgpu_mesh* low_mesh, msmgpu_octree* low_tree,

@@ -234,6 +234,48 @@ def test_adaptive_weights_batch_matches_single(R, oracle_built, meshes):
         assert np.array_equal(o.cpu().numpy().T, ref.astype(np.float32))
 
 
+def test_adaptive_weights_from_kept_forward_maps(R, oracle_built, meshes):
+    """msmgpu_fwd: the weight maps kept by the fused barycentric resample give the same adaptive CSR as querying again."""
+    import ctypes as C
+    import torch
+    L = capi.lib()
+    ctx = R.Context(0)
+    low_xyz, low_tri = synth.rotate_sphere(meshes[4][0], 0.01, 0.02, -0.015), meshes[4][1]
+    S, D = 3, 8
+    src = [R.Mesh(synth.jitter_sphere(meshes[5][0], meshes[5][1], seed=70 + s), meshes[5][1], ctx=ctx) for s in range(S)]
+    low = R.Mesh(low_xyz, low_tri, ctx=ctx)
+    trees = R.Octree.build_batch(src + [low])
+    n_low, nv = len(low_xyz), src[0].nvertices()
+    dev = torch.device("cuda", 0)
+    feat = [torch.randn(nv, D, device=dev) for _ in range(S)]
+    out = [torch.empty(n_low, D, device=dev) for _ in range(S)]
+    d_low = torch.from_numpy(low_xyz).to(dev)
+    tp = (C.c_void_p * S)(*[t.h.value for t in trees[:S]])
+    mp = (C.c_void_p * S)(*[m.h.value for m in src])
+    fp = (C.c_void_p * S)(*[t.data_ptr() for t in feat])
+    op = (C.c_void_p * S)(*[t.data_ptr() for t in out])
+    fwd = C.c_void_p()
+    capi.check(L.msmgpu_fwd_create(ctx.h, S, n_low, C.byref(fwd)))
+    capi.check(L.msmgpu_bary_resample_batch_f32_dev_keep(ctx.h, S, tp, n_low, d_low.data_ptr(), D, fp, op, None, fwd))
+    w1, w2 = (C.c_void_p * S)(), (C.c_void_p * S)()
+    capi.check(L.msmgpu_adaptive_weights_batch_fwd(ctx.h, S, mp, tp, low.h, trees[-1].h, fwd, w1))
+    capi.check(L.msmgpu_adaptive_weights_batch(ctx.h, S, mp, tp, low.h, trees[-1].h, w2))
+    for s in range(S):
+        a, b = R.Weights(L, C.c_void_p(w1[s])), R.Weights(L, C.c_void_p(w2[s]))
+        for x, y in zip(a.csr(), b.csr()):
+            assert np.array_equal(x, y)
+        ref = oracle_built.oracle_adaptive_weights(src[s].xyz, meshes[5][1], low_xyz, low_tri)
+        for x, y in zip(a.csr(), ref):
+            assert np.array_equal(x, y)
+        a.close(); b.close()
+    # a store filled for other trees is refused
+    other = R.Octree.build_batch([src[1], src[0], src[2]])
+    tp2 = (C.c_void_p * S)(*[t.h.value for t in other])
+    w3 = (C.c_void_p * S)()
+    assert L.msmgpu_adaptive_weights_batch_fwd(ctx.h, S, mp, tp2, low.h, trees[-1].h, fwd, w3) != 0
+    L.msmgpu_fwd_destroy(fwd)
+
+
 def test_resident_features_match_host_payload_calls(R, meshes):
     """msmgpu_mesh_set_features_f32 + the two *_mesh_* resamplers give the same floats as the calls that upload per call."""
     import ctypes as C

@@ -61,13 +61,21 @@ def main():
         costs = [M.computePairwiseCostsForLabel(pairs, labeling, l) for l in range(1, L)]
         torch.cuda.synchronize()
         t2 = time.perf_counter()
+        # strain triplets of every subject's control grid (DiscreteGroupCostFunction.cpp:26-52), Fusion's 8 combinations per label
+        ncp = len(cp0)
+        trip = np.concatenate([np.sort(cp_tri + s_ * ncp, axis=1) for s_ in range(S)]).astype(np.int32)
+        orig = np.stack([cp0] * S)
+        tcosts = [M.computeTripletCostsForLabel(cps, orig, rot, labels, trip, labeling, l, 0.2) for l in range(1, L)]
+        t3 = time.perf_counter()
+        run.triplets = (len(trip), t3 - t2, float(np.stack(tcosts).sum()))
         return np.stack(costs), len(pairs), t1 - t0, t2 - t1
 
     costs, P, t_fields, t_pairs = run(dist)
     if rank == 0:
         line = {"demo": "gMSM fields + pair costs", "n_gpus": world, "subjects": S, "labels": L, "channels": D, "data_grid": f"ico{data_level}",
                 "cp_grid": f"ico{cp_level}", "pairs": P, "resamples_per_iteration": S * L, "fields_s": t_fields,
-                "pair_costs_per_s": P * 4 * (L - 1) / t_pairs, "pair_batches_s": t_pairs}
+                "pair_costs_per_s": P * 4 * (L - 1) / t_pairs, "pair_batches_s": t_pairs,
+                "triplets": run.triplets[0], "triplet_costs_per_s": run.triplets[0] * 8 * (L - 1) / run.triplets[1], "triplet_batches_s": run.triplets[1]}
         if world > 1:
             ref, _, tf1, tp1 = run(None)     # unsharded, on this rank alone
             same = np.array_equal(np.nan_to_num(costs, nan=-1.0), np.nan_to_num(ref, nan=-1.0))
