@@ -186,6 +186,48 @@ __global__ void k_bucket_sum(int nkeys, const int* __restrict__ ptr, const doubl
     out[k] = sum;
 }
 
+// Fast path for the vertex areas: a vertex of a surface mesh has a handful of incident triangles, so instead of the generic
+// count / scan / fill / sort pipeline each vertex owns a fixed row of kIncSlots slots. One pass over the triangles stores the
+// (cached) area per triangle and appends the triangle id to its three vertices' rows (atomic cursor, arrival order); a second
+// pass sorts each row by triangle id in registers and sums the areas in that order = mesh.cpp:1275-1283 over tIDbegin..tIDend,
+// which push_triangle fills in ascending triangle id (mesh.cpp:112-118). A vertex with more than kIncSlots triangles raises a flag
+// and the batch falls back to the generic buckets.
+constexpr int kIncSlots = 8;
+__global__ void k_incidence_fill(EmitVertexTriangles e, int* __restrict__ cnt, int* __restrict__ inc, double* __restrict__ tri_area,
+                                 int* __restrict__ overflow) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= e.n_src()) return;
+    const EmitVertexTriangles::Src x = e.load(i);
+    tri_area[i] = x.area;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int v = e.key(x, j);
+        const int slot = atomicAdd(cnt + v, 1);
+        if (slot < kIncSlots) inc[(size_t)v * kIncSlots + slot] = i;   // global triangle index: ascending within a mesh like the local id
+        else *overflow = 1;
+    }
+}
+__global__ void k_incidence_mean(int nkeys, const int* __restrict__ cnt, const int* __restrict__ inc, const double* __restrict__ tri_area,
+                                 double* __restrict__ out) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nkeys) return;
+    const int n = min(cnt[v], kIncSlots);
+    const int4 a = reinterpret_cast<const int4*>(inc)[2 * (size_t)v], b = reinterpret_cast<const int4*>(inc)[2 * (size_t)v + 1];
+    int id[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) if (i >= n) id[i] = INT_MAX;
+#pragma unroll
+    for (int round = 0; round < 8; ++round) {
+#pragma unroll
+        for (int i = round & 1; i + 1 < 8; i += 2)
+            if (id[i] > id[i + 1]) { const int t = id[i]; id[i] = id[i + 1]; id[i + 1] = t; }
+    }
+    double sum = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) if (i < n) sum += __ldg(tri_area + id[i]);
+    out[v] = sum / (double)n;
+}
+
 // vertex areas of a batch of meshes, concatenated: d_out[key_off[s] + v]
 static msmgpu_status vertex_areas_batch(msmgpu_ctx* ctx, int S, msmgpu_mesh* const* meshes, const std::vector<int>& key_off, double* d_out) {
     cudaStream_t s = ctx->stream;
@@ -220,8 +262,28 @@ static msmgpu_status vertex_areas_batch(msmgpu_ctx* ctx, int S, msmgpu_mesh* con
     MSM_CUDA(cudaMemcpyAsync(d_toff.p, h_toff.data(), (S + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
     MSM_CUDA(cudaMemcpyAsync(d_koff.p, key_off.data(), (S + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
     const int total_t = h_toff[S], nkeys = key_off[S];
+    const EmitVertexTriangles emit{d_tri.p, d_rec.p, d_area.p, d_toff.p, d_koff.p, S, total_t};
+    static const bool fast = getenv("MSMGPU_GENERIC_VERTEX_AREAS") == nullptr;
+    if (fast && total_t > 0 && nkeys > 0) {
+        DevBuf<int> cnt, inc, ovf;
+        DevBuf<double> tarea;
+        MSM_CUDA(cnt.alloc((size_t)nkeys, s));
+        MSM_CUDA(inc.alloc((size_t)nkeys * kIncSlots, s));
+        MSM_CUDA(ovf.alloc(1, s));
+        MSM_CUDA(tarea.alloc((size_t)total_t, s));
+        MSM_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)nkeys * sizeof(int), s));
+        MSM_CUDA(cudaMemsetAsync(ovf.p, 0, sizeof(int), s));
+        k_incidence_fill<<<(total_t + 255) / 256, 256, 0, s>>>(emit, cnt.p, inc.p, tarea.p, ovf.p);
+        MSM_LAUNCH_CHECK();
+        k_incidence_mean<<<(nkeys + 255) / 256, 256, 0, s>>>(nkeys, cnt.p, inc.p, tarea.p, d_out);
+        MSM_LAUNCH_CHECK();
+        int h_ovf = 0;
+        MSM_CUDA(cudaMemcpyAsync(&h_ovf, ovf.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        MSM_CUDA(cudaStreamSynchronize(s));
+        if (!h_ovf) return MSMGPU_OK;      // otherwise some vertex has more than kIncSlots triangles: generic path below
+    }
     Buckets B;
-    MSM_TRY(bucketize(EmitVertexTriangles{d_tri.p, d_rec.p, d_area.p, d_toff.p, d_koff.p, S, total_t}, total_t, nkeys, 3 * (size_t)total_t, B, s));
+    MSM_TRY(bucketize(emit, total_t, nkeys, 3 * (size_t)total_t, B, s));
     k_bucket_mean<<<(nkeys + 255) / 256, 256, 0, s>>>(nkeys, B.ptr.p, B.val.p, d_out);
     MSM_LAUNCH_CHECK();
     return MSMGPU_OK;   // (pageable H2D copies are staged before cudaMemcpyAsync returns, the host tables may go)

@@ -234,6 +234,18 @@ def test_adaptive_weights_batch_matches_single(R, oracle_built, meshes):
         assert np.array_equal(o.cpu().numpy().T, ref.astype(np.float32))
 
 
+def test_vertex_areas_high_valence_fallback(R, oracle_built):
+    """Vertex areas (mesh.cpp:1275): the fixed 8-slot incidence rows overflow on a valence-12 vertex and the generic buckets take over."""
+    ring = 12
+    ang = 2 * np.pi * np.arange(ring) / ring
+    xyz = np.concatenate([[[0.0, 0.0, 100.0]], np.stack([30 * np.cos(ang) * (1 + 0.1 * np.sin(3 * ang)), 30 * np.sin(ang), 95 + np.cos(2 * ang)], axis=1)])
+    tri = np.array([[0, 1 + k, 1 + (k + 1) % ring] for k in range(ring)], np.int32)
+    got = R.Mesh(xyz, tri).vertex_areas()
+    assert np.array_equal(got, oracle_built.oracle_vertex_areas(xyz, tri))
+    xyz6, tri6 = synth.icosphere(3)                      # valence 5 / 6: the fast path
+    assert np.array_equal(R.Mesh(xyz6, tri6).vertex_areas(), oracle_built.oracle_vertex_areas(xyz6, tri6))
+
+
 def test_adaptive_weights_from_kept_forward_maps(R, oracle_built, meshes):
     """msmgpu_fwd: the weight maps kept by the fused barycentric resample give the same adaptive CSR as querying again."""
     import ctypes as C
