@@ -214,6 +214,7 @@ static msmgpu_status mesh_create_impl(msmgpu_ctx* ctx, int nv, const double* xyz
     MSM_CUDA(m->tri.alloc(3 * (size_t)nt, s));
     MSM_CUDA(m->rec.alloc((size_t)nt, s));
     MSM_CUDA(m->aabb.alloc(6 * (size_t)nt, s));
+    MSM_CUDA(m->qbox.alloc((size_t)nt, s));
     MSM_CUDA(m->cull.alloc((size_t)nt, s));
     MSM_CUDA(cudaMemcpyAsync(m->xyz.p, xyz, 3 * (size_t)nv * sizeof(double), kind, s));
     if (nt) MSM_CUDA(cudaMemcpyAsync(m->tri.p, tri, 3 * (size_t)nt * sizeof(int), kind, s));

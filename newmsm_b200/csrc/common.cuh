@@ -98,6 +98,7 @@ struct msmgpu_mesh {
     msm::DevBuf<int> tri;      // [nt][3]
     msm::DevBuf<msm::TriRec> rec; // [nt] one 128-byte query record per triangle (gather-free leaf scans)
     msm::DevBuf<double> aabb;  // [nt][6] lo xyz, hi xyz (octree.cpp:46-59)
+    msm::DevBuf<uint4> qbox;   // [nt] the same box on the octree's depth-18 lattice (octree_build.cu: pack_qbox)
     msm::DevBuf<float4> cull;  // [nt] centre + r^2 of the conservative cull sphere (pack_cull)
     msm::DevBuf<float> feat;   // optional resident payload, vertex-major rows [nv][feat_D] (Mesh::pvalues, mesh.h:44)
     int feat_D = 0;

@@ -116,10 +116,46 @@ msmgpu_status exclusive_scan_i32(const int* d_in, int* d_out, int n, int* d_tota
 }
 
 // ------------------------------------------------------------------------------------------
+// Triangle boxes on the octree's own lattice. Every bound the build compares a triangle's AABB with (node lower corner, midpoint,
+// upper corner; node.cpp:79-120) is a line g(k) = -101 + k * 202 / 2^18 of the depth-18 lattice of the root cube, exactly
+// representable in double. For a coordinate x let q = max{k : g(k) <= x} (-1 below the cube, 2^18 at or above its upper face) and
+// e = (g(q) == x). Then  x < g(Q) <=> q < Q  and  x > g(Q) <=> q > Q or (q == Q and not e): the FP64 comparisons of `classify`
+// become integer comparisons with identical outcomes, and the 48-byte AABB gather of the level passes shrinks to 16 bytes
+// (lower corners: q + 1 and e in 20 bits; upper corners only ever appear on the left of '<': q + 1 in 19 bits). Nodes deeper than
+// 17 levels (cells below 1.5e-3 on a radius-100 sphere) use the double-precision path.
+// ------------------------------------------------------------------------------------------
+constexpr int kGridBits = 18;
+constexpr int kGridMaxDepth = kGridBits - 1;
+__host__ __device__ __forceinline__ double grid_line(int k) { return -kBounds + (double)k * (2.0 * kBounds / (double)(1 << kGridBits)); }
+__device__ __forceinline__ int grid_floor(double x, bool& exact) {
+    exact = false;
+    if (!(x >= -kBounds)) return -1;
+    if (x >= kBounds) { exact = x == kBounds; return 1 << kGridBits; }
+    int k = (int)((x + kBounds) / (2.0 * kBounds / (double)(1 << kGridBits)));
+    k = max(0, min(k, (1 << kGridBits) - 1));
+    while (grid_line(k) > x) --k;          // the estimate is off by at most one line
+    while (grid_line(k + 1) <= x) ++k;
+    exact = grid_line(k) == x;
+    return k;
+}
+__device__ __forceinline__ uint4 pack_qbox(const double* lo, const double* hi) {
+    unsigned l[3], h[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        bool e, eh;
+        const int ql = grid_floor(lo[a], e), qh = grid_floor(hi[a], eh);
+        l[a] = ((unsigned)(ql + 1) << 1) | (e ? 1u : 0u);   // 20 bits
+        h[a] = (unsigned)(qh + 1);                           // 19 bits
+    }
+    return make_uint4(l[0] | ((h[0] & 0xfffu) << 20), l[1] | ((h[1] & 0xfffu) << 20), l[2] | ((h[2] & 0xfffu) << 20),
+                      (h[0] >> 12) | ((h[1] >> 12) << 7) | ((h[2] >> 12) << 14));
+}
+
+// ------------------------------------------------------------------------------------------
 // per-triangle tables
 // ------------------------------------------------------------------------------------------
 struct TableJob {
-    const double* xyz; const int* tri; TriRec* rec; double* aabb; float4* cull; int nt;
+    const double* xyz; const int* tri; TriRec* rec; double* aabb; float4* cull; uint4* qbox; int nt;
 };
 
 __global__ void __launch_bounds__(256) k_mesh_tables(const TableJob* __restrict__ jobs) {
@@ -143,6 +179,7 @@ __global__ void __launch_bounds__(256) k_mesh_tables(const TableJob* __restrict_
     }
 #pragma unroll
     for (int a = 0; a < 3; ++a) { job.aabb[6 * (size_t)t + a] = lo[a]; job.aabb[6 * (size_t)t + 3 + a] = hi[a]; }
+    job.qbox[t] = pack_qbox(lo, hi);
     TriRec r;
     make_trirec(V3{cv[0], cv[1], cv[2]}, V3{cv[3], cv[4], cv[5]}, V3{cv[6], cv[7], cv[8]}, r);
     job.rec[t] = r;
@@ -158,7 +195,7 @@ msmgpu_status ensure_tables(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes) 
     for (int i = 0; i < n; ++i) {
         msmgpu_mesh* m = meshes[i];
         if (!m->tables_dirty || m->nt == 0) { m->tables_dirty = false; continue; }
-        jobs.push_back(TableJob{m->xyz.p, m->tri.p, m->rec.p, m->aabb.p, m->cull.p, m->nt});
+        jobs.push_back(TableJob{m->xyz.p, m->tri.p, m->rec.p, m->aabb.p, m->cull.p, m->qbox.p, m->nt});
         max_nt = std::max(max_nt, m->nt);
         m->tables_dirty = false;
     }
@@ -200,6 +237,37 @@ __device__ __forceinline__ void classify(const double* __restrict__ bb, const do
         // node.cpp:112-120 can_contain for the lower / upper child (closed intervals)
         in0[d] = !(thi < b0 || tlo > b1);
         in1[d] = !(thi < b1 || tlo > b2);
+    }
+    a_val = split_size - 3;
+    unsigned m = 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const unsigned x = (c & 4) ? in1[0] : in0[0];
+        const unsigned y = (c & 2) ? in1[1] : in0[1];
+        const unsigned z = (c & 1) ? in1[2] : in0[2];
+        m |= (x & y & z) << c;
+    }
+    child_mask = m;
+}
+
+// `classify` on the lattice (see the note on triangle boxes above): identical decisions, integer compares
+__device__ __forceinline__ void classify_q(const uint4 qb, const int* L0, int Hh, int& a_val, unsigned& child_mask) {
+    int split_size = 8;
+    unsigned in0[3], in1[3];
+    const unsigned w[3] = {qb.x, qb.y, qb.z};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const int B0 = L0[d], B1 = B0 + Hh, B2 = B1 + Hh;
+        const unsigned l20 = w[d] & 0xfffffu;
+        const int qlo = (int)(l20 >> 1) - 1;
+        const bool elo = l20 & 1u;
+        const int qhi = (int)((w[d] >> 20) | (((qb.w >> (7 * d)) & 0x7fu) << 12)) - 1;
+        const bool lo_lt_b1 = qlo < B1, hi_lt_b1 = qhi < B1;
+        if (lo_lt_b1 == hi_lt_b1) split_size >>= 1;
+        const bool lo_gt_b1 = qlo > B1 || (qlo == B1 && !elo);
+        const bool lo_gt_b2 = qlo > B2 || (qlo == B2 && !elo);
+        in0[d] = !(qhi < B0 || lo_gt_b1);
+        in1[d] = !(hi_lt_b1 || lo_gt_b2);
     }
     a_val = split_size - 3;
     unsigned m = 0;
@@ -281,7 +349,8 @@ __device__ __forceinline__ int team_min(int v, int* smem) {
 template <int TPC, int IPT>
 __global__ void __launch_bounds__(TPC == 32 ? 256 : TPC) k_chunk_stats(int node_begin, int n_level, int max_chunks, const int4* __restrict__ nodes,
                                                                         const BuildNode* __restrict__ bn, const int* __restrict__ pairs,
-                                                                        const double* const* __restrict__ mesh_aabb, double root_half,
+                                                                        const double* const* __restrict__ mesh_aabb,
+                                                                        const uint4* const* __restrict__ mesh_qbox, double root_half,
                                                                         int* __restrict__ stats, unsigned char* __restrict__ pmask, int level_base) {
     constexpr int K = TPC * IPT;
     constexpr int TEAMS = TPC == 32 ? 8 : 1;
@@ -299,6 +368,15 @@ __global__ void __launch_bounds__(TPC == 32 ? 256 : TPC) k_chunk_stats(int node_
     const BuildNode b = bn[node_begin + li];
     const double half = ldexp(root_half, -b.depth);
     const double* __restrict__ aabb = mesh_aabb[b.mesh];
+    const uint4* __restrict__ qbox = mesh_qbox[b.mesh];
+    const bool on_grid = b.depth <= kGridMaxDepth;          // uniform over the team
+    int L0[3] = {0, 0, 0}, Hh = 0;
+    if (on_grid) {
+        const double h = 2.0 * kBounds / (double)(1 << kGridBits);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) L0[d] = (int)((b.lo[d] + kBounds) / h);   // exact: the corner is a lattice line
+        Hh = 1 << (kGridMaxDepth - b.depth);
+    }
     const int tl = team_lane<TPC>();
     const int p0 = chunk * K + tl * IPT;
     int a[IPT];
@@ -310,7 +388,9 @@ __global__ void __launch_bounds__(TPC == 32 ? 256 : TPC) k_chunk_stats(int node_
         const int p = p0 + k;
         if (p < cnt) {
             unsigned mask;
-            classify(aabb + 6 * (size_t)__ldg(pairs + nd.y + p), b.lo, half, a[k], mask);
+            const int tid = __ldg(pairs + nd.y + p);
+            if (on_grid) classify_q(__ldg(qbox + tid), L0, Hh, a[k], mask);
+            else classify(aabb + 6 * (size_t)tid, b.lo, half, a[k], mask);
             pmask[(size_t)(nd.y - level_base) + p] = (unsigned char)mask;   // kept for k_scatter_chunk: the 48-byte AABB is gathered once per level, not twice
 #pragma unroll
             for (int c = 0; c < 8; ++c) c8[c] += (mask >> c) & 1u;
@@ -499,11 +579,13 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
     long long total_t = 0;
     std::vector<int> h_nt(n), h_off(n);
     std::vector<const double*> h_aabb(n);
+    std::vector<const uint4*> h_qbox(n);
     for (int i = 0; i < n; ++i) {
         if (!meshes[i] || meshes[i]->ctx != ctx) return fail(MSMGPU_ERR_INVALID, "forest_build: mesh from another context");
         h_nt[i] = meshes[i]->nt;
         h_off[i] = (int)total_t;
         h_aabb[i] = meshes[i]->aabb.p;
+        h_qbox[i] = meshes[i]->qbox.p;
         total_t += meshes[i]->nt;
     }
     // capacities: the sum of list lengths over all levels is ~10x the triangle count on sphere meshes
@@ -518,6 +600,7 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
         F->ctx = ctx;
         DevBuf<BuildNode> bn;
         DevBuf<const double*> d_aabb;
+        DevBuf<const uint4*> d_qbox;
         DevBuf<int> d_nt, d_off;
         MSM_CUDA(F->nodes.alloc(node_cap, s));
         MSM_CUDA(F->pairs.alloc(pair_cap, s));
@@ -529,6 +612,8 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
         MSM_CUDA(F->node_depth.alloc(node_cap, s));
         MSM_CUDA(bn.alloc(node_cap, s));
         MSM_CUDA(d_aabb.alloc(n, s));
+        MSM_CUDA(d_qbox.alloc(n, s));
+        MSM_CUDA(cudaMemcpyAsync(d_qbox.p, h_qbox.data(), n * sizeof(uint4*), cudaMemcpyHostToDevice, s));
         MSM_CUDA(d_nt.alloc(n, s));
         MSM_CUDA(d_off.alloc(n, s));
         MSM_CUDA(cudaMemcpyAsync(d_aabb.p, h_aabb.data(), n * sizeof(double*), cudaMemcpyHostToDevice, s));
@@ -570,11 +655,11 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
             if (max_chunks > 65535) return fail(MSMGPU_ERR_CAPACITY, "forest_build: list too long for the chunk grid");
             const dim3 g_cta((unsigned)n_level, (unsigned)max_chunks), g_warp((unsigned)((n_level + 7) / 8), (unsigned)max_chunks);
             if (K == 8192)
-                k_chunk_stats<1024, 8><<<g_cta, 1024, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_aabb.p, root_half, stats.p, pmask.p, level_base);
+                k_chunk_stats<1024, 8><<<g_cta, 1024, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_aabb.p, d_qbox.p, root_half, stats.p, pmask.p, level_base);
             else if (K == 1024)
-                k_chunk_stats<256, 4><<<g_cta, 256, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_aabb.p, root_half, stats.p, pmask.p, level_base);
+                k_chunk_stats<256, 4><<<g_cta, 256, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_aabb.p, d_qbox.p, root_half, stats.p, pmask.p, level_base);
             else
-                k_chunk_stats<32, 4><<<g_warp, 256, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_aabb.p, root_half, stats.p, pmask.p, level_base);
+                k_chunk_stats<32, 4><<<g_warp, 256, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_aabb.p, d_qbox.p, root_half, stats.p, pmask.p, level_base);
             MSM_LAUNCH_CHECK();
             k_node_combine<<<(n_level + 255) / 256, 256, 0, s>>>(node_begin, n_level, max_chunks, K, F->nodes.p, stats.p, split_flag.p, child_cnt.p);
             MSM_LAUNCH_CHECK();
