@@ -131,7 +131,7 @@ __device__ __forceinline__ int grid_floor(double x, bool& exact) {
     exact = false;
     if (!(x >= -kBounds)) return -1;
     if (x >= kBounds) { exact = x == kBounds; return 1 << kGridBits; }
-    int k = (int)((x + kBounds) / (2.0 * kBounds / (double)(1 << kGridBits)));
+    int k = (int)((x + kBounds) * ((double)(1 << kGridBits) / (2.0 * kBounds)));   // estimate only: corrected against the exact lines below
     k = max(0, min(k, (1 << kGridBits) - 1));
     while (grid_line(k) > x) --k;          // the estimate is off by at most one line
     while (grid_line(k + 1) <= x) ++k;
