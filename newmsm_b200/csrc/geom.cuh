@@ -226,37 +226,39 @@ __device__ __forceinline__ double rec_distance_inside(const V3& pt, const TriRec
 // triangles (n2 = 0, accepted everywhere) get r = +inf and are never culled.
 // ------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ void make_cull(const V3& a, const V3& b, const V3& c, double* out4) {
+    // out4 = centre, RADIUS (not squared: pack_cull adds the float-rounding slack to the radius first).
+    // Only conservativeness matters here, not bit-compatibility with anything: |n2_k| = 2 * area for every edge k, so one cross
+    // product serves all three (the 1e-9 factors cover the rounding differences between the three ways of computing it).
     const double la = vnorm(vsub(b, c)), lb = vnorm(vsub(c, a)), lc = vnorm(vsub(a, b));
     const double per = la + lb + lc;
-    const double n2a = vnorm(vcross(vsub(c, b), vsub(a, b)));   // side (b,c), opposite a
-    const double n2b = vnorm(vcross(vsub(a, c), vsub(b, c)));   // side (c,a), opposite b
-    const double n2c = vnorm(vcross(vsub(b, a), vsub(c, a)));   // side (a,b), opposite c
-    const double lmax = fmax(la, fmax(lb, lc));
+    const double n2 = vnorm(vcross(vsub(b, a), vsub(c, a))) * (1.0 - 1e-9);
+    const double lmax = fmax(la, fmax(lb, lc)), lmin = fmin(la, fmin(lb, lc));
     const double inf = 1.0 / 0.0;
-    double r2 = inf;
+    double r = inf;
     V3 I{0, 0, 0};
-    const double pa = la * n2a, pb = lb * n2b, pc = lc * n2c;
-    if (per > 0 && pa > 0 && pb > 0 && pc > 0) {
+    const double pmin = lmin * n2;
+    if (per > 0 && pmin > 0) {
         I = V3{(la * a.x + lb * b.x + lc * c.x) / per, (la * a.y + lb * b.y + lc * c.y) / per, (la * a.z + lb * b.z + lc * c.z) / per};
-        const double rho = n2c / per;                            // 2 * area / perimeter
-        const double h = (1e-8 / fmin(pa, fmin(pb, pc)) + 1e-12 * (1.0 + lmax)) * 1.000001;
+        const double rho = n2 / per;                             // 2 * area / perimeter (slightly under-estimated: larger lambda)
+        const double h = (1e-8 / pmin + 1e-12 * (1.0 + lmax)) * 1.000001;
         const double lambda = 1.0 + h / rho;
-        const double reach = fmax(vnorm(vsub(a, I)), fmax(vnorm(vsub(b, I)), vnorm(vsub(c, I))));
-        const double r = lambda * reach * (1.0 + 1e-7) + 1e-7;
-        r2 = r * r;
-        if (!(r2 == r2)) r2 = inf;                               // NaN from 0/0 -> never cull
+        const V3 da = vsub(a, I), db = vsub(b, I), dc = vsub(c, I);
+        const double reach = sqrt(fmax(vdot(da, da), fmax(vdot(db, db), vdot(dc, dc)))) * (1.0 + 1e-9);
+        r = lambda * reach * (1.0 + 1e-7) + 1e-7;
+        if (!(r == r)) r = inf;                                  // NaN from 0/0 -> never cull
     }
-    out4[0] = I.x; out4[1] = I.y; out4[2] = I.z; out4[3] = r2;
+    out4[0] = I.x; out4[1] = I.y; out4[2] = I.z; out4[3] = r;
 }
 
 // The record is STORED in single precision (16 bytes: one 128-bit load per candidate, twice as many spheres per cache line):
 // centre rounded to float, radius grown by the ACTUAL rounding error of the centre |C - Cf| (evaluated in double, padded) and r^2
 // rounded up, so the stored sphere contains the double-precision one: still conservative.
-// The test itself stays in double.
+// The test itself stays in double: keep the triangle iff the line through the origin and pt may touch the sphere,
+// |C x pt|^2 <= r^2 |pt|^2.
 __host__ __device__ __forceinline__ float4 pack_cull(const double* c4) {
     const float cx = (float)c4[0], cy = (float)c4[1], cz = (float)c4[2];
     const double ex = c4[0] - (double)cx, ey = c4[1] - (double)cy, ez = c4[2] - (double)cz;
-    const double r = sqrt(c4[3]) + sqrt(ex * ex + ey * ey + ez * ez) * (1.0 + 1e-9) + 1e-9;   // +inf stays +inf (degenerate: never culled)
+    const double r = c4[3] + sqrt(ex * ex + ey * ey + ez * ez) * (1.0 + 1e-9) + 1e-9;   // +inf stays +inf (degenerate: never culled)
     const double r2 = r * r * (1.0 + 1e-6);
     float r2f = (float)r2;
     if ((double)r2f < r2) r2f = nextafterf(r2f, INFINITY);
@@ -269,24 +271,6 @@ __device__ __forceinline__ bool cull_keep_f4(const float4& c, const V3& pt, doub
     const double z = __fma_rn(cx, pt.y, -(cy * pt.x));
     const double d2 = __fma_rn(x, x, __fma_rn(y, y, z * z));
     return !(d2 > (double)c.w * pp);     // written so that NaN keeps the triangle
-}
-
-// keep the triangle iff the line through the origin and pt may touch the sphere:  |C x pt|^2 <= r^2 |pt|^2
-__device__ __forceinline__ bool cull_keep_loaded(const double2& c01, const double2& c23, const V3& pt, double pp) {
-    const double x = __fma_rn(c01.y, pt.z, -(c23.x * pt.y));
-    const double y = __fma_rn(c23.x, pt.x, -(c01.x * pt.z));
-    const double z = __fma_rn(c01.x, pt.y, -(c01.y * pt.x));
-    const double d2 = __fma_rn(x, x, __fma_rn(y, y, z * z));
-    return !(d2 > c23.y * pp);     // written so that NaN keeps the triangle
-}
-__device__ __forceinline__ bool cull_keep(const double* __restrict__ cull4, const V3& pt, double pp) {
-    const double2 c01 = __ldg(reinterpret_cast<const double2*>(cull4));
-    const double2 c23 = __ldg(reinterpret_cast<const double2*>(cull4) + 1);
-    const double x = __fma_rn(c01.y, pt.z, -(c23.x * pt.y));
-    const double y = __fma_rn(c23.x, pt.x, -(c01.x * pt.z));
-    const double z = __fma_rn(c01.x, pt.y, -(c01.y * pt.x));
-    const double d2 = __fma_rn(x, x, __fma_rn(y, y, z * z));
-    return !(d2 > c23.y * pp);     // written so that NaN keeps the triangle
 }
 
 } // namespace msm
