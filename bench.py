@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--target-freq", type=int, default=N_TARGET_FREQ)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-workers", type=int, default=4)
+    ap.add_argument("--e2e-workers", type=int, default=8)
     ap.add_argument("--value-workers", type=int, default=int(os.environ.get("BENCH_VALUE_WORKERS", 1)),
                     help="host threads / CUDA streams the device-resident step is split over (subjects are independent): the "
                          "latency-bound octree builds of one group overlap the bandwidth-bound resampling of another")
