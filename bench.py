@@ -419,9 +419,9 @@ def run_ours(a):
     # DRAM traffic of that kernel per launch from the committed `ncu --set full` capture (bytes per subject x subjects in this launch)
     traffic, traffic_src = None, None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1m_fused_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1u_fused_traffic.json")))
         traffic = float(tr["dram_bytes_per_subject"]) * S
-        traffic_src = "profiles/r1m_fused_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of an 8-subject launch, scaled to %d subjects)" % S
+        traffic_src = "profiles/r1u_fused_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of an 8-subject launch, scaled to %d subjects)" % S
     except Exception:
         pass
     roofline = {"kernel": "k_bary_resample_f32 (fused query + weights + 3-row gather, one launch for the batch)", "bound": "hbm",
