@@ -68,11 +68,15 @@ struct EmitReverse {   // resampler.cpp:91-95: reverse_reorder[target][source] =
     __device__ int id(const Src& x, int) const { return x.local; }
     __device__ double val(const Src& x, int j) const { return rw[3 * (size_t)x.o + j]; }
 };
-struct EmitCsrColumns {   // key = column (source vertex), id = row (target), val = stored value
-    const int* rowptr; const int* col; const double* v; const int* in_off; int n_low; int total;
+struct EmitCsrColumns {   // key = column (source vertex), id = row (target), val = stored value; rows taken from the FORWARD lists only
+    const int* rowptr; const int* col; const double* v; const int* in_off; const int* fne; const int* rr_ptr; int n_low; int total;
     struct Src { int r, b, e, koff; };
     __device__ int n_src() const { return total; }
-    __device__ Src load(int r) const { return Src{r, rowptr[r], rowptr[r + 1], in_off[r / n_low]}; }
+    __device__ Src load(int r) const {
+        const bool reverse_row = rr_ptr[r + 1] - rr_ptr[r] > fne[r];      // such rows are summed straight from the reverse maps (k_area_ratio)
+        const int b = rowptr[r];
+        return Src{r, b, reverse_row ? b : rowptr[r + 1], in_off[r / n_low]};
+    }
     __device__ int count(const Src& x) const { return x.e - x.b; }
     __device__ int key(const Src& x, int j) const { return x.koff + col[x.b + j]; }
     __device__ int id(const Src& x, int) const { return x.r; }
@@ -318,13 +322,39 @@ __global__ void k_fill_rows(int n_rows, int n_low, const int* __restrict__ rowpt
         for (int j = 0; j < r; ++j) { col[o + j] = rr_id[rb + j]; val[o + j] = rr_val[rb + j] * a; }
     }
 }
-// correction[src] = sum of its bucket (ascending target); ratio[src] = oldArea[src] / correction[src] (resampler.cpp:114-123)
-__global__ void k_area_ratio(int nkeys, const int* __restrict__ ptr, const double* __restrict__ val, const double* __restrict__ old_area,
+// correction[src] = sum over the targets whose row holds src, in ascending target order, of the area-scaled weight
+// (resampler.cpp:111-116); ratio[src] = oldArea[src] / correction[src] (resampler.cpp:120-123).
+// A row is either the target's forward list or its transposed reverse list (resampler.cpp:105-109). The reverse-list rows that hold
+// src are exactly the <= 3 targets of src's OWN reverse map (already in ascending target order), so their terms need no transpose;
+// only the forward-list rows go through the column buckets (ptr / id / val, ascending row). The two ascending sequences are merged.
+__global__ void k_area_ratio(int nkeys, int S, int n_low, const int* __restrict__ in_off, const int* __restrict__ ridx,
+                             const double* __restrict__ rw, const int* __restrict__ rne, const int* __restrict__ fne,
+                             const int* __restrict__ rr_ptr, const double* __restrict__ new_area, const int* __restrict__ ptr,
+                             const int* __restrict__ id, const double* __restrict__ val, const double* __restrict__ old_area,
                              double* __restrict__ ratio) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nkeys) return;
+    const int sub = S == 1 ? 0 : find_segment(in_off, S, k);
+    const int row0 = sub * n_low;
+    int an = 0, arow[3];
+    double aval[3];
+    const int ne = rne[k];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        arow[j] = INT_MAX; aval[j] = 0.0;
+        if (j < ne) {
+            const int t = ridx[3 * (size_t)k + j], n = row0 + t;
+            if (rr_ptr[n + 1] - rr_ptr[n] > fne[n]) { arow[an] = n; aval[an] = rw[3 * (size_t)k + j] * new_area[t]; ++an; }
+        }
+    }
     double sum = 0.0;
-    for (int i = ptr[k]; i < ptr[k + 1]; ++i) sum += val[i];
+    int ia = 0, ib = ptr[k];
+    const int eb = ptr[k + 1];
+    while (ia < an || ib < eb) {
+        const int ra = ia < an ? arow[ia] : INT_MAX, rb = ib < eb ? id[ib] : INT_MAX;
+        if (ra < rb) { sum += aval[ia]; ++ia; }
+        else { sum += val[ib]; ++ib; }
+    }
     ratio[k] = old_area[k] / sum;
 }
 // resampler.cpp:120-137: w *= oldArea[src] / correction[src]; then each row normalised to sum 1.
@@ -430,8 +460,10 @@ msmgpu_status adaptive_weights_build_batch(msmgpu_ctx* ctx, int S, msmgpu_mesh* 
 
     // correction[src] = sum over targets (ascending) of the area-scaled weights (resampler.cpp:114-116)
     Buckets cols;
-    MSM_TRY(bucketize(EmitCsrColumns{store->rowptr.p, store->col.p, store->val.p, d_in_off.p, n_low, (int)NL}, (int)NL, (int)NV, cap, cols, s));
-    k_area_ratio<<<(unsigned)((NV + 255) / 256), 256, 0, s>>>((int)NV, cols.ptr.p, cols.val.p, old_area.p, correction.p);   // correction := ratio
+    MSM_TRY(bucketize(EmitCsrColumns{store->rowptr.p, store->col.p, store->val.p, d_in_off.p, fne.p, rr.ptr.p, n_low, (int)NL}, (int)NL, (int)NV,
+                      3 * (size_t)NL, cols, s));
+    k_area_ratio<<<(unsigned)((NV + 255) / 256), 256, 0, s>>>((int)NV, S, n_low, d_in_off.p, ridx.p, rw.p, rne.p, fne.p, rr.ptr.p, new_area.p, cols.ptr.p,
+                                                              cols.id.p, cols.val.p, old_area.p, correction.p);   // correction := ratio
     MSM_LAUNCH_CHECK();
     k_finish_rows<<<(unsigned)((NL * 32 + 255) / 256), 256, 0, s>>>((int)NL, n_low, store->rowptr.p, store->col.p, store->val.p, d_in_off.p, correction.p);
     MSM_LAUNCH_CHECK();
