@@ -13,8 +13,9 @@
 //   * computeTripletCost(t,a,b,c)-> Fusion asks 8 combinations per triplet for one candidate label, from OpenMP workers
 //                                   (Fusion.h:181-196). The first request of a (labeling, label) phase evaluates ALL triplets x 8
 //                                   combinations in one msmgpu_costfn_triplet_batch launch; the others are table look-ups.
-//   * computePairwiseCosts(p)    -> the rotation regulariser table (cpp:190-243) evaluated in parallel on the host (it is
-//                                   libm-bound: estimate_rotation_matrix + acos per entry), identical values.
+//   * computePairwiseCosts(p)    -> the rotation regulariser table (cpp:190-243) evaluated in parallel on the host (libm-bound:
+//                                   acos / pow per entry) with the N*L rotation matrices computed once instead of 2*P*L^2 times,
+//                                   identical values.
 //
 // There is no CPU fallback for the device paths: a failing msmgpu call throws MeshregException with msmgpu_last_error().
 // regoption 4/5 (anatomical strain) are not accelerated: install_gpu_costfunction() leaves the reference's object in place.
@@ -81,21 +82,6 @@ inline std::vector<int32_t> triangles_of(const Mesh& m) {
         for (int k = 0; k < 3; ++k) tri[3 * (size_t)t + k] = m.get_triangle_vertexID(t, k);
     return tri;
 }
-
-// the protected state NonLinearSRegDiscreteCostFunction::computePairwiseCost reads (cpp:190-233), cloned into per-thread workers
-struct PairState {
-    Mesh cp, ocp;
-    std::vector<Point> labels;
-    std::shared_ptr<std::vector<NEWMAT::Matrix>> rot;
-    int* pairs;
-    double mvdmax, lambda, rexp;
-};
-struct PairWorker : newmeshreg::NonLinearSRegDiscreteCostFunction {
-    explicit PairWorker(const PairState& s) {
-        _CPgrid = s.cp; _oCPgrid = s.ocp; _labels = s.labels; ROTATIONS = s.rot; _pairs = s.pairs;
-        MVDmax = s.mvdmax; _reglambda = s.lambda; _rexp = s.rexp;
-    }
-};
 
 struct Timers {   // wall-clock split printed by the integration binary (seconds)
     double source = 0, unary = 0, triplet = 0, pairwise = 0;
@@ -367,22 +353,76 @@ public:
         return tb->val[8 * (size_t)triplet + ((da ? 4 : 0) | (db ? 2 : 0) | (dc ? 1 : 0))];
     }
 
-    // cpp:236-243 runs computePairwiseCost serially because it moves and restores two vertices of the member mesh _CPgrid
-    // (cpp:204-205, 228-229). Each worker here owns a private copy of the cost function's geometry, so the same member function
-    // runs concurrently; every entry is the value the serial loop produces.
+    // The pairwise (regoption 1 / FastPD) table: cost(pair, la, lb) = lambda * (sqrt(2) * theta / theta_MVD)^rexp with theta the angle of
+    // R1^T R2, R1 = estimate_rotation_matrix(CP[n0], ROT[n0] * label[la]), R2 likewise for (n1, lb); FOLDING if a triangle around n0
+    // flips (cpp:190-233). The reference evaluates it serially, entry by entry, through the member mesh (two set_coord + restore per
+    // entry) and recomputes both rotation matrices P * L^2 * 2 times although they only depend on (node, label). Here the N * L
+    // matrices and moved points are computed once (the reference's own estimate_rotation_matrix and operator*), and the table is
+    // filled in parallel with the same expressions in the same order (host libm: acos, pow), so every entry is the reference's value.
     void computePairwiseCosts(const int* pairs) override {
         const double t0 = omp_get_wtime();
-        const int P = this->m_num_pairs, L = (int)this->_labels.size(), LL = this->m_num_labels;
+        const int P = this->m_num_pairs, L = (int)this->_labels.size(), LL = this->m_num_labels, N = this->_CPgrid.nvertices();
         int nthreads = omp_get_max_threads();
         if (const char* e = std::getenv("MSMGPU_HOST_THREADS")) nthreads = std::max(1, std::atoi(e));
-        detail::PairState st{this->_CPgrid, this->_oCPgrid, this->_labels, this->ROTATIONS, this->_pairs, this->MVDmax, this->_reglambda, this->_rexp};
-        #pragma omp parallel num_threads(nthreads)
-        {
-            detail::PairWorker w(st);
-            #pragma omp for schedule(dynamic, 8)
-            for (int i = 0; i < P; ++i)
-                for (int j = 0; j < L; ++j)
-                    for (int k = 0; k < L; ++k) this->paircosts[i * LL * LL + k * LL + j] = w.computePairwiseCost(i, j, k);
+        const Mesh& G = this->_CPgrid;
+        std::vector<Point> cp((size_t)N), moved((size_t)N * L);
+        std::vector<double> R((size_t)N * L * 9);
+        #pragma omp parallel for num_threads(nthreads)
+        for (int n = 0; n < N; ++n) {
+            cp[n] = G.get_coord(n);
+            for (int l = 0; l < L; ++l) {
+                const Point q = (*this->ROTATIONS)[n] * this->_labels[l];
+                moved[(size_t)n * L + l] = q;
+                const NEWMAT::Matrix M = newresampler::estimate_rotation_matrix(cp[n], q);
+                for (int r = 0; r < 3; ++r)
+                    for (int c = 0; c < 3; ++c) R[((size_t)n * L + l) * 9 + 3 * r + c] = M(r + 1, c + 1);
+            }
+        }
+        const int T = G.ntriangles();
+        std::vector<int> tv(3 * (size_t)T);
+        std::vector<Point> onormal((size_t)T);
+        for (int t = 0; t < T; ++t) {
+            for (int k = 0; k < 3; ++k) tv[3 * (size_t)t + k] = G.get_triangle_vertexID(t, k);
+            onormal[t] = this->_oCPgrid.get_triangle(t).normal();
+        }
+        const double theta_MVD = 2 * asin(this->MVDmax / (2 * RAD));
+        const double lambda = this->_reglambda, rexp = this->_rexp;
+        #pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads)
+        for (int i = 0; i < P; ++i) {
+            const int n0 = this->_pairs[2 * i], n1 = this->_pairs[2 * i + 1];
+            const std::vector<int> around(G.tIDbegin(n0), G.tIDend(n0));
+            for (int j = 0; j < L; ++j)
+                for (int k = 0; k < L; ++k) {
+                    const double* R1 = &R[((size_t)n0 * L + j) * 9];
+                    const double* R2 = &R[((size_t)n1 * L + k) * 9];
+                    // Trace of R1.t() * R2 with the matrix product's own summation order (left to right from 0)
+                    double trace = 0.0;
+                    for (int d = 0; d < 3; ++d) {
+                        double sum = 0.0;
+                        for (int m = 0; m < 3; ++m) sum += R1[3 * m + d] * R2[3 * m + d];
+                        trace += sum;
+                    }
+                    double cost = 0.0;
+                    if (fabs(1 - (trace - 1) / 2) > EPSILON) {
+                        const Point& p0 = moved[(size_t)n0 * L + j];
+                        const Point& p1 = moved[(size_t)n1 * L + k];
+                        auto at = [&](int v) -> const Point& { return v == n0 ? p0 : (v == n1 ? p1 : cp[v]); };
+                        bool folded = false;
+                        for (int t : around) {
+                            const Point &a = at(tv[3 * (size_t)t]), &b = at(tv[3 * (size_t)t + 1]), &c = at(tv[3 * (size_t)t + 2]);
+                            Point nrm = (c - a) * (b - a);          // Triangle::normal (triangle.cpp:42-47)
+                            nrm.normalize();
+                            if ((onormal[t] | nrm) < 0.0) { folded = true; break; }
+                        }
+                        if (folded) cost = FOLDING;
+                        else {
+                            const double theta = acos((trace - 1) / 2);
+                            if (rexp == 1) cost = lambda * ((sqrt(2) * theta) / theta_MVD);
+                            else cost = lambda * std::pow(((sqrt(2) * theta) / theta_MVD), rexp);
+                        }
+                    }
+                    this->paircosts[i * LL * LL + k * LL + j] = cost;
+                }
         }
         (void)pairs;
         detail::timers().pairwise += omp_get_wtime() - t0;
