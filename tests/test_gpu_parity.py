@@ -120,6 +120,19 @@ def test_nearest_triangle_bit_exact(R, oracle_built, meshes, key, group):
         capi.check(capi.lib().msmgpu_set_query_group(1))
 
 
+@pytest.mark.parametrize("lo,hi", [(4, 5), (3, 5), (5, 5), (4, 6)])
+def test_nearest_triangle_nested_icospheres(R, oracle_built, lo, hi):
+    """Vertices of a finer icosphere located in a coarser one (what project_CPgrid does between resolution levels,
+    mesh_registration.cpp:141-154): most queries sit exactly on an edge or a vertex of the mesh, i.e. on the ties of the search."""
+    xyz, tri = synth.icosphere(lo)
+    q = synth.icosphere(hi)[0]
+    ot, ov, os_, _ = oracle_built.OracleOctree(xyz, tri).query(q)
+    gt, gv, gs = R.Octree(R.Mesh(xyz, tri)).query(q)
+    assert np.array_equal(gs, np.vectorize(ST.get)(os_)) and np.array_equal(gt, ot)
+    ok = os_ == 0
+    assert ok.all() and np.array_equal(gv[ok], ov[ok])
+
+
 def test_query_raises_like_reference(R, meshes):
     t = R.Octree(R.Mesh(*meshes[3]))
     with pytest.raises(R.MeshException) as e:
