@@ -4,7 +4,8 @@ univariate (D = 1) and multivariate (D = 40) correlation. Prints one JSON line p
   value        costs/s through msmgpu_costfn_unary_table (host rotation matrices + upload + kernel + table download)
   kernel_ms    k_unary_table alone (CUDA events around msmgpu_costfn_unary_table_dev minus nothing: includes the R upload)
   cpu_baseline the CPU restatement of the reference loop (oracle port, all host threads) on the same inputs
-Usage: python tools/bench_unary.py [--cp 4] [--data 6] [--reps 10]
+TEST / MEASUREMENT INFRASTRUCTURE (its cpu_baseline leg runs the oracle port).
+Usage: python tests/bench_unary.py [--cp 4] [--data 6] [--reps 10]
 """
 import argparse
 import json
