@@ -20,6 +20,7 @@ BINS = [os.path.join(ROOT, "integration", "_build", "newmsm_gpu"), os.path.join(
     ("MSMpair", 1, ["--levels-drop", "1", "--it-scale", "0.4"]),            # FastPD, univariate unary table, pairwise regulariser, smoothing
     ("MSMAllStrain", 3, ["--levels-drop", "1", "--it-scale", "0.1"]),       # HOCR, HO multivariate triplet likelihood, strain regulariser
     ("MSMstrain", 1, ["--levels-drop", "2", "--it-scale", "0.1"]),         # HOCR, per-call unary costs from the device table + strain-only triplets
+    ("gMSM", 1, ["--levels-drop", "2", "--it-scale", "0.25", "--group", "3"]),   # groupwise driver: resampling hooks only (stale-area meshes)
 ])
 def test_newmsm_labels_bit_exact(config, D, extra):
     if not all(os.path.exists(b) for b in BINS):

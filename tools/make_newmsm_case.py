@@ -28,6 +28,10 @@ CONFIGS = {
                   "--bulkmod=1.6", "--shearmod=0.4", "--rescaleL"],
     # BASELINE configs[3]: NeuroImage2017 sMSM_STR semantics on ONE level with an ico5 control grid, ico6 data, ico7 sampling grid
     # (SURVEY §8d cfg4): 10 242 control points, 20 480 triplets
+    # docs/guide.md:390-407, the example config of groupwise (gMSM) registration
+    "gMSM": ["--simval=2,2,2", "--sigma_in=0,0,0", "--sigma_ref=0,0,0", "--lambda=0.2,0.2,0.2", "--it=9,9,9", "--opt=DISCRETE,DISCRETE,DISCRETE",
+             "--CPgrid=2,3,4", "--SGgrid=4,5,6", "--datagrid=4,5,6", "--regoption=3", "--regexp=2", "--dopt=HOCR", "--k_exponent=2",
+             "--bulkmod=1.6", "--shearmod=0.4"],
     "sMSMSTRcp5": ["--simval=2", "--sigma_in=2", "--sigma_ref=2", "--lambda=0.025", "--it=40", "--opt=DISCRETE", "--CPgrid=5", "--SGgrid=7",
                    "--datagrid=6", "--regoption=3", "--regexp=2", "--dopt=HOCR", "--VN", "--rescaleL", "--triclique", "--k_exponent=2",
                    "--bulkmod=1.6", "--shearmod=0.4"],
@@ -67,6 +71,7 @@ def main():
     ap.add_argument("--levels-drop", type=int, default=0)
     ap.add_argument("--it-scale", type=float, default=1.0)
     ap.add_argument("--max-disp", type=float, default=8.26)
+    ap.add_argument("--group", type=int, default=0, help="also write a groupwise case: this many subjects (meshes.txt, data.txt, template.asc)")
     a = ap.parse_args()
     os.makedirs(a.out, exist_ok=True)
     xyz, tri = synth.icosphere(a.level)
@@ -79,6 +84,20 @@ def main():
     for name, lines in CONFIGS.items():
         with open(os.path.join(a.out, "conf_" + name), "w") as f:
             f.write("\n".join(scaled(lines, a.levels_drop, a.it_scale)) + "\n")
+    if a.group:
+        # gMSM inputs (src/newmsm.cpp:14-28): a list of subject spheres, a list of their data files, a template sphere
+        tpl = synth.rotate_sphere(xyz, 0.004, -0.003, 0.002)
+        write_asc(os.path.join(a.out, "template.asc"), tpl, tri)
+        meshes, datas = [], []
+        for s_ in range(a.group):
+            sx = synth.smooth_warp(xyz, max_disp=a.max_disp * 0.5, seed=300 + s_)
+            write_asc(os.path.join(a.out, f"subject{s_}.asc"), sx, tri)
+            f = synth.smooth_fields(synth.smooth_warp(xyz, max_disp=a.max_disp * 0.5, seed=400 + s_), a.D, seed0=100, noise=0.05, noise_seed=20 + s_)
+            np.savetxt(os.path.join(a.out, f"subject{s_}.txt"), f.T, fmt="%.9g")
+            meshes.append(os.path.join(a.out, f"subject{s_}.asc"))
+            datas.append(os.path.join(a.out, f"subject{s_}.txt"))
+        open(os.path.join(a.out, "meshes.txt"), "w").write("\n".join(meshes) + "\n")
+        open(os.path.join(a.out, "data.txt"), "w").write("\n".join(datas) + "\n")
     print("wrote", a.out)
 
 
