@@ -137,10 +137,14 @@ constexpr int kResThreads = 256;
 constexpr int kResWarpTile = 32;                                   // targets per warp
 constexpr int kResTile = kResWarpTile * (kResThreads / 32);        // targets per CTA
 
-// U = gather slots in flight per thread, MINB = CTAs per SM the register allocation must allow
-template <int G, int kResUnroll, int MINB>
+// U = gather slots in flight per thread, MINB = CTAs per SM the register allocation must allow.
+// ASYNC: phase B requests its rows with 16-byte asynchronous copies (cp.async.cg, LDGSTS) into a per-warp staging slice of dynamic
+// shared memory instead of loading them into registers: the bytes in flight then cost shared memory (U * 3 * 512 B per warp), not
+// registers, so U can grow without spilling the FP64 geometry of phase A. Same arithmetic, same order.
+template <int G, int kResUnroll, int MINB, bool ASYNC = false>
 __global__ void __launch_bounds__(kResThreads, MINB) k_bary_resample_f32(const ResampleJob* __restrict__ jobs, int n, const double* __restrict__ pts,
                                                                   int D, int* __restrict__ out_status) {
+    extern __shared__ float4 s_stage_all[];   // ASYNC only: [warps][U][3][32] float4
     __shared__ int s_idx_all[kResTile * 3];
     __shared__ double s_w_all[kResTile * 3];
     __shared__ int s_ne_all[kResTile];
@@ -189,34 +193,69 @@ __global__ void __launch_bounds__(kResThreads, MINB) k_bary_resample_f32(const R
         const float4* __restrict__ in4 = reinterpret_cast<const float4*>(fin);
         float4* __restrict__ out4 = reinterpret_cast<float4*>(fout) + (size_t)tile0 * D4;   // the warp's rows are contiguous
         const int slots = rows * D4;
-        for (int s0 = lane; s0 < slots; s0 += 32 * kResUnroll) {
-            // branch-free issue of 12 independent 128-bit loads (out-of-range slots re-read the last slot, absent
-            // map entries re-read entry 0 with weight 0), conversions and FP64 sums only afterwards
-            float4 f[kResUnroll][3];
-            double w[kResUnroll][3];
+        if (ASYNC) {
+            float4* stage = s_stage_all + (size_t)warp * kResUnroll * 3 * 32;
+            for (int s0 = lane; s0 < slots; s0 += 32 * kResUnroll) {
+                double w[kResUnroll][3];
 #pragma unroll
-            for (int u = 0; u < kResUnroll; ++u) {
-                const int s = min(s0 + 32 * u, slots - 1);
-                const int q = s / D4, c = s - q * D4;
-                const int ne = s_ne[q];
+                for (int u = 0; u < kResUnroll; ++u) {
+                    const int s = min(s0 + 32 * u, slots - 1);
+                    const int q = s / D4, c = s - q * D4;
+                    const int ne = s_ne[q];
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    const bool on = j < ne;
-                    const int row = on ? s_idx[3 * q + j] : max(s_idx[3 * q], 0);
-                    w[u][j] = on ? s_w[3 * q + j] : 0.0;
-                    f[u][j] = __ldg(in4 + (size_t)row * D4 + c);
+                    for (int j = 0; j < 3; ++j) {
+                        const bool on = j < ne;
+                        const int row = on ? s_idx[3 * q + j] : max(s_idx[3 * q], 0);
+                        w[u][j] = on ? s_w[3 * q + j] : 0.0;
+                        const unsigned dst = (unsigned)__cvta_generic_to_shared(stage + (u * 3 + j) * 32 + lane);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(in4 + (size_t)row * D4 + c) : "memory");
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                // every lane reads back only what it requested itself: no cross-lane visibility is needed
+#pragma unroll
+                for (int u = 0; u < kResUnroll; ++u) {
+                    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const double ww = w[u][j];
+                        const float4 v = ww != 0.0 ? stage[(u * 3 + j) * 32 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        a0 += (double)v.x * ww; a1 += (double)v.y * ww; a2 += (double)v.z * ww; a3 += (double)v.w * ww;
+                    }
+                    if (s0 + 32 * u < slots) __stcs(out4 + (s0 + 32 * u), make_float4((float)a0, (float)a1, (float)a2, (float)a3));
                 }
             }
-#pragma unroll
-            for (int u = 0; u < kResUnroll; ++u) {
-                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {   // an absent entry contributes (finite or not) * 0 -> guarded by the select below
-                    const double ww = w[u][j];
-                    const float4 v = ww != 0.0 ? f[u][j] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    a0 += (double)v.x * ww; a1 += (double)v.y * ww; a2 += (double)v.z * ww; a3 += (double)v.w * ww;
+        } else {
+            for (int s0 = lane; s0 < slots; s0 += 32 * kResUnroll) {
+                // branch-free issue of 12 independent 128-bit loads (out-of-range slots re-read the last slot, absent
+                // map entries re-read entry 0 with weight 0), conversions and FP64 sums only afterwards
+                float4 f[kResUnroll][3];
+                double w[kResUnroll][3];
+    #pragma unroll
+                for (int u = 0; u < kResUnroll; ++u) {
+                    const int s = min(s0 + 32 * u, slots - 1);
+                    const int q = s / D4, c = s - q * D4;
+                    const int ne = s_ne[q];
+    #pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const bool on = j < ne;
+                        const int row = on ? s_idx[3 * q + j] : max(s_idx[3 * q], 0);
+                        w[u][j] = on ? s_w[3 * q + j] : 0.0;
+                        f[u][j] = __ldg(in4 + (size_t)row * D4 + c);
+                    }
                 }
-                if (s0 + 32 * u < slots) __stcs(out4 + (s0 + 32 * u), make_float4((float)a0, (float)a1, (float)a2, (float)a3));
+    #pragma unroll
+                for (int u = 0; u < kResUnroll; ++u) {
+                    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    #pragma unroll
+                    for (int j = 0; j < 3; ++j) {   // an absent entry contributes (finite or not) * 0 -> guarded by the select below
+                        const double ww = w[u][j];
+                        const float4 v = ww != 0.0 ? f[u][j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        a0 += (double)v.x * ww; a1 += (double)v.y * ww; a2 += (double)v.z * ww; a3 += (double)v.w * ww;
+                    }
+                    if (s0 + 32 * u < slots) __stcs(out4 + (s0 + 32 * u), make_float4((float)a0, (float)a1, (float)a2, (float)a3));
+                }
             }
         }
     } else {
@@ -301,6 +340,17 @@ msmgpu_status launch_blend_coords(const TreeView& t, int n, const double* d_pts,
     return MSMGPU_OK;
 }
 
+template <int G, int U, int MINB>
+static void launch_async(dim3 grid, const ResampleJob* d_jobs, int n, const double* d_pts, int D, int* d_status, cudaStream_t s) {
+    const size_t smem = (size_t)(kResThreads / 32) * U * 3 * 32 * sizeof(float4);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_bary_resample_f32<G, U, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    k_bary_resample_f32<G, U, MINB, true><<<grid, kResThreads, smem, s>>>(d_jobs, n, d_pts, D, d_status);
+}
+
 msmgpu_status launch_bary_resample_f32(const ResampleJob* d_jobs, int n_jobs, int n, const double* d_pts, int D, int* d_status, cudaStream_t s) {
     if (n <= 0 || n_jobs <= 0) return MSMGPU_OK;
     const int g = query_group_width();
@@ -310,6 +360,12 @@ msmgpu_status launch_bary_resample_f32(const ResampleJob* d_jobs, int n_jobs, in
         case 1: MSM_DISPATCH_G(g, (k_bary_resample_f32<G, 2, 3><<<grid, kResThreads, 0, s>>>(d_jobs, n, d_pts, D, d_status))); break;
         case 2: MSM_DISPATCH_G(g, (k_bary_resample_f32<G, 2, 4><<<grid, kResThreads, 0, s>>>(d_jobs, n, d_pts, D, d_status))); break;
         case 3: MSM_DISPATCH_G(g, (k_bary_resample_f32<G, 4, 3><<<grid, kResThreads, 0, s>>>(d_jobs, n, d_pts, D, d_status))); break;
+        case 5: MSM_DISPATCH_G(g, (k_bary_resample_f32<G, 2, 5><<<grid, kResThreads, 0, s>>>(d_jobs, n, d_pts, D, d_status))); break;
+        // asynchronous-copy staging (cp.async): U slots x 3 rows x 512 B per warp of dynamic shared memory
+        case 8: MSM_DISPATCH_G(g, (launch_async<G, 3, 4>(grid, d_jobs, n, d_pts, D, d_status, s))); break;
+        case 9: MSM_DISPATCH_G(g, (launch_async<G, 4, 3>(grid, d_jobs, n, d_pts, D, d_status, s))); break;
+        case 10: MSM_DISPATCH_G(g, (launch_async<G, 2, 4>(grid, d_jobs, n, d_pts, D, d_status, s))); break;
+        case 11: MSM_DISPATCH_G(g, (launch_async<G, 6, 3>(grid, d_jobs, n, d_pts, D, d_status, s))); break;
         default: MSM_DISPATCH_G(g, (k_bary_resample_f32<G, 4, 2><<<grid, kResThreads, 0, s>>>(d_jobs, n, d_pts, D, d_status))); break;
     }
     MSM_LAUNCH_CHECK();
