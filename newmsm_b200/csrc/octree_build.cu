@@ -603,7 +603,7 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
         DevBuf<const uint4*> d_qbox;
         DevBuf<int> d_nt, d_off;
         MSM_CUDA(F->nodes.alloc(node_cap, s));
-        MSM_CUDA(F->pairs.alloc(pair_cap, s));
+        MSM_CUDA(F->pairs.alloc(pair_cap + 4, s));   // + 4: the queries read leaf lists as aligned 128-bit words (query.cuh)
         DevBuf<unsigned char> pmask;   // per list position of the CURRENT level: which of the 8 children the triangle goes to
         long long pmask_cap = 3 * total_t + 4096;
         MSM_CUDA(pmask.alloc((size_t)pmask_cap, s));

@@ -60,8 +60,33 @@ __device__ __forceinline__ int nearest_triangle(const TreeView& T, const V3& pt,
         const int mine = (nd.z - gl + G - 1) / G;             // candidates owned by this lane (may be <= 0)
         const int fast = mine < 64 ? mine : 64;
         // the scan is a chain of dependent loads (id -> cull sphere): batches of 4 candidates, with the ids of the NEXT batch
-        // requested before the spheres of the current one are tested, so one load latency per batch is exposed instead of two
-        {
+        // requested before the spheres of the current one are tested, so one load latency per batch is exposed instead of two.
+        // With one lane per query the lane's candidates are contiguous in the list: they are fetched as ALIGNED 128-bit words
+        // (4 ids per L1 access instead of 1; the kernel is bound by L1 wavefronts of divergent loads, profiles/r1u). The word that
+        // holds the first candidate may start up to 3 ids earlier and the last one may end up to 3 ids later: both stay inside
+        // the `pairs` allocation and those slots are masked out.
+        if (G == 1) {
+            const int lead = nd.y & 3;                                      // ids of the first word that precede the list
+            const int4* __restrict__ words = reinterpret_cast<const int4*>(T.pairs + (nd.y - lead));
+            const int n_words = (lead + fast + 3) >> 2;
+            int4 wn = n_words > 0 ? __ldg(words) : make_int4(0, 0, 0, 0);
+            for (int k = 0; k < n_words; ++k) {
+                const int4 wv = wn;
+                if (k + 1 < n_words) wn = __ldg(words + k + 1);
+                const int jb = 4 * k - lead;                                // list position of wv.x
+                const int t[4] = {wv.x, wv.y, wv.z, wv.w};
+                bool ok[4];
+                float4 cs[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    ok[u] = jb + u >= 0 && jb + u < fast;
+                    cs[u] = __ldg(T.cull + (ok[u] ? t[u] : 0));
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (ok[u] && cull_keep_f4(cs[u], pt, pp)) keep |= 1ull << (jb + u);
+            }
+        } else {
             int tn[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) tn[u] = u < fast ? __ldg(list + gl + u * G) : 0;
