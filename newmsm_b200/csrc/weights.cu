@@ -135,6 +135,20 @@ __global__ void k_bucket_sort(int nkeys, const int* __restrict__ ptr, int* __res
             if (i < len) { id[b + i] = ki[i]; val[b + i] = vi[i]; }
         return;
     }
+    if (len <= 32) {   // medium buckets (a target's share of the reverse weights: ~15): sort a private copy, one read and one write of the bucket
+        int ki[32];
+        double vi[32];
+        for (int i = 0; i < len; ++i) { ki[i] = id[b + i]; vi[i] = val[b + i]; }
+        for (int i = 1; i < len; ++i) {
+            const int k0 = ki[i];
+            const double v0 = vi[i];
+            int j = i - 1;
+            while (j >= 0 && ki[j] > k0) { ki[j + 1] = ki[j]; vi[j + 1] = vi[j]; --j; }
+            ki[j + 1] = k0; vi[j + 1] = v0;
+        }
+        for (int i = 0; i < len; ++i) { id[b + i] = ki[i]; val[b + i] = vi[i]; }
+        return;
+    }
     for (int i = b + 1; i < e; ++i) {
         const int ki = id[i];
         const double vi = val[i];
