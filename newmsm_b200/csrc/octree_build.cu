@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(TPC == 32 ? 256 : TPC) k_chunk_stats(int node_
 
 // one thread per node of the level
 __global__ void k_node_combine(int node_begin, int n_level, int max_chunks, int K, const int4* __restrict__ nodes, int* __restrict__ stats,
-                               int* __restrict__ split_flag, int* __restrict__ child_cnt) {
+                               int* __restrict__ split_flag, int* __restrict__ child_cnt, int* __restrict__ max_child_cnt) {
     const int li = blockIdx.x * blockDim.x + threadIdx.x;
     if (li >= n_level) return;
     const int cnt = nodes[node_begin + li].z;
@@ -448,8 +448,10 @@ __global__ void k_node_combine(int node_begin, int n_level, int max_chunks, int 
         }
     }
     split_flag[li] = split;
+    int mx = 0;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) child_cnt[li * 8 + c] = split ? tot[c] : 0;
+    for (int c = 0; c < 8; ++c) { child_cnt[li * 8 + c] = split ? tot[c] : 0; mx = max(mx, split ? tot[c] : 0); }
+    if (mx > 0) atomicMax(max_child_cnt, mx);   // longest list of the next level (picks its team width)
 }
 
 // One thread per node of the level: create the 8 children of every splitting node.
@@ -539,10 +541,6 @@ __global__ void __launch_bounds__(TPC == 32 ? 256 : TPC) k_scatter_chunk(int nod
     }
 }
 
-__global__ void k_max_i32_build(int n, const int* __restrict__ v, int* __restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && v[i] > 0) atomicMax(out, v[i]);
-}
 
 __global__ void k_save_lists(int node_begin, int n_level, const int4* __restrict__ nodes, int* __restrict__ list_start, int* __restrict__ list_count) {
     const int li = blockIdx.x * blockDim.x + threadIdx.x;
@@ -661,13 +659,12 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
             else
                 k_chunk_stats<32, 4><<<g_warp, 256, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_aabb.p, d_qbox.p, root_half, stats.p, pmask.p, level_base);
             MSM_LAUNCH_CHECK();
-            k_node_combine<<<(n_level + 255) / 256, 256, 0, s>>>(node_begin, n_level, max_chunks, K, F->nodes.p, stats.p, split_flag.p, child_cnt.p);
+            MSM_CUDA(cudaMemsetAsync(totals.p + 2, 0, sizeof(int), s));
+            k_node_combine<<<(n_level + 255) / 256, 256, 0, s>>>(node_begin, n_level, max_chunks, K, F->nodes.p, stats.p, split_flag.p, child_cnt.p,
+                                                                 totals.p + 2);
             MSM_LAUNCH_CHECK();
             MSM_TRY(exclusive_scan_i32(split_flag.p, split_rank.p, n_level, totals.p, s));
             MSM_TRY(exclusive_scan_i32(child_cnt.p, child_off.p, n_level * 8, totals.p + 1, s));
-            MSM_CUDA(cudaMemsetAsync(totals.p + 2, 0, sizeof(int), s));
-            k_max_i32_build<<<(n_level * 8 + 255) / 256, 256, 0, s>>>(n_level * 8, child_cnt.p, totals.p + 2);
-            MSM_LAUNCH_CHECK();
             int h_tot[3];
             MSM_CUDA(cudaMemcpyAsync(h_tot, totals.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, s));
             MSM_CUDA(cudaStreamSynchronize(s));
