@@ -62,6 +62,13 @@ msmgpu_status msmgpu_ctx_create(int device, void* stream, msmgpu_ctx** out);
 void msmgpu_ctx_destroy(msmgpu_ctx* ctx);
 msmgpu_status msmgpu_ctx_sync(msmgpu_ctx* ctx);
 void* msmgpu_ctx_stream(msmgpu_ctx* ctx);
+/* Device buffers for hosts that have no allocator of their own (the C++ adapters; Python callers pass torch storage instead):
+ * plain cudaMalloc / cudaFree on the context's device, and copies ordered on the context's stream (the call returns when done).
+ * msmgpu_device_copy_peer copies between buffers of two contexts (devices), e.g. the per-iteration field shards of gMSM. */
+msmgpu_status msmgpu_device_malloc(msmgpu_ctx* ctx, size_t bytes, void** out);
+void msmgpu_device_free(msmgpu_ctx* ctx, void* ptr);
+msmgpu_status msmgpu_device_download(msmgpu_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes);
+msmgpu_status msmgpu_device_copy_peer(msmgpu_ctx* dst_ctx, void* dst, msmgpu_ctx* src_ctx, const void* src, size_t bytes);
 
 /* replaces: newresampler::Mesh as geometry carrier (msm-newresampler/src/mesh.h:37-58) */
 msmgpu_status msmgpu_mesh_create(msmgpu_ctx* ctx, int nv, const double* xyz, int nt, const int32_t* tri, msmgpu_mesh** out);

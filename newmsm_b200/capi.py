@@ -43,6 +43,10 @@ _SIGNATURES = {
     "msmgpu_ctx_destroy": (None, [_vp]),
     "msmgpu_ctx_sync": (_i, [_vp]),
     "msmgpu_ctx_stream": (_vp, [_vp]),
+    "msmgpu_device_malloc": (_i, [_vp, C.c_size_t, _pp]),
+    "msmgpu_device_free": (None, [_vp, _vp]),
+    "msmgpu_device_download": (_i, [_vp, _vp, _vp, C.c_size_t]),
+    "msmgpu_device_copy_peer": (_i, [_vp, _vp, _vp, _vp, C.c_size_t]),
     "msmgpu_mesh_create": (_i, [_vp, _i, _vp, _i, _vp, _pp]),
     "msmgpu_mesh_create_dev": (_i, [_vp, _i, _vp, _i, _vp, _pp]),
     "msmgpu_mesh_set_coords": (_i, [_vp, _vp]),

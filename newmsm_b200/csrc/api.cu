@@ -202,6 +202,36 @@ msmgpu_status msmgpu_ctx_sync(msmgpu_ctx* c) {
 }
 void* msmgpu_ctx_stream(msmgpu_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
+msmgpu_status msmgpu_device_malloc(msmgpu_ctx* c, size_t bytes, void** out) {
+    if (!c || !out) return fail(MSMGPU_ERR_INVALID, "device_malloc: bad arguments");
+    *out = nullptr;
+    MSM_CUDA(cudaSetDevice(c->device));
+    if (bytes) MSM_CUDA(cudaMalloc(out, bytes));
+    return MSMGPU_OK;
+}
+void msmgpu_device_free(msmgpu_ctx* c, void* ptr) {
+    if (!c || !ptr) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(ptr);
+}
+msmgpu_status msmgpu_device_download(msmgpu_ctx* c, void* host_dst, const void* dev_src, size_t bytes) {
+    if (!c || (bytes && (!host_dst || !dev_src))) return fail(MSMGPU_ERR_INVALID, "device_download: bad arguments");
+    MSM_CUDA(cudaSetDevice(c->device));
+    MSM_CUDA(cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    MSM_CUDA(cudaStreamSynchronize(c->stream));
+    return MSMGPU_OK;
+}
+msmgpu_status msmgpu_device_copy_peer(msmgpu_ctx* dc, void* dst, msmgpu_ctx* sc, const void* src, size_t bytes) {
+    if (!dc || !sc || (bytes && (!dst || !src))) return fail(MSMGPU_ERR_INVALID, "device_copy_peer: bad arguments");
+    MSM_CUDA(cudaSetDevice(sc->device));
+    MSM_CUDA(cudaStreamSynchronize(sc->stream));   // the source was produced on its own context's stream
+    MSM_CUDA(cudaSetDevice(dc->device));
+    MSM_CUDA(cudaMemcpyPeerAsync(dst, dc->device, src, sc->device, bytes, dc->stream));
+    MSM_CUDA(cudaStreamSynchronize(dc->stream));
+    return MSMGPU_OK;
+}
+
 static msmgpu_status mesh_create_impl(msmgpu_ctx* ctx, int nv, const double* xyz, int nt, const int32_t* tri, bool dev, msmgpu_mesh** out) {
     if (!ctx || !out || nv <= 0 || nt < 0 || !xyz || (nt > 0 && !tri)) return fail(MSMGPU_ERR_INVALID, "mesh_create: bad arguments");
     *out = nullptr;

@@ -70,8 +70,8 @@ def main():
     ap.add_argument("--level", type=int, default=6)
     ap.add_argument("--D", type=int, default=1)
     ap.add_argument("--config", default="MSMpair", choices=["MSMpair", "MSMAllStrain", "MSMstrain", "sMSMSTRcp5", "gMSM"])
-    ap.add_argument("--group", type=int, default=0, help="groupwise (gMSM) run with this many subjects: in the unmodified program only the "
-                                                           "resampling hooks apply (the group model cannot be reached at link time, DESIGN.md §8)")
+    ap.add_argument("--group", type=int, default=0, help="groupwise (gMSM) run with this many subjects (integration/newmsm_gpu_group_hooks.cpp binds "
+                                                           "estimate_pairs, get_patch_data and the pair / triplet costs)")
     ap.add_argument("--levels-drop", type=int, default=0)
     ap.add_argument("--it-scale", type=float, default=1.0)
     ap.add_argument("--threads", type=int, default=os.cpu_count())

@@ -20,7 +20,7 @@ BINS = [os.path.join(ROOT, "integration", "_build", "newmsm_gpu"), os.path.join(
     ("MSMpair", 1, ["--levels-drop", "1", "--it-scale", "0.4"]),            # FastPD, univariate unary table, pairwise regulariser, smoothing
     ("MSMAllStrain", 3, ["--levels-drop", "1", "--it-scale", "0.1"]),       # HOCR, HO multivariate triplet likelihood, strain regulariser
     ("MSMstrain", 1, ["--levels-drop", "2", "--it-scale", "0.1"]),         # HOCR, per-call unary costs from the device table + strain-only triplets
-    ("gMSM", 1, ["--levels-drop", "2", "--it-scale", "0.25", "--group", "3"]),   # groupwise driver: resampling hooks only (stale-area meshes)
+    ("gMSM", 1, ["--levels-drop", "2", "--it-scale", "0.25", "--group", "3"]),   # groupwise driver: estimate_pairs, get_patch_data and the pair / triplet costs on the device (integration/newmsm_gpu_group_hooks.cpp)
 ])
 def test_newmsm_labels_bit_exact(config, D, extra):
     if not all(os.path.exists(b) for b in BINS):
@@ -34,3 +34,24 @@ def test_newmsm_labels_bit_exact(config, D, extra):
     assert res["labels_bit_exact"], res["label_mismatch_per_iteration"]
     assert res["all_meshes_bit_exact"], (res["hashes_equal"], res["trace_calls"])
     assert res["final_sphere_max_abs_diff"] == 0.0
+
+
+def test_gmsm_costs_match_reference_in_process():
+    """MSMGPU_VERIFY=1: inside the groupwise run every pair / triplet cost Fusion::optimize asks for is ALSO evaluated by the reference's own
+    computePairwiseCost / computeTripletCost on the reference's own patch maps, in the same process, and compared bit for bit."""
+    import re
+    if not all(os.path.exists(b) for b in BINS):
+        pytest.skip("integration/_build/newmsm_gpu not built (needs /root/reference at build time)")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "newmsm_e2e.py"), "--level", "4", "--config", "gMSM", "--D", "2", "--threads", "4",
+                          "--skip-cpu", "--verify", "--levels-drop", "2", "--it-scale", "0.25", "--group", "3"], capture_output=True, text=True, timeout=1500)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    line = [ln for ln in res["gpu_split"] if "group pair costs" in ln]
+    assert line, res["gpu_split"]
+    m = re.search(r"group pair costs: (\d+) of (\d+) differ.*triplet costs: (\d+) of (\d+) differ", line[0])
+    assert m, line[0]
+    bad_p, n_p, bad_t, n_t = map(int, m.groups())
+    assert n_p > 1000 and n_t > 1000, line[0]
+    assert bad_p == 0 and bad_t == 0, line[0]
+    used = [ln for ln in res["gpu_split"] if ln.startswith("[msmgpu group]")]
+    assert used and "pair batches" in used[0], res["gpu_split"]
