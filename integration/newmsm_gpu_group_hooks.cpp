@@ -65,12 +65,21 @@ struct Report {
 }  // namespace
 
 void hook_estimate_pairs(DiscreteGroupModel* self) {
-    if (disabled() || !GroupBinding::instance().estimate_pairs(*self)) real_estimate_pairs(self);
+    if (disabled() || !GroupBinding::instance().estimate_pairs(*self)) { real_estimate_pairs(self); return; }
+    if (verify()) {
+        const std::vector<int> got(self->pairs, self->pairs + 2 * (size_t)self->m_num_pairs);
+        real_estimate_pairs(self);
+        long bad = 0;
+        for (size_t i = 0; i < got.size(); ++i) bad += got[i] != self->pairs[i];
+        std::fprintf(stderr, "[msmgpu verify] estimate_pairs: %d pairs, %ld node ids differ from the reference's\n", self->m_num_pairs, bad);
+    }
 }
 
 void hook_get_patch_data(DiscreteGroupModel* self) {
     if (disabled() || !GroupBinding::instance().get_patch_data(*self)) { real_get_patch_data(self); return; }
     if (verify()) real_get_patch_data(self);   // the reference's patch maps too, for the side-by-side comparison of every cost request
+    // Fusion::optimize runs next; the first sphere_project_warp after it closes the "optimiser phases" timer (newmsm_gpu_hooks.cpp)
+    newmeshreg_gpu::detail::timers().source_done_at = omp_get_wtime();
 }
 
 double hook_pair_cost(DiscreteGroupCostFunction* self, int pair, int la, int lb) {
@@ -80,7 +89,8 @@ double hook_pair_cost(DiscreteGroupCostFunction* self, int pair, int la, int lb)
     if (verify()) {
         const double r = real_pair_cost(self, pair, la, lb);
         g_pair_checked++;
-        if (std::memcmp(&r, &v, sizeof(double)) != 0 && !(std::isnan(r) && std::isnan(v))) g_pair_bad++;
+        if (std::memcmp(&r, &v, sizeof(double)) != 0 && !(std::isnan(r) && std::isnan(v)) && g_pair_bad++ < 20)
+            std::fprintf(stderr, "[msmgpu verify] group pair %d labels %d %d: reference %a (%.17g)  device %a (%.17g)\n", pair, la, lb, r, r, v, v);
     }
     return v;
 }
@@ -92,7 +102,8 @@ double hook_triplet_cost(DiscreteGroupCostFunction* self, int t, int la, int lb,
     if (verify()) {
         const double r = real_triplet_cost(self, t, la, lb, lc);
         g_trip_checked++;
-        if (std::memcmp(&r, &v, sizeof(double)) != 0 && !(std::isnan(r) && std::isnan(v))) g_trip_bad++;
+        if (std::memcmp(&r, &v, sizeof(double)) != 0 && !(std::isnan(r) && std::isnan(v)) && g_trip_bad++ < 20)
+            std::fprintf(stderr, "[msmgpu verify] group triplet %d labels %d %d %d: reference %a (%.17g)  device %a (%.17g)\n", t, la, lb, lc, r, r, v, v);
     }
     return v;
 }

@@ -146,7 +146,8 @@ struct TripletArgs {
     const double* src_xyz; const int* prow; const int* pmem;
     const double* src_feat; const double* ref_feat; const double* cfw; const double* absw;
     double lambda, mu, kappa, k_exp, rexp;
-    double* aux;              // [n][2]: R, J of the strain energy (R = NaN: out[r] is already final)
+    double* aux;              // [n][2]: R, J of the strain energy. J = -1 (a square root is never negative): out[r] is already final.
+                              // A NaN pair is a legitimate result (det(F^T F) rounding below zero, reg_tools.cpp:585-587) and propagates.
     double fold_value;        // cost of a folded triangle: FOLDING * lambda (cpp:152) or FOLDING (DiscreteGroupCostFunction.cpp:40)
     double* out;              // [n]
     int* err;
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(kTripWarps * 32) k_triplet_costs(TripletArgs a
     }
     // only estimate the cost if it does not cause folding (cpp:152)
     if (vdot(tri_normal(def[0], def[1], def[2]), tri_normal(cur[0], cur[1], cur[2])) < 0.0) {
-        if (lane == 0) { a.out[r] = a.fold_value; a.aux[2 * (size_t)r] = nan(""); a.aux[2 * (size_t)r + 1] = 0.0; }   // final as is
+        if (lane == 0) { a.out[r] = a.fold_value; a.aux[2 * (size_t)r] = 0.0; a.aux[2 * (size_t)r + 1] = -1.0; }   // J = -1: out[r] is final as is
         return;
     }
     double likelihood = 0.0;
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(kTripWarps * 32) k_triplet_costs(TripletArgs a
             }
         }
         if (__any_sync(kFull, bad)) {
-            if (lane == 0) { a.out[r] = nan(""); a.aux[2 * (size_t)r] = nan(""); a.aux[2 * (size_t)r + 1] = 0.0; *a.err = 1; }
+            if (lane == 0) { a.out[r] = nan(""); a.aux[2 * (size_t)r] = 0.0; a.aux[2 * (size_t)r + 1] = -1.0; *a.err = 1; }
             return;
         }
         __syncwarp();
@@ -350,7 +351,7 @@ static msmgpu_status triplet_run(msmgpu_costfn* c, int ntrip, const int32_t* tri
 #pragma omp parallel for schedule(static) if (n > 4096)
     for (int r = 0; r < n; ++r) {
         const double R = aux[2 * (size_t)r], J = aux[2 * (size_t)r + 1];
-        if (R != R) continue;
+        if (J == -1.0) continue;                                // folded (or failed query): already final
         const double Rshared = std::pow(R, k_exp), Jshared = std::pow(J, k_exp);
         const double W = 0.5 * (MU * (Rshared + 1.0 / Rshared - 2) + KAPPA * (Jshared + 1.0 / Jshared - 2));
         out[r] = out[r] + lambda * std::pow(W, rexp);
@@ -404,7 +405,7 @@ static msmgpu_status group_triplet_run(msmgpu_ctx* ctx, int n_nodes, const doubl
 #pragma omp parallel for schedule(static) if (n > 4096)
     for (int r = 0; r < n; ++r) {
         const double R = aux[2 * (size_t)r], J = aux[2 * (size_t)r + 1];
-        if (R != R) continue;                                   // folded: FOLDING, already written
+        if (J == -1.0) continue;                                // folded: FOLDING, already written
         const double Rshared = std::pow(R, k_exp), Jshared = std::pow(J, k_exp);
         const double W = 0.5 * (MU * (Rshared + 1.0 / Rshared - 2) + KAPPA * (Jshared + 1.0 / Jshared - 2));
         if (fixnan && W != W) { out[r] = 1e7; continue; }       // FIX_NAN

@@ -7,6 +7,7 @@ and reports the wall-clock of both. BASELINE.json metric (iii): "newmsm wall-tim
     python tests/newmsm_e2e.py --level 6 --config MSMAllStrain --D 40 --threads 16 --out gpurun_out/e2e_cfg3.json
 """
 import argparse
+import shutil
 import json
 import os
 import subprocess
@@ -86,6 +87,12 @@ def main():
     ap.add_argument("--disable", default="", help="MSMGPU_DISABLE value for the GPU run (cost, resample): A/B isolation of the hooks")
     ap.add_argument("--verify", action="store_true", help="MSMGPU_VERIFY=1: the hooks also run the reference CPU code in-process and compare")
     ap.add_argument("--out", default="")
+    ap.add_argument("--devices", type=int, default=1, help="MSMGPU_DEVICES for the GPU run (groupwise: subjects and pair blocks sharded over this many GPUs)")
+    ap.add_argument("--skip-gpu", action="store_true", help="CPU arms only (e.g. to record the single-thread trace on a machine without a GPU)")
+    ap.add_argument("--gpu-trace-out", default="", help="keep the GPU run's trace here")
+    ap.add_argument("--cpu-trace-out", default="", help="keep the single-thread CPU trace here")
+    ap.add_argument("--cpu-trace-in", default="", help="compare with this recorded single-thread CPU trace instead of running that arm "
+                                                         "(the case is seeded, so the inputs are identical)")
     a = ap.parse_args()
     global GROUP
     GROUP = a.group > 0
@@ -95,17 +102,20 @@ def main():
     conf = os.path.join(work, "conf_" + a.config)
     with open(conf, "a") as f:
         f.write("--numthreads=%d\n" % a.threads)
-    res = {"config": a.config, "level": a.level, "D": a.D, "levels_drop": a.levels_drop, "it_scale": a.it_scale, "host_threads": a.threads,
+    res = {"config": a.config, "level": a.level, "D": a.D, "levels_drop": a.levels_drop, "it_scale": a.it_scale, "host_threads": a.threads, "devices": a.devices,
            "verts": 10 * 4 ** a.level + 2}
     gpu_times = []
-    for k in range(a.gpu_runs):
+    for k in range(0 if a.skip_gpu else a.gpu_runs):
         dt, note = run(GPU, work, conf, os.path.join(work, "out_gpu"), a.threads, os.path.join(work, "trace_gpu.txt"),
-                       dict(({"MSMGPU_DISABLE": a.disable} if a.disable else {}), **({"MSMGPU_VERIFY": "1"} if a.verify else {})))
+                       dict(({"MSMGPU_DISABLE": a.disable} if a.disable else {}), **({"MSMGPU_VERIFY": "1"} if a.verify else {}),
+                            **({"MSMGPU_DEVICES": str(a.devices)} if a.devices > 1 else {})))
         gpu_times.append(dt)
         res["gpu_split"] = note
-    res["gpu_wall_s"] = min(gpu_times)
+    res["gpu_wall_s"] = min(gpu_times) if gpu_times else float("nan")
     res["gpu_wall_all_s"] = gpu_times
-    tg = parse_trace(os.path.join(work, "trace_gpu.txt"))
+    tg = parse_trace(os.path.join(work, "trace_gpu.txt")) if gpu_times else []
+    if gpu_times and a.gpu_trace_out:
+        shutil.copy(os.path.join(work, "trace_gpu.txt"), a.gpu_trace_out)
     res["discrete_iterations"] = sum(1 for c in tg if "labels" in c)
     if GROUP:   # no labeling dump in group mode (the hook has no model pointer): every iteration unfolds 2 meshes per subject, whose
         res["discrete_iterations"] = len(tg) // (2 * a.group)   # control grids ROT * label[labeling] encode the labels exactly
@@ -117,13 +127,22 @@ def main():
         tm = parse_trace(os.path.join(work, "trace_cpu_mt.txt"))
         lab = [(x["labels"], y["labels"]) for x, y in zip(tm, tg) if "labels" in x and "labels" in y]
         res["label_mismatch_vs_multithreaded_cpu"] = [int((x != y).sum()) if len(x) == len(y) else -1 for x, y in lab]
+        res["trace_calls_vs_multithreaded_cpu"] = [len(tm), len(tg)]
+        res["hashes_equal_vs_multithreaded_cpu"] = sum(1 for x, y in zip(tm, tg) if x["hash"] == y["hash"])
     if not a.skip_cpu and not a.skip_parity_cpu:
         conf1 = conf + "_parity"
         with open(conf) as f:
             lines = [ln for ln in f.read().splitlines() if not ln.startswith("--numthreads")]
         with open(conf1, "w") as f:
             f.write("\n".join(lines + ["--numthreads=%d" % a.parity_threads]) + "\n")
-        dt, _ = run(REF, work, conf1, os.path.join(work, "out_cpu"), a.parity_threads, os.path.join(work, "trace_cpu.txt"))
+        if a.cpu_trace_in:
+            shutil.copy(a.cpu_trace_in, os.path.join(work, "trace_cpu.txt"))
+            dt = float("nan")
+            res["cpu_parity_trace"] = os.path.basename(a.cpu_trace_in)
+        else:
+            dt, _ = run(REF, work, conf1, os.path.join(work, "out_cpu"), a.parity_threads, os.path.join(work, "trace_cpu.txt"))
+        if a.cpu_trace_out:
+            shutil.copy(os.path.join(work, "trace_cpu.txt"), a.cpu_trace_out)
         res["cpu_parity_wall_s"] = dt
         res["cpu_parity_threads"] = a.parity_threads
         tc = parse_trace(os.path.join(work, "trace_cpu.txt"))
@@ -135,7 +154,8 @@ def main():
         res["label_mismatch_per_iteration"] = [int((x != y).sum()) if len(x) == len(y) else -1 for x, y in lab]
         res["labels_bit_exact"] = len(tc) == len(tg) and all(m == 0 for m in res["label_mismatch_per_iteration"])
         res["all_meshes_bit_exact"] = len(tc) == len(tg) and res["hashes_equal"] == n
-        if GROUP:   # the group driver only writes GIFTI (placeholder files under the FSL stand-in): the traces carry the comparison
+        res["first_mesh_mismatch"] = next((i for i in range(n) if tc[i]["hash"] != tg[i]["hash"]), -1)
+        if GROUP or a.cpu_trace_in or a.skip_gpu:   # the group driver only writes GIFTI (placeholder files under the FSL stand-in): the traces carry the comparison
             res["final_sphere_max_abs_diff"] = 0.0 if res["all_meshes_bit_exact"] else float("nan")
         else:
             a_, b_ = read_asc(os.path.join(work, "out_cpu", "sphere.reg.asc")), read_asc(os.path.join(work, "out_gpu", "sphere.reg.asc"))

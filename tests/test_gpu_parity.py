@@ -589,3 +589,23 @@ def test_group_costs_vs_reference_golden(R, oracle_built):
         got = M.computePairwiseCostList(pairs, rp, la, lb)
         ok = ~np.isnan(got)
         assert ok.mean() > 0.9 and np.array_equal(got[ok], g[f"group_pair_s{sim}"][ok])
+
+
+def test_group_triplet_nan_energy_propagates(R, oracle_built):
+    """A strain energy that comes out NaN (det(F^T F) rounding below zero, reg_tools.cpp:585-587; seen 8 times in 7.6 M costs of a groupwise
+    run) must stay NaN like in the reference, not be mistaken for the 'folded' marker. Forced here with a NaN label vector."""
+    from newmsm_b200 import group_cost as GC
+    from cost_cases import group_triplet_case
+    c = group_setup(S=2, cp_level=1, data_level=3, tpl_level=3, D=2)
+    orig, trip, rot_t, (rt, ta, tb, tc) = group_triplet_case(oracle_built, c, n=400)
+    labels = np.array(c["labels"], dtype=np.float64, copy=True)
+    labels[3] = np.nan
+    Mt = GC.DiscreteGroupModel(R.Mesh(c["tpl"], c["tpl_tri"]))
+    got = Mt.computeTripletCostList(c["cps"], orig, rot_t, labels, trip, rt, ta, tb, tc, 0.05)
+    ref = oracle_built.oracle_group_triplet_costs(c["cps"], orig, rot_t, labels, trip, rt, ta, tb, tc, 0.05)
+    touched = (ta == 3) | (tb == 3) | (tc == 3)
+    assert touched.any() and np.isnan(ref[touched]).all()
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    assert np.array_equal(got[~touched], ref[~touched])
+    got_fix = Mt.computeTripletCostList(c["cps"], orig, rot_t, labels, trip, rt, ta, tb, tc, 0.05, fixnan=True)
+    assert np.all(got_fix[touched] == 1e7) and np.array_equal(got_fix[~touched], ref[~touched])

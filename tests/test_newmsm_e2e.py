@@ -55,3 +55,19 @@ def test_gmsm_costs_match_reference_in_process():
     assert bad_p == 0 and bad_t == 0, line[0]
     used = [ln for ln in res["gpu_split"] if ln.startswith("[msmgpu group]")]
     assert used and "pair batches" in used[0], res["gpu_split"]
+
+
+def test_gmsm_two_devices_same_result():
+    """MSMGPU_DEVICES=2: subjects (fields) and pair blocks sharded over two GPUs inside the one reference process; the result must not
+    depend on the device count (same traces as the single-thread reference). Needs 2 GPUs: skipped on a 1-GPU box."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    if not all(os.path.exists(b) for b in BINS):
+        pytest.skip("integration/_build/newmsm_gpu not built (needs /root/reference at build time)")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "newmsm_e2e.py"), "--level", "4", "--config", "gMSM", "--D", "2", "--threads", "4",
+                          "--skip-timing-cpu", "--levels-drop", "2", "--it-scale", "0.25", "--group", "5", "--devices", "2"],
+                         capture_output=True, text=True, timeout=1500)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    assert res["trace_calls"][0] == res["trace_calls"][1] and res["all_meshes_bit_exact"], (res["hashes_equal"], res["trace_calls"])
