@@ -243,7 +243,7 @@ static msmgpu_status mesh_create_impl(msmgpu_ctx* ctx, int nv, const double* xyz
     MSM_CUDA(m->xyz.alloc(3 * (size_t)nv, s));
     MSM_CUDA(m->tri.alloc(3 * (size_t)nt, s));
     MSM_CUDA(m->rec.alloc((size_t)nt, s));
-    MSM_CUDA(m->aabb.alloc(6 * (size_t)nt, s));
+    MSM_CUDA(m->area_tab.alloc((size_t)nt, s));
     MSM_CUDA(m->qbox.alloc((size_t)nt, s));
     MSM_CUDA(m->cull.alloc((size_t)nt, s));
     MSM_CUDA(cudaMemcpyAsync(m->xyz.p, xyz, 3 * (size_t)nv * sizeof(double), kind, s));

@@ -97,12 +97,12 @@ struct msmgpu_mesh {
     msm::DevBuf<double> xyz;   // [nv][3]
     msm::DevBuf<int> tri;      // [nt][3]
     msm::DevBuf<msm::TriRec> rec; // [nt] one 128-byte query record per triangle (gather-free leaf scans)
-    msm::DevBuf<double> aabb;  // [nt][6] lo xyz, hi xyz (octree.cpp:46-59)
+    msm::DevBuf<double> area_tab;  // [nt] Triangle::area of the CURRENT coordinates (triangle.cpp:47-50), read by the vertex areas
     msm::DevBuf<uint4> qbox;   // [nt] the same box on the octree's depth-18 lattice (octree_build.cu: pack_qbox)
     msm::DevBuf<float4> cull;  // [nt] centre + r^2 of the conservative cull sphere (pack_cull)
     msm::DevBuf<float> feat;   // optional resident payload, vertex-major rows [nv][feat_D] (Mesh::pvalues, mesh.h:44)
     int feat_D = 0;
-    bool tables_dirty = false;   // rec / aabb / cull not yet computed from xyz (msm::ensure_tables batches that work)
+    bool tables_dirty = false;   // rec / qbox / cull / area_tab not yet computed from xyz (msm::ensure_tables batches that work)
     msmgpu_mesh* area_source = nullptr;   // mesh whose geometry the cached Triangle areas belong to (msmgpu_mesh_set_area_source)
     msm::DevBuf<double> tri_area;         // optional explicit cached Triangle::area values [nt] (msmgpu_mesh_set_triangle_areas)
 };

@@ -155,7 +155,7 @@ __device__ __forceinline__ uint4 pack_qbox(const double* lo, const double* hi) {
 // per-triangle tables
 // ------------------------------------------------------------------------------------------
 struct TableJob {
-    const double* xyz; const int* tri; TriRec* rec; double* aabb; float4* cull; uint4* qbox; int nt;
+    const double* xyz; const int* tri; TriRec* rec; double* area; float4* cull; uint4* qbox; int nt;
 };
 
 __global__ void __launch_bounds__(256) k_mesh_tables(const TableJob* __restrict__ jobs) {
@@ -177,9 +177,8 @@ __global__ void __launch_bounds__(256) k_mesh_tables(const TableJob* __restrict_
             }
         }
     }
-#pragma unroll
-    for (int a = 0; a < 3; ++a) { job.aabb[6 * (size_t)t + a] = lo[a]; job.aabb[6 * (size_t)t + 3 + a] = hi[a]; }
-    job.qbox[t] = pack_qbox(lo, hi);
+    job.qbox[t] = pack_qbox(lo, hi);   // the FP64 box itself is not stored: below the lattice (depth > 17) k_chunk_stats rebuilds it from the record
+    job.area[t] = tri_area_cached(V3{cv[0], cv[1], cv[2]}, V3{cv[3], cv[4], cv[5]}, V3{cv[6], cv[7], cv[8]});   // Triangle::area of this geometry
     TriRec r;
     make_trirec(V3{cv[0], cv[1], cv[2]}, V3{cv[3], cv[4], cv[5]}, V3{cv[6], cv[7], cv[8]}, r);
     job.rec[t] = r;
@@ -195,7 +194,7 @@ msmgpu_status ensure_tables(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes) 
     for (int i = 0; i < n; ++i) {
         msmgpu_mesh* m = meshes[i];
         if (!m->tables_dirty || m->nt == 0) { m->tables_dirty = false; continue; }
-        jobs.push_back(TableJob{m->xyz.p, m->tri.p, m->rec.p, m->aabb.p, m->cull.p, m->qbox.p, m->nt});
+        jobs.push_back(TableJob{m->xyz.p, m->tri.p, m->rec.p, m->area_tab.p, m->cull.p, m->qbox.p, m->nt});
         max_nt = std::max(max_nt, m->nt);
         m->tables_dirty = false;
     }
@@ -349,7 +348,7 @@ __device__ __forceinline__ int team_min(int v, int* smem) {
 template <int TPC, int IPT>
 __global__ void __launch_bounds__(TPC == 32 ? 256 : TPC) k_chunk_stats(int node_begin, int n_level, int max_chunks, const int4* __restrict__ nodes,
                                                                         const BuildNode* __restrict__ bn, const int* __restrict__ pairs,
-                                                                        const double* const* __restrict__ mesh_aabb,
+                                                                        const TriRec* const* __restrict__ mesh_rec,
                                                                         const uint4* const* __restrict__ mesh_qbox, double root_half,
                                                                         int* __restrict__ stats, unsigned char* __restrict__ pmask, int level_base) {
     constexpr int K = TPC * IPT;
@@ -367,7 +366,7 @@ __global__ void __launch_bounds__(TPC == 32 ? 256 : TPC) k_chunk_stats(int node_
     else if (!live) return;                                                // CTA-uniform
     const BuildNode b = bn[node_begin + li];
     const double half = ldexp(root_half, -b.depth);
-    const double* __restrict__ aabb = mesh_aabb[b.mesh];
+    const TriRec* __restrict__ rec = mesh_rec[b.mesh];
     const uint4* __restrict__ qbox = mesh_qbox[b.mesh];
     const bool on_grid = b.depth <= kGridMaxDepth;          // uniform over the team
     int L0[3] = {0, 0, 0}, Hh = 0;
@@ -390,7 +389,20 @@ __global__ void __launch_bounds__(TPC == 32 ? 256 : TPC) k_chunk_stats(int node_
             unsigned mask;
             const int tid = __ldg(pairs + nd.y + p);
             if (on_grid) classify_q(__ldg(qbox + tid), L0, Hh, a[k], mask);
-            else classify(aabb + 6 * (size_t)tid, b.lo, half, a[k], mask);
+            else {   // deeper than the lattice: the triangle's FP64 box from its record, same min / max as k_mesh_tables (octree.cpp:46-59)
+                const double* v = rec[tid].v;
+                double bb[6];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    double lo = v[d], hi = v[d];
+                    if (v[3 + d] < lo) lo = v[3 + d];
+                    if (v[3 + d] > hi) hi = v[3 + d];
+                    if (v[6 + d] < lo) lo = v[6 + d];
+                    if (v[6 + d] > hi) hi = v[6 + d];
+                    bb[d] = lo; bb[3 + d] = hi;
+                }
+                classify(bb, b.lo, half, a[k], mask);
+            }
             pmask[(size_t)(nd.y - level_base) + p] = (unsigned char)mask;   // kept for k_scatter_chunk: the 48-byte AABB is gathered once per level, not twice
 #pragma unroll
             for (int c = 0; c < 8; ++c) c8[c] += (mask >> c) & 1u;
@@ -576,13 +588,13 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
     MSM_TRY(ensure_tables(ctx, n, meshes));
     long long total_t = 0;
     std::vector<int> h_nt(n), h_off(n);
-    std::vector<const double*> h_aabb(n);
+    std::vector<const TriRec*> h_rec(n);
     std::vector<const uint4*> h_qbox(n);
     for (int i = 0; i < n; ++i) {
         if (!meshes[i] || meshes[i]->ctx != ctx) return fail(MSMGPU_ERR_INVALID, "forest_build: mesh from another context");
         h_nt[i] = meshes[i]->nt;
         h_off[i] = (int)total_t;
-        h_aabb[i] = meshes[i]->aabb.p;
+        h_rec[i] = meshes[i]->rec.p;
         h_qbox[i] = meshes[i]->qbox.p;
         total_t += meshes[i]->nt;
     }
@@ -597,7 +609,7 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
         auto F = std::make_shared<Forest>();
         F->ctx = ctx;
         DevBuf<BuildNode> bn;
-        DevBuf<const double*> d_aabb;
+        DevBuf<const TriRec*> d_rec;
         DevBuf<const uint4*> d_qbox;
         DevBuf<int> d_nt, d_off;
         MSM_CUDA(F->nodes.alloc(node_cap, s));
@@ -609,12 +621,12 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
         long long level_entries = total_t;
         MSM_CUDA(F->node_depth.alloc(node_cap, s));
         MSM_CUDA(bn.alloc(node_cap, s));
-        MSM_CUDA(d_aabb.alloc(n, s));
+        MSM_CUDA(d_rec.alloc(n, s));
         MSM_CUDA(d_qbox.alloc(n, s));
         MSM_CUDA(cudaMemcpyAsync(d_qbox.p, h_qbox.data(), n * sizeof(uint4*), cudaMemcpyHostToDevice, s));
         MSM_CUDA(d_nt.alloc(n, s));
         MSM_CUDA(d_off.alloc(n, s));
-        MSM_CUDA(cudaMemcpyAsync(d_aabb.p, h_aabb.data(), n * sizeof(double*), cudaMemcpyHostToDevice, s));
+        MSM_CUDA(cudaMemcpyAsync(d_rec.p, h_rec.data(), n * sizeof(TriRec*), cudaMemcpyHostToDevice, s));
         MSM_CUDA(cudaMemcpyAsync(d_nt.p, h_nt.data(), n * sizeof(int), cudaMemcpyHostToDevice, s));
         MSM_CUDA(cudaMemcpyAsync(d_off.p, h_off.data(), n * sizeof(int), cudaMemcpyHostToDevice, s));
         {
@@ -653,11 +665,11 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
             if (max_chunks > 65535) return fail(MSMGPU_ERR_CAPACITY, "forest_build: list too long for the chunk grid");
             const dim3 g_cta((unsigned)n_level, (unsigned)max_chunks), g_warp((unsigned)((n_level + 7) / 8), (unsigned)max_chunks);
             if (K == 8192)
-                k_chunk_stats<1024, 8><<<g_cta, 1024, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_aabb.p, d_qbox.p, root_half, stats.p, pmask.p, level_base);
+                k_chunk_stats<1024, 8><<<g_cta, 1024, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_rec.p, d_qbox.p, root_half, stats.p, pmask.p, level_base);
             else if (K == 1024)
-                k_chunk_stats<256, 4><<<g_cta, 256, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_aabb.p, d_qbox.p, root_half, stats.p, pmask.p, level_base);
+                k_chunk_stats<256, 4><<<g_cta, 256, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_rec.p, d_qbox.p, root_half, stats.p, pmask.p, level_base);
             else
-                k_chunk_stats<32, 4><<<g_warp, 256, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_aabb.p, d_qbox.p, root_half, stats.p, pmask.p, level_base);
+                k_chunk_stats<32, 4><<<g_warp, 256, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_rec.p, d_qbox.p, root_half, stats.p, pmask.p, level_base);
             MSM_LAUNCH_CHECK();
             MSM_CUDA(cudaMemsetAsync(totals.p + 2, 0, sizeof(int), s));
             k_node_combine<<<(n_level + 255) / 256, 256, 0, s>>>(node_begin, n_level, max_chunks, K, F->nodes.p, stats.p, split_flag.p, child_cnt.p,

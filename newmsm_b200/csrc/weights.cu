@@ -262,7 +262,7 @@ static msmgpu_status vertex_areas_batch(msmgpu_ctx* ctx, int S, msmgpu_mesh* con
     for (int i = 0; i < S; ++i) {
         h_tri[i] = meshes[i]->tri.p;
         h_rec[i] = meshes[i]->rec.p;
-        h_area[i] = meshes[i]->tri_area.p;
+        h_area[i] = meshes[i]->tri_area.p ? meshes[i]->tri_area.p : meshes[i]->area_tab.p;   // explicit cached values, else the table of the current geometry
         h_toff[i + 1] = h_toff[i] + meshes[i]->nt;
     }
     DevBuf<const int*> d_tri;
