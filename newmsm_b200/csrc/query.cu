@@ -71,8 +71,8 @@ __global__ void __launch_bounds__(256) k_bary_weights(TreeView T, int n, const d
 }
 
 // the same for a batch of jobs (blockIdx.y = job): different trees and/or different point sets, outputs concatenated
-template <int G>
-__global__ void __launch_bounds__(256) k_bary_weights_batch(const QueryJob* __restrict__ jobs, int* __restrict__ out_idx, double* __restrict__ out_w,
+template <int G, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_bary_weights_batch(const QueryJob* __restrict__ jobs, int* __restrict__ out_idx, double* __restrict__ out_w,
                                                             int* __restrict__ out_ne, int* __restrict__ out_status) {
     const QueryJob job = jobs[blockIdx.y];
     const int gl = threadIdx.x % G;
@@ -326,7 +326,14 @@ msmgpu_status launch_bary_weights(const TreeView& t, int n, const double* d_pts,
 msmgpu_status launch_bary_weights_batch(const QueryJob* d_jobs, int n_jobs, int max_n, int* d_idx, double* d_w, int* d_ne, int* d_status, cudaStream_t s) {
     if (n_jobs <= 0 || max_n <= 0) return MSMGPU_OK;
     const int g = query_group_width();
-    MSM_DISPATCH_G(g, (k_bary_weights_batch<G><<<dim3(query_blocks(max_n, G), (unsigned)n_jobs), 256, 0, s>>>(d_jobs, d_idx, d_w, d_ne, d_status)));
+    static const int minb = [] { const char* e = getenv("MSMGPU_WEIGHTS_MINB"); return e ? atoi(e) : 4; }();   // tuning knob: resident CTAs per SM (4: 64 registers, measured best)
+    const dim3 grid(query_blocks(max_n, g), (unsigned)n_jobs);
+    switch (minb) {
+        case 2: MSM_DISPATCH_G(g, (k_bary_weights_batch<G, 2><<<grid, 256, 0, s>>>(d_jobs, d_idx, d_w, d_ne, d_status))); break;
+        case 3: MSM_DISPATCH_G(g, (k_bary_weights_batch<G, 3><<<grid, 256, 0, s>>>(d_jobs, d_idx, d_w, d_ne, d_status))); break;
+        case 5: MSM_DISPATCH_G(g, (k_bary_weights_batch<G, 5><<<grid, 256, 0, s>>>(d_jobs, d_idx, d_w, d_ne, d_status))); break;
+        default: MSM_DISPATCH_G(g, (k_bary_weights_batch<G, 4><<<grid, 256, 0, s>>>(d_jobs, d_idx, d_w, d_ne, d_status))); break;
+    }
     MSM_LAUNCH_CHECK();
     return MSMGPU_OK;
 }
