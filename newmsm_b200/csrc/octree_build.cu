@@ -350,20 +350,22 @@ __global__ void __launch_bounds__(TPC == 32 ? 256 : TPC) k_chunk_stats(int node_
                                                                         const BuildNode* __restrict__ bn, const int* __restrict__ pairs,
                                                                         const TriRec* const* __restrict__ mesh_rec,
                                                                         const uint4* const* __restrict__ mesh_qbox, double root_half,
-                                                                        int* __restrict__ stats, unsigned char* __restrict__ pmask, int level_base) {
+                                                                        int* __restrict__ stats, unsigned char* __restrict__ pmask, int level_base,
+                                                                        const int* __restrict__ live, int n_live) {
     constexpr int K = TPC * IPT;
     constexpr int TEAMS = TPC == 32 ? 8 : 1;
     __shared__ int s_scan[TPC == 32 ? 1 : 33];
     __shared__ int s_red[TPC == 32 ? 1 : 32];
-    const int li = blockIdx.x * TEAMS + (TPC == 32 ? (threadIdx.x >> 5) : 0);   // nodes on grid.x (no 65535 limit)
+    const int slot = blockIdx.x * TEAMS + (TPC == 32 ? (threadIdx.x >> 5) : 0);   // live nodes on grid.x (no 65535 limit)
     const int chunk = blockIdx.y;
-    const bool node_ok = li < n_level;
+    const bool node_ok = slot < n_live;
+    const int li = node_ok ? live[slot] : 0;    // only nodes that can still split (>= 50 triangles) get a team; the others are final leaves
     int4 nd = make_int4(0, 0, 0, 0);
     if (node_ok) nd = nodes[node_begin + li];
     const int cnt = nd.z;
-    const bool live = node_ok && cnt >= kMaxTriangles && chunk * K < cnt;   // octree.cpp:69: the test only runs from 50 triangles on
-    if (TPC == 32) { if (!live) return; }                                  // warp-uniform
-    else if (!live) return;                                                // CTA-uniform
+    const bool busy = node_ok && cnt >= kMaxTriangles && chunk * K < cnt;   // octree.cpp:69: the test only runs from 50 triangles on
+    if (TPC == 32) { if (!busy) return; }                                  // warp-uniform
+    else if (!busy) return;                                                // CTA-uniform
     const BuildNode b = bn[node_begin + li];
     const double half = ldexp(root_half, -b.depth);
     const TriRec* __restrict__ rec = mesh_rec[b.mesh];
@@ -442,7 +444,7 @@ __global__ void __launch_bounds__(TPC == 32 ? 256 : TPC) k_chunk_stats(int node_
 
 // one thread per node of the level
 __global__ void k_node_combine(int node_begin, int n_level, int max_chunks, int K, const int4* __restrict__ nodes, int* __restrict__ stats,
-                               int* __restrict__ split_flag, int* __restrict__ child_cnt, int* __restrict__ max_child_cnt) {
+                               int* __restrict__ split_flag, int* __restrict__ child_cnt, int* __restrict__ max_child_cnt, int* __restrict__ n_live_next) {
     const int li = blockIdx.x * blockDim.x + threadIdx.x;
     if (li >= n_level) return;
     const int cnt = nodes[node_begin + li].z;
@@ -460,10 +462,16 @@ __global__ void k_node_combine(int node_begin, int n_level, int max_chunks, int 
         }
     }
     split_flag[li] = split;
-    int mx = 0;
+    int mx = 0, nl = 0;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) { child_cnt[li * 8 + c] = split ? tot[c] : 0; mx = max(mx, split ? tot[c] : 0); }
+    for (int c = 0; c < 8; ++c) {
+        const int v = split ? tot[c] : 0;
+        child_cnt[li * 8 + c] = v;
+        mx = max(mx, v);
+        nl += v >= kMaxTriangles;
+    }
     if (mx > 0) atomicMax(max_child_cnt, mx);   // longest list of the next level (picks its team width)
+    if (nl > 0) atomicAdd(n_live_next, nl);     // children that may split again = the teams of the next level
 }
 
 // One thread per node of the level: create the 8 children of every splitting node.
@@ -471,7 +479,8 @@ __global__ void k_make_children(int node_begin, int n_level, int4* __restrict__ 
                                 unsigned char* __restrict__ node_depth,
                                 const int* __restrict__ split_flag, const int* __restrict__ split_rank,
                                 const int* __restrict__ child_cnt, const int* __restrict__ child_off,
-                                int next_node_begin, int next_pair_base, double root_half, int node_cap) {
+                                int next_node_begin, int next_pair_base, double root_half, int node_cap,
+                                int* __restrict__ live_next, int* __restrict__ live_cursor) {
     const int li = blockIdx.x * blockDim.x + threadIdx.x;
     if (li >= n_level) return;
     if (!split_flag[li]) return;
@@ -496,6 +505,16 @@ __global__ void k_make_children(int node_begin, int n_level, int4* __restrict__ 
         node_depth[first + c] = (unsigned char)(b.depth + 1);
         nodes[first + c] = make_int4(-1, next_pair_base + child_off[li * 8 + c], child_cnt[li * 8 + c], g);
     }
+    // work list of the next level: its nodes with >= 50 triangles (any order: every per-node result is stored by node index)
+    int nl = 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) nl += child_cnt[li * 8 + c] >= kMaxTriangles;
+    if (nl > 0) {
+        int o = atomicAdd(live_cursor, nl);
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            if (child_cnt[li * 8 + c] >= kMaxTriangles) live_next[o++] = 8 * split_rank[li] + c;
+    }
 }
 
 template <int TPC, int IPT>
@@ -504,13 +523,15 @@ __global__ void __launch_bounds__(TPC == 32 ? 256 : TPC) k_scatter_chunk(int nod
                                                                           const int* __restrict__ split_flag,
                                                                           const int* __restrict__ list_start, const int* __restrict__ list_count,
                                                                           const int* __restrict__ child_off, const int* __restrict__ stats,
-                                                                          int next_pair_base) {
+                                                                          int next_pair_base, const int* __restrict__ live, int n_live) {
     constexpr int K = TPC * IPT;
     constexpr int TEAMS = TPC == 32 ? 8 : 1;
     __shared__ unsigned long long s_scan[TPC == 32 ? 1 : 33];
-    const int li = blockIdx.x * TEAMS + (TPC == 32 ? (threadIdx.x >> 5) : 0);   // nodes on grid.x (no 65535 limit)
+    const int slot = blockIdx.x * TEAMS + (TPC == 32 ? (threadIdx.x >> 5) : 0);   // live nodes on grid.x (no 65535 limit)
     const int chunk = blockIdx.y;
-    if (li >= n_level || !split_flag[li]) return;
+    if (slot >= n_live) return;
+    const int li = live[slot];
+    if (!split_flag[li]) return;
     const int cnt = list_count[li];
     if (chunk * K >= cnt) return;
     const int start = list_start[li];
@@ -641,8 +662,15 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
         long long n_pairs = total_t;
         int depth = 0;
         bool overflow = false;
-        DevBuf<int> split_flag, split_rank, child_cnt, child_off, list_start, list_count, totals, stats;
-        MSM_CUDA(totals.alloc(3, s));
+        DevBuf<int> split_flag, split_rank, child_cnt, child_off, list_start, list_count, totals, stats, live, live_next;
+        MSM_CUDA(totals.alloc(5, s));   // [0] splits, [1] new list entries, [2] longest child list, [3] live children, [4] live-list cursor
+        int n_live = n;                 // every root is a candidate
+        MSM_CUDA(live.alloc(n, s));
+        {
+            std::vector<int> ident(n);
+            for (int i = 0; i < n; ++i) ident[i] = i;
+            MSM_CUDA(cudaMemcpyAsync(live.p, ident.data(), n * sizeof(int), cudaMemcpyHostToDevice, s));   // pageable: staged before return
+        }
         int level_max_cnt = 1;
         for (int v : h_nt) level_max_cnt = std::max(level_max_cnt, v);
         while (n_level > 0) {
@@ -663,22 +691,23 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
             max_chunks = std::max(1, (max_cnt + K - 1) / K);
             MSM_CUDA(stats.alloc((size_t)n_level * max_chunks * kStatInts, s));
             if (max_chunks > 65535) return fail(MSMGPU_ERR_CAPACITY, "forest_build: list too long for the chunk grid");
-            const dim3 g_cta((unsigned)n_level, (unsigned)max_chunks), g_warp((unsigned)((n_level + 7) / 8), (unsigned)max_chunks);
-            if (K == 8192)
-                k_chunk_stats<1024, 8><<<g_cta, 1024, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_rec.p, d_qbox.p, root_half, stats.p, pmask.p, level_base);
+            const dim3 g_cta((unsigned)std::max(n_live, 1), (unsigned)max_chunks), g_warp((unsigned)((std::max(n_live, 1) + 7) / 8), (unsigned)max_chunks);
+            if (n_live == 0) {}   // nothing can split: k_node_combine clears the flags and the loop ends
+            else if (K == 8192)
+                k_chunk_stats<1024, 8><<<g_cta, 1024, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_rec.p, d_qbox.p, root_half, stats.p, pmask.p, level_base, live.p, n_live);
             else if (K == 1024)
-                k_chunk_stats<256, 4><<<g_cta, 256, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_rec.p, d_qbox.p, root_half, stats.p, pmask.p, level_base);
+                k_chunk_stats<256, 4><<<g_cta, 256, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_rec.p, d_qbox.p, root_half, stats.p, pmask.p, level_base, live.p, n_live);
             else
-                k_chunk_stats<32, 4><<<g_warp, 256, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_rec.p, d_qbox.p, root_half, stats.p, pmask.p, level_base);
+                k_chunk_stats<32, 4><<<g_warp, 256, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_rec.p, d_qbox.p, root_half, stats.p, pmask.p, level_base, live.p, n_live);
             MSM_LAUNCH_CHECK();
-            MSM_CUDA(cudaMemsetAsync(totals.p + 2, 0, sizeof(int), s));
+            MSM_CUDA(cudaMemsetAsync(totals.p + 2, 0, 3 * sizeof(int), s));
             k_node_combine<<<(n_level + 255) / 256, 256, 0, s>>>(node_begin, n_level, max_chunks, K, F->nodes.p, stats.p, split_flag.p, child_cnt.p,
-                                                                 totals.p + 2);
+                                                                 totals.p + 2, totals.p + 3);
             MSM_LAUNCH_CHECK();
             MSM_TRY(exclusive_scan_i32(split_flag.p, split_rank.p, n_level, totals.p, s));
             MSM_TRY(exclusive_scan_i32(child_cnt.p, child_off.p, n_level * 8, totals.p + 1, s));
-            int h_tot[3];
-            MSM_CUDA(cudaMemcpyAsync(h_tot, totals.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, s));
+            int h_tot[4];
+            MSM_CUDA(cudaMemcpyAsync(h_tot, totals.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
             MSM_CUDA(cudaStreamSynchronize(s));
             const int n_split = h_tot[0];
             const int new_pairs = h_tot[1];
@@ -686,21 +715,24 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
             if ((long long)n_nodes + 8ll * n_split > node_cap || n_pairs + new_pairs > pair_cap) { overflow = true; break; }
             k_save_lists<<<(n_level + 255) / 256, 256, 0, s>>>(node_begin, n_level, F->nodes.p, list_start.p, list_count.p);
             MSM_LAUNCH_CHECK();
+            MSM_CUDA(live_next.alloc((size_t)std::max(h_tot[3], 1), s));
             k_make_children<<<(n_level + 255) / 256, 256, 0, s>>>(node_begin, n_level, F->nodes.p, bn.p, F->node_depth.p, split_flag.p,
                                                                  split_rank.p, child_cnt.p, child_off.p, n_nodes, (int)n_pairs, root_half,
-                                                                 (int)node_cap);
+                                                                 (int)node_cap, live_next.p, totals.p + 4);
             MSM_LAUNCH_CHECK();
             if (K == 8192)
                 k_scatter_chunk<1024, 8><<<g_cta, 1024, 0, s>>>(node_begin, n_level, max_chunks, bn.p, F->pairs.p, pmask.p, level_base, split_flag.p,
-                                                               list_start.p, list_count.p, child_off.p, stats.p, (int)n_pairs);
+                                                               list_start.p, list_count.p, child_off.p, stats.p, (int)n_pairs, live.p, n_live);
             else if (K == 1024)
                 k_scatter_chunk<256, 4><<<g_cta, 256, 0, s>>>(node_begin, n_level, max_chunks, bn.p, F->pairs.p, pmask.p, level_base, split_flag.p,
-                                                             list_start.p, list_count.p, child_off.p, stats.p, (int)n_pairs);
+                                                             list_start.p, list_count.p, child_off.p, stats.p, (int)n_pairs, live.p, n_live);
             else
                 k_scatter_chunk<32, 4><<<g_warp, 256, 0, s>>>(node_begin, n_level, max_chunks, bn.p, F->pairs.p, pmask.p, level_base, split_flag.p,
-                                                             list_start.p, list_count.p, child_off.p, stats.p, (int)n_pairs);
+                                                             list_start.p, list_count.p, child_off.p, stats.p, (int)n_pairs, live.p, n_live);
             MSM_LAUNCH_CHECK();
             level_max_cnt = h_tot[2];
+            std::swap(live, live_next);       // (stream-ordered: the old list is released after the kernels that read it)
+            n_live = h_tot[3];
             level_base = (int)n_pairs;        // the children's lists were appended at the old end of `pairs`
             level_entries = new_pairs;
             node_begin = n_nodes;
