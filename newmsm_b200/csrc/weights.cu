@@ -104,64 +104,72 @@ __global__ void k_bucket_fill(E e, const int* __restrict__ ptr, int* __restrict_
         val[pos] = e.val(x, j);
     }
 }
-// Sort each bucket by id. Buckets hold a handful of entries (vertex valence, or the ~3 N_s / N_t sources that fall
-// into one target's triangles): up to 8 entries are sorted in registers (odd-even transposition network), longer
-// ones by insertion in place.
-__global__ void k_bucket_sort(int nkeys, const int* __restrict__ ptr, int* __restrict__ id, double* __restrict__ val) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= nkeys) return;
-    const int b = ptr[k], e = ptr[k + 1], len = e - b;
-    if (len <= 1) return;
-    if (len <= 8) {
-        int ki[8];
-        double vi[8];
+// Sort each bucket by id. Buckets hold a handful of entries (vertex valence, or the ~3 N_s / N_t sources that fall into one
+// target's triangles, ~15): buckets of up to 32 entries are sorted in REGISTERS by a bitonic network on packed keys
+// (id << 5 | position; ids below 2^26), the values are then moved out of place in the sorted order (val_in -> val_out, no hazard,
+// nothing spilled to local memory). Longer buckets (or larger ids) are copied and sorted by insertion in place.
+template <int N>
+__device__ __forceinline__ void bitonic_sort_keys(int (&key)[N]) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            ki[i] = i < len ? id[b + i] : INT_MAX;
-            vi[i] = i < len ? val[b + i] : 0.0;
-        }
+    for (int k = 2; k <= N; k <<= 1) {
 #pragma unroll
-        for (int round = 0; round < 8; ++round) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
 #pragma unroll
-            for (int i = round & 1; i + 1 < 8; i += 2) {
-                if (ki[i] > ki[i + 1]) {
-                    const int tk = ki[i]; ki[i] = ki[i + 1]; ki[i + 1] = tk;
-                    const double tv = vi[i]; vi[i] = vi[i + 1]; vi[i + 1] = tv;
+            for (int i = 0; i < N; ++i) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const bool up = (i & k) == 0;
+                    const int a = key[i], b = key[l];
+                    const bool sw = up ? a > b : a < b;
+                    key[i] = sw ? b : a;
+                    key[l] = sw ? a : b;
                 }
             }
         }
+    }
+}
+template <int N>
+__device__ __forceinline__ void sort_bucket_regs(int b, int len, int* __restrict__ id, const double* __restrict__ val_in, double* __restrict__ val_out) {
+    int key[N];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-            if (i < len) { id[b + i] = ki[i]; val[b + i] = vi[i]; }
-        return;
-    }
-    if (len <= 32) {   // medium buckets (a target's share of the reverse weights: ~15): sort a private copy, one read and one write of the bucket
-        int ki[32];
-        double vi[32];
-        for (int i = 0; i < len; ++i) { ki[i] = id[b + i]; vi[i] = val[b + i]; }
-        for (int i = 1; i < len; ++i) {
-            const int k0 = ki[i];
-            const double v0 = vi[i];
-            int j = i - 1;
-            while (j >= 0 && ki[j] > k0) { ki[j + 1] = ki[j]; vi[j + 1] = vi[j]; --j; }
-            ki[j + 1] = k0; vi[j + 1] = v0;
+    for (int i = 0; i < N; ++i) key[i] = i < len ? ((id[b + i] << 5) | i) : INT_MAX;
+    bitonic_sort_keys<N>(key);
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+        if (i < len) {
+            id[b + i] = key[i] >> 5;
+            val_out[b + i] = val_in[b + (key[i] & 31)];
         }
-        for (int i = 0; i < len; ++i) { id[b + i] = ki[i]; val[b + i] = vi[i]; }
+}
+__global__ void __launch_bounds__(256) k_bucket_sort(int nkeys, const int* __restrict__ ptr, int* __restrict__ id, const double* __restrict__ val_in,
+                                                     double* __restrict__ val_out, int packable) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nkeys) return;
+    const int b = ptr[k], e = ptr[k + 1], len = e - b;
+    if (len <= 0) return;
+    if (len == 1) { val_out[b] = val_in[b]; return; }
+    if (packable && len <= 32) {
+        if (len <= 4) sort_bucket_regs<4>(b, len, id, val_in, val_out);
+        else if (len <= 8) sort_bucket_regs<8>(b, len, id, val_in, val_out);
+        else if (len <= 16) sort_bucket_regs<16>(b, len, id, val_in, val_out);
+        else sort_bucket_regs<32>(b, len, id, val_in, val_out);
         return;
     }
+    for (int i = b; i < e; ++i) val_out[i] = val_in[i];
     for (int i = b + 1; i < e; ++i) {
         const int ki = id[i];
-        const double vi = val[i];
+        const double vi = val_out[i];
         int j = i - 1;
-        while (j >= b && id[j] > ki) { id[j + 1] = id[j]; val[j + 1] = val[j]; --j; }
-        id[j + 1] = ki; val[j + 1] = vi;
+        while (j >= b && id[j] > ki) { id[j + 1] = id[j]; val_out[j + 1] = val_out[j]; --j; }
+        id[j + 1] = ki; val_out[j + 1] = vi;
     }
 }
 
 // `capacity` >= the number of triples that will be emitted (an upper bound avoids a host round trip)
 template <class E>
-static msmgpu_status bucketize(const E& e, int n_src, int nkeys, size_t capacity, Buckets& B, cudaStream_t s) {
+static msmgpu_status bucketize(const E& e, int n_src, int nkeys, size_t capacity, Buckets& B, cudaStream_t s, int max_id = INT_MAX) {
     DevBuf<int> cnt, cursor;
+    DevBuf<double> unsorted;   // values in arrival order; B.val receives them in sorted order
     MSM_CUDA(cnt.alloc(nkeys, s));
     MSM_CUDA(cursor.alloc(nkeys, s));
     MSM_CUDA(B.ptr.alloc((size_t)nkeys + 1, s));
@@ -177,9 +185,10 @@ static msmgpu_status bucketize(const E& e, int n_src, int nkeys, size_t capacity
     k_bucket_count<E><<<gs, 256, 0, s>>>(e, cnt.p);
     MSM_LAUNCH_CHECK();
     MSM_TRY(exclusive_scan_i32(cnt.p, B.ptr.p, nkeys, B.ptr.p + nkeys, s));
-    k_bucket_fill<E><<<gs, 256, 0, s>>>(e, B.ptr.p, cursor.p, B.id.p, B.val.p);
+    MSM_CUDA(unsorted.alloc(capacity, s));
+    k_bucket_fill<E><<<gs, 256, 0, s>>>(e, B.ptr.p, cursor.p, B.id.p, unsorted.p);
     MSM_LAUNCH_CHECK();
-    k_bucket_sort<<<gk, 256, 0, s>>>(nkeys, B.ptr.p, B.id.p, B.val.p);
+    k_bucket_sort<<<gk, 256, 0, s>>>(nkeys, B.ptr.p, B.id.p, unsorted.p, B.val.p, max_id < (1 << 26) ? 1 : 0);
     MSM_LAUNCH_CHECK();
     return MSMGPU_OK;
 }
@@ -301,7 +310,7 @@ static msmgpu_status vertex_areas_batch(msmgpu_ctx* ctx, int S, msmgpu_mesh* con
         if (!h_ovf) return MSMGPU_OK;      // otherwise some vertex has more than kIncSlots triangles: generic path below
     }
     Buckets B;
-    MSM_TRY(bucketize(emit, total_t, nkeys, 3 * (size_t)total_t, B, s));
+    MSM_TRY(bucketize(emit, total_t, nkeys, 3 * (size_t)total_t, B, s, total_t));   // ids = triangle ids
     k_bucket_mean<<<(nkeys + 255) / 256, 256, 0, s>>>(nkeys, B.ptr.p, B.val.p, d_out);
     MSM_LAUNCH_CHECK();
     return MSMGPU_OK;   // (pageable H2D copies are staged before cudaMemcpyAsync returns, the host tables may go)
@@ -454,7 +463,7 @@ msmgpu_status adaptive_weights_build_batch(msmgpu_ctx* ctx, int S, msmgpu_mesh* 
     MSM_TRY(vertex_areas_batch(ctx, S, in_meshes, in_off, old_area.p));
 
     Buckets rr;   // reverse weights regrouped by (subject, target)
-    MSM_TRY(bucketize(EmitReverse{ridx.p, rw.p, rne.p, d_in_off.p, S, n_low, (int)NV}, (int)NV, (int)NL, 3 * (size_t)NV, rr, s));
+    MSM_TRY(bucketize(EmitReverse{ridx.p, rw.p, rne.p, d_in_off.p, S, n_low, (int)NV}, (int)NV, (int)NL, 3 * (size_t)NV, rr, s, max_nv));   // ids = source vertices
 
     auto store = std::make_shared<WeightsStore>();
     DevBuf<int> len;
@@ -475,7 +484,7 @@ msmgpu_status adaptive_weights_build_batch(msmgpu_ctx* ctx, int S, msmgpu_mesh* 
     // correction[src] = sum over targets (ascending) of the area-scaled weights (resampler.cpp:114-116)
     Buckets cols;
     MSM_TRY(bucketize(EmitCsrColumns{store->rowptr.p, store->col.p, store->val.p, d_in_off.p, fne.p, rr.ptr.p, n_low, (int)NL}, (int)NL, (int)NV,
-                      3 * (size_t)NL, cols, s));
+                      3 * (size_t)NL, cols, s, (int)std::min<long long>(NL, INT_MAX)));   // ids = global rows
     k_area_ratio<<<(unsigned)((NV + 255) / 256), 256, 0, s>>>((int)NV, S, n_low, d_in_off.p, ridx.p, rw.p, rne.p, fne.p, rr.ptr.p, new_area.p, cols.ptr.p,
                                                               cols.id.p, cols.val.p, old_area.p, correction.p);   // correction := ratio
     MSM_LAUNCH_CHECK();
