@@ -275,7 +275,7 @@ def run_ours(a):
         with torch.cuda.stream(st):
             if ev: ev[0].record(st)
             low = R.Mesh.from_device(cx, n_low, d_low_xyz, len(low_tri), d_low_tri)
-            meshes = [R.Mesh.from_device(cx, nv, d_xyz[s_], nt, d_tri) for s_ in g]
+            meshes = R.Mesh.views_from_device(cx, nv, [d_xyz[s_] for s_ in g], nt, d_tri)   # the subjects' coordinates are already in HBM: viewed, not copied
             trees = R.Octree.build_batch(meshes + [low])
             low_tree = trees[-1]
             if ev: ev[1].record(st)

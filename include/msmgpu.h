@@ -73,6 +73,10 @@ msmgpu_status msmgpu_device_copy_peer(msmgpu_ctx* dst_ctx, void* dst, msmgpu_ctx
 /* replaces: newresampler::Mesh as geometry carrier (msm-newresampler/src/mesh.h:37-58) */
 msmgpu_status msmgpu_mesh_create(msmgpu_ctx* ctx, int nv, const double* xyz, int nt, const int32_t* tri, msmgpu_mesh** out);
 msmgpu_status msmgpu_mesh_create_dev(msmgpu_ctx* ctx, int nv, const double* d_xyz, int nt, const int32_t* d_tri, msmgpu_mesh** out);
+/* Device-resident pipelines: n meshes that share one topology and VIEW the caller's device buffers (d_xyz[i] [nv][3], d_tri [nt][3];
+ * no copies; the buffers must stay valid and unchanged for the lifetime of the meshes and of the trees / weights built from them).
+ * The per-triangle tables of the batch live in one allocation. msmgpu_mesh_set_coords is refused on such a mesh. */
+msmgpu_status msmgpu_mesh_create_view_batch(msmgpu_ctx* ctx, int n, int nv, const double* const* d_xyz, int nt, const int32_t* d_tri, msmgpu_mesh** out);
 msmgpu_status msmgpu_mesh_set_coords(msmgpu_mesh* m, const double* xyz);   /* Mesh::set_coord for all vertices */
 void msmgpu_mesh_destroy(msmgpu_mesh* m);
 msmgpu_status msmgpu_mesh_shape(msmgpu_mesh* m, int* nv, int* nt);

@@ -49,6 +49,7 @@ _SIGNATURES = {
     "msmgpu_device_copy_peer": (_i, [_vp, _vp, _vp, _vp, C.c_size_t]),
     "msmgpu_mesh_create": (_i, [_vp, _i, _vp, _i, _vp, _pp]),
     "msmgpu_mesh_create_dev": (_i, [_vp, _i, _vp, _i, _vp, _pp]),
+    "msmgpu_mesh_create_view_batch": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp]),
     "msmgpu_mesh_set_coords": (_i, [_vp, _vp]),
     "msmgpu_mesh_destroy": (None, [_vp]),
     "msmgpu_mesh_shape": (_i, [_vp, _vp, _vp]),

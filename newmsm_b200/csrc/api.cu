@@ -184,6 +184,7 @@ msmgpu_status msmgpu_ctx_create(int device, void* stream, msmgpu_ctx** out) {
         unsigned long long thr = ~0ull;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
+    if (cudaHostAlloc((void**)&c->pinned, 64 * sizeof(int), cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); c->pinned = nullptr; }
     *out = c;
     return MSMGPU_OK;
 }
@@ -191,6 +192,7 @@ msmgpu_status msmgpu_ctx_create(int device, void* stream, msmgpu_ctx** out) {
 void msmgpu_ctx_destroy(msmgpu_ctx* c) {
     if (!c) return;
     cudaStreamSynchronize(c->stream);
+    if (c->pinned) cudaFreeHost(c->pinned);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -265,8 +267,41 @@ msmgpu_status msmgpu_mesh_create_dev(msmgpu_ctx* ctx, int nv, const double* d_xy
     return mesh_create_impl(ctx, nv, d_xyz, nt, d_tri, true, out);
 }
 
+msmgpu_status msmgpu_mesh_create_view_batch(msmgpu_ctx* ctx, int n, int nv, const double* const* d_xyz, int nt, const int32_t* d_tri, msmgpu_mesh** out) {
+    if (!ctx || !out || n <= 0 || nv <= 0 || nt <= 0 || !d_xyz || !d_tri) return fail(MSMGPU_ERR_INVALID, "mesh_create_view_batch: bad arguments");
+    for (int i = 0; i < n; ++i) {
+        out[i] = nullptr;
+        if (!d_xyz[i]) return fail(MSMGPU_ERR_INVALID, "mesh_create_view_batch: NULL coordinates");
+    }
+    MSM_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    // one allocation for the per-triangle tables of the whole batch: [rec | area | qbox | cull] per mesh, each 256-byte aligned
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t b_rec = up((size_t)nt * sizeof(TriRec)), b_area = up((size_t)nt * sizeof(double)), b_qbox = up((size_t)nt * sizeof(uint4)),
+                 b_cull = up((size_t)nt * sizeof(float4)), per_mesh = b_rec + b_area + b_qbox + b_cull;
+    auto slab = std::make_shared<DevBuf<unsigned char>>();
+    MSM_CUDA(slab->alloc(per_mesh * (size_t)n, s));
+    std::vector<std::unique_ptr<msmgpu_mesh>> made;
+    for (int i = 0; i < n; ++i) {
+        auto m = std::unique_ptr<msmgpu_mesh>(new msmgpu_mesh());
+        m->ctx = ctx; m->nv = nv; m->nt = nt; m->view = true; m->slab = slab;
+        unsigned char* base = slab->p + per_mesh * (size_t)i;
+        m->xyz.borrow(const_cast<double*>(d_xyz[i]), 3 * (size_t)nv);
+        m->tri.borrow(const_cast<int*>(d_tri), 3 * (size_t)nt);
+        m->rec.borrow(reinterpret_cast<TriRec*>(base), (size_t)nt);
+        m->area_tab.borrow(reinterpret_cast<double*>(base + b_rec), (size_t)nt);
+        m->qbox.borrow(reinterpret_cast<uint4*>(base + b_rec + b_area), (size_t)nt);
+        m->cull.borrow(reinterpret_cast<float4*>(base + b_rec + b_area + b_qbox), (size_t)nt);
+        m->tables_dirty = true;
+        made.push_back(std::move(m));
+    }
+    for (int i = 0; i < n; ++i) out[i] = made[i].release();
+    return MSMGPU_OK;
+}
+
 msmgpu_status msmgpu_mesh_set_coords(msmgpu_mesh* m, const double* xyz) {
     if (!m || !xyz) return fail(MSMGPU_ERR_INVALID, "mesh_set_coords: bad arguments");
+    if (m->view) return fail(MSMGPU_ERR_INVALID, "mesh_set_coords: the mesh is a view of the caller's buffers");
     MSM_CUDA(cudaSetDevice(m->ctx->device));
     MSM_CUDA(cudaMemcpyAsync(m->xyz.p, xyz, 3 * (size_t)m->nv * sizeof(double), cudaMemcpyHostToDevice, m->ctx->stream));
     MSM_TRY(mesh_refresh_tables(m));

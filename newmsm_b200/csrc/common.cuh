@@ -42,21 +42,26 @@ struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
     cudaStream_t s = nullptr;
+    bool own = true;     // false: a view of memory owned elsewhere (the caller's buffers, or a slab shared by a batch of meshes)
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; o.n = 0; }
-    DevBuf& operator=(DevBuf&& o) noexcept { release(); p = o.p; n = o.n; s = o.s; o.p = nullptr; o.n = 0; return *this; }
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), s(o.s), own(o.own) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { release(); p = o.p; n = o.n; s = o.s; own = o.own; o.p = nullptr; o.n = 0; return *this; }
     ~DevBuf() { release(); }
     cudaError_t alloc(size_t count, cudaStream_t stream) {
         release();
-        s = stream; n = count;
+        s = stream; n = count; own = true;
         if (count == 0) { p = nullptr; return cudaSuccess; }
         return cudaMallocAsync((void**)&p, count * sizeof(T), stream);
     }
+    void borrow(T* ptr, size_t count) {
+        release();
+        p = ptr; n = count; own = false;
+    }
     void release() {
-        if (p) cudaFreeAsync(p, s);
-        p = nullptr; n = 0;
+        if (p && own) cudaFreeAsync(p, s);
+        p = nullptr; n = 0; own = true;
     }
 };
 
@@ -89,6 +94,8 @@ struct msmgpu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    int* pinned = nullptr;   // 64 ints of page-locked host memory: small device -> host results inside launch sequences (level totals of the
+                             // octree build) arrive by plain DMA instead of the staged, stream-draining path of pageable copies
 };
 
 struct msmgpu_mesh {
@@ -103,6 +110,8 @@ struct msmgpu_mesh {
     msm::DevBuf<float> feat;   // optional resident payload, vertex-major rows [nv][feat_D] (Mesh::pvalues, mesh.h:44)
     int feat_D = 0;
     bool tables_dirty = false;   // rec / qbox / cull / area_tab not yet computed from xyz (msm::ensure_tables batches that work)
+    bool view = false;           // xyz / tri are the caller's device buffers (msmgpu_mesh_create_view_batch)
+    std::shared_ptr<msm::DevBuf<unsigned char>> slab;   // the per-triangle tables of a batch of view meshes live in one allocation
     msmgpu_mesh* area_source = nullptr;   // mesh whose geometry the cached Triangle areas belong to (msmgpu_mesh_set_area_source)
     msm::DevBuf<double> tri_area;         // optional explicit cached Triangle::area values [nt] (msmgpu_mesh_set_triangle_areas)
 };

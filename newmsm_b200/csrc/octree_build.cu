@@ -19,6 +19,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <climits>
 
 namespace msm {
@@ -673,7 +674,13 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
         }
         int level_max_cnt = 1;
         for (int v : h_nt) level_max_cnt = std::max(level_max_cnt, v);
+        static const bool timing = getenv("MSMGPU_BUILD_TIMING") != nullptr;
+        auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        double t_enq = 0, t_wait = 0, t_alloc = 0;
+        std::vector<cudaEvent_t> evs;
+        auto mark = [&] { if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); evs.push_back(e); } };
         while (n_level > 0) {
+            const double t0 = timing ? now() : 0;
             MSM_CUDA(split_flag.alloc(n_level, s));
             MSM_CUDA(split_rank.alloc(n_level, s));
             MSM_CUDA(child_cnt.alloc((size_t)n_level * 8, s));
@@ -681,6 +688,7 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
             MSM_CUDA(list_start.alloc(n_level, s));
             MSM_CUDA(list_count.alloc(n_level, s));
             // team width by the longest list of the level: whole CTAs at the top, warps at the bottom
+            if (timing) t_alloc += now() - t0;
             if (level_entries > pmask_cap) {
                 pmask_cap = level_entries + level_entries / 4;
                 MSM_CUDA(pmask.alloc((size_t)pmask_cap, s));
@@ -692,6 +700,7 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
             MSM_CUDA(stats.alloc((size_t)n_level * max_chunks * kStatInts, s));
             if (max_chunks > 65535) return fail(MSMGPU_ERR_CAPACITY, "forest_build: list too long for the chunk grid");
             const dim3 g_cta((unsigned)std::max(n_live, 1), (unsigned)max_chunks), g_warp((unsigned)((std::max(n_live, 1) + 7) / 8), (unsigned)max_chunks);
+            mark();
             if (n_live == 0) {}   // nothing can split: k_node_combine clears the flags and the loop ends
             else if (K == 8192)
                 k_chunk_stats<1024, 8><<<g_cta, 1024, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_rec.p, d_qbox.p, root_half, stats.p, pmask.p, level_base, live.p, n_live);
@@ -700,15 +709,20 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
             else
                 k_chunk_stats<32, 4><<<g_warp, 256, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_rec.p, d_qbox.p, root_half, stats.p, pmask.p, level_base, live.p, n_live);
             MSM_LAUNCH_CHECK();
+            mark();
             MSM_CUDA(cudaMemsetAsync(totals.p + 2, 0, 3 * sizeof(int), s));
             k_node_combine<<<(n_level + 255) / 256, 256, 0, s>>>(node_begin, n_level, max_chunks, K, F->nodes.p, stats.p, split_flag.p, child_cnt.p,
                                                                  totals.p + 2, totals.p + 3);
             MSM_LAUNCH_CHECK();
             MSM_TRY(exclusive_scan_i32(split_flag.p, split_rank.p, n_level, totals.p, s));
             MSM_TRY(exclusive_scan_i32(child_cnt.p, child_off.p, n_level * 8, totals.p + 1, s));
-            int h_tot[4];
+            int h_stack[4];
+            int* h_tot = ctx->pinned ? ctx->pinned : h_stack;
+            mark();
+            const double t1 = timing ? now() : 0;
             MSM_CUDA(cudaMemcpyAsync(h_tot, totals.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
             MSM_CUDA(cudaStreamSynchronize(s));
+            if (timing) { t_enq += t1 - t0; t_wait += now() - t1; }
             const int n_split = h_tot[0];
             const int new_pairs = h_tot[1];
             if (n_split == 0) break;
@@ -730,6 +744,7 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
                 k_scatter_chunk<32, 4><<<g_warp, 256, 0, s>>>(node_begin, n_level, max_chunks, bn.p, F->pairs.p, pmask.p, level_base, split_flag.p,
                                                              list_start.p, list_count.p, child_off.p, stats.p, (int)n_pairs, live.p, n_live);
             MSM_LAUNCH_CHECK();
+            mark();
             level_max_cnt = h_tot[2];
             std::swap(live, live_next);       // (stream-ordered: the old list is released after the kernels that read it)
             n_live = h_tot[3];
@@ -742,6 +757,22 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
             ++depth;
             if (depth > 40) return fail(MSMGPU_ERR_CAPACITY, "forest_build: depth limit (degenerate mesh?)");
         }
+        if (timing) {
+            cudaStreamSynchronize(s);
+            double ph[3] = {0, 0, 0};
+            for (size_t i = 0; i + 1 < evs.size(); ++i) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, evs[i], evs[i + 1]);
+                ph[i % 4 == 3 ? 0 : i % 4] += (i % 4 == 3) ? 0.0 : ms * 1e3;
+                if (i % 4 == 3) ph[2] += 0;   // (level boundary: host turn-around, counted with the wait below)
+            }
+            double turn = 0;
+            for (size_t i = 3; i + 1 < evs.size(); i += 4) { float ms = 0; cudaEventElapsedTime(&ms, evs[i], evs[i + 1]); turn += ms * 1e3; }
+            fprintf(stderr, "[msmgpu build] device time by phase: chunk stats %.0f us, combine + scans %.0f us, children + scatter %.0f us, between levels %.0f us\n",
+                    ph[0], ph[1], ph[2], turn);
+            for (cudaEvent_t e : evs) cudaEventDestroy(e);
+        }
+        if (timing) fprintf(stderr, "[msmgpu build] %d meshes, depth %d: host enqueue %.0f us (of which scratch allocation %.0f us), waiting for the level totals %.0f us\n", n, depth, t_enq, t_alloc, t_wait);
         if (overflow) { pair_cap *= 2; node_cap *= 2; continue; }
         F->n_nodes = n_nodes;
         F->n_pairs = (int)n_pairs;

@@ -72,6 +72,22 @@ class Mesh:
         check(m.L.msmgpu_mesh_create_dev(ctx.h, nv, ptr(d_xyz), nt, ptr(d_tri), C.byref(m.h)))
         return m
 
+    @classmethod
+    def views_from_device(cls, ctx: Context, nv: int, d_xyz_list, nt: int, d_tri) -> "list[Mesh]":
+        """msmgpu_mesh_create_view_batch: meshes that view the caller's device coordinate buffers (no copies, one table allocation)."""
+        n = len(d_xyz_list)
+        xs = (C.c_void_p * n)(*[x.data_ptr() if hasattr(x, "data_ptr") else int(x) for x in d_xyz_list])
+        hs = (C.c_void_p * n)()
+        check(ctx.L.msmgpu_mesh_create_view_batch(ctx.h, n, nv, xs, nt, ptr(d_tri), hs))
+        out = []
+        for i in range(n):
+            m = cls.__new__(cls)
+            m.ctx, m.L, m.xyz, m.tri, m.pvalues = ctx, ctx.L, None, None, None
+            m._keep = (d_xyz_list[i], d_tri)     # the viewed buffers must outlive the mesh
+            m.h = C.c_void_p(hs[i])
+            out.append(m)
+        return out
+
     def nvertices(self) -> int:
         nv = C.c_int()
         check(self.L.msmgpu_mesh_shape(self.h, C.byref(nv), None))

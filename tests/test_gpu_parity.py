@@ -609,3 +609,37 @@ def test_group_triplet_nan_energy_propagates(R, oracle_built):
     assert np.array_equal(got[~touched], ref[~touched])
     got_fix = Mt.computeTripletCostList(c["cps"], orig, rot_t, labels, trip, rt, ta, tb, tc, 0.05, fixnan=True)
     assert np.all(got_fix[touched] == 1e7) and np.array_equal(got_fix[~touched], ref[~touched])
+
+
+def test_view_meshes_match_copied_meshes(R, oracle_built, meshes):
+    """msmgpu_mesh_create_view_batch: meshes that view the caller's device buffers (no copies, one table allocation) give the same forest
+    and the same adaptive CSR as uploaded meshes, i.e. the oracle's; set_coords is refused on a view."""
+    import ctypes as C
+    import torch
+    L = capi.lib()
+    ctx = R.Context(0)
+    dev = torch.device("cuda", 0)
+    low_xyz, low_tri = synth.rotate_sphere(meshes[4][0], 0.01, 0.02, -0.015), meshes[4][1]
+    S = 3
+    xyz = [synth.jitter_sphere(meshes[5][0], meshes[5][1], seed=90 + s) for s in range(S)]
+    tri = np.ascontiguousarray(meshes[5][1], dtype=np.int32)
+    d_xyz = [torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in xyz]
+    d_tri = torch.from_numpy(tri).to(dev)
+    torch.cuda.synchronize()
+    views = R.Mesh.views_from_device(ctx, len(xyz[0]), d_xyz, len(tri), d_tri)
+    low = R.Mesh(low_xyz, low_tri, ctx=ctx)
+    trees = R.Octree.build_batch(views + [low])
+    for s in range(S):
+        ref = R.Octree(R.Mesh(xyz[s], tri, ctx=ctx))
+        for a, b in zip(trees[s].dump(), ref.dump()):
+            assert np.array_equal(a, b)
+    tp = (C.c_void_p * S)(*[t.h.value for t in trees[:S]])
+    mp = (C.c_void_p * S)(*[m.h.value for m in views])
+    w = (C.c_void_p * S)()
+    capi.check(L.msmgpu_adaptive_weights_batch(ctx.h, S, mp, tp, low.h, trees[-1].h, w))
+    for s in range(S):
+        W = R.Weights(L, C.c_void_p(w[s]))
+        for x, y in zip(W.csr(), oracle_built.oracle_adaptive_weights(xyz[s], tri, low_xyz, low_tri)):
+            assert np.array_equal(x, y)
+        W.close()
+    assert L.msmgpu_mesh_set_coords(views[0].h, capi.ptr(np.ascontiguousarray(xyz[1]))) == capi.ERR_INVALID
