@@ -280,7 +280,11 @@ msmgpu_status msmgpu_group_fields(msmgpu_ctx* ctx, int n_subjects, int nv, const
         std::vector<msmgpu_mesh*> meshes(L, nullptr);
         std::vector<msmgpu_weights*> ws(L, nullptr);
         msmgpu_status st = MSMGPU_OK;
-        for (int l = 0; l < L && st == MSMGPU_OK; ++l) st = msmgpu_mesh_create_dev(ctx, nv, d_rot.p + 3 * (size_t)l * nv, nt, d_tri.p, &meshes[l]);
+        {   // the L rotated copies are views of d_rot (no second copy), their tables share one allocation
+            std::vector<const double*> rot_ptrs(L);
+            for (int l = 0; l < L; ++l) rot_ptrs[l] = d_rot.p + 3 * (size_t)l * nv;
+            st = msmgpu_mesh_create_view_batch(ctx, L, nv, rot_ptrs.data(), nt, d_tri.p, meshes.data());
+        }
         // `rotated_mesh` is a COPY of the data mesh that is then moved with set_coord (DiscreteGroupModel.cpp:94-103): its cached
         // triangle areas, hence the source vertex areas metric_resample uses, are those of the un-moved mesh = meshes[0]
         for (int l = 1; l < L && st == MSMGPU_OK; ++l) st = msmgpu_mesh_set_area_source(meshes[l], meshes[0]);

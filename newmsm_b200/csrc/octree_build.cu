@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(TPC == 32 ? 256 : TPC) k_chunk_stats(int node_
     const int p0 = chunk * K + tl * IPT;
     int a[IPT];
     int local_sum = 0;
-    int c8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long lo4 = 0, hi4 = 0;   // per-child counts of this thread's entries, 16 bits per child (a chunk holds K <= 8192 < 2^16 entries)
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
         a[k] = 0;
@@ -408,7 +408,10 @@ __global__ void __launch_bounds__(TPC == 32 ? 256 : TPC) k_chunk_stats(int node_
             }
             pmask[(size_t)(nd.y - level_base) + p] = (unsigned char)mask;   // kept for k_scatter_chunk: the 48-byte AABB is gathered once per level, not twice
 #pragma unroll
-            for (int c = 0; c < 8; ++c) c8[c] += (mask >> c) & 1u;
+            for (int c = 0; c < 4; ++c) {
+                lo4 += (unsigned long long)((mask >> c) & 1u) << (16 * c);
+                hi4 += (unsigned long long)((mask >> (4 + c)) & 1u) << (16 * c);
+            }
         }
         local_sum += a[k];
     }
@@ -423,21 +426,23 @@ __global__ void __launch_bounds__(TPC == 32 ? 256 : TPC) k_chunk_stats(int node_
     }
     mn = team_min<TPC>(mn, s_red);
     int* out = stats + ((size_t)li * max_chunks + chunk) * kStatInts;
+    // the eight child counts of the chunk: packed warp reduction, then one combine over the CTA's warps (a single barrier)
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        int v = c8[c];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (TPC == 32) {
-            if (tl == 0) out[2 + c] = v;
-        } else {
-            __shared__ int s_c[8];
-            if (threadIdx.x < 8) s_c[threadIdx.x] = 0;
-            __syncthreads();
-            if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_c[c], v);
-            __syncthreads();
-            if (threadIdx.x == 0) out[2 + c] = s_c[c];
-            __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) {
+        lo4 += __shfl_xor_sync(0xffffffffu, lo4, o);
+        hi4 += __shfl_xor_sync(0xffffffffu, hi4, o);
+    }
+    if (TPC == 32) {
+        if (tl < 8) out[2 + tl] = (int)(((tl < 4 ? lo4 : hi4) >> (16 * (tl & 3))) & 0xffffull);
+    } else {
+        __shared__ unsigned long long s_part[2 * (TPC / 32)];
+        const int warp = threadIdx.x >> 5;
+        if ((threadIdx.x & 31) == 0) { s_part[2 * warp] = lo4; s_part[2 * warp + 1] = hi4; }
+        __syncthreads();
+        if (threadIdx.x < 8) {
+            unsigned long long acc = 0;
+            for (int w = 0; w < TPC / 32; ++w) acc += s_part[2 * w + (threadIdx.x < 4 ? 0 : 1)];
+            out[2 + threadIdx.x] = (int)((acc >> (16 * (threadIdx.x & 3))) & 0xffffull);
         }
     }
     if (tl == 0) { out[0] = total; out[1] = mn; }
