@@ -57,7 +57,8 @@ const char* msmgpu_debug_take_cuda_error(void);
 msmgpu_status msmgpu_set_query_group(int lanes);
 int msmgpu_get_query_group(void);
 
-/* stream == NULL -> a private non-blocking stream; otherwise a cudaStream_t owned by the caller */
+/* stream == NULL -> a private non-blocking stream; otherwise a cudaStream_t owned by the caller.
+ * A context (and the handles created from it) serves ONE host thread at a time; use one context per thread (or per device) otherwise. */
 msmgpu_status msmgpu_ctx_create(int device, void* stream, msmgpu_ctx** out);
 void msmgpu_ctx_destroy(msmgpu_ctx* ctx);
 msmgpu_status msmgpu_ctx_sync(msmgpu_ctx* ctx);

@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <cmath>
 #include <cstring>
+#include <mutex>
 
 #ifndef MSMGPU_TRACE_ONLY
 #include "newmsm_b200/costfunction_adapter.hpp"
@@ -141,10 +142,15 @@ void wrap_initialize_cost_function(NonLinearSRegDiscreteModel* self, bool MV, my
 // bit for bit (diagnostic mode; timings are meaningless with it).
 static bool verify() { static const bool v = std::getenv("MSMGPU_VERIFY") != nullptr; return v; }
 
+// A context (stream, scratch) serves one host thread at a time. The reference calls the resampler from an OpenMP loop in one place
+// (DiscreteGroupModel::get_patch_data, per subject: reached here with MSMGPU_DISABLE=group, masked groupwise runs or MSMGPU_VERIFY),
+// so the device calls of the hooks are serialised.
+static std::mutex g_device_mutex;
+
 Mesh wrap_metric_resample(const Mesh& in, const Mesh& target, int nthreads, std::shared_ptr<Mesh> EXCL) {
     if (EXCL || disabled("resample")) return real_metric_resample(in, target, nthreads, EXCL);   // exclusion masks: host-side filtering, out of scope
     const double t0 = omp_get_wtime();
-    Mesh out = newresampler_gpu::metric_resample(in, target, nthreads);
+    Mesh out = [&] { std::lock_guard<std::mutex> g(g_device_mutex); return newresampler_gpu::metric_resample(in, target, nthreads); }();
     stats.resample += omp_get_wtime() - t0;
     stats.n_resample++;
     if (verify()) {
@@ -170,7 +176,7 @@ void wrap_sphere_project_warp(Mesh& sphere, const Mesh& from, const Mesh& to, in
     Mesh before;
     if (verify()) before = sphere;
     const double t0 = omp_get_wtime();
-    newresampler_gpu::sphere_project_warp(sphere, from, to, nthreads);
+    { std::lock_guard<std::mutex> g(g_device_mutex); newresampler_gpu::sphere_project_warp(sphere, from, to, nthreads); }
     stats.warp += omp_get_wtime() - t0;
     stats.n_warp++;
     if (verify()) {
@@ -204,7 +210,7 @@ Mesh wrap_smooth_data(Mesh& orig, const Mesh& sphLow, double sigma, int nthreads
     Mesh keep;
     if (verify()) keep = orig;
     const double t0 = omp_get_wtime();
-    Mesh out = newresampler_gpu::smooth_data(orig, sphLow, sigma, nthreads, EXCL);
+    Mesh out = [&] { std::lock_guard<std::mutex> g(g_device_mutex); return newresampler_gpu::smooth_data(orig, sphLow, sigma, nthreads, EXCL); }();
     stats.smooth += omp_get_wtime() - t0;
     stats.n_smooth++;
     if (verify()) {
