@@ -70,7 +70,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--level", type=int, default=6)
     ap.add_argument("--D", type=int, default=1)
-    ap.add_argument("--config", default="MSMpair", choices=["MSMpair", "MSMAllStrain", "MSMstrain", "sMSMSTRcp5", "gMSM"])
+    ap.add_argument("--config", default="MSMpair", choices=["MSMpair", "MSMpairAffine", "MSMAllStrain", "MSMstrain", "sMSMSTRcp5", "gMSM"])
     ap.add_argument("--group", type=int, default=0, help="groupwise (gMSM) run with this many subjects (integration/newmsm_gpu_group_hooks.cpp binds "
                                                            "estimate_pairs, get_patch_data and the pair / triplet costs)")
     ap.add_argument("--levels-drop", type=int, default=0)

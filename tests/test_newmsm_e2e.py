@@ -18,6 +18,7 @@ BINS = [os.path.join(ROOT, "integration", "_build", "newmsm_gpu"), os.path.join(
 
 @pytest.mark.parametrize("config,D,extra", [
     ("MSMpair", 1, ["--levels-drop", "1", "--it-scale", "0.4"]),            # FastPD, univariate unary table, pairwise regulariser, smoothing
+    ("MSMpairAffine", 1, ["--levels-drop", "1", "--it-scale", "0.2"]),     # the shipped basic config: AFFINE level (reference host code) + DISCRETE levels (GPU)
     ("MSMAllStrain", 3, ["--levels-drop", "1", "--it-scale", "0.1"]),       # HOCR, HO multivariate triplet likelihood, strain regulariser
     ("MSMstrain", 1, ["--levels-drop", "2", "--it-scale", "0.1"]),         # HOCR, per-call unary costs from the device table + strain-only triplets
     ("gMSM", 1, ["--levels-drop", "2", "--it-scale", "0.25", "--group", "3"]),   # groupwise driver: estimate_pairs, get_patch_data and the pair / triplet costs on the device (integration/newmsm_gpu_group_hooks.cpp)

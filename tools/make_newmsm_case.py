@@ -18,6 +18,10 @@ CONFIGS = {
     # config/basic_configs/config_standard_MSMpair without the AFFINE level (FastPD, pairwise regulariser)
     "MSMpair": ["--sigma_in=6,4,2", "--sigma_ref=6,4,2", "--lambda=0.1,0.2,0.3", "--it=5,10,10", "--opt=DISCRETE,DISCRETE,DISCRETE",
                 "--CPgrid=2,3,4", "--SGgrid=4,5,6", "--datagrid=5,5,6", "--regoption=1", "--dopt=FastPD"],
+    # config/basic_configs/config_standard_MSMpair AS SHIPPED, i.e. with its AFFINE first level (rigid_costfunction.cpp: not accelerated,
+    # it runs on the reference's host code inside the same program; the three DISCRETE levels use the GPU paths)
+    "MSMpairAffine": ["--sigma_in=6,6,4,2", "--sigma_ref=6,6,4,2", "--lambda=0,0.1,0.2,0.3", "--it=50,5,10,10", "--opt=AFFINE,DISCRETE,DISCRETE,DISCRETE",
+                      "--CPgrid=0,2,3,4", "--SGgrid=0,4,5,6", "--datagrid=5,5,5,6", "--regoption=1"],
     # config/HCP_multimodal_alignment/MSMAllStrainFinalconf1to1_1to3_2 (HOCR, triclique likelihood, strain regulariser)
     "MSMAllStrain": ["--simval=2,2,2", "--sigma_in=0,0,0", "--sigma_ref=0,0,0", "--lambda=0.00001,0.0075,0.01", "--it=10,15,15",
                      "--opt=DISCRETE,DISCRETE,DISCRETE", "--CPgrid=2,3,4", "--SGgrid=4,5,6", "--datagrid=4,5,6", "--regoption=3", "--regexp=2",
