@@ -643,3 +643,85 @@ def test_view_meshes_match_copied_meshes(R, oracle_built, meshes):
             assert np.array_equal(x, y)
         W.close()
     assert L.msmgpu_mesh_set_coords(views[0].h, capi.ptr(np.ascontiguousarray(xyz[1]))) == capi.ERR_INVALID
+
+
+def test_full_size_properties(R):
+    """BASELINE configs[1] at full size (ico7 163 842 V -> 32 492-vertex geodesic sphere, 100 FP32 channels, 2 subjects), where the CPU
+    oracle would take minutes: size-independent properties instead. (a) the fused barycentric resample equals an independent
+    evaluation of its own weight maps (msmgpu_bary_weights, FP64 on the host); (b) adaptive CSR rows are ascending, non-negative and
+    sum to 1; (c) constants are reproduced by both methods; (d) lane-group widths 1 and 8 give identical triangle ids; (e) the
+    batched path equals the per-subject path bit for bit."""
+    import ctypes as C
+    import torch
+    L = capi.lib()
+    ctx = R.Context(0)
+    dev = torch.device("cuda", 0)
+    xyz7, tri7 = synth.icosphere(7)
+    low_xyz, low_tri = synth.geodesic_sphere(57)
+    assert len(xyz7) == 163842 and len(low_xyz) == 32492
+    S, D = 2, 100
+    subj = [synth.jitter_sphere(xyz7, tri7, frac=0.3, seed=1234 + s) for s in range(S)]
+    rng = np.random.default_rng(5)
+    feats = [rng.standard_normal((len(xyz7), D)).astype(np.float32) for _ in range(S)]
+    for f in feats: f[:, 0] = 2.5                                   # channel 0: a constant
+    src = [R.Mesh(x, tri7, ctx=ctx) for x in subj]
+    low = R.Mesh(low_xyz, low_tri, ctx=ctx)
+    trees = R.Octree.build_batch(src + [low])
+    n_low = len(low_xyz)
+    d_feat = [torch.from_numpy(f).to(dev) for f in feats]
+    d_out = [torch.empty(n_low, D, device=dev) for _ in range(S)]
+    d_low = torch.from_numpy(low_xyz).to(dev)
+    tp = (C.c_void_p * S)(*[t.h.value for t in trees[:S]])
+    fp = (C.c_void_p * S)(*[t.data_ptr() for t in d_feat])
+    op = (C.c_void_p * S)(*[t.data_ptr() for t in d_out])
+    capi.check(L.msmgpu_bary_resample_batch_f32_dev(ctx.h, S, tp, n_low, d_low.data_ptr(), D, fp, op, None))
+    ctx.sync()
+    for s in range(S):
+        idx, w, ne = np.zeros((n_low, 3), np.int32), np.zeros((n_low, 3)), np.zeros(n_low, np.int32)
+        capi.check(L.msmgpu_bary_weights(trees[s].h, n_low, capi.ptr(low_xyz), capi.ptr(idx), capi.ptr(w), capi.ptr(ne)))
+        assert (ne == 3).all() and (w >= 0).all() and np.abs(w.sum(1) - 1).max() < 1e-12 and (np.diff(idx, axis=1) > 0).all()
+        acc = np.zeros((n_low, D))
+        for j in range(3):                                          # ascending vertex id = the reference's map order
+            acc += feats[s][idx[:, j]].astype(np.float64) * w[:, j:j + 1]
+        got = d_out[s].cpu().numpy()
+        assert np.array_equal(got, acc.astype(np.float32))          # (a)
+        assert np.abs(got[:, 0] - 2.5).max() < 1e-6                 # (c)
+        # (e) per-subject fused call
+        one = torch.empty(n_low, D, device=dev)
+        capi.check(L.msmgpu_bary_resample_f32_dev(trees[s].h, n_low, d_low.data_ptr(), D, d_feat[s].data_ptr(), one.data_ptr(), None))
+        assert torch.equal(one, d_out[s])
+    # (d)
+    ids1 = trees[0].get_closest_triangle(low_xyz)
+    capi.check(L.msmgpu_set_query_group(8))
+    try:
+        ids8 = trees[0].get_closest_triangle(low_xyz)
+    finally:
+        capi.check(L.msmgpu_set_query_group(1))
+    assert np.array_equal(ids1, ids8)
+    # (b), (c) adaptive
+    mp = (C.c_void_p * S)(*[m.h.value for m in src])
+    wp = (C.c_void_p * S)()
+    capi.check(L.msmgpu_adaptive_weights_batch(ctx.h, S, mp, tp, low.h, trees[-1].h, wp))
+    d_oa = [torch.empty(n_low, D, device=dev) for _ in range(S)]
+    oa = (C.c_void_p * S)(*[t.data_ptr() for t in d_oa])
+    capi.check(L.msmgpu_weights_apply_batch_f32_dev(ctx.h, S, wp, D, fp, oa))
+    ctx.sync()
+    for s in range(S):
+        W = R.Weights(L, C.c_void_p(wp[s]))
+        rowptr, col, val = W.csr()
+        assert rowptr[0] == 0 and (np.diff(rowptr) >= 3).all() and (val >= 0).all()
+        rows = np.repeat(np.arange(n_low), np.diff(rowptr))
+        assert np.abs(np.bincount(rows, weights=val, minlength=n_low) - 1).max() < 1e-12
+        inner = np.ones(len(col), bool); inner[rowptr[1:-1]] = False            # first entry of every row but the first
+        assert (np.diff(col)[inner[1:]] > 0).all()                               # ascending columns inside each row
+        assert col.min() >= 0 and col.max() < len(xyz7) and len(np.unique(col)) > 0.9 * len(xyz7)   # (nearly) every source vertex contributes
+        got = d_oa[s].cpu().numpy()
+        assert np.abs(got[:, 0] - 2.5).max() < 1e-6
+        # independent evaluation of the CSR product (FP64, column order) on a sample of rows
+        for r in rng.integers(0, n_low, 200):
+            b, e = rowptr[r], rowptr[r + 1]
+            acc = np.zeros(D)
+            for k in range(b, e):
+                acc += feats[s][col[k]].astype(np.float64) * val[k]
+            assert np.array_equal(got[r], acc.astype(np.float32))
+        W.close()
