@@ -160,32 +160,53 @@ struct TableJob {
 };
 
 __global__ void __launch_bounds__(256) k_mesh_tables(const TableJob* __restrict__ jobs) {
+    // the 128-byte records of a warp's 32 triangles are contiguous (4 KB): they are transposed through shared memory so that every
+    // store instruction of the warp writes 256 consecutive bytes instead of 32 lines at a 128-byte stride
+    __shared__ double s_rec[8][32 * 17];
     const TableJob job = jobs[blockIdx.y];
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= job.nt) return;
-    double lo[3], hi[3], cv[9];
+    const int lane = threadIdx.x & 31;
+    const bool valid = t < job.nt;
+    double* mine = s_rec[threadIdx.x >> 5];
+    if (valid) {
+        double lo[3], hi[3], cv[9];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const int v = job.tri[3 * (size_t)t + k];
+        for (int k = 0; k < 3; ++k) {
+            const int v = job.tri[3 * (size_t)t + k];
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const double c = job.xyz[3 * (size_t)v + a];
-            cv[3 * k + a] = c;
-            if (k == 0) { lo[a] = c; hi[a] = c; }
-            else { // octree.cpp:52-58
-                if (c < lo[a]) lo[a] = c;
-                if (c > hi[a]) hi[a] = c;
+            for (int a = 0; a < 3; ++a) {
+                const double c = job.xyz[3 * (size_t)v + a];
+                cv[3 * k + a] = c;
+                if (k == 0) { lo[a] = c; hi[a] = c; }
+                else { // octree.cpp:52-58
+                    if (c < lo[a]) lo[a] = c;
+                    if (c > hi[a]) hi[a] = c;
+                }
             }
         }
+        job.qbox[t] = pack_qbox(lo, hi);   // the FP64 box itself is not stored: below the lattice (depth > 17) k_chunk_stats rebuilds it from the record
+        job.area[t] = tri_area_cached(V3{cv[0], cv[1], cv[2]}, V3{cv[3], cv[4], cv[5]}, V3{cv[6], cv[7], cv[8]});   // Triangle::area of this geometry
+        TriRec r;
+        make_trirec(V3{cv[0], cv[1], cv[2]}, V3{cv[3], cv[4], cv[5]}, V3{cv[6], cv[7], cv[8]}, r);
+        static_assert(sizeof(TriRec) == 16 * sizeof(double), "TriRec is 16 doubles");
+        const double rp[16] = {r.v[0], r.v[1], r.v[2], r.v[3], r.v[4], r.v[5], r.v[6], r.v[7], r.v[8], r.s3[0], r.s3[1], r.s3[2], r.d, r.e12, r.e13, r.e23};
+#pragma unroll
+        for (int f = 0; f < 16; ++f) mine[lane * 17 + f] = rp[f];
+        double c4[4];
+        make_cull(V3{cv[0], cv[1], cv[2]}, V3{cv[3], cv[4], cv[5]}, V3{cv[6], cv[7], cv[8]}, c4);
+        job.cull[t] = pack_cull(c4);
     }
-    job.qbox[t] = pack_qbox(lo, hi);   // the FP64 box itself is not stored: below the lattice (depth > 17) k_chunk_stats rebuilds it from the record
-    job.area[t] = tri_area_cached(V3{cv[0], cv[1], cv[2]}, V3{cv[3], cv[4], cv[5]}, V3{cv[6], cv[7], cv[8]});   // Triangle::area of this geometry
-    TriRec r;
-    make_trirec(V3{cv[0], cv[1], cv[2]}, V3{cv[3], cv[4], cv[5]}, V3{cv[6], cv[7], cv[8]}, r);
-    job.rec[t] = r;
-    double c4[4];
-    make_cull(V3{cv[0], cv[1], cv[2]}, V3{cv[3], cv[4], cv[5]}, V3{cv[6], cv[7], cv[8]}, c4);
-    job.cull[t] = pack_cull(c4);
+    __syncwarp();
+    const int t0 = t - lane;   // first triangle of this warp
+    if (t0 < job.nt) {
+        double* out = reinterpret_cast<double*>(job.rec + t0);
+        const int n_valid = min(32, job.nt - t0);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int e = k * 32 + lane, rec = e >> 4;
+            if (rec < n_valid) out[e] = mine[rec * 17 + (e & 15)];
+        }
+    }
 }
 
 // per-triangle tables of every mesh whose coordinates changed since they were last computed, in ONE launch
