@@ -277,6 +277,11 @@ msmgpu_status msmgpu_group_pair_costs(msmgpu_group* g, int P, const int32_t* pai
 /* the 4 combinations Fusion::optimize asks per pair for one candidate label (Fusion.h:164-174): out [P][4] =
  * (cur,cur), (cur,label), (label,cur), (label,label) */
 msmgpu_status msmgpu_group_pair_batch(msmgpu_group* g, int P, const int32_t* pairs, const int32_t* labeling, int label, double* out);
+/* the same with the pair list resident on the device (set once per iteration: estimate_pairs runs once per setupCostFunction) and
+ * the result left on the device: d_out [n_pairs][4] for the pairs [first_pair, first_pair + n_pairs) — any block (sharding).
+ * Asynchronous on the context's stream; labeling is a host array. */
+msmgpu_status msmgpu_group_set_pairs(msmgpu_group* g, int P, const int32_t* pairs);
+msmgpu_status msmgpu_group_pair_batch_dev(msmgpu_group* g, int first_pair, int n_pairs, const int32_t* labeling, int label, double* d_out);
 
 /* replaces: DiscreteGroupCostFunction::computeTripletCost (msm-newmeshreg/src/DiscreteGroupCostFunction.cpp:26-52): the strain energy
  * of a control-grid triangle of one subject under three candidate labels, `subcorr * lambda * W^rexp` with subcorr = 0.1 * S

@@ -53,6 +53,8 @@ class GroupBinding {
         msmgpu_octree* tpl_tree = nullptr;
         double* fields = nullptr;      // [S][L][n_tpl][D] for ALL subjects
         size_t fields_bytes = 0;
+        double* batch_out = nullptr;   // [pairs of this device's block][4]: result of one 4-combination batch before it goes to the host
+        size_t batch_bytes = 0;
         msmgpu_group* group = nullptr;
     };
     std::vector<Device> dev_;
@@ -161,11 +163,12 @@ class GroupBinding {
             });
             group_timers().pair_costs += P_;
         } else {
-            on_devices([&](int d) {
+            on_devices([&](int d) {   // the pair list is resident on every device (get_patch_data); only the labeling goes up, the block's costs come down
                 int b, e;
                 shard(P_, d, n, b, e);
-                if (e > b)
-                    detail::check(msmgpu_group_pair_batch(dev_[d].group, e - b, pairs_.data() + 2 * (size_t)b, tb->snap.data(), label, tb->val.data() + 4 * (size_t)b));
+                if (e <= b) return;
+                detail::check(msmgpu_group_pair_batch_dev(dev_[d].group, b, e - b, tb->snap.data(), label, dev_[d].batch_out));
+                detail::check(msmgpu_device_download(dev_[d].ctx, tb->val.data() + 4 * (size_t)b, dev_[d].batch_out, 4 * (size_t)(e - b) * sizeof(double)));
             });
             group_timers().pair_costs += 4LL * P_;
         }
@@ -361,6 +364,20 @@ public:
                                               &dv.group));
         });
         pairs_.assign(m.pairs, m.pairs + 2 * (size_t)P_);
+        on_devices([&](int d) {
+            Device& dv = dev_[d];
+            detail::check(msmgpu_group_set_pairs(dv.group, P_, pairs_.data()));
+            int b, e;
+            shard(P_, d, n, b, e);
+            const size_t need = 4 * (size_t)std::max(e - b, 1) * sizeof(double);
+            if (dv.batch_bytes < need) {
+                msmgpu_device_free(dv.ctx, dv.batch_out);
+                dv.batch_out = nullptr; dv.batch_bytes = 0;
+                void* p = nullptr;
+                detail::check(msmgpu_device_malloc(dv.ctx, need, &p));
+                dv.batch_out = static_cast<double*>(p); dv.batch_bytes = need;
+            }
+        });
         trip_.assign(m.triplets, m.triplets + 3 * (size_t)T_);
         cps_.resize(3 * (size_t)n_nodes); orig_.resize(3 * (size_t)n_nodes);
         for (int s = 0; s < S_; ++s)

@@ -105,6 +105,8 @@ _SIGNATURES = {
     "msmgpu_group_destroy": (None, [_vp]),
     "msmgpu_group_pair_costs": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "msmgpu_group_pair_batch": (_i, [_vp, _i, _vp, _vp, _i, _vp]),
+    "msmgpu_group_set_pairs": (_i, [_vp, _i, _vp]),
+    "msmgpu_group_pair_batch_dev": (_i, [_vp, _i, _i, _vp, _i, _vp]),
     "msmgpu_costfn_set_cpgrid_ho": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp]),
     "msmgpu_costfn_triplet_costs": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "msmgpu_costfn_triplet_batch": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),

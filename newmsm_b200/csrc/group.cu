@@ -31,6 +31,9 @@ struct msmgpu_group {
     msm::DevBuf<double> thr;            // [S*ncp] chord thresholds
     msm::DevBuf<int> sup_ptr, sup_mem;  // superset candidate lists per node
     int n_sup = 0, max_sup = 0;
+    msm::DevBuf<int> pairs;             // optional device-resident pair list [P][2] (msmgpu_group_set_pairs)
+    msm::DevBuf<int> labeling;          // scratch for the device-output batches
+    int P = 0;
 };
 
 namespace msm {
@@ -343,6 +346,33 @@ msmgpu_status msmgpu_group_pair_costs(msmgpu_group* g, int P, const int32_t* pai
                                       const int32_t* req_lb, double* out) {
     if (!req_pair || !req_la || !req_lb) return fail(MSMGPU_ERR_INVALID, "group_pair_costs: bad arguments");
     return pair_run(g, P, pairs, n, req_pair, req_la, req_lb, nullptr, 0, out);
+}
+
+msmgpu_status msmgpu_group_set_pairs(msmgpu_group* g, int P, const int32_t* pairs) {
+    if (!g || P <= 0 || !pairs) return fail(MSMGPU_ERR_INVALID, "group_set_pairs: bad arguments");
+    MSM_CUDA(cudaSetDevice(g->ctx->device));
+    cudaStream_t s = g->ctx->stream;
+    MSM_TRY(upg(g->pairs, pairs, 2 * (size_t)P, s));
+    MSM_CUDA(cudaStreamSynchronize(s));
+    g->P = P;
+    return MSMGPU_OK;
+}
+
+msmgpu_status msmgpu_group_pair_batch_dev(msmgpu_group* g, int first_pair, int n_pairs, const int32_t* labeling, int label, double* d_out) {
+    if (!g || !labeling || !d_out || label < 0 || label >= g->L || first_pair < 0 || n_pairs <= 0 || first_pair + (long long)n_pairs > g->P)
+        return fail(MSMGPU_ERR_INVALID, "group_pair_batch_dev: bad arguments (msmgpu_group_set_pairs first)");
+    MSM_CUDA(cudaSetDevice(g->ctx->device));
+    cudaStream_t s = g->ctx->stream;
+    // pageable source: staged before the call returns, so one scratch buffer per group is enough for back-to-back batches
+    MSM_TRY(upg(g->labeling, labeling, (size_t)g->S * g->ncp, s));
+    PairArgs a;
+    a.simmeasure = g->simmeasure; a.ncp = g->ncp; a.L = g->L; a.D = g->D; a.n_tpl = g->n_tpl; a.n = 4 * n_pairs;
+    a.fields = g->d_fields; a.tpl = g->tpl_xyz.p; a.rcp = g->rcp.p; a.thr = g->thr.p; a.sup_ptr = g->sup_ptr.p; a.sup_mem = g->sup_mem.p;
+    a.pairs = g->pairs.p + 2 * (size_t)first_pair; a.req_pair = nullptr; a.req_la = nullptr; a.req_lb = nullptr;
+    a.labeling = g->labeling.p; a.label = label; a.out = d_out;
+    k_group_pair_costs<<<(unsigned)((a.n + kPairWarps - 1) / kPairWarps), kPairWarps * 32, 0, s>>>(a);
+    MSM_LAUNCH_CHECK();
+    return MSMGPU_OK;
 }
 
 msmgpu_status msmgpu_group_pair_batch(msmgpu_group* g, int P, const int32_t* pairs, const int32_t* labeling, int label, double* out) {

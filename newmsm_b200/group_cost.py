@@ -153,21 +153,38 @@ class DiscreteGroupModel:
     def computePairwiseCost(self, pairs, pair: int, labelA: int, labelB: int) -> float:
         return float(self.computePairwiseCostList(pairs, [pair], [labelA], [labelB])[0])
 
-    def computePairwiseCostsForLabel(self, pairs, labeling, label: int):
-        """The 4 combinations per pair of Fusion::optimize (Fusion.h:164-174) -> [P, 4]; pairs block-sharded over the ranks."""
+    def setPairs(self, pairs):
+        """The pair list of the iteration (estimate_pairs), kept on the device for the label phases."""
+        pairs = i32(pairs).reshape(-1, 2)
+        check(self.L_.msmgpu_group_set_pairs(self.g, len(pairs), ptr(pairs)))
+        self._pairs_key = (pairs.ctypes.data, len(pairs))
+        self._pairs_ref = pairs
+        self.P = len(pairs)
+
+    def computePairwiseCostsForLabel(self, pairs, labeling, label: int, copy: bool = True):
+        """The 4 combinations per pair of Fusion::optimize (Fusion.h:164-174) -> [P, 4]; pairs block-sharded over the ranks.
+        The pair list stays on the device between label phases, the block results are gathered on the device (NCCL) and come to the
+        host once, into a reused pinned buffer (copy=False returns a view of it, valid until the next call)."""
         import torch
         pairs = i32(pairs).reshape(-1, 2)
+        if getattr(self, "_pairs_key", None) != (pairs.ctypes.data, len(pairs)) or getattr(self, "_pairs_group", None) is not self.g:
+            self.setPairs(pairs)
+            self._pairs_group = self.g
         lab = i32(labeling)
-        P = len(pairs)
-        b, e = shard_range(P, self.coll.rank, self.coll.world)
-        local = np.zeros((e - b, 4))
-        if e > b:
-            blk = np.ascontiguousarray(pairs[b:e])
-            check(self.L_.msmgpu_group_pair_batch(self.g, e - b, ptr(blk), ptr(lab), int(label), ptr(local)))
-        if self.coll.world == 1:
-            return local
+        P = self.P
         dev = torch.device("cuda", self.ctx.device)
-        return self.coll.all_gather_blocks(torch.from_numpy(local).to(dev), P).cpu().numpy()
+        b, e = shard_range(P, self.coll.rank, self.coll.world)
+        local = torch.empty((e - b, 4), dtype=torch.float64, device=dev)
+        torch.cuda.synchronize(dev)
+        if e > b:
+            check(self.L_.msmgpu_group_pair_batch_dev(self.g, b, e - b, ptr(lab), int(label), ptr(local)))
+        self.ctx.sync()
+        full = local if self.coll.world == 1 else self.coll.all_gather_blocks(local, P)
+        if getattr(self, "_host_out", None) is None or self._host_out.shape[0] != P:
+            self._host_out = torch.empty((P, 4), dtype=torch.float64, pin_memory=True)
+        self._host_out.copy_(full)
+        torch.cuda.synchronize(dev)
+        return self._host_out.numpy().copy() if copy else self._host_out.numpy()
 
     # DiscreteGroupCostFunction::computeTripletCost (cpp:26-52): strain of a control-grid triangle of one subject, scaled by subcorr = 0.1 * S
     def computeTripletCostList(self, cps, orig_cps, rotations, labels, triplets, triplet, la, lb, lc, lambda_, shearmodulus=0.4, bulkmodulus=1.6,
@@ -190,10 +207,18 @@ class DiscreteGroupModel:
         S = f64(cps).shape[0]
         rot, labels, trip, lab = f64(rotations).reshape(-1, 9), f64(labels), i32(triplets).reshape(-1, 3), i32(labeling)
         reg = capi.RegParams(lambda_, shearmodulus, bulkmodulus, kexponent, exponent, 3)
-        out = np.zeros((len(trip), 8))
-        check(self.L_.msmgpu_group_triplet_batch(self.ctx.h, len(cp), ptr(cp), ptr(org), ptr(rot), len(labels), ptr(labels), len(trip), ptr(trip),
-                                                 C.byref(reg), 0.1 * S, int(fixnan), ptr(lab), int(label), ptr(out)))
-        return out
+        T = len(trip)
+        b, e = shard_range(T, self.coll.rank, self.coll.world)       # triplets are per subject: block-sharded like the pairs
+        out = np.zeros((e - b, 8))
+        if e > b:
+            blk = np.ascontiguousarray(trip[b:e])
+            check(self.L_.msmgpu_group_triplet_batch(self.ctx.h, len(cp), ptr(cp), ptr(org), ptr(rot), len(labels), ptr(labels), e - b, ptr(blk),
+                                                     C.byref(reg), 0.1 * S, int(fixnan), ptr(lab), int(label), ptr(out)))
+        if self.coll.world == 1:
+            return out
+        import torch
+        dev = torch.device("cuda", self.ctx.device)
+        return self.coll.all_gather_blocks(torch.from_numpy(out).to(dev), T).cpu().numpy()
 
     def close(self):
         if self.g is not None:

