@@ -725,3 +725,49 @@ def test_full_size_properties(R):
                 acc += feats[s][col[k]].astype(np.float64) * val[k]
             assert np.array_equal(got[r], acc.astype(np.float32))
         W.close()
+
+
+def test_device_buffer_functions_and_group_batch_dev(R, oracle_built):
+    """msmgpu_device_malloc / _download / _copy_peer round trip; msmgpu_group_pair_batch_dev needs msmgpu_group_set_pairs first and then
+    equals the host-output batch on any block of pairs."""
+    import ctypes as C
+    import torch
+    from newmsm_b200 import group_cost as GC
+    L = capi.lib()
+    ctx = R.Context(0)
+    a, b = C.c_void_p(), C.c_void_p()
+    capi.check(L.msmgpu_device_malloc(ctx.h, 4096, C.byref(a)))
+    capi.check(L.msmgpu_device_malloc(ctx.h, 4096, C.byref(b)))
+    src = torch.arange(512, dtype=torch.float64, device="cuda:0")
+    torch.cuda.synchronize()
+    capi.check(L.msmgpu_device_copy_peer(ctx.h, a, ctx.h, C.c_void_p(src.data_ptr()), 4096))
+    capi.check(L.msmgpu_device_copy_peer(ctx.h, b, ctx.h, a, 4096))
+    host = np.zeros(512)
+    capi.check(L.msmgpu_device_download(ctx.h, capi.ptr(host), b, 4096))
+    assert np.array_equal(host, np.arange(512.0))
+    L.msmgpu_device_free(ctx.h, a); L.msmgpu_device_free(ctx.h, b)
+    assert L.msmgpu_device_malloc(None, 16, C.byref(a)) == capi.ERR_INVALID
+
+    g = group_setup()
+    M = GC.DiscreteGroupModel(R.Mesh(g["tpl"], g["tpl_tri"]), simmeasure=2)
+    ncp = g["cps"].shape[1]
+    rot = M.get_rotations(g["centre"], g["cps"])
+    spacings = M.get_spacings(g["cps"], g["cp_tri"])
+    pairs = M.estimate_pairs(g["cps"], g["cp_tri"])
+    M.get_patch_data(g["data"], g["dtri"], g["feat"], g["labels"], g["centre"], rot, spacings, 1.0)
+    labeling = np.random.default_rng(11).integers(0, len(g["labels"]), g["cps"].shape[0] * ncp).astype(np.int32)
+    P = len(pairs)
+    d_out = torch.empty((P, 4), dtype=torch.float64, device="cuda:0")
+    torch.cuda.synchronize()
+    assert L.msmgpu_group_pair_batch_dev(M.g, 0, P, capi.ptr(labeling), 2, capi.ptr(d_out)) == capi.ERR_INVALID    # no resident pairs yet
+    M.setPairs(pairs)
+    ref = np.zeros((P, 4))
+    capi.check(L.msmgpu_group_pair_batch(M.g, P, capi.ptr(np.ascontiguousarray(pairs)), capi.ptr(labeling), 2, capi.ptr(ref)))
+    lo, hi = P // 3, P - 5
+    capi.check(L.msmgpu_group_pair_batch_dev(M.g, lo, hi - lo, capi.ptr(labeling), 2, capi.ptr(d_out[lo:hi])))
+    M.ctx.sync()
+    got = d_out[lo:hi].cpu().numpy()
+    assert np.array_equal(np.nan_to_num(got, nan=-1.0), np.nan_to_num(ref[lo:hi], nan=-1.0))
+    assert L.msmgpu_group_pair_batch_dev(M.g, P - 2, 5, capi.ptr(labeling), 2, capi.ptr(d_out)) == capi.ERR_INVALID   # block beyond the list
+    full = M.computePairwiseCostsForLabel(pairs, labeling, 2)
+    assert np.array_equal(np.nan_to_num(full, nan=-1.0), np.nan_to_num(ref, nan=-1.0))
