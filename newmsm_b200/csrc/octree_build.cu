@@ -785,17 +785,15 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
         }
         if (timing) {
             cudaStreamSynchronize(s);
-            double ph[3] = {0, 0, 0};
+            // events per level: before the chunk statistics, after them, before the totals come to the host, after the scatter
+            double ph[4] = {0, 0, 0, 0};   // statistics | combine + scans | totals round trip + children + scatter | between levels
             for (size_t i = 0; i + 1 < evs.size(); ++i) {
                 float ms = 0;
                 cudaEventElapsedTime(&ms, evs[i], evs[i + 1]);
-                ph[i % 4 == 3 ? 0 : i % 4] += (i % 4 == 3) ? 0.0 : ms * 1e3;
-                if (i % 4 == 3) ph[2] += 0;   // (level boundary: host turn-around, counted with the wait below)
+                ph[i % 4] += ms * 1e3;
             }
-            double turn = 0;
-            for (size_t i = 3; i + 1 < evs.size(); i += 4) { float ms = 0; cudaEventElapsedTime(&ms, evs[i], evs[i + 1]); turn += ms * 1e3; }
             fprintf(stderr, "[msmgpu build] device time by phase: chunk stats %.0f us, combine + scans %.0f us, children + scatter %.0f us, between levels %.0f us\n",
-                    ph[0], ph[1], ph[2], turn);
+                    ph[0], ph[1], ph[2], ph[3]);
             for (cudaEvent_t e : evs) cudaEventDestroy(e);
         }
         if (timing) fprintf(stderr, "[msmgpu build] %d meshes, depth %d: host enqueue %.0f us (of which scratch allocation %.0f us), waiting for the level totals %.0f us\n", n, depth, t_enq, t_alloc, t_wait);
