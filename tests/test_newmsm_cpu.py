@@ -55,3 +55,25 @@ def test_gpu_program_fails_loudly_without_a_device():
         assert r.returncode != 0
         assert "CUDA" in r.stdout + r.stderr
         assert not os.path.exists(os.path.join(tmp, "out_g", "sphere.reg.asc"))      # no CPU fallback produced a result
+
+
+@pytest.mark.skipif(not os.path.exists(GPU), reason="integration/_build/newmsm_gpu not built (needs /root/reference)")
+def test_group_members_are_bound_at_link_time():
+    """The four groupwise members resolve to the hooks (strong definitions) and the reference's own code stays reachable as `__real_`
+    aliases (weakened copies of the compiled reference objects, oracle/Makefile: GROUPSYMS); the reference CPU binary has neither."""
+    import shutil
+    if not shutil.which("nm"):
+        pytest.skip("binutils nm not available")
+    syms = ["_ZN10newmeshreg18DiscreteGroupModel14estimate_pairsEv", "_ZN10newmeshreg18DiscreteGroupModel14get_patch_dataEv",
+            "_ZN10newmeshreg25DiscreteGroupCostFunction19computePairwiseCostEiii", "_ZN10newmeshreg25DiscreteGroupCostFunction18computeTripletCostEiiii"]
+    table = {}
+    for line in subprocess.run(["nm", GPU], capture_output=True, text=True, check=True).stdout.splitlines():
+        p = line.split()
+        if len(p) == 3:
+            table[p[2]] = (p[1], p[0])
+    for s_ in syms:
+        assert table.get(s_, ("?",))[0] == "T", (s_, table.get(s_))                     # the hook: a strong text symbol
+        assert table.get("__real_" + s_, ("?",))[0] == "T", s_                          # the reference's body, still linked in
+        assert table[s_][1] != table["__real_" + s_][1]                                 # and they are different functions
+    ref_syms = subprocess.run(["nm", REF], capture_output=True, text=True, check=True).stdout if os.path.exists(REF) else ""
+    assert "__real_" + syms[0] not in ref_syms
