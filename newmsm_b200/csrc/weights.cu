@@ -381,28 +381,30 @@ __global__ void k_area_ratio(int nkeys, int S, int n_low, const int* __restrict_
     ratio[k] = old_area[k] / sum;
 }
 // resampler.cpp:120-137: w *= oldArea[src] / correction[src]; then each row normalised to sum 1.
-// One warp per row: the lanes fetch the row's entries (the random ratio[] loads overlap), the row sum is taken in
-// column order by lane-ordered broadcasts, i.e. the reference's sequential sum.
+// The row sum is the reference's sequential sum (column order).
 __global__ void __launch_bounds__(256) k_finish_rows(int n_rows, int n_low, const int* __restrict__ rowptr, const int* __restrict__ col,
                                                      double* __restrict__ val, const int* __restrict__ in_off, const double* __restrict__ ratio) {
-    const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (n >= n_rows) return;
+    // half a warp per row (rows hold ~15 entries): the 16 lanes fetch a chunk of the row, the row sum is taken in column order by
+    // lane-ordered broadcasts inside the half-warp
+    const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const int hl = threadIdx.x & 15;
+    const unsigned mask = 0xffffu << (threadIdx.x & 16);
+    if (n >= n_rows) return;          // (whole half-warps leave together)
     const int b = rowptr[n], e = rowptr[n + 1];
     const int koff = in_off[n / n_low];
     double ws = 0.0;
-    for (int i0 = b; i0 < e; i0 += 32) {
-        const int i = i0 + lane;
+    for (int i0 = b; i0 < e; i0 += 16) {
+        const int i = i0 + hl;
         double v = 0.0;
         if (i < e) {
             v = val[i] * __ldg(ratio + koff + col[i]);
             val[i] = v;
         }
-        const int m = min(32, e - i0);
-        for (int k = 0; k < m; ++k) ws += __shfl_sync(0xffffffffu, v, k);
+        const int m = min(16, e - i0);
+        for (int k = 0; k < m; ++k) ws += __shfl_sync(mask, v, k, 16);
     }
     if (ws != 0.0)
-        for (int i = b + lane; i < e; i += 32) val[i] /= ws;
+        for (int i = b + hl; i < e; i += 16) val[i] /= ws;
 }
 
 // Builds the S matrices into one shared store; out[s] become views of it.
@@ -488,7 +490,7 @@ msmgpu_status adaptive_weights_build_batch(msmgpu_ctx* ctx, int S, msmgpu_mesh* 
     k_area_ratio<<<(unsigned)((NV + 255) / 256), 256, 0, s>>>((int)NV, S, n_low, d_in_off.p, ridx.p, rw.p, rne.p, fne.p, rr.ptr.p, new_area.p, cols.ptr.p,
                                                               cols.id.p, cols.val.p, old_area.p, correction.p);   // correction := ratio
     MSM_LAUNCH_CHECK();
-    k_finish_rows<<<(unsigned)((NL * 32 + 255) / 256), 256, 0, s>>>((int)NL, n_low, store->rowptr.p, store->col.p, store->val.p, d_in_off.p, correction.p);
+    k_finish_rows<<<(unsigned)((NL * 16 + 255) / 256), 256, 0, s>>>((int)NL, n_low, store->rowptr.p, store->col.p, store->val.p, d_in_off.p, correction.p);
     MSM_LAUNCH_CHECK();
 
     // per-subject views: rowptr offsets of the subject boundaries
