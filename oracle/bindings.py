@@ -497,6 +497,9 @@ class RefMR:
                                                  _i, _vp, _vp, _vp, _vp, _vp, _i]
             L.refmr_group_triplet_costs.argtypes = [_i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _d, _d, _d, _d, _d, _i, _vp, _vp, _vp, _vp, _vp]
             L.refmr_label_sets.argtypes = [_i, _d, _vp, _vp, _i, _vp, _vp]
+            if hasattr(L, "refmr_rigid"):
+                L.refmr_rigid.restype = _i
+                L.refmr_rigid.argtypes = [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _i]
             cls._lib = L
         return cls._lib
 
@@ -526,6 +529,24 @@ def refmr_unary(kind, simmeasure, tgt_xyz, tgt_tri, cp_xyz, cp_tri, rot, labels,
     if n < 0 or n > cap:
         raise RuntimeError("reference unary costs failed")
     return out, rowptr, mem[:n].copy(), absw_out
+
+
+def refmr_rigid(tgt_xyz, tgt_tri, src_xyz, src_tri, src_feat, ref_feat, simmeasure=2, iters=4, stepsize=0.01, gradsampling=0.5, nthreads=1):
+    """The reference's RIGID / AFFINE level (Rigid_cost_function::initialise + run, rigid_costfunction.cpp:32-236).
+    -> (rotated source coords [nv_s][3], cost at zero rotation, neighbour rowptr, neighbour members)"""
+    tx, tt, sx, st = _f64(tgt_xyz), _i32(tgt_tri), _f64(src_xyz), _i32(src_tri)
+    sf, rf = _f64(np.atleast_2d(src_feat)), _f64(np.atleast_2d(ref_feat))
+    out = np.zeros((len(sx), 3))
+    cost0 = C.c_double(0.0)
+    rowptr = np.zeros(len(sx) + 1, np.int32)
+    cap = 512 * len(sx)
+    mem = np.zeros(cap, np.int32)
+    n = RefMR.lib().refmr_rigid(len(tx), _p(tx), len(tt), _p(tt), len(sx), _p(sx), len(st), _p(st), sf.shape[0], _p(sf), _p(rf), int(simmeasure),
+                                int(iters), float(stepsize), float(gradsampling), int(nthreads), _p(out), C.cast(C.byref(cost0), C.c_void_p), _p(rowptr),
+                                _p(mem), cap)
+    if n < 0 or n > cap:
+        raise RuntimeError("reference rigid level failed")
+    return out, cost0.value, rowptr, mem[:n].copy()
 
 
 def refmr_triplet(kind, simmeasure, tgt_xyz, tgt_tri, cp_xyz, cp_tri, orig_cp_xyz, rot, labels, triplets, req_t, req_la, req_lb, req_lc,

@@ -18,6 +18,7 @@
 #include "DiscreteGroupModel.h"
 #include "DiscreteGroupCostFunction.h"
 #include "DiscreteModel.h"
+#include "rigid_costfunction.h"
 
 using namespace newmeshreg;
 using newresampler::Mesh;
@@ -300,6 +301,38 @@ int refmr_label_sets(int sgres, double maxvd, double* samples, double* barycentr
         if (n_bary) *n_bary = (int)m.m_barycentres.size();
         if (centre) { centre[0] = m.centre.X; centre[1] = m.centre.Y; centre[2] = m.centre.Z; }
         return (int)m.m_samples.size();
+    } catch (...) { return -1; }
+}
+
+// The RIGID / AFFINE level (rigid_costfunction.cpp:32-236, mesh_registration.cpp:68-73, 117-121): initialise() (neighbourhoods within
+// 4 mean vertex distances, reg_tools.cpp:31-58, + the sparse similarity columns), the cost at zero rotation, and run(). Outputs: the
+// rotated source coordinates [nv_s][3], the neighbour lists after initialise() (CSR, nearest first), the initial cost.
+// not accelerated yet; these outputs pin a future restatement (tests/golden/rigid.npz).
+int refmr_rigid(int nv_t, const double* tgt_xyz, int nt_t, const int* tgt_tri, int nv_s, const double* src_xyz, int nt_s, const int* src_tri,
+                int D, const double* src_feat, const double* ref_feat, int simmeasure, int iters, double stepsize, double gradsampling, int nthreads,
+                double* out_xyz, double* out_cost0, int* nbh_rowptr, int* nbh_members, int cap) {
+    try {
+        Mesh target = make_mesh(nv_t, tgt_xyz, nt_t, tgt_tri);
+        Mesh source = make_mesh(nv_s, src_xyz, nt_s, src_tri);
+        auto F = make_feat(D, nv_s, src_feat, nv_t, ref_feat);
+        Rigid_cost_function rc(target, source, F);
+        myparam P;
+        P.insert(parameterPair("iters", iters));
+        P.insert(parameterPair("simmeasure", simmeasure));
+        P.insert(parameterPair("verbosity", false));
+        P.insert(parameterPair("stepsize", stepsize));
+        P.insert(parameterPair("gradsampling", gradsampling));
+        P.insert(parameterPair("numthreads", nthreads));
+        rc.set_parameters(P);
+        rc.initialise();
+        const int n = flatten_lists(rc.nbh->neighbours, nbh_rowptr, nbh_members, cap);
+        if (out_cost0) *out_cost0 = rc.rigid_cost_mesh(0.0, 0.0, 0.0);
+        Mesh out = rc.run();
+        for (int i = 0; i < nv_s; ++i) {
+            const Point& p = out.get_coord(i);
+            out_xyz[3 * i] = p.X; out_xyz[3 * i + 1] = p.Y; out_xyz[3 * i + 2] = p.Z;
+        }
+        return n;
     } catch (...) { return -1; }
 }
 

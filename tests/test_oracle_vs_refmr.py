@@ -156,3 +156,24 @@ def test_unary_costs_dice(O, kind, D, sim, pct):
         O.oracle_set_percentile(0.75)
     assert np.array_equal(got, ref)
     assert np.ptp(ref) > 0
+
+
+def test_rigid_level_reference_reproduces_golden(O):
+    """SURVEY §8 f4 groundwork: the reference's RIGID / AFFINE level (rigid_costfunction.cpp:32-236), run through the compiled reference
+    here, reproduces tests/golden/rigid.npz bit for bit and does not depend on the thread count (its OpenMP loops write disjoint entries).
+    No restatement / CUDA path exists for this level yet; the vectors pin the one that comes next."""
+    import os
+    sys_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_rigid", os.path.join(sys_path, "make_golden_rigid.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = np.load(os.path.join(sys_path, "rigid.npz"))
+    for name, D, sim in (("d2_corr", 2, 2), ("d3_ssd", 3, 1)):
+        xyz, tri, src, mov, ref = mod.rigid_case(3, D)
+        for threads in (1, 4):
+            moved, cost0, rowptr, members = O.refmr_rigid(xyz, tri, src, tri, mov, ref, simmeasure=sim, iters=4, nthreads=threads)
+            assert np.array_equal(moved, g[f"{name}_xyz"]) and cost0 == float(g[f"{name}_cost0"])
+            assert np.array_equal(rowptr, g[f"{name}_rowptr"]) and np.array_equal(members, g[f"{name}_members"])
+        assert np.abs(np.linalg.norm(moved, axis=1) - 100).max() < 1e-9          # a rotation: the sphere radius is kept
+        assert rowptr[-1] > 30 * len(xyz)                                       # neighbourhoods of 4 mean vertex distances
