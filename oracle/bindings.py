@@ -91,6 +91,8 @@ class Oracle:
             L.orc_group_fields.argtypes = [_i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i]
             L.orc_group_pair_costs.argtypes = [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _d, _vp, _i, _vp, _vp, _vp, _vp, _i]
             L.orc_ho_patches.argtypes = [_i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i]
+            L.orc_rigid.restype = _i
+            L.orc_rigid.argtypes = [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _d, _d, _vp, _vp, _vp, _vp, _i]
             L.orc_triplet_costs.argtypes = [_i, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp,
                                             _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _d, _d, _d, _d, _d, _vp, _i]
             cls._lib = L
@@ -309,6 +311,22 @@ def oracle_group_triplet_costs(cps, orig_cps, rot, labels, triplets, req_t, req_
                                cp.reshape(-1, 3), None, None, dummy, dummy, None, np.ones(n_nodes), lam, mu, kappa, k_exp, rexp)
     out[out == 1e7 * lam] = 1e7
     return out
+
+
+def oracle_rigid(tgt_xyz, tgt_tri, src_xyz, src_tri, src_feat, ref_feat, simmeasure=2, iters=4, stepsize=0.01, gradsampling=0.5):
+    """Restatement of the RIGID / AFFINE level (rigid_costfunction.cpp:32-236); same outputs as refmr_rigid."""
+    tx, tt, sx, st = _f64(tgt_xyz), _i32(tgt_tri), _f64(src_xyz), _i32(src_tri)
+    sf, rf = _f64(np.atleast_2d(src_feat)), _f64(np.atleast_2d(ref_feat))
+    out = np.zeros((len(sx), 3))
+    cost0 = C.c_double(0.0)
+    rowptr = np.zeros(len(sx) + 1, np.int32)
+    cap = 512 * len(sx)
+    mem = np.zeros(cap, np.int32)
+    n = Oracle.lib().orc_rigid(len(tx), _p(tx), len(tt), _p(tt), len(sx), _p(sx), len(st), _p(st), sf.shape[0], _p(sf), _p(rf), int(simmeasure),
+                               int(iters), float(stepsize), float(gradsampling), _p(out), C.cast(C.byref(cost0), C.c_void_p), _p(rowptr), _p(mem), cap)
+    if n < 0 or n > cap:
+        raise RuntimeError("oracle rigid level failed")
+    return out, cost0.value, rowptr, mem[:n].copy()
 
 
 # --------------------------------------------------------------------------------------

@@ -5,6 +5,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <iterator>
 #include <limits>
@@ -989,3 +991,285 @@ int orc_group_pair_costs(int simmeasure, int S, int ncp, int L, int D, int n_tpl
 }
 
 } // extern "C"
+
+// ======================================================================================================================
+// RIGID / AFFINE level: restatement of msm-newmeshreg/src/rigid_costfunction.cpp:32-236 with
+// Neighbourhood::update (reg_tools.cpp:31-58), calculate_tangs (reg_tools.cpp:205-266), the full-matrix part of
+// sparsesimkernel (similarities.cpp:27-128), euler_rotate (point.cpp:154-171), Mesh::local_normal / calculate_MeanVD /
+// push_triangle adjacency order (mesh.cpp:112-141, 276-294). Pinned by tests/golden/rigid.npz (outputs of the compiled reference).
+// ======================================================================================================================
+namespace {
+
+struct RigidMesh {
+    int nv = 0, nt = 0;
+    std::vector<P3> v;
+    std::vector<int> tri;
+    std::vector<std::vector<int>> nbr, inc;   // vertex neighbours / incident triangles in push_triangle order (mesh.cpp:112-131)
+    void build(int nv_, const double* xyz, int nt_, const int* t) {
+        nv = nv_; nt = nt_;
+        v.resize(nv); tri.assign(t, t + 3 * (size_t)nt);
+        for (int i = 0; i < nv; ++i) v[i] = P3{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+        nbr.assign(nv, {}); inc.assign(nv, {});
+        auto add = [&](int a, int b) { if (std::find(nbr[a].begin(), nbr[a].end(), b) == nbr[a].end()) nbr[a].push_back(b); };
+        for (int k = 0; k < nt; ++k) {
+            const int n0 = tri[3 * k], n1 = tri[3 * k + 1], n2 = tri[3 * k + 2];
+            inc[n0].push_back(k); inc[n1].push_back(k); inc[n2].push_back(k);
+            add(n0, n1); add(n0, n2); add(n1, n0); add(n1, n2); add(n2, n0); add(n2, n1);
+        }
+    }
+    P3 tri_n(int t) const { return tri_normal(v[tri[3 * t]], v[tri[3 * t + 1]], v[tri[3 * t + 2]]); }
+    P3 local_normal(int pt) const {   // mesh.cpp:133-141
+        P3 a{0, 0, 0};
+        for (int t : inc[pt]) { const P3 n = tri_n(t); a.X += n.X; a.Y += n.Y; a.Z += n.Z; }
+        normalize(a);
+        return a;
+    }
+    double mean_vd() const {          // mesh.cpp:276-294
+        int k = 0;
+        double kr = 0.0;
+        for (int i = 0; i < nv; ++i)
+            for (int j : nbr[i]) { ++k; kr += norm(sub(v[j], v[i])); }
+        return kr / k;
+    }
+};
+
+struct RTangs { P3 e1, e2; };
+RTangs rigid_tangs(int ind, const RigidMesh& M) {   // reg_tools.cpp:205-266
+    RTangs T;
+    double mag;
+    P3 a = M.local_normal(ind);
+    if (dot(a, M.v[ind]) < 0) a = mul(a, -1);
+    // `abs(a.X)` in reg_tools.cpp:213-229 is the C library's int abs(int) in that translation unit (no `using std::abs`, no <cmath>
+    // overload in scope): the components of a unit normal are truncated to 0 (or +-1), so the first branch is taken unless a
+    // component is exactly +-1. Restated as compiled.
+    auto iabs = [](double x) { return std::abs((int)x); };
+    if (iabs(a.X) >= iabs(a.Y) && iabs(a.X) >= iabs(a.Z)) {
+        mag = std::sqrt(a.Z * a.Z + a.Y * a.Y);
+        if (mag == 0) T.e1 = P3{0, 0, 1};
+        else T.e1 = P3{0, -a.Z / mag, a.Y / mag};
+    } else if (iabs(a.Y) >= iabs(a.X) && iabs(a.Y) >= iabs(a.Z)) {
+        mag = std::sqrt(a.Z * a.Z + a.X * a.X);
+        if (mag == 0) T.e1 = P3{0, 0, 1};
+        else T.e1 = P3{-a.Z / mag, 0, a.X / mag};
+    } else {
+        mag = std::sqrt(a.Y * a.Y + a.X * a.X);
+        if (mag == 0) T.e1 = P3{1, 0, 0};
+        else T.e1 = P3{-a.Y / mag, a.X / mag, 0};
+    }
+    T.e2 = cross(a, T.e1);
+    normalize(T.e2);
+    return T;
+}
+
+struct RigidState {
+    RigidMesh target, source;
+    orc_octree* tree = nullptr;
+    int D = 0, simmeasure = 2;
+    const double* A = nullptr;   // input data  [D][nv_s]
+    const double* B = nullptr;   // reference   [D][nv_t]
+    std::vector<double> meanA, meanB, current_sim;
+    std::vector<std::vector<int>> nbh;
+    std::vector<std::map<int, double>> sim;   // sim[source column] : target row -> value (SpMat::Set / Peek)
+    double min_sigma = 0.0;
+    ~RigidState() { delete tree; }
+
+    static void means(int D, int n, const double* M, std::vector<double>& out) {   // similarities.cpp:106-126
+        out.assign(n, 0.0);
+        if (D == 1) {
+            double sum = 0.0;
+            for (int i = 0; i < n; ++i) sum += M[i];
+            for (int i = 0; i < n; ++i) out[i] = sum / n;
+        } else
+            for (int i = 0; i < n; ++i) {
+                double sum = 0.0;
+                for (int j = 0; j < D; ++j) sum += M[(size_t)j * n + i];
+                out[i] = sum / D;
+            }
+    }
+    double corr(int i, int j) const {   // similarities.cpp:52-85, full matrices (i: source column, j: target column; 0-based here)
+        double prod = 0.0, varA = 0.0, varB = 0.0;
+        const int ns = source.nv, ntg = target.nv;
+        for (int r = 0; r < D; ++r) {
+            const double a = A[(size_t)r * ns + i], b = B[(size_t)r * ntg + j];
+            prod += (a - meanA[i]) * (b - meanB[j]);
+            varA += (a - meanA[i]) * (a - meanA[i]);
+            varB += (b - meanB[j]) * (b - meanB[j]);
+        }
+        if (varA == 0.0 || varB == 0.0) return 0.0;
+        return prod / (std::sqrt(varA) * std::sqrt(varB));
+    }
+    double ssd(int i, int j) const {    // similarities.cpp:87-104
+        double prod = 0.0;
+        const int ns = source.nv, ntg = target.nv;
+        for (int r = 0; r < D; ++r) {
+            const double a = A[(size_t)r * ns + i], b = B[(size_t)r * ntg + j];
+            prod += (a - b) * (a - b);
+        }
+        return std::sqrt(prod) / D;
+    }
+    void sim_column(int ind) {          // similarities.cpp:37-50 (a neighbour with id 0 is skipped, sic)
+        for (int nb : nbh[ind])
+            if (nb != 0) sim[ind][nb] = simmeasure == 1 ? -ssd(ind, nb) : corr(ind, nb);
+    }
+    double peek(int row, int col) const {
+        auto it = sim[col].find(row);
+        return it == sim[col].end() ? 0.0 : it->second;
+    }
+
+    void neighbourhoods(double ang) {   // reg_tools.cpp:31-58
+        nbh.assign(source.nv, {});
+        for (int index = 0; index < source.nv; ++index) {
+            P3 cr = source.v[index];
+            normalize(cr);
+            std::vector<std::pair<double, int>> c;
+            for (int n = 0; n < target.nv; ++n) {
+                P3 actual = target.v[n];
+                normalize(actual);
+                if (dot(actual, cr) >= std::cos(ang)) c.emplace_back(norm(sub(actual, cr)), n);
+            }
+            std::sort(c.begin(), c.end(), [](const auto& l, const auto& r) -> bool { return l.first < r.first; });
+            for (const auto& n : c) nbh[index].push_back(n.second);
+        }
+    }
+
+    void initialise() {                 // rigid_costfunction.cpp:32-50
+        current_sim.assign(source.nv, 0.0);
+        const double MVD = source.mean_vd();
+        min_sigma = MVD;
+        sim.assign(source.nv, {});
+        means(D, source.nv, A, meanA);
+        means(D, target.nv, B, meanB);
+        neighbourhoods(2 * std::asin(4 * MVD / (2 * RAD)));
+        for (int i = 0; i < source.nv; ++i) sim_column(i);
+    }
+
+    bool all_neighbours(int index, std::vector<int>& N, int n, std::vector<char>& found) {   // rigid_costfunction.cpp:143-165
+        bool update = false;
+        for (int j : target.inc[n]) {
+            const int n0 = target.tri[3 * j], n1 = target.tri[3 * j + 1], n2 = target.tri[3 * j + 2];
+            if (nbh[index][0] != n0 || nbh[index][0] != n1 || nbh[index][0] != n2) update = true;
+            if (!found[n0]) { N.push_back(n0); found[n0] = 1; }
+            if (!found[n1]) { N.push_back(n1); found[n1] = 1; }
+            if (!found[n2]) { N.push_back(n2); found[n2] = 1; }
+        }
+        return update;
+    }
+
+    void wls(const RTangs& tg, int index, const std::vector<int>& q) {   // rigid_costfunction.cpp:63-90
+        double SUM = 0.0, JPsim = 0.0;
+        P3 origin = cross(tg.e1, tg.e2);
+        normalize(origin);
+        origin = mul(origin, RAD);
+        const P3 ys = sub(source.v[index], origin);
+        const double y11 = dot(ys, tg.e1), y21 = dot(ys, tg.e2);
+        for (int qp : q) {
+            const P3 xs = sub(target.v[qp], origin);
+            const double x11 = dot(xs, tg.e1), x21 = dot(xs, tg.e2);
+            const double d1 = x11 - y11, d2 = x21 - y21;
+            if ((d1 * d1 + d2 * d2) > 0) {
+                const double weight = std::exp(-(d1 * d1 + d2 * d2) / (2 * min_sigma * min_sigma));
+                SUM += weight;
+                JPsim += peek(qp, index) * weight;
+            }
+        }
+        if (SUM > 0) JPsim /= SUM;
+        current_sim[index] = JPsim;
+    }
+
+    void evaluate(int i, const RTangs& tg) {   // rigid_costfunction.cpp:92-114
+        if (nbh[i].empty()) return;
+        std::vector<char> found(target.nv, 0);
+        std::vector<int> q;
+        int st = 0;
+        const int t = closest_triangle(tree, source.v[i], &st, nullptr);
+        if (t < 0) throw 1;
+        bool update = false;
+        if (all_neighbours(i, q, target.tri[3 * t], found)) update = true;
+        if (all_neighbours(i, q, target.tri[3 * t + 1], found) || update) update = true;
+        if (all_neighbours(i, q, target.tri[3 * t + 2], found) || update) update = true;
+        if (update) { nbh[i] = q; sim_column(i); }
+        wls(tg, i, q);
+    }
+
+    void rotate(double w1, double w2, double w3) {   // rigid_costfunction.cpp:116-128 + point.cpp:154-171
+        const double R[9] = {std::cos(w2) * std::cos(w3), -std::cos(w1) * std::sin(w3) + std::sin(w1) * std::sin(w2) * std::cos(w3),
+                             std::sin(w1) * std::sin(w3) + std::cos(w1) * std::sin(w2) * std::cos(w3),
+                             std::cos(w2) * std::sin(w3), std::cos(w1) * std::cos(w3) + std::sin(w1) * std::sin(w2) * std::sin(w3),
+                             -std::sin(w1) * std::cos(w3) + std::cos(w1) * std::sin(w2) * std::sin(w3),
+                             -std::sin(w2), std::sin(w1) * std::cos(w2), std::cos(w1) * std::cos(w2)};
+        for (P3& p : source.v) {      // rotation.t() * vector: row r of the product = sum over k of R(k, r) * v(k), from zero, k ascending
+            const double vv[3] = {p.X, p.Y, p.Z};
+            double o[3];
+            for (int r = 0; r < 3; ++r) {
+                double sum = 0.0;
+                for (int k = 0; k < 3; ++k) sum += R[3 * k + r] * vv[k];
+                o[r] = sum;
+            }
+            p = P3{o[0], o[1], o[2]};
+        }
+    }
+
+    double cost(double dw1, double dw2, double dw3) {   // rigid_costfunction.cpp:130-141
+        const std::vector<P3> keep = source.v;
+        rotate(dw1, dw2, dw3);
+        for (int index = 0; index < source.nv; ++index) evaluate(index, rigid_tangs(index, source));
+        double SUM = 0.0;
+        for (int i = 0; i < source.nv; ++i) SUM += current_sim[i];
+        source.v = keep;
+        return SUM;
+    }
+
+    void run(int iters, double stepsize, double spacing) {   // rigid_costfunction.cpp:167-236
+        double Euler1 = 0.0, Euler2 = 0.0, Euler3 = 0.0;
+        int min_iter = 0, loop = 0;
+        double grad_zero = cost(Euler1, Euler2, Euler3);
+        double mingrad_zero = grad_zero;
+        while (spacing > 0.05) {
+            double step = stepsize;
+            const double per = spacing;
+            for (int it = 1; it <= iters; ++it) {
+                Euler1 = 0.0; Euler2 = 0.0; Euler3 = 0.0;
+                P3 grad;
+                grad.X = (cost(Euler1 + per, Euler2, Euler3) - grad_zero) / per;
+                grad.Y = (cost(Euler1, Euler2 + per, Euler3) - grad_zero) / per;
+                grad.Z = (cost(Euler1, Euler2, Euler3 + per) - grad_zero) / per;
+                normalize(grad);
+                Euler1 += step * grad.X; Euler2 += step * grad.Y; Euler3 += step * grad.Z;
+                const std::vector<P3> tmp = source.v;
+                rotate(Euler1, Euler2, Euler3);
+                grad_zero = cost(Euler1, Euler2, Euler3);
+                if (grad_zero > mingrad_zero) { mingrad_zero = grad_zero; min_iter = (loop * iters) + it; }
+                if ((loop * iters) + it - min_iter > 0) { step *= 0.5; source.v = tmp; }
+                if (step < 1e-3) break;
+            }
+            ++loop;
+            spacing *= 0.5;
+        }
+    }
+};
+
+} // namespace
+
+int orc_rigid(int nv_t, const double* tgt_xyz, int nt_t, const int* tgt_tri, int nv_s, const double* src_xyz, int nt_s, const int* src_tri,
+              int D, const double* src_feat, const double* ref_feat, int simmeasure, int iters, double stepsize, double gradsampling,
+              double* out_xyz, double* out_cost0, int* nbh_rowptr, int* nbh_members, int cap) {
+    try {
+        RigidState S;
+        S.target.build(nv_t, tgt_xyz, nt_t, tgt_tri);
+        S.source.build(nv_s, src_xyz, nt_s, src_tri);
+        S.tree = build_tree(nv_t, tgt_xyz, nt_t, tgt_tri);
+        S.D = D; S.simmeasure = simmeasure; S.A = src_feat; S.B = ref_feat;
+        S.initialise();
+        int pos = 0;
+        for (int i = 0; i < nv_s; ++i) {
+            nbh_rowptr[i] = pos;
+            for (int n : S.nbh[i]) { if (pos < cap) nbh_members[pos] = n; ++pos; }
+        }
+        nbh_rowptr[nv_s] = pos;
+        if (out_cost0) *out_cost0 = S.cost(0.0, 0.0, 0.0);
+        S.run(iters, stepsize, gradsampling);
+        for (int i = 0; i < nv_s; ++i) { out_xyz[3 * i] = S.source.v[i].X; out_xyz[3 * i + 1] = S.source.v[i].Y; out_xyz[3 * i + 2] = S.source.v[i].Z; }
+        return pos;
+    } catch (...) { return -1; }
+}
+

@@ -113,6 +113,12 @@ int orc_group_pair_costs(int simmeasure, int S, int ncp, int L, int D, int n_tpl
                          const double* rot, const double* labels, const double* spacings, double range, const int* pairs,
                          int n, const int* req_pair, const int* req_la, const int* req_lb, double* out, int nthreads);
 
+/* RIGID / AFFINE level (rigid_costfunction.cpp:32-236): initialise + cost at zero rotation + run; same outputs as
+ * oracle/ref_meshreg_driver.cpp: refmr_rigid. src_feat [D][nv_s], ref_feat [D][nv_t]. Returns the number of neighbour entries. */
+int orc_rigid(int nv_t, const double* tgt_xyz, int nt_t, const int* tgt_tri, int nv_s, const double* src_xyz, int nt_s, const int* src_tri,
+              int D, const double* src_feat, const double* ref_feat, int simmeasure, int iters, double stepsize, double gradsampling,
+              double* out_xyz, double* out_cost0, int* nbh_rowptr, int* nbh_members, int cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -130,3 +130,20 @@ def test_group_costs_golden(oracle_built):
         got = oracle_built.oracle_group_pair_costs(sim, c["cps"].shape[1], c["tpl"], fields, rot, c["labels"], spacings, 1.0, pairs, rp, la, lb)
         ok = ~np.isnan(got)          # empty intersections: undefined behaviour in the reference, not compared
         assert ok.mean() > 0.9 and np.array_equal(got[ok], g[f"group_pair_s{sim}"][ok])
+
+
+def test_rigid_level_golden(oracle_built):
+    """RIGID / AFFINE level: the CPU restatement (oracle/msm_oracle.cpp: orc_rigid) reproduces the compiled reference's
+    neighbour lists, cost at zero rotation and final rotated source bit for bit (tests/golden/rigid.npz)."""
+    import importlib.util
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden_rigid", os.path.join(here, "golden", "make_golden_rigid.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = np.load(os.path.join(here, "golden", "rigid.npz"))
+    for name, D, sim in (("d2_corr", 2, 2), ("d1_corr", 1, 2), ("d3_ssd", 3, 1)):
+        xyz, tri, src, mov, ref = mod.rigid_case(3, D)
+        moved, cost0, rowptr, members = oracle_built.oracle_rigid(xyz, tri, src, tri, mov, ref, simmeasure=sim, iters=4)
+        assert np.array_equal(rowptr, g[f"{name}_rowptr"]) and np.array_equal(members, g[f"{name}_members"])
+        assert cost0 == float(g[f"{name}_cost0"])
+        assert np.array_equal(moved, g[f"{name}_xyz"])

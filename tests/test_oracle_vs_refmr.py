@@ -177,3 +177,19 @@ def test_rigid_level_reference_reproduces_golden(O):
             assert np.array_equal(rowptr, g[f"{name}_rowptr"]) and np.array_equal(members, g[f"{name}_members"])
         assert np.abs(np.linalg.norm(moved, axis=1) - 100).max() < 1e-9          # a rotation: the sphere radius is kept
         assert rowptr[-1] > 30 * len(xyz)                                       # neighbourhoods of 4 mean vertex distances
+
+
+@pytest.mark.parametrize("sim,D,seed", [(2, 3, 5), (1, 2, 9)])
+def test_rigid_level_oracle_matches_reference(O, sim, D, seed):
+    """The restated RIGID / AFFINE level against the reference's own Rigid_cost_function on a jittered ico4 source that differs from
+    the target (the golden cases use one icosphere for both): everything bit-exact."""
+    from newmsm_b200 import synth
+    xyz, tri = synth.icosphere(4)
+    src = synth.rotate_sphere(synth.jitter_sphere(xyz, tri, frac=0.2, seed=seed), -0.02, 0.05, 0.01)
+    ref = synth.smooth_fields(xyz, D, seed0=40)
+    mov = synth.smooth_fields(src, D, seed0=41)
+    a = O.oracle_rigid(xyz, tri, src, tri, mov, ref, simmeasure=sim, iters=2)
+    b = O.refmr_rigid(xyz, tri, src, tri, mov, ref, simmeasure=sim, iters=2, nthreads=4)
+    assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])     # neighbourhoods (reg_tools.cpp:31-58, incl. the tie order of std::sort)
+    assert a[1] == b[1]                                                  # cost at zero rotation
+    assert np.array_equal(a[0], b[0])                                    # rotated source after run()
