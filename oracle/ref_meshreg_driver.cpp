@@ -307,7 +307,7 @@ int refmr_label_sets(int sgres, double maxvd, double* samples, double* barycentr
 // The RIGID / AFFINE level (rigid_costfunction.cpp:32-236, mesh_registration.cpp:68-73, 117-121): initialise() (neighbourhoods within
 // 4 mean vertex distances, reg_tools.cpp:31-58, + the sparse similarity columns), the cost at zero rotation, and run(). Outputs: the
 // rotated source coordinates [nv_s][3], the neighbour lists after initialise() (CSR, nearest first), the initial cost.
-// not accelerated yet; these outputs pin a future restatement (tests/golden/rigid.npz).
+// not accelerated yet; these outputs pin the CPU restatement (msm_oracle.cpp: orc_rigid, tests/golden/rigid.npz).
 int refmr_rigid(int nv_t, const double* tgt_xyz, int nt_t, const int* tgt_tri, int nv_s, const double* src_xyz, int nt_s, const int* src_tri,
                 int D, const double* src_feat, const double* ref_feat, int simmeasure, int iters, double stepsize, double gradsampling, int nthreads,
                 double* out_xyz, double* out_cost0, int* nbh_rowptr, int* nbh_members, int cap) {

@@ -1,7 +1,7 @@
 """Generates tests/golden/rigid.npz from the UNMODIFIED reference compiled into oracle/_ref/libref_newmeshreg.so (needs
 /root/reference; run from the repo root: python tests/golden/make_golden_rigid.py): outputs of the reference's RIGID / AFFINE level
-(Rigid_cost_function::initialise + rigid_cost_mesh(0,0,0) + run, rigid_costfunction.cpp:32-236) on seeded inputs. SURVEY §8 f4: that
-level is not restated / accelerated yet; these vectors pin the restatement that comes next."""
+(Rigid_cost_function::initialise + rigid_cost_mesh(0,0,0) + run, rigid_costfunction.cpp:32-236) on seeded inputs. SURVEY §8 f4: the level
+is restated in the CPU oracle (orc_rigid, pinned by these vectors) and has no CUDA path yet."""
 import os
 import sys
 

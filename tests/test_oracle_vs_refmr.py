@@ -161,7 +161,7 @@ def test_unary_costs_dice(O, kind, D, sim, pct):
 def test_rigid_level_reference_reproduces_golden(O):
     """SURVEY §8 f4 groundwork: the reference's RIGID / AFFINE level (rigid_costfunction.cpp:32-236), run through the compiled reference
     here, reproduces tests/golden/rigid.npz bit for bit and does not depend on the thread count (its OpenMP loops write disjoint entries).
-    No restatement / CUDA path exists for this level yet; the vectors pin the one that comes next."""
+    The CPU restatement is pinned by the same vectors (test_oracle_golden.py::test_rigid_level_golden); no CUDA path exists yet."""
     import os
     sys_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
     import importlib.util
