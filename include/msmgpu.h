@@ -57,6 +57,11 @@ const char* msmgpu_debug_take_cuda_error(void);
 msmgpu_status msmgpu_set_query_group(int lanes);
 int msmgpu_get_query_group(void);
 
+/* Other tuning knobs with no effect on results (launch variants that profiles/ compares): "gather" (1 = bulk-copy row gather for
+ * rows >= 128 bytes, 0 = register-path kernels), "gather_variant", "gather_variant_bary", "resample_variant", "weights_minb",
+ * "query_order" ... Each starts from its MSMGPU_<NAME> environment variable. */
+msmgpu_status msmgpu_set_tuning(const char* name, int value);
+
 /* stream == NULL -> a private non-blocking stream; otherwise a cudaStream_t owned by the caller.
  * A context (and the handles created from it) serves ONE host thread at a time; use one context per thread (or per device) otherwise. */
 msmgpu_status msmgpu_ctx_create(int device, void* stream, msmgpu_ctx** out);
@@ -169,6 +174,10 @@ msmgpu_status msmgpu_bary_resample_batch_f32_dev_keep(msmgpu_ctx* ctx, int n_sub
                                                       msmgpu_fwd* keep);
 msmgpu_status msmgpu_adaptive_weights_batch_fwd(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* in_meshes, msmgpu_octree* const* in_trees,
                                                 msmgpu_mesh* low_mesh, msmgpu_octree* low_tree, const msmgpu_fwd* fwd, msmgpu_weights** out);
+/* replaces: the interpolation loop of barycentric_data_interpolation (resampler.cpp:40-52) over weight maps that are already known:
+ * applies the kept forward maps of a batch to (other) feature rows of the same subjects — the gather kernel alone.
+ * Rows must be 16-byte aligned multiples of 16 bytes between 128 B and 2 KB. */
+msmgpu_status msmgpu_fwd_apply_batch_f32_dev(msmgpu_ctx* ctx, const msmgpu_fwd* fwd, int D, const float* const* d_feat_in, float* const* d_feat_out);
 msmgpu_status msmgpu_bary_resample_f32(msmgpu_octree* t, int n, const double* pts, int D, const float* feat_in, float* feat_out);
 /* the same two resamplers on the mesh's resident features: only the result crosses PCIe. feat_out channel-major [D][n] floats */
 msmgpu_status msmgpu_mesh_bary_resample_f32(msmgpu_octree* t, int n, const double* pts, float* feat_out);

@@ -120,6 +120,14 @@ struct Stats {
     }
 } stats;
 
+// the hooks are reachable from the reference's OpenMP loops: the counters are updated under a lock
+static std::mutex g_stats_mutex;
+static void stat_add(double& seconds, long* calls, double dt) {
+    std::lock_guard<std::mutex> g(g_stats_mutex);
+    seconds += dt;
+    if (calls) ++*calls;
+}
+
 // the model's protected wiring, reachable from a derived view (no reference header is changed)
 struct ModelView : NonLinearSRegDiscreteModel {
     static void install(NonLinearSRegDiscreteModel* m, myparam& P) {
@@ -151,8 +159,7 @@ Mesh wrap_metric_resample(const Mesh& in, const Mesh& target, int nthreads, std:
     if (EXCL || disabled("resample")) return real_metric_resample(in, target, nthreads, EXCL);   // exclusion masks: host-side filtering, out of scope
     const double t0 = omp_get_wtime();
     Mesh out = [&] { std::lock_guard<std::mutex> g(g_device_mutex); return newresampler_gpu::metric_resample(in, target, nthreads); }();
-    stats.resample += omp_get_wtime() - t0;
-    stats.n_resample++;
+    stat_add(stats.resample, &stats.n_resample, omp_get_wtime() - t0);
     if (verify()) {
         const Mesh ref = real_metric_resample(in, target, nthreads, EXCL);
         long bad = 0;
@@ -172,13 +179,12 @@ void wrap_sphere_project_warp(Mesh& sphere, const Mesh& from, const Mesh& to, in
     if (disabled("resample")) return real_sphere_project_warp(sphere, from, to, nthreads);
     // the first warp after get_source_data closes the optimiser phase of a discrete iteration (mesh_registration.cpp:170-222)
     double& mark = newmeshreg_gpu::detail::timers().source_done_at;
-    if (mark > 0) { stats.optimise += omp_get_wtime() - mark; mark = 0; }
+    if (mark > 0) { stat_add(stats.optimise, nullptr, omp_get_wtime() - mark); mark = 0; }
     Mesh before;
     if (verify()) before = sphere;
     const double t0 = omp_get_wtime();
     { std::lock_guard<std::mutex> g(g_device_mutex); newresampler_gpu::sphere_project_warp(sphere, from, to, nthreads); }
-    stats.warp += omp_get_wtime() - t0;
-    stats.n_warp++;
+    stat_add(stats.warp, &stats.n_warp, omp_get_wtime() - t0);
     if (verify()) {
         real_sphere_project_warp(before, from, to, nthreads);
         long bad = 0;
@@ -199,8 +205,7 @@ Mesh wrap_make_mesh_from_icosa(int n) {
     if (disabled("icosa")) return real_make_mesh_from_icosa(n);
     const double t0 = omp_get_wtime();
     Mesh m = newresampler_gpu::make_mesh_from_icosa(n);
-    stats.icosa += omp_get_wtime() - t0;
-    stats.n_icosa++;
+    stat_add(stats.icosa, &stats.n_icosa, omp_get_wtime() - t0);
     return m;
 }
 
@@ -211,8 +216,7 @@ Mesh wrap_smooth_data(Mesh& orig, const Mesh& sphLow, double sigma, int nthreads
     if (verify()) keep = orig;
     const double t0 = omp_get_wtime();
     Mesh out = [&] { std::lock_guard<std::mutex> g(g_device_mutex); return newresampler_gpu::smooth_data(orig, sphLow, sigma, nthreads, EXCL); }();
-    stats.smooth += omp_get_wtime() - t0;
-    stats.n_smooth++;
+    stat_add(stats.smooth, &stats.n_smooth, omp_get_wtime() - t0);
     if (verify()) {
         const Mesh ref = real_smooth_data(keep, sphLow, sigma, nthreads, EXCL);
         long bad = 0;
@@ -230,7 +234,7 @@ Mesh wrap_smooth_data(Mesh& orig, const Mesh& sphLow, double sigma, int nthreads
 Mesh wrap_featurespace_initialise(newmeshreg::featurespace* self, int ico, std::vector<Mesh>& IN, bool exclude) {   // timing only
     const double t0 = omp_get_wtime();
     Mesh m = real_featurespace_initialise(self, ico, IN, exclude);
-    stats.featinit += omp_get_wtime() - t0;
+    stat_add(stats.featinit, nullptr, omp_get_wtime() - t0);
     return m;
 }
 #endif

@@ -39,6 +39,8 @@ _SIGNATURES = {
     "msmgpu_debug_take_cuda_error": (C.c_char_p, []),
     "msmgpu_set_query_group": (_i, [_i]),
     "msmgpu_get_query_group": (_i, []),
+    "msmgpu_set_tuning": (_i, [C.c_char_p, _i]),
+    "msmgpu_fwd_apply_batch_f32_dev": (_i, [_vp, _vp, _i, _vp, _vp]),
     "msmgpu_ctx_create": (_i, [_i, _vp, _pp]),
     "msmgpu_ctx_destroy": (None, [_vp]),
     "msmgpu_ctx_sync": (_i, [_vp]),

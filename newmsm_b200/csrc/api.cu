@@ -7,16 +7,39 @@
 #include <cmath>
 #include <cstring>
 #include <functional>
+#include <map>
+#include <mutex>
 
 namespace msm {
 
+// Tuning knobs (no effect on results): initialised from the environment on first use, changeable through msmgpu_set_tuning.
+static std::mutex g_tuning_mutex;
+static std::map<std::string, int>& tuning_map() { static std::map<std::string, int> m; return m; }
+int tuning_get(const char* name, const char* env, int def) {
+    std::lock_guard<std::mutex> g(g_tuning_mutex);
+    auto& m = tuning_map();
+    auto it = m.find(name);
+    if (it != m.end()) return it->second;
+    const char* e = env ? getenv(env) : nullptr;
+    const int v = e ? atoi(e) : def;
+    m[name] = v;
+    return v;
+}
+
 static thread_local std::string g_last_error;
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0};
 
 void set_error(const std::string& msg) { g_last_error = msg; }
 msmgpu_status fail(msmgpu_status st, const std::string& msg) {
     g_last_error = msg;
     return st;
+}
+
+msmgpu_status ctx_aux(msmgpu_ctx* ctx) {
+    if (ctx->aux_stream) return MSMGPU_OK;
+    MSM_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t& e : ctx->aux_ev) MSM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return MSMGPU_OK;
 }
 
 msmgpu_status status_to_error(int code) {
@@ -156,7 +179,14 @@ const char* msmgpu_debug_take_cuda_error(void) {
     return e == cudaSuccess ? "" : cudaGetErrorString(e);
 }
 
-unsigned long long msmgpu_launch_count(void) { return g_launch_count; }
+msmgpu_status msmgpu_set_tuning(const char* name, int value) {
+    if (!name) return fail(MSMGPU_ERR_INVALID, "set_tuning: name is NULL");
+    std::lock_guard<std::mutex> g(g_tuning_mutex);
+    tuning_map()[name] = value;
+    return MSMGPU_OK;
+}
+
+unsigned long long msmgpu_launch_count(void) { return g_launch_count.load(std::memory_order_relaxed); }
 
 int msmgpu_device_count(void) {
     int n = 0;
@@ -192,6 +222,8 @@ msmgpu_status msmgpu_ctx_create(int device, void* stream, msmgpu_ctx** out) {
 void msmgpu_ctx_destroy(msmgpu_ctx* c) {
     if (!c) return;
     cudaStreamSynchronize(c->stream);
+    if (c->aux_stream) { cudaStreamSynchronize(c->aux_stream); cudaStreamDestroy(c->aux_stream); }
+    for (cudaEvent_t e : c->aux_ev) if (e) cudaEventDestroy(e);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -474,8 +506,72 @@ msmgpu_status msmgpu_bary_resample_batch_f32_dev_keep(msmgpu_ctx* ctx, int n_sub
     cudaStream_t s = ctx->stream;
     std::vector<ResampleJob> jobs(n_subjects);
     if (keep) { keep->trees.assign(trees, trees + n_subjects); keep->filled = true; }
-    for (int i = 0; i < n_subjects; ++i) {
+    for (int i = 0; i < n_subjects; ++i)
         if (!trees[i] || trees[i]->mesh->ctx != ctx) return fail(MSMGPU_ERR_INVALID, "bary_resample_batch: tree from another context");
+    if (n == 0) return MSMGPU_OK;
+    // Rows of >= 128 bytes: two kernels. (1) the queries + weight maps of all subjects (k_bary_weights_batch) into the forward store
+    // (the caller's `keep`, or a scratch one), (2) the bulk-copy row gather (gather.cu) over those maps. The fused kernel below is
+    // kept for short rows and as the A/B reference (MSMGPU_GATHER=0).
+    bool aligned = true;
+    for (int i = 0; i < n_subjects; ++i) aligned = aligned && ((reinterpret_cast<uintptr_t>(d_feat_in[i]) | reinterpret_cast<uintptr_t>(d_feat_out[i])) & 15) == 0;
+    // "gather": 1 (default) = two kernels, queries + bulk-copy row gather; 0 = the fused register-path kernel below.
+    const int mode = tuning_get("gather", "MSMGPU_GATHER", 1);
+    if (aligned && gather_bulk_supported(D) && mode != 0) {
+        DevBuf<int> t_idx, t_ne, t_st;
+        DevBuf<double> t_w;
+        int *p_idx, *p_ne;
+        double* p_w;
+        const size_t tot = (size_t)n_subjects * n;
+        if (keep) { p_idx = keep->idx.p; p_w = keep->w.p; p_ne = keep->ne.p; }
+        else {
+            MSM_CUDA(t_idx.alloc(3 * tot, s)); MSM_CUDA(t_w.alloc(3 * tot, s)); MSM_CUDA(t_ne.alloc(tot, s));
+            p_idx = t_idx.p; p_w = t_w.p; p_ne = t_ne.p;
+        }
+        int* p_st = d_status;
+        if (!p_st) { MSM_CUDA(t_st.alloc(tot, s)); p_st = t_st.p; }
+        std::vector<QueryJob> qj(n_subjects);
+        std::vector<GatherJob> gj(n_subjects);
+        DevBuf<int> perm;
+        // forward queries (few points per tree, trees streamed from HBM) measured slightly SLOWER in Morton order (profiles/r2b): opt-in
+        if (tuning_get("query_order", "MSMGPU_QUERY_ORDER", 1) >= 2) MSM_TRY(morton_order(d_pts, n, perm, s));
+        for (int i = 0; i < n_subjects; ++i) {
+            qj[i] = QueryJob{trees[i]->view(), d_pts, n, (int)((size_t)i * n), perm.p};
+            gj[i] = GatherJob{nullptr, p_idx + 3 * (size_t)i * n, p_w + 3 * (size_t)i * n, d_feat_in[i], d_feat_out[i]};
+        }
+        if (tot > 0x7fffffffull / 3) return fail(MSMGPU_ERR_CAPACITY, "bary_resample_batch: batch too large");
+        DevBuf<QueryJob> d_qj;
+        DevBuf<GatherJob> d_gj;
+        MSM_CUDA(d_qj.alloc(n_subjects, s));
+        MSM_CUDA(d_gj.alloc(n_subjects, s));
+        MSM_CUDA(cudaMemcpyAsync(d_qj.p, qj.data(), qj.size() * sizeof(QueryJob), cudaMemcpyHostToDevice, s));
+        MSM_CUDA(cudaMemcpyAsync(d_gj.p, gj.data(), gj.size() * sizeof(GatherJob), cudaMemcpyHostToDevice, s));
+        // Subject chunks: the gather of chunk k runs on the context's second stream while the queries of chunk k+1 run on the first
+        // (queries are latency-bound on the octree, the gather is bandwidth-bound on the feature rows). The call stays asynchronous
+        // on the context's stream: the second stream is forked from it and joined back before returning.
+        // Measured (profiles/r2c_tune_gather_first_version.txt): no gain from 2 - 16 chunks — the query kernel's CTAs occupy every SM
+        // before the gather of the previous chunk is admitted — so one chunk is the default.
+        int chunks = std::max(1, std::min(tuning_get("bary_chunks", "MSMGPU_BARY_CHUNKS", 1), n_subjects));
+        const int cap = tuning_get("gather_ctas_per_sm", "MSMGPU_GATHER_CTAS_PER_SM", 0);
+        if (chunks == 1) {
+            MSM_TRY(launch_bary_weights_batch(d_qj.p, n_subjects, n, p_idx, p_w, p_ne, p_st, s));
+            return launch_gather_rows_bulk(d_gj.p, n_subjects, n, D, true, ctx->device, s, cap);
+        }
+        MSM_TRY(ctx_aux(ctx));
+        MSM_CUDA(cudaEventRecord(ctx->aux_ev[0], s));                      // fork: the job tables are uploaded, earlier work is done
+        MSM_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_ev[0], 0));
+        for (int c = 0; c < chunks; ++c) {
+            const int b = (int)((long long)n_subjects * c / chunks), e = (int)((long long)n_subjects * (c + 1) / chunks);
+            if (e <= b) continue;
+            MSM_TRY(launch_bary_weights_batch(d_qj.p + b, e - b, n, p_idx, p_w, p_ne, p_st, s));
+            MSM_CUDA(cudaEventRecord(ctx->aux_ev[1], s));
+            MSM_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_ev[1], 0));
+            MSM_TRY(launch_gather_rows_bulk(d_gj.p + b, e - b, n, D, true, ctx->device, ctx->aux_stream, cap));
+        }
+        MSM_CUDA(cudaEventRecord(ctx->aux_ev[2], ctx->aux_stream));         // join
+        MSM_CUDA(cudaStreamWaitEvent(s, ctx->aux_ev[2], 0));
+        return MSMGPU_OK;
+    }
+    for (int i = 0; i < n_subjects; ++i) {
         jobs[i] = ResampleJob{trees[i]->view(), d_feat_in[i], d_feat_out[i], keep ? keep->idx.p + 3 * (size_t)i * n : nullptr,
                               keep ? keep->w.p + 3 * (size_t)i * n : nullptr, keep ? keep->ne.p + (size_t)i * n : nullptr};
     }
@@ -484,6 +580,22 @@ msmgpu_status msmgpu_bary_resample_batch_f32_dev_keep(msmgpu_ctx* ctx, int n_sub
     // pageable source: the runtime stages it before returning, so `jobs` may go out of scope
     MSM_CUDA(cudaMemcpyAsync(d_jobs.p, jobs.data(), jobs.size() * sizeof(ResampleJob), cudaMemcpyHostToDevice, s));
     return launch_bary_resample_f32(d_jobs.p, n_subjects, n, d_pts, D, d_status, s);
+}
+
+msmgpu_status msmgpu_fwd_apply_batch_f32_dev(msmgpu_ctx* ctx, const msmgpu_fwd* fwd, int D, const float* const* d_feat_in, float* const* d_feat_out) {
+    if (!ctx || !fwd || fwd->ctx != ctx || !fwd->filled || D <= 0 || !d_feat_in || !d_feat_out) return fail(MSMGPU_ERR_INVALID, "fwd_apply_batch: bad arguments");
+    MSM_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const int S = fwd->S, n = fwd->n;
+    bool aligned = true;
+    for (int i = 0; i < S; ++i) aligned = aligned && ((reinterpret_cast<uintptr_t>(d_feat_in[i]) | reinterpret_cast<uintptr_t>(d_feat_out[i])) & 15) == 0;
+    if (!(aligned && gather_bulk_supported(D))) return fail(MSMGPU_ERR_INVALID, "fwd_apply_batch: rows must be 16-byte aligned multiples of 16 bytes, 128 B .. 2 KB");
+    std::vector<GatherJob> gj(S);
+    for (int i = 0; i < S; ++i) gj[i] = GatherJob{nullptr, fwd->idx.p + 3 * (size_t)i * n, fwd->w.p + 3 * (size_t)i * n, d_feat_in[i], d_feat_out[i]};
+    DevBuf<GatherJob> d_gj;
+    MSM_CUDA(d_gj.alloc(S, s));
+    MSM_CUDA(cudaMemcpyAsync(d_gj.p, gj.data(), gj.size() * sizeof(GatherJob), cudaMemcpyHostToDevice, s));
+    return launch_gather_rows_bulk(d_gj.p, S, n, D, true, ctx->device, s);
 }
 
 msmgpu_status msmgpu_bary_resample_f32_dev(msmgpu_octree* t, int n, const double* d_pts, int D, const float* d_feat_in, float* d_feat_out, int32_t* d_status) {

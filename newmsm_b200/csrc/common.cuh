@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <atomic>
 #include <cstdio>
 #include <memory>
 #include <string>
@@ -23,10 +24,10 @@ msmgpu_status fail(msmgpu_status st, const std::string& msg);
     } while (0)
 
 // after every kernel launch: count it (msmgpu_launch_count) and pick up launch errors
-extern unsigned long long g_launch_count;
+extern std::atomic<unsigned long long> g_launch_count;   // contexts are driven from several host threads
 #define MSM_LAUNCH_CHECK()                 \
     do {                                   \
-        ++::msm::g_launch_count;           \
+        ::msm::g_launch_count.fetch_add(1, std::memory_order_relaxed); \
         MSM_CUDA(cudaGetLastError());      \
     } while (0)
 
@@ -94,6 +95,8 @@ struct msmgpu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t aux_stream = nullptr;      // lazily created second stream: the gather of one subject chunk overlaps the queries of the next
+    cudaEvent_t aux_ev[3] = {nullptr, nullptr, nullptr};   // fork / chunk-ready / join (timing disabled)
     int* pinned = nullptr;   // 64 ints of page-locked host memory: small device -> host results inside launch sequences (level totals of the
                              // octree build) arrive by plain DMA instead of the staged, stream-draining path of pageable copies
 };
@@ -160,10 +163,24 @@ msmgpu_status mesh_refresh_tables(msmgpu_mesh* m);
 msmgpu_status ensure_tables(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes);   // one launch for every dirty mesh
 msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, std::shared_ptr<Forest>& out, std::vector<int>& roots);
 
+int tuning_get(const char* name, const char* env, int def);   // api.cu: knob registry (environment default, msmgpu_set_tuning)
 int query_group_width();
 msmgpu_status launch_nearest(const TreeView& t, int n, const double* d_pts, int* d_tri, int* d_vertex, int* d_status, cudaStream_t s);
 msmgpu_status launch_bary_weights(const TreeView& t, int n, const double* d_pts, int* d_idx, double* d_w, int* d_ne, int* d_status, cudaStream_t s);
 msmgpu_status launch_blend_coords(const TreeView& t, int n, const double* d_pts, const double* d_payload_xyz, double* d_out, int reproject, int* d_status, cudaStream_t s);
+// row gather through bulk asynchronous copies (gather.cu), shared by the barycentric maps and the CSR rows of the adaptive weights
+struct GatherJob {
+    const int* rowptr;   // CSR: n_rows + 1 absolute offsets into col / val; barycentric maps: unused (three slots per row)
+    const int* col;      // source row of every entry (barycentric maps: col < 0 = absent entry)
+    const double* val;
+    const float* in;     // [n_cols][D]
+    float* out;          // [n_rows][D]
+};
+bool gather_bulk_supported(int D);
+bool gather_bulk_enabled();
+msmgpu_status launch_gather_rows_bulk(const GatherJob* d_jobs, int n_jobs, int n_rows, int D, bool bary, int device, cudaStream_t s, int max_ctas_per_sm = 0);
+msmgpu_status ctx_aux(msmgpu_ctx* ctx);   // creates ctx->aux_stream / aux_ev on first use
+
 msmgpu_status launch_gather_channels_f64(int n, int nv, int D, const int* d_vtx, const double* d_in, double* d_out, cudaStream_t s);
 
 struct QueryJob {         // one subject of a batched barycentric-weights launch
@@ -171,7 +188,9 @@ struct QueryJob {         // one subject of a batched barycentric-weights launch
     const double* pts;      // [n][3]
     int n;
     int out_off;            // first output slot of this job in the concatenated outputs
+    const int* perm;        // optional processing order (order.cu): thread k handles point perm[k]; outputs stay at the point's index
 };
+msmgpu_status morton_order(const double* d_xyz, int n, DevBuf<int>& perm, cudaStream_t s);
 msmgpu_status launch_bary_weights_batch(const QueryJob* d_jobs, int n_jobs, int max_n, int* d_idx, double* d_w, int* d_ne, int* d_status, cudaStream_t s);
 
 struct ResampleJob {      // one subject of a batched fused resample

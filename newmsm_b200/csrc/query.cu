@@ -76,9 +76,10 @@ __global__ void __launch_bounds__(256, MINB) k_bary_weights_batch(const QueryJob
                                                             int* __restrict__ out_ne, int* __restrict__ out_status) {
     const QueryJob job = jobs[blockIdx.y];
     const int gl = threadIdx.x % G;
-    const int q = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int k = (blockIdx.x * blockDim.x + threadIdx.x) / G;
     if ((blockIdx.x * blockDim.x) / G >= job.n) return;     // whole CTA beyond this job's points
-    const bool active = q < job.n;
+    const bool active = k < job.n;
+    const int q = (active && job.perm) ? __ldg(job.perm + k) : k;   // processing order only; outputs are indexed by the point
     const V3 pt = active ? load_pt(job.pts, q) : V3{0, 0, 0};
     int st;
     const int t = nearest_triangle<G>(job.tree, pt, active, gl, st);
@@ -197,11 +198,13 @@ __global__ void __launch_bounds__(kResThreads, MINB) k_bary_resample_f32(const R
             float4* stage = s_stage_all + (size_t)warp * kResUnroll * 3 * 32;
             for (int s0 = lane; s0 < slots; s0 += 32 * kResUnroll) {
                 double w[kResUnroll][3];
+                int nes[kResUnroll];
 #pragma unroll
                 for (int u = 0; u < kResUnroll; ++u) {
                     const int s = min(s0 + 32 * u, slots - 1);
                     const int q = s / D4, c = s - q * D4;
                     const int ne = s_ne[q];
+                    nes[u] = ne;
 #pragma unroll
                     for (int j = 0; j < 3; ++j) {
                         const bool on = j < ne;
@@ -220,7 +223,7 @@ __global__ void __launch_bounds__(kResThreads, MINB) k_bary_resample_f32(const R
 #pragma unroll
                     for (int j = 0; j < 3; ++j) {
                         const double ww = w[u][j];
-                        const float4 v = ww != 0.0 ? stage[(u * 3 + j) * 32 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4 v = j < nes[u] ? stage[(u * 3 + j) * 32 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
                         a0 += (double)v.x * ww; a1 += (double)v.y * ww; a2 += (double)v.z * ww; a3 += (double)v.w * ww;
                     }
                     if (s0 + 32 * u < slots) __stcs(out4 + (s0 + 32 * u), make_float4((float)a0, (float)a1, (float)a2, (float)a3));
@@ -232,11 +235,13 @@ __global__ void __launch_bounds__(kResThreads, MINB) k_bary_resample_f32(const R
                 // map entries re-read entry 0 with weight 0), conversions and FP64 sums only afterwards
                 float4 f[kResUnroll][3];
                 double w[kResUnroll][3];
+                int nes[kResUnroll];
     #pragma unroll
                 for (int u = 0; u < kResUnroll; ++u) {
                     const int s = min(s0 + 32 * u, slots - 1);
                     const int q = s / D4, c = s - q * D4;
                     const int ne = s_ne[q];
+                    nes[u] = ne;
     #pragma unroll
                     for (int j = 0; j < 3; ++j) {
                         const bool on = j < ne;
@@ -249,9 +254,9 @@ __global__ void __launch_bounds__(kResThreads, MINB) k_bary_resample_f32(const R
                 for (int u = 0; u < kResUnroll; ++u) {
                     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     #pragma unroll
-                    for (int j = 0; j < 3; ++j) {   // an absent entry contributes (finite or not) * 0 -> guarded by the select below
+                    for (int j = 0; j < 3; ++j) {   // an ABSENT entry adds 0; a present one with weight 0 still multiplies (NaN * 0 = NaN, resampler.cpp:46-48)
                         const double ww = w[u][j];
-                        const float4 v = ww != 0.0 ? f[u][j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4 v = j < nes[u] ? f[u][j] : make_float4(0.f, 0.f, 0.f, 0.f);
                         a0 += (double)v.x * ww; a1 += (double)v.y * ww; a2 += (double)v.z * ww; a3 += (double)v.w * ww;
                     }
                     if (s0 + 32 * u < slots) __stcs(out4 + (s0 + 32 * u), make_float4((float)a0, (float)a1, (float)a2, (float)a3));
@@ -280,20 +285,20 @@ __global__ void k_gather_channels_f64(int n, int nv, int D, const int* __restric
 }
 
 // ------------------------------------------------------------------------------------------
-// launchers. The group width is a tuning knob (MSMGPU_QUERY_GROUP = 1,2,4,8,16,32; default 8).
+// launchers. The group width is a tuning knob (MSMGPU_QUERY_GROUP = 1,2,4,8,16,32; default 1).
 // ------------------------------------------------------------------------------------------
-static int g_query_group = 0;   // 0 = not yet chosen
-
 static bool valid_group(int v) { return v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32; }
 
-int query_group_width() {
-    if (g_query_group == 0) {
+static std::atomic<int>& query_group_slot() {   // initialised once (thread-safe function-local static) from the environment
+    static std::atomic<int> g{[] {
         const char* e = getenv("MSMGPU_QUERY_GROUP");
         const int v = e ? atoi(e) : 1;
-        g_query_group = valid_group(v) ? v : 1;
-    }
-    return g_query_group;
+        return valid_group(v) ? v : 1;
+    }()};
+    return g;
 }
+
+int query_group_width() { return query_group_slot().load(std::memory_order_relaxed); }
 
 #define MSM_DISPATCH_G(G_, ...)                          \
     switch (G_) {                                        \
@@ -326,7 +331,7 @@ msmgpu_status launch_bary_weights(const TreeView& t, int n, const double* d_pts,
 msmgpu_status launch_bary_weights_batch(const QueryJob* d_jobs, int n_jobs, int max_n, int* d_idx, double* d_w, int* d_ne, int* d_status, cudaStream_t s) {
     if (n_jobs <= 0 || max_n <= 0) return MSMGPU_OK;
     const int g = query_group_width();
-    static const int minb = [] { const char* e = getenv("MSMGPU_WEIGHTS_MINB"); return e ? atoi(e) : 4; }();   // tuning knob: resident CTAs per SM (4: 64 registers, measured best)
+    const int minb = tuning_get("weights_minb", "MSMGPU_WEIGHTS_MINB", 4);   // tuning knob: resident CTAs per SM (4: 64 registers, measured best)
     const dim3 grid(query_blocks(max_n, g), (unsigned)n_jobs);
     switch (minb) {
         case 2: MSM_DISPATCH_G(g, (k_bary_weights_batch<G, 2><<<grid, 256, 0, s>>>(d_jobs, d_idx, d_w, d_ne, d_status))); break;
@@ -362,7 +367,7 @@ msmgpu_status launch_bary_resample_f32(const ResampleJob* d_jobs, int n_jobs, in
     if (n <= 0 || n_jobs <= 0) return MSMGPU_OK;
     const int g = query_group_width();
     const dim3 grid((unsigned)((n + kResTile - 1) / kResTile), (unsigned)n_jobs);
-    static const int variant = [] { const char* e = getenv("MSMGPU_RESAMPLE_VARIANT"); return e ? atoi(e) : 2; }();
+    const int variant = tuning_get("resample_variant", "MSMGPU_RESAMPLE_VARIANT", 2);
     switch (variant) {   // tuning knob (profiles/): registers per thread vs loads in flight
         case 1: MSM_DISPATCH_G(g, (k_bary_resample_f32<G, 2, 3><<<grid, kResThreads, 0, s>>>(d_jobs, n, d_pts, D, d_status))); break;
         case 2: MSM_DISPATCH_G(g, (k_bary_resample_f32<G, 2, 4><<<grid, kResThreads, 0, s>>>(d_jobs, n, d_pts, D, d_status))); break;
@@ -391,7 +396,7 @@ msmgpu_status launch_gather_channels_f64(int n, int nv, int D, const int* d_vtx,
 
 extern "C" msmgpu_status msmgpu_set_query_group(int lanes) {
     if (!msm::valid_group(lanes)) return msm::fail(MSMGPU_ERR_INVALID, "set_query_group: lanes must be 1, 2, 4, 8, 16 or 32");
-    msm::g_query_group = lanes;
+    msm::query_group_slot().store(lanes, std::memory_order_relaxed);
     return MSMGPU_OK;
 }
 extern "C" int msmgpu_get_query_group(void) { return msm::query_group_width(); }

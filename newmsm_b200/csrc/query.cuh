@@ -152,7 +152,9 @@ __device__ __forceinline__ int nearest_triangle(const TreeView& T, const V3& pt,
         const bool need2 = need && best_t < 0;
         if (__any_sync(kFull, need2)) {
             if (need2) {   // fallback 2, octree.cpp:194-208: triangle owning the geodesically nearest corner.
-                // 2R asin(c/2R) is increasing in the chord c, so the chord is compared directly.
+                // 2R asin(c/2R) is increasing in the chord c for c <= 2R, so the chord is compared directly. Known difference: two
+                // DISTINCT chords whose asin values round to the same double tie in the reference (first corner kept) and not here
+                // (smaller chord kept); asin is not evaluated on the device because it is not bit-identical to glibc's.
                 int base = 0;
                 for (int c = 0; c < 8; ++c) {
                     const int4 ch = __ldg(T.nodes + first_child + c);
@@ -162,7 +164,8 @@ __device__ __forceinline__ int nearest_triangle(const TreeView& T, const V3& pt,
 #pragma unroll
                         for (int k = 0; k < 3; ++k) {
                             const double d = vnorm(vsub(V3{v[3 * k], v[3 * k + 1], v[3 * k + 2]}, pt));
-                            if (d < best_d) { best_d = d; best_pos = 3 * (base + i) + k; best_t = t; }
+                            // a chord longer than the diameter makes the reference's asin NaN and its `<` false: corner skipped
+                            if (d <= 2.0 * kRad && d < best_d) { best_d = d; best_pos = 3 * (base + i) + k; best_t = t; }
                         }
                     }
                     base += ch.z;

@@ -60,6 +60,10 @@ using namespace msm;
 extern "C" msmgpu_status msmgpu_smooth_neighbourhoods(msmgpu_ctx* ctx, int n, const double* low_xyz, const int32_t* closest, double cos_ang,
                                                       int32_t* rowptr, int64_t cap, int32_t* members, double* chords) {
     if (!ctx || n <= 0 || !low_xyz || !closest || !rowptr) return fail(MSMGPU_ERR_INVALID, "smooth_neighbourhoods: bad arguments");
+    // closest[] indexes low_xyz (the reference reads sphLow through ids that came from `orig`, resampler.cpp:185-186: valid only
+    // when both meshes have the same vertices); an id outside [0, n) would be an out-of-bounds read on the device
+    for (int i = 0; i < n; ++i)
+        if (closest[i] < 0 || closest[i] >= n) return fail(MSMGPU_ERR_INVALID, "smooth_neighbourhoods: closest[] holds a vertex id outside the mesh");
     MSM_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     DevBuf<double> d_xyz, d_unit, d_ch;

@@ -422,10 +422,17 @@ msmgpu_status adaptive_weights_build_batch(msmgpu_ctx* ctx, int S, msmgpu_mesh* 
     if (3 * (NV + NL) > 0x7fffffffll) return fail(MSMGPU_ERR_CAPACITY, "adaptive_weights: batch too large for 32-bit offsets");
 
     // forward: targets located in each input mesh; reverse: input vertices located in the target mesh (resampler.cpp:74-78)
+    // processing order of the queries (order.cu): one Morton permutation of the first input mesh serves every subject with the same
+    // vertex count (a batch shares one topology and nearly the same geometry); one of the target vertices serves the forward queries
+    DevBuf<int> perm_rev, perm_fwd;
+    const int ordered = tuning_get("query_order", "MSMGPU_QUERY_ORDER", 1);   // 0 off, 1 reverse queries (default), 2 forward queries too
+    if (ordered >= 1) MSM_TRY(morton_order(in_meshes[0]->xyz.p, in_meshes[0]->nv, perm_rev, s));
+    if (ordered >= 2 && !fwd) MSM_TRY(morton_order(low_mesh->xyz.p, n_low, perm_fwd, s));
     std::vector<QueryJob> jobs(2 * (size_t)S);
     for (int i = 0; i < S; ++i) {
-        jobs[i] = QueryJob{in_trees[i]->view(), low_mesh->xyz.p, n_low, i * n_low};
-        jobs[S + i] = QueryJob{low_tree->view(), in_meshes[i]->xyz.p, in_meshes[i]->nv, in_off[i]};
+        jobs[i] = QueryJob{in_trees[i]->view(), low_mesh->xyz.p, n_low, i * n_low, perm_fwd.p};
+        jobs[S + i] = QueryJob{low_tree->view(), in_meshes[i]->xyz.p, in_meshes[i]->nv, in_off[i],
+                               in_meshes[i]->nv == in_meshes[0]->nv ? perm_rev.p : nullptr};
     }
     DevBuf<QueryJob> d_jobs;
     DevBuf<int> d_in_off;
@@ -587,6 +594,18 @@ static msmgpu_status csr_apply_batch(msmgpu_ctx* ctx, int n, msmgpu_weights* con
         vec = vec && ((reinterpret_cast<uintptr_t>(d_in[i]) | reinterpret_cast<uintptr_t>(d_out[i])) & 15) == 0;
     }
     if (n_rows == 0) return MSMGPU_OK;
+    // The bulk-copy gather (gather.cu) is opt-in for CSR rows ("gather_csr"): a row of the adaptive matrix has ~15 entries and every
+    // source row is re-read ~3 times from L2, so the kernel moves 12.6 GB through the copy engine, whose measured rate for 400-byte rows
+    // (~16 B/clk/SM, profiles/r2a_tune_gather.txt) makes it 1.6x SLOWER than the 128-bit register loads below, which go through L1.
+    if (vec && gather_bulk_supported(D) && tuning_get("gather_csr", "MSMGPU_GATHER_CSR", 0) != 0) {
+        std::vector<GatherJob> gj(n);
+        for (int i = 0; i < n; ++i)
+            gj[i] = GatherJob{Ws[i]->rowptr, store->col.p, store->val.p, reinterpret_cast<const float*>(d_in[i]), reinterpret_cast<float*>(d_out[i])};
+        DevBuf<GatherJob> d_gj;
+        MSM_CUDA(d_gj.alloc(n, s));
+        MSM_CUDA(cudaMemcpyAsync(d_gj.p, gj.data(), n * sizeof(GatherJob), cudaMemcpyHostToDevice, s));   // pageable: staged before return
+        return launch_gather_rows_bulk(d_gj.p, n, n_rows, D, false, ctx->device, s);
+    }
     DevBuf<ApplyJob> d_jobs;
     MSM_CUDA(d_jobs.alloc(n, s));
     MSM_CUDA(cudaMemcpyAsync(d_jobs.p, jobs.data(), n * sizeof(ApplyJob), cudaMemcpyHostToDevice, s));   // pageable: staged before return

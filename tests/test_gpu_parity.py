@@ -689,6 +689,7 @@ def test_full_size_properties(R):
         # (e) per-subject fused call
         one = torch.empty(n_low, D, device=dev)
         capi.check(L.msmgpu_bary_resample_f32_dev(trees[s].h, n_low, d_low.data_ptr(), D, d_feat[s].data_ptr(), one.data_ptr(), None))
+        ctx.sync()      # the library's stream is not torch's current stream
         assert torch.equal(one, d_out[s])
     # (d)
     ids1 = trees[0].get_closest_triangle(low_xyz)
