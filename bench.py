@@ -52,7 +52,12 @@ def parse():
     ap.add_argument("--target-freq", type=int, default=N_TARGET_FREQ)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the full-size check of subject 0 against the reference's outputs")
     ap.add_argument("--e2e-workers", type=int, default=8)
+    ap.add_argument("--no-gmsm", action="store_true", help="skip the secondary groupwise (gMSM, BASELINE configs[4]) leg")
+    ap.add_argument("--gmsm-subjects", type=int, default=int(os.environ.get("BENCH_GMSM_SUBJECTS", 64)))
+    ap.add_argument("--gmsm-data-level", type=int, default=6)
+    ap.add_argument("--gmsm-cp-level", type=int, default=4)
     ap.add_argument("--value-workers", type=int, default=int(os.environ.get("BENCH_VALUE_WORKERS", 1)),
                     help="host threads / CUDA streams the device-resident step is split over (subjects are independent): the "
                          "latency-bound octree builds of one group overlap the bandwidth-bound resampling of another")
@@ -60,11 +65,19 @@ def parse():
 
 
 def workload_config(a, nv, nt, n_low):
+    """Identical in both arms (the driver compares the two dicts). The metric is a RATE (resampled verts/s): the GPU arm resamples
+    a batch of subjects per step, the reference arm one subject per step; the ratio of the two lines compares rates."""
     return {
         "workload": f"batch resampling ico{a.native_level} native sphere ({nv} V, jittered per subject) -> {n_low}-vertex sphere, "
-                    f"{a.channels} FP32 channels, barycentric + adaptive-barycentric, octree builds included",
-        "subjects_per_gpu_per_step": a.subjects, "channels": a.channels, "native_vertices": nv, "native_triangles": nt,
-        "target_vertices": n_low, "methods": ["barycentric", "adaptive_barycentric"],
+                    f"{a.channels} channels, barycentric + adaptive-barycentric, octree builds included",
+        "channels": a.channels, "native_vertices": nv, "native_triangles": nt, "target_vertices": n_low,
+        "methods": ["barycentric", "adaptive_barycentric"],
+        "subjects_per_step": {"gpu_arm_per_gpu": a.subjects, "reference_arm": 1},
+        "payload": {"gpu_arm": "FP32 feature rows, FP64 geometry / weights / accumulation, one rounding to FP32 on output",
+                    "reference_arm": "FP64 (Mesh::pvalues), the reference's own types"},
+        "l2_policy": f"GPU arm: inputs larger than L2 ({a.subjects * nv * a.channels * 4 / 1e9:.2f} GB of feature rows streamed per step), no flush needed; "
+                     "reference arm: host memory",
+        "rate_note": "metric is a rate; value = resampled target vertices (x channels each) per second, both methods counted",
     }
 
 
@@ -212,10 +225,64 @@ def run_reference(a):
     print(json.dumps(line), flush=True)
 
 
+def reference_outputs(xyz, tri, low_xyz, low_tri, feat_cm):
+    """The reference's own outputs for ONE subject (oracle/_ref = the unmodified sources compiled here; the CPU restatement when
+    that library is absent): barycentric resample at full thread count (deterministic), adaptive weights + metric_resample on ONE
+    thread (the reference's adaptive weights race at > 1 thread). Used only as the checker of the parity block."""
+    from oracle import bindings as B
+    threads = os.cpu_count() or 1
+    if B.have_ref():
+        mi, ml = B.RefMesh(xyz, tri, feat=feat_cm), B.RefMesh(low_xyz, low_tri)
+        ref_b, _ = B.ref_bary_resample(mi, ml, nthreads=threads)
+        ref_a, _ = B.ref_metric_resample(mi, ml, nthreads=1)
+        rp, col, val = B.ref_adaptive_weights(mi, ml, nthreads=1)
+        tri_ids = B.RefOctree(mi).query(low_xyz)[0]
+        return "reference (oracle/_ref)", ref_b, ref_a, (rp, col, val), tri_ids
+    B.build(ref=False)
+    ref_b = B.oracle_bary_resample(xyz, tri, low_xyz, feat_cm, nthreads=threads)
+    ref_a = B.oracle_metric_resample(xyz, tri, low_xyz, low_tri, feat_cm, nthreads=threads)
+    rp, col, val = B.oracle_adaptive_weights(xyz, tri, low_xyz, low_tri)
+    tri_ids = B.OracleOctree(xyz, tri).query(low_xyz)[0]
+    return "port (oracle/msm_oracle.cpp)", ref_b, ref_a, (rp, col, val), tri_ids
+
+
+def parity_block(R, capi, L, xyz, tri, low_xyz, low_tri, d_feat0, d_out_b0, d_out_a0):
+    """GPU outputs of the timed subject 0 against the reference's outputs for the same inputs, at the full BASELINE configs[1] size,
+    outside the timed region: nearest-triangle ids, adaptive CSR and FP64 metric_resample bit-exact; FP32-payload outputs within 1e-5."""
+    t0 = time.perf_counter()
+    feat_cm = d_feat0.T.contiguous().double().cpu().numpy()          # [D][nv]: the FP32 payload, exactly representable
+    kind, ref_b, ref_a, (rp, col, val), ref_tri = reference_outputs(xyz, tri, low_xyz, low_tri, feat_cm)
+    gpu_b = d_out_b0.T.contiguous().cpu().numpy().astype(np.float64)
+    gpu_a = d_out_a0.T.contiguous().cpu().numpy().astype(np.float64)
+    rel = lambda got, ref: float(np.abs(got - ref).max() / np.abs(ref).max())
+    m = R.Mesh(xyz, tri, feat_cm)
+    low = R.Mesh(low_xyz, low_tri)
+    tree = R.Octree(m)
+    got_tri = tree.get_closest_triangle(low_xyz)
+    W = R.Resampler().get_adaptive_barycentric_weights(m, low)
+    g_rp, g_col, g_val = W.csr()
+    got64 = R.metric_resample(m, low)
+    out = {"checked": True, "subject": 0, "against": kind, "reference_threads": {"barycentric": os.cpu_count() or 1, "adaptive": 1},
+           "nearest_triangle_ids_bit_exact": bool(np.array_equal(got_tri, ref_tri)),
+           "adaptive_csr_bit_exact": bool(np.array_equal(g_rp, rp) and np.array_equal(g_col, col) and np.array_equal(g_val, val)),
+           "adaptive_f64_output_bit_exact": bool(np.array_equal(got64, ref_a)),
+           "barycentric_f32_max_rel": rel(gpu_b, ref_b), "adaptive_f32_max_rel": rel(gpu_a, ref_a),
+           "barycentric_f32_equals_rounded_reference": bool(np.array_equal(gpu_b, ref_b.astype(np.float32).astype(np.float64))),
+           "adaptive_f32_equals_rounded_reference": bool(np.array_equal(gpu_a, ref_a.astype(np.float32).astype(np.float64))),
+           "tolerance_f32": 1e-5, "nnz": int(len(col)), "seconds": None}
+    out["ok"] = bool(out["nearest_triangle_ids_bit_exact"] and out["adaptive_csr_bit_exact"] and out["adaptive_f64_output_bit_exact"]
+                     and out["barycentric_f32_max_rel"] <= 1e-5 and out["adaptive_f32_max_rel"] <= 1e-5)
+    out["seconds"] = round(time.perf_counter() - t0, 1)
+    return out
+
+
 # --------------------------------------------------------------------------------------------
 # our arm (GPU)
 # --------------------------------------------------------------------------------------------
 def run_ours(a):
+    if "WORLD_SIZE" in os.environ and "BENCH_KEEP_OMP" not in os.environ:
+        # torchrun pins OMP_NUM_THREADS to 1; the library's host-side finishes (libm pow / acos of the cost paths) are OpenMP loops
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // int(os.environ["WORLD_SIZE"])))
     import torch
     import torch.distributed as dist
     from newmsm_b200 import build, capi, resampler as R
@@ -375,32 +442,39 @@ def run_ours(a):
     for _ in range(2):
         device_step(stage_ms)
     breakdown = {k: float(np.mean(v)) for k, v in stage_ms.items()}
+    tune = lambda name, v: capi.check(L.msmgpu_set_tuning(name.encode(), int(v)))
+
+    def timed_launches(fn, reps=7, warm=3):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+        for i in range(reps + warm):      # warm launches first; inputs (4.2 GB of feature rows) exceed the 126 MB L2
+            if i >= warm: evs[i - warm].record(stream)
+            fn()
+        evs[reps].record(stream)
+        stream.synchronize()
+        return float(np.median([evs[i].elapsed_time(evs[i + 1]) for i in range(reps)]))
+
     with torch.cuda.stream(stream):
         low = R.Mesh.from_device(ctx, n_low, d_low_xyz, len(low_tri), d_low_tri)
         meshes = [R.Mesh.from_device(ctx, nv, d_xyz[s], nt, d_tri) for s in range(S)]
         trees = R.Octree.build_batch(meshes + [low])
         tree_ptrs = (capi.C.c_void_p * S)(*[t.h.value for t in trees[:S]])
-        reps = 5
-        evs = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
-        for i in range(reps + 3):      # 3 warm launches; inputs (4.2 GB of features) exceed the 126 MB L2
-            if i >= 3: evs[i - 3].record(stream)
-            capi.check(L.msmgpu_bary_resample_batch_f32_dev(ctx.h, S, tree_ptrs, n_low, capi.ptr(d_low_xyz), D, feat_ptrs, outb_ptrs, None))
-        evs[reps].record(stream)
-        stream.synchronize()
-        k_ms = float(np.mean([evs[i].elapsed_time(evs[i + 1]) for i in range(reps)]))
+        fwd = capi.C.c_void_p()
+        capi.check(L.msmgpu_fwd_create(ctx.h, S, n_low, capi.C.byref(fwd)))
+        bary_call = lambda: capi.check(L.msmgpu_bary_resample_batch_f32_dev_keep(ctx.h, S, tree_ptrs, n_low, capi.ptr(d_low_xyz), D, feat_ptrs, outb_ptrs, None, fwd))
+        bary_ms = timed_launches(bary_call)                                   # the path of the step: queries kernel + bulk-copy gather
+        gather_ms = timed_launches(lambda: capi.check(L.msmgpu_fwd_apply_batch_f32_dev(ctx.h, fwd, D, feat_ptrs, outb_ptrs)))   # the gather kernel alone
+        mode0 = int(os.environ.get("MSMGPU_GATHER", "1"))
+        tune("gather", 0)
+        fused_ms = timed_launches(bary_call)                                  # the fused register-path kernel (A/B reference)
+        tune("gather", mode0)
         # adaptive apply alone (one launch for the batch)
         mesh_ptrs = (capi.C.c_void_p * S)(*[m.h.value for m in meshes])
         w_ptrs = (capi.C.c_void_p * S)()
-        capi.check(L.msmgpu_adaptive_weights_batch(ctx.h, S, mesh_ptrs, tree_ptrs, low.h, trees[-1].h, w_ptrs))
+        capi.check(L.msmgpu_adaptive_weights_batch_fwd(ctx.h, S, mesh_ptrs, tree_ptrs, low.h, trees[-1].h, fwd, w_ptrs))
         Ws = [R.Weights(L, capi.C.c_void_p(w_ptrs[s])) for s in range(S)]
         nnz = sum(w.shape()[2] for w in Ws)
-        ea = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
-        for i in range(reps + 2):
-            if i >= 2: ea[i - 2].record(stream)
-            capi.check(L.msmgpu_weights_apply_batch_f32_dev(ctx.h, S, w_ptrs, D, feat_ptrs, outa_ptrs))
-        ea[reps].record(stream)
-        stream.synchronize()
-        apply_ms = float(np.mean([ea[i].elapsed_time(ea[i + 1]) for i in range(reps)]))
+        apply_ms = timed_launches(lambda: capi.check(L.msmgpu_weights_apply_batch_f32_dev(ctx.h, S, w_ptrs, D, feat_ptrs, outa_ptrs)), warm=2)
+        L.msmgpu_fwd_destroy(fwd)
         for W in Ws: W.close()
         for t_ in trees: t_.close()
         for m in meshes: m.close()
@@ -412,29 +486,42 @@ def run_ours(a):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    # B_bary = 24 N_t + 24 V_s + 12 T_s + 4 D min(3 N_t, V_s) + 4 D N_t  per subject
+    # B_bary = 24 N_t + 24 V_s + 12 T_s + 4 D min(3 N_t, V_s) + 4 D N_t  per subject; the gather kernel's share of it is the
+    # compulsory feature rows + the output rows, plus the 40-byte weight map it reads per target (ids, weights, count)
     bytes_bary = 24 * n_low + 24 * nv + 12 * nt + 4 * D * min(3 * n_low, nv) + 4 * D * n_low
-    achieved = S * bytes_bary / (k_ms * 1e-3) / 1e9
+    bytes_gather = 4 * D * min(3 * n_low, nv) + 4 * D * n_low + 36 * n_low
     bytes_apply = S * (4 * D * nv + 4 * D * n_low + 4 * (n_low + 1)) + 12 * nnz
-    # DRAM traffic of that kernel per launch from the committed `ncu --set full` capture (bytes per subject x subjects in this launch)
+    bytes_adaptive = 4 * D * nv + 4 * D * n_low + 8 * (nv + n_low) + 24 * nv + 12 * nt      # SURVEY §8d "adaptive": every source row + areas + mesh
+    gbs = lambda b, ms: b / (ms * 1e-3) / 1e9
+    # DRAM traffic of the gather kernel per launch from the committed `ncu --set full` capture (bytes per subject x subjects in this launch)
     traffic, traffic_src = None, None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1u_fused_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r2_gather_traffic.json")))
         traffic = float(tr["dram_bytes_per_subject"]) * S
-        traffic_src = "profiles/r1u_fused_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of an 8-subject launch, scaled to %d subjects)" % S
+        traffic_src = "profiles/r2_gather_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of a 16-subject launch, scaled to %d subjects)" % S
     except Exception:
         pass
-    roofline = {"kernel": "k_bary_resample_f32 (fused query + weights + 3-row gather, one launch for the batch)", "bound": "hbm",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-                "peak_source": peak_src,
-                "launch_ms": k_ms, "algorithmic_bytes_per_launch": S * bytes_bary,
+    roofline = {"kernel": "k_gather_rows_bulk<BARY> (cp.async.bulk + mbarrier row gather of the barycentric resample: one launch for the batch)",
+                "bound": "hbm", "achieved": gbs(S * bytes_gather, gather_ms), "peak": peak, "unit": "GB/s", "frac": gbs(S * bytes_gather, gather_ms) / peak,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "launch_ms": gather_ms,
+                "algorithmic_bytes_per_launch": S * bytes_gather,
+                "algorithmic_bytes_note": "per subject: 4 D min(3 N_t, V_s) feature rows + 4 D N_t output + 36 N_t weight maps (SURVEY §8d feature / output terms)",
+                "barycentric_total": {"kernels": "k_bary_weights_batch (queries + weight maps) + k_gather_rows_bulk", "launch_ms": bary_ms,
+                                      "algorithmic_bytes_per_launch": S * bytes_bary, "achieved": gbs(S * bytes_bary, bary_ms),
+                                      "frac": gbs(S * bytes_bary, bary_ms) / peak},
+                "barycentric_fused_register_path": {"kernel": "k_bary_resample_f32 (round-1 kernel, MSMGPU_GATHER=0)", "launch_ms": fused_ms,
+                                                    "achieved": gbs(S * bytes_bary, fused_ms), "frac": gbs(S * bytes_bary, fused_ms) / peak},
                 "adaptive_apply": {"kernel": "k_csr_apply_f32x4", "launch_ms": apply_ms, "algorithmic_bytes_per_launch": bytes_apply,
-                                   "achieved": bytes_apply / (apply_ms * 1e-3) / 1e9, "frac": bytes_apply / (apply_ms * 1e-3) / 1e9 / peak}}
+                                   "achieved": gbs(bytes_apply, apply_ms), "frac": gbs(bytes_apply, apply_ms) / peak,
+                                   "bound_note": "XU pipe (FP32->FP64 conversions) 47 % busy, issue 51 %: profiles/r2_gather_summary.md"},
+                "whole_step": {"algorithmic_bytes_per_step": S * (bytes_bary + bytes_adaptive), "ms_per_step": ms_step,
+                               "achieved": gbs(S * (bytes_bary + bytes_adaptive), ms_step), "frac": gbs(S * (bytes_bary + bytes_adaptive), ms_step) / peak,
+                               "note": "both methods' SURVEY §8d bytes over the whole step (octree builds, queries, weight construction, both gathers)"}}
 
     # ---- end to end through the host-buffer C ABI ------------------------------------------------
     e2e = None
     if not a.no_e2e:
-        e2e = run_e2e(a, torch, R, capi, L, local, S, D, host_xyz, tri, low_xyz, low_tri, d_feat, n_low, nv, nt, world, dist)
+        e2e = run_e2e(a, torch, R, capi, L, local, S, D, host_xyz, tri, low_xyz, low_tri, d_feat, n_low, nv, nt, world, dist, d_out_b, d_out_a)
 
     cpu_base = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -444,14 +531,30 @@ def run_ours(a):
         except Exception as ex:   # the checker is optional for the measurement itself
             cpu_base = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"unavailable: {ex}"}
 
+    gmsm = None
+    if not a.no_gmsm:
+        try:
+            gmsm = run_gmsm(a, torch, dist, rank, world, local)
+        except Exception as ex:
+            gmsm = {"error": f"{type(ex).__name__}: {ex}"}
+    parity = None
+    if rank == 0 and not a.no_parity:
+        try:
+            parity = parity_block(R, capi, L, host_xyz[0], tri, low_xyz, low_tri, d_feat[0], d_out_b[0], d_out_a[0])
+        except Exception as ex:     # the checker is test infrastructure: its absence must not hide the measurement
+            parity = {"checked": False, "error": f"{type(ex).__name__}: {ex}"}
+
     if rank == 0:
         cfg = workload_config(a, nv, nt, n_low)
-        cfg.update({"l2_policy": f"inputs larger than L2: {S * nv * D * 4 / 1e9:.2f} GB of features streamed per step, no flush needed",
-                    "query_group_lanes": int(L.msmgpu_get_query_group()), "breakdown_ms_per_step": breakdown,
-                    "value_streams": NW, "breakdown_note": f"stage times of one of the {NW} concurrent subject groups ({len(groups[0])} subjects)"})
+        detail = {"query_group_lanes": int(L.msmgpu_get_query_group()), "breakdown_ms_per_step": breakdown, "value_streams": NW,
+                  "breakdown_note": f"stage times of one of the {NW} concurrent subject groups ({len(groups[0])} subjects)"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic", "config": cfg, "clocks": clk, "gpu_launches": launches, "roofline": roofline}
+                "data": "synthetic", "config": cfg, "clocks": clk, "gpu_launches": launches, "roofline": roofline, "detail": detail}
+        if parity is not None:
+            line["parity"] = parity
+        if gmsm is not None:
+            line["gmsm"] = gmsm
         if e2e is not None:
             line["e2e"] = e2e
         if cpu_base is not None:
@@ -462,7 +565,129 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
-def run_e2e(a, torch, R, capi, L, local, S, D, host_xyz, tri, low_xyz, low_tri, d_feat, n_low, nv, nt, world, dist):
+def run_gmsm(a, torch, dist, rank, world, local):
+    """Secondary leg: ONE discrete iteration of groupwise registration at BASELINE configs[4] scale (S synthetic ico6 subjects, ico6
+    template, ico4 control grids, 19 labels; docs/guide.md:390-407) on the ranks of this run:
+      get_patch_data   subjects block-sharded, every rank resamples its subjects for all labels (msmgpu_group_fields)
+      ONE ncclAllGather of the fields [S][L][N_t][D] f64 (torch.distributed all_gather_into_tensor on the device buffers)
+      pair costs       pair blocks sharded, 18 label phases of Fusion's 4 combinations, blocks gathered on the device for the host solver
+      triplet costs    triplet blocks sharded, 18 label phases of 8 combinations (strain; pow() finish on the host libm)
+    Times are max over ranks. Rank 0 re-computes a sample unsharded and compares bit for bit."""
+    from newmsm_b200 import group_cost as GC, resampler as R, synth
+    S, D = a.gmsm_subjects, 1
+    dev = torch.device("cuda", local)
+    ctx = R.Context(local)
+    cp0, cp_tri = synth.icosphere(a.gmsm_cp_level)
+    d0, dtri = synth.icosphere(a.gmsm_data_level)
+    tpl, tpl_tri = d0.copy(), dtri
+    data = np.stack([synth.smooth_warp(d0, max_disp=2.0, seed=40 + s_) for s_ in range(S)])
+    cps = np.stack([synth.smooth_warp(cp0, max_disp=1.0, seed=60 + s_) for s_ in range(S)])
+    feat = np.stack([synth.smooth_fields(data[s_], D, seed0=100, noise=0.1, noise_seed=7 + s_) for s_ in range(S)])
+    centre = np.array([0.0, 0.0, 100.0])
+    spacing = 2 * 100 * np.arcsin(np.linalg.norm(cp0[cp_tri[:, 0]] - cp0[cp_tri[:, 1]], axis=1).max() / 200)
+    labels = [centre]
+    for ring, n in ((0.25, 6), (0.5, 12)):      # 19 labels like the barycentre + vertex sets of the sampling grid (DiscreteModel.cpp:124-190)
+        for k in range(n):
+            q = centre + ring * spacing * np.array([np.cos(2 * np.pi * k / n), np.sin(2 * np.pi * k / n), 0.0])
+            labels.append(q / np.linalg.norm(q) * 100)
+    labels = np.array(labels)
+    Lb = len(labels)
+    ncp = len(cp0)
+
+    def sync():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+
+    def tmax(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    M = GC.DiscreteGroupModel(R.Mesh(tpl, tpl_tri, ctx=ctx), simmeasure=2, dist=dist if world > 1 else None)
+    spac = M.get_spacings(cps, cp_tri)
+    rot = M.get_rotations(centre, cps)
+    pairs = M.estimate_pairs(cps, cp_tri)
+    trip = np.concatenate([np.sort(cp_tri + s_ * ncp, axis=1) for s_ in range(S)]).astype(np.int32)
+    orig = np.stack([cp0] * S)
+    labeling = np.zeros(S * ncp, np.int32)
+    launches0 = capi_launches()
+    out = {}
+    for it in range(2):                          # one warm iteration, one timed
+        sync(); t0 = time.perf_counter()
+        M.get_patch_data(data, dtri, feat, labels, centre, rot, spac, 1.0)          # fields + all-gather + group state
+        sync(); t1 = time.perf_counter()
+        sample = []
+        for l in range(1, Lb):
+            c = M.computePairwiseCostsForLabel(pairs, labeling, l, copy=False)
+            sample.append(c[::997].ravel().copy())
+        sync(); t2 = time.perf_counter()
+        tsum = 0.0
+        for l in range(1, Lb):
+            tsum += float(M.computeTripletCostsForLabel(cps, orig, rot, labels, trip, labeling, l, 0.2).sum())
+        sync(); t3 = time.perf_counter()
+        out = {"fields_s": tmax(t1 - t0), "pair_sweep_s": tmax(t2 - t1), "triplet_sweep_s": tmax(t3 - t2), "iteration_s": tmax(t3 - t0)}
+    # the collective alone: all-gather of the field shards, CUDA events on this rank's stream, max over ranks
+    ag_bytes = int(M.fields.numel() * 8)
+    ag_ms = None
+    if world > 1:
+        b, e = GC.shard_range(S, rank, world)
+        local_blk = M.fields[b:e].contiguous()
+        full = torch.empty_like(M.fields)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        uneven = len(set(GC.shard_counts(S, world))) > 1
+        for i in range(4):
+            sync()
+            e0.record()
+            if uneven: M.coll.all_gather_blocks(local_blk, S)
+            else: dist.all_gather_into_tensor(full, local_blk)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ag_ms = tmax(e0.elapsed_time(e1))
+    # bitwise check on rank 0: the sharded results against an unsharded computation of the same batch on this rank alone
+    same = None
+    if world > 1:
+        lab_chk = 7
+        got_pairs = M.computePairwiseCostsForLabel(pairs, labeling, lab_chk).copy()
+        got_trip = M.computeTripletCostsForLabel(cps, orig, rot, labels, trip, labeling, lab_chk, 0.2)
+        # every rank holds the gathered fields; only rank 0 re-computes
+        if rank == 0:
+            M1 = GC.DiscreteGroupModel(R.Mesh(tpl, tpl_tri, ctx=ctx), simmeasure=2, dist=None)
+            other = [s_ for s_ in (S - 1, S // 2) if not (GC.shard_range(S, 0, world)[0] <= s_ < GC.shard_range(S, 0, world)[1])][:1] or [S - 1]
+            M1.get_patch_data(data[other], dtri, feat[other], labels, centre, rot[other[0] * ncp:(other[0] + 1) * ncp], spac[other], 1.0)
+            same_fields = bool(torch.equal(M1.fields[0], M.fields[other[0]]))
+            M1.close()
+            M.coll = GC.Collective(None)         # this rank alone, on the gathered fields
+            M._pairs_key = None
+            ref_pairs = M.computePairwiseCostsForLabel(pairs, labeling, lab_chk)
+            ref_trip = M.computeTripletCostsForLabel(cps, orig, rot, labels, trip, labeling, lab_chk, 0.2)
+            eq = lambda x, y: bool(np.array_equal(np.nan_to_num(x, nan=-1.0), np.nan_to_num(y, nan=-1.0)))
+            same = {"fields_of_a_remote_subject": same_fields, "pair_batch": eq(got_pairs, ref_pairs), "triplet_batch": eq(got_trip, ref_trip)}
+        dist.barrier()
+    P, T = len(pairs), len(trip)
+    res = {"workload": f"gMSM, one discrete iteration: {S} subjects ico{a.gmsm_data_level} ({len(d0)} V), template ico{a.gmsm_data_level}, control grids ico{a.gmsm_cp_level} "
+                       f"({ncp} nodes per subject), {Lb} labels, D = {D}, simmeasure 2",
+           "n_gpus": world, "subjects": S, "labels": Lb, "pairs": P, "triplets": T, "resamples_per_iteration": S * Lb,
+           **out,
+           "pair_costs_per_s": P * 4 * (Lb - 1) / out["pair_sweep_s"], "triplet_costs_per_s": T * 8 * (Lb - 1) / out["triplet_sweep_s"],
+           "allgather": {"collective": "ncclAllGather (torch.distributed.all_gather_into_tensor on the device field shards)" if world > 1 else "none (1 rank)",
+                         "bytes_total": ag_bytes, "ms": ag_ms,
+                         "bus_GBs": (ag_bytes * (world - 1) / world / (ag_ms * 1e-3) / 1e9) if ag_ms else None},
+           "sharded_equals_unsharded_bitwise": same,
+           "limiter_note": "fields: host libm rotation matrices + per-rank build; pairs: device-bound (k_group_pair_costs); triplets: the three pow() per cost "
+                           "are finished on the host libm (bit-exactness, DESIGN §4.8) with cpu_count / ranks OpenMP threads per rank",
+           "gpu_launches": int(capi_launches() - launches0), "timing": "wall clock between device synchronisations + barriers, max over ranks; second of two iterations"}
+    M.close()      # the context is released with the last object that holds it (meshes / trees keep a reference)
+    return res
+
+
+def capi_launches():
+    from newmsm_b200 import capi
+    return int(capi.lib().msmgpu_launch_count())
+
+
+def run_e2e(a, torch, R, capi, L, local, S, D, host_xyz, tri, low_xyz, low_tri, d_feat, n_low, nv, nt, world, dist, d_out_b, d_out_a):
     """Per subject, through the calls a reference-side adapter makes: Mesh upload (msmgpu_mesh_create), Octree
     (msmgpu_octree_build), barycentric resample and metric_resample on HOST channel-major FP32 buffers."""
     C = capi.C
@@ -523,12 +748,15 @@ def run_e2e(a, torch, R, capi, L, local, S, D, host_xyz, tri, low_xyz, low_tri, 
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dt = float(tt.item())
-    # sanity: the host-path outputs equal the device-path outputs of the same subject
+    # the host-path outputs equal the device-path outputs of the same subjects bit for bit (same kernels, same inputs)
+    same = True
+    for s_ in sorted({0, S - 1}):
+        same = same and bool(torch.equal(h_out_b[s_], d_out_b[s_].T.cpu())) and bool(torch.equal(h_out_a[s_], d_out_a[s_].T.cpu()))
     h2d = S * (D * nv * 4 + nv * 24 + nt * 12 + n_low * 24) + workers * (n_low * 24 + len(low_tri) * 12)
     d2h = S * 2 * D * n_low * 4
     for c in ctxs: c.close()
     return {"value": 2 * S * n_low * world * a.steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "ms_per_step": 1e3 * dt / a.steps, "workers": workers,
+            "ms_per_step": 1e3 * dt / a.steps, "workers": workers, "outputs_equal_device_path": same,
             "api": "per subject: msmgpu_mesh_create + msmgpu_mesh_set_features_f32 + msmgpu_octree_build + msmgpu_mesh_bary_resample_f32 + msmgpu_mesh_metric_resample_f32, pinned host buffers"}
 
 

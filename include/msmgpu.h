@@ -264,6 +264,24 @@ msmgpu_status msmgpu_costfn_triplet_costs(msmgpu_costfn* c, int ntrip, const int
 msmgpu_status msmgpu_costfn_triplet_batch(msmgpu_costfn* c, int ntrip, const int32_t* triplets, int L, const double* labels, const double* rotations,
                                           const double* orig_cp_xyz, const msmgpu_reg_params* prm, const int32_t* labeling, int label, double* out);
 
+/* ---- AFFINE / RIGID level (msm-newmeshreg/src/rigid_costfunction.cpp) ---- */
+typedef struct msmgpu_rigid msmgpu_rigid;
+/* replaces: Mesh::calculate_MeanVD (msm-newresampler/src/mesh.cpp:276-294) for a mesh built by push_triangle in triangle order. Host code. */
+msmgpu_status msmgpu_mean_vertex_distance(int nv, const double* xyz, int nt, const int32_t* tri, double* out);
+/* replaces: Rigid_cost_function::initialise (rigid_costfunction.cpp:32-50): TARGET octree, similarity means (similarities.cpp:106-126),
+ * Neighbourhood::update (reg_tools.cpp:31-58; only "does vertex i have a neighbour" outlives the first evaluation). Features are
+ * channel-major doubles: src_feat [D][nv_s] = FEAT input data, ref_feat [D][nv_t] = FEAT reference data; simmeasure 1 = SSD, 2 = correlation.
+ * mean_vertex_distance = SOURCE.calculate_MeanVD() (cpp:35: MVD = min_sigma). */
+msmgpu_status msmgpu_rigid_create(msmgpu_ctx* ctx, int nv_t, const double* tgt_xyz, int nt_t, const int32_t* tgt_tri, int nv_s, const double* src_xyz,
+                                  int nt_s, const int32_t* src_tri, int D, const double* src_feat, const double* ref_feat, int simmeasure,
+                                  double mean_vertex_distance, msmgpu_rigid** out);
+void msmgpu_rigid_destroy(msmgpu_rigid* r);
+/* replaces: Rigid_cost_function::rigid_cost_mesh (rigid_costfunction.cpp:130-141) = rotate_in_mesh + Evaluate_SIMGradient for every source
+ * vertex (calculate_tangs reg_tools.cpp:205-266, closest TARGET triangle, get_all_neighbours, calculate_sim_column_nbh, WLS_simgradient) + the
+ * sum of current_sim. src_xyz [nv_s][3] = the CURRENT source coordinates (NULL: those of the previous call); the source is not modified
+ * (the reference restores it, cpp:139). exp() of the weights and the sequential sums run on the host libm inside this call. */
+msmgpu_status msmgpu_rigid_cost(msmgpu_rigid* r, const double* src_xyz, double dw1, double dw2, double dw3, double* cost);
+
 /* ---- groupwise registration (gMSM): msm-newmeshreg/src/DiscreteGroupModel.cpp, DiscreteGroupCostFunction.cpp ---- */
 typedef struct msmgpu_group msmgpu_group;
 

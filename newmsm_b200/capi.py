@@ -40,6 +40,10 @@ _SIGNATURES = {
     "msmgpu_set_query_group": (_i, [_i]),
     "msmgpu_get_query_group": (_i, []),
     "msmgpu_set_tuning": (_i, [C.c_char_p, _i]),
+    "msmgpu_mean_vertex_distance": (_i, [_i, _vp, _i, _vp, _vp]),
+    "msmgpu_rigid_create": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _d, _pp]),
+    "msmgpu_rigid_destroy": (None, [_vp]),
+    "msmgpu_rigid_cost": (_i, [_vp, _vp, _d, _d, _d, _vp]),
     "msmgpu_fwd_apply_batch_f32_dev": (_i, [_vp, _vp, _i, _vp, _vp]),
     "msmgpu_ctx_create": (_i, [_i, _vp, _pp]),
     "msmgpu_ctx_destroy": (None, [_vp]),

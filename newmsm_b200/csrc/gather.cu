@@ -6,7 +6,7 @@
 // FP64 accumulation in ascending-column order (the std::map iteration order of the reference), one rounding to FP32 on output.
 //
 // sm_100a data path. A source row is D*4 contiguous bytes at a data-dependent address. Every warp owns a private ring of NST stages in
-// shared memory; a stage holds G rows (128-byte aligned slots). The warp issues one `cp.async.bulk.shared::cluster.global` per row
+// shared memory; a stage holds G rows. The warp issues one `cp.async.bulk.shared::cluster.global` per row
 // (UBLKCP in SASS; the instruction takes uniform operands, so the compiler serialises the lanes of a group with ELECT / R2UR) — the
 // copy engine moves the whole row, no register or L1 line is held while the bytes are in flight — and the copies of a stage complete
 // on the stage's mbarrier (`mbarrier.arrive.expect_tx` by lane 0 with the byte count of the stage = SYNCS.ARRIVE.TRANS64, complete_tx
@@ -35,9 +35,10 @@ namespace msm {
 // CH = ceil(D4 / 32): 16-byte chunks of a row per lane. BARY: rows have three entry slots at [3r, 3r+3), absent entries col < 0
 // (G must then be a multiple of 3); otherwise CSR with absolute offsets rowptr[r] .. rowptr[r+1] into col / val.
 template <int G, int NST, int CH, bool BARY, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, (CH == 1 && G <= 8) ? (WARPS == 8 ? 2 : 4) : 1) k_gather_rows_bulk(const GatherJob* __restrict__ jobs, int n_jobs, int n_rows, int D4, int R) {
+__global__ void __launch_bounds__(WARPS * 32, (CH == 1 && G <= 8) ? (WARPS == 8 ? 2 : 4) : 1) k_gather_rows_bulk(const GatherJob* __restrict__ jobs, int n_jobs, int n_rows, int D4, int R_csr) {
     // R = rows per warp tile (CSR: <= 32, one row start per lane). The tiles in flight at any moment are consecutive: #warps * R rows.
     // For CSR rows that window decides the L2 reuse of source rows shared by neighbouring targets (profiles/r2f)
+    const int R = BARY ? 96 : R_csr;     // barycentric maps: 288 entries per tile, a compile-time constant (the unrolled consumer depends on it)
     extern __shared__ __align__(128) unsigned char g_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     GatherRing<G, NST> ring;

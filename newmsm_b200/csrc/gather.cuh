@@ -35,9 +35,9 @@ __device__ __forceinline__ void bulk_row_g2s(uint32_t dst, const void* src, uint
 template <int G, int NST>
 struct GatherSmem {
     static __host__ __device__ constexpr size_t header_bytes() { return ((size_t)NST * 8 + (size_t)NST * G * (8 + 4) + 127) / 128 * 128; }
-    // row slots are 128-byte aligned (pitch rounded up): a bulk copy into a slot that is only 16-byte aligned runs at ~16 B/clk per SM
-    // instead of one row per ~8 clk (profiles/r2c_bulk_copy_probe.txt, profiles/r2g)
-    static __host__ __device__ int slot_f4(int D4) { return (D4 + 7) / 8 * 8; }
+    // slot pitch in 16-byte units = the row length: padding the slots to 128-byte alignment was measured and is SLOWER (0.78 vs 0.62 ms for
+    // the barycentric maps, profiles/r2h_tune_gather.txt: the larger ring costs more than the alignment gains)
+    static __host__ __device__ int slot_f4(int D4) { return D4; }
     static __host__ __device__ size_t warp_bytes(int D4) { return header_bytes() + (size_t)NST * G * slot_f4(D4) * 16; }
 };
 

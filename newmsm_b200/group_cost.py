@@ -104,13 +104,14 @@ class DiscreteGroupModel:
         cp = f64(cp_xyz)
         S, n = cp.shape[0], cp.shape[1]
         trees = [Octree(Mesh(cp[s], cp_tri, ctx=self.ctx)) for s in range(S)]
-        closest = {(a, b): trees[b].get_closest_vertex_ID(cp[a]) for a in range(S) for b in range(a + 1, S)}
-        pairs = []
-        for a in range(S):
-            for v in range(n):
-                for b in range(a + 1, S):
-                    pairs.append((a * n + v, b * n + int(closest[(a, b)][v])))
-        return np.asarray(pairs, dtype=np.int32).reshape(-1, 2)
+        blocks = []
+        for a in range(S - 1):        # order of the reference's loops: subject a, vertex v, partner subject b > a
+            partners = np.stack([trees[b].get_closest_vertex_ID(cp[a]) + b * n for b in range(a + 1, S)], axis=1)     # [n][S-a-1]
+            first = np.repeat(a * n + np.arange(n), S - a - 1)
+            blocks.append(np.stack([first, partners.reshape(-1)], axis=1))
+        if not blocks:
+            return np.zeros((0, 2), np.int32)
+        return np.ascontiguousarray(np.concatenate(blocks).astype(np.int32))
 
     # DiscreteGroupModel::get_patch_data (cpp:88-121) + DiscreteGroupCostFunction::set_patch_data
     def get_patch_data(self, data_xyz, data_tri, feat, labels, centre, rotations, spacings, range_):

@@ -189,8 +189,9 @@ class Octree:
 class Weights:
     """Device CSR resampling matrix; `rows()` gives the reference's vector<map<int,double>> view."""
 
-    def __init__(self, L, handle):
+    def __init__(self, L, handle, owner=None):
         self.L, self.h = L, handle
+        self._owner = owner     # the Context (or a mesh of it): destroying the matrix needs the context's stream alive
 
     def shape(self):
         a, b, c = C.c_int(), C.c_int(), C.c_int64()
@@ -238,7 +239,7 @@ class Resampler:
             raise NotImplementedError("exclusion masks are outside the accelerated path (SURVEY §8)")
         h = C.c_void_p()
         check(in_mesh.L.msmgpu_adaptive_weights(in_mesh.h, sphLow.h, C.byref(h)))
-        return Weights(in_mesh.L, h)
+        return Weights(in_mesh.L, h, owner=in_mesh.ctx)
 
     def get_adaptive_barycentric_weights_batch(self, in_meshes, sphLow: Mesh, in_trees=None, low_tree: Octree | None = None):
         """The same for a batch of subjects resampled onto one target: one set of launches (msmgpu_adaptive_weights_batch)."""
@@ -248,7 +249,7 @@ class Resampler:
         th = (C.c_void_p * n)(*[(t.h.value if t is not None else None) for t in in_trees]) if in_trees else None
         out = (C.c_void_p * n)()
         check(ctx.L.msmgpu_adaptive_weights_batch(ctx.h, n, mh, th, sphLow.h, low_tree.h if low_tree else None, out))
-        return [Weights(ctx.L, C.c_void_p(out[i])) for i in range(n)]
+        return [Weights(ctx.L, C.c_void_p(out[i]), owner=ctx) for i in range(n)]
 
     def barycentric_data_interpolation(self, metric_in: Mesh, sphLow: Mesh, nthreads: int = 1, EXCL=None):
         """resampler.cpp:30-70: adaptive-barycentric resampling of metric_in.pvalues -> [D, n_low]."""
