@@ -186,15 +186,29 @@ __device__ __forceinline__ void gather_tile(GatherRing<G, NST>& ring, Src& src, 
         const uint32_t st = ring.n_done % NST;
         mbar_wait(smem_u32(ring.bars + st), (ring.n_done / NST) & 1u);
         const float4* __restrict__ sl = ring.slots + (size_t)st * G * SP;
+        // all shared-memory reads of the group are issued before the first conversion (the per-entry form, LDS -> F2F -> DMUL -> DADD
+        // in a chain, was 27 % slower at 16 resident warps: profiles/r2_gather_summary.md)
+        float4 vv[G][CH];
+        double ww[G];
+        int cc[G];
 #pragma unroll
         for (int j = 0; j < G; ++j) {
-            const int cj = ring.s_c[st * G + j];
-            const double wj = ring.s_w[st * G + j];
+            cc[j] = ring.s_c[st * G + j];
+            ww[j] = ring.s_w[st * G + j];
+#pragma unroll
+            for (int h = 0; h < CH; ++h) {
+                const int c = lane + 32 * h;
+                vv[j][h] = c < D4 ? sl[j * SP + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            const int cj = cc[j];
+            const double wj = ww[j];
             if (cj >= 0) {      // a present entry multiplies even when its weight is 0 (NaN * 0 = NaN, resampler.cpp:46-48)
 #pragma unroll
                 for (int h = 0; h < CH; ++h) {
-                    const int c = lane + 32 * h;
-                    const float4 v = c < D4 ? sl[(size_t)j * SP + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 v = vv[j][h];
                     acc[h][0] += (double)v.x * wj; acc[h][1] += (double)v.y * wj;
                     acc[h][2] += (double)v.z * wj; acc[h][3] += (double)v.w * wj;
                 }

@@ -18,7 +18,7 @@ BINS = [os.path.join(ROOT, "integration", "_build", "newmsm_gpu"), os.path.join(
 
 @pytest.mark.parametrize("config,D,extra", [
     ("MSMpair", 1, ["--levels-drop", "1", "--it-scale", "0.4"]),            # FastPD, univariate unary table, pairwise regulariser, smoothing
-    ("MSMpairAffine", 1, ["--levels-drop", "1", "--it-scale", "0.2"]),     # the shipped basic config: AFFINE level (reference host code) + DISCRETE levels (GPU)
+    ("MSMpairAffine", 1, ["--levels-drop", "1", "--it-scale", "0.2"]),     # the shipped basic config: AFFINE level (csrc/rigid.cu through integration/newmsm_gpu_rigid_hooks.cpp) + DISCRETE levels
     ("MSMAllStrain", 3, ["--levels-drop", "1", "--it-scale", "0.1"]),       # HOCR, HO multivariate triplet likelihood, strain regulariser
     ("MSMstrain", 1, ["--levels-drop", "2", "--it-scale", "0.1"]),         # HOCR, per-call unary costs from the device table + strain-only triplets
     ("gMSM", 1, ["--levels-drop", "2", "--it-scale", "0.25", "--group", "3"]),   # groupwise driver: estimate_pairs, get_patch_data and the pair / triplet costs on the device (integration/newmsm_gpu_group_hooks.cpp)
@@ -35,6 +35,24 @@ def test_newmsm_labels_bit_exact(config, D, extra):
     assert res["labels_bit_exact"], res["label_mismatch_per_iteration"]
     assert res["all_meshes_bit_exact"], (res["hashes_equal"], res["trace_calls"])
     assert res["final_sphere_max_abs_diff"] == 0.0
+
+
+def test_affine_level_costs_match_reference_in_process():
+    """MSMGPU_VERIFY=1 on the shipped basic config: every Rigid_cost_function::rigid_cost_mesh call of the AFFINE level is evaluated by the
+    device path AND by the reference's own member in the same process (rigid_costfunction.cpp:130-141) and compared bit for bit."""
+    import re
+    if not all(os.path.exists(b) for b in BINS):
+        pytest.skip("integration/_build/newmsm_gpu not built (needs /root/reference at build time)")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "newmsm_e2e.py"), "--level", "4", "--config", "MSMpairAffine", "--D", "1", "--threads", "4",
+                          "--skip-cpu", "--verify", "--levels-drop", "2", "--it-scale", "0.2"], capture_output=True, text=True, timeout=1500)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    line = [ln for ln in res["gpu_split"] if "rigid_cost_mesh:" in ln]
+    assert line, res["gpu_split"]
+    m = re.search(r"rigid_cost_mesh: (\d+) of (\d+) costs differ", line[0])
+    assert m, line[0]
+    bad, n = map(int, m.groups())
+    assert n >= 8 and bad == 0, line[0]
 
 
 def test_gmsm_costs_match_reference_in_process():
