@@ -201,6 +201,24 @@ msmgpu_status msmgpu_nn_resample(msmgpu_mesh* in_mesh, int n, const double* low_
 msmgpu_status msmgpu_smooth_neighbourhoods(msmgpu_ctx* ctx, int n, const double* low_xyz, const int32_t* closest, double cos_ang,
                                            int32_t* rowptr, int64_t cap, int32_t* members, double* chords);
 
+/* replaces: newresampler::smooth_data (resampler.cpp:169-230) as one call, exclusion mask included (201-225): neighbourhood scan on the
+ * device, Gaussian weights and the reference's sequential sums on the host libm. feat_cm [D][n_feat] = orig's pvalues (indexed by the
+ * vertex ids of low_xyz, as the reference does), excl NULL or [n_excl] = EXCL's values; out_cm [D][n]; excl_out [n] (with a mask). */
+msmgpu_status msmgpu_smooth_data(msmgpu_ctx* ctx, int n, const double* low_xyz, const int32_t* closest, double sigma, int D, int n_feat,
+                                 const double* feat_cm, int n_excl, const double* excl, double* out_cm, double* excl_out);
+
+/* ---- exclusion masks (`--excl` / cut thresholds, featurespace.cpp:61-70): EXCL = a Mesh whose first channel is 0 where data is ignored ---- */
+/* replaces: get_adaptive_barycentric_weights(in, low, nthreads, EXCL) (resampler.cpp:72-140): targets whose closest source vertex is masked
+ * out (cpp:100) get empty rows and do not enter the correction sums. excl [nv_in] host doubles. */
+msmgpu_status msmgpu_adaptive_weights_excl(msmgpu_mesh* in_mesh, msmgpu_mesh* low_mesh, const double* excl, msmgpu_weights** out);
+/* replaces: barycentric_data_interpolation / metric_resample with EXCL (resampler.cpp:30-70, 304): masked weights, sums that skip masked
+ * source vertices (cpp:46-47), and the mask resampled with the same weights (cpp:55-67; excl_out [nv_low] replaces *EXCL) */
+msmgpu_status msmgpu_metric_resample_excl(msmgpu_mesh* in_mesh, msmgpu_mesh* low_mesh, int D, const double* feat_in, const double* excl_in,
+                                          double* feat_out, double* excl_out);
+/* replaces: nearest_neighbour_interpolation with EXCL (resampler.cpp:232-258) */
+msmgpu_status msmgpu_nn_resample_excl(msmgpu_mesh* in_mesh, int n, const double* low_xyz, int D, const double* feat_in, const double* excl_in,
+                                      double* feat_out, double* excl_out);
+
 msmgpu_status msmgpu_rotation_matrices(msmgpu_ctx* ctx, int n, const double* ci, const double* index, double* R);
 
 /* ---- discrete-optimisation cost evaluation (msm-newmeshreg/src/DiscreteCostFunction.{h,cpp}) ---- */

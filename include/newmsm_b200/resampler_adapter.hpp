@@ -101,6 +101,19 @@ inline Mesh with_pvalues(const Mesh& geometry, int D, const std::vector<double>&
     return out;
 }
 
+// an exclusion mask's values: Mesh::get_pvalue(i) of its first channel (resampler.cpp:47, 100)
+inline std::vector<double> mask_of(const Mesh& excl) {
+    std::vector<double> e((size_t)excl.nvertices());
+    for (int i = 0; i < excl.nvertices(); ++i) e[i] = excl.get_pvalue(i);
+    return e;
+}
+// `Mesh exclusion = sphLow; exclusion.set_pvalue(k, v)` (resampler.cpp:36, 64): a copy of the geometry carrying the new mask in channel 0
+inline Mesh with_mask(const Mesh& geometry, const std::vector<double>& values) {
+    Mesh out = geometry;
+    for (int k = 0; k < out.nvertices(); ++k) out.set_pvalue(k, values[k]);
+    return out;
+}
+
 }  // namespace detail
 
 // octree.h:39-59. Besides the reference's per-point calls there are batched ones: a GPU launch per point
@@ -154,10 +167,14 @@ public:
 
     std::vector<std::map<int, double>> get_adaptive_barycentric_weights(const Mesh& in_mesh, const Mesh& sphLow, int /*nthreads*/ = 1,
                                                                         std::shared_ptr<Mesh> EXCL = std::shared_ptr<Mesh>()) {
-        if (EXCL) return newresampler::Resampler().get_adaptive_barycentric_weights(in_mesh, sphLow, 1, EXCL);   // masks: host path, out of scope
         detail::DeviceMesh a(in_mesh), b(sphLow);
         msmgpu_weights* W = nullptr;
-        detail::check(msmgpu_adaptive_weights(a.h, b.h, &W));
+        if (EXCL) {   // resampler.cpp:100, 121: targets whose closest source vertex is masked out get no row
+            if (EXCL->nvertices() != in_mesh.nvertices()) throw MeshException("Exclusion mask differs in nvertices from data");
+            detail::check(msmgpu_adaptive_weights_excl(a.h, b.h, detail::mask_of(*EXCL).data(), &W));
+        } else {
+            detail::check(msmgpu_adaptive_weights(a.h, b.h, &W));
+        }
         int n_rows = 0;
         int64_t nnz = 0;
         msmgpu_weights_shape(W, &n_rows, nullptr, &nnz);
@@ -174,12 +191,18 @@ public:
 
     Mesh barycentric_data_interpolation(const Mesh& metric_in, const Mesh& sphLow, int nthreads = 1,
                                         std::shared_ptr<Mesh> EXCL = std::shared_ptr<Mesh>()) {
-        if (EXCL) return newresampler::Resampler().barycentric_data_interpolation(metric_in, sphLow, nthreads, EXCL);
+        if (EXCL && EXCL->nvertices() != metric_in.nvertices()) throw MeshException("Exclusion mask differs in nvertices from data");   // resampler.cpp:33-34
         detail::DeviceMesh a(metric_in), b(sphLow);
         const int D = metric_in.get_dimension();
         const std::vector<double> fin = detail::pvalues_of(metric_in);
         std::vector<double> fout((size_t)D * sphLow.nvertices());
-        detail::check(msmgpu_metric_resample(a.h, b.h, D, fin.data(), fout.data()));
+        if (EXCL) {   // masked weights and sums + the mask resampled with the same weights, which replaces *EXCL (resampler.cpp:55-67)
+            std::vector<double> eout((size_t)sphLow.nvertices());
+            detail::check(msmgpu_metric_resample_excl(a.h, b.h, D, fin.data(), detail::mask_of(*EXCL).data(), fout.data(), eout.data()));
+            *EXCL = detail::with_mask(sphLow, eout);
+        } else {
+            detail::check(msmgpu_metric_resample(a.h, b.h, D, fin.data(), fout.data()));
+        }
         return detail::with_pvalues(sphLow, D, fout);
     }
 };
@@ -213,12 +236,18 @@ inline void sphere_project_warp(Mesh& sphere, const Mesh& from, const Mesh& to, 
 }
 
 inline Mesh nearest_neighbour_interpolation(Mesh& orig, const Mesh& sphLow, int nthreads = 1, std::shared_ptr<Mesh> EXCL = std::shared_ptr<Mesh>()) {
-    if (EXCL) return newresampler::nearest_neighbour_interpolation(orig, sphLow, nthreads, EXCL);   // resampler.cpp:232-258
+    newresampler::check_scale(orig, sphLow);   // resampler.cpp:232-258
     detail::DeviceMesh a(orig);
     const int D = orig.get_dimension();
     const std::vector<double> fin = detail::pvalues_of(orig), low = detail::coords_of(sphLow);
     std::vector<double> fout((size_t)D * sphLow.nvertices());
-    detail::check(msmgpu_nn_resample(a.h, sphLow.nvertices(), low.data(), D, fin.data(), fout.data()));
+    if (EXCL) {
+        std::vector<double> eout((size_t)sphLow.nvertices());
+        detail::check(msmgpu_nn_resample_excl(a.h, sphLow.nvertices(), low.data(), D, fin.data(), detail::mask_of(*EXCL).data(), fout.data(), eout.data()));
+        *EXCL = detail::with_mask(sphLow, eout);
+    } else {
+        detail::check(msmgpu_nn_resample(a.h, sphLow.nvertices(), low.data(), D, fin.data(), fout.data()));
+    }
     return detail::with_pvalues(sphLow, D, fout);
 }
 
@@ -229,37 +258,21 @@ namespace newresampler_gpu {
 // smooth_data (resampler.cpp:169-230): Gaussian smoothing of the per-vertex data with an O(V^2) neighbourhood scan per call
 // (1.7e9 pair tests at ico6). The scan is pure IEEE arithmetic and runs on the device (msmgpu_smooth_neighbourhoods); the weights
 // need asin / exp and are evaluated on the host libm, on the short lists only, with the reference's expression and summation
-// order, so the result is the reference's bit for bit. Exclusion masks: forwarded to the reference's CPU code.
-inline Mesh smooth_data(Mesh& orig, const Mesh& sphLow, double sigma, int nthreads = 1, std::shared_ptr<Mesh> EXCL = std::shared_ptr<Mesh>()) {
-    if (EXCL) return newresampler::smooth_data(orig, sphLow, sigma, nthreads, EXCL);
+// order (inside msmgpu_smooth_data), so the result is the reference's bit for bit, exclusion masks included (resampler.cpp:201-225).
+inline Mesh smooth_data(Mesh& orig, const Mesh& sphLow, double sigma, int /*nthreads*/ = 1, std::shared_ptr<Mesh> EXCL = std::shared_ptr<Mesh>()) {
     newresampler::check_scale(orig, sphLow);
     const int n = sphLow.nvertices(), D = orig.get_dimension();
-    const double ang = 4 * std::asin(sigma / (2 * RAD));
     std::vector<Point> pts((size_t)n);
     for (int i = 0; i < n; ++i) pts[i] = sphLow.get_coord(i);
     const std::vector<int> closest = Octree(orig).get_closest_vertex_IDs(pts);   // oct_search.get_closest_vertex_ID(ci), resampler.cpp:184
-    const std::vector<double> low = detail::coords_of(sphLow);
-    std::vector<int32_t> c32(closest.begin(), closest.end()), rowptr((size_t)n + 1);
-    detail::check(msmgpu_smooth_neighbourhoods(detail::context(), n, low.data(), c32.data(), std::cos(ang), rowptr.data(), 0, nullptr, nullptr));
-    std::vector<int32_t> members((size_t)rowptr[n]);
-    std::vector<double> chords((size_t)rowptr[n]);
-    detail::check(msmgpu_smooth_neighbourhoods(detail::context(), n, low.data(), c32.data(), std::cos(ang), rowptr.data(), rowptr[n], members.data(),
-                                               chords.data()));
-    std::vector<double> out((size_t)D * n, 0.0);
-    const std::vector<double> fin = detail::pvalues_of(orig);
-    const int V = orig.nvertices();
-    #pragma omp parallel for schedule(dynamic, 256)
-    for (int i = 0; i < n; ++i) {
-        double SUM = 0.0;
-        for (int e = rowptr[i]; e < rowptr[i + 1]; ++e) {   // resampler.cpp:204-212, neighbours in ascending id
-            const double geodesic_dist = 2 * RAD * std::asin(chords[e] / (2 * RAD));
-            const double weight = (1 / std::sqrt(2 * M_PI * sigma * sigma)) * std::exp(-(geodesic_dist * geodesic_dist) / (2 * sigma * sigma));
-            SUM += weight;
-            for (int d = 0; d < D; ++d) out[(size_t)d * n + i] += fin[(size_t)d * V + members[e]] * weight;
-        }
-        for (int d = 0; d < D; ++d)
-            if (SUM != 0.0) out[(size_t)d * n + i] /= SUM;
-    }
+    const std::vector<double> low = detail::coords_of(sphLow), fin = detail::pvalues_of(orig);
+    std::vector<int32_t> c32(closest.begin(), closest.end());
+    std::vector<double> out((size_t)D * n), eout;
+    std::vector<double> mask;
+    if (EXCL) { mask = detail::mask_of(*EXCL); eout.resize((size_t)n); }
+    detail::check(msmgpu_smooth_data(detail::context(), n, low.data(), c32.data(), sigma, D, orig.nvertices(), fin.data(), (int)mask.size(),
+                                     EXCL ? mask.data() : nullptr, out.data(), EXCL ? eout.data() : nullptr));
+    if (EXCL) *EXCL = detail::with_mask(sphLow, eout);     // resampler.cpp:226
     return detail::with_pvalues(sphLow, D, out);
 }
 

@@ -137,6 +137,33 @@ int main() {
             EXPECT(same_pvalues(smooth_data(c, c, 2.0, 1), newresampler_gpu::smooth_data(d, d, 2.0, 1)), "smooth_data (sigma 2, rotated ico4): identical values");
         }
 
+        // exclusion masks (resampler.cpp:30-140, 169-258 with EXCL): data AND the replaced *EXCL mesh, reference vs adapter
+        {
+            auto mask = [&](const Mesh& g) {
+                auto e = std::make_shared<Mesh>(g);
+                e->initialize_pvalues(1);
+                for (int v = 0; v < e->nvertices(); ++v) {
+                    const double z = e->get_coord(v).Z;
+                    e->set_pvalue(v, z > 55.0 ? 0.0 : (z > 30.0 ? 0.5 + 0.5 * (55.0 - z) / 25.0 : 1.0), 0);
+                }
+                return e;
+            };
+            std::shared_ptr<Mesh> e1 = mask(in), e2 = mask(in);
+            EXPECT(same_pvalues(metric_resample(in, low, 1, e1), newresampler_gpu::metric_resample(in, low, 1, e2)) && same_pvalues(*e1, *e2),
+                   "metric_resample with EXCL: identical data and identical resampled mask");
+            e1 = mask(in); e2 = mask(in);
+            EXPECT(rc.get_adaptive_barycentric_weights(in, low, 1, e1) == rg.get_adaptive_barycentric_weights(in, low, 1, e2),
+                   "get_adaptive_barycentric_weights with EXCL: identical maps");
+            e1 = mask(in); e2 = mask(in);
+            Mesh a = in, b = in;
+            EXPECT(same_pvalues(smooth_data(a, a, 4.0, 1, e1), newresampler_gpu::smooth_data(b, b, 4.0, 1, e2)) && same_pvalues(*e1, *e2),
+                   "smooth_data with EXCL: identical data and identical new mask");
+            e1 = mask(in); e2 = mask(in);
+            EXPECT(same_pvalues(nearest_neighbour_interpolation(a, low, 1, e1), newresampler_gpu::nearest_neighbour_interpolation(b, low, 1, e2)) &&
+                       same_pvalues(*e1, *e2),
+                   "nearest_neighbour_interpolation with EXCL: identical data and identical new mask");
+        }
+
         // error behaviour: the reference's exception with the reference's message (octree.cpp:158)
         bool threw = false;
         try { og.get_closest_triangle(Point(0, 0, 150)); } catch (MeshException& e) { threw = std::strstr(e.what(), "bounding box") != nullptr; }

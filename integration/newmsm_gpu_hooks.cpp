@@ -156,14 +156,20 @@ static bool verify() { static const bool v = std::getenv("MSMGPU_VERIFY") != nul
 static std::mutex g_device_mutex;
 
 Mesh wrap_metric_resample(const Mesh& in, const Mesh& target, int nthreads, std::shared_ptr<Mesh> EXCL) {
-    if (EXCL || disabled("resample")) return real_metric_resample(in, target, nthreads, EXCL);   // exclusion masks: host-side filtering, out of scope
+    if (disabled("resample")) return real_metric_resample(in, target, nthreads, EXCL);
     const double t0 = omp_get_wtime();
-    Mesh out = [&] { std::lock_guard<std::mutex> g(g_device_mutex); return newresampler_gpu::metric_resample(in, target, nthreads); }();
+    std::shared_ptr<Mesh> excl_before = (EXCL && verify()) ? std::make_shared<Mesh>(*EXCL) : std::shared_ptr<Mesh>();
+    Mesh out = [&] { std::lock_guard<std::mutex> g(g_device_mutex); return newresampler_gpu::metric_resample(in, target, nthreads, EXCL); }();
     stat_add(stats.resample, &stats.n_resample, omp_get_wtime() - t0);
     if (verify()) {
-        const Mesh ref = real_metric_resample(in, target, nthreads, EXCL);
+        const Mesh ref = real_metric_resample(in, target, nthreads, excl_before);   // (the mask was replaced by the call above: use its copy)
         long bad = 0;
         double worst = 0;
+        if (EXCL)
+            for (int v = 0; v < EXCL->nvertices(); ++v) {
+                const double a = excl_before->get_pvalue(v), b = EXCL->get_pvalue(v);
+                if (std::memcmp(&a, &b, sizeof(double)) != 0) ++bad;
+            }
         for (int d = 0; d < ref.get_dimension(); ++d)
             for (int v = 0; v < ref.nvertices(); ++v) {
                 const double a = ref.get_pvalue(v, d), b = out.get_pvalue(v, d);
@@ -211,15 +217,21 @@ Mesh wrap_make_mesh_from_icosa(int n) {
 
 // resampler.cpp:169-230 -> device neighbourhood scan + host-libm weights (resampler adapter)
 Mesh wrap_smooth_data(Mesh& orig, const Mesh& sphLow, double sigma, int nthreads, std::shared_ptr<Mesh> EXCL) {
-    if (EXCL || disabled("smooth")) return real_smooth_data(orig, sphLow, sigma, nthreads, EXCL);
+    if (disabled("smooth")) return real_smooth_data(orig, sphLow, sigma, nthreads, EXCL);
     Mesh keep;
     if (verify()) keep = orig;
+    std::shared_ptr<Mesh> excl_before = (EXCL && verify()) ? std::make_shared<Mesh>(*EXCL) : std::shared_ptr<Mesh>();
     const double t0 = omp_get_wtime();
     Mesh out = [&] { std::lock_guard<std::mutex> g(g_device_mutex); return newresampler_gpu::smooth_data(orig, sphLow, sigma, nthreads, EXCL); }();
     stat_add(stats.smooth, &stats.n_smooth, omp_get_wtime() - t0);
     if (verify()) {
-        const Mesh ref = real_smooth_data(keep, sphLow, sigma, nthreads, EXCL);
+        const Mesh ref = real_smooth_data(keep, sphLow, sigma, nthreads, excl_before);
         long bad = 0;
+        if (EXCL)
+            for (int v = 0; v < EXCL->nvertices(); ++v) {
+                const double a = excl_before->get_pvalue(v), b = EXCL->get_pvalue(v);
+                bad += std::memcmp(&a, &b, sizeof(double)) != 0;
+            }
         for (int d = 0; d < ref.get_dimension(); ++d)
             for (int v = 0; v < ref.nvertices(); ++v) {
                 const double a = ref.get_pvalue(v, d), b = out.get_pvalue(v, d);

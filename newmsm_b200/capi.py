@@ -92,6 +92,10 @@ _SIGNATURES = {
     "msmgpu_surface_resample": (_i, [_vp, _vp, _i, _vp, _vp]),
     "msmgpu_nn_resample": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
     "msmgpu_rotation_matrices": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "msmgpu_smooth_data": (_i, [_vp, _i, _vp, _vp, _d, _i, _i, _vp, _i, _vp, _vp, _vp]),
+    "msmgpu_adaptive_weights_excl": (_i, [_vp, _vp, _vp, _pp]),
+    "msmgpu_metric_resample_excl": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "msmgpu_nn_resample_excl": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "msmgpu_smooth_neighbourhoods": (_i, [_vp, _i, _vp, _vp, _d, _vp, C.c_int64, _vp, _vp]),
     "msmgpu_costfn_create": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _pp]),
     "msmgpu_costfn_destroy": (None, [_vp]),

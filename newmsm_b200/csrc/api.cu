@@ -732,6 +732,36 @@ msmgpu_status msmgpu_nn_resample(msmgpu_mesh* in_mesh, int n, const double* low_
     return finish_queries(d_st.p, n, nullptr, s);
 }
 
+// nearest_neighbour_interpolation with an exclusion mask (resampler.cpp:232-258): a target whose closest source vertex is masked out
+// keeps 0 in every channel and in the new mask; the others copy the vertex's values and its mask value
+msmgpu_status msmgpu_nn_resample_excl(msmgpu_mesh* in_mesh, int n, const double* low_xyz, int D, const double* feat_in, const double* excl_in,
+                                      double* feat_out, double* excl_out) {
+    if (!in_mesh || n <= 0 || D <= 0 || !low_xyz || !feat_in || !excl_in || !feat_out || !excl_out) return fail(MSMGPU_ERR_INVALID, "nn_resample_excl: bad arguments");
+    msmgpu_ctx* ctx = in_mesh->ctx;
+    MSM_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    msmgpu_octree* t = nullptr;
+    MSM_TRY(msmgpu_octree_build(in_mesh, &t));
+    std::unique_ptr<msmgpu_octree> guard(t);
+    DevBuf<double> d_q;
+    DevBuf<int> d_vtx, d_st;
+    MSM_TRY(upload(d_q, low_xyz, 3 * (size_t)n, s));
+    MSM_CUDA(d_vtx.alloc(n, s));
+    MSM_CUDA(d_st.alloc(n, s));
+    MSM_TRY(launch_nearest(t->view(), n, d_q.p, nullptr, d_vtx.p, d_st.p, s));
+    std::vector<int> vtx((size_t)n);
+    MSM_CUDA(cudaMemcpyAsync(vtx.data(), d_vtx.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    MSM_TRY(finish_queries(d_st.p, n, nullptr, s));
+    const int nv = in_mesh->nv;
+    for (int i = 0; i < n; ++i) {
+        const int cv = vtx[i];
+        const bool on = cv >= 0 && excl_in[cv] != 0;
+        excl_out[i] = on ? excl_in[cv] : 0.0;
+        for (int d = 0; d < D; ++d) feat_out[(size_t)d * n + i] = on ? feat_in[(size_t)d * nv + cv] : 0.0;
+    }
+    return MSMGPU_OK;
+}
+
 msmgpu_status msmgpu_rotation_matrices(msmgpu_ctx*, int n, const double* ci, const double* index, double* R) {
     if (n < 0 || (n > 0 && (!ci || !index || !R))) return fail(MSMGPU_ERR_INVALID, "rotation_matrices: bad arguments");
     bool ok = true;

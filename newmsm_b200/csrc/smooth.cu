@@ -8,6 +8,8 @@
 #include "common.cuh"
 #include "query.cuh"
 
+#include <cmath>
+
 namespace msm {
 
 __global__ void k_unit_points(int n, const double* __restrict__ xyz, double* __restrict__ unit) {   // Point::normalize, point.cpp:26-34
@@ -95,5 +97,45 @@ extern "C" msmgpu_status msmgpu_smooth_neighbourhoods(msmgpu_ctx* ctx, int n, co
     MSM_CUDA(cudaMemcpyAsync(members, d_mem.p, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, s));
     MSM_CUDA(cudaMemcpyAsync(chords, d_ch.p, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, s));
     MSM_CUDA(cudaStreamSynchronize(s));
+    return MSMGPU_OK;
+}
+
+// newresampler::smooth_data (resampler.cpp:169-230) as one call: the O(V^2) neighbourhood scan on the device (above), the Gaussian
+// weights (asin, exp, sqrt on the host libm) and the reference's sequential sums on the host over the short lists, with the reference's
+// expressions and order, so values are the reference's bit for bit. With an exclusion mask (excl != NULL, resampler.cpp:201-225): a
+// target whose closest vertex has EXCL <= 0 keeps zeros; otherwise every weight is multiplied by the neighbour's mask value and the new
+// mask is the ratio of the masked to the unmasked weight sum. feat_cm [D][n_feat] = orig's pvalues (indexed by the ids of low_xyz's
+// vertices, like the reference does), out_cm [D][n], excl_out [n] (written only with a mask).
+extern "C" msmgpu_status msmgpu_smooth_data(msmgpu_ctx* ctx, int n, const double* low_xyz, const int32_t* closest, double sigma, int D, int n_feat,
+                                            const double* feat_cm, int n_excl, const double* excl, double* out_cm, double* excl_out) {
+    if (!ctx || n <= 0 || D <= 0 || !low_xyz || !closest || !feat_cm || !out_cm || n_feat < n || (excl && (!excl_out || n_excl < n)))
+        return fail(MSMGPU_ERR_INVALID, "smooth_data: bad arguments");
+    if (excl)
+        for (int i = 0; i < n; ++i)
+            if (closest[i] < 0 || closest[i] >= n_excl) return fail(MSMGPU_ERR_INVALID, "smooth_data: closest[] holds a vertex id outside the mask");
+    const double ang = 4 * std::asin(sigma / (2 * kRad));
+    std::vector<int32_t> rowptr((size_t)n + 1);
+    MSM_TRY(msmgpu_smooth_neighbourhoods(ctx, n, low_xyz, closest, std::cos(ang), rowptr.data(), 0, nullptr, nullptr));
+    std::vector<int32_t> members((size_t)rowptr[n]);
+    std::vector<double> chords((size_t)rowptr[n]);
+    MSM_TRY(msmgpu_smooth_neighbourhoods(ctx, n, low_xyz, closest, std::cos(ang), rowptr.data(), rowptr[n], members.data(), chords.data()));
+    for (size_t k = 0; k < (size_t)D * n; ++k) out_cm[k] = 0.0;
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int i = 0; i < n; ++i) {
+        if (excl) excl_out[i] = 0.0;
+        if (excl && !(excl[closest[i]] > 0)) continue;
+        double SUM = 0.0, excl_sum = 0.0;
+        for (int e = rowptr[i]; e < rowptr[i + 1]; ++e) {   // resampler.cpp:203-214, neighbours in ascending id
+            const double geodesic_dist = 2 * kRad * std::asin(chords[e] / (2 * kRad));
+            double weight = (1 / std::sqrt(2 * M_PI * sigma * sigma)) * std::exp(-(geodesic_dist * geodesic_dist) / (2 * sigma * sigma));
+            excl_sum += weight;
+            if (excl) weight = excl[members[e]] * weight;
+            SUM += weight;
+            for (int d = 0; d < D; ++d) out_cm[(size_t)d * n + i] += feat_cm[(size_t)d * n_feat + members[e]] * weight;
+        }
+        if (excl_sum != 0.0 && excl) excl_out[i] = SUM / excl_sum;
+        for (int d = 0; d < D; ++d)
+            if (SUM != 0.0) out_cm[(size_t)d * n + i] /= SUM;
+    }
     return MSMGPU_OK;
 }

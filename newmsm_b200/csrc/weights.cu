@@ -408,8 +408,31 @@ __global__ void __launch_bounds__(256) k_finish_rows(int n_rows, int n_low, cons
 }
 
 // Builds the S matrices into one shared store; out[s] become views of it.
+// Exclusion masks (resampler.cpp:100, 121): a target whose CLOSEST SOURCE VERTEX is masked out gets no row and adds nothing to the
+// correction sums. Both follow from dropping its forward list and every reverse-map entry that points at it before the rows are built.
+__global__ void k_mask_forward(int n_rows, const unsigned char* __restrict__ active, int* __restrict__ fne) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < n_rows && !active[n]) fne[n] = 0;
+}
+__global__ void k_mask_reverse(int nkeys, int S, int n_low, const int* __restrict__ in_off, const unsigned char* __restrict__ active,
+                               int* __restrict__ ridx, double* __restrict__ rw, int* __restrict__ rne) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nkeys) return;
+    const int row0 = (S == 1 ? 0 : find_segment(in_off, S, k)) * n_low;
+    const int ne = rne[k];
+    int m = 0;
+    for (int j = 0; j < ne; ++j) {            // stable compaction of the (ascending) entries that survive
+        const int t = ridx[3 * (size_t)k + j];
+        const double w = rw[3 * (size_t)k + j];
+        if (active[row0 + t]) { ridx[3 * (size_t)k + m] = t; rw[3 * (size_t)k + m] = w; ++m; }
+    }
+    for (int j = m; j < 3; ++j) { ridx[3 * (size_t)k + j] = -1; rw[3 * (size_t)k + j] = 0.0; }
+    rne[k] = m;
+}
+
 msmgpu_status adaptive_weights_build_batch(msmgpu_ctx* ctx, int S, msmgpu_mesh* const* in_meshes, msmgpu_octree* const* in_trees,
-                                           msmgpu_mesh* low_mesh, msmgpu_octree* low_tree, msmgpu_weights** out, const msmgpu_fwd* fwd) {
+                                           msmgpu_mesh* low_mesh, msmgpu_octree* low_tree, msmgpu_weights** out, const msmgpu_fwd* fwd,
+                                           const unsigned char* d_active = nullptr) {
     cudaStream_t s = ctx->stream;
     const int n_low = low_mesh->nv;
     std::vector<int> in_off(S + 1, 0);
@@ -463,6 +486,16 @@ msmgpu_status adaptive_weights_build_batch(msmgpu_ctx* ctx, int S, msmgpu_mesh* 
     int code = 0;
     MSM_TRY(first_error(st.p, (size_t)(NL + NV), s, &code));   // synchronises: `jobs` / `in_off` may now go
     if (code) return status_to_error(code);
+    DevBuf<int> fne_masked;
+    if (d_active) {
+        MSM_CUDA(fne_masked.alloc((size_t)NL, s));
+        MSM_CUDA(cudaMemcpyAsync(fne_masked.p, fne.p, (size_t)NL * sizeof(int), cudaMemcpyDeviceToDevice, s));
+        k_mask_forward<<<(unsigned)((NL + 255) / 256), 256, 0, s>>>((int)NL, d_active, fne_masked.p);
+        MSM_LAUNCH_CHECK();
+        fne.p = fne_masked.p;
+        k_mask_reverse<<<(unsigned)((NV + 255) / 256), 256, 0, s>>>((int)NV, S, n_low, d_in_off.p, d_active, ridx.p, rw.p, rne.p);
+        MSM_LAUNCH_CHECK();
+    }
 
     DevBuf<double> new_area, old_area, correction;
     MSM_CUDA(new_area.alloc(n_low, s));
@@ -528,6 +561,7 @@ struct ApplyJob {
     const int* rowptr;   // n_rows + 1 absolute offsets
     const void* in;      // [n_cols][D]
     void* out;           // [n_rows][D]
+    const double* excl;  // optional [n_cols]: entries whose source vertex has excl == 0 are skipped (resampler.cpp:46-47, 62-63)
 };
 
 __global__ void __launch_bounds__(256) k_csr_apply_f32x4(const ApplyJob* __restrict__ jobs, int n_rows, const int* __restrict__ col,
@@ -575,13 +609,18 @@ __global__ void __launch_bounds__(256) k_csr_apply(const ApplyJob* __restrict__ 
     const int c = (int)(slot - (long long)r * D);
     const T* __restrict__ in = static_cast<const T*>(job.in);
     double a = 0.0;
-    for (int i = __ldg(job.rowptr + r); i < __ldg(job.rowptr + r + 1); ++i) a += (double)__ldg(in + (size_t)__ldg(col + i) * D + c) * __ldg(val + i);
+    for (int i = __ldg(job.rowptr + r); i < __ldg(job.rowptr + r + 1); ++i) {
+        const int cc = __ldg(col + i);
+        if (job.excl && __ldg(job.excl + cc) == 0) continue;
+        a += (double)__ldg(in + (size_t)cc * D + c) * __ldg(val + i);
+    }
     static_cast<T*>(job.out)[(size_t)r * D + c] = (T)a;
 }
 
 // all weights must share one store (one batch) and have the same n_rows
 template <typename T>
-static msmgpu_status csr_apply_batch(msmgpu_ctx* ctx, int n, msmgpu_weights* const* Ws, int D, const T* const* d_in, T* const* d_out) {
+static msmgpu_status csr_apply_batch(msmgpu_ctx* ctx, int n, msmgpu_weights* const* Ws, int D, const T* const* d_in, T* const* d_out,
+                                     const double* const* d_excl = nullptr) {
     cudaStream_t s = ctx->stream;
     if (n <= 0 || D <= 0) return MSMGPU_OK;
     const WeightsStore* store = Ws[0]->store.get();
@@ -590,8 +629,8 @@ static msmgpu_status csr_apply_batch(msmgpu_ctx* ctx, int n, msmgpu_weights* con
     std::vector<ApplyJob> jobs(n);
     for (int i = 0; i < n; ++i) {
         if (Ws[i]->store.get() != store || Ws[i]->n_rows != n_rows) return fail(MSMGPU_ERR_INVALID, "weights_apply_batch: weights from different batches");
-        jobs[i] = ApplyJob{Ws[i]->rowptr, d_in[i], d_out[i]};
-        vec = vec && ((reinterpret_cast<uintptr_t>(d_in[i]) | reinterpret_cast<uintptr_t>(d_out[i])) & 15) == 0;
+        jobs[i] = ApplyJob{Ws[i]->rowptr, d_in[i], d_out[i], d_excl ? d_excl[i] : nullptr};
+        vec = vec && !jobs[i].excl && ((reinterpret_cast<uintptr_t>(d_in[i]) | reinterpret_cast<uintptr_t>(d_out[i])) & 15) == 0;
     }
     if (n_rows == 0) return MSMGPU_OK;
     // The bulk-copy gather (gather.cu) is opt-in for CSR rows ("gather_csr"): a row of the adaptive matrix has ~15 entries and every
@@ -773,6 +812,79 @@ msmgpu_status msmgpu_metric_resample(msmgpu_mesh* in_mesh, msmgpu_mesh* low_mesh
     MSM_TRY(csr_apply_f64(W, D, rows_in.p, rows_out.p));
     MSM_TRY(launch_transpose_f64(nl, D, rows_out.p, cm_out.p, s));
     MSM_CUDA(cudaMemcpyAsync(feat_out, cm_out.p, (size_t)D * nl * sizeof(double), cudaMemcpyDeviceToHost, s));
+    MSM_CUDA(cudaStreamSynchronize(s));
+    return MSMGPU_OK;
+}
+
+__global__ void k_active_from_excl(int n, const int* __restrict__ vtx, const double* __restrict__ excl, unsigned char* __restrict__ active) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) active[i] = (vtx[i] >= 0 && excl[vtx[i]] != 0) ? 1 : 0;
+}
+
+// get_adaptive_barycentric_weights with an exclusion mask (resampler.cpp:72-140 with EXCL): d_excl = device copy of EXCL's values
+static msmgpu_status adaptive_weights_excl_dev(msmgpu_mesh* in_mesh, msmgpu_mesh* low_mesh, const double* d_excl, msmgpu_weights** out) {
+    msmgpu_ctx* ctx = in_mesh->ctx;
+    cudaStream_t s = ctx->stream;
+    msmgpu_mesh* ms[2] = {in_mesh, low_mesh};
+    msmgpu_octree* ts[2] = {nullptr, nullptr};
+    MSM_TRY(msmgpu_octree_build_batch(ctx, 2, ms, ts));
+    std::unique_ptr<msmgpu_octree> g0(ts[0]), g1(ts[1]);
+    // active targets: EXCL(octreeSearch_in.get_closest_vertex_ID(target)) != 0 (resampler.cpp:100)
+    const int nl = low_mesh->nv;
+    DevBuf<int> tri, vtx, st;
+    DevBuf<unsigned char> active;
+    MSM_CUDA(tri.alloc(nl, s)); MSM_CUDA(vtx.alloc(nl, s)); MSM_CUDA(st.alloc(nl, s)); MSM_CUDA(active.alloc(nl, s));
+    MSM_TRY(launch_nearest(ts[0]->view(), nl, low_mesh->xyz.p, tri.p, vtx.p, st.p, s));
+    int code = 0;
+    MSM_TRY(first_error(st.p, (size_t)nl, s, &code));
+    if (code) return status_to_error(code);
+    k_active_from_excl<<<(nl + 255) / 256, 256, 0, s>>>(nl, vtx.p, d_excl, active.p);
+    MSM_LAUNCH_CHECK();
+    return adaptive_weights_build_batch(ctx, 1, &in_mesh, &ts[0], low_mesh, ts[1], out, nullptr, active.p);
+}
+
+msmgpu_status msmgpu_adaptive_weights_excl(msmgpu_mesh* in_mesh, msmgpu_mesh* low_mesh, const double* excl, msmgpu_weights** out) {
+    if (!in_mesh || !low_mesh || !excl || !out || in_mesh->ctx != low_mesh->ctx) return fail(MSMGPU_ERR_INVALID, "adaptive_weights_excl: bad arguments");
+    MSM_CUDA(cudaSetDevice(in_mesh->ctx->device));
+    cudaStream_t s = in_mesh->ctx->stream;
+    DevBuf<double> d_excl;
+    MSM_CUDA(d_excl.alloc(in_mesh->nv, s));
+    MSM_CUDA(cudaMemcpyAsync(d_excl.p, excl, (size_t)in_mesh->nv * sizeof(double), cudaMemcpyHostToDevice, s));
+    MSM_TRY(adaptive_weights_excl_dev(in_mesh, low_mesh, d_excl.p, out));
+    MSM_CUDA(cudaStreamSynchronize(s));
+    return MSMGPU_OK;
+}
+
+// barycentric_data_interpolation / metric_resample with EXCL (resampler.cpp:30-70): masked weights, masked sums, and the mask itself
+// resampled with the same weights (excl_out replaces *EXCL, cpp:66)
+msmgpu_status msmgpu_metric_resample_excl(msmgpu_mesh* in_mesh, msmgpu_mesh* low_mesh, int D, const double* feat_in, const double* excl_in,
+                                          double* feat_out, double* excl_out) {
+    if (!in_mesh || !low_mesh || D <= 0 || !feat_in || !excl_in || !feat_out || !excl_out || in_mesh->ctx != low_mesh->ctx)
+        return fail(MSMGPU_ERR_INVALID, "metric_resample_excl: bad arguments");
+    msmgpu_ctx* ctx = in_mesh->ctx;
+    MSM_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const int nv = in_mesh->nv, nl = low_mesh->nv;
+    DevBuf<double> d_excl, cm_in, rows_in, rows_out, cm_out, excl_rows;
+    MSM_CUDA(d_excl.alloc(nv, s));
+    MSM_CUDA(cudaMemcpyAsync(d_excl.p, excl_in, (size_t)nv * sizeof(double), cudaMemcpyHostToDevice, s));
+    msmgpu_weights* W = nullptr;
+    MSM_TRY(adaptive_weights_excl_dev(in_mesh, low_mesh, d_excl.p, &W));
+    std::unique_ptr<msmgpu_weights> guard(W);
+    MSM_CUDA(cm_in.alloc((size_t)D * nv, s));
+    MSM_CUDA(rows_in.alloc((size_t)D * nv, s));
+    MSM_CUDA(rows_out.alloc((size_t)D * nl, s));
+    MSM_CUDA(cm_out.alloc((size_t)D * nl, s));
+    MSM_CUDA(excl_rows.alloc(nl, s));
+    MSM_CUDA(cudaMemcpyAsync(cm_in.p, feat_in, (size_t)D * nv * sizeof(double), cudaMemcpyHostToDevice, s));
+    MSM_TRY(launch_transpose_f64(D, nv, cm_in.p, rows_in.p, s));
+    const double* in1 = rows_in.p; double* out1 = rows_out.p; const double* ex = d_excl.p;
+    MSM_TRY(csr_apply_batch<double>(ctx, 1, &W, D, &in1, &out1, &ex));
+    const double* in2 = d_excl.p; double* out2 = excl_rows.p;
+    MSM_TRY(csr_apply_batch<double>(ctx, 1, &W, 1, &in2, &out2, &ex));
+    MSM_TRY(launch_transpose_f64(nl, D, rows_out.p, cm_out.p, s));
+    MSM_CUDA(cudaMemcpyAsync(feat_out, cm_out.p, (size_t)D * nl * sizeof(double), cudaMemcpyDeviceToHost, s));
+    MSM_CUDA(cudaMemcpyAsync(excl_out, excl_rows.p, (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, s));
     MSM_CUDA(cudaStreamSynchronize(s));
     return MSMGPU_OK;
 }

@@ -262,8 +262,34 @@ class Resampler:
 
 
 def metric_resample(in_mesh: Mesh, target: Mesh, nthreads: int = 1, EXCL=None):
-    """resampler.cpp:304-309."""
-    return Resampler().barycentric_data_interpolation(in_mesh, target, nthreads, EXCL)
+    """resampler.cpp:304-309. EXCL (optional): the exclusion mask's values [nv_in]; then returns (resampled data, resampled mask),
+    the mask being what the reference writes back into *EXCL (resampler.cpp:55-67)."""
+    if EXCL is None:
+        return Resampler().barycentric_data_interpolation(in_mesh, target, nthreads, None)
+    feat, excl = in_mesh.pvalues, f64(EXCL)
+    out, eo = np.zeros((feat.shape[0], target.nvertices())), np.zeros(target.nvertices())
+    check(in_mesh.L.msmgpu_metric_resample_excl(in_mesh.h, target.h, feat.shape[0], ptr(feat), ptr(excl), ptr(out), ptr(eo)))
+    return out, eo
+
+
+def adaptive_weights_excl(in_mesh: Mesh, target: Mesh, EXCL) -> "Weights":
+    """get_adaptive_barycentric_weights with an exclusion mask (resampler.cpp:72-140)."""
+    h = C.c_void_p()
+    check(in_mesh.L.msmgpu_adaptive_weights_excl(in_mesh.h, target.h, ptr(f64(EXCL)), C.byref(h)))
+    return Weights(in_mesh.L, h, owner=in_mesh.ctx)
+
+
+def smooth_data(orig: Mesh, sphLow: Mesh, sigma: float, nthreads: int = 1, EXCL=None):
+    """resampler.cpp:169-230 -> smoothed data [D, n_low] (and the new mask when EXCL is given)."""
+    n = sphLow.nvertices()
+    closest = Octree(orig).get_closest_vertex_ID(sphLow.xyz).astype(np.int32)
+    feat = orig.pvalues
+    out = np.zeros((feat.shape[0], n))
+    excl = f64(EXCL) if EXCL is not None else None
+    eo = np.zeros(n) if excl is not None else None
+    check(orig.L.msmgpu_smooth_data(orig.ctx.h, n, ptr(sphLow.xyz), ptr(closest), float(sigma), feat.shape[0], feat.shape[1], ptr(feat),
+                                    len(excl) if excl is not None else 0, ptr(excl), ptr(out), ptr(eo)))
+    return out if excl is None else (out, eo)
 
 
 def metric_resample_f32(in_mesh: Mesh, target: Mesh, feat_f32, in_tree: Octree | None = None, target_tree: Octree | None = None):
@@ -303,13 +329,17 @@ def surface_resample(anat_xyz, sph: Mesh, low_xyz, nthreads: int = 1):
 project_anatomical_mesh = surface_resample
 
 
-def nearest_neighbour_interpolation(in_mesh: Mesh, low_xyz, feat=None, nthreads: int = 1):
-    """resampler.cpp:232-258 (no exclusion)."""
+def nearest_neighbour_interpolation(in_mesh: Mesh, low_xyz, feat=None, nthreads: int = 1, EXCL=None):
+    """resampler.cpp:232-258. With EXCL (the mask's values [nv_in]) returns (data, new mask)."""
     feat = in_mesh.pvalues if feat is None else f64(np.atleast_2d(feat))
     low = f64(low_xyz)
     out = np.zeros((feat.shape[0], len(low)))
-    check(in_mesh.L.msmgpu_nn_resample(in_mesh.h, len(low), ptr(low), feat.shape[0], ptr(feat), ptr(out)))
-    return out
+    if EXCL is None:
+        check(in_mesh.L.msmgpu_nn_resample(in_mesh.h, len(low), ptr(low), feat.shape[0], ptr(feat), ptr(out)))
+        return out
+    eo = np.zeros(len(low))
+    check(in_mesh.L.msmgpu_nn_resample_excl(in_mesh.h, len(low), ptr(low), feat.shape[0], ptr(feat), ptr(f64(EXCL)), ptr(out), ptr(eo)))
+    return out, eo
 
 
 def estimate_rotation_matrix(ci, index):

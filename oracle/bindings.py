@@ -176,6 +176,44 @@ def oracle_bary_resample(xyz_in, tri_in, xyz_low, feat, nthreads=8):
     return out
 
 
+def oracle_metric_resample_excl(xyz_in, tri_in, xyz_low, tri_low, feat, excl):
+    """metric_resample with an exclusion mask -> (out [D][n_low], resampled mask, (rowptr, col, val) of the masked weights)."""
+    a, b, c, d = _f64(xyz_in), _i32(tri_in), _f64(xyz_low), _i32(tri_low)
+    f, e = _f64(np.atleast_2d(feat)), _f64(excl)
+    out, eo = np.zeros((f.shape[0], len(c))), np.zeros(len(c))
+    rowptr = np.zeros(len(c) + 1, np.int32)
+    cap = 64 * max(len(a), len(c))
+    col, val = np.zeros(cap, np.int32), np.zeros(cap)
+    L = Oracle.lib()
+    L.orc_metric_resample_excl.argtypes = [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]
+    n = L.orc_metric_resample_excl(len(a), _p(a), len(b), _p(b), len(c), _p(c), len(d), _p(d), f.shape[0], _p(f), _p(e), _p(out), _p(eo),
+                                   _p(rowptr), _p(col), _p(val), cap)
+    if n < 0 or n > cap:
+        raise RuntimeError("oracle metric_resample (EXCL) failed")
+    return out, eo, (rowptr, col[:n].copy(), val[:n].copy())
+
+
+def oracle_nn_resample_excl(low, xyz, tri, feat, excl):
+    a, b, c, f, e = _f64(low), _f64(xyz), _i32(tri), _f64(np.atleast_2d(feat)), _f64(excl)
+    out, eo = np.zeros((f.shape[0], len(a))), np.zeros(len(a))
+    L = Oracle.lib()
+    L.orc_nn_resample_excl.argtypes = [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp]
+    if L.orc_nn_resample_excl(len(a), _p(a), len(b), _p(b), len(c), _p(c), f.shape[0], _p(f), _p(e), _p(out), _p(eo)):
+        raise RuntimeError("oracle nn resample (EXCL) failed")
+    return out, eo
+
+
+def oracle_smooth_data(xyz, tri, low, sigma, feat, excl=None):
+    a, b, c, f = _f64(xyz), _i32(tri), _f64(low), _f64(np.atleast_2d(feat))
+    e = _f64(excl) if excl is not None else None
+    out, eo = np.zeros((f.shape[0], len(c))), np.zeros(len(c))
+    L = Oracle.lib()
+    L.orc_smooth_data.argtypes = [_i, _vp, _i, _vp, _i, _vp, _d, _i, _vp, _vp, _vp, _vp]
+    if L.orc_smooth_data(len(a), _p(a), len(b), _p(b), len(c), _p(c), float(sigma), f.shape[0], _p(f), _p(e) if e is not None else None, _p(out), _p(eo)):
+        raise RuntimeError("oracle smooth_data failed")
+    return out, (eo if e is not None else None)
+
+
 def oracle_sphere_project_warp(sphere, from_xyz, tri, to_xyz, nthreads=8):
     s, a, t, b = _f64(sphere), _f64(from_xyz), _i32(tri), _f64(to_xyz)
     out = np.zeros_like(s)
@@ -366,6 +404,10 @@ class Ref:
             L.ref_surface_resample.argtypes = [_vp, _vp, _vp, _i, _vp]
             L.ref_nn_resample.argtypes = [_vp, _vp, _i, _vp]
             L.ref_rotation_matrix.argtypes = [_vp, _vp, _vp]
+            L.ref_metric_resample_excl.argtypes = [_vp, _vp, _i, _vp, _vp, _vp]
+            L.ref_adaptive_weights_excl.argtypes = [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i]
+            L.ref_smooth_data.argtypes = [_vp, _vp, _d, _i, _vp, _vp, _vp]
+            L.ref_nn_resample_excl.argtypes = [_vp, _vp, _i, _vp, _vp, _vp]
             cls._lib = L
         return cls._lib
 
@@ -483,6 +525,44 @@ def ref_nn_resample(m_in: RefMesh, m_low: RefMesh, nthreads=1):
     if Ref.lib().ref_nn_resample(m_in.h, m_low.h, nthreads, _p(out)):
         raise RuntimeError("reference nn resample failed")
     return out
+
+
+def ref_metric_resample_excl(m_in: RefMesh, m_low: RefMesh, excl, nthreads=1):
+    """metric_resample with an exclusion mask (resampler.cpp:30-70): (out [D][n_low], resampled mask [n_low])."""
+    e = _f64(excl)
+    out, eo = np.zeros((m_in.D, m_low.nv)), np.zeros(m_low.nv)
+    if Ref.lib().ref_metric_resample_excl(m_in.h, m_low.h, nthreads, _p(e), _p(out), _p(eo)):
+        raise RuntimeError("reference metric_resample (EXCL) failed")
+    return out, eo
+
+
+def ref_adaptive_weights_excl(m_in: RefMesh, m_low: RefMesh, excl, nthreads=1):
+    L = Ref.lib()
+    e = _f64(excl)
+    rowptr = np.zeros(m_low.nv + 1, np.int32)
+    cap = 64 * max(m_low.nv, m_in.nv)
+    col, val = np.zeros(cap, np.int32), np.zeros(cap)
+    nnz = L.ref_adaptive_weights_excl(m_in.h, m_low.h, nthreads, _p(e), _p(rowptr), _p(col), _p(val), cap)
+    if nnz < 0 or nnz > cap:
+        raise RuntimeError("reference adaptive weights (EXCL) failed")
+    return rowptr, col[:nnz].copy(), val[:nnz].copy()
+
+
+def ref_smooth_data(m_orig: RefMesh, m_low: RefMesh, sigma, excl=None, nthreads=1):
+    """smooth_data (resampler.cpp:169-230), optional exclusion mask: (out [D][n_low], new mask or None)."""
+    out, eo = np.zeros((m_orig.D, m_low.nv)), np.zeros(m_low.nv)
+    e = _f64(excl) if excl is not None else None
+    if Ref.lib().ref_smooth_data(m_orig.h, m_low.h, float(sigma), nthreads, _p(e) if e is not None else None, _p(out), _p(eo)):
+        raise RuntimeError("reference smooth_data failed")
+    return out, (eo if e is not None else None)
+
+
+def ref_nn_resample_excl(m_in: RefMesh, m_low: RefMesh, excl, nthreads=1):
+    e = _f64(excl)
+    out, eo = np.zeros((m_in.D, m_low.nv)), np.zeros(m_low.nv)
+    if Ref.lib().ref_nn_resample_excl(m_in.h, m_low.h, nthreads, _p(e), _p(out), _p(eo)):
+        raise RuntimeError("reference nn resample (EXCL) failed")
+    return out, eo
 
 
 def ref_rotation_matrix(ci, index):

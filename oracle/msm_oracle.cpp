@@ -345,13 +345,22 @@ void vertex_areas(int nv, const double* xyz, int nt, const int* tri, double* out
 // resampler.cpp:72-140 without EXCL, single-thread order
 int adaptive_maps(int nv_in, const double* xyz_in, int nt_in, const int* tri_in,
                   int nv_low, const double* xyz_low, int nt_low, const int* tri_low,
-                  std::vector<std::map<int, double>>& adapt, const double* area_xyz_in = nullptr) {
+                  std::vector<std::map<int, double>>& adapt, const double* area_xyz_in = nullptr, const double* excl = nullptr) {
     // area_xyz_in: coordinates the source mesh had when its Triangle objects were last (re)created. Triangle::area is
     // cached at construction and NOT refreshed by Mesh::set_coord (triangle.cpp:31,39), so a mesh that was
     // copied and then moved (DiscreteGroupModel.cpp:94-103) keeps the vertex areas of its pre-move geometry.
     orc_octree* tin = build_tree(nv_in, xyz_in, nt_in, tri_in);
     std::vector<std::map<int, double>> forward, reverse;
     int e = bary_weight_maps(tin, nv_low, xyz_low, forward);
+    // exclusion mask (resampler.cpp:100, 121): a target is used iff EXCL at its closest source vertex is non-zero
+    std::vector<char> active(nv_low, 1);
+    if (excl && !e)
+        for (int n = 0; n < nv_low; ++n) {
+            const P3 p{xyz_low[3 * n], xyz_low[3 * n + 1], xyz_low[3 * n + 2]};
+            int st = 0;
+            const int id = closest_triangle(tin, p, &st, nullptr);
+            active[n] = id >= 0 && excl[closest_vertex_of(tin, p, id)] != 0;
+        }
     delete tin;
     if (e) return e;
     orc_octree* tlow = build_tree(nv_low, xyz_low, nt_low, tri_low);
@@ -367,11 +376,13 @@ int adaptive_maps(int nv_in, const double* xyz_in, int nt_in, const int* tri_in,
     for (int o = 0; o < nv_in; ++o)
         for (auto& it : reverse[o]) rr[it.first][o] = it.second;
     for (int n = 0; n < nv_low; ++n) {
+        if (!active[n]) continue;
         if (rr[n].size() <= forward[n].size()) adapt[n] = forward[n];
         else adapt[n] = rr[n];
         for (auto& it : adapt[n]) { it.second *= newA[n]; correction[it.first] += it.second; }
     }
     for (int n = 0; n < nv_low; ++n) {
+        if (!active[n]) continue;
         double ws = 0.0;
         for (auto& it : adapt[n]) { it.second *= oldA[it.first] / correction[it.first]; ws += it.second; }
         if (ws != 0.0) for (auto& it : adapt[n]) it.second /= ws;
@@ -462,6 +473,95 @@ int orc_metric_resample(int nv_in, const double* xyz_in, int nt_in, const int* t
         }
     }
     return 0;
+}
+
+// resampler.cpp:30-70 with EXCL: masked weights, sums that skip masked source vertices, and the resampled mask (excl_out);
+// rowptr / col / val (optional) = the masked weight maps as CSR
+int orc_metric_resample_excl(int nv_in, const double* xyz_in, int nt_in, const int* tri_in,
+                             int nv_low, const double* xyz_low, int nt_low, const int* tri_low,
+                             int D, const double* feat_in, const double* excl, double* feat_out, double* excl_out,
+                             int* rowptr, int* col, double* val, int cap) {
+    std::vector<std::map<int, double>> adapt;
+    if (adaptive_maps(nv_in, xyz_in, nt_in, tri_in, nv_low, xyz_low, nt_low, tri_low, adapt, nullptr, excl)) return -1;
+    for (int d = 0; d < D; ++d)
+        for (int k = 0; k < nv_low; ++k) {
+            double v = 0.0;
+            for (auto& it : adapt[k])
+                if (excl[it.first] != 0) v += feat_in[(size_t)d * nv_in + it.first] * it.second;
+            feat_out[(size_t)d * nv_low + k] = v;
+        }
+    for (int k = 0; k < nv_low; ++k) {
+        double v = 0.0;
+        for (auto& it : adapt[k])
+            if (excl[it.first] != 0) v += excl[it.first] * it.second;
+        excl_out[k] = v;
+    }
+    int pos = 0;
+    if (rowptr) {
+        for (int r = 0; r < nv_low; ++r) {
+            rowptr[r] = pos;
+            for (auto& it : adapt[r]) { if (pos < cap) { col[pos] = it.first; val[pos] = it.second; } ++pos; }
+        }
+        rowptr[nv_low] = pos;
+    }
+    return pos;
+}
+
+// resampler.cpp:232-258 with EXCL
+int orc_nn_resample_excl(int n, const double* low_xyz, int nv, const double* xyz, int nt, const int* tri,
+                         int D, const double* feat_in, const double* excl, double* feat_out, double* excl_out) {
+    orc_octree* t = build_tree(nv, xyz, nt, tri);
+    std::vector<int> tr(n), vx(n), st(n);
+    orc_octree_query(t, n, low_xyz, tr.data(), vx.data(), st.data(), nullptr, 1);
+    delete t;
+    for (int i = 0; i < n; ++i) if (st[i]) return st[i];
+    for (int i = 0; i < n; ++i) {
+        const bool on = excl[vx[i]] != 0;
+        excl_out[i] = on ? excl[vx[i]] : 0.0;
+        for (int d = 0; d < D; ++d) feat_out[(size_t)d * n + i] = on ? feat_in[(size_t)d * nv + vx[i]] : 0.0;
+    }
+    return 0;
+}
+
+// resampler.cpp:169-230: Gaussian smoothing of orig's data over sphLow's vertices (n vertices, feat [D][n_feat] indexed by sphLow ids like
+// the reference does), optional exclusion mask
+int orc_smooth_data(int nv_orig, const double* orig_xyz, int nt_orig, const int* orig_tri, int n, const double* low_xyz, double sigma,
+                    int D, const double* feat, const double* excl, double* out, double* excl_out) {
+    orc_octree* t = build_tree(nv_orig, orig_xyz, nt_orig, orig_tri);
+    const double ang = 4 * std::asin(sigma / (2 * RAD));
+    for (size_t k = 0; k < (size_t)D * n; ++k) out[k] = 0.0;
+    int err = 0;
+    for (int i = 0; i < n && !err; ++i) {
+        if (excl) excl_out[i] = 0.0;
+        const P3 ci{low_xyz[3 * i], low_xyz[3 * i + 1], low_xyz[3 * i + 2]};
+        int st = 0;
+        const int id = closest_triangle(t, ci, &st, nullptr);
+        if (id < 0) { err = st ? st : 2; break; }
+        const int cv = closest_vertex_of(t, ci, id);
+        P3 ref{low_xyz[3 * cv], low_xyz[3 * cv + 1], low_xyz[3 * cv + 2]};
+        normalize(ref);
+        std::vector<std::pair<int, double>> nb;
+        for (int m = 0; m < n; ++m) {
+            P3 actual{low_xyz[3 * m], low_xyz[3 * m + 1], low_xyz[3 * m + 2]};
+            normalize(actual);
+            if (dot(actual, ref) >= std::cos(ang)) nb.emplace_back(m, norm(sub(ref, actual)));
+        }
+        if (excl && !(excl[cv] > 0)) continue;
+        double SUM = 0.0, excl_sum = 0.0;
+        for (const auto& q : nb) {
+            const double g = 2 * RAD * std::asin(q.second / (2 * RAD));
+            double w = (1 / std::sqrt(2 * M_PI * sigma * sigma)) * std::exp(-(g * g) / (2 * sigma * sigma));
+            excl_sum += w;
+            if (excl) w = excl[q.first] * w;
+            SUM += w;
+            for (int d = 0; d < D; ++d) out[(size_t)d * n + i] += feat[(size_t)d * nv_orig + q.first] * w;
+        }
+        if (excl_sum != 0.0 && excl) excl_out[i] = SUM / excl_sum;
+        for (int d = 0; d < D; ++d)
+            if (SUM != 0.0) out[(size_t)d * n + i] /= SUM;
+    }
+    delete t;
+    return err;
 }
 
 int orc_bary_resample(int nv_in, const double* xyz_in, int nt_in, const int* tri_in,

@@ -41,6 +41,14 @@ void orc_vertex_areas(int nv, const double* xyz, int nt, const int* tri, double*
 
 /* resampler.cpp:72-140 (no exclusion mask), single-thread summation order. CSR out.
  * Returns nnz, or -1 on a failed query. rowptr[n_low+1]; col/val written up to cap. */
+/* exclusion masks (resampler.cpp:30-140, 169-258 with EXCL) */
+int orc_metric_resample_excl(int nv_in, const double* xyz_in, int nt_in, const int* tri_in, int nv_low, const double* xyz_low, int nt_low,
+                             const int* tri_low, int D, const double* feat_in, const double* excl, double* feat_out, double* excl_out,
+                             int* rowptr, int* col, double* val, int cap);
+int orc_nn_resample_excl(int n, const double* low_xyz, int nv, const double* xyz, int nt, const int* tri, int D, const double* feat_in,
+                         const double* excl, double* feat_out, double* excl_out);
+int orc_smooth_data(int nv_orig, const double* orig_xyz, int nt_orig, const int* orig_tri, int n, const double* low_xyz, double sigma, int D,
+                    const double* feat, const double* excl, double* out, double* excl_out);
 int orc_adaptive_weights(int nv_in, const double* xyz_in, int nt_in, const int* tri_in,
                          int nv_low, const double* xyz_low, int nt_low, const int* tri_low,
                          int* rowptr, int* col, double* val, int cap);

@@ -243,6 +243,66 @@ int ref_nn_resample(void* in, void* low, int nthreads, double* out) {
     return 0;
 }
 
+// ---- exclusion masks: the reference's functions with EXCL (a Mesh with one channel), resampler.cpp:30-70, 169-258 ----
+static std::shared_ptr<Mesh> excl_mesh(const Mesh& geometry, const double* excl) {
+    auto m = std::make_shared<Mesh>(geometry);
+    m->initialize_pvalues(1);
+    for (int v = 0; v < m->nvertices(); ++v) m->set_pvalue(v, excl[v], 0);
+    return m;
+}
+static void export_pvalues(const Mesh& r, double* out) {
+    const int D = r.get_dimension(), N = r.nvertices();
+    for (int d = 0; d < D; ++d)
+        for (int v = 0; v < N; ++v) out[(size_t)d * N + v] = r.get_pvalue(v, d);
+}
+// metric_resample(in, low, nthreads, EXCL): out [D][N_low], excl_out [N_low] = the resampled mask that replaces *EXCL
+int ref_metric_resample_excl(void* in, void* low, int nthreads, const double* excl, double* out, double* excl_out) {
+    try {
+        Mesh* mi = static_cast<Mesh*>(in);
+        std::shared_ptr<Mesh> E = excl_mesh(*mi, excl);
+        Mesh res = metric_resample(*mi, *static_cast<Mesh*>(low), nthreads, E);
+        export_pvalues(res, out);
+        for (int v = 0; v < E->nvertices(); ++v) excl_out[v] = E->get_pvalue(v);
+    } catch (MeshException&) { return 1; }
+    return 0;
+}
+// get_adaptive_barycentric_weights(in, low, nthreads, EXCL) as CSR
+int ref_adaptive_weights_excl(void* in, void* low, int nthreads, const double* excl, int* rowptr, int* col, double* val, int cap) {
+    try {
+        Mesh* mi = static_cast<Mesh*>(in);
+        Resampler r;
+        std::vector<std::map<int, double>> w = r.get_adaptive_barycentric_weights(*mi, *static_cast<Mesh*>(low), nthreads, excl_mesh(*mi, excl));
+        int pos = 0;
+        for (size_t k = 0; k < w.size(); ++k) {
+            rowptr[k] = pos;
+            for (const auto& e : w[k]) { if (pos < cap) { col[pos] = e.first; val[pos] = e.second; } ++pos; }
+        }
+        rowptr[w.size()] = pos;
+        return pos;
+    } catch (MeshException&) { return -1; }
+}
+// smooth_data(orig, low, sigma, nthreads, EXCL or none): out [D][N_low]; excl NULL = no mask
+int ref_smooth_data(void* orig, void* low, double sigma, int nthreads, const double* excl, double* out, double* excl_out) {
+    try {
+        Mesh* mo = static_cast<Mesh*>(orig);
+        std::shared_ptr<Mesh> E = excl ? excl_mesh(*mo, excl) : std::shared_ptr<Mesh>();
+        Mesh res = smooth_data(*mo, *static_cast<Mesh*>(low), sigma, nthreads, E);
+        export_pvalues(res, out);
+        if (E) for (int v = 0; v < E->nvertices(); ++v) excl_out[v] = E->get_pvalue(v);
+    } catch (MeshException&) { return 1; }
+    return 0;
+}
+int ref_nn_resample_excl(void* in, void* low, int nthreads, const double* excl, double* out, double* excl_out) {
+    try {
+        Mesh* mi = static_cast<Mesh*>(in);
+        std::shared_ptr<Mesh> E = excl_mesh(*mi, excl);
+        Mesh res = nearest_neighbour_interpolation(*mi, *static_cast<Mesh*>(low), nthreads, E);
+        export_pvalues(res, out);
+        for (int v = 0; v < E->nvertices(); ++v) excl_out[v] = E->get_pvalue(v);
+    } catch (MeshException&) { return 1; }
+    return 0;
+}
+
 // estimate_rotation_matrix(ci, index) (point.cpp:97) -> row-major 3x3
 void ref_rotation_matrix(const double* ci, const double* index, double* R) {
     NEWMAT::Matrix M = estimate_rotation_matrix(Point(ci[0], ci[1], ci[2]), Point(index[0], index[1], index[2]));

@@ -947,3 +947,42 @@ def test_rigid_level_vs_reference_golden(R, oracle_built, name, D, sim):
     cf.initialise()
     assert cf.rigid_cost_mesh(0.0, 0.0, 0.0) == want_cost0
     assert np.array_equal(cf.run(), want_xyz)
+
+
+@pytest.mark.parametrize("name,sl,ll", [("down", 4, 3), ("up", 3, 4), ("same", 3, 3)])
+def test_exclusion_masks_vs_reference_golden(R, oracle_built, name, sl, ll):
+    """Exclusion masks on the device path (no CPU fallback): masked adaptive weights, metric_resample + the resampled
+    mask, nearest-neighbour interpolation — bit-exact against the reference's own outputs (tests/golden/excl.npz) and the oracle."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_excl", os.path.join(G, "make_golden_excl.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = load("excl.npz")
+    xyz, tri, low, low_tri, feat, excl = mod.excl_case(sl, ll)
+    m, ml = R.Mesh(xyz, tri, feat), R.Mesh(low, low_tri)
+    out, eo = R.metric_resample(m, ml, EXCL=excl)
+    assert np.array_equal(out, g[f"{name}_metric"]) and np.array_equal(eo, g[f"{name}_metric_excl"])
+    rp, col, val = R.adaptive_weights_excl(m, ml, excl).csr()
+    assert np.array_equal(rp, g[f"{name}_rowptr"]) and np.array_equal(col, g[f"{name}_col"]) and np.array_equal(val, g[f"{name}_val"])
+    assert (np.diff(rp) == 0).any(), "the case must contain targets without a row"
+    n, en = R.nearest_neighbour_interpolation(m, low, EXCL=excl)
+    assert np.array_equal(n, g[f"{name}_nn"]) and np.array_equal(en, g[f"{name}_nn_excl"])
+    # an all-ones mask changes nothing
+    ones = np.ones(len(xyz))
+    o1, e1 = R.metric_resample(m, ml, EXCL=ones)
+    assert np.array_equal(o1, R.metric_resample(m, ml))
+    assert np.abs(e1 - 1).max() < 1e-12
+
+
+def test_smooth_data_with_exclusion_mask_golden(R, oracle_built):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_excl", os.path.join(G, "make_golden_excl.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = load("excl.npz")
+    xyz, tri, _, _, feat, excl = mod.excl_case(4, 3)
+    m = R.Mesh(xyz, tri, feat)
+    for sigma in (4.0, 9.0):
+        assert np.array_equal(R.smooth_data(m, m, sigma), g[f"smooth{int(sigma)}"])
+        s1, e1 = R.smooth_data(m, m, sigma, EXCL=excl)
+        assert np.array_equal(s1, g[f"smooth{int(sigma)}_masked"]) and np.array_equal(e1, g[f"smooth{int(sigma)}_excl"])

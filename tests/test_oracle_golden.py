@@ -147,3 +147,28 @@ def test_rigid_level_golden(oracle_built):
         assert np.array_equal(rowptr, g[f"{name}_rowptr"]) and np.array_equal(members, g[f"{name}_members"])
         assert cost0 == float(g[f"{name}_cost0"])
         assert np.array_equal(moved, g[f"{name}_xyz"])
+
+
+def test_exclusion_masks_golden(oracle_built):
+    """Exclusion masks (resampler.cpp:30-140, 169-258 with EXCL): the CPU restatement reproduces the compiled reference's outputs
+    (tests/golden/excl.npz, generator make_golden_excl.py) bit for bit: masked adaptive weights, metric_resample + resampled mask,
+    nearest-neighbour interpolation, Gaussian smoothing with and without a mask."""
+    import importlib.util
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden_excl", os.path.join(here, "golden", "make_golden_excl.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = np.load(os.path.join(here, "golden", "excl.npz"))
+    for name, (sl, ll) in {"down": (4, 3), "up": (3, 4), "same": (3, 3)}.items():
+        xyz, tri, low, low_tri, feat, excl = mod.excl_case(sl, ll)
+        out, eo, (rp, col, val) = oracle_built.oracle_metric_resample_excl(xyz, tri, low, low_tri, feat, excl)
+        assert np.array_equal(rp, g[f"{name}_rowptr"]) and np.array_equal(col, g[f"{name}_col"]) and np.array_equal(val, g[f"{name}_val"])
+        assert np.array_equal(out, g[f"{name}_metric"]) and np.array_equal(eo, g[f"{name}_metric_excl"])
+        n, en = oracle_built.oracle_nn_resample_excl(low, xyz, tri, feat, excl)
+        assert np.array_equal(n, g[f"{name}_nn"]) and np.array_equal(en, g[f"{name}_nn_excl"])
+    xyz, tri, _, _, feat, excl = mod.excl_case(4, 3)
+    for sigma in (4.0, 9.0):
+        s0, _ = oracle_built.oracle_smooth_data(xyz, tri, xyz, sigma, feat)
+        s1, e1 = oracle_built.oracle_smooth_data(xyz, tri, xyz, sigma, feat, excl)
+        assert np.array_equal(s0, g[f"smooth{int(sigma)}"])
+        assert np.array_equal(s1, g[f"smooth{int(sigma)}_masked"]) and np.array_equal(e1, g[f"smooth{int(sigma)}_excl"])
