@@ -315,6 +315,10 @@ msmgpu_status msmgpu_group_fields(msmgpu_ctx* ctx, int n_subjects, int nv, const
 msmgpu_status msmgpu_group_create(msmgpu_ctx* ctx, int simmeasure, int S, int ncp, int L, int D, msmgpu_mesh* tpl, const double* d_fields,
                                   const double* rotations, const double* labels, const double* spacings, double range, msmgpu_group** out);
 void msmgpu_group_destroy(msmgpu_group* g);
+/* replaces: DiscreteGroupCostFunction::set_masks (DiscreteGroupCostFunction.h:50; DiscreteGroupModel.cpp:164): with a cost mask the
+ * weight of a common template vertex p in the weighted similarity is std::abs(_MASK.get_pvalue(p)) instead of 1
+ * (DiscreteGroupCostFunction.cpp:77). mask: [n_tpl] host doubles (channel 0 of the mask mesh); NULL removes the mask. */
+msmgpu_status msmgpu_group_set_mask(msmgpu_group* g, const double* mask);
 /* replaces: DiscreteGroupCostFunction::computePairwiseCost (DiscreteGroupCostFunction.cpp:54-97) for n requests (pair, la, lb);
  * pairs [P][2] global node ids (subject*ncp + vertex, DiscreteGroupModel.cpp:37-55). Any sub-array of pairs may be passed (sharding). */
 msmgpu_status msmgpu_group_pair_costs(msmgpu_group* g, int P, const int32_t* pairs, int n, const int32_t* req_pair, const int32_t* req_la,

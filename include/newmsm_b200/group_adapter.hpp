@@ -22,7 +22,8 @@
 // MSMGPU_DEVICES=n (default 1): one context per device; the subjects of get_patch_data and the pair blocks of every batch are
 // sharded over them (subject fields are exchanged device to device once per iteration); results do not depend on n.
 //
-// Not covered (the functions return false and the caller runs the reference code): exclusion/cost masks (`set_masks`).
+// Cost masks (`set_masks`, DiscreteGroupModel.cpp:164): the mask mesh's values go to the device with the iteration state
+// (msmgpu_group_set_mask); the pair costs weight every common template vertex by |mask| (DiscreteGroupCostFunction.cpp:77).
 #pragma once
 
 #include <thread>
@@ -244,7 +245,6 @@ public:
     // DiscreteGroupModel.cpp:37-55: for every control point of subject A, the closest control point of every later subject B.
     // One forest over the S control grids, then one batched query per subject B with the control points of all A < B.
     bool estimate_pairs(Model& m) {
-        if (m.is_masked) return false;
         const double t0 = omp_get_wtime();
         ensure_devices();
         msmgpu_ctx* ctx = dev_[0].ctx;
@@ -287,7 +287,7 @@ public:
     bool get_patch_data(Model& m) {
         drop_iteration_state();
         auto* cf = dynamic_cast<CostFn*>(m.costfct.get());
-        if (!cf || m.is_masked || m.m_num_subjects < 2) return false;
+        if (!cf || m.m_num_subjects < 2) return false;
         const double t0 = omp_get_wtime();
         ensure_devices();
         model_ = &m; cf_ = cf;
@@ -358,10 +358,17 @@ public:
                     detail::check(msmgpu_device_copy_peer(dev_[dst].ctx, dev_[dst].fields + (size_t)b * per_subject, dev_[src].ctx,
                                                           dev_[src].fields + (size_t)b * per_subject, (size_t)(e - b) * per_subject * sizeof(double)));
             }
+        std::vector<double> mask;
+        if (cf->is_masked) {   // set_masks (DiscreteGroupCostFunction.h:50): channel 0 of the mask mesh, one value per template vertex
+            if (cf->_MASK.nvertices() != n_tpl) throw MeshregException("Group cost mask differs in nvertices from the template");
+            mask.resize((size_t)n_tpl);
+            for (int p = 0; p < n_tpl; ++p) mask[p] = cf->_MASK.get_pvalue(p);
+        }
         on_devices([&](int d) {
             Device& dv = dev_[d];
             detail::check(msmgpu_group_create(dv.ctx, cf->_simmeasure, S_, ncp_, L_, D_, dv.tpl, dv.fields, rot_.data(), labels_.data(), spacing.data(), m.range,
                                               &dv.group));
+            if (cf->is_masked) detail::check(msmgpu_group_set_mask(dv.group, mask.data()));
         });
         pairs_.assign(m.pairs, m.pairs + 2 * (size_t)P_);
         on_devices([&](int d) {

@@ -113,6 +113,7 @@ _SIGNATURES = {
     "msmgpu_group_fields": (_i, [_vp, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "msmgpu_group_create": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _d, _pp]),
     "msmgpu_group_destroy": (None, [_vp]),
+    "msmgpu_group_set_mask": (_i, [_vp, _vp]),
     "msmgpu_group_pair_costs": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "msmgpu_group_pair_batch": (_i, [_vp, _i, _vp, _vp, _i, _vp]),
     "msmgpu_group_set_pairs": (_i, [_vp, _i, _vp]),

@@ -57,6 +57,20 @@ double patch_chord_threshold(double limit) {
     return dhi;
 }
 
+// The same decision on the SQUARED chord: sqrt is correctly rounded, hence monotone over the doubles, so there is a largest s with
+// sqrt(s) < thr and `sqrt(s) < thr  <=>  s < chord_sq_threshold(thr)` for every representable s. Found by stepping ulps around thr^2.
+double chord_sq_threshold(double thr) {
+    if (!(thr > 0.0)) return thr == thr ? 0.0 : thr;            // nobody is a member (NaN stays NaN: every compare false)
+    const double inf = std::numeric_limits<double>::infinity();
+    if (thr == inf) return inf;
+    double s = thr * thr;
+    if (s == inf) s = std::numeric_limits<double>::max();
+    while (s > 0.0 && std::sqrt(s) >= thr) s = std::nextafter(s, 0.0);       // now sqrt(s) < thr (or s = 0)
+    if (std::sqrt(s) >= thr) return 0.0;
+    while (std::sqrt(std::nextafter(s, inf)) < thr) s = std::nextafter(s, inf);
+    return std::nextafter(s, inf);
+}
+
 __device__ __forceinline__ bool in_patch(const V3& c, const double* __restrict__ src, int i, double thr) {
     const V3 s{__ldg(src + 3 * (size_t)i), __ldg(src + 3 * (size_t)i + 1), __ldg(src + 3 * (size_t)i + 2)};
     return vnorm(vsub(c, s)) < thr;

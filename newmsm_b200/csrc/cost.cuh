@@ -25,6 +25,7 @@ struct msmgpu_costfn {
 namespace msm {
 
 double patch_chord_threshold(double limit);   // cost.cu: host bisection, member <=> chord < threshold
+double chord_sq_threshold(double thr);         // cost.cu: chord < thr <=> chord^2 < chord_sq_threshold(thr), exactly
 bool host_rotation_matrix(const double* ci, const double* index, double* R);   // api.cu
 msmgpu_status build_patch_lists(int n_cp, const double* d_cp, int n_src, const double* d_src, const double* d_thr, DevBuf<int>& prow,
                                 DevBuf<int>& pmem, int& total, int& max_len, cudaStream_t s);

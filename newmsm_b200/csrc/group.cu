@@ -29,6 +29,8 @@ struct msmgpu_group {
     msm::DevBuf<double> tpl_xyz;        // [n_tpl][3]
     msm::DevBuf<double> rcp;            // [S*ncp][L][3] rotated control points
     msm::DevBuf<double> thr;            // [S*ncp] chord thresholds
+    msm::DevBuf<double> thr2;           // [S*ncp] the same decision on the squared chord (chord_sq_threshold)
+    msm::DevBuf<double> mask;           // [n_tpl] |mask value| per template vertex, empty: unit weights (msmgpu_group_set_mask)
     msm::DevBuf<int> sup_ptr, sup_mem;  // superset candidate lists per node
     int n_sup = 0, max_sup = 0;
     msm::DevBuf<int> pairs;             // optional device-resident pair list [P][2] (msmgpu_group_set_pairs)
@@ -61,7 +63,9 @@ __global__ void k_rotated_cps(int n_nodes, int L, const double* __restrict__ rot
 
 struct PairArgs {
     int simmeasure, ncp, L, D, n_tpl, n;
-    const double* fields; const double* tpl; const double* rcp; const double* thr;
+    const double* fields; const double* tpl; const double* rcp;
+    const double* thr2;      // [S*ncp] squared-chord thresholds: chord < thr  <=>  chord^2 < thr2 (chord_sq_threshold, cost.cu)
+    const double* mask;      // [n_tpl] |_MASK.get_pvalue(p)| (DiscreteGroupCostFunction.cpp:77), or NULL: unit weights
     const int* sup_ptr; const int* sup_mem;
     const int* pairs;        // [P][2]
     const int* req_pair; const int* req_la; const int* req_lb;   // list mode, or NULL:
@@ -71,14 +75,12 @@ struct PairArgs {
 
 constexpr int kPairWarps = 4;
 
-// one warp per request. Lane d owns channel d (d + 32, ...): the intersection is found 32 candidates at a time
-// (one chord test pair per lane, ballot), then every member is visited in ascending template id and each lane
-// adds its channel's value -> the reference's sequential sums, coalesced over the channels.
-__global__ void __launch_bounds__(kPairWarps * 32) k_group_pair_costs(PairArgs a) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int r = blockIdx.x * kPairWarps + warp;
-    if (r >= a.n) return;
-    int pair, la, lb;
+__device__ __forceinline__ double chord2(const V3& c, const V3& t) {   // the argument of the square root in Point::norm (vnorm)
+    const V3 d = vsub(c, t);
+    return d.x * d.x + d.y * d.y + d.z * d.z;
+}
+
+__device__ __forceinline__ void pair_request(const PairArgs& a, int r, int& pair, int& la, int& lb) {
     if (a.req_pair) {
         pair = a.req_pair[r]; la = a.req_la[r]; lb = a.req_lb[r];
     } else {   // Fusion.h:170-173: (cur,cur), (cur,label), (label,cur), (label,label)
@@ -87,22 +89,28 @@ __global__ void __launch_bounds__(kPairWarps * 32) k_group_pair_costs(PairArgs a
         la = (combo & 2) ? a.label : a.labeling[a.pairs[2 * (size_t)pair]];
         lb = (combo & 1) ? a.label : a.labeling[a.pairs[2 * (size_t)pair + 1]];
     }
+}
+
+// ---- D > 8: one warp per request. Lane d owns channel d (d + 32, ...): the intersection is found 32 candidates at a time
+// (one chord test pair per lane, ballot), then every member is visited in ascending template id and each lane
+// adds its channel's value -> the reference's sequential sums, coalesced over the channels.
+__global__ void __launch_bounds__(kPairWarps * 32) k_group_pair_costs(PairArgs a) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * kPairWarps + warp;
+    if (r >= a.n) return;
+    int pair, la, lb;
+    pair_request(a, r, pair, la, lb);
     const int nA = a.pairs[2 * (size_t)pair], nB = a.pairs[2 * (size_t)pair + 1];
     const V3 cA = load_pt(a.rcp, nA * a.L + la), cB = load_pt(a.rcp, nB * a.L + lb);
-    const double tA = a.thr[nA], tB = a.thr[nB];
+    const double tA = a.thr2[nA], tB = a.thr2[nB];
     const int sA = nA / a.ncp, sB = nB / a.ncp;
     const double* __restrict__ fA = a.fields + ((size_t)sA * a.L + la) * a.n_tpl * a.D;
     const double* __restrict__ fB = a.fields + ((size_t)sB * a.L + lb) * a.n_tpl * a.D;
+    const double* __restrict__ mask = a.mask;
     const int b = a.sup_ptr[nA], e = a.sup_ptr[nA + 1];
 
-    double cost = 0.0;   // lane 0 accumulates the per-channel similarities in channel order
-    int n_common = 0;
-    for (int d0 = 0; d0 < a.D; d0 += 32) {
-        const int d = d0 + lane;
-        const bool has = d < a.D;
-        // pass 1: count, sum A, sum B
-        double sumA = 0.0, sumB = 0.0;
-        int cnt = 0;
+    // every member of the intersection, in ascending template id, to f(template vertex)
+    auto members = [&](auto f) {
         for (int i0 = b; i0 < e; i0 += 32) {
             const int i = i0 + lane;
             int p = -1;
@@ -110,69 +118,56 @@ __global__ void __launch_bounds__(kPairWarps * 32) k_group_pair_costs(PairArgs a
             if (i < e) {
                 p = __ldg(a.sup_mem + i);
                 const V3 t = load_pt(a.tpl, p);
-                in = vnorm(vsub(cA, t)) < tA && vnorm(vsub(cB, t)) < tB;
+                in = chord2(cA, t) < tA && chord2(cB, t) < tB;
             }
             unsigned m = __ballot_sync(kFull, in);
             while (m) {
                 const int src = __ffs(m) - 1;
                 m &= m - 1;
-                const int pp = __shfl_sync(kFull, p, src);
-                ++cnt;
-                if (has) { sumA += fA[(size_t)pp * a.D + d]; sumB += fB[(size_t)pp * a.D + d]; }
+                f(__shfl_sync(kFull, p, src));
             }
         }
+    };
+
+    double cost = 0.0;   // lane 0 accumulates the per-channel similarities in channel order
+    int n_common = 0;
+    for (int d0 = 0; d0 < a.D; d0 += 32) {
+        const int d = d0 + lane;
+        const bool has = d < a.D;
+        // pass 1: count, weight sum, weighted sums of A and B (similarities.cpp:132-137)
+        double sum = 0.0, meanA = 0.0, meanB = 0.0;
+        int cnt = 0;
+        members([&](int pp) {
+            ++cnt;
+            const double w = mask ? __ldg(mask + pp) : 1.0;
+            sum += w;
+            if (has) { meanA += w * fA[(size_t)pp * a.D + d]; meanB += w * fB[(size_t)pp * a.D + d]; }
+        });
         n_common = cnt;
         double sim = 0.0;
         if (cnt > 0) {
-            if (a.simmeasure == 2) {   // similarities.cpp:129-158 with unit weights
-                const double sum = (double)cnt;   // sum of cnt ones, exact
-                const double meanA = sumA / sum, meanB = sumB / sum;
+            if (a.simmeasure == 2) {   // similarities.cpp:139-158
+                if (sum > 0.0) { meanA /= sum; meanB /= sum; }
                 double prod = 0.0, varA = 0.0, varB = 0.0;
-                for (int i0 = b; i0 < e; i0 += 32) {
-                    const int i = i0 + lane;
-                    int p = -1;
-                    bool in = false;
-                    if (i < e) {
-                        p = __ldg(a.sup_mem + i);
-                        const V3 t = load_pt(a.tpl, p);
-                        in = vnorm(vsub(cA, t)) < tA && vnorm(vsub(cB, t)) < tB;
+                members([&](int pp) {
+                    if (has) {
+                        const double w = mask ? __ldg(mask + pp) : 1.0;
+                        const double x = fA[(size_t)pp * a.D + d] - meanA, y = fB[(size_t)pp * a.D + d] - meanB;
+                        prod += w * x * y; varA += w * x * x; varB += w * y * y;
                     }
-                    unsigned m = __ballot_sync(kFull, in);
-                    while (m) {
-                        const int src = __ffs(m) - 1;
-                        m &= m - 1;
-                        const int pp = __shfl_sync(kFull, p, src);
-                        if (has) {
-                            const double x = fA[(size_t)pp * a.D + d] - meanA, y = fB[(size_t)pp * a.D + d] - meanB;
-                            prod += 1.0 * x * y; varA += 1.0 * x * x; varB += 1.0 * y * y;
-                        }
-                    }
-                }
-                prod /= sum; varA /= sum; varB /= sum;
+                });
+                if (sum > 0.0) { prod /= sum; varA /= sum; varB /= sum; }
                 const double corr = (varA == 0.0 || varB == 0.0) ? 0.0 : prod / (sqrt(varA) * sqrt(varB));
                 sim = 1 - (1 + corr) * 0.5;
             } else {   // SSD, similarities.cpp:179-188
                 double prod = 0.0;
-                for (int i0 = b; i0 < e; i0 += 32) {
-                    const int i = i0 + lane;
-                    int p = -1;
-                    bool in = false;
-                    if (i < e) {
-                        p = __ldg(a.sup_mem + i);
-                        const V3 t = load_pt(a.tpl, p);
-                        in = vnorm(vsub(cA, t)) < tA && vnorm(vsub(cB, t)) < tB;
+                members([&](int pp) {
+                    if (has) {
+                        const double w = mask ? __ldg(mask + pp) : 1.0;
+                        const double dd = fA[(size_t)pp * a.D + d] - fB[(size_t)pp * a.D + d];
+                        prod += w * dd * dd;
                     }
-                    unsigned m = __ballot_sync(kFull, in);
-                    while (m) {
-                        const int src = __ffs(m) - 1;
-                        m &= m - 1;
-                        const int pp = __shfl_sync(kFull, p, src);
-                        if (has) {
-                            const double dd = fA[(size_t)pp * a.D + d] - fB[(size_t)pp * a.D + d];
-                            prod += 1.0 * dd * dd;
-                        }
-                    }
-                }
+                });
                 sim = sqrt(prod) / cnt;
             }
         }
@@ -181,6 +176,133 @@ __global__ void __launch_bounds__(kPairWarps * 32) k_group_pair_costs(PairArgs a
         for (int k = 0; k < nd; ++k) cost += __shfl_sync(kFull, sim, k);
     }
     if (lane == 0) a.out[r] = n_common > 0 ? cost / a.D : nan("");   // empty intersection: the reference reads patch_data_A[0] of an empty vector
+}
+
+// ---- D <= 8: one THREAD per request. With a handful of channels a warp per request leaves 31 lanes idle in every sequential sum
+// (ncu of the warp kernel at D = 1: profiles/s2_pair_costs_ncu.md). A thread tests its node's superset once (membership bits kept in
+// a small private bit array), then walks the members twice -- weighted sums, centred products -- DC channels at a time, with the
+// reference's sequential FP64 order per channel. The 4 requests of a pair (Fusion's combinations) sit in neighbouring lanes and read
+// the same superset list and template points.
+constexpr int kFlagWords = 32;   // membership bits for supersets of up to 1024 candidates; longer lists are re-tested in every walk
+
+template <int DC>
+__global__ void __launch_bounds__(128) k_group_pair_costs_thread(PairArgs a) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.n) return;
+    int pair, la, lb;
+    pair_request(a, r, pair, la, lb);
+    const int nA = a.pairs[2 * (size_t)pair], nB = a.pairs[2 * (size_t)pair + 1];
+    const V3 cA = load_pt(a.rcp, nA * a.L + la), cB = load_pt(a.rcp, nB * a.L + lb);
+    const double tA = a.thr2[nA], tB = a.thr2[nB];
+    const int sA = nA / a.ncp, sB = nB / a.ncp;
+    const int D = a.D;
+    const double* __restrict__ fA = a.fields + ((size_t)sA * a.L + la) * a.n_tpl * D;
+    const double* __restrict__ fB = a.fields + ((size_t)sB * a.L + lb) * a.n_tpl * D;
+    const double* __restrict__ mask = a.mask;
+    const int* __restrict__ sup = a.sup_mem + a.sup_ptr[nA];
+    const int len = a.sup_ptr[nA + 1] - a.sup_ptr[nA];
+    const bool cached = len <= 32 * kFlagWords;
+    unsigned flags[kFlagWords];
+
+    auto test = [&](int p) {
+        const V3 t = load_pt(a.tpl, p);
+        return chord2(cA, t) < tA && chord2(cB, t) < tB;
+    };
+    int cnt = 0;
+    for (int w0 = 0; w0 < len; w0 += 32) {
+        unsigned m = 0;
+        const int nb = min(32, len - w0);
+        for (int k = 0; k < nb; ++k) m |= (unsigned)test(__ldg(sup + w0 + k)) << k;
+        if (cached) flags[w0 >> 5] = m;
+        cnt += __popc(m);
+    }
+    if (cnt == 0) { a.out[r] = nan(""); return; }   // empty intersection: the reference reads patch_data_A[0] of an empty vector
+    auto members = [&](auto f) {   // ascending template id
+        for (int w0 = 0; w0 < len; w0 += 32) {
+            unsigned m;
+            if (cached) {
+                m = flags[w0 >> 5];
+            } else {
+                m = 0;
+                const int nb = min(32, len - w0);
+                for (int k = 0; k < nb; ++k) m |= (unsigned)test(__ldg(sup + w0 + k)) << k;
+            }
+            while (m) {
+                const int k = __ffs(m) - 1;
+                m &= m - 1;
+                f(__ldg(sup + w0 + k));
+            }
+        }
+    };
+
+    double cost = 0.0;
+    for (int d0 = 0; d0 < D; d0 += DC) {
+        double sum = 0.0, meanA[DC], meanB[DC];
+#pragma unroll
+        for (int c = 0; c < DC; ++c) meanA[c] = meanB[c] = 0.0;
+        members([&](int p) {   // similarities.cpp:132-137
+            const double w = mask ? __ldg(mask + p) : 1.0;
+            sum += w;
+#pragma unroll
+            for (int c = 0; c < DC; ++c)
+                if (d0 + c < D) { meanA[c] += w * fA[(size_t)p * D + d0 + c]; meanB[c] += w * fB[(size_t)p * D + d0 + c]; }
+        });
+        double acc[3 * DC];
+#pragma unroll
+        for (int c = 0; c < 3 * DC; ++c) acc[c] = 0.0;
+        if (a.simmeasure == 2) {   // similarities.cpp:139-158
+            if (sum > 0.0) {
+#pragma unroll
+                for (int c = 0; c < DC; ++c) { meanA[c] /= sum; meanB[c] /= sum; }
+            }
+            members([&](int p) {
+                const double w = mask ? __ldg(mask + p) : 1.0;
+#pragma unroll
+                for (int c = 0; c < DC; ++c)
+                    if (d0 + c < D) {
+                        const double x = fA[(size_t)p * D + d0 + c] - meanA[c], y = fB[(size_t)p * D + d0 + c] - meanB[c];
+                        acc[3 * c] += w * x * y; acc[3 * c + 1] += w * x * x; acc[3 * c + 2] += w * y * y;
+                    }
+            });
+#pragma unroll
+            for (int c = 0; c < DC; ++c)
+                if (d0 + c < D) {
+                    double prod = acc[3 * c], varA = acc[3 * c + 1], varB = acc[3 * c + 2];
+                    if (sum > 0.0) { prod /= sum; varA /= sum; varB /= sum; }
+                    const double corr = (varA == 0.0 || varB == 0.0) ? 0.0 : prod / (sqrt(varA) * sqrt(varB));
+                    cost += 1 - (1 + corr) * 0.5;   // pair_cost += sim, channel by channel (DiscreteGroupCostFunction.cpp:86-91)
+                }
+        } else {   // SSD, similarities.cpp:179-188
+            members([&](int p) {
+                const double w = mask ? __ldg(mask + p) : 1.0;
+#pragma unroll
+                for (int c = 0; c < DC; ++c)
+                    if (d0 + c < D) {
+                        const double dd = fA[(size_t)p * D + d0 + c] - fB[(size_t)p * D + d0 + c];
+                        acc[c] += w * dd * dd;
+                    }
+            });
+#pragma unroll
+            for (int c = 0; c < DC; ++c)
+                if (d0 + c < D) cost += sqrt(acc[c]) / cnt;
+        }
+    }
+    a.out[r] = cost / D;
+}
+
+static msmgpu_status launch_pair_costs(const PairArgs& a, cudaStream_t s) {
+    const char* force = std::getenv("MSMGPU_PAIR_KERNEL");   // "warp" / "thread": A/B runs (tools, profiles)
+    const bool thread = force ? force[0] == 't' : a.D <= 8;
+    if (thread) {
+        const unsigned grid = (unsigned)((a.n + 127) / 128);
+        if (a.D == 1) k_group_pair_costs_thread<1><<<grid, 128, 0, s>>>(a);
+        else if (a.D == 2) k_group_pair_costs_thread<2><<<grid, 128, 0, s>>>(a);
+        else k_group_pair_costs_thread<4><<<grid, 128, 0, s>>>(a);
+    } else {
+        k_group_pair_costs<<<(unsigned)((a.n + kPairWarps - 1) / kPairWarps), kPairWarps * 32, 0, s>>>(a);
+    }
+    MSM_LAUNCH_CHECK();
+    return MSMGPU_OK;
 }
 
 template <typename T>
@@ -225,11 +347,10 @@ static msmgpu_status pair_run(msmgpu_group* g, int P, const int32_t* pairs, int 
     MSM_CUDA(d_out.alloc((size_t)n, s));
     PairArgs a;
     a.simmeasure = g->simmeasure; a.ncp = g->ncp; a.L = g->L; a.D = g->D; a.n_tpl = g->n_tpl; a.n = n;
-    a.fields = g->d_fields; a.tpl = g->tpl_xyz.p; a.rcp = g->rcp.p; a.thr = g->thr.p; a.sup_ptr = g->sup_ptr.p; a.sup_mem = g->sup_mem.p;
+    a.fields = g->d_fields; a.tpl = g->tpl_xyz.p; a.rcp = g->rcp.p; a.thr2 = g->thr2.p; a.mask = g->mask.p; a.sup_ptr = g->sup_ptr.p; a.sup_mem = g->sup_mem.p;
     a.pairs = d_pairs.p; a.req_pair = req_pair ? d_rp.p : nullptr; a.req_la = d_la.p; a.req_lb = d_lb.p;
     a.labeling = d_labeling.p; a.label = label; a.out = d_out.p;
-    k_group_pair_costs<<<(unsigned)((n + kPairWarps - 1) / kPairWarps), kPairWarps * 32, 0, s>>>(a);
-    MSM_LAUNCH_CHECK();
+    MSM_TRY(launch_pair_costs(a, s));
     MSM_CUDA(cudaMemcpyAsync(out, d_out.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
     MSM_CUDA(cudaStreamSynchronize(s));
     return MSMGPU_OK;
@@ -317,13 +438,17 @@ msmgpu_status msmgpu_group_create(msmgpu_ctx* ctx, int simmeasure, int S, int nc
     auto g = std::unique_ptr<msmgpu_group>(new msmgpu_group());
     g->ctx = ctx; g->simmeasure = simmeasure; g->S = S; g->ncp = ncp; g->L = L; g->D = D; g->n_tpl = tpl->nv; g->d_fields = d_fields;
     const int n_nodes = S * ncp;
-    std::vector<double> thr(n_nodes);
+    std::vector<double> thr(n_nodes), thr2(n_nodes);
 #pragma omp parallel for
-    for (int k = 0; k < n_nodes; ++k) thr[k] = patch_chord_threshold(range * spacings[k]);   // DiscreteGroupModel.cpp:111
+    for (int k = 0; k < n_nodes; ++k) {
+        thr[k] = patch_chord_threshold(range * spacings[k]);   // DiscreteGroupModel.cpp:111
+        thr2[k] = chord_sq_threshold(thr[k]);
+    }
     DevBuf<double> d_rot, d_labels, anchor, thr_super;
     MSM_TRY(upg(d_rot, rotations, 9 * (size_t)n_nodes, s));
     MSM_TRY(upg(d_labels, labels, 3 * (size_t)L, s));
     MSM_TRY(upg(g->thr, thr.data(), (size_t)n_nodes, s));
+    MSM_TRY(upg(g->thr2, thr2.data(), (size_t)n_nodes, s));
     MSM_CUDA(g->rcp.alloc(3 * (size_t)n_nodes * L, s));
     MSM_CUDA(anchor.alloc(3 * (size_t)n_nodes, s));
     MSM_CUDA(thr_super.alloc((size_t)n_nodes, s));
@@ -340,6 +465,18 @@ void msmgpu_group_destroy(msmgpu_group* g) {
     if (!g) return;
     cudaSetDevice(g->ctx->device);
     delete g;
+}
+
+msmgpu_status msmgpu_group_set_mask(msmgpu_group* g, const double* mask) {
+    if (!g) return fail(MSMGPU_ERR_INVALID, "group_set_mask: bad arguments");
+    MSM_CUDA(cudaSetDevice(g->ctx->device));
+    cudaStream_t s = g->ctx->stream;
+    if (!mask) { g->mask.release(); return MSMGPU_OK; }
+    std::vector<double> w((size_t)g->n_tpl);
+    for (int p = 0; p < g->n_tpl; ++p) w[p] = std::fabs(mask[p]);   // std::abs(_MASK.get_pvalue(e.first)), DiscreteGroupCostFunction.cpp:77
+    MSM_TRY(upg(g->mask, w.data(), w.size(), s));
+    MSM_CUDA(cudaStreamSynchronize(s));
+    return MSMGPU_OK;
 }
 
 msmgpu_status msmgpu_group_pair_costs(msmgpu_group* g, int P, const int32_t* pairs, int n, const int32_t* req_pair, const int32_t* req_la,
@@ -367,12 +504,10 @@ msmgpu_status msmgpu_group_pair_batch_dev(msmgpu_group* g, int first_pair, int n
     MSM_TRY(upg(g->labeling, labeling, (size_t)g->S * g->ncp, s));
     PairArgs a;
     a.simmeasure = g->simmeasure; a.ncp = g->ncp; a.L = g->L; a.D = g->D; a.n_tpl = g->n_tpl; a.n = 4 * n_pairs;
-    a.fields = g->d_fields; a.tpl = g->tpl_xyz.p; a.rcp = g->rcp.p; a.thr = g->thr.p; a.sup_ptr = g->sup_ptr.p; a.sup_mem = g->sup_mem.p;
+    a.fields = g->d_fields; a.tpl = g->tpl_xyz.p; a.rcp = g->rcp.p; a.thr2 = g->thr2.p; a.mask = g->mask.p; a.sup_ptr = g->sup_ptr.p; a.sup_mem = g->sup_mem.p;
     a.pairs = g->pairs.p + 2 * (size_t)first_pair; a.req_pair = nullptr; a.req_la = nullptr; a.req_lb = nullptr;
     a.labeling = g->labeling.p; a.label = label; a.out = d_out;
-    k_group_pair_costs<<<(unsigned)((a.n + kPairWarps - 1) / kPairWarps), kPairWarps * 32, 0, s>>>(a);
-    MSM_LAUNCH_CHECK();
-    return MSMGPU_OK;
+    return launch_pair_costs(a, s);
 }
 
 msmgpu_status msmgpu_group_pair_batch(msmgpu_group* g, int P, const int32_t* pairs, const int32_t* labeling, int label, double* out) {

@@ -79,6 +79,14 @@ class DiscreteGroupModel:
         self.coll = Collective(dist)
         self.g = None
         self.fields = None
+        self.mask = None
+
+    # DiscreteGroupModel::set_masks / DiscreteGroupCostFunction::set_masks (DiscreteGroupModel.h:51, DiscreteGroupCostFunction.h:50)
+    def set_masks(self, mask):
+        """mask: [n_tpl] values of the mask mesh's first channel; the pair costs weight a common vertex by |mask| (cpp:77)."""
+        self.mask = None if mask is None else f64(mask).reshape(-1)
+        if self.g is not None:
+            check(self.L_.msmgpu_group_set_mask(self.g, ptr(self.mask) if self.mask is not None else None))
 
     # DiscreteGroupModel::get_spacings (cpp:123-143): largest geodesic distance to a mesh neighbour, per control point
     @staticmethod
@@ -141,6 +149,8 @@ class DiscreteGroupModel:
         rot, sp = f64(rotations).reshape(-1, 9), f64(spacings).reshape(-1)
         check(self.L_.msmgpu_group_create(self.ctx.h, self.simmeasure, S, self.ncp, L, D, self.template.h, ptr(self.fields), ptr(rot),
                                           ptr(labels), ptr(sp), float(range_), C.byref(self.g)))
+        if self.mask is not None:
+            check(self.L_.msmgpu_group_set_mask(self.g, ptr(self.mask)))
         return self.fields
 
     # DiscreteGroupCostFunction::computePairwiseCost (cpp:54-97)

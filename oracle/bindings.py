@@ -90,6 +90,7 @@ class Oracle:
                                           _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i]
             L.orc_group_fields.argtypes = [_i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i]
             L.orc_group_pair_costs.argtypes = [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _d, _vp, _i, _vp, _vp, _vp, _vp, _i]
+            L.orc_group_pair_costs_masked.argtypes = [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _d, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i]
             L.orc_ho_patches.argtypes = [_i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i]
             L.orc_rigid.restype = _i
             L.orc_rigid.argtypes = [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _d, _d, _vp, _vp, _vp, _vp, _i]
@@ -327,13 +328,14 @@ def oracle_group_fields(data_xyz, tri, feat, labels, centre, tpl_xyz, tpl_tri, n
     return out
 
 
-def oracle_group_pair_costs(simmeasure, ncp, tpl_xyz, fields, rot, labels, spacings, range_, pairs, req_pair, req_la, req_lb, nthreads=8):
+def oracle_group_pair_costs(simmeasure, ncp, tpl_xyz, fields, rot, labels, spacings, range_, pairs, req_pair, req_la, req_lb, nthreads=8, mask=None):
     tx, fields, rot, labels, sp = _f64(tpl_xyz), _f64(fields), _f64(rot), _f64(labels), _f64(spacings).reshape(-1)
     pairs, rp, la, lb = _i32(pairs), _i32(req_pair), _i32(req_la), _i32(req_lb)
     S, L, D = fields.shape[0], fields.shape[1], fields.shape[2]
     out = np.zeros(len(rp))
-    Oracle.lib().orc_group_pair_costs(simmeasure, S, ncp, L, D, len(tx), _p(tx), _p(fields), _p(rot), _p(labels), _p(sp), float(range_), _p(pairs),
-                                      len(rp), _p(rp), _p(la), _p(lb), _p(out), nthreads)
+    mask = None if mask is None else _f64(mask).reshape(-1)      # cost mask on the template (DiscreteGroupCostFunction.cpp:77)
+    Oracle.lib().orc_group_pair_costs_masked(simmeasure, S, ncp, L, D, len(tx), _p(tx), _p(fields), _p(rot), _p(labels), _p(sp), float(range_), _p(pairs),
+                                             len(rp), _p(rp), _p(la), _p(lb), _p(mask), _p(out), nthreads)
     return out
 
 
@@ -593,6 +595,10 @@ class RefMR:
             L.refmr_pairwise_reg.argtypes = [_i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _d, _d, _d, _i, _vp, _vp, _vp, _vp]
             L.refmr_group_pair_costs.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _d, _i, _vp,
                                                  _i, _vp, _vp, _vp, _vp, _vp, _i]
+            if hasattr(L, "refmr_group_pair_costs_masked"):
+                L.refmr_group_pair_costs_masked.restype = _i
+                L.refmr_group_pair_costs_masked.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _d, _i, _vp,
+                                                            _i, _vp, _vp, _vp, _vp, _vp, _vp, _i]
             L.refmr_group_triplet_costs.argtypes = [_i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _d, _d, _d, _d, _d, _i, _vp, _vp, _vp, _vp, _vp]
             L.refmr_label_sets.argtypes = [_i, _d, _vp, _vp, _i, _vp, _vp]
             if hasattr(L, "refmr_rigid"):
@@ -678,15 +684,17 @@ def refmr_pairwise_reg(cp_xyz, cp_tri, rot, labels, pairs, lambda_, rexp, mvdmax
 
 
 def refmr_group_pair_costs(simmeasure, data_xyz, tri, feat, labels, centre, tpl_xyz, tpl_tri, ncp, rot, spacings, range_, pairs, req_pair, req_la, req_lb,
-                           want_fields=False, nthreads=8):
+                           want_fields=False, nthreads=8, mask=None):
     xyz, tri, feat, labels, centre = _f64(data_xyz), _i32(tri), _f64(feat), _f64(labels), _f64(centre)
     tx, tt, rot, sp, pairs = _f64(tpl_xyz), _i32(tpl_tri), _f64(rot), _f64(spacings).reshape(-1), _i32(pairs)
     rp, la, lb = _i32(req_pair), _i32(req_la), _i32(req_lb)
     S, nv, D, L = xyz.shape[0], xyz.shape[1], feat.shape[1], len(labels)
     out = np.zeros(len(rp))
     fields = np.full((S, L, D, len(tx)), np.nan) if want_fields else None
-    if RefMR.lib().refmr_group_pair_costs(simmeasure, S, nv, _p(xyz), len(tri), _p(tri), D, _p(feat), L, _p(labels), _p(centre), len(tx), _p(tx), len(tt), _p(tt),
-                                          ncp, _p(rot), _p(sp), float(range_), len(pairs), _p(pairs), len(rp), _p(rp), _p(la), _p(lb), _p(out), _p(fields), nthreads):
+    mask = None if mask is None else _f64(mask).reshape(-1)
+    if RefMR.lib().refmr_group_pair_costs_masked(simmeasure, S, nv, _p(xyz), len(tri), _p(tri), D, _p(feat), L, _p(labels), _p(centre), len(tx), _p(tx),
+                                                 len(tt), _p(tt), ncp, _p(rot), _p(sp), float(range_), len(pairs), _p(pairs), len(rp), _p(rp), _p(la),
+                                                 _p(lb), _p(mask), _p(out), _p(fields), nthreads):
         raise RuntimeError("reference group pair costs failed")
     return (out, fields) if want_fields else out
 

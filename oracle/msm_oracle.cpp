@@ -1060,6 +1060,14 @@ int orc_group_fields(int S, int nv, const double* data_xyz /*[S][nv][3]*/, int n
 int orc_group_pair_costs(int simmeasure, int S, int ncp, int L, int D, int n_tpl, const double* tpl_xyz, const double* fields,
                          const double* rot, const double* labels, const double* spacings, double range, const int* pairs,
                          int n, const int* req_pair, const int* req_la, const int* req_lb, double* out, int nthreads) {
+    return orc_group_pair_costs_masked(simmeasure, S, ncp, L, D, n_tpl, tpl_xyz, fields, rot, labels, spacings, range, pairs, n, req_pair, req_la,
+                                       req_lb, nullptr, out, nthreads);
+}
+
+// with a cost mask (DiscreteGroupCostFunction.cpp:77): weight of a common template vertex = |mask[vertex]|; mask == NULL: unit weights
+int orc_group_pair_costs_masked(int simmeasure, int S, int ncp, int L, int D, int n_tpl, const double* tpl_xyz, const double* fields,
+                                const double* rot, const double* labels, const double* spacings, double range, const int* pairs,
+                                int n, const int* req_pair, const int* req_la, const int* req_lb, const double* mask, double* out, int nthreads) {
     #pragma omp parallel for num_threads(nthreads > 0 ? nthreads : 1)
     for (int r = 0; r < n; ++r) {
         const int nodes[2] = {pairs[2 * req_pair[r]], pairs[2 * req_pair[r] + 1]};
@@ -1078,6 +1086,7 @@ int orc_group_pair_costs(int simmeasure, int S, int ncp, int L, int D, int n_tpl
         if (n_c == 0) { out[r] = std::numeric_limits<double>::quiet_NaN(); continue; }   // the reference dereferences an empty vector here
         const int sa = nodes[0] / ncp, sb = nodes[1] / ncp;
         std::vector<double> a(n_c), b(n_c), w(n_c, 1.0);
+        if (mask) for (int i = 0; i < n_c; ++i) w[i] = std::fabs(mask[common[i]]);
         double cost = 0.0;
         for (int d = 0; d < D; ++d) {
             const double* fa = fields + (((size_t)sa * L + lab[0]) * D + d) * n_tpl;

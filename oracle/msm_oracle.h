@@ -120,6 +120,9 @@ int orc_group_fields(int S, int nv, const double* data_xyz, int nt, const int* t
 int orc_group_pair_costs(int simmeasure, int S, int ncp, int L, int D, int n_tpl, const double* tpl_xyz, const double* fields,
                          const double* rot, const double* labels, const double* spacings, double range, const int* pairs,
                          int n, const int* req_pair, const int* req_la, const int* req_lb, double* out, int nthreads);
+int orc_group_pair_costs_masked(int simmeasure, int S, int ncp, int L, int D, int n_tpl, const double* tpl_xyz, const double* fields,
+                         const double* rot, const double* labels, const double* spacings, double range, const int* pairs,
+                         int n, const int* req_pair, const int* req_la, const int* req_lb, const double* mask, double* out, int nthreads);
 
 /* RIGID / AFFINE level (rigid_costfunction.cpp:32-236): initialise + cost at zero rotation + run; same outputs as
  * oracle/ref_meshreg_driver.cpp: refmr_rigid. src_feat [D][nv_s], ref_feat [D][nv_t]. Returns the number of neighbour entries. */

@@ -214,10 +214,26 @@ int refmr_pairwise_reg(int ncp, const double* cp_xyz, int ncp_tri, const int* cp
 // data_xyz [S][nv][3] (one data mesh per subject, shared faces), feat [S][D][nv], rot [S*ncp][9],
 // spacings [S][ncp], pairs [P][2] global node ids. fields_out (optional) [S][L][D][n_tpl] receives the resampled
 // values of every template vertex that is a member of at least one patch (others stay NaN-free: untouched).
+int refmr_group_pair_costs_masked(int simmeasure, int S, int nv, const double* data_xyz, int nt, const int* tri, int D, const double* feat,
+                                  int L, const double* labels, const double* centre, int n_tpl, const double* tpl_xyz, int nt_tpl, const int* tpl_tri,
+                                  int ncp, const double* rot, const double* spacings, double range, int P, const int* pairs,
+                                  int n, const int* req_pair, const int* req_la, const int* req_lb, const double* mask, double* out,
+                                  double* fields_out, int nthreads);
 int refmr_group_pair_costs(int simmeasure, int S, int nv, const double* data_xyz, int nt, const int* tri, int D, const double* feat,
                            int L, const double* labels, const double* centre, int n_tpl, const double* tpl_xyz, int nt_tpl, const int* tpl_tri,
                            int ncp, const double* rot, const double* spacings, double range, int P, const int* pairs,
                            int n, const int* req_pair, const int* req_la, const int* req_lb, double* out, double* fields_out, int nthreads) {
+    return refmr_group_pair_costs_masked(simmeasure, S, nv, data_xyz, nt, tri, D, feat, L, labels, centre, n_tpl, tpl_xyz, nt_tpl, tpl_tri, ncp, rot,
+                                         spacings, range, P, pairs, n, req_pair, req_la, req_lb, nullptr, out, fields_out, nthreads);
+}
+
+// the same with a cost mask installed like DiscreteGroupModel::Initialize does (`costfct->set_masks(mask)`, DiscreteGroupModel.cpp:164):
+// mask [n_tpl] = channel 0 of a mask mesh on the template
+int refmr_group_pair_costs_masked(int simmeasure, int S, int nv, const double* data_xyz, int nt, const int* tri, int D, const double* feat,
+                                  int L, const double* labels, const double* centre, int n_tpl, const double* tpl_xyz, int nt_tpl, const int* tpl_tri,
+                                  int ncp, const double* rot, const double* spacings, double range, int P, const int* pairs,
+                                  int n, const int* req_pair, const int* req_la, const int* req_lb, const double* mask, double* out,
+                                  double* fields_out, int nthreads) {
     try {
         DiscreteGroupModel model;
         model._nthreads = nthreads;
@@ -249,6 +265,12 @@ int refmr_group_pair_costs(int simmeasure, int S, int nv, const double* data_xyz
         cf->m_num_labels = L;
         std::vector<int> pr(pairs, pairs + 2 * (size_t)P);
         cf->setPairs(pr.data());
+        if (mask) {
+            Mesh mm = model.target_space;
+            mm.initialize_pvalues(1);
+            for (int p = 0; p < n_tpl; ++p) mm.set_pvalue(p, mask[p]);
+            model.costfct->set_masks(mm);
+        }
         if (fields_out)
             for (int s = 0; s < S; ++s)
                 for (int k = 0; k < ncp; ++k)

@@ -70,6 +70,16 @@ def group_setup(S=3, cp_level=2, data_level=4, tpl_level=4, D=2):
 
 
 
+def group_mask(g):
+    """A cost mask on the template (`set_masks`, DiscreteGroupModel.cpp:164): smooth signed values, a zero band (weight 0 vertices)
+    and a region of exact ones. The cost function uses std::abs of it (DiscreteGroupCostFunction.cpp:77)."""
+    t = g["tpl"] / 100.0
+    m = np.sin(3.0 * t[:, 0]) * np.cos(2.0 * t[:, 1]) + 0.3 * t[:, 2]
+    m[np.abs(m) < 0.15] = 0.0
+    m[m > 0.9] = 1.0
+    return np.ascontiguousarray(m)
+
+
 def golden_group_glue(O, g, n=800):
     """Host glue of DiscreteGroupModel for a group case: rotations (get_rotations, cpp:76-86), spacings (get_spacings, 123-145),
     pairs (estimate_pairs, 37-55: partner = nearest control point of subject B) and a seeded request list."""

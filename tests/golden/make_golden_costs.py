@@ -10,7 +10,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from cost_cases import GOLDEN_CP as CP, GOLDEN_DATA as DATA, cost_setup, golden_digest as digest, golden_group_glue, group_setup, group_triplet_case, triplet_setup  # noqa: E402
+from cost_cases import GOLDEN_CP as CP, GOLDEN_DATA as DATA, cost_setup, golden_digest as digest, golden_group_glue, group_mask, group_setup, group_triplet_case, triplet_setup  # noqa: E402
 from newmsm_b200 import synth  # noqa: E402
 from oracle import bindings as B  # noqa: E402
 
@@ -53,6 +53,8 @@ def main():
         c, fields = B.refmr_group_pair_costs(sim, g["data"], g["dtri"], g["feat"], g["labels"], g["centre"], g["tpl"], g["tpl_tri"], ncp, rot, spacings, 1.0,
                                              pairs, rp, la, lb, want_fields=True)
         out[f"group_pair_s{sim}"] = c
+        out[f"group_pair_masked_s{sim}"] = B.refmr_group_pair_costs(sim, g["data"], g["dtri"], g["feat"], g["labels"], g["centre"], g["tpl"], g["tpl_tri"], ncp,
+                                                                    rot, spacings, 1.0, pairs, rp, la, lb, mask=group_mask(g))
     out["group_fields"] = fields          # NaN where no patch of any (CP, label) contains the template vertex
     orig, trip, rot_t, (rt, ta, tb, tc) = group_triplet_case(B, g)
     out["group_triplet"] = B.refmr_group_triplet_costs(g["cps"], orig, g["cp_tri"], rot_t, g["labels"], trip, 0.05, 0.4, 1.6, 2.0, 2.0, rt, ta, tb, tc)

@@ -44,6 +44,7 @@ def read_asc(path):
 
 
 GROUP = False   # --group: the gMSM driver (src/newmsm.cpp:14-28)
+MASK = False    # --mask: groupwise run with a cost mask (src/newmsm.cpp:25, DiscreteGroupModel.cpp:164)
 
 
 def run(binary, case, conf, out, threads, trace, extra_env=None):
@@ -53,6 +54,8 @@ def run(binary, case, conf, out, threads, trace, extra_env=None):
     if GROUP:
         cmd = [binary, "--groupwise", "--meshes=" + os.path.join(case, "meshes.txt"), "--data=" + os.path.join(case, "data.txt"),
                "--template=" + os.path.join(case, "template.asc"), "--conf=" + conf, "--out=" + out + "/"]
+        if MASK:
+            cmd.append("--mask=" + os.path.join(case, "mask.txt"))
     else:
         cmd = [binary, "--inmesh=" + os.path.join(case, "sphere.asc"), "--refmesh=" + os.path.join(case, "sphere.asc"),
                "--indata=" + os.path.join(case, "indata.txt"), "--refdata=" + os.path.join(case, "refdata.txt"),
@@ -87,6 +90,7 @@ def main():
     ap.add_argument("--disable", default="", help="MSMGPU_DISABLE value for the GPU run (cost, resample): A/B isolation of the hooks")
     ap.add_argument("--verify", action="store_true", help="MSMGPU_VERIFY=1: the hooks also run the reference CPU code in-process and compare")
     ap.add_argument("--out", default="")
+    ap.add_argument("--mask", action="store_true", help="groupwise only: run with the case's cost mask (newmsm --mask)")
     ap.add_argument("--devices", type=int, default=1, help="MSMGPU_DEVICES for the GPU run (groupwise: subjects and pair blocks sharded over this many GPUs)")
     ap.add_argument("--skip-gpu", action="store_true", help="CPU arms only (e.g. to record the single-thread trace on a machine without a GPU)")
     ap.add_argument("--gpu-trace-out", default="", help="keep the GPU run's trace here")
@@ -94,8 +98,9 @@ def main():
     ap.add_argument("--cpu-trace-in", default="", help="compare with this recorded single-thread CPU trace instead of running that arm "
                                                          "(the case is seeded, so the inputs are identical)")
     a = ap.parse_args()
-    global GROUP
+    global GROUP, MASK
     GROUP = a.group > 0
+    MASK = bool(a.mask)
     work = tempfile.mkdtemp(prefix="newmsm_case_")
     subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_newmsm_case.py"), "--out", work, "--level", str(a.level), "--D", str(a.D),
                     "--levels-drop", str(a.levels_drop), "--it-scale", str(a.it_scale), "--group", str(a.group)], check=True, stdout=subprocess.DEVNULL)

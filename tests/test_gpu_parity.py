@@ -524,6 +524,45 @@ def test_group_fields_and_pair_costs(R, oracle_built, sim):
     assert np.nanmax(np.abs(z)) < 1e-12
 
 
+@pytest.mark.parametrize("D", [1, 3, 12])
+def test_group_pair_costs_channel_counts_and_mask(R, oracle_built, D, monkeypatch):
+    """The pair-cost kernels (thread per request for D <= 8 in chunks of 1 / 2 / 4 channels, warp per request above) against the oracle,
+    without and with a cost mask (set_masks: weights |mask|, DiscreteGroupCostFunction.cpp:77), both similarity measures; the two
+    kernels agree bit for bit where both apply."""
+    from newmsm_b200 import group_cost as GC
+    from cost_cases import group_mask
+    g = group_setup(S=3, cp_level=2, data_level=3, tpl_level=4, D=D)
+    ncp = g["cps"].shape[1]
+    mask = group_mask(g)
+    rng = np.random.default_rng(11)
+    ref_fields = None
+    for sim in (2, 1):
+        M = GC.DiscreteGroupModel(R.Mesh(g["tpl"], g["tpl_tri"]), simmeasure=sim)
+        spacings = M.get_spacings(g["cps"], g["cp_tri"])
+        rot = M.get_rotations(g["centre"], g["cps"])
+        pairs = M.estimate_pairs(g["cps"], g["cp_tri"])
+        fields = M.get_patch_data(g["data"], g["dtri"], g["feat"], g["labels"], g["centre"], rot, spacings, 1.0)
+        if ref_fields is None:
+            ref_fields = oracle_built.oracle_group_fields(g["data"], g["dtri"], g["feat"], g["labels"], g["centre"], g["tpl"], g["tpl_tri"])
+        assert np.array_equal(fields.cpu().numpy().transpose(0, 1, 3, 2), ref_fields)
+        n, L = 2500, len(g["labels"])
+        rp, la, lb = rng.integers(0, len(pairs), n), rng.integers(0, L, n), rng.integers(0, L, n)
+        for mk in (None, mask):
+            M.set_masks(mk)
+            ref = oracle_built.oracle_group_pair_costs(sim, ncp, g["tpl"], ref_fields, rot, g["labels"], spacings, 1.0, pairs, rp, la, lb, mask=mk)
+            got = {}
+            for kern in ("thread", "warp"):
+                monkeypatch.setenv("MSMGPU_PAIR_KERNEL", kern)
+                got[kern] = M.computePairwiseCostList(pairs, rp, la, lb)
+            monkeypatch.delenv("MSMGPU_PAIR_KERNEL")
+            dflt = M.computePairwiseCostList(pairs, rp, la, lb)
+            ok = ~np.isnan(ref)
+            assert ok.mean() > 0.9
+            for v in (got["thread"], got["warp"], dflt):
+                assert np.array_equal(np.isnan(v), np.isnan(ref)) and np.array_equal(v[ok], ref[ok])
+        M.close()
+
+
 # ---------------------------------------------------------------------------------------------
 # CUDA path against the outputs of the reference's OWN cost-function classes (tests/golden/costs.npz,
 # generated by tests/golden/make_golden_costs.py from oracle/_ref/libref_newmeshreg.so)
@@ -605,6 +644,9 @@ def test_group_costs_vs_reference_golden(R, oracle_built):
         got = M.computePairwiseCostList(pairs, rp, la, lb)
         ok = ~np.isnan(got)
         assert ok.mean() > 0.9 and np.array_equal(got[ok], g[f"group_pair_s{sim}"][ok])
+        from cost_cases import group_mask
+        M.set_masks(group_mask(c))                     # the reference's own class with set_masks (DiscreteGroupModel.cpp:164)
+        assert np.array_equal(M.computePairwiseCostList(pairs, rp, la, lb)[ok], g[f"group_pair_masked_s{sim}"][ok])
 
 
 def test_group_triplet_nan_energy_propagates(R, oracle_built):

@@ -55,14 +55,17 @@ def test_affine_level_costs_match_reference_in_process():
     assert n >= 8 and bad == 0, line[0]
 
 
-def test_gmsm_costs_match_reference_in_process():
+@pytest.mark.parametrize("mask", [False, True])
+def test_gmsm_costs_match_reference_in_process(mask):
     """MSMGPU_VERIFY=1: inside the groupwise run every pair / triplet cost Fusion::optimize asks for is ALSO evaluated by the reference's own
-    computePairwiseCost / computeTripletCost on the reference's own patch maps, in the same process, and compared bit for bit."""
+    computePairwiseCost / computeTripletCost on the reference's own patch maps, in the same process, and compared bit for bit.
+    mask=True: `newmsm --mask` (cost mask on the template, DiscreteGroupModel.cpp:164, DiscreteGroupCostFunction.cpp:77) on the device path."""
     import re
     if not all(os.path.exists(b) for b in BINS):
         pytest.skip("integration/_build/newmsm_gpu not built (needs /root/reference at build time)")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "newmsm_e2e.py"), "--level", "4", "--config", "gMSM", "--D", "2", "--threads", "4",
-                          "--skip-cpu", "--verify", "--levels-drop", "2", "--it-scale", "0.25", "--group", "3"], capture_output=True, text=True, timeout=1500)
+                          "--skip-cpu", "--verify", "--levels-drop", "2", "--it-scale", "0.25", "--group", "3"] + (["--mask"] if mask else []),
+                         capture_output=True, text=True, timeout=1500)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     res = json.loads(out.stdout.strip().splitlines()[-1])
     line = [ln for ln in res["gpu_split"] if "group pair costs" in ln]

@@ -130,6 +130,10 @@ def test_group_costs_golden(oracle_built):
         got = oracle_built.oracle_group_pair_costs(sim, c["cps"].shape[1], c["tpl"], fields, rot, c["labels"], spacings, 1.0, pairs, rp, la, lb)
         ok = ~np.isnan(got)          # empty intersections: undefined behaviour in the reference, not compared
         assert ok.mean() > 0.9 and np.array_equal(got[ok], g[f"group_pair_s{sim}"][ok])
+        from cost_cases import group_mask
+        got_m = oracle_built.oracle_group_pair_costs(sim, c["cps"].shape[1], c["tpl"], fields, rot, c["labels"], spacings, 1.0, pairs, rp, la, lb,
+                                                     mask=group_mask(c))
+        assert np.array_equal(got_m[ok], g[f"group_pair_masked_s{sim}"][ok])
 
 
 def test_rigid_level_golden(oracle_built):

@@ -6,7 +6,7 @@ Bit-exact unless a tolerance is written next to the assert. Skipped when oracle/
 import numpy as np
 import pytest
 
-from cost_cases import cost_setup, group_setup, group_triplet_case, triplet_setup
+from cost_cases import cost_setup, group_mask, group_setup, group_triplet_case, triplet_setup
 
 
 @pytest.fixture(scope="module")
@@ -125,6 +125,14 @@ def test_group_patch_data_and_pair_costs(O, sim):
     ok = ~np.isnan(got)
     assert ok.mean() > 0.9
     assert np.array_equal(got[ok], ref[ok])
+    # with a cost mask (set_masks, DiscreteGroupModel.cpp:164): common vertices weighted by |mask| (DiscreteGroupCostFunction.cpp:77)
+    mask = group_mask(g)
+    ref_m = O.refmr_group_pair_costs(sim, g["data"], g["dtri"], g["feat"], g["labels"], g["centre"], g["tpl"], g["tpl_tri"], ncp, rot, spacings, 1.0,
+                                     pairs, rp, la, lb, mask=mask)
+    got_m = O.oracle_group_pair_costs(sim, ncp, g["tpl"], fields, rot, g["labels"], spacings, 1.0, pairs, rp, la, lb, mask=mask)
+    assert np.array_equal(np.isnan(got_m), np.isnan(got))
+    assert np.array_equal(got_m[ok], ref_m[ok])
+    assert (got_m[ok] != got[ok]).mean() > 0.5           # the mask matters
 
 
 @pytest.mark.parametrize("kexp,rexp", [(2.0, 2.0), (1.5, 1.3)])

@@ -100,6 +100,11 @@ def main():
             np.savetxt(os.path.join(a.out, f"subject{s_}.txt"), f.T, fmt="%.9g")
             meshes.append(os.path.join(a.out, f"subject{s_}.asc"))
             datas.append(os.path.join(a.out, f"subject{s_}.txt"))
+        # a cost mask on the template (newmsm --mask, groupwise mode only: msmOptions.h:85): signed smooth values with a zero band
+        t = tpl / 100.0
+        mk = np.sin(3.0 * t[:, 0]) * np.cos(2.0 * t[:, 1]) + 0.3 * t[:, 2]
+        mk[np.abs(mk) < 0.15] = 0.0
+        np.savetxt(os.path.join(a.out, "mask.txt"), mk[:, None], fmt="%.9g")
         open(os.path.join(a.out, "meshes.txt"), "w").write("\n".join(meshes) + "\n")
         open(os.path.join(a.out, "data.txt"), "w").write("\n".join(datas) + "\n")
     print("wrote", a.out)
