@@ -624,8 +624,9 @@ def run_gmsm(a, torch, dist, rank, world, local):
             sample.append(c[::997].ravel().copy())
         sync(); t2 = time.perf_counter()
         tsum = 0.0
+        M.reset_triplet_state(cps, orig, rot, labels, trip)      # once per iteration, like reset_CPgrid / estimate_triplets
         for l in range(1, Lb):
-            tsum += float(M.computeTripletCostsForLabel(cps, orig, rot, labels, trip, labeling, l, 0.2).sum())
+            tsum += float(M.computeTripletCostsForLabel(None, None, None, None, None, labeling, l, 0.2).sum())
         sync(); t3 = time.perf_counter()
         out = {"fields_s": tmax(t1 - t0), "pair_sweep_s": tmax(t2 - t1), "triplet_sweep_s": tmax(t3 - t2), "iteration_s": tmax(t3 - t0)}
     # the collective alone: all-gather of the field shards, CUDA events on this rank's stream, max over ranks
@@ -650,7 +651,7 @@ def run_gmsm(a, torch, dist, rank, world, local):
     if world > 1:
         lab_chk = 7
         got_pairs = M.computePairwiseCostsForLabel(pairs, labeling, lab_chk).copy()
-        got_trip = M.computeTripletCostsForLabel(cps, orig, rot, labels, trip, labeling, lab_chk, 0.2)
+        got_trip = M.computeTripletCostsForLabel(None, None, None, None, None, labeling, lab_chk, 0.2)   # the resident plan, sharded
         # every rank holds the gathered fields; only rank 0 re-computes
         if rank == 0:
             M1 = GC.DiscreteGroupModel(R.Mesh(tpl, tpl_tri, ctx=ctx), simmeasure=2, dist=None)
@@ -675,11 +676,18 @@ def run_gmsm(a, torch, dist, rank, world, local):
                          "bytes_total": ag_bytes, "ms": ag_ms,
                          "bus_GBs": (ag_bytes * (world - 1) / world / (ag_ms * 1e-3) / 1e9) if ag_ms else None},
            "sharded_equals_unsharded_bitwise": same,
-           "limiter_note": "fields: host libm rotation matrices + per-rank build; pairs: device-bound (k_group_pair_costs); triplets: the three pow() per cost "
-                           "are finished on the host libm (bit-exactness, DESIGN §4.8) with cpu_count / ranks OpenMP threads per rank",
+           "limiter_note": "fields: host libm rotation matrices + per-rank build; pairs: device-bound (k_group_pair_costs_thread); triplets: strain + the three "
+                           "pow() per cost on the device (glibc's algorithm with the host library's tables, csrc/hostpow.cuh; device_pow_enabled below), "
+                           "bound by the D2H copy of the [T][8] table per label phase",
+           "device_pow_enabled": bool(capi_device_pow()),
            "gpu_launches": int(capi_launches() - launches0), "timing": "wall clock between device synchronisations + barriers, max over ranks; second of two iterations"}
     M.close()      # the context is released with the last object that holds it (meshes / trees keep a reference)
     return res
+
+
+def capi_device_pow():
+    from newmsm_b200 import capi
+    return int(capi.lib().msmgpu_device_pow_enabled())
 
 
 def capi_launches():

@@ -300,6 +300,14 @@ void msmgpu_rigid_destroy(msmgpu_rigid* r);
  * (the reference restores it, cpp:139). exp() of the weights and the sequential sums run on the host libm inside this call. */
 msmgpu_status msmgpu_rigid_cost(msmgpu_rigid* r, const double* src_xyz, double dw1, double dw2, double dw3, double* cost);
 
+/* ---- pow() of the host C library on the device (csrc/hostpow.cuh) ----
+ * The three std::pow calls per triplet cost (reg_tools.cpp:596-597, DiscreteCostFunction.cpp:187, DiscreteGroupCostFunction.cpp:51) are
+ * evaluated on the device with glibc's own algorithm and the tables of the libm mapped into the process, after a host-side self-test
+ * against std::pow. Returns 1 when that path is active, 0 when the costs are finished with the host libm (MSMGPU_DEVICE_POW=0 forces 0). */
+int msmgpu_device_pow_enabled(void);
+/* test hook: out[i] = pow(x[i], y[i]) evaluated on the device (compared with the host's std::pow by the tests) */
+msmgpu_status msmgpu_debug_device_pow(msmgpu_ctx* ctx, int n, const double* x, const double* y, double* out);
+
 /* ---- groupwise registration (gMSM): msm-newmeshreg/src/DiscreteGroupModel.cpp, DiscreteGroupCostFunction.cpp ---- */
 typedef struct msmgpu_group msmgpu_group;
 
@@ -343,6 +351,15 @@ msmgpu_status msmgpu_group_triplet_costs(msmgpu_ctx* ctx, int n_nodes, const dou
 msmgpu_status msmgpu_group_triplet_batch(msmgpu_ctx* ctx, int n_nodes, const double* cp_xyz, const double* orig_xyz, const double* rotations, int L,
                                          const double* labels, int ntrip, const int32_t* triplets, const msmgpu_reg_params* prm, double subcorr, int fixnan,
                                          const int32_t* labeling, int label, double* out);
+/* the same with the per-iteration arrays (control grids, rotations, labels, triplets) resident on the device: a label phase of
+ * Fusion::optimize then only sends the labeling. _batch evaluates the triplets [first_triplet, first_triplet + n_triplets)
+ * (any block: sharding), out [n_triplets][8]. */
+typedef struct msmgpu_triplet_plan msmgpu_triplet_plan;
+msmgpu_status msmgpu_triplet_plan_create(msmgpu_ctx* ctx, int n_nodes, const double* cp_xyz, const double* orig_xyz, const double* rotations, int L,
+                                         const double* labels, int ntrip, const int32_t* triplets, msmgpu_triplet_plan** out);
+void msmgpu_triplet_plan_destroy(msmgpu_triplet_plan* p);
+msmgpu_status msmgpu_triplet_plan_batch(msmgpu_triplet_plan* p, const msmgpu_reg_params* prm, double subcorr, int fixnan, int first_triplet,
+                                        int n_triplets, const int32_t* labeling, int label, double* out);
 
 #ifdef __cplusplus
 }

@@ -57,6 +57,7 @@ class GroupBinding {
         double* batch_out = nullptr;   // [pairs of this device's block][4]: result of one 4-combination batch before it goes to the host
         size_t batch_bytes = 0;
         msmgpu_group* group = nullptr;
+        msmgpu_triplet_plan* plan = nullptr;   // control grids, rotations, labels and triplets of the iteration, resident for the label phases
     };
     std::vector<Device> dev_;
 
@@ -107,6 +108,8 @@ class GroupBinding {
     void drop_iteration_state() {
         for (Device& d : dev_) {
             if (d.group) msmgpu_group_destroy(d.group);
+            if (d.plan) msmgpu_triplet_plan_destroy(d.plan);
+            d.plan = nullptr;
             if (d.tpl_tree) msmgpu_octree_destroy(d.tpl_tree);
             if (d.tpl) msmgpu_mesh_destroy(d.tpl);
             d.group = nullptr; d.tpl_tree = nullptr; d.tpl = nullptr;
@@ -220,9 +223,15 @@ class GroupBinding {
             detail::check(msmgpu_group_triplet_costs(ctx, n_nodes, cps_.data(), orig_.data(), rot_.data(), L_, labels_.data(), T_, trip_.data(), &prm,
                                                      cf_->subcorr, cf_->fixnan ? 1 : 0, T_, rt.data(), la.data(), lb.data(), lc.data(), tb->val.data()));
             group_timers().triplet_costs += T_;
-        } else {
-            detail::check(msmgpu_group_triplet_batch(ctx, n_nodes, cps_.data(), orig_.data(), rot_.data(), L_, labels_.data(), T_, trip_.data(), &prm,
-                                                     cf_->subcorr, cf_->fixnan ? 1 : 0, tb->snap.data(), label, tb->val.data()));
+        } else {   // the iteration's arrays are resident on every device (get_patch_data); triplet blocks sharded like the pair blocks
+            const int n = (int)dev_.size();
+            on_devices([&](int d) {
+                int b, e;
+                shard(T_, d, n, b, e);
+                if (e > b)
+                    detail::check(msmgpu_triplet_plan_batch(dev_[d].plan, &prm, cf_->subcorr, cf_->fixnan ? 1 : 0, b, e - b, tb->snap.data(), label,
+                                                            tb->val.data() + 8 * (size_t)b));
+            });
             group_timers().triplet_costs += 8LL * T_;
         }
         group_timers().triplet_batches += omp_get_wtime() - t0;
@@ -395,6 +404,10 @@ public:
                 pc[0] = c.X; pc[1] = c.Y; pc[2] = c.Z;
                 po[0] = o.X; po[1] = o.Y; po[2] = o.Z;
             }
+        on_devices([&](int d) {
+            detail::check(msmgpu_triplet_plan_create(dev_[d].ctx, n_nodes, cps_.data(), orig_.data(), rot_.data(), L_, labels_.data(), T_, trip_.data(),
+                                                     &dev_[d].plan));
+        });
         active_ = true;
         group_timers().fields += omp_get_wtime() - t0;
         group_timers().n_iterations++;

@@ -110,6 +110,8 @@ _SIGNATURES = {
     "msmgpu_costfn_unary_table": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     "msmgpu_costfn_unary_table_dev": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     "msmgpu_weights_apply_batch_f64_dev": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
+    "msmgpu_device_pow_enabled": (_i, []),
+    "msmgpu_debug_device_pow": (_i, [_vp, _i, _vp, _vp, _vp]),
     "msmgpu_group_fields": (_i, [_vp, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "msmgpu_group_create": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _d, _pp]),
     "msmgpu_group_destroy": (None, [_vp]),
@@ -122,6 +124,9 @@ _SIGNATURES = {
     "msmgpu_costfn_triplet_costs": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "msmgpu_costfn_triplet_batch": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "msmgpu_group_triplet_costs": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _d, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "msmgpu_triplet_plan_create": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _pp]),
+    "msmgpu_triplet_plan_destroy": (None, [_vp]),
+    "msmgpu_triplet_plan_batch": (_i, [_vp, _vp, _d, _i, _i, _i, _vp, _i, _vp]),
     "msmgpu_group_triplet_batch": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _d, _i, _vp, _i, _vp]),
 }
 

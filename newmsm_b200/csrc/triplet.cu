@@ -16,6 +16,7 @@
 // on the target (query.cuh) and park (ids, weights) in the warp's shared-memory slice; similarity sums are the
 // reference's sequential FP64 sums (cost.cuh). Lane 0 evaluates the strain energy.
 #include "cost.cuh"
+#include "hostpow.cuh"
 
 #include <algorithm>
 
@@ -50,10 +51,11 @@ __host__ __device__ __forceinline__ double det3(const double* m) {
     return m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
 }
 
-// The three pow() calls of the path (reg_tools.cpp:596, DiscreteCostFunction.cpp:187) are evaluated with the HOST libm, like
-// estimate_rotation_matrix: glibc's pow(x, 2.0) is not always the correctly rounded x*x and CUDA's pow is not
-// glibc's, while the costs feed a discrete optimiser. The kernel stops at the pow arguments (R = major/minor stretch ratio,
-// J = area ratio); triplet_run() finishes W and the cost on the host with the reference's own expression order.
+// The three pow() calls of the path (reg_tools.cpp:596, DiscreteCostFunction.cpp:187): glibc's pow(x, 2.0) is not always the correctly
+// rounded x*x and CUDA's pow is not glibc's, while the costs feed a discrete optimiser. Default: the kernel evaluates them itself with
+// the host library's own algorithm and tables (hostpow.cuh: host_pow, enabled after a self-test against std::pow). Otherwise
+// (MSMGPU_DEVICE_POW=0, or a host library the self-test does not recognise) the kernel stops at the pow arguments (R = major/minor
+// stretch ratio, J = area ratio) and finish_on_host() completes W and the cost with the host libm in the reference's expression order.
 
 __device__ void triangle_strain_dev(const double* AA, const double* BB, double& R_out, double& J_out) {   // reg_tools.cpp:551-594
     const double c0 = AA[3] - AA[0], c1 = AA[4] - AA[1], c4 = AA[6] - AA[0], c5 = AA[7] - AA[1];
@@ -151,7 +153,79 @@ struct TripletArgs {
     double fold_value;        // cost of a folded triangle: FOLDING * lambda (cpp:152) or FOLDING (DiscreteGroupCostFunction.cpp:40)
     double* out;              // [n]
     int* err;
+    int dev_pow;              // 1: finish the cost here with host_pow (aux unused), 0: write aux, the host finishes
+    int group;                // 1: gMSM form `subcorr * lambda * W^rexp` with FIX_NAN (DiscreteGroupCostFunction.cpp:49-51), 0: `likelihood + lambda * W^rexp`
+    int fixnan;
+    double subcorr;
+    PowTables pw;
 };
+
+// reg_tools.cpp:596-597 + DiscreteCostFunction.cpp:187 / DiscreteGroupCostFunction.cpp:49-51, the reference's expression order
+__host__ __device__ __forceinline__ double finish_cost(double likelihood, double R, double J, double MU, double KAPPA, double k_exp, double rexp,
+                                                       double lambda, int group, int fixnan, double subcorr, const PowTables* pw) {
+#ifdef __CUDA_ARCH__
+    const double Rshared = host_pow(R, k_exp, *pw), Jshared = host_pow(J, k_exp, *pw);
+#else
+    const double Rshared = pw ? host_pow(R, k_exp, *pw) : std::pow(R, k_exp), Jshared = pw ? host_pow(J, k_exp, *pw) : std::pow(J, k_exp);
+#endif
+    const double W = 0.5 * (MU * (Rshared + 1.0 / Rshared - 2) + KAPPA * (Jshared + 1.0 / Jshared - 2));
+    if (group) {
+        if (fixnan && W != W) return 1e7;       // FIX_NAN
+#ifdef __CUDA_ARCH__
+        return subcorr * lambda * host_pow(W, rexp, *pw);
+#else
+        return subcorr * lambda * (pw ? host_pow(W, rexp, *pw) : std::pow(W, rexp));
+#endif
+    }
+#ifdef __CUDA_ARCH__
+    return likelihood + lambda * host_pow(W, rexp, *pw);
+#else
+    return likelihood + lambda * (pw ? host_pow(W, rexp, *pw) : std::pow(W, rexp));
+#endif
+}
+
+__device__ __forceinline__ void triplet_labels(const TripletArgs& a, int r, int& t, int* lab) {
+    if (a.req_t) {
+        t = a.req_t[r];
+        lab[0] = a.req_la[r]; lab[1] = a.req_lb[r]; lab[2] = a.req_lc[r];
+    } else {   // Fusion.h:181-196: request r = 8 * triplet + combination
+        t = r >> 3;
+        const int combo = r & 7;
+        for (int k = 0; k < 3; ++k) lab[k] = (combo >> (2 - k)) & 1 ? a.label : a.labeling[a.triplets[3 * (size_t)t + k]];
+    }
+}
+
+// strain-only requests (no HO likelihood: the Univariate / Multivariate / Patchwise unary kinds and the gMSM triplet term): one THREAD per
+// request -- a warp per request leaves 31 lanes idle here
+__global__ void __launch_bounds__(128) k_strain_costs(TripletArgs a) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.n) return;
+    int t, lab[3];
+    triplet_labels(a, r, t, lab);
+    V3 def[3], cur[3], org[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int id = a.triplets[3 * (size_t)t + k];
+        const double* lb = a.labels + 3 * (size_t)lab[k];
+        def[k] = mat_apply(a.rot + 9 * (size_t)id, V3{lb[0], lb[1], lb[2]});
+        cur[k] = load_pt(a.cp_xyz, id);
+        org[k] = load_pt(a.orig_xyz, id);
+    }
+    if (vdot(tri_normal(def[0], def[1], def[2]), tri_normal(cur[0], cur[1], cur[2])) < 0.0) {
+        a.out[r] = a.fold_value;
+        if (!a.dev_pow) { a.aux[2 * (size_t)r] = 0.0; a.aux[2 * (size_t)r + 1] = -1.0; }
+        return;
+    }
+    double R, J;
+    triangular_strain_dev(org, def, R, J);
+    if (a.dev_pow) {
+        a.out[r] = finish_cost(0.0, R, J, a.mu, a.kappa, a.k_exp, a.rexp, a.lambda, a.group, a.fixnan, a.subcorr, &a.pw);
+    } else {
+        a.out[r] = 0.0;
+        a.aux[2 * (size_t)r] = R;
+        a.aux[2 * (size_t)r + 1] = J;
+    }
+}
 
 constexpr int kTripWarps = 4;
 
@@ -169,14 +243,7 @@ __global__ void __launch_bounds__(kTripWarps * 32) k_triplet_costs(TripletArgs a
     int* s_idx = reinterpret_cast<int*>(s_sim + a.max_patch);
 
     int t, lab[3];
-    if (a.req_t) {
-        t = a.req_t[r];
-        lab[0] = a.req_la[r]; lab[1] = a.req_lb[r]; lab[2] = a.req_lc[r];
-    } else {
-        t = r >> 3;
-        const int combo = r & 7;
-        for (int k = 0; k < 3; ++k) lab[k] = (combo >> (2 - k)) & 1 ? a.label : a.labeling[a.triplets[3 * (size_t)t + k]];
-    }
+    triplet_labels(a, r, t, lab);
     V3 def[3], cur[3], org[3];
     int ids[3];
 #pragma unroll
@@ -189,7 +256,10 @@ __global__ void __launch_bounds__(kTripWarps * 32) k_triplet_costs(TripletArgs a
     }
     // only estimate the cost if it does not cause folding (cpp:152)
     if (vdot(tri_normal(def[0], def[1], def[2]), tri_normal(cur[0], cur[1], cur[2])) < 0.0) {
-        if (lane == 0) { a.out[r] = a.fold_value; a.aux[2 * (size_t)r] = 0.0; a.aux[2 * (size_t)r + 1] = -1.0; }   // J = -1: out[r] is final as is
+        if (lane == 0) {
+            a.out[r] = a.fold_value;
+            if (!a.dev_pow) { a.aux[2 * (size_t)r] = 0.0; a.aux[2 * (size_t)r + 1] = -1.0; }   // J = -1: out[r] is final as is
+        }
         return;
     }
     double likelihood = 0.0;
@@ -229,7 +299,11 @@ __global__ void __launch_bounds__(kTripWarps * 32) k_triplet_costs(TripletArgs a
             }
         }
         if (__any_sync(kFull, bad)) {
-            if (lane == 0) { a.out[r] = nan(""); a.aux[2 * (size_t)r] = 0.0; a.aux[2 * (size_t)r + 1] = -1.0; *a.err = 1; }
+            if (lane == 0) {
+                a.out[r] = nan("");
+                if (!a.dev_pow) { a.aux[2 * (size_t)r] = 0.0; a.aux[2 * (size_t)r + 1] = -1.0; }
+                *a.err = 1;
+            }
             return;
         }
         __syncwarp();
@@ -266,9 +340,13 @@ __global__ void __launch_bounds__(kTripWarps * 32) k_triplet_costs(TripletArgs a
     if (lane == 0) {   // regoption 2/3 (cpp:158-166), then cpp:187
         double R, J;
         triangular_strain_dev(org, def, R, J);
-        a.out[r] = likelihood;             // + lambda * pow(W(R, J), rexp), added by the host (see the note on pow above)
-        a.aux[2 * (size_t)r] = R;
-        a.aux[2 * (size_t)r + 1] = J;
+        if (a.dev_pow) {
+            a.out[r] = finish_cost(likelihood, R, J, a.mu, a.kappa, a.k_exp, a.rexp, a.lambda, a.group, a.fixnan, a.subcorr, &a.pw);
+        } else {
+            a.out[r] = likelihood;         // + lambda * pow(W(R, J), rexp), added by finish_on_host()
+            a.aux[2 * (size_t)r] = R;
+            a.aux[2 * (size_t)r + 1] = J;
+        }
     }
 }
 
@@ -287,6 +365,62 @@ static msmgpu_status up(DevBuf<T>& b, const T* host, size_t n, cudaStream_t s) {
     return MSMGPU_OK;
 }
 
+// the host finish of the path without device pow: reg_tools.cpp:596-597 and DiscreteCostFunction.cpp:187 with the host libm
+// (this translation unit is built with -ffp-contract=off)
+static void finish_on_host(int n, const double* aux, double* out, const msmgpu_reg_params* prm, int group, int fixnan, double subcorr) {
+    const double MU = prm->shear_modulus, KAPPA = prm->bulk_modulus, k_exp = prm->k_exponent, rexp = prm->exponent, lambda = prm->lambda;
+#pragma omp parallel for schedule(static) if (n > 4096)
+    for (int r = 0; r < n; ++r) {
+        const double R = aux[2 * (size_t)r], J = aux[2 * (size_t)r + 1];
+        if (J == -1.0) continue;                                // folded (or failed query): already final
+        out[r] = finish_cost(out[r], R, J, MU, KAPPA, k_exp, rexp, lambda, group, fixnan, subcorr, nullptr);
+    }
+}
+
+// launches the request kernel for `a` (everything but out / aux / err / pow set by the caller) and brings the costs to `out`
+static msmgpu_status run_requests(msmgpu_ctx* ctx, TripletArgs& a, bool ho, const msmgpu_reg_params* prm, double* out) {
+    cudaStream_t s = ctx->stream;
+    const int n = a.n;
+    const DevicePow& dp = device_pow(ctx->device);
+    a.dev_pow = dp.enabled ? 1 : 0;
+    a.pw = dp.t;
+    DevBuf<double> d_out, d_aux;
+    DevBuf<int> d_err;
+    MSM_CUDA(d_out.alloc((size_t)n, s));
+    if (!a.dev_pow) MSM_CUDA(d_aux.alloc(2 * (size_t)n, s));
+    MSM_CUDA(d_err.alloc(1, s));
+    MSM_CUDA(cudaMemsetAsync(d_err.p, 0, sizeof(int), s));
+    a.out = d_out.p; a.aux = d_aux.p; a.err = d_err.p;
+    if (!ho) {
+        k_strain_costs<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(a);
+        MSM_LAUNCH_CHECK();
+    } else {
+        const size_t slice = ((size_t)a.max_patch * (4 * sizeof(double) + 3 * sizeof(int)) + 15) & ~(size_t)15;
+        const size_t smem = slice * kTripWarps;
+        if (smem > 200 * 1024) return fail(MSMGPU_ERR_CAPACITY, "costfn_triplet: patch too large for shared memory");
+        switch (query_group_width()) {
+            case 2: MSM_TRY(launch_triplet_g<2>(a, smem, s)); break;
+            case 4: MSM_TRY(launch_triplet_g<4>(a, smem, s)); break;
+            case 8: MSM_TRY(launch_triplet_g<8>(a, smem, s)); break;
+            case 16: MSM_TRY(launch_triplet_g<16>(a, smem, s)); break;
+            case 32: MSM_TRY(launch_triplet_g<32>(a, smem, s)); break;
+            default: MSM_TRY(launch_triplet_g<1>(a, smem, s)); break;
+        }
+    }
+    int h_err = 0;
+    std::vector<double> aux;
+    MSM_CUDA(cudaMemcpyAsync(out, d_out.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (!a.dev_pow) {
+        aux.resize(2 * (size_t)n);
+        MSM_CUDA(cudaMemcpyAsync(aux.data(), d_aux.p, aux.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    MSM_CUDA(cudaMemcpyAsync(&h_err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MSM_CUDA(cudaStreamSynchronize(s));
+    if (h_err) return status_to_error(MSMGPU_ERR_NO_TRIANGLE);
+    if (!a.dev_pow) finish_on_host(n, aux.data(), out, prm, a.group, a.fixnan, a.subcorr);
+    return MSMGPU_OK;
+}
+
 static msmgpu_status triplet_run(msmgpu_costfn* c, int ntrip, const int32_t* triplets, int L, const double* labels, const double* rotations,
                                  const double* orig_cp_xyz, const msmgpu_reg_params* prm, int n, const int32_t* req_t, const int32_t* req_la,
                                  const int32_t* req_lb, const int32_t* req_lc, const int32_t* labeling, int label, double* out) {
@@ -299,8 +433,8 @@ static msmgpu_status triplet_run(msmgpu_costfn* c, int ntrip, const int32_t* tri
     if (ho && c->n_patch_rows != ntrip) return fail(MSMGPU_ERR_INVALID, "costfn_triplet: HO patches were built for a different CP-grid triangle count");
     MSM_CUDA(cudaSetDevice(c->ctx->device));
     cudaStream_t s = c->ctx->stream;
-    DevBuf<int> d_trip, d_rt, d_la, d_lb, d_lc, d_labeling, d_err;
-    DevBuf<double> d_labels, d_rot, d_orig, d_out;
+    DevBuf<int> d_trip, d_rt, d_la, d_lb, d_lc, d_labeling;
+    DevBuf<double> d_labels, d_rot, d_orig;
     MSM_TRY(up(d_trip, triplets, 3 * (size_t)ntrip, s));
     MSM_TRY(up(d_labels, labels, 3 * (size_t)L, s));
     MSM_TRY(up(d_rot, rotations, 9 * (size_t)c->ncp, s));
@@ -313,12 +447,7 @@ static msmgpu_status triplet_run(msmgpu_costfn* c, int ntrip, const int32_t* tri
     } else {
         MSM_TRY(up(d_labeling, labeling, (size_t)c->ncp, s));
     }
-    DevBuf<double> d_aux;
-    MSM_CUDA(d_out.alloc((size_t)n, s));
-    MSM_CUDA(d_aux.alloc(2 * (size_t)n, s));
-    MSM_CUDA(d_err.alloc(1, s));
-    MSM_CUDA(cudaMemsetAsync(d_err.p, 0, sizeof(int), s));
-    TripletArgs a;
+    TripletArgs a{};
     a.tree = c->tree->view();
     a.kind = c->kind; a.simmeasure = c->simmeasure; a.percentile = c->percentile; a.ncp = c->ncp; a.nsrc = c->nsrc; a.D = c->D; a.cfw_rows = c->cfw_rows; a.n = n;
     a.max_patch = ho ? std::max(c->max_patch, 1) : 1;
@@ -327,91 +456,68 @@ static msmgpu_status triplet_run(msmgpu_costfn* c, int ntrip, const int32_t* tri
     a.src_xyz = c->src_xyz.p; a.prow = c->prow.p; a.pmem = c->pmem.p; a.src_feat = c->src_feat.p; a.ref_feat = c->ref_feat.p;
     a.cfw = c->cfw.p; a.absw = c->absw.p;
     a.lambda = prm->lambda; a.mu = prm->shear_modulus; a.kappa = prm->bulk_modulus; a.k_exp = prm->k_exponent; a.rexp = prm->exponent;
-    a.out = d_out.p; a.aux = d_aux.p; a.err = d_err.p; a.fold_value = 1e7 * prm->lambda;
-    const size_t slice = ((size_t)a.max_patch * (4 * sizeof(double) + 3 * sizeof(int)) + 15) & ~(size_t)15;
-    const size_t smem = slice * kTripWarps;
-    if (smem > 200 * 1024) return fail(MSMGPU_ERR_CAPACITY, "costfn_triplet: patch too large for shared memory");
-    switch (query_group_width()) {
-        case 2: MSM_TRY(launch_triplet_g<2>(a, smem, s)); break;
-        case 4: MSM_TRY(launch_triplet_g<4>(a, smem, s)); break;
-        case 8: MSM_TRY(launch_triplet_g<8>(a, smem, s)); break;
-        case 16: MSM_TRY(launch_triplet_g<16>(a, smem, s)); break;
-        case 32: MSM_TRY(launch_triplet_g<32>(a, smem, s)); break;
-        default: MSM_TRY(launch_triplet_g<1>(a, smem, s)); break;
-    }
-    int h_err = 0;
-    std::vector<double> aux(2 * (size_t)n);
-    MSM_CUDA(cudaMemcpyAsync(out, d_out.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
-    MSM_CUDA(cudaMemcpyAsync(aux.data(), d_aux.p, aux.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
-    MSM_CUDA(cudaMemcpyAsync(&h_err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-    MSM_CUDA(cudaStreamSynchronize(s));
-    if (h_err) return status_to_error(MSMGPU_ERR_NO_TRIANGLE);
-    // reg_tools.cpp:596-597 and DiscreteCostFunction.cpp:187 with the host libm (this translation unit is built with -ffp-contract=off)
-    const double MU = prm->shear_modulus, KAPPA = prm->bulk_modulus, k_exp = prm->k_exponent, rexp = prm->exponent, lambda = prm->lambda;
-#pragma omp parallel for schedule(static) if (n > 4096)
-    for (int r = 0; r < n; ++r) {
-        const double R = aux[2 * (size_t)r], J = aux[2 * (size_t)r + 1];
-        if (J == -1.0) continue;                                // folded (or failed query): already final
-        const double Rshared = std::pow(R, k_exp), Jshared = std::pow(J, k_exp);
-        const double W = 0.5 * (MU * (Rshared + 1.0 / Rshared - 2) + KAPPA * (Jshared + 1.0 / Jshared - 2));
-        out[r] = out[r] + lambda * std::pow(W, rexp);
-    }
-    return MSMGPU_OK;
+    a.fold_value = 1e7 * prm->lambda;
+    a.group = 0; a.fixnan = 0; a.subcorr = 1.0;
+    return run_requests(c->ctx, a, ho, prm, out);
 }
+
+} // namespace msm
 
 // gMSM triplet term (DiscreteGroupCostFunction.cpp:26-52): the same strain energy on the per-subject control grids, no likelihood,
 // scaled by subcorr = 0.1 * S; a folded triangle costs FOLDING (not FOLDING * lambda), a NaN energy costs FIX_NAN when --fixnan.
 // Node ids in `triplets` are global (subject * ncp + vertex), so the per-subject grids are simply concatenated.
-static msmgpu_status group_triplet_run(msmgpu_ctx* ctx, int n_nodes, const double* cp_xyz, const double* orig_xyz, const double* rotations, int L,
-                                       const double* labels, int ntrip, const int32_t* triplets, const msmgpu_reg_params* prm, double subcorr,
-                                       int fixnan, int n, const int32_t* req_t, const int32_t* req_la, const int32_t* req_lb, const int32_t* req_lc,
-                                       const int32_t* labeling, int label, double* out) {
-    if (!ctx || n_nodes <= 0 || !cp_xyz || !orig_xyz || !rotations || L <= 0 || !labels || ntrip <= 0 || !triplets || !prm || n <= 0 || !out)
+// The per-iteration arrays (grids, rotations, labels, triplets) are uploaded once into a plan; a label phase only sends the labeling.
+struct msmgpu_triplet_plan {
+    msmgpu_ctx* ctx = nullptr;
+    int n_nodes = 0, L = 0, ntrip = 0;
+    msm::DevBuf<int> trip, labeling;
+    msm::DevBuf<double> labels, rot, orig, cp;
+};
+
+namespace msm {
+
+static msmgpu_status plan_create(msmgpu_ctx* ctx, int n_nodes, const double* cp_xyz, const double* orig_xyz, const double* rotations, int L,
+                                 const double* labels, int ntrip, const int32_t* triplets, std::unique_ptr<msmgpu_triplet_plan>& out) {
+    if (!ctx || n_nodes <= 0 || !cp_xyz || !orig_xyz || !rotations || L <= 0 || !labels || ntrip <= 0 || !triplets)
         return fail(MSMGPU_ERR_INVALID, "group_triplet: bad arguments");
     MSM_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
-    DevBuf<int> d_trip, d_rt, d_la, d_lb, d_lc, d_labeling, d_err;
-    DevBuf<double> d_labels, d_rot, d_orig, d_cp, d_out, d_aux;
-    MSM_TRY(up(d_trip, triplets, 3 * (size_t)ntrip, s));
-    MSM_TRY(up(d_labels, labels, 3 * (size_t)L, s));
-    MSM_TRY(up(d_rot, rotations, 9 * (size_t)n_nodes, s));
-    MSM_TRY(up(d_orig, orig_xyz, 3 * (size_t)n_nodes, s));
-    MSM_TRY(up(d_cp, cp_xyz, 3 * (size_t)n_nodes, s));
+    out.reset(new msmgpu_triplet_plan());
+    out->ctx = ctx; out->n_nodes = n_nodes; out->L = L; out->ntrip = ntrip;
+    MSM_TRY(up(out->trip, triplets, 3 * (size_t)ntrip, s));
+    MSM_TRY(up(out->labels, labels, 3 * (size_t)L, s));
+    MSM_TRY(up(out->rot, rotations, 9 * (size_t)n_nodes, s));
+    MSM_TRY(up(out->orig, orig_xyz, 3 * (size_t)n_nodes, s));
+    MSM_TRY(up(out->cp, cp_xyz, 3 * (size_t)n_nodes, s));
+    MSM_CUDA(cudaStreamSynchronize(s));   // the host arrays may go away after the call
+    return MSMGPU_OK;
+}
+
+static msmgpu_status plan_run(msmgpu_triplet_plan* p, const msmgpu_reg_params* prm, double subcorr, int fixnan, int first_triplet, int n_triplets,
+                              int n, const int32_t* req_t, const int32_t* req_la, const int32_t* req_lb, const int32_t* req_lc,
+                              const int32_t* labeling, int label, double* out) {
+    if (!p || !prm || n <= 0 || !out) return fail(MSMGPU_ERR_INVALID, "group_triplet: bad arguments");
+    MSM_CUDA(cudaSetDevice(p->ctx->device));
+    cudaStream_t s = p->ctx->stream;
+    DevBuf<int> d_rt, d_la, d_lb, d_lc;
     if (req_t) {
         MSM_TRY(up(d_rt, req_t, (size_t)n, s));
         MSM_TRY(up(d_la, req_la, (size_t)n, s));
         MSM_TRY(up(d_lb, req_lb, (size_t)n, s));
         MSM_TRY(up(d_lc, req_lc, (size_t)n, s));
     } else {
-        MSM_TRY(up(d_labeling, labeling, (size_t)n_nodes, s));
+        MSM_TRY(up(p->labeling, labeling, (size_t)p->n_nodes, s));
     }
-    MSM_CUDA(d_out.alloc((size_t)n, s));
-    MSM_CUDA(d_aux.alloc(2 * (size_t)n, s));
-    MSM_CUDA(d_err.alloc(1, s));
-    MSM_CUDA(cudaMemsetAsync(d_err.p, 0, sizeof(int), s));
     TripletArgs a{};
-    a.kind = MSMGPU_COST_UNIVARIATE; a.simmeasure = 2; a.ncp = n_nodes; a.n = n; a.max_patch = 1;
-    a.triplets = d_trip.p; a.req_t = req_t ? d_rt.p : nullptr; a.req_la = d_la.p; a.req_lb = d_lb.p; a.req_lc = d_lc.p;
-    a.labeling = d_labeling.p; a.label = label; a.labels = d_labels.p; a.rot = d_rot.p; a.cp_xyz = d_cp.p; a.orig_xyz = d_orig.p;
+    a.kind = MSMGPU_COST_UNIVARIATE; a.simmeasure = 2; a.ncp = p->n_nodes; a.n = n; a.max_patch = 1;
+    a.triplets = p->trip.p + 3 * (size_t)(req_t ? 0 : first_triplet);
+    a.req_t = req_t ? d_rt.p : nullptr; a.req_la = d_la.p; a.req_lb = d_lb.p; a.req_lc = d_lc.p;
+    a.labeling = p->labeling.p; a.label = label; a.labels = p->labels.p; a.rot = p->rot.p; a.cp_xyz = p->cp.p; a.orig_xyz = p->orig.p;
     a.lambda = prm->lambda; a.mu = prm->shear_modulus; a.kappa = prm->bulk_modulus; a.k_exp = prm->k_exponent; a.rexp = prm->exponent;
-    a.out = d_out.p; a.aux = d_aux.p; a.err = d_err.p; a.fold_value = 1e7;
-    const size_t smem = (((size_t)(4 * sizeof(double) + 3 * sizeof(int)) + 15) & ~(size_t)15) * kTripWarps;
-    MSM_TRY(launch_triplet_g<1>(a, smem, s));
-    std::vector<double> aux(2 * (size_t)n);
-    MSM_CUDA(cudaMemcpyAsync(out, d_out.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
-    MSM_CUDA(cudaMemcpyAsync(aux.data(), d_aux.p, aux.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
-    MSM_CUDA(cudaStreamSynchronize(s));
-    const double MU = prm->shear_modulus, KAPPA = prm->bulk_modulus, k_exp = prm->k_exponent, rexp = prm->exponent, lambda = prm->lambda;
-#pragma omp parallel for schedule(static) if (n > 4096)
-    for (int r = 0; r < n; ++r) {
-        const double R = aux[2 * (size_t)r], J = aux[2 * (size_t)r + 1];
-        if (J == -1.0) continue;                                // folded: FOLDING, already written
-        const double Rshared = std::pow(R, k_exp), Jshared = std::pow(J, k_exp);
-        const double W = 0.5 * (MU * (Rshared + 1.0 / Rshared - 2) + KAPPA * (Jshared + 1.0 / Jshared - 2));
-        if (fixnan && W != W) { out[r] = 1e7; continue; }       // FIX_NAN
-        out[r] = subcorr * lambda * std::pow(W, rexp);
-    }
-    return MSMGPU_OK;
+    a.fold_value = 1e7;
+    a.group = 1; a.fixnan = fixnan; a.subcorr = subcorr;
+    (void)n_triplets;
+    return run_requests(p->ctx, a, false, prm, out);
 }
 
 } // namespace msm
@@ -424,16 +530,41 @@ msmgpu_status msmgpu_group_triplet_costs(msmgpu_ctx* ctx, int n_nodes, const dou
                                          const double* labels, int ntrip, const int32_t* triplets, const msmgpu_reg_params* prm, double subcorr, int fixnan,
                                          int n, const int32_t* req_triplet, const int32_t* req_la, const int32_t* req_lb, const int32_t* req_lc, double* out) {
     if (!req_triplet || !req_la || !req_lb || !req_lc) return fail(MSMGPU_ERR_INVALID, "group_triplet_costs: bad arguments");
-    return group_triplet_run(ctx, n_nodes, cp_xyz, orig_xyz, rotations, L, labels, ntrip, triplets, prm, subcorr, fixnan, n, req_triplet, req_la, req_lb,
-                             req_lc, nullptr, 0, out);
+    std::unique_ptr<msmgpu_triplet_plan> p;
+    MSM_TRY(plan_create(ctx, n_nodes, cp_xyz, orig_xyz, rotations, L, labels, ntrip, triplets, p));
+    return plan_run(p.get(), prm, subcorr, fixnan, 0, ntrip, n, req_triplet, req_la, req_lb, req_lc, nullptr, 0, out);
 }
 
 msmgpu_status msmgpu_group_triplet_batch(msmgpu_ctx* ctx, int n_nodes, const double* cp_xyz, const double* orig_xyz, const double* rotations, int L,
                                          const double* labels, int ntrip, const int32_t* triplets, const msmgpu_reg_params* prm, double subcorr, int fixnan,
                                          const int32_t* labeling, int label, double* out) {
     if (!labeling || label < 0 || label >= L) return fail(MSMGPU_ERR_INVALID, "group_triplet_batch: bad arguments");
-    return group_triplet_run(ctx, n_nodes, cp_xyz, orig_xyz, rotations, L, labels, ntrip, triplets, prm, subcorr, fixnan, 8 * ntrip, nullptr, nullptr,
-                             nullptr, nullptr, labeling, label, out);
+    std::unique_ptr<msmgpu_triplet_plan> p;
+    MSM_TRY(plan_create(ctx, n_nodes, cp_xyz, orig_xyz, rotations, L, labels, ntrip, triplets, p));
+    return plan_run(p.get(), prm, subcorr, fixnan, 0, ntrip, 8 * ntrip, nullptr, nullptr, nullptr, nullptr, labeling, label, out);
+}
+
+msmgpu_status msmgpu_triplet_plan_create(msmgpu_ctx* ctx, int n_nodes, const double* cp_xyz, const double* orig_xyz, const double* rotations, int L,
+                                         const double* labels, int ntrip, const int32_t* triplets, msmgpu_triplet_plan** out) {
+    if (!out) return fail(MSMGPU_ERR_INVALID, "triplet_plan_create: bad arguments");
+    *out = nullptr;
+    std::unique_ptr<msmgpu_triplet_plan> p;
+    MSM_TRY(plan_create(ctx, n_nodes, cp_xyz, orig_xyz, rotations, L, labels, ntrip, triplets, p));
+    *out = p.release();
+    return MSMGPU_OK;
+}
+
+void msmgpu_triplet_plan_destroy(msmgpu_triplet_plan* p) {
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    delete p;
+}
+
+msmgpu_status msmgpu_triplet_plan_batch(msmgpu_triplet_plan* p, const msmgpu_reg_params* prm, double subcorr, int fixnan, int first_triplet,
+                                        int n_triplets, const int32_t* labeling, int label, double* out) {
+    if (!p || !labeling || label < 0 || label >= p->L || first_triplet < 0 || n_triplets <= 0 || first_triplet + (long long)n_triplets > p->ntrip)
+        return fail(MSMGPU_ERR_INVALID, "triplet_plan_batch: bad arguments");
+    return plan_run(p, prm, subcorr, fixnan, first_triplet, n_triplets, 8 * n_triplets, nullptr, nullptr, nullptr, nullptr, labeling, label, out);
 }
 
 msmgpu_status msmgpu_costfn_set_cpgrid_ho(msmgpu_costfn* c, int ncp, const double* cp_xyz, int ntri, const int32_t* cp_tri,

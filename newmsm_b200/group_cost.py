@@ -211,20 +211,40 @@ class DiscreteGroupModel:
                                                  C.byref(reg), 0.1 * S, int(fixnan), len(t), ptr(t), ptr(a), ptr(b), ptr(c), ptr(out)))
         return out
 
+    def reset_triplet_state(self, cps, orig_cps, rotations, labels, triplets):
+        """The per-iteration arrays of the triplet term (control grids after reset_CPgrid, m_ROT, the label set, estimate_triplets) go to the
+        device once; computeTripletCostsForLabel(None, ...) then only sends the labeling of each label phase."""
+        cp, org = f64(cps).reshape(-1, 3), f64(orig_cps).reshape(-1, 3)
+        rot, labels, trip = f64(rotations).reshape(-1, 9), f64(labels), i32(triplets).reshape(-1, 3)
+        if getattr(self, "_plan", None) is not None:
+            self.L_.msmgpu_triplet_plan_destroy(self._plan)
+        self._plan = C.c_void_p()
+        check(self.L_.msmgpu_triplet_plan_create(self.ctx.h, len(cp), ptr(cp), ptr(org), ptr(rot), len(labels), ptr(labels), len(trip), ptr(trip),
+                                                 C.byref(self._plan)))
+        self._plan_S, self._plan_T = f64(cps).shape[0], len(trip)
+
     def computeTripletCostsForLabel(self, cps, orig_cps, rotations, labels, triplets, labeling, label, lambda_, shearmodulus=0.4, bulkmodulus=1.6,
                                     kexponent=2.0, exponent=2.0, fixnan=False):
-        """The 8 combinations per triplet of Fusion::optimize (Fusion.h:181-196) -> [T, 8]."""
-        cp, org = f64(cps).reshape(-1, 3), f64(orig_cps).reshape(-1, 3)
-        S = f64(cps).shape[0]
-        rot, labels, trip, lab = f64(rotations).reshape(-1, 9), f64(labels), i32(triplets).reshape(-1, 3), i32(labeling)
+        """The 8 combinations per triplet of Fusion::optimize (Fusion.h:181-196) -> [T, 8]. cps=None: the arrays set by reset_triplet_state."""
         reg = capi.RegParams(lambda_, shearmodulus, bulkmodulus, kexponent, exponent, 3)
-        T = len(trip)
-        b, e = shard_range(T, self.coll.rank, self.coll.world)       # triplets are per subject: block-sharded like the pairs
-        out = np.zeros((e - b, 8))
-        if e > b:
-            blk = np.ascontiguousarray(trip[b:e])
-            check(self.L_.msmgpu_group_triplet_batch(self.ctx.h, len(cp), ptr(cp), ptr(org), ptr(rot), len(labels), ptr(labels), e - b, ptr(blk),
-                                                     C.byref(reg), 0.1 * S, int(fixnan), ptr(lab), int(label), ptr(out)))
+        lab = i32(labeling)
+        if cps is None:
+            S, T = self._plan_S, self._plan_T
+            b, e = shard_range(T, self.coll.rank, self.coll.world)       # triplets are per subject: block-sharded like the pairs
+            out = np.zeros((e - b, 8))
+            if e > b:
+                check(self.L_.msmgpu_triplet_plan_batch(self._plan, C.byref(reg), 0.1 * S, int(fixnan), b, e - b, ptr(lab), int(label), ptr(out)))
+        else:
+            cp, org = f64(cps).reshape(-1, 3), f64(orig_cps).reshape(-1, 3)
+            S = f64(cps).shape[0]
+            rot, labels, trip = f64(rotations).reshape(-1, 9), f64(labels), i32(triplets).reshape(-1, 3)
+            T = len(trip)
+            b, e = shard_range(T, self.coll.rank, self.coll.world)
+            out = np.zeros((e - b, 8))
+            if e > b:
+                blk = np.ascontiguousarray(trip[b:e])
+                check(self.L_.msmgpu_group_triplet_batch(self.ctx.h, len(cp), ptr(cp), ptr(org), ptr(rot), len(labels), ptr(labels), e - b, ptr(blk),
+                                                         C.byref(reg), 0.1 * S, int(fixnan), ptr(lab), int(label), ptr(out)))
         if self.coll.world == 1:
             return out
         import torch
@@ -235,6 +255,9 @@ class DiscreteGroupModel:
         if self.g is not None:
             self.L_.msmgpu_group_destroy(self.g)
             self.g = None
+        if getattr(self, "_plan", None) is not None:
+            self.L_.msmgpu_triplet_plan_destroy(self._plan)
+            self._plan = None
 
     def __del__(self):
         try:

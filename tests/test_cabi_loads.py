@@ -7,6 +7,8 @@ import pytest
 
 from newmsm_b200 import build, capi
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 
 @pytest.fixture(scope="module")
 def lib():
@@ -44,3 +46,16 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.lower() or f == "synth.py", f"{f} mentions the oracle"
+
+
+def test_device_pow_self_test_on_this_host():
+    """csrc/hostpow.cu: the pow tables of the C library mapped into the process are found and the host-side restatement of its algorithm
+    agrees with std::pow on ~2 M arguments (bit for bit); a corrupted table entry is noticed and switches the device path off."""
+    import subprocess, sys
+    flags = open("/proc/cpuinfo").read()
+    code = "from newmsm_b200 import capi; print('POW', capi.lib().msmgpu_device_pow_enabled())"
+    run = lambda extra: subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **extra), capture_output=True, text=True, cwd=ROOT).stdout
+    if " fma " in flags and " avx2 " in flags:      # glibc selects the variant restated in hostpow.cuh on FMA + AVX2 hosts
+        assert "POW 1" in run({})
+    assert "POW 0" in run({"MSMGPU_POW_SELFTEST_CORRUPT": "1"})
+    assert "POW 0" in run({"MSMGPU_DEVICE_POW": "0"})

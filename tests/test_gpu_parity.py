@@ -480,6 +480,53 @@ def test_ho_triplet_likelihood(R, oracle_built, kind, D, sim):
 
 
 # ---------------------------------------------------------------------------------------------
+# pow() of the host C library on the device (csrc/hostpow.cuh): the strain costs call it three times per request
+# ---------------------------------------------------------------------------------------------
+def test_device_pow_equals_host_libm_bit_for_bit(R):
+    import ctypes
+    L = capi.lib()
+    if not L.msmgpu_device_pow_enabled():
+        pytest.skip("the host C library's pow tables were not recognised: costs are finished on the host (no device pow to test)")
+    libm = ctypes.CDLL("libm.so.6")
+    libm.pow.restype = ctypes.c_double
+    libm.pow.argtypes = [ctypes.c_double, ctypes.c_double]
+    rng = np.random.default_rng(5)
+    n = 60000
+    near1 = 1.0 + rng.uniform(-0.5, 1.0, n) * 2.0 ** -rng.integers(0, 30, n)
+    small = rng.uniform(0, 1, n) * 2.0 ** -rng.integers(0, 60, n).astype(np.float64)
+    wide = np.exp(rng.uniform(-20, 20, n))
+    anyb = rng.integers(0, 2 ** 63, n, dtype=np.int64).view(np.float64) * rng.choice([-1.0, 1.0], n)
+    x = np.concatenate([near1, small, wide, anyb, np.abs(anyb), -np.ldexp(1.0 + rng.uniform(0, 1, n), rng.integers(-20, 20, n)),
+                        [0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 5e-324, 1e-310, 1.7976931348623157e308]])
+    y = np.concatenate([rng.choice([2.0, 1.0, 0.5, 3.0, 1.5, 1.3], 2 * n), rng.uniform(-4, 4, n), rng.integers(0, 2 ** 63, n, dtype=np.int64).view(np.float64),
+                        rng.uniform(-1200, 1200, n), rng.integers(-20, 21, n).astype(np.float64),
+                        [2.0, 2.0, np.inf, np.inf, 2.0, 3.0, 0.0, 2.0, 0.5, 2.0]])
+    x, y = np.ascontiguousarray(x), np.ascontiguousarray(y)
+    assert len(x) == len(y)
+    got = np.zeros(len(x))
+    ctx = R.Context(0)
+    capi.check(L.msmgpu_debug_device_pow(ctx.h, len(x), capi.ptr(x), capi.ptr(y), capi.ptr(got)))
+    ref = np.array([libm.pow(float(a), float(b)) for a, b in zip(x, y)])
+    nan = np.isnan(ref)
+    assert np.array_equal(np.isnan(got), nan)
+    assert np.array_equal(got[~nan].view(np.int64), ref[~nan].view(np.int64)), "device pow differs from the host C library's pow"
+    assert np.isfinite(ref).mean() > 0.6
+    ctx.close()
+
+
+def test_triplet_costs_same_with_host_finish():
+    """MSMGPU_DEVICE_POW=0 (the fallback when the host library is not recognised): the kernels stop at the pow arguments and the host libm
+    finishes; the reference-golden triplet tests must pass on that path too (the switch is read once per process: own interpreter)."""
+    import subprocess, sys
+    env = dict(os.environ, MSMGPU_DEVICE_POW="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k",
+                        "test_triplet_costs_vs_reference_golden or test_group_costs_vs_reference_golden or test_group_triplet_nan"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
+
+
+# ---------------------------------------------------------------------------------------------
 # groupwise (gMSM): resampled fields per (subject,label) and pair costs (oracle pinned in tests/test_oracle_vs_refmr.py)
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("sim", [2, 1])
