@@ -237,7 +237,7 @@ typedef struct {
     double bulk_modulus;    /* "bulkmodulus"   _kappa  (default 1.6) */
     double k_exponent;      /* "kexponent"     _k_exp  (default 2) */
     double exponent;        /* "exponent"      _rexp   (default 2) */
-    int rmode;              /* "regularisermode": 2 or 3 = spherical strain (4/5 need anatomical meshes: not accelerated) */
+    int rmode;              /* "regularisermode": 2 or 3 = spherical strain; 4 or 5 = anatomical strain (msmgpu_costfn_set_anatomical first) */
 } msmgpu_reg_params;
 
 /* replaces: set_meshes + set_featurespace + set_octrees (DiscreteCostFunction.h:173-189).
@@ -281,6 +281,24 @@ msmgpu_status msmgpu_costfn_triplet_costs(msmgpu_costfn* c, int ntrip, const int
  * out[t][b] = cost(t, b&4 ? label : labeling[A], b&2 ? label : labeling[B], b&1 ? label : labeling[C]) */
 msmgpu_status msmgpu_costfn_triplet_batch(msmgpu_costfn* c, int ntrip, const int32_t* triplets, int L, const double* labels, const double* rotations,
                                           const double* orig_cp_xyz, const msmgpu_reg_params* prm, const int32_t* labeling, int label, double* out);
+
+/* replaces: set_anatomical + set_anatomical_neighbourhood + initialize_regulariser (DiscreteCostFunction.h:160-169) for regoption 4 / 5:
+ * the triplet regulariser becomes the MEAN strain energy of the anatomical faces that belong to the control triangle, each deformed by
+ * deform_anatomy (DiscreteCostFunction.cpp:169-181, 245-301): a face vertex moves with its barycentric weights in the displaced control
+ * triangle, is located on _TARGEThi (octree `anattree`) and takes the barycentric blend of the _aTARGET coordinates there.
+ *   asource:  _aSOURCE (n_av vertices, n_at faces)      thi: _TARGEThi (n_hv vertices, n_ht faces), atarget_xyz: _aTARGET [n_hv][3]
+ *   face_ptr / face_ids: NEARESTFACES as CSR over the ntrip control triangles (ids into asource_tri, the reference's order)
+ *   bary_ptr / bary_key / bary_w: _ANATbaryweights as CSR over the _aSOURCE vertices, keys (control-point ids) ascending like std::map
+ * A vertex whose location query fails gets NaN coordinates and the cost is NaN: the reference catches the exception and carries on with
+ * a zero triangle whose weights are 0/0 (cpp:268-274). */
+typedef struct {
+    int n_av; const double* asource_xyz; int n_at; const int32_t* asource_tri;
+    int n_hv; const double* thi_xyz; int n_ht; const int32_t* thi_tri;
+    const double* atarget_xyz;
+    const int32_t* face_ptr; const int32_t* face_ids;
+    const int32_t* bary_ptr; const int32_t* bary_key; const double* bary_w;
+} msmgpu_anatomical;
+msmgpu_status msmgpu_costfn_set_anatomical(msmgpu_costfn* c, int ntrip, const msmgpu_anatomical* a);
 
 /* ---- AFFINE / RIGID level (msm-newmeshreg/src/rigid_costfunction.cpp) ---- */
 typedef struct msmgpu_rigid msmgpu_rigid;

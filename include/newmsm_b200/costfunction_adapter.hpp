@@ -18,7 +18,8 @@
 //                                   identical values.
 //
 // There is no CPU fallback for the device paths: a failing msmgpu call throws MeshregException with msmgpu_last_error().
-// regoption 4/5 (anatomical strain) are not accelerated: install_gpu_costfunction() leaves the reference's object in place.
+// regoption 4/5 (anatomical strain, cpp:169-181, 245-301): the anatomical meshes and maps the model received through set_anatomical /
+// set_anatomical_neighbourhood are uploaded once per level (msmgpu_costfn_set_anatomical) and the same batches evaluate them.
 #pragma once
 
 #include <algorithm>
@@ -116,7 +117,7 @@ class GpuCostFunction : public Base {
     // per-iteration host copies handed to the C ABI
     std::vector<double> labels_, rot_, orig_cp_;
     std::vector<int32_t> trip_;
-    bool iter_arrays_ready_ = false;
+    bool iter_arrays_ready_ = false, anat_ready_ = false;
 
     std::mutex mu_;
     std::atomic<bool> unary_ready_{false};
@@ -137,6 +138,7 @@ class GpuCostFunction : public Base {
         if (d_tree_) msmgpu_octree_destroy(d_tree_);
         if (d_target_) msmgpu_mesh_destroy(d_target_);
         d_cf_ = nullptr; d_tree_ = nullptr; d_target_ = nullptr;
+        anat_ready_ = false;
     }
 
     void ensure_device() {
@@ -172,7 +174,38 @@ class GpuCostFunction : public Base {
             trip_.assign(this->_triplets, this->_triplets + 3 * (size_t)this->m_num_triplets);
             orig_cp_ = detail::coords_of(this->_ORIG, N);   // _ORIG.get_coord(node) (cpp:166-168): the nested icosphere's first N vertices
         }
+        if (this->_rmode >= 4) ensure_anatomical();
         iter_arrays_ready_ = true;
+    }
+
+    // regoption 4/5: _aSOURCE, _TARGEThi, _aTARGET, NEARESTFACES and _ANATbaryweights (DiscreteCostFunction.h:160-169) are fixed for the
+    // lifetime of this object (mesh_registration.cpp:93-98 sets them once per level, before the first iteration)
+    void ensure_anatomical() {
+        if (anat_ready_) return;
+        const int T = this->m_num_triplets;
+        if ((int)this->NEARESTFACES.size() < T || this->_aSOURCE.nvertices() == 0)
+            throw MeshregException("msmgpu: regoption 4/5 without anatomical meshes (set_anatomical / set_anatomical_neighbourhood)");
+        const std::vector<double> as = detail::coords_of(this->_aSOURCE), th = detail::coords_of(this->_TARGEThi), at = detail::coords_of(this->_aTARGET);
+        const std::vector<int32_t> ast = detail::triangles_of(this->_aSOURCE), tht = detail::triangles_of(this->_TARGEThi);
+        if (this->_aTARGET.nvertices() != this->_TARGEThi.nvertices()) throw MeshregException("msmgpu: _aTARGET and _TARGEThi differ in size");
+        std::vector<int32_t> fptr(T + 1, 0), fids, bptr(this->_aSOURCE.nvertices() + 1, 0), bkey;
+        std::vector<double> bw;
+        for (int t = 0; t < T; ++t) {
+            fids.insert(fids.end(), this->NEARESTFACES[t].begin(), this->NEARESTFACES[t].end());
+            fptr[t + 1] = (int32_t)fids.size();
+        }
+        for (int v = 0; v < this->_aSOURCE.nvertices(); ++v) {
+            if (v < (int)this->_ANATbaryweights.size())
+                for (const auto& it : this->_ANATbaryweights[v]) { bkey.push_back(it.first); bw.push_back(it.second); }   // std::map: ascending keys
+            bptr[v + 1] = (int32_t)bkey.size();
+        }
+        msmgpu_anatomical A;
+        A.n_av = this->_aSOURCE.nvertices(); A.asource_xyz = as.data(); A.n_at = this->_aSOURCE.ntriangles(); A.asource_tri = ast.data();
+        A.n_hv = this->_TARGEThi.nvertices(); A.thi_xyz = th.data(); A.n_ht = this->_TARGEThi.ntriangles(); A.thi_tri = tht.data();
+        A.atarget_xyz = at.data();
+        A.face_ptr = fptr.data(); A.face_ids = fids.data(); A.bary_ptr = bptr.data(); A.bary_key = bkey.data(); A.bary_w = bw.data();
+        detail::check(msmgpu_costfn_set_anatomical(d_cf_, T, &A));
+        anat_ready_ = true;
     }
 
     msmgpu_reg_params reg_params() const {
@@ -319,7 +352,6 @@ public:
     }
 
     double computeTripletCost(int triplet, int labelA, int labelB, int labelC) override {
-        if (this->_rmode != 2 && this->_rmode != 3) return Base::computeTripletCost(triplet, labelA, labelB, labelC);
         const int* lab = model_->getLabeling();
         const int a = this->_triplets[3 * triplet], b = this->_triplets[3 * triplet + 1], c = this->_triplets[3 * triplet + 2];
         const bool da = labelA != lab[a], db = labelB != lab[b], dc = labelC != lab[c];

@@ -132,7 +132,6 @@ static void stat_add(double& seconds, long* calls, double dt) {
 struct ModelView : NonLinearSRegDiscreteModel {
     static void install(NonLinearSRegDiscreteModel* m, myparam& P) {
         ModelView* v = static_cast<ModelView*>(m);
-        if (v->m_regoption == 4 || v->m_regoption == 5) return;   // anatomical strain: not accelerated, the reference object stays
         v->costfct = newmeshreg_gpu::make_gpu_costfunction(m, v->m_multivariate, v->m_patchwise, v->m_triclique);
         v->costfct->set_parameters(P);
     }

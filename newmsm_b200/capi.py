@@ -124,6 +124,7 @@ _SIGNATURES = {
     "msmgpu_costfn_triplet_costs": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "msmgpu_costfn_triplet_batch": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "msmgpu_group_triplet_costs": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _d, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "msmgpu_costfn_set_anatomical": (_i, [_vp, _i, _vp]),
     "msmgpu_triplet_plan_create": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _pp]),
     "msmgpu_triplet_plan_destroy": (None, [_vp]),
     "msmgpu_triplet_plan_batch": (_i, [_vp, _vp, _d, _i, _i, _i, _vp, _i, _vp]),
@@ -135,6 +136,13 @@ class RegParams(C.Structure):
     """msmgpu_reg_params (include/msmgpu.h)"""
     _fields_ = [("lambda_", C.c_double), ("shear_modulus", C.c_double), ("bulk_modulus", C.c_double),
                 ("k_exponent", C.c_double), ("exponent", C.c_double), ("rmode", C.c_int)]
+
+
+class Anatomical(C.Structure):
+    """msmgpu_anatomical (include/msmgpu.h): the anatomical meshes and maps of regoption 4/5"""
+    _fields_ = [("n_av", C.c_int), ("asource_xyz", C.c_void_p), ("n_at", C.c_int), ("asource_tri", C.c_void_p),
+                ("n_hv", C.c_int), ("thi_xyz", C.c_void_p), ("n_ht", C.c_int), ("thi_tri", C.c_void_p), ("atarget_xyz", C.c_void_p),
+                ("face_ptr", C.c_void_p), ("face_ids", C.c_void_p), ("bary_ptr", C.c_void_p), ("bary_key", C.c_void_p), ("bary_w", C.c_void_p)]
 
 
 _lib = None

@@ -1,6 +1,7 @@
 // Shared by cost.cu (unary tables) and triplet.cu (HO patches, triplet costs): the device state of one
 // DiscreteCostFunction and the sequential FP64 similarities.
 #pragma once
+#include <memory>
 #include "query.cuh"
 
 struct msmgpu_costfn {
@@ -20,6 +21,18 @@ struct msmgpu_costfn {
     int n_patch = 0, max_patch = 0, n_patch_rows = 0;
     // HO (triclique) state: the CP-grid triangles the patches hang on (DiscreteCostFunction.cpp:468-485)
     int n_cp_tri = 0;
+    // anatomical strain (regoption 4/5, DiscreteCostFunction.cpp:169-181, 245-301): msmgpu_costfn_set_anatomical
+    struct Anat {
+        int ntrip = 0, n_av = 0, max_u = 0, max_f = 0;
+        msmgpu_mesh* thi = nullptr;          // _TARGEThi
+        msmgpu_octree* tree = nullptr;       // anattree
+        msm::DevBuf<double> asource_xyz, atarget_xyz, bary_w;
+        msm::DevBuf<int> asource_tri, face_ptr, face_ids, face_local /* [faces][3]: corner -> index in the triplet's vertex list */,
+            uv_ptr, uv_ids /* per triplet: the distinct _aSOURCE vertices of its faces, first-seen order */, bary_ptr, bary_key;
+        std::vector<int> h_face_ptr;         // host copy (the host finish without device pow needs the face counts)
+        ~Anat();
+    };
+    std::unique_ptr<Anat> anat;
 };
 
 namespace msm {

@@ -158,30 +158,46 @@ struct TripletArgs {
     int fixnan;
     double subcorr;
     PowTables pw;
+    // regoption 4 / 5 (anatomical strain): rmode >= 4
+    int rmode, an_max_u, an_max_f;
+    size_t slice_bytes;       // per-warp shared-memory slice: [HO part | anatomical part]
+    TreeView an_tree;         // anattree over _TARGEThi
+    const double* an_src; const int* an_src_tri; const double* an_tgt;
+    const int* an_face_ptr; const int* an_face_ids; const int* an_face_local; const int* an_uv_ptr; const int* an_uv_ids;
+    const int* an_bary_ptr; const int* an_bary_key; const double* an_bary_w;
+    double* aux_anat;         // [n][2 * an_max_f] (R, J) per face when the host finishes the costs
 };
 
-// reg_tools.cpp:596-597 + DiscreteCostFunction.cpp:187 / DiscreteGroupCostFunction.cpp:49-51, the reference's expression order
-__host__ __device__ __forceinline__ double finish_cost(double likelihood, double R, double J, double MU, double KAPPA, double k_exp, double rexp,
-                                                       double lambda, int group, int fixnan, double subcorr, const PowTables* pw) {
+// W of one deformed triangle (reg_tools.cpp:596-597)
+__host__ __device__ __forceinline__ double strain_energy(double R, double J, double MU, double KAPPA, double k_exp, const PowTables* pw) {
 #ifdef __CUDA_ARCH__
     const double Rshared = host_pow(R, k_exp, *pw), Jshared = host_pow(J, k_exp, *pw);
 #else
     const double Rshared = pw ? host_pow(R, k_exp, *pw) : std::pow(R, k_exp), Jshared = pw ? host_pow(J, k_exp, *pw) : std::pow(J, k_exp);
 #endif
-    const double W = 0.5 * (MU * (Rshared + 1.0 / Rshared - 2) + KAPPA * (Jshared + 1.0 / Jshared - 2));
+    return 0.5 * (MU * (Rshared + 1.0 / Rshared - 2) + KAPPA * (Jshared + 1.0 / Jshared - 2));
+}
+
+// DiscreteCostFunction.cpp:187 / DiscreteGroupCostFunction.cpp:49-51 from the strain energy W, the reference's expression order
+__host__ __device__ __forceinline__ double finish_from_energy(double likelihood, double W, double rexp, double lambda, int group, int fixnan,
+                                                              double subcorr, const PowTables* pw) {
+#ifdef __CUDA_ARCH__
     if (group) {
         if (fixnan && W != W) return 1e7;       // FIX_NAN
-#ifdef __CUDA_ARCH__
         return subcorr * lambda * host_pow(W, rexp, *pw);
-#else
-        return subcorr * lambda * (pw ? host_pow(W, rexp, *pw) : std::pow(W, rexp));
-#endif
     }
-#ifdef __CUDA_ARCH__
     return likelihood + lambda * host_pow(W, rexp, *pw);
 #else
+    if (group) {
+        if (fixnan && W != W) return 1e7;
+        return subcorr * lambda * (pw ? host_pow(W, rexp, *pw) : std::pow(W, rexp));
+    }
     return likelihood + lambda * (pw ? host_pow(W, rexp, *pw) : std::pow(W, rexp));
 #endif
+}
+__host__ __device__ __forceinline__ double finish_cost(double likelihood, double R, double J, double MU, double KAPPA, double k_exp, double rexp,
+                                                       double lambda, int group, int fixnan, double subcorr, const PowTables* pw) {
+    return finish_from_energy(likelihood, strain_energy(R, J, MU, KAPPA, k_exp, pw), rexp, lambda, group, fixnan, subcorr, pw);
 }
 
 __device__ __forceinline__ void triplet_labels(const TripletArgs& a, int r, int& t, int* lab) {
@@ -235,9 +251,10 @@ __global__ void __launch_bounds__(kTripWarps * 32) k_triplet_costs(TripletArgs a
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = blockIdx.x * kTripWarps + warp;
     if (r >= a.n) return;
-    // per-warp slice: w[max_patch][3] doubles | sim[max_patch] doubles | idx[max_patch][3] ints
+    // per-warp slice: w[max_patch][3] doubles | sim[max_patch] doubles | idx[max_patch][3] ints | anatomical part (regoption 4/5)
     const size_t slice = (size_t)a.max_patch * (4 * sizeof(double) + 3 * sizeof(int));
-    unsigned char* base = smem_raw + (size_t)warp * ((slice + 15) & ~(size_t)15);
+    unsigned char* base = smem_raw + (size_t)warp * a.slice_bytes;
+    double* s_an = reinterpret_cast<double*>(base + ((slice + 15) & ~(size_t)15));   // [an_max_u][3] deformed vertices | [an_max_f] face energies
     double* s_w = reinterpret_cast<double*>(base);
     double* s_sim = s_w + 3 * (size_t)a.max_patch;
     int* s_idx = reinterpret_cast<int*>(s_sim + a.max_patch);
@@ -337,6 +354,80 @@ __global__ void __launch_bounds__(kTripWarps * 32) k_triplet_costs(TripletArgs a
         }
         if (lane == 0) likelihood = (__ldg(a.absw + ids[0]) + __ldg(a.absw + ids[1]) + __ldg(a.absw + ids[2])) / 3.0 * cost;
     }
+    if (a.rmode >= 4) {   // regoption 4/5 (cpp:169-181): mean strain energy of the triplet's anatomical faces, each deformed by deform_anatomy
+        const int u0 = a.an_uv_ptr[t], U = a.an_uv_ptr[t + 1] - u0;
+        const int f0 = a.an_face_ptr[t], F = a.an_face_ptr[t + 1] - f0;
+        for (int ub = 0; ub < U; ub += 32) {   // cpp:245-301, once per distinct vertex (`moved` / `transformed`)
+            const int u = ub + lane;
+            const bool active = u < U;
+            V3 np{0, 0, 0};
+            if (active) {
+                const int tindex = __ldg(a.an_uv_ids + u0 + u);
+                // `vertex[it.first] * it.second` over the ascending keys; a key that is not a node of this triplet reads a zero Point
+                for (int e = __ldg(a.an_bary_ptr + tindex); e < __ldg(a.an_bary_ptr + tindex + 1); ++e) {
+                    const int key = __ldg(a.an_bary_key + e);
+                    const double w = __ldg(a.an_bary_w + e);
+                    V3 v{0, 0, 0};
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) if (ids[k] == key) v = def[k];
+                    const V3 c = vscale(v, w);
+                    np = V3{np.x + c.x, np.y + c.y, np.z + c.z};
+                }
+            }
+            int st;
+            const int tt = nearest_triangle<1>(a.an_tree, np, active, 0, st);
+            if (active) {
+                V3 res{0, 0, 0};
+                if (tt < 0) {   // the reference carries on with a zero triangle: weights 0/0 (cpp:268-274)
+                    res = V3{nan(""), nan(""), nan("")};
+                } else {
+                    int idx[3];
+                    double w[3];
+                    const int ne = sorted_weights(a.an_tree, tt, np, idx, w);
+#pragma unroll
+                    for (int j = 0; j < 3; ++j)
+                        if (j < ne) {
+                            const V3 c = vscale(load_pt(a.an_tgt, idx[j]), w[j]);
+                            res = V3{res.x + c.x, res.y + c.y, res.z + c.z};
+                        }
+                }
+                s_an[3 * u] = res.x; s_an[3 * u + 1] = res.y; s_an[3 * u + 2] = res.z;
+            }
+        }
+        __syncwarp();
+        double* s_e = s_an + 3 * (size_t)a.an_max_u;
+        for (int f = lane; f < F; f += 32) {
+            const int face = __ldg(a.an_face_ids + f0 + f);
+            V3 O[3], Fv[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                O[i] = load_pt(a.an_src, __ldg(a.an_src_tri + 3 * (size_t)face + i));
+                const int lu = __ldg(a.an_face_local + 3 * (size_t)(f0 + f) + i);
+                Fv[i] = V3{s_an[3 * lu], s_an[3 * lu + 1], s_an[3 * lu + 2]};
+            }
+            double R, J;
+            triangular_strain_dev(O, Fv, R, J);
+            if (a.dev_pow) {
+                s_e[f] = strain_energy(R, J, a.mu, a.kappa, a.k_exp, &a.pw);
+            } else {
+                a.aux_anat[2 * ((size_t)r * a.an_max_f + f)] = R;
+                a.aux_anat[2 * ((size_t)r * a.an_max_f + f) + 1] = J;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            if (a.dev_pow) {
+                double W = 0.0;
+                for (int f = 0; f < F; ++f) W += s_e[f];
+                W = W / (double)F;
+                a.out[r] = finish_from_energy(likelihood, W, a.rexp, a.lambda, 0, 0, 1.0, &a.pw);
+            } else {
+                a.out[r] = likelihood;
+                a.aux[2 * (size_t)r] = 0.0; a.aux[2 * (size_t)r + 1] = 0.0;   // J != -1: not final
+            }
+        }
+        return;
+    }
     if (lane == 0) {   // regoption 2/3 (cpp:158-166), then cpp:187
         double R, J;
         triangular_strain_dev(org, def, R, J);
@@ -377,28 +468,62 @@ static void finish_on_host(int n, const double* aux, double* out, const msmgpu_r
     }
 }
 
-// launches the request kernel for `a` (everything but out / aux / err / pow set by the caller) and brings the costs to `out`
-static msmgpu_status run_requests(msmgpu_ctx* ctx, TripletArgs& a, bool ho, const msmgpu_reg_params* prm, double* out) {
+// regoption 4/5 without device pow: W_f per face, their sequential mean, then cpp:187 -- all with the host libm
+static void finish_on_host_anat(int n, const double* aux, const double* aux_anat, int max_f, const std::vector<int>& face_ptr, const int32_t* h_req_t,
+                                double* out, const msmgpu_reg_params* prm) {
+    const double MU = prm->shear_modulus, KAPPA = prm->bulk_modulus, k_exp = prm->k_exponent, rexp = prm->exponent, lambda = prm->lambda;
+#pragma omp parallel for schedule(static) if (n > 1024)
+    for (int r = 0; r < n; ++r) {
+        if (aux[2 * (size_t)r + 1] == -1.0) continue;           // folded (or failed HO query): already final
+        const int t = h_req_t ? h_req_t[r] : r >> 3;
+        const int F = face_ptr[t + 1] - face_ptr[t];
+        double W = 0.0;
+        for (int f = 0; f < F; ++f)
+            W += strain_energy(aux_anat[2 * ((size_t)r * max_f + f)], aux_anat[2 * ((size_t)r * max_f + f) + 1], MU, KAPPA, k_exp, nullptr);
+        W = W / (double)F;
+        out[r] = finish_from_energy(out[r], W, rexp, lambda, 0, 0, 1.0, nullptr);
+    }
+}
+
+// launches the request kernel for `a` (everything but out / aux / err / pow / shared-memory layout set by the caller) and brings the costs to `out`
+static msmgpu_status run_requests(msmgpu_ctx* ctx, TripletArgs& a, bool ho, const msmgpu_reg_params* prm, double* out,
+                                  const msmgpu_costfn::Anat* anat = nullptr, const int32_t* h_req_t = nullptr) {
     cudaStream_t s = ctx->stream;
     const int n = a.n;
     const DevicePow& dp = device_pow(ctx->device);
     a.dev_pow = dp.enabled ? 1 : 0;
     a.pw = dp.t;
-    DevBuf<double> d_out, d_aux;
+    a.rmode = prm->rmode;
+    DevBuf<double> d_out, d_aux, d_aux_anat;
     DevBuf<int> d_err;
     MSM_CUDA(d_out.alloc((size_t)n, s));
     if (!a.dev_pow) MSM_CUDA(d_aux.alloc(2 * (size_t)n, s));
     MSM_CUDA(d_err.alloc(1, s));
     MSM_CUDA(cudaMemsetAsync(d_err.p, 0, sizeof(int), s));
     a.out = d_out.p; a.aux = d_aux.p; a.err = d_err.p;
-    if (!ho) {
+    const bool an = a.rmode >= 4;
+    if (an) {
+        a.an_max_u = anat->max_u; a.an_max_f = anat->max_f;
+        a.an_tree = anat->tree->view();
+        a.an_src = anat->asource_xyz.p; a.an_src_tri = anat->asource_tri.p; a.an_tgt = anat->atarget_xyz.p;
+        a.an_face_ptr = anat->face_ptr.p; a.an_face_ids = anat->face_ids.p; a.an_face_local = anat->face_local.p;
+        a.an_uv_ptr = anat->uv_ptr.p; a.an_uv_ids = anat->uv_ids.p;
+        a.an_bary_ptr = anat->bary_ptr.p; a.an_bary_key = anat->bary_key.p; a.an_bary_w = anat->bary_w.p;
+        if (!a.dev_pow) {
+            MSM_CUDA(d_aux_anat.alloc(2 * (size_t)n * anat->max_f, s));
+            a.aux_anat = d_aux_anat.p;
+        }
+    }
+    if (!ho && !an) {
         k_strain_costs<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(a);
         MSM_LAUNCH_CHECK();
     } else {
-        const size_t slice = ((size_t)a.max_patch * (4 * sizeof(double) + 3 * sizeof(int)) + 15) & ~(size_t)15;
-        const size_t smem = slice * kTripWarps;
+        const size_t ho_part = ((size_t)a.max_patch * (4 * sizeof(double) + 3 * sizeof(int)) + 15) & ~(size_t)15;
+        const size_t an_part = an ? (((size_t)3 * anat->max_u + anat->max_f) * sizeof(double) + 15) & ~(size_t)15 : 0;
+        a.slice_bytes = ho_part + an_part;
+        const size_t smem = a.slice_bytes * kTripWarps;
         if (smem > 200 * 1024) return fail(MSMGPU_ERR_CAPACITY, "costfn_triplet: patch too large for shared memory");
-        switch (query_group_width()) {
+        switch (ho ? query_group_width() : 1) {
             case 2: MSM_TRY(launch_triplet_g<2>(a, smem, s)); break;
             case 4: MSM_TRY(launch_triplet_g<4>(a, smem, s)); break;
             case 8: MSM_TRY(launch_triplet_g<8>(a, smem, s)); break;
@@ -408,16 +533,23 @@ static msmgpu_status run_requests(msmgpu_ctx* ctx, TripletArgs& a, bool ho, cons
         }
     }
     int h_err = 0;
-    std::vector<double> aux;
+    std::vector<double> aux, aux_anat;
     MSM_CUDA(cudaMemcpyAsync(out, d_out.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (!a.dev_pow) {
         aux.resize(2 * (size_t)n);
         MSM_CUDA(cudaMemcpyAsync(aux.data(), d_aux.p, aux.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (an) {
+            aux_anat.resize(2 * (size_t)n * anat->max_f);
+            MSM_CUDA(cudaMemcpyAsync(aux_anat.data(), d_aux_anat.p, aux_anat.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+        }
     }
     MSM_CUDA(cudaMemcpyAsync(&h_err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     MSM_CUDA(cudaStreamSynchronize(s));
     if (h_err) return status_to_error(MSMGPU_ERR_NO_TRIANGLE);
-    if (!a.dev_pow) finish_on_host(n, aux.data(), out, prm, a.group, a.fixnan, a.subcorr);
+    if (!a.dev_pow) {
+        if (an) finish_on_host_anat(n, aux.data(), aux_anat.data(), anat->max_f, anat->h_face_ptr, h_req_t, out, prm);
+        else finish_on_host(n, aux.data(), out, prm, a.group, a.fixnan, a.subcorr);
+    }
     return MSMGPU_OK;
 }
 
@@ -427,8 +559,10 @@ static msmgpu_status triplet_run(msmgpu_costfn* c, int ntrip, const int32_t* tri
     if (!c || ntrip <= 0 || !triplets || L <= 0 || !labels || !rotations || !orig_cp_xyz || !prm || n <= 0 || !out)
         return fail(MSMGPU_ERR_INVALID, "costfn_triplet: bad arguments");
     if (c->ncp <= 0) return fail(MSMGPU_ERR_INVALID, "costfn_triplet: set the control-point grid first");
-    if (prm->rmode != 2 && prm->rmode != 3)
-        return fail(MSMGPU_ERR_INVALID, "DiscreteModel computeTripletCost regoption does not exist");   // cpp:183 (4/5 need anatomical meshes: not accelerated)
+    if (prm->rmode < 2 || prm->rmode > 5)
+        return fail(MSMGPU_ERR_INVALID, "DiscreteModel computeTripletCost regoption does not exist");   // cpp:183
+    if (prm->rmode >= 4 && (!c->anat || c->anat->ntrip != ntrip))
+        return fail(MSMGPU_ERR_INVALID, "costfn_triplet: regoption 4/5 needs msmgpu_costfn_set_anatomical for this control grid");
     const bool ho = c->kind >= MSMGPU_COST_HO_UNIVARIATE;
     if (ho && c->n_patch_rows != ntrip) return fail(MSMGPU_ERR_INVALID, "costfn_triplet: HO patches were built for a different CP-grid triangle count");
     MSM_CUDA(cudaSetDevice(c->ctx->device));
@@ -458,7 +592,7 @@ static msmgpu_status triplet_run(msmgpu_costfn* c, int ntrip, const int32_t* tri
     a.lambda = prm->lambda; a.mu = prm->shear_modulus; a.kappa = prm->bulk_modulus; a.k_exp = prm->k_exponent; a.rexp = prm->exponent;
     a.fold_value = 1e7 * prm->lambda;
     a.group = 0; a.fixnan = 0; a.subcorr = 1.0;
-    return run_requests(c->ctx, a, ho, prm, out);
+    return run_requests(c->ctx, a, ho, prm, out, c->anat.get(), req_t);
 }
 
 } // namespace msm
@@ -565,6 +699,66 @@ msmgpu_status msmgpu_triplet_plan_batch(msmgpu_triplet_plan* p, const msmgpu_reg
     if (!p || !labeling || label < 0 || label >= p->L || first_triplet < 0 || n_triplets <= 0 || first_triplet + (long long)n_triplets > p->ntrip)
         return fail(MSMGPU_ERR_INVALID, "triplet_plan_batch: bad arguments");
     return plan_run(p, prm, subcorr, fixnan, first_triplet, n_triplets, 8 * n_triplets, nullptr, nullptr, nullptr, nullptr, labeling, label, out);
+}
+
+msmgpu_costfn::Anat::~Anat() {
+    if (tree) msmgpu_octree_destroy(tree);
+    if (thi) msmgpu_mesh_destroy(thi);
+}
+
+msmgpu_status msmgpu_costfn_set_anatomical(msmgpu_costfn* c, int ntrip, const msmgpu_anatomical* A) {
+    if (!c || ntrip <= 0 || !A || A->n_av <= 0 || !A->asource_xyz || A->n_at <= 0 || !A->asource_tri || A->n_hv <= 0 || !A->thi_xyz || A->n_ht <= 0 ||
+        !A->thi_tri || !A->atarget_xyz || !A->face_ptr || !A->face_ids || !A->bary_ptr || !A->bary_key || !A->bary_w)
+        return fail(MSMGPU_ERR_INVALID, "costfn_set_anatomical: bad arguments");
+    MSM_CUDA(cudaSetDevice(c->ctx->device));
+    cudaStream_t s = c->ctx->stream;
+    const int n_faces = A->face_ptr[ntrip];
+    if (A->face_ptr[0] != 0 || n_faces <= 0) return fail(MSMGPU_ERR_INVALID, "costfn_set_anatomical: NEARESTFACES is empty");
+    // per control triangle: the distinct _aSOURCE vertices of its faces in first-seen order (what `moved` / `transformed` hold after the
+    // loop of cpp:174-179) and, per face corner, the position of its vertex in that list
+    std::vector<int> uv_ptr(ntrip + 1, 0), uv_ids, face_local(3 * (size_t)n_faces);
+    int max_u = 0, max_f = 0;
+    for (int t = 0; t < ntrip; ++t) {
+        const int f0 = A->face_ptr[t], f1 = A->face_ptr[t + 1];
+        if (f1 <= f0) return fail(MSMGPU_ERR_INVALID, "costfn_set_anatomical: a control triangle has no anatomical face (the reference divides by zero)");
+        const size_t u0 = uv_ids.size();
+        for (int f = f0; f < f1; ++f) {
+            const int face = A->face_ids[f];
+            if (face < 0 || face >= A->n_at) return fail(MSMGPU_ERR_INVALID, "costfn_set_anatomical: face id out of range");
+            for (int i = 0; i < 3; ++i) {
+                const int v = A->asource_tri[3 * (size_t)face + i];
+                if (v < 0 || v >= A->n_av) return fail(MSMGPU_ERR_INVALID, "costfn_set_anatomical: vertex id out of range");
+                size_t k = u0;
+                while (k < uv_ids.size() && uv_ids[k] != v) ++k;
+                if (k == uv_ids.size()) uv_ids.push_back(v);
+                face_local[3 * (size_t)f + i] = (int)(k - u0);
+            }
+        }
+        uv_ptr[t + 1] = (int)uv_ids.size();
+        max_u = std::max(max_u, (int)(uv_ids.size() - u0));
+        max_f = std::max(max_f, f1 - f0);
+    }
+    for (int e = 0; e < A->bary_ptr[A->n_av]; ++e)
+        if (A->bary_key[e] < 0 || A->bary_key[e] >= c->ncp) return fail(MSMGPU_ERR_INVALID, "costfn_set_anatomical: weight key is not a control point (set the control grid first)");
+    std::unique_ptr<msmgpu_costfn::Anat> an(new msmgpu_costfn::Anat());
+    an->ntrip = ntrip; an->n_av = A->n_av; an->max_u = max_u; an->max_f = max_f;
+    an->h_face_ptr.assign(A->face_ptr, A->face_ptr + ntrip + 1);
+    MSM_TRY(msmgpu_mesh_create(c->ctx, A->n_hv, A->thi_xyz, A->n_ht, A->thi_tri, &an->thi));
+    MSM_TRY(msmgpu_octree_build(an->thi, &an->tree));
+    MSM_TRY(up(an->asource_xyz, A->asource_xyz, 3 * (size_t)A->n_av, s));
+    MSM_TRY(up(an->asource_tri, A->asource_tri, 3 * (size_t)A->n_at, s));
+    MSM_TRY(up(an->atarget_xyz, A->atarget_xyz, 3 * (size_t)A->n_hv, s));
+    MSM_TRY(up(an->face_ptr, A->face_ptr, (size_t)ntrip + 1, s));
+    MSM_TRY(up(an->face_ids, A->face_ids, (size_t)n_faces, s));
+    MSM_TRY(up(an->face_local, face_local.data(), face_local.size(), s));
+    MSM_TRY(up(an->uv_ptr, uv_ptr.data(), uv_ptr.size(), s));
+    MSM_TRY(up(an->uv_ids, uv_ids.data(), uv_ids.size(), s));
+    MSM_TRY(up(an->bary_ptr, A->bary_ptr, (size_t)A->n_av + 1, s));
+    MSM_TRY(up(an->bary_key, A->bary_key, (size_t)A->bary_ptr[A->n_av], s));
+    MSM_TRY(up(an->bary_w, A->bary_w, (size_t)A->bary_ptr[A->n_av], s));
+    MSM_CUDA(cudaStreamSynchronize(s));
+    c->anat = std::move(an);
+    return MSMGPU_OK;
 }
 
 msmgpu_status msmgpu_costfn_set_cpgrid_ho(msmgpu_costfn* c, int ncp, const double* cp_xyz, int ntri, const int32_t* cp_tri,

@@ -93,6 +93,17 @@ class NonLinearSRegDiscreteCostFunction:
         self._rot = f64(ROTATIONS).reshape(-1, 9)
         self._orig = f64(ORIG_xyz).reshape(-1, 3)
 
+    # set_anatomical + set_anatomical_neighbourhood (h:160-169): what regoption 4/5 reads (cpp:169-181, 245-301)
+    def set_anatomical(self, asource_xyz, asource_tri, thi_xyz, thi_tri, atarget_xyz, face_ptr, face_ids, bary_ptr, bary_key, bary_w):
+        k = dict(asource_xyz=f64(asource_xyz), asource_tri=capi.i32(asource_tri), thi_xyz=f64(thi_xyz), thi_tri=capi.i32(thi_tri),
+                 atarget_xyz=f64(atarget_xyz), face_ptr=capi.i32(face_ptr), face_ids=capi.i32(face_ids), bary_ptr=capi.i32(bary_ptr),
+                 bary_key=capi.i32(bary_key), bary_w=f64(bary_w))
+        A = capi.Anatomical(len(k["asource_xyz"].reshape(-1, 3)), k["asource_xyz"].ctypes.data, len(k["asource_tri"].reshape(-1, 3)), k["asource_tri"].ctypes.data,
+                            len(k["thi_xyz"].reshape(-1, 3)), k["thi_xyz"].ctypes.data, len(k["thi_tri"].reshape(-1, 3)), k["thi_tri"].ctypes.data,
+                            k["atarget_xyz"].ctypes.data, k["face_ptr"].ctypes.data, k["face_ids"].ctypes.data, k["bary_ptr"].ctypes.data,
+                            k["bary_key"].ctypes.data, k["bary_w"].ctypes.data)
+        check(self.L.msmgpu_costfn_set_anatomical(self.h, len(k["face_ptr"]) - 1, C.byref(A)))
+
     def computeTripletCostList(self, triplet, la, lb, lc):
         """computeTripletCost (cpp:135-188) for arrays of requests."""
         t, a, b, c_ = (capi.i32(x) for x in (triplet, la, lb, lc))

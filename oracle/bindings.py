@@ -57,6 +57,24 @@ def _i32(a):
 # --------------------------------------------------------------------------------------
 # our restatement
 # --------------------------------------------------------------------------------------
+class Anat(C.Structure):
+    """orc_anat / refmr_anat / msmgpu_anatomical: the anatomical meshes and maps of regoption 4/5 (DiscreteCostFunction.h:164-169)."""
+    _fields_ = [("n_av", _i), ("asource_xyz", _vp), ("n_at", _i), ("asource_tri", _vp),
+                ("n_hv", _i), ("thi_xyz", _vp), ("n_ht", _i), ("thi_tri", _vp), ("atarget_xyz", _vp),
+                ("face_ptr", _vp), ("face_ids", _vp), ("bary_ptr", _vp), ("bary_key", _vp), ("bary_w", _vp)]
+
+
+def make_anat(a):
+    """dict with asource_xyz, asource_tri, thi_xyz, thi_tri, atarget_xyz, face_ptr, face_ids, bary_ptr, bary_key, bary_w -> (Anat, keep-alive dict)"""
+    keep = dict(asource_xyz=_f64(a["asource_xyz"]), asource_tri=_i32(a["asource_tri"]), thi_xyz=_f64(a["thi_xyz"]), thi_tri=_i32(a["thi_tri"]),
+                atarget_xyz=_f64(a["atarget_xyz"]), face_ptr=_i32(a["face_ptr"]), face_ids=_i32(a["face_ids"]), bary_ptr=_i32(a["bary_ptr"]),
+                bary_key=_i32(a["bary_key"]), bary_w=_f64(a["bary_w"]))
+    A = Anat(len(keep["asource_xyz"]), _p(keep["asource_xyz"]), len(keep["asource_tri"]), _p(keep["asource_tri"]),
+             len(keep["thi_xyz"]), _p(keep["thi_xyz"]), len(keep["thi_tri"]), _p(keep["thi_tri"]), _p(keep["atarget_xyz"]),
+             _p(keep["face_ptr"]), _p(keep["face_ids"]), _p(keep["bary_ptr"]), _p(keep["bary_key"]), _p(keep["bary_w"]))
+    return A, keep
+
+
 class Oracle:
     _lib = None
 
@@ -96,6 +114,8 @@ class Oracle:
             L.orc_rigid.argtypes = [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _d, _d, _vp, _vp, _vp, _vp, _i]
             L.orc_triplet_costs.argtypes = [_i, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp,
                                             _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _d, _d, _d, _d, _d, _vp, _i]
+            L.orc_triplet_costs_anat.argtypes = [_i, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp,
+                                                 _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _d, _d, _d, _d, _d, _i, _vp, _vp, _i]
             cls._lib = L
         return cls._lib
 
@@ -296,7 +316,7 @@ def oracle_ho_patches(cp_xyz, cp_tri, src_xyz):
 
 
 def oracle_triplet_costs(kind, simmeasure, tree, cp_xyz, orig_cp_xyz, rot, labels, triplets, req_t, req_la, req_lb, req_lc,
-                         src_xyz, prow, pmem, src_feat, ref_feat, cfw, absw, lambda_, mu=0.4, kappa=1.6, k_exp=2.0, rexp=2.0, nthreads=8):
+                         src_xyz, prow, pmem, src_feat, ref_feat, cfw, absw, lambda_, mu=0.4, kappa=1.6, k_exp=2.0, rexp=2.0, nthreads=8, rmode=3, anat=None):
     cp, org, rot, labels = _f64(cp_xyz), _f64(orig_cp_xyz), _f64(rot), _f64(labels)
     trip = _i32(triplets)
     rt, la, lb, lc = _i32(req_t), _i32(req_la), _i32(req_lb), _i32(req_lc)
@@ -307,9 +327,11 @@ def oracle_triplet_costs(kind, simmeasure, tree, cp_xyz, orig_cp_xyz, rot, label
     cfw_rows = 0 if cfw is None else np.atleast_2d(cfw).shape[0]
     cfw_a = None if cfw is None else _f64(np.atleast_2d(cfw))
     out = np.zeros(len(rt))
-    e = Oracle.lib().orc_triplet_costs(kind, simmeasure, tree.h if tree is not None else None, len(cp), _p(cp), _p(org), _p(rot), len(labels), _p(labels),
-                                       len(trip), _p(trip), len(rt), _p(rt), _p(la), _p(lb), _p(lc), len(src), _p(src), _p(prow), _p(pmem),
-                                       sf.shape[0], _p(sf), _p(rf), cfw_rows, _p(cfw_a), _p(absw), lambda_, mu, kappa, k_exp, rexp, _p(out), nthreads)
+    A, keep = make_anat(anat) if anat is not None else (None, None)
+    e = Oracle.lib().orc_triplet_costs_anat(kind, simmeasure, tree.h if tree is not None else None, len(cp), _p(cp), _p(org), _p(rot), len(labels), _p(labels),
+                                            len(trip), _p(trip), len(rt), _p(rt), _p(la), _p(lb), _p(lc), len(src), _p(src), _p(prow), _p(pmem),
+                                            sf.shape[0], _p(sf), _p(rf), cfw_rows, _p(cfw_a), _p(absw), lambda_, mu, kappa, k_exp, rexp, int(rmode),
+                                            C.byref(A) if A is not None else None, _p(out), nthreads)
     if e:
         raise RuntimeError("oracle triplet costs: a query failed")
     return out
@@ -592,6 +614,11 @@ class RefMR:
             L.refmr_triplet.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp,
                                         _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp,
                                         _d, _d, _d, _d, _d, _i, _vp, _vp, _vp, _i, _i]
+            if hasattr(L, "refmr_triplet_anat"):
+                L.refmr_triplet_anat.restype = _i
+                L.refmr_triplet_anat.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp,
+                                                 _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp,
+                                                 _d, _d, _d, _d, _d, _i, _vp, _vp, _vp, _vp, _i, _i]
             L.refmr_pairwise_reg.argtypes = [_i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _d, _d, _d, _i, _vp, _vp, _vp, _vp]
             L.refmr_group_pair_costs.argtypes = [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _d, _i, _vp,
                                                  _i, _vp, _vp, _vp, _vp, _vp, _i]
@@ -654,8 +681,8 @@ def refmr_rigid(tgt_xyz, tgt_tri, src_xyz, src_tri, src_feat, ref_feat, simmeasu
 
 
 def refmr_triplet(kind, simmeasure, tgt_xyz, tgt_tri, cp_xyz, cp_tri, orig_cp_xyz, rot, labels, triplets, req_t, req_la, req_lb, req_lc,
-                  src_xyz, src_tri, src_feat, ref_feat, cfw, absw, lambda_, mu=0.4, kappa=1.6, k_exp=2.0, rexp=2.0, rmode=3, nthreads=8):
-    """The reference's computeTripletCost for a request list. -> (costs [n], HO patch rowptr, members)"""
+                  src_xyz, src_tri, src_feat, ref_feat, cfw, absw, lambda_, mu=0.4, kappa=1.6, k_exp=2.0, rexp=2.0, rmode=3, nthreads=8, anat=None):
+    """The reference's computeTripletCost for a request list. -> (costs [n], HO patch rowptr, members). anat: the inputs of regoption 4/5."""
     tx, tt, cp, ct, org, rot, labels = _f64(tgt_xyz), _i32(tgt_tri), _f64(cp_xyz), _i32(cp_tri), _f64(orig_cp_xyz), _f64(rot), _f64(labels)
     trip, rt, la, lb, lc = _i32(triplets), _i32(req_t), _i32(req_la), _i32(req_lb), _i32(req_lc)
     sx, st = _f64(src_xyz), _i32(src_tri)
@@ -665,9 +692,11 @@ def refmr_triplet(kind, simmeasure, tgt_xyz, tgt_tri, cp_xyz, cp_tri, orig_cp_xy
     absw_a = None if absw is None else _f64(absw)
     out = np.zeros(len(rt))
     rowptr, mem = np.zeros(len(ct) + 1, np.int32), np.zeros(len(sx), np.int32)
-    n = RefMR.lib().refmr_triplet(kind, simmeasure, len(tx), _p(tx), len(tt), _p(tt), len(cp), _p(cp), len(ct), _p(ct), _p(org), _p(rot), len(labels), _p(labels),
-                                  len(trip), _p(trip), len(rt), _p(rt), _p(la), _p(lb), _p(lc), len(sx), _p(sx), len(st), _p(st), sf.shape[0], _p(sf), _p(rf),
-                                  cfw_rows, _p(cfw_a), _p(absw_a), lambda_, mu, kappa, k_exp, rexp, rmode, _p(out), _p(rowptr), _p(mem), len(sx), nthreads)
+    A, keep = make_anat(anat) if anat is not None else (None, None)
+    n = RefMR.lib().refmr_triplet_anat(kind, simmeasure, len(tx), _p(tx), len(tt), _p(tt), len(cp), _p(cp), len(ct), _p(ct), _p(org), _p(rot), len(labels),
+                                       _p(labels), len(trip), _p(trip), len(rt), _p(rt), _p(la), _p(lb), _p(lc), len(sx), _p(sx), len(st), _p(st),
+                                       sf.shape[0], _p(sf), _p(rf), cfw_rows, _p(cfw_a), _p(absw_a), lambda_, mu, kappa, k_exp, rexp, rmode,
+                                       C.byref(A) if A is not None else None, _p(out), _p(rowptr), _p(mem), len(sx), nthreads)
     if n < 0:
         raise RuntimeError("reference triplet costs failed")
     return out, rowptr, mem[:n].copy()

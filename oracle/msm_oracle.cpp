@@ -938,8 +938,27 @@ int orc_triplet_costs(int kind, int simmeasure, const orc_octree* T, int ncp, co
                       int nsrc, const double* src_xyz, const int* prow, const int* pmem, int D, const double* src_feat,
                       const double* ref_feat, int cfw_rows, const double* cfw, const double* absw,
                       double lambda, double mu, double kappa, double k_exp, double rexp, double* out, int nthreads) {
+    return orc_triplet_costs_anat(kind, simmeasure, T, ncp, cp_xyz, orig_cp_xyz, rot, L, labels, ntrip, triplets, n, req_triplet, req_la, req_lb, req_lc,
+                                  nsrc, src_xyz, prow, pmem, D, src_feat, ref_feat, cfw_rows, cfw, absw, lambda, mu, kappa, k_exp, rexp, 3, nullptr, out,
+                                  nthreads);
+}
+
+// the same with the regulariser of regoption 4/5 when rmode >= 4 (anat != NULL): mean strain energy of the anatomical faces of the
+// triplet, each deformed by deform_anatomy (DiscreteCostFunction.cpp:169-181, 245-301)
+int orc_triplet_costs_anat(int kind, int simmeasure, const orc_octree* T, int ncp, const double* cp_xyz, const double* orig_cp_xyz,
+                           const double* rot, int L, const double* labels, int ntrip, const int* triplets,
+                           int n, const int* req_triplet, const int* req_la, const int* req_lb, const int* req_lc,
+                           int nsrc, const double* src_xyz, const int* prow, const int* pmem, int D, const double* src_feat,
+                           const double* ref_feat, int cfw_rows, const double* cfw, const double* absw,
+                           double lambda, double mu, double kappa, double k_exp, double rexp, int rmode, const orc_anat* anat,
+                           double* out, int nthreads) {
     int err = 0;
     const int nvt = T ? T->nv : 0;
+    orc_octree* AT = nullptr;   // anattree = Octree(_TARGEThi), DiscreteCostFunction.h:160-163
+    if (rmode >= 4) {
+        if (!anat) return 3;
+        AT = orc_octree_build(anat->n_hv, anat->thi_xyz, anat->n_ht, anat->thi_tri);
+    }
     #pragma omp parallel for num_threads(nthreads > 0 ? nthreads : 1)
     for (int r = 0; r < n; ++r) {
         const int t = req_triplet[r];
@@ -1003,9 +1022,56 @@ int orc_triplet_costs(int kind, int simmeasure, const orc_octree* T, int ncp, co
             }
             likelihood = (absw[ids[0]] + absw[ids[1]] + absw[ids[2]]) / 3.0 * cost;
         }
-        const double W = triangular_strain(org, def, mu, kappa, k_exp); // rmode 2/3, cpp:158-166
+        double W;
+        if (rmode <= 3) {
+            W = triangular_strain(org, def, mu, kappa, k_exp); // rmode 2/3, cpp:158-166
+        } else {   // rmode 4/5, cpp:169-181
+            const int f0 = anat->face_ptr[t], f1 = anat->face_ptr[t + 1];
+            std::map<int, P3> transformed;   // `moved2` / `transformed_points`: every vertex of the neighbourhood is deformed once per request
+            W = 0.0;
+            for (int f = f0; f < f1; ++f) {
+                const int face = anat->face_ids[f];
+                P3 O[3], Fv[3];
+                for (int i = 0; i < 3; ++i) {   // deform_anatomy, cpp:245-301
+                    const int tindex = anat->asource_tri[3 * face + i];
+                    O[i] = P3{anat->asource_xyz[3 * tindex], anat->asource_xyz[3 * tindex + 1], anat->asource_xyz[3 * tindex + 2]};
+                    auto it = transformed.find(tindex);
+                    if (it == transformed.end()) {
+                        P3 np{0, 0, 0};
+                        // `vertex[it.first]` on a std::map holding the three displaced control points: a key that is not one of the
+                        // triplet's nodes default-constructs a zero Point (mesh_registration.cpp:307-327 overwrites the weights of a
+                        // vertex shared by several control triangles with those of the LAST one)
+                        for (int e = anat->bary_ptr[tindex]; e < anat->bary_ptr[tindex + 1]; ++e) {
+                            P3 v{0, 0, 0};
+                            for (int k = 0; k < 3; ++k) if (ids[k] == anat->bary_key[e]) v = def[k];
+                            const P3 c = mul(v, anat->bary_w[e]);
+                            np.X += c.X; np.Y += c.Y; np.Z += c.Z;
+                        }
+                        int st;
+                        const int tt = closest_triangle(AT, np, &st, nullptr);
+                        P3 res{0, 0, 0};
+                        if (tt < 0) {
+                            // the reference catches the exception and continues with an all-zero Triangle (ids 0, 1, 2): its weights are 0/0
+                            res.X = res.Y = res.Z = std::numeric_limits<double>::quiet_NaN();
+                        } else {
+                            int idx[3]; double w[3];
+                            const int ne = bary_weights_of(AT, np, tt, idx, w);
+                            for (int j = 0; j < ne; ++j) {
+                                const P3 c = mul(P3{anat->atarget_xyz[3 * idx[j]], anat->atarget_xyz[3 * idx[j] + 1], anat->atarget_xyz[3 * idx[j] + 2]}, w[j]);
+                                res.X += c.X; res.Y += c.Y; res.Z += c.Z;
+                            }
+                        }
+                        it = transformed.emplace(tindex, res).first;
+                    }
+                    Fv[i] = it->second;
+                }
+                W += triangular_strain(O, Fv, mu, kappa, k_exp);
+            }
+            W = W / (double)(f1 - f0);
+        }
         out[r] = likelihood + lambda * std::pow(W, rexp);
     }
+    if (AT) orc_octree_free(AT);
     return err;
 }
 

@@ -106,6 +106,22 @@ int orc_ho_patches(int ncp, const double* cp_xyz, int ntri, const int* cp_tri, i
 
 /* computeTripletCost (DiscreteCostFunction.cpp:135-188) for n requests; PARITY UNPINNED (see msm_oracle.cpp).
  * kind 0..2: likelihood 0; 3: HOUnivariate; 4: HOMultivariate. rmode 2/3 (spherical strain) only. */
+/* regoption 4/5 (anatomical strain, DiscreteCostFunction.cpp:169-181, 245-301): the meshes and maps of set_anatomical /
+ * set_anatomical_neighbourhood (DiscreteCostFunction.h:160-168). Same layout as msmgpu_anatomical (include/msmgpu.h). */
+typedef struct {
+    int n_av; const double* asource_xyz; int n_at; const int* asource_tri;     /* _aSOURCE */
+    int n_hv; const double* thi_xyz; int n_ht; const int* thi_tri;             /* _TARGEThi (the octree `anattree` is built over it) */
+    const double* atarget_xyz;                                                 /* _aTARGET coordinates [n_hv][3] */
+    const int* face_ptr; const int* face_ids;                                  /* NEARESTFACES as CSR over the triplets */
+    const int* bary_ptr; const int* bary_key; const double* bary_w;            /* _ANATbaryweights as CSR over _aSOURCE vertices, ascending key */
+} orc_anat;
+int orc_triplet_costs_anat(int kind, int simmeasure, const orc_octree* T, int ncp, const double* cp_xyz, const double* orig_cp_xyz,
+                           const double* rot, int L, const double* labels, int ntrip, const int* triplets,
+                           int n, const int* req_triplet, const int* req_la, const int* req_lb, const int* req_lc,
+                           int nsrc, const double* src_xyz, const int* prow, const int* pmem, int D, const double* src_feat,
+                           const double* ref_feat, int cfw_rows, const double* cfw, const double* absw,
+                           double lambda, double mu, double kappa, double k_exp, double rexp, int rmode, const orc_anat* anat,
+                           double* out, int nthreads);
 int orc_triplet_costs(int kind, int simmeasure, const orc_octree* T, int ncp, const double* cp_xyz, const double* orig_cp_xyz,
                       const double* rot, int L, const double* labels, int ntrip, const int* triplets,
                       int n, const int* req_triplet, const int* req_la, const int* req_lb, const int* req_lc,

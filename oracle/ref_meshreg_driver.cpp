@@ -161,6 +161,23 @@ int refmr_unary(int kind, int simmeasure, int nv_t, const double* tgt_xyz, int n
 // (cpp:487-531, 565-618). rmode 2/3 only (spherical strain, reg_tools.cpp:551-743). orig_cp_xyz supplies the
 // coordinates _ORIG.get_coord(node) reads for the undeformed triangle. Returns HO patch entries (kinds 3/4; CSR
 // over CP-grid triangles) or 0, -1 on a reference exception.
+// the anatomical meshes and maps of regoption 4/5 (set_anatomical / set_anatomical_neighbourhood, DiscreteCostFunction.h:164-169);
+// same layout as orc_anat (oracle/msm_oracle.h) and msmgpu_anatomical (include/msmgpu.h)
+struct refmr_anat {
+    int n_av; const double* asource_xyz; int n_at; const int* asource_tri;
+    int n_hv; const double* thi_xyz; int n_ht; const int* thi_tri;
+    const double* atarget_xyz;
+    const int* face_ptr; const int* face_ids;
+    const int* bary_ptr; const int* bary_key; const double* bary_w;
+};
+int refmr_triplet_anat(int kind, int simmeasure, int nv_t, const double* tgt_xyz, int nt_t, const int* tgt_tri,
+                  int ncp, const double* cp_xyz, int ncp_tri, const int* cp_tri, const double* orig_cp_xyz,
+                  const double* rot, int L, const double* labels, int ntrip, const int* triplets,
+                  int n, const int* req_triplet, const int* req_la, const int* req_lb, const int* req_lc,
+                  int nsrc, const double* src_xyz, int nsrc_tri, const int* src_tri, int D, const double* src_feat, const double* ref_feat,
+                  int cfw_rows, const double* cfw, const double* absw_in,
+                  double lambda, double mu, double kappa, double k_exp, double rexp, int rmode, const refmr_anat* anat,
+                  double* out, int* patch_rowptr, int* patch_members, int cap, int nthreads);
 int refmr_triplet(int kind, int simmeasure, int nv_t, const double* tgt_xyz, int nt_t, const int* tgt_tri,
                   int ncp, const double* cp_xyz, int ncp_tri, const int* cp_tri, const double* orig_cp_xyz,
                   const double* rot, int L, const double* labels, int ntrip, const int* triplets,
@@ -168,6 +185,19 @@ int refmr_triplet(int kind, int simmeasure, int nv_t, const double* tgt_xyz, int
                   int nsrc, const double* src_xyz, int nsrc_tri, const int* src_tri, int D, const double* src_feat, const double* ref_feat,
                   int cfw_rows, const double* cfw, const double* absw_in,
                   double lambda, double mu, double kappa, double k_exp, double rexp, int rmode,
+                  double* out, int* patch_rowptr, int* patch_members, int cap, int nthreads) {
+    return refmr_triplet_anat(kind, simmeasure, nv_t, tgt_xyz, nt_t, tgt_tri, ncp, cp_xyz, ncp_tri, cp_tri, orig_cp_xyz, rot, L, labels, ntrip, triplets,
+                              n, req_triplet, req_la, req_lb, req_lc, nsrc, src_xyz, nsrc_tri, src_tri, D, src_feat, ref_feat, cfw_rows, cfw, absw_in,
+                              lambda, mu, kappa, k_exp, rexp, rmode, nullptr, out, patch_rowptr, patch_members, cap, nthreads);
+}
+
+int refmr_triplet_anat(int kind, int simmeasure, int nv_t, const double* tgt_xyz, int nt_t, const int* tgt_tri,
+                  int ncp, const double* cp_xyz, int ncp_tri, const int* cp_tri, const double* orig_cp_xyz,
+                  const double* rot, int L, const double* labels, int ntrip, const int* triplets,
+                  int n, const int* req_triplet, const int* req_la, const int* req_lb, const int* req_lc,
+                  int nsrc, const double* src_xyz, int nsrc_tri, const int* src_tri, int D, const double* src_feat, const double* ref_feat,
+                  int cfw_rows, const double* cfw, const double* absw_in,
+                  double lambda, double mu, double kappa, double k_exp, double rexp, int rmode, const refmr_anat* anat,
                   double* out, int* patch_rowptr, int* patch_members, int cap, int nthreads) {
     try {
         std::vector<double> sep(ncp, 0.0);
@@ -185,6 +215,18 @@ int refmr_triplet(int kind, int simmeasure, int nv_t, const double* tgt_xyz, int
             total = flatten_lists(cf._sourceinrange, patch_rowptr, patch_members, cap);
         }
         cf.setTriplets(trip.data());
+        if (anat) {   // what Mesh_registration::run_discrete_opt hands over before the optimisation (mesh_registration.cpp:93-98)
+            Mesh thi = make_mesh(anat->n_hv, anat->thi_xyz, anat->n_ht, anat->thi_tri);
+            cf.set_anatomical(thi, make_mesh(anat->n_hv, anat->atarget_xyz, anat->n_ht, anat->thi_tri), thi,
+                              make_mesh(anat->n_av, anat->asource_xyz, anat->n_at, anat->asource_tri));
+            std::vector<std::map<int, double>> bw(anat->n_av);
+            for (int v = 0; v < anat->n_av; ++v)
+                for (int e = anat->bary_ptr[v]; e < anat->bary_ptr[v + 1]; ++e) bw[v][anat->bary_key[e]] = anat->bary_w[e];
+            std::vector<std::vector<int>> nf(ntrip);
+            for (int t = 0; t < ntrip; ++t) nf[t].assign(anat->face_ids + anat->face_ptr[t], anat->face_ids + anat->face_ptr[t + 1]);
+            cf.set_anatomical_neighbourhood(bw, nf);
+            cf.initialize_regulariser();
+        }
         #pragma omp parallel for num_threads(nthreads) schedule(dynamic, 64)
         for (int i = 0; i < n; ++i) out[i] = cf.computeTripletCost(req_triplet[i], req_la[i], req_lb[i], req_lc[i]);
         return total;

@@ -52,6 +52,47 @@ def triplet_setup(O, cp_level, data_level, D):
     return s
 
 
+def anat_case(O, s, depth=1):
+    """Inputs of the anatomical strain regulariser (regoption 4/5, DiscreteCostFunction.cpp:169-181, 245-301) for a triplet_setup() case, built
+    the way Mesh_registration::resample_anatomy does (mesh_registration.cpp:251-331): the anatomical grid is the control grid subdivided
+    `depth` times, NEARESTFACES[t] = its faces inside control triangle t, _ANATbaryweights[v] = barycentric weights of vertex v in a control
+    triangle that holds it (the LAST one that touches it, like the reference's loop), _aSOURCE / _aTARGET = two synthetic folded surfaces."""
+    level = {12: 0, 42: 1, 162: 2, 642: 3, 2562: 4}[len(s["cp"])]
+    aico, a_tri = synth.icosphere(level + depth)
+    cp, cp_tri = s["cp"], s["cp_tri"]
+    cen = aico[a_tri].mean(axis=1)
+    cen = cen / np.linalg.norm(cen, axis=1, keepdims=True) * 100.0
+    owner = O.OracleOctree(cp, cp_tri).query(cen)[0]                       # control triangle of every anatomical face
+    order = np.argsort(owner, kind="stable")
+    face_ptr = np.concatenate([[0], np.cumsum(np.bincount(owner, minlength=len(cp_tri)))]).astype(np.int32)
+    face_ids = order.astype(np.int32)
+    keys = np.zeros((len(aico), 3), np.int32)
+    wts = np.zeros((len(aico), 3))
+
+    def area(a, b, c):
+        return 0.5 * np.linalg.norm(np.cross(b - a, c - a), axis=-1)
+
+    for t in range(len(cp_tri)):                                            # ascending: the last control triangle touching a vertex wins
+        fs = face_ids[face_ptr[t]:face_ptr[t + 1]]
+        vs = np.unique(a_tri[fs])
+        v0, v1, v2 = cp[cp_tri[t, 0]], cp[cp_tri[t, 1]], cp[cp_tri[t, 2]]
+        nrm = np.cross(v2 - v0, v1 - v0)
+        nrm /= np.linalg.norm(nrm)
+        P = aico[vs]
+        PP = P - ((P - v0) @ nrm)[:, None] * nrm[None, :]
+        w = np.stack([area(PP, v1, v2), area(PP, v0, v2), area(PP, v0, v1)], axis=1)
+        w /= w.sum(axis=1, keepdims=True)
+        o = np.argsort(cp_tri[t])
+        keys[vs] = cp_tri[t][o]
+        wts[vs] = w[:, o]
+    f1, f2 = synth.smooth_fields(aico, 1, seed0=71)[0], synth.smooth_fields(aico, 1, seed0=83)[0]
+    asource = aico * (0.62 + 0.12 * f1 / np.abs(f1).max())[:, None]
+    moved = synth.smooth_warp(aico, max_disp=1.0, seed=91)
+    atarget = moved * (0.60 + 0.14 * f2 / np.abs(f2).max())[:, None]
+    return dict(asource_xyz=asource, asource_tri=a_tri, thi_xyz=aico, thi_tri=a_tri, atarget_xyz=atarget, face_ptr=face_ptr, face_ids=face_ids,
+                bary_ptr=(3 * np.arange(len(aico) + 1)).astype(np.int32), bary_key=keys.reshape(-1), bary_w=wts.reshape(-1))
+
+
 def group_setup(S=3, cp_level=2, data_level=4, tpl_level=4, D=2):
     cp0, cp_tri = synth.icosphere(cp_level)
     dxyz0, dtri = synth.icosphere(data_level)

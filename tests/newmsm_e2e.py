@@ -44,6 +44,7 @@ def read_asc(path):
 
 
 GROUP = False   # --group: the gMSM driver (src/newmsm.cpp:14-28)
+ANAT = False    # aMSM: --inanat / --refanat (anatomical strain, regoption 5)
 MASK = False    # --mask: groupwise run with a cost mask (src/newmsm.cpp:25, DiscreteGroupModel.cpp:164)
 
 
@@ -60,6 +61,8 @@ def run(binary, case, conf, out, threads, trace, extra_env=None):
         cmd = [binary, "--inmesh=" + os.path.join(case, "sphere.asc"), "--refmesh=" + os.path.join(case, "sphere.asc"),
                "--indata=" + os.path.join(case, "indata.txt"), "--refdata=" + os.path.join(case, "refdata.txt"),
                "--conf=" + conf, "--out=" + out + "/", "-f", "ASCII"]
+        if ANAT:
+            cmd += ["--inanat=" + os.path.join(case, "inanat.asc"), "--refanat=" + os.path.join(case, "refanat.asc")]
     t0 = time.perf_counter()
     r = subprocess.run(cmd, env=env, capture_output=True, text=True)
     dt = time.perf_counter() - t0
@@ -73,7 +76,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--level", type=int, default=6)
     ap.add_argument("--D", type=int, default=1)
-    ap.add_argument("--config", default="MSMpair", choices=["MSMpair", "MSMpairAffine", "MSMAllStrain", "MSMstrain", "sMSMSTRcp5", "gMSM"])
+    ap.add_argument("--config", default="MSMpair", choices=["MSMpair", "MSMpairAffine", "MSMAllStrain", "MSMstrain", "sMSMSTRcp5", "gMSM", "aMSMSTR"])
     ap.add_argument("--group", type=int, default=0, help="groupwise (gMSM) run with this many subjects (integration/newmsm_gpu_group_hooks.cpp binds "
                                                            "estimate_pairs, get_patch_data and the pair / triplet costs)")
     ap.add_argument("--levels-drop", type=int, default=0)
@@ -98,7 +101,8 @@ def main():
     ap.add_argument("--cpu-trace-in", default="", help="compare with this recorded single-thread CPU trace instead of running that arm "
                                                          "(the case is seeded, so the inputs are identical)")
     a = ap.parse_args()
-    global GROUP, MASK
+    global GROUP, MASK, ANAT
+    ANAT = a.config == "aMSMSTR"
     GROUP = a.group > 0
     MASK = bool(a.mask)
     work = tempfile.mkdtemp(prefix="newmsm_case_")

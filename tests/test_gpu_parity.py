@@ -521,7 +521,7 @@ def test_triplet_costs_same_with_host_finish():
     import subprocess, sys
     env = dict(os.environ, MSMGPU_DEVICE_POW="0")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k",
-                        "test_triplet_costs_vs_reference_golden or test_group_costs_vs_reference_golden or test_group_triplet_nan"],
+                        "test_triplet_costs_vs_reference_golden or test_group_costs_vs_reference_golden or test_group_triplet_nan or test_anatomical_strain"],
                        env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " passed" in r.stdout
@@ -664,6 +664,62 @@ def test_triplet_costs_vs_reference_golden(R, oracle_built):
         got = cf.computeTripletCostList(rt, la, lb, lc)
         ref = g[f"triplet_k{kind}"]
         assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("kind,D,depth", [(0, 1, 1), (0, 1, 2), (3, 1, 2)])
+def test_anatomical_strain_vs_reference_golden(R, oracle_built, kind, D, depth):
+    """regoption 5 (anatomical strain, DiscreteCostFunction.cpp:169-181, 245-301): list form vs the reference's own outputs, and Fusion's
+    8-combination batch vs the list form."""
+    from newmsm_b200 import discrete_cost as DC
+    from cost_cases import GOLDEN_CP, GOLDEN_DATA, anat_case, golden_digest
+    g = load("anat.npz")
+    s = triplet_setup(oracle_built, GOLDEN_CP, GOLDEN_DATA, D)
+    a = anat_case(oracle_built, s, depth)
+    assert np.array_equal(np.concatenate([golden_digest(s), golden_digest(a)]), g[f"k{kind}_d{depth}_digest"]), "seeded inputs drifted: regenerate"
+    rt, la, lb, lc = s["req"]
+    cfw = np.random.default_rng(5).uniform(0.2, 1.0, size=(D, len(s["src"])))
+    cls = {0: DC.UnivariateNonLinearSRegDiscreteCostFunction, 3: DC.HOUnivariateNonLinearSRegDiscreteCostFunction}[kind]
+    cf = cls(simmeasure=2)
+    cf.set_meshes(R.Mesh(s["xyz"], s["tri"]), s["src"], s["src_feat"], s["ref_feat"])
+    if kind >= 3:
+        cf.reset_CPgrid(s["cp_now"], s["cp_tri"], HIGHREScfweight=cfw, AbsoluteWeights=s["absw"])
+    else:
+        cf.reset_CPgrid(s["cp_now"], s["maxsep"], 1.0)
+    cf.set_parameters(0.05, regularisermode=5)
+    cf.setTriplets(s["triplets"], s["labels"], s["rot_now"], s["orig"])
+    with pytest.raises(RuntimeError):
+        cf.computeTripletCostList(rt, la, lb, lc)            # regoption 4/5 before set_anatomical: an error, not a silent spherical strain
+    cf.set_anatomical(**a)
+    got = cf.computeTripletCostList(rt, la, lb, lc)
+    assert np.array_equal(got, g[f"k{kind}_d{depth}"])
+    labeling = np.random.default_rng(3).integers(0, len(s["labels"]), len(s["cp"])).astype(np.int32)
+    batch = cf.computeTripletCostsForLabel(labeling, 2)
+    T = len(s["triplets"])
+    tt = np.repeat(np.arange(T, dtype=np.int32), 8)
+    combo = np.tile(np.arange(8), T)
+    pick = lambda k, bit: np.where((combo >> bit) & 1, 2, labeling[s["triplets"][tt, k]]).astype(np.int32)
+    assert np.array_equal(batch.reshape(-1), cf.computeTripletCostList(tt, pick(0, 2), pick(1, 1), pick(2, 0)))
+
+
+@pytest.mark.parametrize("kexp,rexp", [(1.5, 1.3), (2.0, 1.0)])
+def test_anatomical_strain_vs_oracle(R, oracle_built, kexp, rexp):
+    """The same at a larger grid (control ico3, anatomical ico5) and non-default exponents vs the oracle (pinned in test_oracle_vs_refmr.py)."""
+    from newmsm_b200 import discrete_cost as DC
+    from cost_cases import anat_case
+    s = triplet_setup(oracle_built, 3, 5, 1)
+    a = anat_case(oracle_built, s, 2)
+    rt, la, lb, lc = s["req"]
+    cf = DC.UnivariateNonLinearSRegDiscreteCostFunction()
+    cf.set_meshes(R.Mesh(s["xyz"], s["tri"]), s["src"], s["src_feat"], s["ref_feat"])
+    cf.reset_CPgrid(s["cp_now"], s["maxsep"], 1.0)
+    cf.set_parameters(0.1, 0.4, 1.6, kexp, rexp, 4)
+    cf.setTriplets(s["triplets"], s["labels"], s["rot_now"], s["orig"])
+    cf.set_anatomical(**a)
+    got = cf.computeTripletCostList(rt, la, lb, lc)
+    ref = oracle_built.oracle_triplet_costs(0, 2, None, s["cp_now"], s["orig"], s["rot_now"], s["labels"], s["triplets"], rt, la, lb, lc,
+                                            s["src"], None, None, s["src_feat"], s["ref_feat"], None, np.ones(len(s["cp"])), 0.1, 0.4, 1.6, kexp, rexp,
+                                            rmode=4, anat=a)
+    assert np.array_equal(got, ref)
 
 
 def test_group_costs_vs_reference_golden(R, oracle_built):

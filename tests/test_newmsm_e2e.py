@@ -21,6 +21,7 @@ BINS = [os.path.join(ROOT, "integration", "_build", "newmsm_gpu"), os.path.join(
     ("MSMpairAffine", 1, ["--levels-drop", "1", "--it-scale", "0.2"]),     # the shipped basic config: AFFINE level (csrc/rigid.cu through integration/newmsm_gpu_rigid_hooks.cpp) + DISCRETE levels
     ("MSMAllStrain", 3, ["--levels-drop", "1", "--it-scale", "0.1"]),       # HOCR, HO multivariate triplet likelihood, strain regulariser
     ("MSMstrain", 1, ["--levels-drop", "2", "--it-scale", "0.1"]),         # HOCR, per-call unary costs from the device table + strain-only triplets
+    ("aMSMSTR", 1, ["--levels-drop", "2", "--it-scale", "0.05"]),           # aMSM: anatomical strain (regoption 5) with --inanat / --refanat, triclique likelihood
     ("gMSM", 1, ["--levels-drop", "2", "--it-scale", "0.25", "--group", "3"]),   # groupwise driver: estimate_pairs, get_patch_data and the pair / triplet costs on the device (integration/newmsm_gpu_group_hooks.cpp)
 ])
 def test_newmsm_labels_bit_exact(config, D, extra):

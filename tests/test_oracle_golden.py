@@ -176,3 +176,23 @@ def test_exclusion_masks_golden(oracle_built):
         s1, e1 = oracle_built.oracle_smooth_data(xyz, tri, xyz, sigma, feat, excl)
         assert np.array_equal(s0, g[f"smooth{int(sigma)}"])
         assert np.array_equal(s1, g[f"smooth{int(sigma)}_masked"]) and np.array_equal(e1, g[f"smooth{int(sigma)}_excl"])
+
+
+def test_anatomical_strain_golden(oracle_built):
+    """regoption 5 triplet costs of the reference's own class (tests/golden/make_golden_anat.py) vs the restatement."""
+    from cost_cases import GOLDEN_CP, GOLDEN_DATA, anat_case, golden_digest, triplet_setup
+    O = oracle_built
+    g = load("anat.npz")
+    for kind, D, depth in ((0, 1, 1), (0, 1, 2), (3, 1, 2)):
+        s = triplet_setup(O, GOLDEN_CP, GOLDEN_DATA, D)
+        a = anat_case(O, s, depth)
+        assert np.array_equal(np.concatenate([golden_digest(s), golden_digest(a)]), g[f"k{kind}_d{depth}_digest"]), "seeded inputs drifted: regenerate"
+        rt, la, lb, lc = s["req"]
+        cfw = np.random.default_rng(5).uniform(0.2, 1.0, size=(D, len(s["src"])))
+        prow = pmem = ot = None
+        if kind >= 3:
+            prow, pmem = O.oracle_ho_patches(s["cp_now"], s["cp_tri"], s["src"])
+            ot = O.OracleOctree(s["xyz"], s["tri"])
+        got = O.oracle_triplet_costs(kind, 2, ot, s["cp_now"], s["orig"], s["rot_now"], s["labels"], s["triplets"], rt, la, lb, lc,
+                                     s["src"], prow, pmem, s["src_feat"], s["ref_feat"], cfw, s["absw"], 0.05, rmode=5, anat=a)
+        assert np.array_equal(got, g[f"k{kind}_d{depth}"])

@@ -94,6 +94,31 @@ def test_ho_triplet_likelihood(O, kind, D, sim):
     assert np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("kind,D,depth,kexp,rexp", [(0, 1, 1, 2.0, 2.0), (0, 1, 2, 1.5, 1.3), (3, 1, 2, 2.0, 2.0)])
+def test_triplet_anatomical_strain(O, kind, D, depth, kexp, rexp):
+    """regoption 5 (DiscreteCostFunction.cpp:169-181, 245-301): the restatement vs the reference's own computeTripletCost with the anatomical
+    meshes and maps handed over the way Mesh_registration does (mesh_registration.cpp:93-98)."""
+    from cost_cases import anat_case
+    s = triplet_setup(O, 3, 5, D)
+    a = anat_case(O, s, depth)
+    rt, la, lb, lc = s["req"]
+    cfw = np.random.default_rng(5).uniform(0.2, 1.0, size=(D, len(s["src"])))
+    ref, prow, pmem = O.refmr_triplet(kind, 2, s["xyz"], s["tri"], s["cp_now"], s["cp_tri"], s["orig"], s["rot_now"], s["labels"], s["triplets"],
+                                      rt, la, lb, lc, s["src"], s["tri"], s["src_feat"], s["ref_feat"], cfw, s["absw"], 0.1, 0.4, 1.6, kexp, rexp, 5,
+                                      nthreads=1, anat=a)
+    ot = O.OracleOctree(s["xyz"], s["tri"]) if kind >= 3 else None
+    got = O.oracle_triplet_costs(kind, 2, ot, s["cp_now"], s["orig"], s["rot_now"], s["labels"], s["triplets"], rt, la, lb, lc,
+                                 s["src"], prow if kind >= 3 else None, pmem if kind >= 3 else None, s["src_feat"], s["ref_feat"], cfw, s["absw"],
+                                 0.1, 0.4, 1.6, kexp, rexp, rmode=5, anat=a)
+    assert np.all(np.isfinite(ref)) and (ref == 1e7 * 0.1).sum() > 0
+    assert np.array_equal(got, ref)
+    # the regulariser differs from the spherical one (the case exercises the anatomical branch)
+    sph = O.oracle_triplet_costs(kind, 2, ot, s["cp_now"], s["orig"], s["rot_now"], s["labels"], s["triplets"], rt, la, lb, lc,
+                                 s["src"], prow if kind >= 3 else None, pmem if kind >= 3 else None, s["src_feat"], s["ref_feat"], cfw, s["absw"],
+                                 0.1, 0.4, 1.6, kexp, rexp)
+    assert (sph != got).mean() > 0.9
+
+
 @pytest.mark.parametrize("sim", [2, 1])
 def test_group_patch_data_and_pair_costs(O, sim):
     g = group_setup()

@@ -36,6 +36,11 @@ CONFIGS = {
     "gMSM": ["--simval=2,2,2", "--sigma_in=0,0,0", "--sigma_ref=0,0,0", "--lambda=0.2,0.2,0.2", "--it=9,9,9", "--opt=DISCRETE,DISCRETE,DISCRETE",
              "--CPgrid=2,3,4", "--SGgrid=4,5,6", "--datagrid=4,5,6", "--regoption=3", "--regexp=2", "--dopt=HOCR", "--k_exponent=2",
              "--bulkmod=1.6", "--shearmod=0.4"],
+    # config/NeuroImage2017_configs/aMSM_STR_longitudinal_alignment (anatomical strain, regoption 5: run with --inanat / --refanat, the
+    # anatomical grid two levels above the control grid like the shipped --anatgrid=4,5,6 for --CPgrid=2,3,4)
+    "aMSMSTR": ["--simval=2,2,2", "--sigma_in=6,4,2", "--sigma_ref=6,4,2", "--lambda=0.025,0.025,0.025", "--it=40,40,40",
+                "--opt=DISCRETE,DISCRETE,DISCRETE", "--CPgrid=2,3,4", "--SGgrid=4,5,6", "--datagrid=4,5,6", "--anatgrid=4,5,6", "--regoption=5",
+                "--regexp=2", "--dopt=HOCR", "--VN", "--rescaleL", "--triclique", "--k_exponent=2", "--bulkmod=1.6", "--shearmod=0.4"],
     "sMSMSTRcp5": ["--simval=2", "--sigma_in=2", "--sigma_ref=2", "--lambda=0.025", "--it=40", "--opt=DISCRETE", "--CPgrid=5", "--SGgrid=7",
                    "--datagrid=6", "--regoption=3", "--regexp=2", "--dopt=HOCR", "--VN", "--rescaleL", "--triclique", "--k_exponent=2",
                    "--bulkmod=1.6", "--shearmod=0.4"],
@@ -85,6 +90,11 @@ def main():
     mov = synth.smooth_fields(warped, a.D, seed0=100)
     np.savetxt(os.path.join(a.out, "refdata.txt"), ref.T, fmt="%.9g")
     np.savetxt(os.path.join(a.out, "indata.txt"), mov.T, fmt="%.9g")
+    # anatomical surfaces (--inanat / --refanat, mesh_registration.cpp:434): smooth folded surfaces over the same topology, the reference one
+    # grown and displaced (a "later time point")
+    f1, f2 = synth.smooth_fields(xyz, 1, seed0=71)[0], synth.smooth_fields(xyz, 1, seed0=83)[0]
+    write_asc(os.path.join(a.out, "inanat.asc"), xyz * (0.62 + 0.10 * f1 / np.abs(f1).max())[:, None], tri)
+    write_asc(os.path.join(a.out, "refanat.asc"), synth.smooth_warp(xyz, max_disp=2.0, seed=91) * (0.66 + 0.12 * f2 / np.abs(f2).max())[:, None], tri)
     for name, lines in CONFIGS.items():
         with open(os.path.join(a.out, "conf_" + name), "w") as f:
             f.write("\n".join(scaled(lines, a.levels_drop, a.it_scale)) + "\n")
