@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the full-size check of subject 0 against the reference's outputs")
     ap.add_argument("--e2e-workers", type=int, default=8)
+    ap.add_argument("--no-adapter-e2e", action="store_true", help="skip the C++ adapter leg (Mesh in / Mesh out, pageable FP64)")
     ap.add_argument("--no-gmsm", action="store_true", help="skip the secondary groupwise (gMSM, BASELINE configs[4]) leg")
     ap.add_argument("--gmsm-subjects", type=int, default=int(os.environ.get("BENCH_GMSM_SUBJECTS", 64)))
     ap.add_argument("--gmsm-data-level", type=int, default=6)
@@ -544,6 +545,13 @@ def run_ours(a):
         except Exception as ex:     # the checker is test infrastructure: its absence must not hide the measurement
             parity = {"checked": False, "error": f"{type(ex).__name__}: {ex}"}
 
+    adapter = None
+    if rank == 0 and world == 1 and not a.no_adapter_e2e:
+        try:
+            adapter = run_adapter_e2e(a, host_xyz[0], tri, low_xyz, low_tri)
+        except Exception as ex:
+            adapter = {"error": f"{type(ex).__name__}: {ex}"}
+
     if rank == 0:
         cfg = workload_config(a, nv, nt, n_low)
         detail = {"query_group_lanes": int(L.msmgpu_get_query_group()), "breakdown_ms_per_step": breakdown, "value_streams": NW,
@@ -557,6 +565,8 @@ def run_ours(a):
             line["gmsm"] = gmsm
         if e2e is not None:
             line["e2e"] = e2e
+        if adapter is not None:
+            line["e2e_adapter"] = adapter
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
         print(json.dumps(line), flush=True)
@@ -682,6 +692,41 @@ def run_gmsm(a, torch, dist, rank, world, local):
            "device_pow_enabled": bool(capi_device_pow()),
            "gpu_launches": int(capi_launches() - launches0), "timing": "wall clock between device synchronisations + barriers, max over ranks; second of two iterations"}
     M.close()      # the context is released with the last object that holds it (meshes / trees keep a reference)
+    return res
+
+
+def run_adapter_e2e(a, xyz, tri, low_xyz, low_tri):
+    """The reference-facing C++ adapter on the reference's own types: newresampler_gpu::metric_resample(Mesh, Mesh) with pageable FP64
+    Mesh::pvalues in and a reference Mesh out (include/newmsm_b200/resampler_adapter.hpp), one subject of the bench workload per call,
+    timed by integration/_build/adapter_bench (built in the container: it contains the compiled reference Mesh class) next to
+    newresampler::metric_resample of the compiled reference on the same objects; outputs compared bit for bit."""
+    import subprocess
+    import tempfile
+    exe = os.path.join(ROOT, "integration", "_build", "adapter_bench")
+    if not os.path.exists(exe):
+        return {"unavailable": "integration/_build/adapter_bench not built (needs /root/reference at build time)"}
+
+    def write_asc(path, v, t):
+        with open(path, "w") as f:
+            f.write("#!ascii synthetic\n%d %d\n" % (len(v), len(t)))
+            np.savetxt(f, np.column_stack([v, np.zeros(len(v))]), fmt="%.17g %.17g %.17g %d")
+            np.savetxt(f, np.column_stack([t, np.zeros(len(t), np.int64)]), fmt="%d")
+    with tempfile.TemporaryDirectory(prefix="adapter_e2e_") as d:
+        write_asc(os.path.join(d, "in.asc"), xyz, tri)
+        write_asc(os.path.join(d, "low.asc"), low_xyz, low_tri)
+        r = subprocess.run([exe, "--in", os.path.join(d, "in.asc"), "--low", os.path.join(d, "low.asc"), "--D", str(a.channels), "--reps", "4",
+                            "--ref-threads", str(os.cpu_count() or 1)], capture_output=True, text=True, timeout=900,
+                           env=dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 1)))
+    if r.returncode != 0:
+        return {"error": (r.stdout + r.stderr)[-500:]}
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    n_low = len(low_xyz)
+    res["verts_per_s"] = n_low / (res["adapter_ms"] * 1e-3)
+    res["reference_verts_per_s"] = n_low / (res["reference_ms"] * 1e-3)
+    res["speedup_vs_reference"] = res["reference_ms"] / res["adapter_ms"]
+    res["note"] = ("adaptive-barycentric method only (metric_resample, resampler.cpp:304), one subject per call; every millisecond between the "
+                   "caller's Mesh and the returned Mesh is inside adapter_ms (flattening Mesh::pvalues, H2D/D2H of pageable FP64, the Mesh copy "
+                   "the reference also makes, resampler.cpp:37-38)")
     return res
 
 

@@ -75,6 +75,11 @@ msmgpu_status msmgpu_device_malloc(msmgpu_ctx* ctx, size_t bytes, void** out);
 void msmgpu_device_free(msmgpu_ctx* ctx, void* ptr);
 msmgpu_status msmgpu_device_download(msmgpu_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes);
 msmgpu_status msmgpu_device_copy_peer(msmgpu_ctx* dst_ctx, void* dst, msmgpu_ctx* src_ctx, const void* src, size_t bytes);
+/* Page-locked host memory (cudaHostAlloc) for callers that flatten their own containers anyway (the reference keeps Mesh::pvalues as
+ * vector<vector<double>>, mesh.h:44): a host-pointer entry point handed such a buffer copies by DMA at link speed instead of through the
+ * driver's staging copy of pageable memory. Any host pointer stays valid input; this is an optimisation, not a requirement. */
+msmgpu_status msmgpu_host_alloc(msmgpu_ctx* ctx, size_t bytes, void** out);
+void msmgpu_host_free(msmgpu_ctx* ctx, void* ptr);
 
 /* replaces: newresampler::Mesh as geometry carrier (msm-newresampler/src/mesh.h:37-58) */
 msmgpu_status msmgpu_mesh_create(msmgpu_ctx* ctx, int nv, const double* xyz, int nt, const int32_t* tri, msmgpu_mesh** out);
@@ -206,6 +211,11 @@ msmgpu_status msmgpu_smooth_neighbourhoods(msmgpu_ctx* ctx, int n, const double*
  * vertex ids of low_xyz, as the reference does), excl NULL or [n_excl] = EXCL's values; out_cm [D][n]; excl_out [n] (with a mask). */
 msmgpu_status msmgpu_smooth_data(msmgpu_ctx* ctx, int n, const double* low_xyz, const int32_t* closest, double sigma, int D, int n_feat,
                                  const double* feat_cm, int n_excl, const double* excl, double* out_cm, double* excl_out);
+
+/* replaces: newmeshreg::variance_normalise (msm-newmeshreg/src/reg_tools.cpp:804-844), the last stage of featurespace::initialise
+ * (featurespace.cpp:79-82): every channel of data_cm [D][n] becomes (x - mean) / sqrt(var) over the vertices with excl > 0 (all when
+ * excl is NULL), mean / var from the reference's sequential Welford recurrence in vertex order; excluded vertices keep their values. */
+msmgpu_status msmgpu_variance_normalise(msmgpu_ctx* ctx, int D, int n, double* data_cm, const double* excl);
 
 /* ---- exclusion masks (`--excl` / cut thresholds, featurespace.cpp:61-70): EXCL = a Mesh whose first channel is 0 where data is ignored ---- */
 /* replaces: get_adaptive_barycentric_weights(in, low, nthreads, EXCL) (resampler.cpp:72-140): targets whose closest source vertex is masked

@@ -12,9 +12,13 @@
 
 #include <cmath>
 #include <cstdint>
+#include <cstring>
+#include <list>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -52,52 +56,142 @@ inline msmgpu_ctx* context() {   // one context per process on $MSMGPU_DEVICE (d
     return ctx;
 }
 
+// The marshalling between the reference's Mesh (shared_ptr<Mpoint> per vertex, vector<vector<double>> pvalues: mesh.h:38-44) and the flat
+// arrays of the C ABI is memory-bound host work: the loops below are spread over the host threads.
 inline std::vector<double> coords_of(const Mesh& m) {
-    std::vector<double> xyz(3 * (size_t)m.nvertices());
-    for (int i = 0; i < m.nvertices(); ++i) {
+    const int n = m.nvertices();
+    std::vector<double> xyz(3 * (size_t)n);
+#pragma omp parallel for schedule(static) if (n > 4096)
+    for (int i = 0; i < n; ++i) {
         const Point& p = m.get_coord(i);
         xyz[3 * (size_t)i] = p.X; xyz[3 * (size_t)i + 1] = p.Y; xyz[3 * (size_t)i + 2] = p.Z;
     }
     return xyz;
 }
 
-inline std::vector<double> pvalues_of(const Mesh& m) {   // channel-major [D][V] like Mesh::pvalues (mesh.h:44)
+inline void flatten_pvalues(const Mesh& m, double* f) {   // channel-major [D][V] like Mesh::pvalues (mesh.h:44)
     const int D = m.get_dimension(), V = m.nvertices();
-    std::vector<double> f((size_t)D * V);
+#pragma omp parallel for collapse(2) schedule(static) if ((size_t)D * V > 16384)
     for (int d = 0; d < D; ++d)
         for (int v = 0; v < V; ++v) f[(size_t)d * V + v] = m.get_pvalue(v, d);
+}
+inline std::vector<double> pvalues_of(const Mesh& m) {
+    std::vector<double> f((size_t)m.get_dimension() * m.nvertices());
+    flatten_pvalues(m, f.data());
     return f;
 }
 
-// device copy of a reference Mesh (geometry only)
+// Grow-only page-locked staging buffers (msmgpu_host_alloc), one per role, kept for the life of the process: Mesh::pvalues has to be
+// flattened anyway, and flattening straight into page-locked memory lets the C ABI's copies run as DMA at link speed (pageable memory
+// goes through the driver's staging copy at a fifth of that). One adapter call at a time uses them (adapter_lock()).
+class Staging {
+    double* p = nullptr;
+    size_t cap = 0;
+
+public:
+    double* get(size_t n) {
+        if (n > cap) {
+            if (p) msmgpu_host_free(context(), p);
+            p = nullptr; cap = 0;
+            check(msmgpu_host_alloc(context(), n * sizeof(double), reinterpret_cast<void**>(&p)));
+            cap = n;
+        }
+        return p;
+    }
+};
+inline Staging& staging(int role) { static Staging s[2]; return s[role]; }   // 0: input channels, 1: output channels
+inline std::mutex& adapter_lock() { static std::mutex m; return m; }
+
+// result = copy of `geometry` (the copy resampler.cpp:37-38 makes too: one shared_ptr<Mpoint> with two adjacency vectors per vertex,
+// 14 ms at ico6) carrying D channels produced by device_work(double* out_cm). The copy is host-only work and does not depend on the
+// device's result, so the C-ABI call runs on a helper thread meanwhile.
+template <class F>
+inline Mesh resampled_mesh(const Mesh& geometry, int D, F&& device_work) {
+    const size_t V = (size_t)geometry.nvertices();
+    double* cm = staging(1).get((size_t)D * V);
+    std::string err;
+    struct Joiner { std::thread t; ~Joiner() { if (t.joinable()) t.join(); } } helper;
+    helper.t = std::thread([&] {
+        try { device_work(cm); } catch (const MeshException& e) { err = e.what(); if (err.empty()) err = "msmgpu call failed"; }
+    });
+    Mesh out = geometry;
+    helper.t.join();
+    if (!err.empty()) {
+        static thread_local std::string msg;   // MeshException keeps the pointer (meshException.h:31)
+        msg = err;
+        throw MeshException(msg.c_str());
+    }
+    out.initialize_pvalues(0);   // clear (mesh.cpp:252-258); whole channels are appended instead of D * V bounds-checked set_pvalue calls
+    for (int d = 0; d < D; ++d) out.push_pvalues(std::vector<double>(cm + (size_t)d * V, cm + (size_t)(d + 1) * V));
+    return out;
+}
+
+// device copy of a reference Mesh (geometry only) with its octree, built on first use
 class DeviceMesh {
 public:
-    explicit DeviceMesh(const Mesh& m) : nv(m.nvertices()), nt(m.ntriangles()) {
-        const std::vector<double> xyz = coords_of(m);
-        tri.resize(3 * (size_t)nt);
-        for (int t = 0; t < nt; ++t)
-            for (int k = 0; k < 3; ++k) tri[3 * (size_t)t + k] = m.get_triangle_vertexID(t, k);
+    DeviceMesh(int nv_, int nt_, std::vector<double>&& xyz_, std::vector<int32_t>&& tri_, std::vector<double>&& area_)
+        : nv(nv_), nt(nt_), xyz(std::move(xyz_)), tri(std::move(tri_)), area(std::move(area_)) {
         check(msmgpu_mesh_create(context(), nv, xyz.data(), nt, tri.data(), &h));
         // Triangle::area is cached at construction and survives set_coord (triangle.cpp:31,39): hand over the values this Mesh
         // object actually holds, so compute_vertex_area (mesh.cpp:1275) is reproduced whatever the object's history
-        std::vector<double> area((size_t)nt);
-        for (int t = 0; t < nt; ++t) area[t] = m.get_triangle_area(t);
         if (nt > 0) check(msmgpu_mesh_set_triangle_areas(h, area.data()));
     }
-    ~DeviceMesh() { msmgpu_mesh_destroy(h); }
+    ~DeviceMesh() {
+        if (tree_) msmgpu_octree_destroy(tree_);
+        msmgpu_mesh_destroy(h);
+    }
     DeviceMesh(const DeviceMesh&) = delete;
     DeviceMesh& operator=(const DeviceMesh&) = delete;
+    msmgpu_octree* tree() {
+        if (!tree_) check(msmgpu_octree_build(h, &tree_));
+        return tree_;
+    }
+    bool holds(int nv_, int nt_, const std::vector<double>& x, const std::vector<int32_t>& t, const std::vector<double>& a) const {
+        return nv_ == nv && nt_ == nt && std::memcmp(x.data(), xyz.data(), x.size() * sizeof(double)) == 0 &&
+               std::memcmp(t.data(), tri.data(), t.size() * sizeof(int32_t)) == 0 && std::memcmp(a.data(), area.data(), a.size() * sizeof(double)) == 0;
+    }
     msmgpu_mesh* h = nullptr;
     int nv, nt;
+    std::vector<double> xyz;     // host copies: the key of the cache below
     std::vector<int32_t> tri;
+    std::vector<double> area;
+
+private:
+    msmgpu_octree* tree_ = nullptr;
 };
+
+// The device copy of `m`. The reference's drivers hand the same meshes to the resampler again and again (the input spheres and the
+// data grids of featurespace::initialise at every level, the control grid of every resample_weights call, mesh_registration.cpp:
+// 170-222): the last few device meshes are kept, keyed by CONTENT (coordinates, faces and cached triangle areas compared bit for
+// bit), so a repeated mesh costs one pass over its host arrays instead of an upload, the per-triangle tables and an octree build.
+inline std::shared_ptr<DeviceMesh> device_mesh(const Mesh& m) {
+    const int nv = m.nvertices(), nt = m.ntriangles();
+    std::vector<double> xyz = coords_of(m), area((size_t)nt);
+    std::vector<int32_t> tri(3 * (size_t)nt);
+#pragma omp parallel for schedule(static) if (nt > 4096)
+    for (int t = 0; t < nt; ++t) {
+        for (int k = 0; k < 3; ++k) tri[3 * (size_t)t + k] = m.get_triangle_vertexID(t, k);
+        area[t] = m.get_triangle_area(t);
+    }
+    static std::mutex mu;
+    static std::list<std::shared_ptr<DeviceMesh>> cache;
+    constexpr size_t kKeep = 6;
+    std::lock_guard<std::mutex> g(mu);
+    for (auto it = cache.begin(); it != cache.end(); ++it)
+        if ((*it)->holds(nv, nt, xyz, tri, area)) {
+            cache.splice(cache.begin(), cache, it);
+            return cache.front();
+        }
+    cache.push_front(std::make_shared<DeviceMesh>(nv, nt, std::move(xyz), std::move(tri), std::move(area)));
+    if (cache.size() > kKeep) cache.pop_back();
+    return cache.front();
+}
 
 inline Mesh with_pvalues(const Mesh& geometry, int D, const std::vector<double>& cm) {   // like resampler.cpp:37-38, 54-57
     Mesh out = geometry;
-    out.initialize_pvalues(D);
-    const int V = out.nvertices();
-    for (int d = 0; d < D; ++d)
-        for (int v = 0; v < V; ++v) out.set_pvalue(v, cm[(size_t)d * V + v], d);
+    out.initialize_pvalues(0);   // clear (mesh.cpp:252-258); whole channels are appended instead of D * V bounds-checked set_pvalue calls
+    const size_t V = (size_t)out.nvertices();
+    for (int d = 0; d < D; ++d) out.push_pvalues(std::vector<double>(cm.begin() + (size_t)d * V, cm.begin() + (size_t)(d + 1) * V));
     return out;
 }
 
@@ -119,13 +213,12 @@ inline Mesh with_mask(const Mesh& geometry, const std::vector<double>& values) {
 // octree.h:39-59. Besides the reference's per-point calls there are batched ones: a GPU launch per point
 // would be absurd, so hot callers pass all their points at once.
 class Octree {
-    std::unique_ptr<detail::DeviceMesh> dm;
+    std::shared_ptr<detail::DeviceMesh> dm;   // shared with the cache: the tree lives as long as this object or the cache entry
     msmgpu_octree* h = nullptr;
     const Mesh* target;
 
 public:
-    explicit Octree(const Mesh& t) : dm(new detail::DeviceMesh(t)), target(&t) { detail::check(msmgpu_octree_build(dm->h, &h)); }
-    ~Octree() { msmgpu_octree_destroy(h); }
+    explicit Octree(const Mesh& t) : dm(detail::device_mesh(t)), h(dm->tree()), target(&t) {}
     Octree(const Octree&) = delete;
     Octree& operator=(const Octree&) = delete;
 
@@ -167,7 +260,8 @@ public:
 
     std::vector<std::map<int, double>> get_adaptive_barycentric_weights(const Mesh& in_mesh, const Mesh& sphLow, int /*nthreads*/ = 1,
                                                                         std::shared_ptr<Mesh> EXCL = std::shared_ptr<Mesh>()) {
-        detail::DeviceMesh a(in_mesh), b(sphLow);
+        const auto pa = detail::device_mesh(in_mesh), pb = detail::device_mesh(sphLow);
+        detail::DeviceMesh &a = *pa, &b = *pb;
         msmgpu_weights* W = nullptr;
         if (EXCL) {   // resampler.cpp:100, 121: targets whose closest source vertex is masked out get no row
             if (EXCL->nvertices() != in_mesh.nvertices()) throw MeshException("Exclusion mask differs in nvertices from data");
@@ -192,18 +286,22 @@ public:
     Mesh barycentric_data_interpolation(const Mesh& metric_in, const Mesh& sphLow, int nthreads = 1,
                                         std::shared_ptr<Mesh> EXCL = std::shared_ptr<Mesh>()) {
         if (EXCL && EXCL->nvertices() != metric_in.nvertices()) throw MeshException("Exclusion mask differs in nvertices from data");   // resampler.cpp:33-34
-        detail::DeviceMesh a(metric_in), b(sphLow);
+        const auto pa = detail::device_mesh(metric_in), pb = detail::device_mesh(sphLow);
+        detail::DeviceMesh &a = *pa, &b = *pb;
         const int D = metric_in.get_dimension();
-        const std::vector<double> fin = detail::pvalues_of(metric_in);
-        std::vector<double> fout((size_t)D * sphLow.nvertices());
+        std::lock_guard<std::mutex> g(detail::adapter_lock());
+        double* fin = detail::staging(0).get((size_t)D * metric_in.nvertices());
+        detail::flatten_pvalues(metric_in, fin);
         if (EXCL) {   // masked weights and sums + the mask resampled with the same weights, which replaces *EXCL (resampler.cpp:55-67)
             std::vector<double> eout((size_t)sphLow.nvertices());
-            detail::check(msmgpu_metric_resample_excl(a.h, b.h, D, fin.data(), detail::mask_of(*EXCL).data(), fout.data(), eout.data()));
+            const std::vector<double> ein = detail::mask_of(*EXCL);
+            Mesh out = detail::resampled_mesh(sphLow, D, [&](double* fout) {
+                detail::check(msmgpu_metric_resample_excl(a.h, b.h, D, fin, ein.data(), fout, eout.data()));
+            });
             *EXCL = detail::with_mask(sphLow, eout);
-        } else {
-            detail::check(msmgpu_metric_resample(a.h, b.h, D, fin.data(), fout.data()));
+            return out;
         }
-        return detail::with_pvalues(sphLow, D, fout);
+        return detail::resampled_mesh(sphLow, D, [&](double* fout) { detail::check(msmgpu_metric_resample(a.h, b.h, D, fin, fout)); });
     }
 };
 
@@ -214,7 +312,8 @@ inline Mesh metric_resample(const Mesh& in, const Mesh& target, int nthreads = 1
 
 inline Mesh surface_resample(const Mesh& anat_orig, const Mesh& sphere_orig, const Mesh& sphere_low, int /*nthreads*/ = 1) {
     // resampler.cpp:284-302: new coordinates of sphere_low's vertices = blend of anat_orig over sphere_orig's triangles
-    detail::DeviceMesh s(sphere_orig);
+    const auto ps = detail::device_mesh(sphere_orig);
+    detail::DeviceMesh& s = *ps;
     const std::vector<double> anat = detail::coords_of(anat_orig), low = detail::coords_of(sphere_low);
     std::vector<double> out(low.size());
     detail::check(msmgpu_surface_resample(s.h, anat.data(), sphere_low.nvertices(), low.data(), out.data()));
@@ -228,7 +327,8 @@ inline Mesh project_anatomical_mesh(const Mesh& orig, const Mesh& target, const 
 }
 
 inline void sphere_project_warp(Mesh& sphere, const Mesh& from, const Mesh& to, int /*nthreads*/ = 1) {   // resampler.cpp:311-328
-    detail::DeviceMesh f(from);
+    const auto pf = detail::device_mesh(from);
+    detail::DeviceMesh& f = *pf;
     const std::vector<double> t = detail::coords_of(to), q = detail::coords_of(sphere);
     std::vector<double> out(q.size());
     detail::check(msmgpu_sphere_project_warp(f.h, t.data(), sphere.nvertices(), q.data(), out.data()));
@@ -237,18 +337,23 @@ inline void sphere_project_warp(Mesh& sphere, const Mesh& from, const Mesh& to, 
 
 inline Mesh nearest_neighbour_interpolation(Mesh& orig, const Mesh& sphLow, int nthreads = 1, std::shared_ptr<Mesh> EXCL = std::shared_ptr<Mesh>()) {
     newresampler::check_scale(orig, sphLow);   // resampler.cpp:232-258
-    detail::DeviceMesh a(orig);
+    const auto pa = detail::device_mesh(orig);
+    detail::DeviceMesh& a = *pa;
     const int D = orig.get_dimension();
-    const std::vector<double> fin = detail::pvalues_of(orig), low = detail::coords_of(sphLow);
-    std::vector<double> fout((size_t)D * sphLow.nvertices());
+    const std::vector<double> low = detail::coords_of(sphLow);
+    std::lock_guard<std::mutex> g(detail::adapter_lock());
+    double* fin = detail::staging(0).get((size_t)D * orig.nvertices());
+    detail::flatten_pvalues(orig, fin);
     if (EXCL) {
         std::vector<double> eout((size_t)sphLow.nvertices());
-        detail::check(msmgpu_nn_resample_excl(a.h, sphLow.nvertices(), low.data(), D, fin.data(), detail::mask_of(*EXCL).data(), fout.data(), eout.data()));
+        const std::vector<double> ein = detail::mask_of(*EXCL);
+        Mesh out = detail::resampled_mesh(sphLow, D, [&](double* fout) {
+            detail::check(msmgpu_nn_resample_excl(a.h, sphLow.nvertices(), low.data(), D, fin, ein.data(), fout, eout.data()));
+        });
         *EXCL = detail::with_mask(sphLow, eout);
-    } else {
-        detail::check(msmgpu_nn_resample(a.h, sphLow.nvertices(), low.data(), D, fin.data(), fout.data()));
+        return out;
     }
-    return detail::with_pvalues(sphLow, D, fout);
+    return detail::resampled_mesh(sphLow, D, [&](double* fout) { detail::check(msmgpu_nn_resample(a.h, sphLow.nvertices(), low.data(), D, fin, fout)); });
 }
 
 }  // namespace newresampler_gpu
@@ -265,15 +370,19 @@ inline Mesh smooth_data(Mesh& orig, const Mesh& sphLow, double sigma, int /*nthr
     std::vector<Point> pts((size_t)n);
     for (int i = 0; i < n; ++i) pts[i] = sphLow.get_coord(i);
     const std::vector<int> closest = Octree(orig).get_closest_vertex_IDs(pts);   // oct_search.get_closest_vertex_ID(ci), resampler.cpp:184
-    const std::vector<double> low = detail::coords_of(sphLow), fin = detail::pvalues_of(orig);
+    const std::vector<double> low = detail::coords_of(sphLow);
     std::vector<int32_t> c32(closest.begin(), closest.end());
-    std::vector<double> out((size_t)D * n), eout;
-    std::vector<double> mask;
+    std::vector<double> eout, mask;
     if (EXCL) { mask = detail::mask_of(*EXCL); eout.resize((size_t)n); }
-    detail::check(msmgpu_smooth_data(detail::context(), n, low.data(), c32.data(), sigma, D, orig.nvertices(), fin.data(), (int)mask.size(),
-                                     EXCL ? mask.data() : nullptr, out.data(), EXCL ? eout.data() : nullptr));
+    std::lock_guard<std::mutex> g(detail::adapter_lock());
+    double* fin = detail::staging(0).get((size_t)D * orig.nvertices());
+    detail::flatten_pvalues(orig, fin);
+    Mesh res = detail::resampled_mesh(sphLow, D, [&](double* out) {
+        detail::check(msmgpu_smooth_data(detail::context(), n, low.data(), c32.data(), sigma, D, orig.nvertices(), fin, (int)mask.size(),
+                                         EXCL ? mask.data() : nullptr, out, EXCL ? eout.data() : nullptr));
+    });
     if (EXCL) *EXCL = detail::with_mask(sphLow, eout);     // resampler.cpp:226
-    return detail::with_pvalues(sphLow, D, out);
+    return res;
 }
 
 // make_mesh_from_icosa (mesh.cpp:1111-1196) without the O(V^2) duplicate-midpoint scan of retessellate (mesh.cpp:910-1008):

@@ -1,7 +1,16 @@
-// Host-side cost of the resampler adapter per call (TEST/TUNING tool, built by `make -C oracle adapter_bench`): where the time of
-// newresampler_gpu::metric_resample goes for the sizes newmsm uses (ico6 data grid -> ico4 control grid, D = 1).
+// End-to-end cost of the resampler adapter per call, on the types the reference actually uses (MEASUREMENT tool, built by
+// `make -C oracle adapter_bench` into integration/_build/): newresampler_gpu::metric_resample(Mesh, Mesh) -- pageable FP64
+// Mesh::pvalues in, a reference Mesh out -- against newresampler::metric_resample (resampler.cpp:304) of the compiled reference on the
+// same objects, with the split of the adapter's time (marshalling vs the C-ABI call) and a bit-for-bit comparison of the two outputs
+// (the reference single-threaded for that: its adaptive weights race at > 1 thread).
+//
+//   adapter_bench --in sphere.asc --low low.asc --D 100 --reps 5 --ref-threads 16 [--skip-ref]
+//   adapter_bench --hi 6 --lo 4 --D 1            (icospheres made in-process)
+// Prints human-readable lines and, last, one JSON line.
 #include <chrono>
 #include <cstdio>
+#include <cstring>
+#include <string>
 
 #include "newmsm_b200/resampler_adapter.hpp"
 
@@ -10,37 +19,97 @@ using clk = std::chrono::steady_clock;
 static double since(clk::time_point t0) { return std::chrono::duration<double, std::milli>(clk::now() - t0).count(); }
 
 int main(int argc, char** argv) {
-    const int hi = argc > 1 ? std::atoi(argv[1]) : 6, lo = argc > 2 ? std::atoi(argv[2]) : 4, D = argc > 3 ? std::atoi(argv[3]) : 1;
-    Mesh in = newresampler_gpu::make_mesh_from_icosa(hi), low = newresampler_gpu::make_mesh_from_icosa(lo);
-    true_rescale(in, RAD);
-    true_rescale(low, RAD);
+    int hi = 6, lo = 4, D = 1, reps = 5, ref_threads = 1;
+    bool skip_ref = false;
+    std::string in_path, low_path;
+    for (int i = 1; i < argc; ++i) {
+        const std::string a = argv[i];
+        auto next = [&] { return i + 1 < argc ? argv[++i] : ""; };
+        if (a == "--hi") hi = std::atoi(next());
+        else if (a == "--lo") lo = std::atoi(next());
+        else if (a == "--D") D = std::atoi(next());
+        else if (a == "--reps") reps = std::atoi(next());
+        else if (a == "--ref-threads") ref_threads = std::atoi(next());
+        else if (a == "--in") in_path = next();
+        else if (a == "--low") low_path = next();
+        else if (a == "--skip-ref") skip_ref = true;
+    }
+    Mesh in, low;
+    if (!in_path.empty()) in.load(in_path); else { in = newresampler_gpu::make_mesh_from_icosa(hi); true_rescale(in, RAD); }
+    if (!low_path.empty()) low.load(low_path); else { low = newresampler_gpu::make_mesh_from_icosa(lo); true_rescale(low, RAD); }
     in.initialize_pvalues(D);
-    for (int d = 0; d < D; ++d)
-        for (int v = 0; v < in.nvertices(); ++v) in.set_pvalue(v, 0.01 * in.get_coord(v).X * (d + 1), d);
-    for (int rep = 0; rep < 6; ++rep) {
+    for (int d = 0; d < D; ++d)   // smooth synthetic channels
+        for (int v = 0; v < in.nvertices(); ++v) {
+            const Point& p = in.get_coord(v);
+            in.set_pvalue(v, std::sin(0.031 * (d + 1) * p.X) + 0.5 * std::cos(0.017 * (d + 2) * p.Y) + 0.01 * p.Z, d);
+        }
+    const int V = in.nvertices(), N = low.nvertices();
+    double best_total = 1e30, best_core = 1e30, best_pv = 1e30, best_wp = 1e30, best_dm = 1e30, best_warp = 1e30;
+    Mesh out;
+    for (int rep = 0; rep < reps + 1; ++rep) {   // rep 0 = warm-up (CUDA start-up, first-use module loads)
         auto t0 = clk::now();
-        Mesh out = newresampler_gpu::metric_resample(in, low, 1);
+        out = newresampler_gpu::metric_resample(in, low, 1);
         const double total = since(t0);
         t0 = clk::now();
-        { newresampler_gpu::detail::DeviceMesh a(in), b(low); }
+        const auto a = newresampler_gpu::detail::device_mesh(in), b = newresampler_gpu::detail::device_mesh(low);
         const double dm = since(t0);
         t0 = clk::now();
-        const std::vector<double> fin = newresampler_gpu::detail::pvalues_of(in);
+        double* fin = newresampler_gpu::detail::staging(0).get((size_t)D * V);
+        newresampler_gpu::detail::flatten_pvalues(in, fin);
         const double pv = since(t0);
+        double* fout = newresampler_gpu::detail::staging(1).get((size_t)D * N);
         t0 = clk::now();
-        Mesh cp = newresampler_gpu::detail::with_pvalues(low, D, std::vector<double>((size_t)D * low.nvertices(), 0.0));
-        const double wp = since(t0);
-        newresampler_gpu::detail::DeviceMesh a(in), b(low);
-        std::vector<double> fout((size_t)D * low.nvertices());
-        t0 = clk::now();
-        newresampler_gpu::detail::check(msmgpu_metric_resample(a.h, b.h, D, fin.data(), fout.data()));
+        newresampler_gpu::detail::check(msmgpu_metric_resample(a->h, b->h, D, fin, fout));
         const double core = since(t0);
         t0 = clk::now();
+        {
+            Mesh cp = low;
+            cp.initialize_pvalues(0);
+            for (int d = 0; d < D; ++d) cp.push_pvalues(std::vector<double>(fout + (size_t)d * N, fout + (size_t)(d + 1) * N));
+        }
+        const double wp = since(t0);
+        t0 = clk::now();
         Mesh sp = low;
+        const double cpy = since(t0);
+        t0 = clk::now();
         newresampler_gpu::sphere_project_warp(sp, in, in, 1);
         const double warp = since(t0);
-        std::printf("rep %d: metric_resample %d->%d D=%d total %.2f ms | 2x DeviceMesh %.2f | pvalues_of %.2f | with_pvalues %.2f | msmgpu_metric_resample %.2f | sphere_project_warp %.2f\n",
-                    rep, in.nvertices(), low.nvertices(), D, total, dm, pv, wp, core, warp);
+        std::printf("rep %d: metric_resample %d->%d D=%d total %.2f ms | device_mesh x2 (cached) %.2f | flatten pvalues (page-locked) %.2f | msmgpu_metric_resample %.2f | Mesh copy + channels %.2f "
+                    "(Mesh copy alone %.2f, overlapped with the device call inside the adapter) | sphere_project_warp %.2f\n", rep, V, N, D, total, dm, pv, core, wp, cpy, warp);
+        if (rep == 0) continue;
+        best_total = std::min(best_total, total); best_core = std::min(best_core, core); best_pv = std::min(best_pv, pv);
+        best_wp = std::min(best_wp, wp); best_dm = std::min(best_dm, dm); best_warp = std::min(best_warp, warp);
     }
+    double ref_ms = -1, ref1_ms = -1;
+    long differ = -1;
+    if (!skip_ref) {
+        auto t0 = clk::now();
+        const Mesh ref1 = newresampler::metric_resample(in, low, 1);
+        ref1_ms = since(t0);
+        differ = 0;
+        for (int d = 0; d < D; ++d)
+            for (int v = 0; v < N; ++v) {
+                const double x = ref1.get_pvalue(v, d), y = out.get_pvalue(v, d);
+                differ += std::memcmp(&x, &y, sizeof(double)) != 0;
+            }
+        ref_ms = ref1_ms;
+        if (ref_threads > 1) {
+            ref_ms = 1e30;
+            for (int rep = 0; rep < 2; ++rep) {
+                t0 = clk::now();
+                const Mesh r = newresampler::metric_resample(in, low, ref_threads);
+                ref_ms = std::min(ref_ms, since(t0));
+            }
+        }
+        std::printf("reference metric_resample: %.1f ms single-threaded, %.1f ms with %d threads; %ld of %ld output values differ from the adapter's\n",
+                    ref1_ms, ref_ms, ref_threads, differ, (long)D * N);
+    }
+    std::printf("{\"call\": \"newresampler_gpu::metric_resample(Mesh, Mesh)\", \"source_vertices\": %d, \"target_vertices\": %d, \"channels\": %d, "
+                "\"payload\": \"FP64 Mesh::pvalues, pageable host memory, Mesh in / Mesh out\", \"adapter_ms\": %.3f, \"c_abi_call_ms\": %.3f, "
+                "\"marshalling_ms\": {\"device_mesh_x2_cached\": %.3f, \"flatten_pvalues_into_page_locked\": %.3f, \"mesh_copy_plus_channels\": %.3f}, \"adapter_over_c_abi\": %.3f, "
+                "\"sphere_project_warp_ms\": %.3f, \"reference_ms\": %.3f, \"reference_threads\": %d, \"reference_single_thread_ms\": %.3f, "
+                "\"values_differing_from_single_thread_reference\": %ld, \"h2d_bytes\": %zu, \"d2h_bytes\": %zu}\n",
+                V, N, D, best_total, best_core, best_dm, best_pv, best_wp, best_total / best_core, best_warp, ref_ms, ref_threads, ref1_ms, differ,
+                (size_t)D * V * sizeof(double), (size_t)D * N * sizeof(double));
     return 0;
 }

@@ -13,6 +13,7 @@
 // Compiled with -fno-access-control: the binding reads the private state of the two reference classes (a maintainer would put
 // the same four calls into the members themselves). MSMGPU_DISABLE=group keeps the reference's code;
 // MSMGPU_TIMING=1 prints the split at exit.
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -64,8 +65,16 @@ struct Report {
 
 }  // namespace
 
+// a call that leaves the device path says so once (never silently): MSMGPU_DISABLE=group, or a shape the binding does not take
+static void left_to_reference(const char* what, bool by_request) {
+    static std::atomic<int> said{0};
+    if (said.fetch_add(1) < 4)
+        std::fprintf(stderr, "[msmgpu] %s runs on the reference's CPU code (%s)\n", what,
+                     by_request ? "MSMGPU_DISABLE=group" : "fewer than 2 subjects, or the subjects' data meshes differ in size");
+}
+
 void hook_estimate_pairs(DiscreteGroupModel* self) {
-    if (disabled() || !GroupBinding::instance().estimate_pairs(*self)) { real_estimate_pairs(self); return; }
+    if (disabled() || !GroupBinding::instance().estimate_pairs(*self)) { left_to_reference("DiscreteGroupModel::estimate_pairs", disabled()); real_estimate_pairs(self); return; }
     if (verify()) {
         const std::vector<int> got(self->pairs, self->pairs + 2 * (size_t)self->m_num_pairs);
         real_estimate_pairs(self);
@@ -76,7 +85,7 @@ void hook_estimate_pairs(DiscreteGroupModel* self) {
 }
 
 void hook_get_patch_data(DiscreteGroupModel* self) {
-    if (disabled() || !GroupBinding::instance().get_patch_data(*self)) { real_get_patch_data(self); return; }
+    if (disabled() || !GroupBinding::instance().get_patch_data(*self)) { left_to_reference("DiscreteGroupModel::get_patch_data and the group costs", disabled()); real_get_patch_data(self); return; }
     if (verify()) real_get_patch_data(self);   // the reference's patch maps too, for the side-by-side comparison of every cost request
     // Fusion::optimize runs next; the first sphere_project_warp after it closes the "optimiser phases" timer (newmsm_gpu_hooks.cpp)
     newmeshreg_gpu::detail::timers().source_done_at = omp_get_wtime();

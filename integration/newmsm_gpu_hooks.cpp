@@ -21,6 +21,7 @@
 #include <cmath>
 #include <cstring>
 #include <mutex>
+#include <thread>
 
 #ifndef MSMGPU_TRACE_ONLY
 #include "newmsm_b200/costfunction_adapter.hpp"
@@ -38,6 +39,7 @@ using newresampler::Mesh;
 #define SYM_ICOSA "_ZN12newresampler20make_mesh_from_icosaEi"
 #define SYM_SMOOTH "_ZN12newresampler11smooth_dataERNS_4MeshERKS0_diSt10shared_ptrIS0_E"
 #define SYM_FEATINIT "_ZN10newmeshreg12featurespace10initialiseEiRSt6vectorIN12newresampler4MeshESaIS3_EEb"
+#define SYM_VARNORM "_ZN10newmeshreg18variance_normaliseERSt10shared_ptrIN9MISCMATHS8BFMatrixEERS0_IN12newresampler4MeshEEi"
 
 #define SYM_UNFOLD "_ZN10newmeshreg6unfoldERN12newresampler4MeshEb"
 #define SYM_INIT_CF "_ZN10newmeshreg26NonLinearSRegDiscreteModel24initialize_cost_functionEbRSt3mapINSt7__cxx1112basic_stringIcSt11char_traitsIcESaIcEEESt7variantIJiS7_dbEESt4lessIS7_ESaISt4pairIKS7_S9_EEE"
@@ -95,6 +97,8 @@ Mesh real_smooth_data(Mesh& orig, const Mesh& sphLow, double sigma, int nthreads
 Mesh wrap_smooth_data(Mesh& orig, const Mesh& sphLow, double sigma, int nthreads, std::shared_ptr<Mesh> EXCL) asm("__wrap_" SYM_SMOOTH);
 Mesh real_featurespace_initialise(newmeshreg::featurespace* self, int ico, std::vector<Mesh>& IN, bool exclude) asm("__real_" SYM_FEATINIT);
 Mesh wrap_featurespace_initialise(newmeshreg::featurespace* self, int ico, std::vector<Mesh>& IN, bool exclude) asm("__wrap_" SYM_FEATINIT);
+void real_variance_normalise(std::shared_ptr<MISCMATHS::BFMatrix>& DATA, std::shared_ptr<Mesh>& EXCL, int nthreads) asm("__real_" SYM_VARNORM);
+void wrap_variance_normalise(std::shared_ptr<MISCMATHS::BFMatrix>& DATA, std::shared_ptr<Mesh>& EXCL, int nthreads) asm("__wrap_" SYM_VARNORM);
 
 namespace {
 
@@ -104,8 +108,8 @@ bool disabled(const char* what) {
 }
 
 struct Stats {
-    double resample = 0, warp = 0, icosa = 0, featinit = 0, optimise = 0, smooth = 0;
-    long n_resample = 0, n_warp = 0, n_icosa = 0, n_smooth = 0;
+    double resample = 0, warp = 0, icosa = 0, featinit = 0, optimise = 0, smooth = 0, varnorm = 0;
+    long n_resample = 0, n_warp = 0, n_icosa = 0, n_smooth = 0, n_varnorm = 0;
     const double t_start = omp_get_wtime();
     ~Stats() {
         if (!std::getenv("MSMGPU_TIMING")) return;
@@ -113,12 +117,24 @@ struct Stats {
         std::fprintf(stderr,
                      "[msmgpu] get_source_data %.3f s | unary tables %ld in %.3f s | triplet batches %ld in %.3f s | pairwise tables %.3f s | "
                      "metric_resample %ld in %.3f s | sphere_project_warp %ld in %.3f s | make_mesh_from_icosa %ld in %.3f s | smooth_data %ld in %.3f s | "
-                     "featurespace::initialise %.3f s (incl. its resamples) | optimiser phases (solver + cost calls) %.3f s | process %.3f s | "
+                     "variance_normalise %ld in %.3f s | featurespace::initialise %.3f s (incl. its resamples) | optimiser phases (solver + cost calls) %.3f s | process %.3f s | "
                      "kernel launches %llu\n",
                      t.source, t.unary_tables, t.unary, t.triplet_batches, t.triplet, t.pairwise, n_resample, resample, n_warp, warp, n_icosa, icosa,
-                     n_smooth, smooth, featinit, optimise, omp_get_wtime() - t_start, msmgpu_launch_count());
+                     n_smooth, smooth, n_varnorm, varnorm, featinit, optimise, omp_get_wtime() - t_start, msmgpu_launch_count());
     }
 } stats;
+
+// CUDA start-up (cuInit + the primary context: 1.9 s on a B200 box, tools/init_probe.py) runs on a helper thread from program start, so
+// it overlaps the reference's own start-up (option parsing, reading the meshes and the data files). The first device call waits for it
+// (function-local static of detail::context()). MSMGPU_NO_PREWARM=1 switches it off.
+struct Prewarm {
+    std::thread th;
+    Prewarm() {
+        if (std::getenv("MSMGPU_NO_PREWARM")) return;
+        th = std::thread([] { try { newresampler_gpu::detail::context(); } catch (...) {} });
+    }
+    ~Prewarm() { if (th.joinable()) th.join(); }
+} g_prewarm;
 
 // the hooks are reachable from the reference's OpenMP loops: the counters are updated under a lock
 static std::mutex g_stats_mutex;
@@ -148,6 +164,8 @@ void wrap_initialize_cost_function(NonLinearSRegDiscreteModel* self, bool MV, my
 // MSMGPU_VERIFY=1: every hooked call ALSO runs the reference's CPU implementation in-process and the two results are compared
 // bit for bit (diagnostic mode; timings are meaningless with it).
 static bool verify() { static const bool v = std::getenv("MSMGPU_VERIFY") != nullptr; return v; }
+// MSMGPU_TIMING=2: one line per hooked resampler call (sizes, milliseconds)
+static bool per_call_timing() { static const bool v = std::getenv("MSMGPU_TIMING") && std::atoi(std::getenv("MSMGPU_TIMING")) >= 2; return v; }
 
 // A context (stream, scratch) serves one host thread at a time. The reference calls the resampler from an OpenMP loop in one place
 // (DiscreteGroupModel::get_patch_data, per subject: reached here with MSMGPU_DISABLE=group, masked groupwise runs or MSMGPU_VERIFY),
@@ -160,6 +178,9 @@ Mesh wrap_metric_resample(const Mesh& in, const Mesh& target, int nthreads, std:
     std::shared_ptr<Mesh> excl_before = (EXCL && verify()) ? std::make_shared<Mesh>(*EXCL) : std::shared_ptr<Mesh>();
     Mesh out = [&] { std::lock_guard<std::mutex> g(g_device_mutex); return newresampler_gpu::metric_resample(in, target, nthreads, EXCL); }();
     stat_add(stats.resample, &stats.n_resample, omp_get_wtime() - t0);
+    if (per_call_timing())
+        std::fprintf(stderr, "[msmgpu call] metric_resample %d -> %d vertices, D=%d%s: %.2f ms\n", in.nvertices(), target.nvertices(), in.get_dimension(),
+                     EXCL ? " (EXCL)" : "", 1e3 * (omp_get_wtime() - t0));
     if (verify()) {
         const Mesh ref = real_metric_resample(in, target, nthreads, excl_before);   // (the mask was replaced by the call above: use its copy)
         long bad = 0;
@@ -242,10 +263,44 @@ Mesh wrap_smooth_data(Mesh& orig, const Mesh& sphLow, double sigma, int nthreads
     return out;
 }
 
+// variance_normalise (reg_tools.cpp:804-844), the last stage of featurespace::initialise (featurespace.cpp:79-82): through the BFMatrix
+// interface (Peek / Set, so a sparse float matrix rounds on Set exactly as it does in the reference), the recurrence on the device
+void wrap_variance_normalise(std::shared_ptr<MISCMATHS::BFMatrix>& DATA, std::shared_ptr<Mesh>& EXCL, int nthreads) {
+    if (disabled("varnorm") || !DATA || DATA->Nrows() == 0 || DATA->Ncols() == 0) return real_variance_normalise(DATA, EXCL, nthreads);
+    const double t0 = omp_get_wtime();
+    const int D = (int)DATA->Nrows(), n = (int)DATA->Ncols();
+    std::vector<double> cm((size_t)D * n), excl;
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int d = 0; d < D; ++d)
+        for (int i = 0; i < n; ++i) cm[(size_t)d * n + i] = DATA->Peek(d + 1, i + 1);
+    if (EXCL) excl = newresampler_gpu::detail::mask_of(*EXCL);
+    std::shared_ptr<MISCMATHS::BFMatrix> ref;
+    if (verify()) { ref = std::make_shared<MISCMATHS::FullBFMatrix>(DATA->AsMatrix()); real_variance_normalise(ref, EXCL, nthreads); }
+    {
+        std::lock_guard<std::mutex> g(g_device_mutex);
+        newresampler_gpu::detail::check(msmgpu_variance_normalise(newresampler_gpu::detail::context(), D, n, cm.data(), EXCL ? excl.data() : nullptr));
+    }
+#pragma omp parallel for schedule(static)
+    for (int d = 0; d < D; ++d)
+        for (int i = 0; i < n; ++i)
+            if (!EXCL || excl[i] > 0.0) DATA->Set(d + 1, i + 1, cm[(size_t)d * n + i]);   // cpp:836-843
+    stat_add(stats.varnorm, &stats.n_varnorm, omp_get_wtime() - t0);
+    if (ref) {
+        long bad = 0;
+        for (int d = 0; d < D; ++d)
+            for (int i = 0; i < n; ++i) {
+                const double a = ref->Peek(d + 1, i + 1), b = DATA->Peek(d + 1, i + 1);
+                bad += std::memcmp(&a, &b, sizeof(double)) != 0;
+            }
+        std::fprintf(stderr, "[msmgpu verify] variance_normalise %d x %d%s: %ld values differ\n", D, n, EXCL ? " (EXCL)" : "", bad);
+    }
+}
+
 Mesh wrap_featurespace_initialise(newmeshreg::featurespace* self, int ico, std::vector<Mesh>& IN, bool exclude) {   // timing only
     const double t0 = omp_get_wtime();
     Mesh m = real_featurespace_initialise(self, ico, IN, exclude);
     stat_add(stats.featinit, nullptr, omp_get_wtime() - t0);
+    if (per_call_timing()) std::fprintf(stderr, "[msmgpu call] featurespace::initialise ico %d: %.2f ms\n", ico, 1e3 * (omp_get_wtime() - t0));
     return m;
 }
 #endif

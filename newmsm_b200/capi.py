@@ -50,6 +50,9 @@ _SIGNATURES = {
     "msmgpu_ctx_sync": (_i, [_vp]),
     "msmgpu_ctx_stream": (_vp, [_vp]),
     "msmgpu_device_malloc": (_i, [_vp, C.c_size_t, _pp]),
+    "msmgpu_host_alloc": (_i, [_vp, C.c_size_t, _pp]),
+    "msmgpu_variance_normalise": (_i, [_vp, _i, _i, _vp, _vp]),
+    "msmgpu_host_free": (None, [_vp, _vp]),
     "msmgpu_device_free": (None, [_vp, _vp]),
     "msmgpu_device_download": (_i, [_vp, _vp, _vp, C.c_size_t]),
     "msmgpu_device_copy_peer": (_i, [_vp, _vp, _vp, _vp, C.c_size_t]),

@@ -243,6 +243,19 @@ msmgpu_status msmgpu_device_malloc(msmgpu_ctx* c, size_t bytes, void** out) {
     if (bytes) MSM_CUDA(cudaMalloc(out, bytes));
     return MSMGPU_OK;
 }
+msmgpu_status msmgpu_host_alloc(msmgpu_ctx* c, size_t bytes, void** out) {
+    if (!c || !out) return fail(MSMGPU_ERR_INVALID, "host_alloc: bad arguments");
+    *out = nullptr;
+    MSM_CUDA(cudaSetDevice(c->device));
+    if (bytes) MSM_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return MSMGPU_OK;
+}
+void msmgpu_host_free(msmgpu_ctx* c, void* ptr) {
+    if (!c || !ptr) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFreeHost(ptr);
+}
 void msmgpu_device_free(msmgpu_ctx* c, void* ptr) {
     if (!c || !ptr) return;
     cudaSetDevice(c->device);
@@ -338,6 +351,8 @@ msmgpu_status msmgpu_mesh_set_coords(msmgpu_mesh* m, const double* xyz) {
     MSM_CUDA(cudaMemcpyAsync(m->xyz.p, xyz, 3 * (size_t)m->nv * sizeof(double), cudaMemcpyHostToDevice, m->ctx->stream));
     MSM_TRY(mesh_refresh_tables(m));
     MSM_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    delete m->own_tree;   // built for the previous coordinates
+    m->own_tree = nullptr;
     return MSMGPU_OK;
 }
 
@@ -609,8 +624,8 @@ msmgpu_status msmgpu_bary_resample(msmgpu_mesh* in_mesh, int n, const double* pt
     MSM_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     msmgpu_octree* t = nullptr;
-    MSM_TRY(msmgpu_octree_build(in_mesh, &t));
-    std::unique_ptr<msmgpu_octree> guard(t);
+    std::vector<std::unique_ptr<msmgpu_octree>> guard;
+    MSM_TRY(mesh_tree(in_mesh, &t, guard));
     const int nv = in_mesh->nv;
     DevBuf<double> d_pts, d_cm_in, d_cm_out;
     DevBuf<float> d_rows_in, d_rows_out;
@@ -691,8 +706,8 @@ static msmgpu_status blend_impl(msmgpu_mesh* mesh, const double* payload, int n,
     MSM_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     msmgpu_octree* t = nullptr;
-    MSM_TRY(msmgpu_octree_build(mesh, &t));
-    std::unique_ptr<msmgpu_octree> guard(t);
+    std::vector<std::unique_ptr<msmgpu_octree>> guard;
+    MSM_TRY(mesh_tree(mesh, &t, guard));
     DevBuf<double> d_q, d_pay, d_out;
     DevBuf<int> d_st;
     MSM_TRY(upload(d_q, q, 3 * (size_t)n, s));
@@ -717,8 +732,8 @@ msmgpu_status msmgpu_nn_resample(msmgpu_mesh* in_mesh, int n, const double* low_
     MSM_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     msmgpu_octree* t = nullptr;
-    MSM_TRY(msmgpu_octree_build(in_mesh, &t));
-    std::unique_ptr<msmgpu_octree> guard(t);
+    std::vector<std::unique_ptr<msmgpu_octree>> guard;
+    MSM_TRY(mesh_tree(in_mesh, &t, guard));
     DevBuf<double> d_q, d_in, d_out;
     DevBuf<int> d_vtx, d_st;
     MSM_TRY(upload(d_q, low_xyz, 3 * (size_t)n, s));
@@ -741,8 +756,8 @@ msmgpu_status msmgpu_nn_resample_excl(msmgpu_mesh* in_mesh, int n, const double*
     MSM_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     msmgpu_octree* t = nullptr;
-    MSM_TRY(msmgpu_octree_build(in_mesh, &t));
-    std::unique_ptr<msmgpu_octree> guard(t);
+    std::vector<std::unique_ptr<msmgpu_octree>> guard;
+    MSM_TRY(mesh_tree(in_mesh, &t, guard));
     DevBuf<double> d_q;
     DevBuf<int> d_vtx, d_st;
     MSM_TRY(upload(d_q, low_xyz, 3 * (size_t)n, s));

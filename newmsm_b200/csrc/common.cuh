@@ -101,6 +101,7 @@ struct msmgpu_ctx {
                              // octree build) arrive by plain DMA instead of the staged, stream-draining path of pageable copies
 };
 
+struct msmgpu_octree;
 struct msmgpu_mesh {
     msmgpu_ctx* ctx = nullptr;
     int nv = 0, nt = 0;
@@ -117,6 +118,10 @@ struct msmgpu_mesh {
     std::shared_ptr<msm::DevBuf<unsigned char>> slab;   // the per-triangle tables of a batch of view meshes live in one allocation
     msmgpu_mesh* area_source = nullptr;   // mesh whose geometry the cached Triangle areas belong to (msmgpu_mesh_set_area_source)
     msm::DevBuf<double> tri_area;         // optional explicit cached Triangle::area values [nt] (msmgpu_mesh_set_triangle_areas)
+    // the mesh's own octree: built by the first entry point that is handed the mesh without a tree (msm::mesh_tree), kept until the
+    // coordinates change (msmgpu_mesh_set_coords). Never set for views of caller buffers, whose contents the library does not track.
+    msmgpu_octree* own_tree = nullptr;
+    ~msmgpu_mesh();
 };
 
 struct msmgpu_octree {
@@ -160,6 +165,12 @@ namespace msm {
 
 // ---- launchers implemented in the .cu files -------------------------------------------------
 msmgpu_status mesh_refresh_tables(msmgpu_mesh* m);
+// octrees of meshes handed over without one: the cached own_tree (built here when missing, all missing ones as one forest);
+// views get a fresh tree that `owned` keeps alive for the caller's scope
+msmgpu_status mesh_trees(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, msmgpu_octree** out, std::vector<std::unique_ptr<msmgpu_octree>>& owned);
+inline msmgpu_status mesh_tree(msmgpu_mesh* m, msmgpu_octree** out, std::vector<std::unique_ptr<msmgpu_octree>>& owned) {
+    return mesh_trees(m->ctx, 1, &m, out, owned);
+}
 msmgpu_status ensure_tables(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes);   // one launch for every dirty mesh
 msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, std::shared_ptr<Forest>& out, std::vector<int>& roots);
 

@@ -235,6 +235,27 @@ msmgpu_status mesh_refresh_tables(msmgpu_mesh* m) {
     return ensure_tables(m->ctx, 1, &m);
 }
 
+msmgpu_status mesh_trees(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, msmgpu_octree** out, std::vector<std::unique_ptr<msmgpu_octree>>& owned) {
+    std::vector<msmgpu_mesh*> need;
+    for (int i = 0; i < n; ++i)
+        if (meshes[i]->view || !meshes[i]->own_tree) {
+            bool seen = false;
+            for (msmgpu_mesh* m : need) seen = seen || m == meshes[i];
+            if (!seen) need.push_back(meshes[i]);
+        }
+    std::vector<msmgpu_octree*> built(need.size(), nullptr);
+    if (!need.empty()) MSM_TRY(msmgpu_octree_build_batch(ctx, (int)need.size(), need.data(), built.data()));
+    for (size_t k = 0; k < need.size(); ++k) {
+        if (need[k]->view) owned.emplace_back(built[k]);
+        else need[k]->own_tree = built[k];
+    }
+    for (int i = 0; i < n; ++i) {
+        if (!meshes[i]->view) { out[i] = meshes[i]->own_tree; continue; }
+        for (size_t k = 0; k < need.size(); ++k) if (need[k] == meshes[i]) out[i] = built[k];
+    }
+    return MSMGPU_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // level-synchronous build
 // ------------------------------------------------------------------------------------------
@@ -810,3 +831,5 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
 }
 
 } // namespace msm
+
+msmgpu_mesh::~msmgpu_mesh() { delete own_tree; }

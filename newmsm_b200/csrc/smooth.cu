@@ -139,3 +139,64 @@ extern "C" msmgpu_status msmgpu_smooth_data(msmgpu_ctx* ctx, int n, const double
     }
     return MSMGPU_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// variance_normalise (msm-newmeshreg/src/reg_tools.cpp:804-844): per channel, over the vertices the exclusion mask keeps, Welford's
+// running mean / variance in vertex order, then (x - mean) / sqrt(var). The recurrence is sequential by definition (every step divides
+// by the running count), so one thread walks one channel (IEEE + - * / only: the reference's bits); the rescaling is elementwise.
+// ---------------------------------------------------------------------------------------------------------------------------------
+namespace msm {
+
+__global__ void k_welford_channels(int D, int n, const double* __restrict__ data, const double* __restrict__ excl, double* __restrict__ mean_var) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= D) return;
+    const double* x = data + (size_t)d * n;
+    double mean = 0.0, var = 0.0;
+    unsigned int j = 0;   // the reference's loop counter over the compacted vector (cpp:820-825)
+    for (int i = 0; i < n; ++i) {
+        if (excl && !(excl[i] > 0.0)) continue;   // cpp:811
+        const double v = x[i];
+        const double delta = v - mean;
+        mean += delta / (double)(j + 1u);
+        var += delta * (v - mean);
+        ++j;
+    }
+    var /= (double)((size_t)j - (size_t)1);   // `_data[i].size() - 1` in size_t (cpp:827): 2^64 - 1 for an empty channel, 0 for one value
+    mean_var[2 * d] = mean;
+    mean_var[2 * d + 1] = var;
+}
+
+__global__ void k_rescale_channels(int D, int n, double* __restrict__ data, const double* __restrict__ excl, const double* __restrict__ mean_var) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)D * n) return;
+    const int d = (int)(i / n), v = (int)(i % n);
+    if (excl && !(excl[v] > 0.0)) return;         // excluded vertices keep their values (cpp:841)
+    const double mean = mean_var[2 * d], var = mean_var[2 * d + 1];
+    double x = data[i] - mean;
+    if (var > 0.0) x /= sqrt(var);               // cpp:831-832
+    data[i] = x;
+}
+
+}  // namespace msm
+
+extern "C" msmgpu_status msmgpu_variance_normalise(msmgpu_ctx* ctx, int D, int n, double* data_cm, const double* excl) {
+    using namespace msm;
+    if (!ctx || D <= 0 || n <= 0 || !data_cm) return fail(MSMGPU_ERR_INVALID, "variance_normalise: bad arguments");
+    MSM_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    DevBuf<double> d_data, d_excl, d_mv;
+    MSM_CUDA(d_data.alloc((size_t)D * n, s));
+    MSM_CUDA(d_mv.alloc(2 * (size_t)D, s));
+    MSM_CUDA(cudaMemcpyAsync(d_data.p, data_cm, (size_t)D * n * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (excl) {
+        MSM_CUDA(d_excl.alloc((size_t)n, s));
+        MSM_CUDA(cudaMemcpyAsync(d_excl.p, excl, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+    }
+    k_welford_channels<<<(unsigned)((D + 31) / 32), 32, 0, s>>>(D, n, d_data.p, excl ? d_excl.p : nullptr, d_mv.p);
+    MSM_LAUNCH_CHECK();
+    k_rescale_channels<<<(unsigned)(((size_t)D * n + 255) / 256), 256, 0, s>>>(D, n, d_data.p, excl ? d_excl.p : nullptr, d_mv.p);
+    MSM_LAUNCH_CHECK();
+    MSM_CUDA(cudaMemcpyAsync(data_cm, d_data.p, (size_t)D * n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    MSM_CUDA(cudaStreamSynchronize(s));
+    return MSMGPU_OK;
+}

@@ -714,10 +714,7 @@ msmgpu_status msmgpu_adaptive_weights_batch_fwd(msmgpu_ctx* ctx, int n, msmgpu_m
     else if (low_tree->mesh != low_mesh) return fail(MSMGPU_ERR_INVALID, "adaptive_weights: tree/mesh mismatch");
     std::vector<msmgpu_octree*> built(need.size(), nullptr);
     std::vector<std::unique_ptr<msmgpu_octree>> owned;
-    if (!need.empty()) {
-        MSM_TRY(msmgpu_octree_build_batch(ctx, (int)need.size(), need.data(), built.data()));
-        for (auto* t : built) owned.emplace_back(t);
-    }
+    if (!need.empty()) MSM_TRY(mesh_trees(ctx, (int)need.size(), need.data(), built.data(), owned));   // the meshes' own (cached) trees
     std::vector<msmgpu_octree*> trees(n);
     size_t k = 0;
     for (int i = 0; i < n; ++i) trees[i] = (in_trees && in_trees[i]) ? in_trees[i] : built[k++];
@@ -827,8 +824,8 @@ static msmgpu_status adaptive_weights_excl_dev(msmgpu_mesh* in_mesh, msmgpu_mesh
     cudaStream_t s = ctx->stream;
     msmgpu_mesh* ms[2] = {in_mesh, low_mesh};
     msmgpu_octree* ts[2] = {nullptr, nullptr};
-    MSM_TRY(msmgpu_octree_build_batch(ctx, 2, ms, ts));
-    std::unique_ptr<msmgpu_octree> g0(ts[0]), g1(ts[1]);
+    std::vector<std::unique_ptr<msmgpu_octree>> owned;
+    MSM_TRY(mesh_trees(ctx, 2, ms, ts, owned));
     // active targets: EXCL(octreeSearch_in.get_closest_vertex_ID(target)) != 0 (resampler.cpp:100)
     const int nl = low_mesh->nv;
     DevBuf<int> tri, vtx, st;

@@ -292,6 +292,14 @@ def smooth_data(orig: Mesh, sphLow: Mesh, sigma: float, nthreads: int = 1, EXCL=
     return out if excl is None else (out, eo)
 
 
+def variance_normalise(ctx: "Context", DATA, EXCL=None):
+    """newmeshreg::variance_normalise (reg_tools.cpp:804-844): [D, n] -> normalised copy; EXCL = mask values [n] or None."""
+    data = f64(np.atleast_2d(DATA)).copy()
+    excl = f64(EXCL) if EXCL is not None else None
+    check(capi.lib().msmgpu_variance_normalise(ctx.h, data.shape[0], data.shape[1], ptr(data), ptr(excl)))
+    return data
+
+
 def metric_resample_f32(in_mesh: Mesh, target: Mesh, feat_f32, in_tree: Octree | None = None, target_tree: Octree | None = None):
     """FP32 payload variant of metric_resample (GIFTI stores floats, mesh.cpp:625): [D,V] -> [D,n]."""
     feat = f32(feat_f32)

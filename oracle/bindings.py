@@ -635,6 +635,28 @@ class RefMR:
         return cls._lib
 
 
+def refmr_variance_normalise(data, excl=None, nthreads=1):
+    """The reference's newmeshreg::variance_normalise (reg_tools.cpp:804-844) on [D][n] -> normalised copy."""
+    L = RefMR.lib()
+    L.refmr_variance_normalise.restype = _i
+    L.refmr_variance_normalise.argtypes = [_i, _i, _vp, _vp, _i]
+    d = _f64(np.atleast_2d(data)).copy()
+    e = None if excl is None else _f64(excl)
+    if L.refmr_variance_normalise(d.shape[0], d.shape[1], _p(d), _p(e), nthreads) != 0:
+        raise RuntimeError("reference variance_normalise failed")
+    return d
+
+
+def oracle_variance_normalise(data, excl=None):
+    L = Oracle.lib()
+    L.orc_variance_normalise.restype = None
+    L.orc_variance_normalise.argtypes = [_i, _i, _vp, _vp]
+    d = _f64(np.atleast_2d(data)).copy()
+    e = None if excl is None else _f64(excl)
+    L.orc_variance_normalise(d.shape[0], d.shape[1], _p(d), _p(e))
+    return d
+
+
 def refmr_set_percentile(p):
     RefMR.lib().refmr_set_percentile(C.c_double(p))
 

@@ -1448,3 +1448,27 @@ int orc_rigid(int nv_t, const double* tgt_xyz, int nt_t, const int* tgt_tri, int
     } catch (...) { return -1; }
 }
 
+
+// variance_normalise, reg_tools.cpp:804-844: the compacted per-channel vectors, Welford's recurrence in vertex order (cpp:820-825),
+// var / (size - 1) in size_t (cpp:827), then (x - mean) and, when var > 0, / sqrt(var) (cpp:829-833), written back to the kept vertices
+void orc_variance_normalise(int D, int n, double* data, const double* excl) {
+    for (int k = 0; k < D; ++k) {
+        std::vector<double> v;
+        for (int i = 0; i < n; ++i)
+            if (!excl || excl[i] > 0.0) v.push_back(data[(size_t)k * n + i]);
+        double mean = 0.0, var = 0.0;
+        for (unsigned int j = 0; j < v.size(); j++) {
+            const double delta = v[j] - mean;
+            mean += delta / (j + 1);
+            var += delta * (v[j] - mean);
+        }
+        var /= (v.size() - 1);
+        for (unsigned int j = 0; j < v.size(); ++j) {
+            v[j] -= mean;
+            if (var > 0.0) v[j] /= std::sqrt(var);
+        }
+        int idx = 0;
+        for (int i = 0; i < n; ++i)
+            if (!excl || excl[i] > 0.0) data[(size_t)k * n + i] = v[idx++];
+    }
+}

@@ -104,6 +104,9 @@ int orc_unary_costs(int kind, int simmeasure, const orc_octree* target_tree,
 int orc_ho_patches(int ncp, const double* cp_xyz, int ntri, const int* cp_tri, int nsrc, const double* src_xyz,
                    int* rowptr, int* members, int cap);
 
+/* variance_normalise (msm-newmeshreg/src/reg_tools.cpp:804-844) in place on data [D][n]; excl NULL or [n] (kept where > 0). */
+void orc_variance_normalise(int D, int n, double* data, const double* excl);
+
 /* computeTripletCost (DiscreteCostFunction.cpp:135-188) for n requests; PARITY UNPINNED (see msm_oracle.cpp).
  * kind 0..2: likelihood 0; 3: HOUnivariate; 4: HOMultivariate. rmode 2/3 (spherical strain) only. */
 /* regoption 4/5 (anatomical strain, DiscreteCostFunction.cpp:169-181, 245-301): the meshes and maps of set_anatomical /

@@ -401,3 +401,24 @@ int refmr_rigid(int nv_t, const double* tgt_xyz, int nt_t, const int* tgt_tri, i
 }
 
 }  // extern "C"
+
+// newmeshreg::variance_normalise (reg_tools.cpp:804-844) on data [D][n] in place; excl NULL or [n] = the first channel of the EXCL mesh
+extern "C" int refmr_variance_normalise(int D, int n, double* data, const double* excl, int nthreads) {
+    try {
+        NEWMAT::Matrix M(D, n);
+        for (int d = 0; d < D; ++d)
+            for (int i = 0; i < n; ++i) M(d + 1, i + 1) = data[(size_t)d * n + i];
+        std::shared_ptr<MISCMATHS::BFMatrix> B = std::make_shared<MISCMATHS::FullBFMatrix>(M);
+        std::shared_ptr<Mesh> E;
+        if (excl) {
+            E = std::make_shared<Mesh>();
+            for (int i = 0; i < n; ++i) E->push_point(std::make_shared<newresampler::Mpoint>(0.0, 0.0, 0.0, i));
+            E->initialize_pvalues(1);
+            for (int i = 0; i < n; ++i) E->set_pvalue(i, excl[i]);
+        }
+        newmeshreg::variance_normalise(B, E, nthreads);
+        for (int d = 0; d < D; ++d)
+            for (int i = 0; i < n; ++i) data[(size_t)d * n + i] = B->Peek(d + 1, i + 1);
+        return 0;
+    } catch (...) { return -1; }
+}

@@ -50,7 +50,7 @@ MASK = False    # --mask: groupwise run with a cost mask (src/newmsm.cpp:25, Dis
 
 def run(binary, case, conf, out, threads, trace, extra_env=None):
     os.makedirs(out, exist_ok=True)
-    env = dict(os.environ, OMP_NUM_THREADS=str(threads), MSMGPU_TRACE=trace, MSMGPU_TIMING="1")
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads), MSMGPU_TRACE=trace, MSMGPU_TIMING=os.environ.get("MSMGPU_TIMING", "1"))
     env.update(extra_env or {})
     if GROUP:
         cmd = [binary, "--groupwise", "--meshes=" + os.path.join(case, "meshes.txt"), "--data=" + os.path.join(case, "data.txt"),

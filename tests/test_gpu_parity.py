@@ -1132,3 +1132,18 @@ def test_smooth_data_with_exclusion_mask_golden(R, oracle_built):
         assert np.array_equal(R.smooth_data(m, m, sigma), g[f"smooth{int(sigma)}"])
         s1, e1 = R.smooth_data(m, m, sigma, EXCL=excl)
         assert np.array_equal(s1, g[f"smooth{int(sigma)}_masked"]) and np.array_equal(e1, g[f"smooth{int(sigma)}_excl"])
+
+
+@pytest.mark.parametrize("masked", [False, True])
+def test_variance_normalise(R, oracle_built, masked):
+    """newmeshreg::variance_normalise (reg_tools.cpp:804-844) on the device vs the oracle (pinned against the reference in
+    tests/test_oracle_vs_refmr.py::test_variance_normalise), bit-exact."""
+    from test_oracle_vs_refmr import variance_cases
+    data, excl = variance_cases()
+    e = excl if masked else None
+    ctx = R.Context(0)
+    got = R.variance_normalise(ctx, data, e)
+    assert np.array_equal(got, oracle_built.oracle_variance_normalise(data, e), equal_nan=True)
+    assert np.array_equal(R.variance_normalise(ctx, data[:, :1]), oracle_built.oracle_variance_normalise(data[:, :1]), equal_nan=True)
+    big = np.random.default_rng(5).normal(size=(40, 40962))
+    assert np.array_equal(R.variance_normalise(ctx, big), oracle_built.oracle_variance_normalise(big))

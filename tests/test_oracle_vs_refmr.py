@@ -226,3 +226,28 @@ def test_rigid_level_oracle_matches_reference(O, sim, D, seed):
     assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])     # neighbourhoods (reg_tools.cpp:31-58, incl. the tie order of std::sort)
     assert a[1] == b[1]                                                  # cost at zero rotation
     assert np.array_equal(a[0], b[0])                                    # rotated source after run()
+
+
+def variance_cases():
+    rng = np.random.default_rng(77)
+    n = 2562
+    data = rng.normal(3.0, 2.5, size=(5, n)) * np.array([1.0, 1e-6, 1e6, 1.0, 0.0])[:, None]   # incl. a constant (zero-variance) channel
+    data[3] = np.round(data[3])                                                                   # many ties
+    excl = (rng.uniform(size=n) > 0.3).astype(np.float64) * rng.uniform(0.5, 2.0, size=n)       # 0 = excluded, positive = kept
+    excl[rng.integers(0, n, 50)] = -1.0                                                          # negative values are excluded too (> 0.0 test)
+    return data, excl
+
+
+@pytest.mark.parametrize("masked", [False, True])
+def test_variance_normalise(O, masked):
+    """newmeshreg::variance_normalise (reg_tools.cpp:804-844, last stage of featurespace::initialise): restatement vs the reference."""
+    data, excl = variance_cases()
+    e = excl if masked else None
+    ref = O.refmr_variance_normalise(data, e, nthreads=4)
+    got = O.oracle_variance_normalise(data, e)
+    assert np.array_equal(got, ref, equal_nan=True)
+    keep = (excl > 0) if masked else np.ones(data.shape[1], bool)
+    assert np.allclose(ref[0][keep].mean(), 0, atol=1e-12) and np.allclose(ref[0][keep].std(ddof=1), 1)
+    assert np.array_equal(ref[:, ~keep], data[:, ~keep])                 # excluded vertices keep their values
+    one = O.refmr_variance_normalise(data[:, :1]), O.oracle_variance_normalise(data[:, :1])   # a single value: 0 / 0 variance, value - mean = 0
+    assert np.array_equal(one[0], one[1], equal_nan=True)

@@ -1,5 +1,5 @@
 """Per-kernel device time of ONE bench step from an `ncu --metrics gpu__time_duration.sum -k regex:^k_ --csv` launch list
-(the step between the 4th and 5th fused-resample launch). Usage: python tools/step_kernels.py launches.csv [other.csv]"""
+(one step = from one k_mesh_tables launch, the first kernel of a step, to the next; the 4th such step of the list). Usage: python tools/step_kernels.py launches.csv [other.csv]"""
 import collections
 import csv
 import re
@@ -14,7 +14,7 @@ def load(path):
             continue
         v = float(r["Metric Value"].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(r["Metric Unit"], 1.0)
         data.append((re.sub(r"\(.*", "", r["Kernel Name"]).replace("void ", "").replace("msm::", ""), v))
-    b = [i for i, (n, _) in enumerate(data) if n.startswith("k_bary_resample_f32")]
+    b = [i for i, (n, _) in enumerate(data) if n.startswith("k_mesh_tables")]
     agg = collections.defaultdict(lambda: [0, 0.0])
     for k, v in data[b[3]:b[4]]:
         agg[k][0] += 1
