@@ -132,6 +132,10 @@ struct UnaryArgs {
     double* out;              // [L][ncp]
     int* tri_out;             // [L][n_patch] or NULL
     int* err;                 // set to 1 when a query finds no triangle
+    // multivariate kind: per-thread staging tiles [D][kCostThreads] doubles in shared memory at byte offset stage_off
+    // (0 = none, 1 = blended target values, 2 = target + source values); see the MULTIVARIATE branch of the kernel
+    int stage;
+    unsigned stage_off;
 };
 
 constexpr int kCostThreads = 64;
@@ -210,12 +214,42 @@ __global__ void __launch_bounds__(kCostThreads) k_unary_table(UnaryArgs a) {
                                [&](int i) { return cr >= 1 ? __ldg(a.cfw + (size_t)srcv(i) * cr) : 1.0; }, a.percentile);
         }
     } else if (a.kind == MSMGPU_COST_MULTIVARIATE) {   // cpp:444-458: per-vertex similarity across channels, mean over the patch
+        // A thread owns a patch point and walks its D channels sequentially (the reference's summation order). sim_corr reads every
+        // value twice (means, then covariances) and neighbouring lanes read different rows, so straight from global memory the kernel
+        // is bound by L1 wavefronts (ncu: 96 % l1tex, profiles/s3_cost_kernels_ncu.md). The rows are therefore read ONCE, with 16-byte
+        // loads, into a thread-private column of a shared tile (no barrier: a thread only reads back what it wrote); the arithmetic on
+        // the staged values is the same expression in the same order.
         const int cr = a.cfw_rows;
+        double* s_b = a.stage >= 1 ? reinterpret_cast<double*>(smem_raw + a.stage_off) + threadIdx.x : nullptr;
+        double* s_a = a.stage >= 2 ? s_b + (size_t)D * kCostThreads : nullptr;
         for (int i = threadIdx.x; i < P; i += kCostThreads) {
             const int sv = srcv(i);
+            if (s_b) {
+                const double w0 = s_w[3 * i], w1 = s_w[3 * i + 1], w2 = s_w[3 * i + 2];
+                const double *r0 = rf + (size_t)s_idx[3 * i] * D, *r1 = rf + (size_t)s_idx[3 * i + 1] * D, *r2 = rf + (size_t)s_idx[3 * i + 2] * D;
+                const double* ra = sf + (size_t)sv * D;
+                if ((D & 1) == 0) {   // rows start on 16-byte boundaries
+                    for (int d = 0; d < D; d += 2) {
+                        const double2 x0 = __ldg(reinterpret_cast<const double2*>(r0 + d)), x1 = __ldg(reinterpret_cast<const double2*>(r1 + d)),
+                                      x2 = __ldg(reinterpret_cast<const double2*>(r2 + d));
+                        s_b[(size_t)d * kCostThreads] = w0 * x0.x + w1 * x1.x + w2 * x2.x;
+                        s_b[(size_t)(d + 1) * kCostThreads] = w0 * x0.y + w1 * x1.y + w2 * x2.y;
+                        if (s_a) {
+                            const double2 xa = __ldg(reinterpret_cast<const double2*>(ra + d));
+                            s_a[(size_t)d * kCostThreads] = xa.x;
+                            s_a[(size_t)(d + 1) * kCostThreads] = xa.y;
+                        }
+                    }
+                } else {
+                    for (int d = 0; d < D; ++d) {
+                        s_b[(size_t)d * kCostThreads] = w0 * __ldg(r0 + d) + w1 * __ldg(r1 + d) + w2 * __ldg(r2 + d);
+                        if (s_a) s_a[(size_t)d * kCostThreads] = __ldg(ra + d);
+                    }
+                }
+            }
             s_sim[i] = sim_for_min(a.simmeasure, D,
-                                   [&](int d) { return __ldg(sf + (size_t)sv * D + d); },
-                                   [&](int d) { return tgt(i, d); },
+                                   [&](int d) { return s_a ? s_a[(size_t)d * kCostThreads] : __ldg(sf + (size_t)sv * D + d); },
+                                   [&](int d) { return s_b ? s_b[(size_t)d * kCostThreads] : tgt(i, d); },
                                    [&](int d) { return cr >= d + 1 ? __ldg(a.cfw + (size_t)sv * cr + d) : 1.0; }, a.percentile);
         }
         __syncthreads();
@@ -281,9 +315,21 @@ static msmgpu_status launch_unary_g(const UnaryArgs& a, size_t smem, cudaStream_
     return MSMGPU_OK;
 }
 
-static msmgpu_status launch_unary(const UnaryArgs& a, int max_patch, cudaStream_t s) {
-    const size_t smem = unary_smem_bytes(max_patch, a.D);
+static msmgpu_status launch_unary(UnaryArgs& a, int max_patch, cudaStream_t s) {
+    size_t smem = unary_smem_bytes(max_patch, a.D);
     if (smem > 200 * 1024) return fail(MSMGPU_ERR_CAPACITY, "unary_table: patch too large for shared memory");
+    a.stage = 0;
+    a.stage_off = (unsigned)((smem + 15) & ~(size_t)15);
+    if (a.kind == MSMGPU_COST_MULTIVARIATE) {
+        // staging while eight CTAs still fit an SM (measured, ico4 grid on ico6 data, 19 labels: D = 40 table 4.37 ms without, 3.18 ms with
+        // the target tile, 3.56 ms with target + source tiles; D = 100, where a tile leaves four CTAs per SM: 7.66 ms without, 8.35 ms with).
+        // Knob unary_stage = 0 / 1 / 2 tiles.
+        const size_t tile = (size_t)a.D * kCostThreads * sizeof(double);
+        const int want = tuning_get("unary_stage", "MSMGPU_UNARY_STAGE", 1);
+        for (int lvl = want < 2 ? want : 2; lvl >= 1; --lvl)
+            if (a.stage_off + lvl * tile <= 28 * 1024) { a.stage = lvl; break; }
+        smem = a.stage_off + a.stage * tile;
+    }
     switch (query_group_width()) {
         case 1: return launch_unary_g<1>(a, smem, s);
         case 2: return launch_unary_g<2>(a, smem, s);
