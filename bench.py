@@ -280,10 +280,33 @@ def parity_block(R, capi, L, xyz, tri, low_xyz, low_tri, d_feat0, d_out_b0, d_ou
 # --------------------------------------------------------------------------------------------
 # our arm (GPU)
 # --------------------------------------------------------------------------------------------
+def bind_to_gpu_numa(torch, local):
+    """Pin this rank's host threads (and, by first touch, its page-locked staging buffers) to the CPUs NVML names as closest to its GPU:
+    with several ranks per node the e2e path moves ~4.8 GB of host memory per rank and step, and a rank whose buffers sit on the other
+    socket pays the inter-socket link on every copy. Best effort: a cpuset that excludes those CPUs leaves the affinity as it was."""
+    info = {"cpus_before": len(os.sched_getaffinity(0))}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local)
+        bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        allowed = os.sched_getaffinity(0)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        ideal = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        use = ideal & allowed
+        if use and use != allowed:
+            os.sched_setaffinity(0, use)
+        info.update({"gpu_pci": bus, "ideal_cpus": len(ideal), "cpus_after": len(os.sched_getaffinity(0)), "bound": bool(use) and use != allowed})
+    except Exception as ex:   # no NVML, no permission: measure unbound
+        info.update({"bound": False, "note": f"{type(ex).__name__}: {ex}"})
+    return info
+
+
 def run_ours(a):
     if "WORLD_SIZE" in os.environ and "BENCH_KEEP_OMP" not in os.environ:
         # torchrun pins OMP_NUM_THREADS to 1; the library's host-side finishes (libm pow / acos of the cost paths) are OpenMP loops
-        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // int(os.environ["WORLD_SIZE"])))
+        os.environ["OMP_NUM_THREADS"] = str(max(1, len(os.sched_getaffinity(0)) // int(os.environ["WORLD_SIZE"])))
     import torch
     import torch.distributed as dist
     from newmsm_b200 import build, capi, resampler as R
@@ -295,6 +318,7 @@ def run_ours(a):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    host_binding = bind_to_gpu_numa(torch, local) if (world > 1 and "BENCH_NO_BIND" not in os.environ) else {"bound": False, "note": "single rank"}
     build.build_library()
     L = capi.lib()
     assert L.msmgpu_device_count() > 0, "bench.py needs a CUDA device (no CPU fallback)"
@@ -555,7 +579,8 @@ def run_ours(a):
     if rank == 0:
         cfg = workload_config(a, nv, nt, n_low)
         detail = {"query_group_lanes": int(L.msmgpu_get_query_group()), "breakdown_ms_per_step": breakdown, "value_streams": NW,
-                  "breakdown_note": f"stage times of one of the {NW} concurrent subject groups ({len(groups[0])} subjects)"}
+                  "breakdown_note": f"stage times of one of the {NW} concurrent subject groups ({len(groups[0])} subjects)",
+                  "host_binding_rank0": host_binding}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": cfg, "clocks": clk, "gpu_launches": launches, "roofline": roofline, "detail": detail}
@@ -636,7 +661,7 @@ def run_gmsm(a, torch, dist, rank, world, local):
         tsum = 0.0
         M.reset_triplet_state(cps, orig, rot, labels, trip)      # once per iteration, like reset_CPgrid / estimate_triplets
         for l in range(1, Lb):
-            tsum += float(M.computeTripletCostsForLabel(None, None, None, None, None, labeling, l, 0.2).sum())
+            tsum += float(M.computeTripletCostsForLabel(None, None, None, None, None, labeling, l, 0.2, copy=False)[::997].sum())
         sync(); t3 = time.perf_counter()
         out = {"fields_s": tmax(t1 - t0), "pair_sweep_s": tmax(t2 - t1), "triplet_sweep_s": tmax(t3 - t2), "iteration_s": tmax(t3 - t0)}
     # the collective alone: all-gather of the field shards, CUDA events on this rank's stream, max over ranks

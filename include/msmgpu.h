@@ -388,6 +388,9 @@ msmgpu_status msmgpu_triplet_plan_create(msmgpu_ctx* ctx, int n_nodes, const dou
 void msmgpu_triplet_plan_destroy(msmgpu_triplet_plan* p);
 msmgpu_status msmgpu_triplet_plan_batch(msmgpu_triplet_plan* p, const msmgpu_reg_params* prm, double subcorr, int fixnan, int first_triplet,
                                         int n_triplets, const int32_t* labeling, int label, double* out);
+/* the same with the costs left on the device (d_out [n_triplets][8] device doubles, the call returns when they are complete): a sharded host gathers the blocks device to device and copies once */
+msmgpu_status msmgpu_triplet_plan_batch_dev(msmgpu_triplet_plan* p, const msmgpu_reg_params* prm, double subcorr, int fixnan, int first_triplet,
+                                            int n_triplets, const int32_t* labeling, int label, double* d_out);
 
 #ifdef __cplusplus
 }

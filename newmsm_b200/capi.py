@@ -131,6 +131,7 @@ _SIGNATURES = {
     "msmgpu_triplet_plan_create": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _pp]),
     "msmgpu_triplet_plan_destroy": (None, [_vp]),
     "msmgpu_triplet_plan_batch": (_i, [_vp, _vp, _d, _i, _i, _i, _vp, _i, _vp]),
+    "msmgpu_triplet_plan_batch_dev": (_i, [_vp, _vp, _d, _i, _i, _i, _vp, _i, _vp]),
     "msmgpu_group_triplet_batch": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _d, _i, _vp, _i, _vp]),
 }
 

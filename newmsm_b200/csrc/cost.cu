@@ -136,97 +136,107 @@ struct UnaryArgs {
     // (0 = none, 1 = blended target values, 2 = target + source values); see the MULTIVARIATE branch of the kernel
     int stage;
     unsigned stage_off;
+    int lb;                   // labels per CTA (<= kMaxLabelBlock)
 };
 
 constexpr int kCostThreads = 64;
+constexpr int kMaxLabelBlock = 8;   // labels per CTA (UnaryArgs::lb)
 
+// One CTA (64 threads) per (control point k, block of `lb` labels). A patch of this size (~67 points at range 1) fills a 64-thread
+// round only once and a bit, so with one label per CTA the second round of BOTH phases ran nearly empty; the (label, point) items of a
+// label block are therefore flattened: item q -> label l0 + q / P, patch point q % P. The sequential sums that follow (one lane per
+// independent sum, the reference's order) then also run for the block's labels side by side in neighbouring lanes.
 template <int G>
 __global__ void __launch_bounds__(kCostThreads) k_unary_table(UnaryArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int k = blockIdx.x, l = blockIdx.y;
+    const int k = blockIdx.x, l0 = blockIdx.y * a.lb, nl = min(a.lb, a.L - l0);
     const int p0 = a.prow[k], P = a.prow[k + 1] - p0;
-    // shared: w[P][3] doubles | sims[max(P,D)] doubles | idx[P][3] ints | bad flag
+    const int NP = nl * P;
+    const int D = a.D;
+    // shared: w[NP][3] doubles | sims[max(NP, nl * D)] doubles | idx[NP][3] ints | staging tiles at stage_off (launch_unary)
     double* s_w = reinterpret_cast<double*>(smem_raw);
-    const int n_sims = P > a.D ? P : a.D;
-    double* s_sim = s_w + 3 * (size_t)P;
+    const int n_sims = NP > nl * D ? NP : nl * D;
+    double* s_sim = s_w + 3 * (size_t)NP;
     int* s_idx = reinterpret_cast<int*>(s_sim + n_sims);
-    __shared__ int s_bad;
-    if (threadIdx.x == 0) s_bad = 0;
+    __shared__ int s_bad[kMaxLabelBlock];
+    if (threadIdx.x < kMaxLabelBlock) s_bad[threadIdx.x] = 0;
     __syncthreads();
-
-    double R[9];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) R[i] = __ldg(a.R + ((size_t)l * a.ncp + k) * 9 + i);
 
     // phase 1 (get_target_data, cpp:353-376 / 410-442 / 652-678): rotate, locate, weights
     const int gl = threadIdx.x % G;
-    const int rounds = (P + kCostThreads / G - 1) / (kCostThreads / G);
+    const int rounds = (NP + kCostThreads / G - 1) / (kCostThreads / G);
     for (int r = 0; r < rounds; ++r) {
-        const int i = r * (kCostThreads / G) + threadIdx.x / G;
-        const bool active = i < P;
+        const int q = r * (kCostThreads / G) + threadIdx.x / G;
+        const bool active = q < NP;
+        const int lq = active ? q / P : 0, i = active ? q - lq * P : 0;
         V3 tmp{0, 0, 0};
         if (active) {
+            const double* Rm = a.R + ((size_t)(l0 + lq) * a.ncp + k) * 9;
+            double R[9];
+#pragma unroll
+            for (int j = 0; j < 9; ++j) R[j] = __ldg(Rm + j);
             const int sv = __ldg(a.pmem + p0 + i);
             tmp = mat_apply(R, V3{__ldg(a.src_xyz + 3 * (size_t)sv), __ldg(a.src_xyz + 3 * (size_t)sv + 1), __ldg(a.src_xyz + 3 * (size_t)sv + 2)});
         }
         int st;
         const int t = nearest_triangle<G>(a.tree, tmp, active, gl, st);
         if (active && gl == 0) {
-            if (a.tri_out) a.tri_out[(size_t)l * a.n_patch + p0 + i] = t;
+            if (a.tri_out) a.tri_out[(size_t)(l0 + lq) * a.n_patch + p0 + i] = t;
             if (t < 0) {
-                s_bad = 1;
+                s_bad[lq] = 1;
             } else {
                 const double* v = a.tree.rec[t].v;
                 double w[3];
                 bary_weights_raw(tmp, V3{v[0], v[1], v[2]}, V3{v[3], v[4], v[5]}, V3{v[6], v[7], v[8]}, w);
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
-                    s_w[3 * i + j] = w[j];
-                    s_idx[3 * i + j] = __ldg(a.tree.tri + 3 * (size_t)t + j);
+                    s_w[3 * q + j] = w[j];
+                    s_idx[3 * q + j] = __ldg(a.tree.tri + 3 * (size_t)t + j);
                 }
             }
         }
     }
     __syncthreads();
-    if (s_bad) {   // the reference throws here (octree.cpp:211); the table entry is NaN and the call reports the error
-        if (threadIdx.x == 0) { a.out[(size_t)l * a.ncp + k] = nan(""); *a.err = 1; }
-        return;
-    }
+    bool any_bad = false;
+    for (int j = 0; j < nl; ++j) any_bad = any_bad || s_bad[j];
+    if (any_bad && threadIdx.x == 0) *a.err = 1;   // the reference throws here (octree.cpp:211); the entries of that label are NaN
 
-    const int D = a.D;
     const double* __restrict__ rf = a.ref_feat;
     const double* __restrict__ sf = a.src_feat;
-    // target value of patch point i in channel d (triangle.cpp:156: Aa*va1 + Ab*va2 + Ac*va3)
-    auto tgt = [&](int i, int d) -> double {
-        return s_w[3 * i] * __ldg(rf + (size_t)s_idx[3 * i] * D + d) + s_w[3 * i + 1] * __ldg(rf + (size_t)s_idx[3 * i + 1] * D + d) +
-               s_w[3 * i + 2] * __ldg(rf + (size_t)s_idx[3 * i + 2] * D + d);
+    // target value of item q in channel d (triangle.cpp:156: Aa*va1 + Ab*va2 + Ac*va3); items of a label with a failed query are skipped
+    auto tgt = [&](int q, int d) -> double {
+        return s_w[3 * q] * __ldg(rf + (size_t)s_idx[3 * q] * D + d) + s_w[3 * q + 1] * __ldg(rf + (size_t)s_idx[3 * q + 1] * D + d) +
+               s_w[3 * q + 2] * __ldg(rf + (size_t)s_idx[3 * q + 2] * D + d);
     };
     auto srcv = [&](int i) -> int { return __ldg(a.pmem + p0 + i); };
+    const int cr = a.cfw_rows;
     double cost = 0.0;
+    const int lt = threadIdx.x;   // the label of this block whose sequential sums this lane owns (lt < nl)
     if (a.kind == MSMGPU_COST_UNIVARIATE) {   // cpp:378-383
-        for (int i = threadIdx.x; i < P; i += kCostThreads) s_sim[i] = tgt(i, 0);   // parallel gather, sequential sums below
+        for (int q = threadIdx.x; q < NP; q += kCostThreads)
+            if (!s_bad[q / P]) s_sim[q] = tgt(q, 0);   // parallel gather, sequential sums below
         __syncthreads();
-        if (threadIdx.x == 0) {
-            const int cr = a.cfw_rows;
+        if (lt < nl && !s_bad[lt]) {
+            const double* sim = s_sim + (size_t)lt * P;
             cost = sim_for_min(a.simmeasure, P,
                                [&](int i) { return __ldg(sf + (size_t)srcv(i) * D); },
-                               [&](int i) { return s_sim[i]; },
+                               [&](int i) { return sim[i]; },
                                [&](int i) { return cr >= 1 ? __ldg(a.cfw + (size_t)srcv(i) * cr) : 1.0; }, a.percentile);
         }
     } else if (a.kind == MSMGPU_COST_MULTIVARIATE) {   // cpp:444-458: per-vertex similarity across channels, mean over the patch
-        // A thread owns a patch point and walks its D channels sequentially (the reference's summation order). sim_corr reads every
+        // A thread owns an item and walks its D channels sequentially (the reference's summation order). sim_corr reads every
         // value twice (means, then covariances) and neighbouring lanes read different rows, so straight from global memory the kernel
         // is bound by L1 wavefronts (ncu: 96 % l1tex, profiles/s3_cost_kernels_ncu.md). The rows are therefore read ONCE, with 16-byte
         // loads, into a thread-private column of a shared tile (no barrier: a thread only reads back what it wrote); the arithmetic on
         // the staged values is the same expression in the same order.
-        const int cr = a.cfw_rows;
         double* s_b = a.stage >= 1 ? reinterpret_cast<double*>(smem_raw + a.stage_off) + threadIdx.x : nullptr;
         double* s_a = a.stage >= 2 ? s_b + (size_t)D * kCostThreads : nullptr;
-        for (int i = threadIdx.x; i < P; i += kCostThreads) {
-            const int sv = srcv(i);
+        for (int q = threadIdx.x; q < NP; q += kCostThreads) {
+            if (s_bad[q / P]) continue;
+            const int sv = srcv(q % P);
             if (s_b) {
-                const double w0 = s_w[3 * i], w1 = s_w[3 * i + 1], w2 = s_w[3 * i + 2];
-                const double *r0 = rf + (size_t)s_idx[3 * i] * D, *r1 = rf + (size_t)s_idx[3 * i + 1] * D, *r2 = rf + (size_t)s_idx[3 * i + 2] * D;
+                const double w0 = s_w[3 * q], w1 = s_w[3 * q + 1], w2 = s_w[3 * q + 2];
+                const double *r0 = rf + (size_t)s_idx[3 * q] * D, *r1 = rf + (size_t)s_idx[3 * q + 1] * D, *r2 = rf + (size_t)s_idx[3 * q + 2] * D;
                 const double* ra = sf + (size_t)sv * D;
                 if ((D & 1) == 0) {   // rows start on 16-byte boundaries
                     for (int d = 0; d < D; d += 2) {
@@ -247,31 +257,32 @@ __global__ void __launch_bounds__(kCostThreads) k_unary_table(UnaryArgs a) {
                     }
                 }
             }
-            s_sim[i] = sim_for_min(a.simmeasure, D,
+            s_sim[q] = sim_for_min(a.simmeasure, D,
                                    [&](int d) { return s_a ? s_a[(size_t)d * kCostThreads] : __ldg(sf + (size_t)sv * D + d); },
-                                   [&](int d) { return s_b ? s_b[(size_t)d * kCostThreads] : tgt(i, d); },
+                                   [&](int d) { return s_b ? s_b[(size_t)d * kCostThreads] : tgt(q, d); },
                                    [&](int d) { return cr >= d + 1 ? __ldg(a.cfw + (size_t)sv * cr + d) : 1.0; }, a.percentile);
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int i = 0; i < P; ++i) cost += s_sim[i];
+        if (lt < nl && !s_bad[lt]) {
+            for (int i = 0; i < P; ++i) cost += s_sim[(size_t)lt * P + i];
             if (P > 0) cost /= P;
         }
     } else {   // cpp:681-692: per-channel similarity across the patch, mean over channels
-        const int cr = a.cfw_rows;
-        for (int d = threadIdx.x; d < D; d += kCostThreads) {
-            s_sim[d] = sim_for_min(a.simmeasure, P,
+        for (int q = threadIdx.x; q < nl * D; q += kCostThreads) {
+            const int lq = q / D, d = q - lq * D;
+            if (s_bad[lq]) continue;
+            s_sim[q] = sim_for_min(a.simmeasure, P,
                                    [&](int i) { return __ldg(sf + (size_t)srcv(i) * D + d); },
-                                   [&](int i) { return tgt(i, d); },
+                                   [&](int i) { return tgt(lq * P + i, d); },
                                    [&](int i) { return cr >= 1 ? __ldg(a.cfw + (size_t)srcv(i) * cr) : 1.0; }, a.percentile);
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int d = 0; d < D; ++d) cost += s_sim[d];
+        if (lt < nl && !s_bad[lt]) {
+            for (int d = 0; d < D; ++d) cost += s_sim[(size_t)lt * D + d];
             cost /= D;
         }
     }
-    if (threadIdx.x == 0) a.out[(size_t)l * a.ncp + k] = __ldg(a.absw + k) * cost;
+    if (lt < nl) a.out[(size_t)(l0 + lt) * a.ncp + k] = s_bad[lt] ? nan("") : __ldg(a.absw + k) * cost;
 }
 
 // CSR lists {i : |cp_k - src_i| < thr_k}, ascending i, for n_cp centres (count pass, scan, write pass); synchronises
@@ -310,13 +321,19 @@ static size_t unary_smem_bytes(int max_patch, int D) {
 template <int G>
 static msmgpu_status launch_unary_g(const UnaryArgs& a, size_t smem, cudaStream_t s) {
     if (smem > 48 * 1024) MSM_CUDA(cudaFuncSetAttribute(k_unary_table<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_unary_table<G><<<dim3((unsigned)a.ncp, (unsigned)a.L), kCostThreads, smem, s>>>(a);
+    k_unary_table<G><<<dim3((unsigned)a.ncp, (unsigned)((a.L + a.lb - 1) / a.lb)), kCostThreads, smem, s>>>(a);
     MSM_LAUNCH_CHECK();
     return MSMGPU_OK;
 }
 
 static msmgpu_status launch_unary(UnaryArgs& a, int max_patch, cudaStream_t s) {
-    size_t smem = unary_smem_bytes(max_patch, a.D);
+    // labels per CTA: up to `unary_labels` (default 4) while the per-item arrays of the largest patch stay within 24 KB
+    a.lb = tuning_get("unary_labels", "MSMGPU_UNARY_LABELS", 4);
+    if (a.lb > kMaxLabelBlock) a.lb = kMaxLabelBlock;
+    if (a.lb > a.L) a.lb = a.L;
+    if (a.lb < 1) a.lb = 1;
+    while (a.lb > 1 && unary_smem_bytes(max_patch * a.lb, a.D * a.lb) > 24 * 1024) --a.lb;
+    size_t smem = unary_smem_bytes(max_patch * a.lb, a.D * a.lb);
     if (smem > 200 * 1024) return fail(MSMGPU_ERR_CAPACITY, "unary_table: patch too large for shared memory");
     a.stage = 0;
     a.stage_off = (unsigned)((smem + 15) & ~(size_t)15);

@@ -486,8 +486,10 @@ static void finish_on_host_anat(int n, const double* aux, const double* aux_anat
 }
 
 // launches the request kernel for `a` (everything but out / aux / err / pow / shared-memory layout set by the caller) and brings the costs to `out`
+// d_user != NULL: the costs stay on the device in the caller's buffer (`out` is then only scratch for the host finish when the device
+// pow is disabled)
 static msmgpu_status run_requests(msmgpu_ctx* ctx, TripletArgs& a, bool ho, const msmgpu_reg_params* prm, double* out,
-                                  const msmgpu_costfn::Anat* anat = nullptr, const int32_t* h_req_t = nullptr) {
+                                  const msmgpu_costfn::Anat* anat = nullptr, const int32_t* h_req_t = nullptr, double* d_user = nullptr) {
     cudaStream_t s = ctx->stream;
     const int n = a.n;
     const DevicePow& dp = device_pow(ctx->device);
@@ -496,11 +498,11 @@ static msmgpu_status run_requests(msmgpu_ctx* ctx, TripletArgs& a, bool ho, cons
     a.rmode = prm->rmode;
     DevBuf<double> d_out, d_aux, d_aux_anat;
     DevBuf<int> d_err;
-    MSM_CUDA(d_out.alloc((size_t)n, s));
+    if (!d_user) MSM_CUDA(d_out.alloc((size_t)n, s));
     if (!a.dev_pow) MSM_CUDA(d_aux.alloc(2 * (size_t)n, s));
     MSM_CUDA(d_err.alloc(1, s));
     MSM_CUDA(cudaMemsetAsync(d_err.p, 0, sizeof(int), s));
-    a.out = d_out.p; a.aux = d_aux.p; a.err = d_err.p;
+    a.out = d_user ? d_user : d_out.p; a.aux = d_aux.p; a.err = d_err.p;
     const bool an = a.rmode >= 4;
     if (an) {
         a.an_max_u = anat->max_u; a.an_max_f = anat->max_f;
@@ -534,7 +536,9 @@ static msmgpu_status run_requests(msmgpu_ctx* ctx, TripletArgs& a, bool ho, cons
     }
     int h_err = 0;
     std::vector<double> aux, aux_anat;
-    MSM_CUDA(cudaMemcpyAsync(out, d_out.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    std::vector<double> scratch;
+    if (d_user && !a.dev_pow) { scratch.resize((size_t)n); out = scratch.data(); }
+    if (!d_user || !a.dev_pow) MSM_CUDA(cudaMemcpyAsync(out, a.out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (!a.dev_pow) {
         aux.resize(2 * (size_t)n);
         MSM_CUDA(cudaMemcpyAsync(aux.data(), d_aux.p, aux.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -549,6 +553,10 @@ static msmgpu_status run_requests(msmgpu_ctx* ctx, TripletArgs& a, bool ho, cons
     if (!a.dev_pow) {
         if (an) finish_on_host_anat(n, aux.data(), aux_anat.data(), anat->max_f, anat->h_face_ptr, h_req_t, out, prm);
         else finish_on_host(n, aux.data(), out, prm, a.group, a.fixnan, a.subcorr);
+        if (d_user) {
+            MSM_CUDA(cudaMemcpyAsync(d_user, out, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+            MSM_CUDA(cudaStreamSynchronize(s));
+        }
     }
     return MSMGPU_OK;
 }
@@ -629,8 +637,8 @@ static msmgpu_status plan_create(msmgpu_ctx* ctx, int n_nodes, const double* cp_
 
 static msmgpu_status plan_run(msmgpu_triplet_plan* p, const msmgpu_reg_params* prm, double subcorr, int fixnan, int first_triplet, int n_triplets,
                               int n, const int32_t* req_t, const int32_t* req_la, const int32_t* req_lb, const int32_t* req_lc,
-                              const int32_t* labeling, int label, double* out) {
-    if (!p || !prm || n <= 0 || !out) return fail(MSMGPU_ERR_INVALID, "group_triplet: bad arguments");
+                              const int32_t* labeling, int label, double* out, double* d_user = nullptr) {
+    if (!p || !prm || n <= 0 || (!out && !d_user)) return fail(MSMGPU_ERR_INVALID, "group_triplet: bad arguments");
     MSM_CUDA(cudaSetDevice(p->ctx->device));
     cudaStream_t s = p->ctx->stream;
     DevBuf<int> d_rt, d_la, d_lb, d_lc;
@@ -651,7 +659,7 @@ static msmgpu_status plan_run(msmgpu_triplet_plan* p, const msmgpu_reg_params* p
     a.fold_value = 1e7;
     a.group = 1; a.fixnan = fixnan; a.subcorr = subcorr;
     (void)n_triplets;
-    return run_requests(p->ctx, a, false, prm, out);
+    return run_requests(p->ctx, a, false, prm, out, nullptr, nullptr, d_user);
 }
 
 } // namespace msm
@@ -699,6 +707,13 @@ msmgpu_status msmgpu_triplet_plan_batch(msmgpu_triplet_plan* p, const msmgpu_reg
     if (!p || !labeling || label < 0 || label >= p->L || first_triplet < 0 || n_triplets <= 0 || first_triplet + (long long)n_triplets > p->ntrip)
         return fail(MSMGPU_ERR_INVALID, "triplet_plan_batch: bad arguments");
     return plan_run(p, prm, subcorr, fixnan, first_triplet, n_triplets, 8 * n_triplets, nullptr, nullptr, nullptr, nullptr, labeling, label, out);
+}
+
+msmgpu_status msmgpu_triplet_plan_batch_dev(msmgpu_triplet_plan* p, const msmgpu_reg_params* prm, double subcorr, int fixnan, int first_triplet,
+                                            int n_triplets, const int32_t* labeling, int label, double* d_out) {
+    if (!p || !labeling || !d_out || label < 0 || label >= p->L || first_triplet < 0 || n_triplets <= 0 || first_triplet + (long long)n_triplets > p->ntrip)
+        return fail(MSMGPU_ERR_INVALID, "triplet_plan_batch_dev: bad arguments");
+    return plan_run(p, prm, subcorr, fixnan, first_triplet, n_triplets, 8 * n_triplets, nullptr, nullptr, nullptr, nullptr, labeling, label, nullptr, d_out);
 }
 
 msmgpu_costfn::Anat::~Anat() {

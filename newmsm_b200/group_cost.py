@@ -224,16 +224,28 @@ class DiscreteGroupModel:
         self._plan_S, self._plan_T = f64(cps).shape[0], len(trip)
 
     def computeTripletCostsForLabel(self, cps, orig_cps, rotations, labels, triplets, labeling, label, lambda_, shearmodulus=0.4, bulkmodulus=1.6,
-                                    kexponent=2.0, exponent=2.0, fixnan=False):
-        """The 8 combinations per triplet of Fusion::optimize (Fusion.h:181-196) -> [T, 8]. cps=None: the arrays set by reset_triplet_state."""
+                                    kexponent=2.0, exponent=2.0, fixnan=False, copy=True):
+        """The 8 combinations per triplet of Fusion::optimize (Fusion.h:181-196) -> [T, 8]. cps=None: the arrays set by reset_triplet_state
+        (copy=False then returns a view of the reused pinned buffer, valid until the next call)."""
         reg = capi.RegParams(lambda_, shearmodulus, bulkmodulus, kexponent, exponent, 3)
         lab = i32(labeling)
         if cps is None:
+            # resident plan: the block's costs stay on the device, the blocks are gathered device to device (NCCL) and come to the host
+            # once, into a reused pinned buffer -- the same data path as the pair batches above
+            import torch
             S, T = self._plan_S, self._plan_T
+            dev = torch.device("cuda", self.ctx.device)
             b, e = shard_range(T, self.coll.rank, self.coll.world)       # triplets are per subject: block-sharded like the pairs
-            out = np.zeros((e - b, 8))
+            local = torch.empty((e - b, 8), dtype=torch.float64, device=dev)
+            torch.cuda.synchronize(dev)
             if e > b:
-                check(self.L_.msmgpu_triplet_plan_batch(self._plan, C.byref(reg), 0.1 * S, int(fixnan), b, e - b, ptr(lab), int(label), ptr(out)))
+                check(self.L_.msmgpu_triplet_plan_batch_dev(self._plan, C.byref(reg), 0.1 * S, int(fixnan), b, e - b, ptr(lab), int(label), ptr(local)))
+            full = local if self.coll.world == 1 else self.coll.all_gather_blocks(local, T)
+            if getattr(self, "_host_trip", None) is None or self._host_trip.shape[0] != T:
+                self._host_trip = torch.empty((T, 8), dtype=torch.float64, pin_memory=True)
+            self._host_trip.copy_(full)
+            torch.cuda.synchronize(dev)
+            return self._host_trip.numpy().copy() if copy else self._host_trip.numpy()
         else:
             cp, org = f64(cps).reshape(-1, 3), f64(orig_cps).reshape(-1, 3)
             S = f64(cps).shape[0]

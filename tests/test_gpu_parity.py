@@ -737,6 +737,10 @@ def test_group_costs_vs_reference_golden(R, oracle_built):
     tt = np.repeat(np.arange(T, dtype=np.int32), 8); combo = np.tile(np.arange(8), T)
     pick = lambda k, bit: np.where((combo >> bit) & 1, 2, labeling[trip[tt, k]]).astype(np.int32)
     assert np.array_equal(batch.reshape(-1), Mt.computeTripletCostList(c["cps"], orig, rot_t, c["labels"], trip, tt, pick(0, 2), pick(1, 1), pick(2, 0), 0.05))
+    # the resident plan with the costs left on the device (msmgpu_triplet_plan_batch_dev: the sharded hosts' data path) gives the same table
+    Mt.reset_triplet_state(c["cps"], orig, rot_t, c["labels"], trip)
+    assert np.array_equal(Mt.computeTripletCostsForLabel(None, None, None, None, None, labeling, 2, 0.05), batch)
+    assert np.array_equal(Mt.computeTripletCostsForLabel(None, None, None, None, None, labeling, 2, 0.05, copy=False), batch)
     assert np.array_equal(golden_digest(c), g["group_digest"]), "seeded inputs drifted: regenerate the fixture"
     rot, spacings, pairs, (rp, la, lb) = golden_group_glue(oracle_built, c)
     for sim in (1, 2):
