@@ -654,14 +654,15 @@ def run_gmsm(a, torch, dist, rank, world, local):
         M.get_patch_data(data, dtri, feat, labels, centre, rot, spac, 1.0)          # fields + all-gather + group state
         sync(); t1 = time.perf_counter()
         sample = []
-        for l in range(1, Lb):
-            c = M.computePairwiseCostsForLabel(pairs, labeling, l, copy=False)
-            sample.append(c[::997].ravel().copy())
+        for l in range(1, Lb):       # the host solver lives on rank 0: every rank computes its block and gathers, rank 0 downloads the table
+            c = M.computePairwiseCostsForLabel(pairs, labeling, l, copy=False, to_host=(rank == 0))
+            if c is not None: sample.append(c[::997].ravel().copy())
         sync(); t2 = time.perf_counter()
         tsum = 0.0
         M.reset_triplet_state(cps, orig, rot, labels, trip)      # once per iteration, like reset_CPgrid / estimate_triplets
         for l in range(1, Lb):
-            tsum += float(M.computeTripletCostsForLabel(None, None, None, None, None, labeling, l, 0.2, copy=False)[::997].sum())
+            c = M.computeTripletCostsForLabel(None, None, None, None, None, labeling, l, 0.2, copy=False, to_host=(rank == 0))
+            if c is not None: tsum += float(c[::997].sum())
         sync(); t3 = time.perf_counter()
         out = {"fields_s": tmax(t1 - t0), "pair_sweep_s": tmax(t2 - t1), "triplet_sweep_s": tmax(t3 - t2), "iteration_s": tmax(t3 - t0)}
     # the collective alone: all-gather of the field shards, CUDA events on this rank's stream, max over ranks
@@ -713,7 +714,8 @@ def run_gmsm(a, torch, dist, rank, world, local):
            "sharded_equals_unsharded_bitwise": same,
            "limiter_note": "fields: host libm rotation matrices + per-rank build; pairs: device-bound (k_group_pair_costs_thread); triplets: strain + the three "
                            "pow() per cost on the device (glibc's algorithm with the host library's tables, csrc/hostpow.cuh; device_pow_enabled below), "
-                           "bound by the D2H copy of the [T][8] table per label phase",
+                           "bound by the D2H copy of the [T][8] table per label phase; the cost tables of a label phase are gathered on every rank's device (NCCL) "
+                           "and downloaded by rank 0 only, where the host solver runs",
            "device_pow_enabled": bool(capi_device_pow()),
            "gpu_launches": int(capi_launches() - launches0), "timing": "wall clock between device synchronisations + barriers, max over ranks; second of two iterations"}
     M.close()      # the context is released with the last object that holds it (meshes / trees keep a reference)

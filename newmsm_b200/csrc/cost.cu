@@ -333,20 +333,25 @@ static msmgpu_status launch_unary(UnaryArgs& a, int max_patch, cudaStream_t s) {
     if (a.lb > a.L) a.lb = a.L;
     if (a.lb < 1) a.lb = 1;
     while (a.lb > 1 && unary_smem_bytes(max_patch * a.lb, a.D * a.lb) > 24 * 1024) --a.lb;
-    size_t smem = unary_smem_bytes(max_patch * a.lb, a.D * a.lb);
-    if (smem > 200 * 1024) return fail(MSMGPU_ERR_CAPACITY, "unary_table: patch too large for shared memory");
     a.stage = 0;
-    a.stage_off = (unsigned)((smem + 15) & ~(size_t)15);
+    const size_t kStageBudget = 28 * 1024;   // eight CTAs per SM
     if (a.kind == MSMGPU_COST_MULTIVARIATE) {
-        // staging while eight CTAs still fit an SM (measured, ico4 grid on ico6 data, 19 labels: D = 40 table 4.37 ms without, 3.18 ms with
-        // the target tile, 3.56 ms with target + source tiles; D = 100, where a tile leaves four CTAs per SM: 7.66 ms without, 8.35 ms with).
-        // Knob unary_stage = 0 / 1 / 2 tiles.
+        // Staging tiles while eight CTAs still fit an SM, and the label block shrinks before the tile is given up (measured, ico4 grid on
+        // ico6 data, 19 labels, D = 40, whole call: no tile 4.37 ms; target tile 3.18 ms; target + source tiles 3.56 ms; tile with 2 labels
+        // per CTA 3.14 ms; 4 labels per CTA without room for the tile 4.46 ms. D = 100, where a tile leaves four CTAs per SM: 7.66 ms
+        // without, 8.35 ms with). Knob unary_stage = 0 / 1 / 2 tiles.
         const size_t tile = (size_t)a.D * kCostThreads * sizeof(double);
         const int want = tuning_get("unary_stage", "MSMGPU_UNARY_STAGE", 1);
-        for (int lvl = want < 2 ? want : 2; lvl >= 1; --lvl)
-            if (a.stage_off + lvl * tile <= 28 * 1024) { a.stage = lvl; break; }
-        smem = a.stage_off + a.stage * tile;
+        if (want >= 1 && unary_smem_bytes(max_patch, a.D) + 16 + tile <= kStageBudget) {
+            while (a.lb > 1 && ((unary_smem_bytes(max_patch * a.lb, a.D * a.lb) + 15) & ~(size_t)15) + tile > kStageBudget) --a.lb;
+            const size_t base = (unary_smem_bytes(max_patch * a.lb, a.D * a.lb) + 15) & ~(size_t)15;
+            a.stage = (want >= 2 && base + 2 * tile <= kStageBudget) ? 2 : 1;
+        }
     }
+    size_t smem = unary_smem_bytes(max_patch * a.lb, a.D * a.lb);
+    if (smem > 200 * 1024) return fail(MSMGPU_ERR_CAPACITY, "unary_table: patch too large for shared memory");
+    a.stage_off = (unsigned)((smem + 15) & ~(size_t)15);
+    if (a.stage) smem = a.stage_off + a.stage * (size_t)a.D * kCostThreads * sizeof(double);
     switch (query_group_width()) {
         case 1: return launch_unary_g<1>(a, smem, s);
         case 2: return launch_unary_g<2>(a, smem, s);

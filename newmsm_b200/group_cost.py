@@ -172,10 +172,11 @@ class DiscreteGroupModel:
         self._pairs_ref = pairs
         self.P = len(pairs)
 
-    def computePairwiseCostsForLabel(self, pairs, labeling, label: int, copy: bool = True):
+    def computePairwiseCostsForLabel(self, pairs, labeling, label: int, copy: bool = True, to_host: bool = True):
         """The 4 combinations per pair of Fusion::optimize (Fusion.h:164-174) -> [P, 4]; pairs block-sharded over the ranks.
         The pair list stays on the device between label phases, the block results are gathered on the device (NCCL) and come to the
-        host once, into a reused pinned buffer (copy=False returns a view of it, valid until the next call)."""
+        host once, into a reused pinned buffer (copy=False returns a view of it, valid until the next call). to_host=False: this rank
+        takes part in the computation and the gather but does not download the table (the host solver runs on one rank) -> None."""
         import torch
         pairs = i32(pairs).reshape(-1, 2)
         if getattr(self, "_pairs_key", None) != (pairs.ctypes.data, len(pairs)) or getattr(self, "_pairs_group", None) is not self.g:
@@ -191,6 +192,9 @@ class DiscreteGroupModel:
             check(self.L_.msmgpu_group_pair_batch_dev(self.g, b, e - b, ptr(lab), int(label), ptr(local)))
         self.ctx.sync()
         full = local if self.coll.world == 1 else self.coll.all_gather_blocks(local, P)
+        if not to_host:
+            torch.cuda.synchronize(dev)
+            return None
         if getattr(self, "_host_out", None) is None or self._host_out.shape[0] != P:
             self._host_out = torch.empty((P, 4), dtype=torch.float64, pin_memory=True)
         self._host_out.copy_(full)
@@ -224,7 +228,7 @@ class DiscreteGroupModel:
         self._plan_S, self._plan_T = f64(cps).shape[0], len(trip)
 
     def computeTripletCostsForLabel(self, cps, orig_cps, rotations, labels, triplets, labeling, label, lambda_, shearmodulus=0.4, bulkmodulus=1.6,
-                                    kexponent=2.0, exponent=2.0, fixnan=False, copy=True):
+                                    kexponent=2.0, exponent=2.0, fixnan=False, copy=True, to_host=True):
         """The 8 combinations per triplet of Fusion::optimize (Fusion.h:181-196) -> [T, 8]. cps=None: the arrays set by reset_triplet_state
         (copy=False then returns a view of the reused pinned buffer, valid until the next call)."""
         reg = capi.RegParams(lambda_, shearmodulus, bulkmodulus, kexponent, exponent, 3)
@@ -241,6 +245,9 @@ class DiscreteGroupModel:
             if e > b:
                 check(self.L_.msmgpu_triplet_plan_batch_dev(self._plan, C.byref(reg), 0.1 * S, int(fixnan), b, e - b, ptr(lab), int(label), ptr(local)))
             full = local if self.coll.world == 1 else self.coll.all_gather_blocks(local, T)
+            if not to_host:      # the solver's rank downloads, the others only compute and gather
+                torch.cuda.synchronize(dev)
+                return None
             if getattr(self, "_host_trip", None) is None or self._host_trip.shape[0] != T:
                 self._host_trip = torch.empty((T, 8), dtype=torch.float64, pin_memory=True)
             self._host_trip.copy_(full)
