@@ -1151,3 +1151,53 @@ def test_variance_normalise(R, oracle_built, masked):
     assert np.array_equal(R.variance_normalise(ctx, data[:, :1]), oracle_built.oracle_variance_normalise(data[:, :1]), equal_nan=True)
     big = np.random.default_rng(5).normal(size=(40, 40962))
     assert np.array_equal(R.variance_normalise(ctx, big), oracle_built.oracle_variance_normalise(big))
+
+
+def test_mesh_keeps_its_octree_until_the_coordinates_change(R, oracle_built, meshes):
+    """A mesh handed to a mesh-taking entry point (metric_resample, sphere_project_warp, nn interpolation) builds its octree once and
+    keeps it (csrc: msm::mesh_trees); msmgpu_mesh_set_coords must drop it. Repeated calls, a coordinate change in between, the same
+    mesh as source AND target, all against fresh meshes / the oracle."""
+    xyz, tri = meshes[4]
+    low, ltri = meshes[3]
+    low = synth.rotate_sphere(low)
+    feat = synth.smooth_fields(xyz, 3)
+    m, ml = R.Mesh(xyz, tri, feat), R.Mesh(low, ltri)
+    first = R.metric_resample(m, ml)
+    assert np.array_equal(first, oracle_built.oracle_metric_resample(xyz, tri, low, ltri, feat))
+    assert np.array_equal(R.metric_resample(m, ml), first)                                   # cached trees, same result
+    warped = synth.smooth_warp(xyz, max_disp=3.0, seed=5)
+    m.set_coords(warped)                                                                      # Mesh::set_coord for every vertex
+    moved = R.metric_resample(m, ml)
+    fresh = R.Mesh(warped, tri, feat)
+    fresh_tree_ids = R.Octree(fresh).get_closest_triangle(low)
+    # the triangle ids the kept-then-dropped tree answers with are those of a fresh tree over the new coordinates ...
+    assert np.array_equal(R.nearest_neighbour_interpolation(m, low), R.nearest_neighbour_interpolation(fresh, low))
+    assert np.array_equal(R.sphere_project_warp(low, m, xyz), R.sphere_project_warp(low, fresh, xyz))
+    assert np.array_equal(R.Octree(m).get_closest_triangle(low), fresh_tree_ids)
+    assert not np.array_equal(moved, first)
+    # ... and a mesh may be its own target (one tree serves both sides)
+    same = R.metric_resample(m, m)
+    assert same.shape == feat.shape and np.all(np.isfinite(same))
+
+
+def test_page_locked_host_buffers_are_plain_inputs(R, meshes):
+    """msmgpu_host_alloc: the adapter flattens Mesh::pvalues into such buffers; results do not depend on where the host bytes live."""
+    import ctypes as C
+    xyz, tri = meshes[4]
+    low, ltri = meshes[3]
+    feat = np.ascontiguousarray(synth.smooth_fields(xyz, 4))
+    m, ml = R.Mesh(xyz, tri), R.Mesh(synth.rotate_sphere(low), ltri)
+    L = capi.lib()
+    want = np.zeros((4, len(low)))
+    capi.check(L.msmgpu_metric_resample(m.h, ml.h, 4, capi.ptr(feat), capi.ptr(want)))
+    pin_in, pin_out = C.c_void_p(), C.c_void_p()
+    capi.check(L.msmgpu_host_alloc(m.ctx.h, feat.nbytes, C.byref(pin_in)))
+    capi.check(L.msmgpu_host_alloc(m.ctx.h, want.nbytes, C.byref(pin_out)))
+    try:
+        C.memmove(pin_in, feat.ctypes.data, feat.nbytes)
+        capi.check(L.msmgpu_metric_resample(m.h, ml.h, 4, pin_in, pin_out))
+        got = np.frombuffer((C.c_char * want.nbytes).from_address(pin_out.value), dtype=np.float64).reshape(want.shape).copy()
+    finally:
+        L.msmgpu_host_free(m.ctx.h, pin_in)
+        L.msmgpu_host_free(m.ctx.h, pin_out)
+    assert np.array_equal(got, want)
