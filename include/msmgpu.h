@@ -187,6 +187,19 @@ msmgpu_status msmgpu_bary_resample_f32(msmgpu_octree* t, int n, const double* pt
 /* the same two resamplers on the mesh's resident features: only the result crosses PCIe. feat_out channel-major [D][n] floats */
 msmgpu_status msmgpu_mesh_bary_resample_f32(msmgpu_octree* t, int n, const double* pts, float* feat_out);
 msmgpu_status msmgpu_mesh_metric_resample_f32(msmgpu_mesh* in_mesh, msmgpu_octree* in_tree, msmgpu_mesh* low_mesh, msmgpu_octree* low_tree, float* feat_out);
+/* replaces: the per-subject loop of a batch resampling job on HOST buffers (BASELINE configs[1]: S subjects with their own coordinates
+ * over one topology, resampled onto one target sphere with the barycentric method — Octree + get_barycentric_weights +
+ * resampler.cpp:40-52 — and / or metric_resample, resampler.cpp:304). One call, pipelined inside the library: chunk k+1 is uploaded
+ * while chunk k runs through the BATCHED kernels and chunk k-1 is downloaded, so the job runs at the rate of the host link.
+ *   xyz[s]      host [nv][3] doubles            tri        host [nt][3], shared by the subjects
+ *   feat_cm[s]  host [D][nv] floats (Mesh::pvalues layout)
+ *   out_bary_cm[s] / out_adaptive_cm[s]  host [D][n_low] floats; either array may be NULL to skip that method
+ *   chunk       subjects per pipeline stage (0: default 4, knob "batch_chunk")
+ * Page-locked host buffers (msmgpu_host_alloc or the caller's own) make the copies asynchronous; pageable ones work, serialised.
+ * Results are those of the per-subject calls (msmgpu_mesh_bary_resample_f32 / msmgpu_mesh_metric_resample_f32) bit for bit. */
+msmgpu_status msmgpu_resample_batch_host_f32(msmgpu_ctx* ctx, int n_subjects, int nv, const double* const* xyz, int nt, const int32_t* tri,
+                                             int n_low, const double* low_xyz, int n_low_tri, const int32_t* low_tri, int D,
+                                             const float* const* feat_cm, float* const* out_bary_cm, float* const* out_adaptive_cm, int chunk);
 /* host-buffer convenience (channel-major double in/out), used by the parity tests */
 msmgpu_status msmgpu_bary_resample(msmgpu_mesh* in_mesh, int n, const double* pts, int D, const double* feat_in, double* feat_out);
 

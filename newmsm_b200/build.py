@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libmsmgpu.so")
 OBJDIR = os.path.join(HERE, "build")
-SOURCES = ["api.cu", "octree_build.cu", "query.cu", "weights.cu", "cost.cu", "triplet.cu", "group.cu", "smooth.cu", "gather.cu", "order.cu", "rigid.cu", "hostpow.cu"]
+SOURCES = ["api.cu", "octree_build.cu", "query.cu", "weights.cu", "cost.cu", "triplet.cu", "group.cu", "smooth.cu", "gather.cu", "order.cu", "rigid.cu", "hostpow.cu", "batch.cu"]
 HEADERS = ["common.cuh", "geom.cuh", "query.cuh", "cost.cuh", "gather.cuh", "hostpow.cuh", os.path.join("..", "..", "include", "msmgpu.h")]
 
 

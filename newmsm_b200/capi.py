@@ -51,6 +51,7 @@ _SIGNATURES = {
     "msmgpu_ctx_stream": (_vp, [_vp]),
     "msmgpu_device_malloc": (_i, [_vp, C.c_size_t, _pp]),
     "msmgpu_host_alloc": (_i, [_vp, C.c_size_t, _pp]),
+    "msmgpu_resample_batch_host_f32": (_i, [_vp, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i]),
     "msmgpu_variance_normalise": (_i, [_vp, _i, _i, _vp, _vp]),
     "msmgpu_host_free": (None, [_vp, _vp]),
     "msmgpu_device_free": (None, [_vp, _vp]),

@@ -292,6 +292,25 @@ def smooth_data(orig: Mesh, sphLow: Mesh, sigma: float, nthreads: int = 1, EXCL=
     return out if excl is None else (out, eo)
 
 
+def resample_batch_host(ctx: "Context", xyz_list, tri, low_xyz, low_tri, feat_list, out_bary=None, out_adaptive=None, chunk: int = 0):
+    """Batch job on HOST buffers, pipelined inside the library (msmgpu_resample_batch_host_f32): subject s has coordinates xyz_list[s]
+    [nv][3] f64 over the shared topology `tri`, channel-major FP32 features feat_list[s] [D][nv]; the results land in out_bary[s] /
+    out_adaptive[s] [D][n_low] f32 (lists of numpy arrays or CPU torch tensors, ideally page-locked; either list may be None)."""
+    S = len(xyz_list)
+
+    def addr(a):
+        return a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data
+
+    def arr(lst):
+        return None if lst is None else (C.c_void_p * S)(*[addr(a) for a in lst])
+    t32, l32, low = i32(tri), i32(low_tri), f64(low_xyz)
+    nv = len(xyz_list[0]) if not hasattr(xyz_list[0], "data_ptr") else xyz_list[0].shape[0]
+    f0 = feat_list[0]
+    D = f0.shape[0]
+    check(capi.lib().msmgpu_resample_batch_host_f32(ctx.h, S, nv, arr(xyz_list), len(t32), ptr(t32), len(low), ptr(low), len(l32), ptr(l32), D,
+                                                    arr(feat_list), arr(out_bary), arr(out_adaptive), int(chunk)))
+
+
 def variance_normalise(ctx: "Context", DATA, EXCL=None):
     """newmeshreg::variance_normalise (reg_tools.cpp:804-844): [D, n] -> normalised copy; EXCL = mask values [n] or None."""
     data = f64(np.atleast_2d(DATA)).copy()
