@@ -335,6 +335,9 @@ __device__ __forceinline__ void classify_q(const uint4 qb, const int* L0, int Hh
 // ------------------------------------------------------------------------------------------
 constexpr int kStatInts = 10;   // sum_a, min_prefix, cnt[8]
 
+// node of slot li of the current level: levels made by the level passes are contiguous, the first level after the top phase is a list
+__device__ __forceinline__ int level_node(const int* __restrict__ node_map, int node_begin, int li) { return node_map ? __ldg(node_map + li) : node_begin + li; }
+
 template <int TPC>
 __device__ __forceinline__ int team_lane() { return TPC == 32 ? (threadIdx.x & 31) : threadIdx.x; }
 
@@ -394,7 +397,7 @@ __global__ void __launch_bounds__(TPC == 32 ? 256 : TPC) k_chunk_stats(int node_
                                                                         const TriRec* const* __restrict__ mesh_rec,
                                                                         const uint4* const* __restrict__ mesh_qbox, double root_half,
                                                                         int* __restrict__ stats, unsigned char* __restrict__ pmask, int level_base,
-                                                                        const int* __restrict__ live, int n_live) {
+                                                                        const int* __restrict__ live, int n_live, const int* __restrict__ node_map) {
     constexpr int K = TPC * IPT;
     constexpr int TEAMS = TPC == 32 ? 8 : 1;
     __shared__ int s_scan[TPC == 32 ? 1 : 33];
@@ -404,12 +407,13 @@ __global__ void __launch_bounds__(TPC == 32 ? 256 : TPC) k_chunk_stats(int node_
     const bool node_ok = slot < n_live;
     const int li = node_ok ? live[slot] : 0;    // only nodes that can still split (>= 50 triangles) get a team; the others are final leaves
     int4 nd = make_int4(0, 0, 0, 0);
-    if (node_ok) nd = nodes[node_begin + li];
+    const int gnode = node_ok ? level_node(node_map, node_begin, li) : 0;
+    if (node_ok) nd = nodes[gnode];
     const int cnt = nd.z;
     const bool busy = node_ok && cnt >= kMaxTriangles && chunk * K < cnt;   // octree.cpp:69: the test only runs from 50 triangles on
     if (TPC == 32) { if (!busy) return; }                                  // warp-uniform
     else if (!busy) return;                                                // CTA-uniform
-    const BuildNode b = bn[node_begin + li];
+    const BuildNode b = bn[gnode];
     const double half = ldexp(root_half, -b.depth);
     const TriRec* __restrict__ rec = mesh_rec[b.mesh];
     const uint4* __restrict__ qbox = mesh_qbox[b.mesh];
@@ -492,10 +496,11 @@ __global__ void __launch_bounds__(TPC == 32 ? 256 : TPC) k_chunk_stats(int node_
 
 // one thread per node of the level
 __global__ void k_node_combine(int node_begin, int n_level, int max_chunks, int K, const int4* __restrict__ nodes, int* __restrict__ stats,
-                               int* __restrict__ split_flag, int* __restrict__ child_cnt, int* __restrict__ max_child_cnt, int* __restrict__ n_live_next) {
+                               int* __restrict__ split_flag, int* __restrict__ child_cnt, int* __restrict__ max_child_cnt, int* __restrict__ n_live_next,
+                               const int* __restrict__ node_map) {
     const int li = blockIdx.x * blockDim.x + threadIdx.x;
     if (li >= n_level) return;
-    const int cnt = nodes[node_begin + li].z;
+    const int cnt = nodes[level_node(node_map, node_begin, li)].z;
     int tot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int split = 0;
     if (cnt >= kMaxTriangles) {
@@ -528,11 +533,11 @@ __global__ void k_make_children(int node_begin, int n_level, int4* __restrict__ 
                                 const int* __restrict__ split_flag, const int* __restrict__ split_rank,
                                 const int* __restrict__ child_cnt, const int* __restrict__ child_off,
                                 int next_node_begin, int next_pair_base, double root_half, int node_cap,
-                                int* __restrict__ live_next, int* __restrict__ live_cursor) {
+                                int* __restrict__ live_next, int* __restrict__ live_cursor, const int* __restrict__ node_map) {
     const int li = blockIdx.x * blockDim.x + threadIdx.x;
     if (li >= n_level) return;
     if (!split_flag[li]) return;
-    const int g = node_begin + li;
+    const int g = level_node(node_map, node_begin, li);
     const int first = next_node_begin + 8 * split_rank[li];
     if (first + 8 > node_cap) return;   // capacity checked on the host from the scan totals
     const BuildNode b = bn[g];
@@ -623,10 +628,11 @@ __global__ void __launch_bounds__(TPC == 32 ? 256 : TPC) k_scatter_chunk(int nod
 }
 
 
-__global__ void k_save_lists(int node_begin, int n_level, const int4* __restrict__ nodes, int* __restrict__ list_start, int* __restrict__ list_count) {
+__global__ void k_save_lists(int node_begin, int n_level, const int4* __restrict__ nodes, int* __restrict__ list_start, int* __restrict__ list_count,
+                             const int* __restrict__ node_map) {
     const int li = blockIdx.x * blockDim.x + threadIdx.x;
     if (li >= n_level) return;
-    const int4 nd = nodes[node_begin + li];
+    const int4 nd = nodes[level_node(node_map, node_begin, li)];
     list_start[li] = nd.y;
     list_count[li] = nd.z;
 }
@@ -647,6 +653,393 @@ __global__ void k_init_roots(int n, int4* nodes, BuildNode* bn, unsigned char* n
         bn[r] = b;
         node_depth[r] = 0;
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// Top phase: the first D0 levels of a dense mesh in ONE pass over its triangles instead of D0 level passes.
+//
+// A node splits when it holds n >= 50 triangles and total_size < 3 n (octree.cpp:69-102, evaluated at every insertion from the
+// 50th on). Let m_t be the number of the node's 8 child cubes that triangle t TOUCHES (closed boxes, can_contain). Per axis a
+// triangle that does not straddle the midpoint touches one half -- or both when its lower corner lies exactly on the midpoint --
+// so m_t >= split_size_t and  sum over the children of their triangle counts = sum_t m_t >= total_size.  Hence
+//        count(node) >= 50  and  sum_c count(child c) < 3 count(node)
+// is SUFFICIENT for the split (the whole list is one of the prefixes the reference tests), and it needs no order and nothing but
+// the number of triangles touching each cell of the 8^d lattices of the root cube, d <= D0:
+//   k_top_count     every triangle adds 1 to the cells it touches at every depth (32-bit reds; depths 1..3 through block-local
+//                   shared-memory counters, which every block hits)
+//   k_top_decide    per dense cell: the sufficient condition -> top bit of its counter
+//   k_top_children  depth by depth over the dense cells: a decided cell gets its 8 children (node records, boxes, list space
+//                   from one atomic cursor per warp)
+//   k_top_fill      every triangle appends its id to the list of each touched cell that exists and was not split
+//   k_top_sort_*    the lists are put in ascending id order = the order the reference's sequential insertion produces
+// A cell with count >= 50 that fails the sufficient test is simply not decided here: it keeps its list and goes, like the depth-D0
+// cells, on the work list of the exact level passes below, which evaluate the prefix rule. Decisions are therefore the reference's
+// in every case; only the node numbering differs (atomic cursors), which no result depends on. D0 is chosen per mesh from its
+// triangle count (cells of depth D0-1 hold >= 64 triangles on average on a sphere); knob "build_top" (MSMGPU_BUILD_TOP): -1 auto,
+// 0 off, k force D0 = k.
+// ------------------------------------------------------------------------------------------
+constexpr int kTopMaxDepth = 6;
+constexpr int kTopTrisPerBlock = 1024;   // k_top_count: 256 threads x 4 triangles
+constexpr int kTopNone = -0x40000000;    // nid entries at or below this: the cell has no node
+__host__ __device__ __forceinline__ long long top_cells_before(int d) { return ((1ll << (3 * d)) - 1) / 7; }   // cells of depths < d
+
+struct TopJob { const uint4* qbox; int nt; int d0; };
+
+__device__ __forceinline__ unsigned top_spread(unsigned v) {
+    return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6) | ((v & 16u) << 8) | ((v & 32u) << 10);
+}
+__device__ __forceinline__ unsigned top_cell(int ix, int iy, int iz) {   // child digit per level = 4 x + 2 y + z (classify's numbering)
+    return (top_spread((unsigned)ix) << 2) | (top_spread((unsigned)iy) << 1) | top_spread((unsigned)iz);
+}
+struct TopBox { int qlo[3], qhi[3]; bool elo[3]; };
+__device__ __forceinline__ TopBox top_unpack(const uint4 qb) {
+    TopBox b;
+    const unsigned w[3] = {qb.x, qb.y, qb.z};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const unsigned l20 = w[d] & 0xfffffu;
+        b.qlo[d] = (int)(l20 >> 1) - 1;
+        b.elo[d] = l20 & 1u;
+        b.qhi[d] = (int)((w[d] >> 20) | (((qb.w >> (7 * d)) & 0x7fu) << 12)) - 1;
+    }
+    return b;
+}
+// cells [lo, hi] of depth d whose closed interval the triangle's [tlo, thi] touches on one axis (node.cpp:112-120 on the lattice)
+__device__ __forceinline__ void top_range(const TopBox& b, int axis, int d, int& lo, int& hi) {
+    const int sh = kGridBits - d;
+    hi = min(b.qhi[axis] >> sh, (1 << d) - 1);
+    const int q = b.qlo[axis];
+    if (q < 0) lo = 0;
+    else {
+        int k = q >> sh;
+        if (b.elo[axis] && (q & ((1 << sh) - 1)) == 0) --k;   // the lower corner lies exactly on the line: the cell below touches it too
+        lo = max(k, 0);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_top_count(const TopJob* __restrict__ jobs, unsigned* __restrict__ cnt, long long cells_per_mesh) {
+    __shared__ unsigned s_cnt[8 + 64 + 512];   // depths 1..3
+    const TopJob job = jobs[blockIdx.y];
+    const int t0 = blockIdx.x * kTopTrisPerBlock;
+    if (t0 >= job.nt || job.d0 <= 0) return;
+    for (int i = threadIdx.x; i < 8 + 64 + 512; i += blockDim.x) s_cnt[i] = 0u;
+    __syncthreads();
+    unsigned* g = cnt + (size_t)blockIdx.y * cells_per_mesh;
+    for (int t = t0 + threadIdx.x; t < min(t0 + kTopTrisPerBlock, job.nt); t += blockDim.x) {
+        const TopBox b = top_unpack(__ldg(job.qbox + t));
+        for (int d = 1; d <= job.d0; ++d) {
+            int lo[3], hi[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) top_range(b, a, d, lo[a], hi[a]);
+            for (int ix = lo[0]; ix <= hi[0]; ++ix)
+                for (int iy = lo[1]; iy <= hi[1]; ++iy)
+                    for (int iz = lo[2]; iz <= hi[2]; ++iz) {
+                        const unsigned cell = top_cell(ix, iy, iz);
+                        if (d <= 3) atomicAdd(&s_cnt[top_cells_before(d) - 1 + cell], 1u);
+                        else atomicAdd(g + top_cells_before(d) + cell, 1u);
+                    }
+        }
+    }
+    __syncthreads();
+    const int n_sm = (int)top_cells_before(min(job.d0, 3) + 1) - 1;
+    for (int i = threadIdx.x; i < n_sm; i += blockDim.x)
+        if (s_cnt[i]) atomicAdd(g + 1 + i, s_cnt[i]);
+}
+
+// the sufficient condition, for every dense cell of the depths below the mesh's D0 -> top bit of the counter
+__global__ void k_top_decide(int n, int dmax, const TopJob* __restrict__ jobs, unsigned* __restrict__ cnt, long long cells_per_mesh) {
+    const long long per = top_cells_before(dmax);   // cells of depths 0 .. dmax-1
+    const long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= per * n) return;
+    const int m = (int)(gi / per);
+    const long long c = gi % per;
+    int d = 0;
+    while (top_cells_before(d + 1) <= c) ++d;
+    const TopJob job = jobs[m];
+    if (d >= job.d0) return;
+    unsigned* g = cnt + (size_t)m * cells_per_mesh;
+    const unsigned cell = (unsigned)(c - top_cells_before(d));
+    const unsigned own = d == 0 ? (unsigned)job.nt : g[c];   // the root receives every triangle (octree.cpp:42-61)
+    if (d == 0) g[0] = own;
+    if (own < (unsigned)kMaxTriangles) return;
+    const unsigned* ch = g + top_cells_before(d + 1) + ((size_t)cell << 3);
+    unsigned long long sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sum += ch[k] & 0x7fffffffu;   // (a child's own flag may already be set)
+    if (sum < 3ull * own) g[c] = own | 0x80000000u;
+}
+
+struct TopCursors { unsigned long long pairs; int nodes, live, max_live_cnt, max_list, overflow, pad; };
+
+// nid entry of a dense cell: <= kTopNone = no node; -2 - id = node id, split by the top phase; >= 0: a node that keeps its list --
+// its id at the depths below the mesh's D0 (write cursor in `fillc`), and at depth D0 directly the write cursor of its list
+__device__ __forceinline__ int top_nid_split(int id) { return -2 - id; }
+
+// one atomic per warp on a cursor every lane advances: returns this lane's start
+__device__ __forceinline__ int warp_reserve(int* cursor, int want) {
+    const int lane = threadIdx.x & 31;
+    int inc = want;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, inc, 31);
+    int base = 0;
+    if (lane == 31 && total > 0) base = atomicAdd(cursor, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    return base + inc - want;
+}
+__device__ __forceinline__ unsigned long long warp_reserve64(unsigned long long* cursor, int want) {
+    const int lane = threadIdx.x & 31;
+    int inc = want;   // a warp's lists stay far below 2^31 entries
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, inc, 31);
+    unsigned long long base = 0;
+    if (lane == 31 && total > 0) base = atomicAdd(cursor, (unsigned long long)total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    return base + (unsigned long long)(inc - want);
+}
+
+// roots: node m = root of mesh m
+__global__ void k_top_roots(int n, const TopJob* __restrict__ jobs, const unsigned* __restrict__ cnt, long long cells_per_mesh,
+                            int* __restrict__ nid, int4* __restrict__ nodes, BuildNode* __restrict__ bn, unsigned char* __restrict__ node_depth,
+                            TopCursors* __restrict__ cur, int* __restrict__ live, int live_cap) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    const TopJob job = jobs[m];
+    BuildNode b;
+    b.lo[0] = b.lo[1] = b.lo[2] = -kBounds;
+    b.mesh = m;
+    b.depth = 0;
+    bn[m] = b;
+    node_depth[m] = 0;
+    if (job.d0 > 0 && (cnt[(size_t)m * cells_per_mesh] >> 31)) {
+        nid[(size_t)m * cells_per_mesh] = top_nid_split(m);
+        nodes[m] = make_int4(-1, 0, 0, -1);
+        return;
+    }
+    nid[(size_t)m * cells_per_mesh] = kTopNone;   // the root keeps the identity list (k_top_root_lists); nothing is appended to it
+    const int off = (int)atomicAdd(&cur->pairs, (unsigned long long)job.nt);
+    nodes[m] = make_int4(-1, off, job.nt, -1);
+    if (job.nt >= kMaxTriangles) {
+        const int o = atomicAdd(&cur->live, 1);
+        if (o < live_cap) live[o] = m; else cur->overflow = 1;
+        atomicMax(&cur->max_live_cnt, job.nt);
+    }
+}
+__global__ void k_top_root_lists(const int* __restrict__ nid, long long cells_per_mesh, const int4* __restrict__ nodes, int* __restrict__ pairs) {
+    if (nid[(size_t)blockIdx.y * cells_per_mesh] > kTopNone) return;   // the root was split
+    const int4 nd = nodes[blockIdx.y];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nd.z; i += gridDim.x * blockDim.x) pairs[nd.y + i] = i;
+}
+
+// one thread per dense cell of depth d: the 8 children of every cell the top phase splits
+__global__ void __launch_bounds__(256) k_top_children(int n, int d, const TopJob* __restrict__ jobs, const unsigned* __restrict__ cnt,
+                                                      long long cells_per_mesh, int* __restrict__ nid, int* __restrict__ fillc, long long fillc_per_mesh,
+                                                      int4* __restrict__ nodes, BuildNode* __restrict__ bn, unsigned char* __restrict__ node_depth,
+                                                      TopCursors* __restrict__ cur, int* __restrict__ live, int live_cap, int node_cap, double root_half) {
+    const long long per = 1ll << (3 * d);
+    const long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in_range = gi < per * n;
+    const int m = in_range ? (int)(gi / per) : 0;
+    const unsigned cell = in_range ? (unsigned)(gi % per) : 0u;
+    const size_t mb = (size_t)m * cells_per_mesh;
+    const int code = in_range ? nid[mb + top_cells_before(d) + cell] : kTopNone;
+    const bool split = code <= -2 && code > kTopNone;
+    const int id = split ? -2 - code : -1;
+    const int d0 = split ? jobs[m].d0 : 0;
+    const size_t cb = mb + top_cells_before(d + 1) + ((size_t)cell << 3);
+    unsigned v[8];
+    int list_total = 0, n_live = 0, max_list = 0;
+    if (split) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            v[c] = cnt[cb + c];
+            if (v[c] >> 31) continue;   // split in its turn (only below D0 - 1: k_top_decide)
+            const int k = (int)v[c];
+            list_total += k;
+            n_live += k >= kMaxTriangles;
+            max_list = max(max_list, k);
+        }
+    }
+    // per-warp reservations: node records, list space, work-list slots
+    const int first = warp_reserve(&cur->nodes, split ? 8 : 0);
+    unsigned long long off = warp_reserve64(&cur->pairs, list_total);
+    int lslot = warp_reserve(&cur->live, n_live);
+    const int wmax = __reduce_max_sync(0xffffffffu, max_list);
+    if ((threadIdx.x & 31) == 0 && wmax > 1) {
+        atomicMax(&cur->max_list, wmax);
+        if (wmax >= kMaxTriangles) atomicMax(&cur->max_live_cnt, wmax);
+    }
+    if (!split) return;
+    if (first + 8 > node_cap || off + (unsigned long long)list_total > 0x7fffffffull) { cur->overflow = 1; return; }
+    const int parent = nodes[id].w;
+    nodes[id] = make_int4(first, 0, 0, parent);
+    const BuildNode b = bn[id];
+    const double half = ldexp(root_half, -d);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        BuildNode ch;
+        ch.lo[0] = b.lo[0] + ((c & 4) ? half : 0.0);   // node.cpp:99-106
+        ch.lo[1] = b.lo[1] + ((c & 2) ? half : 0.0);
+        ch.lo[2] = b.lo[2] + ((c & 1) ? half : 0.0);
+        ch.mesh = m;
+        ch.depth = d + 1;
+        bn[first + c] = ch;
+        node_depth[first + c] = (unsigned char)(d + 1);
+        if (v[c] >> 31) {
+            nid[cb + c] = top_nid_split(first + c);
+            nodes[first + c] = make_int4(-1, 0, 0, id);
+            continue;
+        }
+        const int k = (int)v[c];
+        nodes[first + c] = make_int4(-1, (int)off, k, id);
+        if (d + 1 == d0) nid[cb + c] = (int)off;   // depth D0: the entry is the list's write cursor
+        else {
+            nid[cb + c] = first + c;
+            fillc[(size_t)m * fillc_per_mesh + top_cells_before(d + 1) + ((size_t)cell << 3) + c] = (int)off;
+        }
+        off += (unsigned long long)k;
+        if (k >= kMaxTriangles) {
+            if (lslot < live_cap) live[lslot] = first + c; else cur->overflow = 1;
+            ++lslot;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_top_fill(const TopJob* __restrict__ jobs, int* __restrict__ nid, long long cells_per_mesh,
+                                                  int* __restrict__ fillc, long long fillc_per_mesh, int* __restrict__ pairs) {
+    const TopJob job = jobs[blockIdx.y];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= job.nt || job.d0 <= 0) return;
+    int* __restrict__ ids = nid + (size_t)blockIdx.y * cells_per_mesh;
+    const TopBox b = top_unpack(__ldg(job.qbox + t));
+    // the common case first: every touched cell of depth D0 exists (all its ancestors were split); its nid entry is the write cursor
+    bool missing = false;
+    {
+        int lo[3], hi[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) top_range(b, a, job.d0, lo[a], hi[a]);
+        for (int ix = lo[0]; ix <= hi[0]; ++ix)
+            for (int iy = lo[1]; iy <= hi[1]; ++iy)
+                for (int iz = lo[2]; iz <= hi[2]; ++iz) {
+                    const int pos = atomicAdd(ids + top_cells_before(job.d0) + top_cell(ix, iy, iz), 1);
+                    if (pos >= 0) pairs[pos] = t;
+                    else missing = true;   // (the entry of a cell without node stays far below zero)
+                }
+    }
+    if (!missing) return;
+    int* __restrict__ fc = fillc + (size_t)blockIdx.y * fillc_per_mesh;
+    for (int d = 1; d < job.d0; ++d) {   // some ancestor was not split: the list-keeping cells above
+        int lo[3], hi[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) top_range(b, a, d, lo[a], hi[a]);
+        bool any = false;
+        for (int ix = lo[0]; ix <= hi[0]; ++ix)
+            for (int iy = lo[1]; iy <= hi[1]; ++iy)
+                for (int iz = lo[2]; iz <= hi[2]; ++iz) {
+                    const long long ci = top_cells_before(d) + top_cell(ix, iy, iz);
+                    const int id = ids[ci];
+                    if (id <= kTopNone) continue;
+                    any = true;
+                    if (id >= 0) pairs[atomicAdd(fc + ci, 1)] = t;
+                }
+        if (!any) break;   // none of the touched cells exists: their descendants do not exist either
+    }
+}
+
+// ascending id order inside every list the top phase filled = the order the reference's sequential insertion produces.
+// One warp per node, bitonic network on E registers per lane (element e = r * 32 + lane): exchanges at distance >= 32 stay inside the
+// lane, shorter ones are one shuffle.
+template <int E>
+__device__ __forceinline__ void warp_bitonic(int (&v)[E]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 2; k <= 32 * E; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+                const int rj = j >> 5;
+#pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    if (r & rj) continue;
+                    const bool asc = (((r << 5) | lane) & k) == 0;
+                    const int x = v[r], y = v[r | rj];
+                    if ((x > y) == asc) { v[r] = y; v[r | rj] = x; }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    const int o = __shfl_xor_sync(0xffffffffu, v[r], j);
+                    const bool asc = (((r << 5) | lane) & k) == 0;
+                    const bool lower = (lane & j) == 0;
+                    v[r] = (lower == asc) ? min(v[r], o) : max(v[r], o);
+                }
+            }
+        }
+    }
+}
+template <int E>
+__device__ __forceinline__ void warp_sort_list(int* __restrict__ list, int cnt) {
+    const int lane = threadIdx.x & 31;
+    int v[E];
+#pragma unroll
+    for (int r = 0; r < E; ++r) { const int e = (r << 5) | lane; v[r] = e < cnt ? list[e] : INT_MAX; }
+    warp_bitonic<E>(v);
+#pragma unroll
+    for (int r = 0; r < E; ++r) { const int e = (r << 5) | lane; if (e < cnt) list[e] = v[r]; }
+}
+__global__ void __launch_bounds__(256) k_top_sort_warp(int first_node, int n_nodes, const int4* __restrict__ nodes, int* __restrict__ pairs) {
+    const int id = first_node + blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (id >= n_nodes) return;
+    const int4 nd = nodes[id];
+    if (nd.x != -1 || nd.z <= 1 || nd.z > 256) return;
+    int* list = pairs + nd.y;
+    if (nd.z <= 32) warp_sort_list<1>(list, nd.z);
+    else if (nd.z <= 64) warp_sort_list<2>(list, nd.z);
+    else if (nd.z <= 128) warp_sort_list<4>(list, nd.z);
+    else warp_sort_list<8>(list, nd.z);
+}
+constexpr int kTopSortCap = 4096;
+__global__ void __launch_bounds__(256) k_top_sort_block(int first_node, int n_nodes, const int4* __restrict__ nodes, int* __restrict__ pairs) {
+    __shared__ int buf[kTopSortCap];
+    const int id = first_node + blockIdx.x;
+    if (id >= n_nodes) return;
+    const int4 nd = nodes[id];
+    if (nd.x != -1 || nd.z <= 256 || nd.z > kTopSortCap) return;
+    int N = 512;
+    while (N < nd.z) N <<= 1;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) buf[i] = i < nd.z ? pairs[nd.y + i] : INT_MAX;
+    __syncthreads();
+    for (int k = 2; k <= N; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < N; i += blockDim.x) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const int x = buf[i], y = buf[p];
+                    if (((i & k) == 0) == (x > y)) { buf[i] = y; buf[p] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = threadIdx.x; i < nd.z; i += blockDim.x) pairs[nd.y + i] = buf[i];
+}
+__global__ void k_iota(int n, int* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = i;
+}
+
+static int top_depth_for(int nt, int knob) {
+    if (knob == 0) return 0;
+    if (knob > 0) return std::min(knob, kTopMaxDepth);
+    int d0 = 0;
+    while (d0 < kTopMaxDepth && (1ll << (2 * d0)) * 245 <= nt) ++d0;   // 4^(D0-1) <= nt / 245: cells of depth D0-1 hold >= 64 triangles on a sphere
+    return d0;
 }
 
 msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, std::shared_ptr<Forest>& out, std::vector<int>& roots) {
@@ -673,7 +1066,8 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
     long long node_cap = total_t + 4096ll * n;
     const double root_half = kBounds;   // half width of the root cube
 
-    for (int attempt = 0; attempt < 4; ++attempt) {
+    bool top_disabled = false;
+    for (int attempt = 0; attempt < 5; ++attempt) {
         if (pair_cap > 0x7fffffffll || node_cap > 0x7fffffffll) return fail(MSMGPU_ERR_CAPACITY, "forest_build: batch too large for 32-bit offsets");
         auto F = std::make_shared<Forest>();
         F->ctx = ctx;
@@ -698,13 +1092,6 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
         MSM_CUDA(cudaMemcpyAsync(d_rec.p, h_rec.data(), n * sizeof(TriRec*), cudaMemcpyHostToDevice, s));
         MSM_CUDA(cudaMemcpyAsync(d_nt.p, h_nt.data(), n * sizeof(int), cudaMemcpyHostToDevice, s));
         MSM_CUDA(cudaMemcpyAsync(d_off.p, h_off.data(), n * sizeof(int), cudaMemcpyHostToDevice, s));
-        {
-            int max_nt = 1;
-            for (int v : h_nt) max_nt = v > max_nt ? v : max_nt;
-            dim3 grid((unsigned)std::min((max_nt + 255) / 256, 1024), (unsigned)n);
-            k_init_roots<<<grid, 256, 0, s>>>(n, F->nodes.p, bn.p, F->node_depth.p, F->pairs.p, d_off.p, d_nt.p);
-            MSM_LAUNCH_CHECK();
-        }
         int node_begin = 0, n_level = n;
         int n_nodes = n;
         long long n_pairs = total_t;
@@ -713,14 +1100,107 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
         DevBuf<int> split_flag, split_rank, child_cnt, child_off, list_start, list_count, totals, stats, live, live_next;
         MSM_CUDA(totals.alloc(5, s));   // [0] splits, [1] new list entries, [2] longest child list, [3] live children, [4] live-list cursor
         int n_live = n;                 // every root is a candidate
-        MSM_CUDA(live.alloc(n, s));
+        int level_max_cnt = 1;
+        for (int v : h_nt) level_max_cnt = std::max(level_max_cnt, v);
+        int max_nt = 1;
+        for (int v : h_nt) max_nt = v > max_nt ? v : max_nt;
+        // ---- top phase (see the note above k_top_count): the first levels of the dense meshes without level passes ----
+        std::vector<TopJob> top_jobs(n);
+        int top_dmax = 0;
         {
+            const int knob = top_disabled ? 0 : tuning_get("build_top", "MSMGPU_BUILD_TOP", -1);
+            for (int i = 0; i < n; ++i) {
+                top_jobs[i] = TopJob{h_qbox[i], h_nt[i], top_depth_for(h_nt[i], knob)};
+                top_dmax = std::max(top_dmax, top_jobs[i].d0);
+            }
+        }
+        bool top_done = false;
+        DevBuf<int> top_nodes;          // nodes of the first level after the top phase (node_map of the level kernels)
+        const int* node_map = nullptr;
+        if (top_dmax > 0) {
+            const long long cells_per_mesh = top_cells_before(top_dmax + 1);
+            const long long fillc_per_mesh = top_cells_before(top_dmax);       // write cursors of list-keeping cells above their mesh's D0
+            const size_t n_cells = (size_t)n * (size_t)cells_per_mesh;
+            const int live_cap = (int)std::min<long long>(pair_cap / kMaxTriangles + n, 0x3fffffffll);
+            if (node_cap >= -(long long)kTopNone - 2) return fail(MSMGPU_ERR_CAPACITY, "forest_build: batch too large for the top phase's node codes");
+            DevBuf<TopJob> d_jobs;
+            DevBuf<unsigned> cnt;
+            DevBuf<int> nid, fillc;
+            DevBuf<TopCursors> cur;
+            MSM_CUDA(d_jobs.alloc(n, s));
+            MSM_CUDA(cudaMemcpyAsync(d_jobs.p, top_jobs.data(), n * sizeof(TopJob), cudaMemcpyHostToDevice, s));   // pageable: staged before return
+            MSM_CUDA(cnt.alloc(n_cells, s));
+            MSM_CUDA(nid.alloc(n_cells, s));
+            MSM_CUDA(fillc.alloc((size_t)n * (size_t)fillc_per_mesh, s));
+            MSM_CUDA(cur.alloc(1, s));
+            MSM_CUDA(top_nodes.alloc((size_t)live_cap, s));
+            MSM_CUDA(cudaMemsetAsync(cnt.p, 0, n_cells * sizeof(unsigned), s));
+            MSM_CUDA(cudaMemsetAsync(nid.p, 0x80, n_cells * sizeof(int), s));   // 0x80808080 < kTopNone, and stays there under k_top_fill's increments
+            TopCursors h_cur{};
+            h_cur.nodes = n;   // the roots are nodes 0 .. n-1
+            MSM_CUDA(cudaMemcpyAsync(cur.p, &h_cur, sizeof(TopCursors), cudaMemcpyHostToDevice, s));
+            k_top_count<<<dim3((unsigned)((max_nt + kTopTrisPerBlock - 1) / kTopTrisPerBlock), (unsigned)n), 256, 0, s>>>(d_jobs.p, cnt.p, cells_per_mesh);
+            MSM_LAUNCH_CHECK();
+            {
+                const long long threads = (long long)n * top_cells_before(top_dmax);
+                k_top_decide<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(n, top_dmax, d_jobs.p, cnt.p, cells_per_mesh);
+                MSM_LAUNCH_CHECK();
+            }
+            k_top_roots<<<(n + 127) / 128, 128, 0, s>>>(n, d_jobs.p, cnt.p, cells_per_mesh, nid.p, F->nodes.p, bn.p, F->node_depth.p, cur.p, top_nodes.p, live_cap);
+            MSM_LAUNCH_CHECK();
+            for (int d = 0; d < top_dmax; ++d) {
+                const long long threads = (long long)n << (3 * d);
+                k_top_children<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(n, d, d_jobs.p, cnt.p, cells_per_mesh, nid.p, fillc.p, fillc_per_mesh, F->nodes.p,
+                                                                                 bn.p, F->node_depth.p, cur.p, top_nodes.p, live_cap, (int)node_cap, root_half);
+                MSM_LAUNCH_CHECK();
+            }
+            TopCursors* h_res = reinterpret_cast<TopCursors*>(ctx->pinned ? (void*)ctx->pinned : (void*)&h_cur);
+            MSM_CUDA(cudaMemcpyAsync(h_res, cur.p, sizeof(TopCursors), cudaMemcpyDeviceToHost, s));
+            MSM_CUDA(cudaStreamSynchronize(s));
+            const TopCursors r = *h_res;
+            if (r.overflow || (long long)r.pairs > pair_cap || r.nodes > node_cap || r.live > live_cap) { pair_cap *= 2; node_cap *= 2; continue; }
+            if (r.max_list > kTopSortCap) { top_disabled = true; continue; }   // a list longer than the sort kernels take: exact level passes from the root
+            // roots that keep their list (meshes too small to split, D0 = 0, or undecided): the identity, octree.cpp:42-61
+            k_top_root_lists<<<dim3((unsigned)std::min((max_nt + 255) / 256, 64), (unsigned)n), 256, 0, s>>>(nid.p, cells_per_mesh, F->nodes.p, F->pairs.p);
+            MSM_LAUNCH_CHECK();
+            k_top_fill<<<dim3((unsigned)((max_nt + 255) / 256), (unsigned)n), 256, 0, s>>>(d_jobs.p, nid.p, cells_per_mesh, fillc.p, fillc_per_mesh, F->pairs.p);
+            MSM_LAUNCH_CHECK();
+            if (r.nodes > n) {
+                k_top_sort_warp<<<(unsigned)((r.nodes - n + 7) / 8), 256, 0, s>>>(n, r.nodes, F->nodes.p, F->pairs.p);
+                MSM_LAUNCH_CHECK();
+                if (r.max_list > 256) {
+                    k_top_sort_block<<<(unsigned)(r.nodes - n), 256, 0, s>>>(n, r.nodes, F->nodes.p, F->pairs.p);
+                    MSM_LAUNCH_CHECK();
+                }
+            }
+            // the exact level passes continue on ONE level made of the nodes that still hold >= 50 triangles (depth-D0 cells and
+            // undecided ones, whatever their depth: BuildNode carries it), addressed through node_map
+            node_map = top_nodes.p;
+            node_begin = 0;
+            n_level = r.live;
+            n_nodes = r.nodes;
+            n_pairs = (long long)r.pairs;
+            level_entries = n_pairs;
+            level_base = 0;
+            n_live = r.live;
+            level_max_cnt = std::max(1, r.max_live_cnt);
+            depth = top_dmax;
+            MSM_CUDA(live.alloc((size_t)std::max(n_live, 1), s));
+            if (n_live > 0) {
+                k_iota<<<(n_live + 255) / 256, 256, 0, s>>>(n_live, live.p);
+                MSM_LAUNCH_CHECK();
+            }
+            top_done = true;
+        }
+        if (!top_done) {
+            dim3 grid((unsigned)std::min((max_nt + 255) / 256, 1024), (unsigned)n);
+            k_init_roots<<<grid, 256, 0, s>>>(n, F->nodes.p, bn.p, F->node_depth.p, F->pairs.p, d_off.p, d_nt.p);
+            MSM_LAUNCH_CHECK();
+            MSM_CUDA(live.alloc(n, s));
             std::vector<int> ident(n);
             for (int i = 0; i < n; ++i) ident[i] = i;
             MSM_CUDA(cudaMemcpyAsync(live.p, ident.data(), n * sizeof(int), cudaMemcpyHostToDevice, s));   // pageable: staged before return
         }
-        int level_max_cnt = 1;
-        for (int v : h_nt) level_max_cnt = std::max(level_max_cnt, v);
         static const bool timing = getenv("MSMGPU_BUILD_TIMING") != nullptr;
         auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         double t_enq = 0, t_wait = 0, t_alloc = 0;
@@ -750,16 +1230,16 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
             mark();
             if (n_live == 0) {}   // nothing can split: k_node_combine clears the flags and the loop ends
             else if (K == 8192)
-                k_chunk_stats<1024, 8><<<g_cta, 1024, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_rec.p, d_qbox.p, root_half, stats.p, pmask.p, level_base, live.p, n_live);
+                k_chunk_stats<1024, 8><<<g_cta, 1024, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_rec.p, d_qbox.p, root_half, stats.p, pmask.p, level_base, live.p, n_live, node_map);
             else if (K == 1024)
-                k_chunk_stats<256, 4><<<g_cta, 256, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_rec.p, d_qbox.p, root_half, stats.p, pmask.p, level_base, live.p, n_live);
+                k_chunk_stats<256, 4><<<g_cta, 256, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_rec.p, d_qbox.p, root_half, stats.p, pmask.p, level_base, live.p, n_live, node_map);
             else
-                k_chunk_stats<32, 4><<<g_warp, 256, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_rec.p, d_qbox.p, root_half, stats.p, pmask.p, level_base, live.p, n_live);
+                k_chunk_stats<32, 4><<<g_warp, 256, 0, s>>>(node_begin, n_level, max_chunks, F->nodes.p, bn.p, F->pairs.p, d_rec.p, d_qbox.p, root_half, stats.p, pmask.p, level_base, live.p, n_live, node_map);
             MSM_LAUNCH_CHECK();
             mark();
             MSM_CUDA(cudaMemsetAsync(totals.p + 2, 0, 3 * sizeof(int), s));
             k_node_combine<<<(n_level + 255) / 256, 256, 0, s>>>(node_begin, n_level, max_chunks, K, F->nodes.p, stats.p, split_flag.p, child_cnt.p,
-                                                                 totals.p + 2, totals.p + 3);
+                                                                 totals.p + 2, totals.p + 3, node_map);
             MSM_LAUNCH_CHECK();
             MSM_TRY(exclusive_scan_i32(split_flag.p, split_rank.p, n_level, totals.p, s));
             MSM_TRY(exclusive_scan_i32(child_cnt.p, child_off.p, n_level * 8, totals.p + 1, s));
@@ -774,12 +1254,12 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
             const int new_pairs = h_tot[1];
             if (n_split == 0) break;
             if ((long long)n_nodes + 8ll * n_split > node_cap || n_pairs + new_pairs > pair_cap) { overflow = true; break; }
-            k_save_lists<<<(n_level + 255) / 256, 256, 0, s>>>(node_begin, n_level, F->nodes.p, list_start.p, list_count.p);
+            k_save_lists<<<(n_level + 255) / 256, 256, 0, s>>>(node_begin, n_level, F->nodes.p, list_start.p, list_count.p, node_map);
             MSM_LAUNCH_CHECK();
             MSM_CUDA(live_next.alloc((size_t)std::max(h_tot[3], 1), s));
             k_make_children<<<(n_level + 255) / 256, 256, 0, s>>>(node_begin, n_level, F->nodes.p, bn.p, F->node_depth.p, split_flag.p,
                                                                  split_rank.p, child_cnt.p, child_off.p, n_nodes, (int)n_pairs, root_half,
-                                                                 (int)node_cap, live_next.p, totals.p + 4);
+                                                                 (int)node_cap, live_next.p, totals.p + 4, node_map);
             MSM_LAUNCH_CHECK();
             if (K == 8192)
                 k_scatter_chunk<1024, 8><<<g_cta, 1024, 0, s>>>(node_begin, n_level, max_chunks, bn.p, F->pairs.p, pmask.p, level_base, split_flag.p,
@@ -794,6 +1274,7 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
             mark();
             level_max_cnt = h_tot[2];
             std::swap(live, live_next);       // (stream-ordered: the old list is released after the kernels that read it)
+            node_map = nullptr;               // the children just made are contiguous
             n_live = h_tot[3];
             level_base = (int)n_pairs;        // the children's lists were appended at the old end of `pairs`
             level_entries = new_pairs;

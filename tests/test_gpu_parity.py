@@ -1238,3 +1238,34 @@ def test_batch_host_call_matches_per_subject_calls(R, meshes, which):
     R.resample_batch_host(ctx, xyzs[:3], tri, low, ltri, feats[:3], got_b[:3] if got_b else None, got_a[:3] if got_a else None)
     if got_b is not None: assert np.array_equal(got_b[2], want_b[2])
     if got_a is not None: assert np.array_equal(got_a[2], want_a[2])
+
+
+@pytest.mark.parametrize("top", [1, 2, 3, 4, 5, 6, -1])
+def test_octree_top_phase_matches_level_passes(R, oracle_built, meshes, top):
+    """The one-pass construction of the first levels (octree_build.cu: k_top_count ... k_top_sort_*, knob "build_top") against the
+    exact level passes from the root (knob 0) and the oracle: identical topology and identical leaf lists for every forced depth,
+    single meshes and a mixed batch (per-mesh depths differ in the auto mode), a jittered mesh, and a mesh too small to split."""
+    L = capi.lib()
+    keys = [2, 4, "j5", 5, 6]
+    try:
+        capi.check(L.msmgpu_set_tuning(b"build_top", 0))
+        want = {k: R.Octree(R.Mesh(*meshes[k])).dump() for k in keys}
+        for k in (3, "j5"):
+            ref = oracle_built.OracleOctree(*meshes[k]).dump()
+            got = want[k] if k in want else R.Octree(R.Mesh(*meshes[k])).dump()
+            assert all(np.array_equal(a, b) for a, b in zip(ref, got))
+        capi.check(L.msmgpu_set_tuning(b"build_top", top))
+        for k in keys:
+            got = R.Octree(R.Mesh(*meshes[k])).dump()
+            assert all(np.array_equal(a, b) for a, b in zip(want[k], got)), f"single mesh {k}"
+        tiny = (np.array([[100.0, 0, 0], [0, 100, 0], [0, 0, 100], [-100, 0, 0]]), np.array([[0, 1, 2], [1, 2, 3]], np.int32))
+        ms = [R.Mesh(*meshes[k]) for k in keys] + [R.Mesh(*tiny)]
+        trees = R.Octree.build_batch(ms)
+        for k, t in zip(keys, trees):
+            assert all(np.array_equal(a, b) for a, b in zip(want[k], t.dump())), f"batch, mesh {k}"
+            q = synth.rotate_sphere(meshes[k][0])
+            assert np.array_equal(t.get_closest_triangle(q), oracle_built.OracleOctree(*meshes[k]).query(q)[0])
+        kinds, counts, tris = trees[-1].dump()
+        assert list(kinds) == [1] and list(counts) == [2] and list(tris) == [0, 1]
+    finally:
+        capi.check(L.msmgpu_set_tuning(b"build_top", -1))
