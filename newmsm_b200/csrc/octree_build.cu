@@ -717,6 +717,47 @@ __device__ __forceinline__ void top_range(const TopBox& b, int axis, int d, int&
     }
 }
 
+// The touched cells of ALL depths <= d0 from the ranges at depth d0: on every axis the range at depth d is the range at depth d0
+// shifted right by (d0 - d) (the "corner exactly on a line" correction of top_range survives the shift: a lattice line of depth d is
+// one of depth d0), and a dilated coordinate (bit b at position 3b) shifts by 3 (d0 - d). Common case: at most two cells per axis.
+struct TopSpan {
+    unsigned lo[3], hi[3];   // dilated coordinates at depth d0, already moved to their bit lane (x << 2, y << 1, z)
+    bool narrow;             // every axis touches one or two cells at depth d0
+    bool empty;              // the triangle lies outside the root cube on some axis
+};
+__device__ __forceinline__ TopSpan top_span(const TopBox& b, int d0) {
+    TopSpan sp;
+    sp.narrow = true;
+    sp.empty = false;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        int lo, hi;
+        top_range(b, a, d0, lo, hi);
+        if (hi < lo) sp.empty = true;
+        if (hi - lo > 1) sp.narrow = false;
+        sp.lo[a] = top_spread((unsigned)max(lo, 0)) << (2 - a);
+        sp.hi[a] = top_spread((unsigned)max(hi, 0)) << (2 - a);
+    }
+    return sp;
+}
+// calls f(cell) for every cell of depth d (= d0 - up) the triangle touches; narrow spans only
+template <typename F>
+__device__ __forceinline__ void top_for_cells(const TopSpan& sp, int up, F&& f) {
+    const int s3 = 3 * up;
+    const unsigned x0 = sp.lo[0] >> s3 & 0x24924u << 0, x1 = sp.hi[0] >> s3 & 0x24924u;   // (bits of the lower lanes shifted in are masked off)
+    const unsigned y0 = sp.lo[1] >> s3 & 0x12492u, y1 = sp.hi[1] >> s3 & 0x12492u;
+    const unsigned z0 = sp.lo[2] >> s3 & 0x09249u, z1 = sp.hi[2] >> s3 & 0x09249u;
+    const bool dx = x1 != x0, dy = y1 != y0, dz = z1 != z0;
+    f(x0 | y0 | z0);
+    if (dz) f(x0 | y0 | z1);
+    if (dy) { f(x0 | y1 | z0); if (dz) f(x0 | y1 | z1); }
+    if (dx) {
+        f(x1 | y0 | z0);
+        if (dz) f(x1 | y0 | z1);
+        if (dy) { f(x1 | y1 | z0); if (dz) f(x1 | y1 | z1); }
+    }
+}
+
 __global__ void __launch_bounds__(256) k_top_count(const TopJob* __restrict__ jobs, unsigned* __restrict__ cnt, long long cells_per_mesh) {
     __shared__ unsigned s_cnt[8 + 64 + 512];   // depths 1..3
     const TopJob job = jobs[blockIdx.y];
@@ -727,7 +768,17 @@ __global__ void __launch_bounds__(256) k_top_count(const TopJob* __restrict__ jo
     unsigned* g = cnt + (size_t)blockIdx.y * cells_per_mesh;
     for (int t = t0 + threadIdx.x; t < min(t0 + kTopTrisPerBlock, job.nt); t += blockDim.x) {
         const TopBox b = top_unpack(__ldg(job.qbox + t));
-        for (int d = 1; d <= job.d0; ++d) {
+        const TopSpan sp = top_span(b, job.d0);
+        if (sp.empty) continue;   // outside the root cube: only the root holds it
+        if (sp.narrow) {
+            for (int d = job.d0; d >= 1; --d) {
+                const int base = (int)top_cells_before(d);
+                if (d <= 3) top_for_cells(sp, job.d0 - d, [&](unsigned cell) { atomicAdd(&s_cnt[base - 1 + cell], 1u); });
+                else top_for_cells(sp, job.d0 - d, [&](unsigned cell) { atomicAdd(g + base + cell, 1u); });
+            }
+            continue;
+        }
+        for (int d = 1; d <= job.d0; ++d) {   // a triangle wider than a cell of depth d0 (coarse meshes at a forced depth)
             int lo[3], hi[3];
 #pragma unroll
             for (int a = 0; a < 3; ++a) top_range(b, a, d, lo[a], hi[a]);
@@ -921,16 +972,25 @@ __global__ void __launch_bounds__(256) k_top_fill(const TopJob* __restrict__ job
     const TopBox b = top_unpack(__ldg(job.qbox + t));
     // the common case first: every touched cell of depth D0 exists (all its ancestors were split); its nid entry is the write cursor
     bool missing = false;
-    {
+    const TopSpan sp = top_span(b, job.d0);
+    if (sp.empty) return;   // outside the root cube: no cell below the root holds it
+    int* __restrict__ cur0 = ids + top_cells_before(job.d0);
+    if (sp.narrow) {
+        top_for_cells(sp, 0, [&](unsigned cell) {
+            const int pos = atomicAdd(cur0 + cell, 1);
+            if (pos >= 0) pairs[pos] = t;
+            else missing = true;   // (the entry of a cell without node stays far below zero)
+        });
+    } else {
         int lo[3], hi[3];
 #pragma unroll
         for (int a = 0; a < 3; ++a) top_range(b, a, job.d0, lo[a], hi[a]);
         for (int ix = lo[0]; ix <= hi[0]; ++ix)
             for (int iy = lo[1]; iy <= hi[1]; ++iy)
                 for (int iz = lo[2]; iz <= hi[2]; ++iz) {
-                    const int pos = atomicAdd(ids + top_cells_before(job.d0) + top_cell(ix, iy, iz), 1);
+                    const int pos = atomicAdd(cur0 + top_cell(ix, iy, iz), 1);
                     if (pos >= 0) pairs[pos] = t;
-                    else missing = true;   // (the entry of a cell without node stays far below zero)
+                    else missing = true;
                 }
     }
     if (!missing) return;

@@ -255,6 +255,40 @@ __global__ void k_incidence_mean(int nkeys, const int* __restrict__ cnt, const i
     out[v] = sum / (double)n;
 }
 
+// Subjects that share one topology (msmgpu_mesh_create_view_batch) share the vertex -> triangles incidence: it is built once, sorted
+// once, and every subject only gathers its own cached areas through it (same ascending-id sum as k_incidence_mean).
+__global__ void k_incidence_sort(int nkeys, const int* __restrict__ cnt, int* __restrict__ inc) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nkeys) return;
+    const int n = min(cnt[v], kIncSlots);
+    int4* row = reinterpret_cast<int4*>(inc) + 2 * (size_t)v;
+    const int4 a = row[0], b = row[1];
+    int id[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) if (i >= n) id[i] = INT_MAX;
+#pragma unroll
+    for (int round = 0; round < 8; ++round) {
+#pragma unroll
+        for (int i = round & 1; i + 1 < 8; i += 2)
+            if (id[i] > id[i + 1]) { const int t = id[i]; id[i] = id[i + 1]; id[i + 1] = t; }
+    }
+    row[0] = make_int4(id[0], id[1], id[2], id[3]);
+    row[1] = make_int4(id[4], id[5], id[6], id[7]);
+}
+__global__ void k_incidence_mean_shared(int nv, const int* __restrict__ cnt, const int* __restrict__ inc, const double* const* __restrict__ area,
+                                        const int* __restrict__ key_off, double* __restrict__ out) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nv) return;
+    const int n = min(__ldg(cnt + v), kIncSlots);
+    const int4 a = __ldg(reinterpret_cast<const int4*>(inc) + 2 * (size_t)v), b = __ldg(reinterpret_cast<const int4*>(inc) + 2 * (size_t)v + 1);
+    const int id[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    const double* __restrict__ ar = area[blockIdx.y];
+    double sum = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) if (i < n) sum += __ldg(ar + id[i]);
+    out[key_off[blockIdx.y] + v] = sum / (double)n;
+}
+
 // vertex areas of a batch of meshes, concatenated: d_out[key_off[s] + v]
 static msmgpu_status vertex_areas_batch(msmgpu_ctx* ctx, int S, msmgpu_mesh* const* meshes, const std::vector<int>& key_off, double* d_out) {
     cudaStream_t s = ctx->stream;
@@ -291,6 +325,32 @@ static msmgpu_status vertex_areas_batch(msmgpu_ctx* ctx, int S, msmgpu_mesh* con
     const int total_t = h_toff[S], nkeys = key_off[S];
     const EmitVertexTriangles emit{d_tri.p, d_rec.p, d_area.p, d_toff.p, d_koff.p, S, total_t};
     static const bool fast = getenv("MSMGPU_GENERIC_VERTEX_AREAS") == nullptr;
+    bool shared = fast && S > 1 && meshes[0]->nt > 0 && meshes[0]->nv > 0 && getenv("MSMGPU_NO_SHARED_INCIDENCE") == nullptr;
+    for (int i = 0; shared && i < S; ++i)
+        shared = h_tri[i] == h_tri[0] && meshes[i]->nt == meshes[0]->nt && meshes[i]->nv == meshes[0]->nv && h_area[i] != nullptr &&
+                 key_off[i + 1] - key_off[i] == meshes[0]->nv;
+    if (shared) {
+        const int nv = meshes[0]->nv, nt = meshes[0]->nt;
+        const EmitVertexTriangles one{d_tri.p, d_rec.p, d_area.p, d_toff.p, d_toff.p /* key offset 0 */, 1, nt};
+        DevBuf<int> cnt, inc, ovf;
+        DevBuf<double> scratch;
+        MSM_CUDA(cnt.alloc((size_t)nv, s));
+        MSM_CUDA(inc.alloc((size_t)nv * kIncSlots, s));
+        MSM_CUDA(ovf.alloc(1, s));
+        MSM_CUDA(scratch.alloc((size_t)nt, s));
+        MSM_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)nv * sizeof(int), s));
+        MSM_CUDA(cudaMemsetAsync(ovf.p, 0, sizeof(int), s));
+        k_incidence_fill<<<(nt + 255) / 256, 256, 0, s>>>(one, cnt.p, inc.p, scratch.p, ovf.p);
+        MSM_LAUNCH_CHECK();
+        k_incidence_sort<<<(nv + 255) / 256, 256, 0, s>>>(nv, cnt.p, inc.p);
+        MSM_LAUNCH_CHECK();
+        k_incidence_mean_shared<<<dim3((unsigned)((nv + 255) / 256), (unsigned)S), 256, 0, s>>>(nv, cnt.p, inc.p, d_area.p, d_koff.p, d_out);
+        MSM_LAUNCH_CHECK();
+        int h_ovf = 0;
+        MSM_CUDA(cudaMemcpyAsync(&h_ovf, ovf.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        MSM_CUDA(cudaStreamSynchronize(s));
+        if (!h_ovf) return MSMGPU_OK;      // otherwise some vertex has more than kIncSlots triangles: the per-mesh paths below
+    }
     if (fast && total_t > 0 && nkeys > 0) {
         DevBuf<int> cnt, inc, ovf;
         DevBuf<double> tarea;
