@@ -322,7 +322,10 @@ msmgpu_status msmgpu_mesh_create_view_batch(msmgpu_ctx* ctx, int n, int nv, cons
     cudaStream_t s = ctx->stream;
     // one allocation for the per-triangle tables of the whole batch: [rec | area | qbox | cull] per mesh, each 256-byte aligned
     auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    const size_t b_rec = up((size_t)nt * sizeof(TriRec)), b_area = up((size_t)nt * sizeof(double)), b_qbox = up((size_t)nt * sizeof(uint4)),
+    // the 128-byte records are deferred (lazy_rec): the batch paths query such meshes a few 10^4 times each and build the record
+    // values of the few surviving candidates on the fly; any other consumer materialises them on first use (msmgpu_octree::view)
+    const bool lazy = tuning_get("lazy_records", "MSMGPU_LAZY_RECORDS", 1) != 0;
+    const size_t b_rec = lazy ? 0 : up((size_t)nt * sizeof(TriRec)), b_area = up((size_t)nt * sizeof(double)), b_qbox = up((size_t)nt * sizeof(uint4)),
                  b_cull = up((size_t)nt * sizeof(float4)), per_mesh = b_rec + b_area + b_qbox + b_cull;
     auto slab = std::make_shared<DevBuf<unsigned char>>();
     MSM_CUDA(slab->alloc(per_mesh * (size_t)n, s));
@@ -333,7 +336,8 @@ msmgpu_status msmgpu_mesh_create_view_batch(msmgpu_ctx* ctx, int n, int nv, cons
         unsigned char* base = slab->p + per_mesh * (size_t)i;
         m->xyz.borrow(const_cast<double*>(d_xyz[i]), 3 * (size_t)nv);
         m->tri.borrow(const_cast<int*>(d_tri), 3 * (size_t)nt);
-        m->rec.borrow(reinterpret_cast<TriRec*>(base), (size_t)nt);
+        if (!lazy) m->rec.borrow(reinterpret_cast<TriRec*>(base), (size_t)nt);
+        m->lazy_rec = lazy;
         m->area_tab.borrow(reinterpret_cast<double*>(base + b_rec), (size_t)nt);
         m->qbox.borrow(reinterpret_cast<uint4*>(base + b_rec + b_area), (size_t)nt);
         m->cull.borrow(reinterpret_cast<float4*>(base + b_rec + b_area + b_qbox), (size_t)nt);
@@ -549,8 +553,10 @@ msmgpu_status msmgpu_bary_resample_batch_f32_dev_keep(msmgpu_ctx* ctx, int n_sub
         DevBuf<int> perm;
         // forward queries (few points per tree, trees streamed from HBM) measured slightly SLOWER in Morton order (profiles/r2b): opt-in
         if (tuning_get("query_order", "MSMGPU_QUERY_ORDER", 1) >= 2) MSM_TRY(morton_order(d_pts, n, perm, s));
+        bool lazy = true;   // every tree without stored records -> the LAZY query kernel; a mixed batch materialises the missing ones
+        for (int i = 0; i < n_subjects; ++i) lazy = lazy && !trees[i]->mesh->rec.p;
         for (int i = 0; i < n_subjects; ++i) {
-            qj[i] = QueryJob{trees[i]->view(), d_pts, n, (int)((size_t)i * n), perm.p};
+            qj[i] = QueryJob{lazy ? trees[i]->view_lazy() : trees[i]->view(), d_pts, n, (int)((size_t)i * n), perm.p};
             gj[i] = GatherJob{nullptr, p_idx + 3 * (size_t)i * n, p_w + 3 * (size_t)i * n, d_feat_in[i], d_feat_out[i]};
         }
         if (tot > 0x7fffffffull / 3) return fail(MSMGPU_ERR_CAPACITY, "bary_resample_batch: batch too large");
@@ -568,7 +574,7 @@ msmgpu_status msmgpu_bary_resample_batch_f32_dev_keep(msmgpu_ctx* ctx, int n_sub
         int chunks = std::max(1, std::min(tuning_get("bary_chunks", "MSMGPU_BARY_CHUNKS", 1), n_subjects));
         const int cap = tuning_get("gather_ctas_per_sm", "MSMGPU_GATHER_CTAS_PER_SM", 0);
         if (chunks == 1) {
-            MSM_TRY(launch_bary_weights_batch(d_qj.p, n_subjects, n, p_idx, p_w, p_ne, p_st, s));
+            MSM_TRY(launch_bary_weights_batch(d_qj.p, n_subjects, n, p_idx, p_w, p_ne, p_st, s, lazy));
             return launch_gather_rows_bulk(d_gj.p, n_subjects, n, D, true, ctx->device, s, cap);
         }
         MSM_TRY(ctx_aux(ctx));
@@ -577,7 +583,7 @@ msmgpu_status msmgpu_bary_resample_batch_f32_dev_keep(msmgpu_ctx* ctx, int n_sub
         for (int c = 0; c < chunks; ++c) {
             const int b = (int)((long long)n_subjects * c / chunks), e = (int)((long long)n_subjects * (c + 1) / chunks);
             if (e <= b) continue;
-            MSM_TRY(launch_bary_weights_batch(d_qj.p + b, e - b, n, p_idx, p_w, p_ne, p_st, s));
+            MSM_TRY(launch_bary_weights_batch(d_qj.p + b, e - b, n, p_idx, p_w, p_ne, p_st, s, lazy));
             MSM_CUDA(cudaEventRecord(ctx->aux_ev[1], s));
             MSM_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_ev[1], 0));
             MSM_TRY(launch_gather_rows_bulk(d_gj.p + b, e - b, n, D, true, ctx->device, ctx->aux_stream, cap));

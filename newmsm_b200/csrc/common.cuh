@@ -87,6 +87,8 @@ struct TreeView {
     const float4* cull; // [nt] conservative bounding spheres, single-precision record (geom.cuh make_cull / pack_cull)
     const int* tri;     // [nt][3]
     int root;
+    const double* xyz;  // [nv][3]: with rec == nullptr (a mesh whose records were never asked for) the queries build a triangle's
+                        // record values from its corners with the same expressions (query.cuh, LAZY)
 };
 
 } // namespace msm
@@ -115,6 +117,8 @@ struct msmgpu_mesh {
     int feat_D = 0;
     bool tables_dirty = false;   // rec / qbox / cull / area_tab not yet computed from xyz (msm::ensure_tables batches that work)
     bool view = false;           // xyz / tri are the caller's device buffers (msmgpu_mesh_create_view_batch)
+    bool lazy_rec = false;       // `rec` is filled on first use (msm::ensure_records): a subject of a batch resampling job is queried a few
+                                 // 10^4 times, its 128-byte records would be 75 % of the per-triangle table traffic and mostly never read
     std::shared_ptr<msm::DevBuf<unsigned char>> slab;   // the per-triangle tables of a batch of view meshes live in one allocation
     msmgpu_mesh* area_source = nullptr;   // mesh whose geometry the cached Triangle areas belong to (msmgpu_mesh_set_area_source)
     msm::DevBuf<double> tri_area;         // optional explicit cached Triangle::area values [nt] (msmgpu_mesh_set_triangle_areas)
@@ -129,9 +133,9 @@ struct msmgpu_octree {
     std::shared_ptr<msm::Forest> forest;
     int root = 0;
     msmgpu_mesh* mesh = nullptr;
-    msm::TreeView view() const {
-        return msm::TreeView{forest->nodes.p, forest->pairs.p, mesh->rec.p, mesh->cull.p, mesh->tri.p, root};
-
+    msm::TreeView view() const;   // records materialised if the mesh deferred them (octree_build.cu)
+    msm::TreeView view_lazy() const {   // for kernels that can do without (rec may be nullptr)
+        return msm::TreeView{forest->nodes.p, forest->pairs.p, mesh->rec.p, mesh->cull.p, mesh->tri.p, root, mesh->xyz.p};
     }
 };
 
@@ -202,7 +206,9 @@ struct QueryJob {         // one subject of a batched barycentric-weights launch
     const int* perm;        // optional processing order (order.cu): thread k handles point perm[k]; outputs stay at the point's index
 };
 msmgpu_status morton_order(const double* d_xyz, int n, DevBuf<int>& perm, cudaStream_t s);
-msmgpu_status launch_bary_weights_batch(const QueryJob* d_jobs, int n_jobs, int max_n, int* d_idx, double* d_w, int* d_ne, int* d_status, cudaStream_t s);
+msmgpu_status launch_bary_weights_batch(const QueryJob* d_jobs, int n_jobs, int max_n, int* d_idx, double* d_w, int* d_ne, int* d_status, cudaStream_t s,
+                                        bool lazy = false);   // lazy: every job's tree comes without records
+msmgpu_status ensure_records(msmgpu_mesh* m);
 
 struct ResampleJob {      // one subject of a batched fused resample
     TreeView tree;

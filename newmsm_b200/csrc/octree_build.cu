@@ -184,21 +184,25 @@ __global__ void __launch_bounds__(256) k_mesh_tables(const TableJob* __restrict_
                 }
             }
         }
-        job.qbox[t] = pack_qbox(lo, hi);   // the FP64 box itself is not stored: below the lattice (depth > 17) k_chunk_stats rebuilds it from the record
-        job.area[t] = tri_area_cached(V3{cv[0], cv[1], cv[2]}, V3{cv[3], cv[4], cv[5]}, V3{cv[6], cv[7], cv[8]});   // Triangle::area of this geometry
-        TriRec r;
-        make_trirec(V3{cv[0], cv[1], cv[2]}, V3{cv[3], cv[4], cv[5]}, V3{cv[6], cv[7], cv[8]}, r);
-        static_assert(sizeof(TriRec) == 16 * sizeof(double), "TriRec is 16 doubles");
-        const double rp[16] = {r.v[0], r.v[1], r.v[2], r.v[3], r.v[4], r.v[5], r.v[6], r.v[7], r.v[8], r.s3[0], r.s3[1], r.s3[2], r.d, r.e12, r.e13, r.e23};
+        if (job.qbox) job.qbox[t] = pack_qbox(lo, hi);   // the FP64 box itself is not stored: below the lattice (depth > 17) k_chunk_stats rebuilds it from the record
+        if (job.area) job.area[t] = tri_area_cached(V3{cv[0], cv[1], cv[2]}, V3{cv[3], cv[4], cv[5]}, V3{cv[6], cv[7], cv[8]});   // Triangle::area of this geometry
+        if (job.rec) {   // (uniform over the launch's job: a mesh either stores its records or defers them, msmgpu_mesh::lazy_rec)
+            TriRec r;
+            make_trirec(V3{cv[0], cv[1], cv[2]}, V3{cv[3], cv[4], cv[5]}, V3{cv[6], cv[7], cv[8]}, r);
+            static_assert(sizeof(TriRec) == 16 * sizeof(double), "TriRec is 16 doubles");
+            const double rp[16] = {r.v[0], r.v[1], r.v[2], r.v[3], r.v[4], r.v[5], r.v[6], r.v[7], r.v[8], r.s3[0], r.s3[1], r.s3[2], r.d, r.e12, r.e13, r.e23};
 #pragma unroll
-        for (int f = 0; f < 16; ++f) mine[lane * 17 + f] = rp[f];
-        double c4[4];
-        make_cull(V3{cv[0], cv[1], cv[2]}, V3{cv[3], cv[4], cv[5]}, V3{cv[6], cv[7], cv[8]}, c4);
-        job.cull[t] = pack_cull(c4);
+            for (int f = 0; f < 16; ++f) mine[lane * 17 + f] = rp[f];
+        }
+        if (job.cull) {
+            double c4[4];
+            make_cull(V3{cv[0], cv[1], cv[2]}, V3{cv[3], cv[4], cv[5]}, V3{cv[6], cv[7], cv[8]}, c4);
+            job.cull[t] = pack_cull(c4);
+        }
     }
     __syncwarp();
     const int t0 = t - lane;   // first triangle of this warp
-    if (t0 < job.nt) {
+    if (job.rec && t0 < job.nt) {
         double* out = reinterpret_cast<double*>(job.rec + t0);
         const int n_valid = min(32, job.nt - t0);
 #pragma unroll
@@ -226,6 +230,20 @@ msmgpu_status ensure_tables(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes) 
     MSM_CUDA(d_jobs.alloc(jobs.size(), s));
     MSM_CUDA(cudaMemcpyAsync(d_jobs.p, jobs.data(), jobs.size() * sizeof(TableJob), cudaMemcpyHostToDevice, s));   // pageable: staged before return
     k_mesh_tables<<<dim3((unsigned)((max_nt + 255) / 256), (unsigned)jobs.size()), 256, 0, s>>>(d_jobs.p);
+    MSM_LAUNCH_CHECK();
+    return MSMGPU_OK;
+}
+
+// the 128-byte query records of a mesh that deferred them (msmgpu_mesh::lazy_rec), for the consumers that read them
+msmgpu_status ensure_records(msmgpu_mesh* m) {
+    if (m->rec.p || m->nt == 0) return MSMGPU_OK;
+    cudaStream_t s = m->ctx->stream;
+    MSM_CUDA(m->rec.alloc((size_t)m->nt, s));
+    const TableJob job{m->xyz.p, m->tri.p, m->rec.p, nullptr, nullptr, nullptr, m->nt};
+    DevBuf<TableJob> d_job;
+    MSM_CUDA(d_job.alloc(1, s));
+    MSM_CUDA(cudaMemcpyAsync(d_job.p, &job, sizeof(TableJob), cudaMemcpyHostToDevice, s));   // pageable: staged before return
+    k_mesh_tables<<<dim3((unsigned)((m->nt + 255) / 256), 1u), 256, 0, s>>>(d_job.p);
     MSM_LAUNCH_CHECK();
     return MSMGPU_OK;
 }
@@ -683,7 +701,7 @@ constexpr int kTopTrisPerBlock = 1024;   // k_top_count: 256 threads x 4 triangl
 constexpr int kTopNone = -0x40000000;    // nid entries at or below this: the cell has no node
 __host__ __device__ __forceinline__ long long top_cells_before(int d) { return ((1ll << (3 * d)) - 1) / 7; }   // cells of depths < d
 
-struct TopJob { const uint4* qbox; int nt; int d0; };
+struct TopJob { const uint4* qbox; int nt; int d0; const int* perm; };   // perm: processing order of the triangles (optional)
 
 __device__ __forceinline__ unsigned top_spread(unsigned v) {
     return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6) | ((v & 16u) << 8) | ((v & 32u) << 10);
@@ -740,25 +758,53 @@ __device__ __forceinline__ TopSpan top_span(const TopBox& b, int d0) {
     }
     return sp;
 }
-// calls f(cell) for every cell of depth d (= d0 - up) the triangle touches; narrow spans only
+// The up-to-8 cells of depth d (= d0 - up) a narrow span touches, as 8 slots (x, y, z each low / high): slot c exists iff every axis
+// it takes the high cell on really has a second cell.
+struct TopCells { unsigned x0, x1, y0, y1, z0, z1; bool dx, dy, dz; };
+__device__ __forceinline__ TopCells top_cells(const TopSpan& sp, int up) {
+    const int s3 = 3 * up;   // (a dilated coordinate shifted by a multiple of 3 stays in its bit lane)
+    TopCells c;
+    c.x0 = sp.lo[0] >> s3; c.x1 = sp.hi[0] >> s3;
+    c.y0 = sp.lo[1] >> s3; c.y1 = sp.hi[1] >> s3;
+    c.z0 = sp.lo[2] >> s3; c.z1 = sp.hi[2] >> s3;
+    c.dx = c.x1 != c.x0; c.dy = c.y1 != c.y0; c.dz = c.z1 != c.z0;
+    return c;
+}
+__device__ __forceinline__ bool top_slot(const TopCells& c, int slot, unsigned& cell) {
+    cell = ((slot & 4) ? c.x1 : c.x0) | ((slot & 2) ? c.y1 : c.y0) | ((slot & 1) ? c.z1 : c.z0);
+    return (!(slot & 4) || c.dx) && (!(slot & 2) || c.dy) && (!(slot & 1) || c.dz);
+}
 template <typename F>
-__device__ __forceinline__ void top_for_cells(const TopSpan& sp, int up, F&& f) {
-    const int s3 = 3 * up;
-    const unsigned x0 = sp.lo[0] >> s3 & 0x24924u << 0, x1 = sp.hi[0] >> s3 & 0x24924u;   // (bits of the lower lanes shifted in are masked off)
-    const unsigned y0 = sp.lo[1] >> s3 & 0x12492u, y1 = sp.hi[1] >> s3 & 0x12492u;
-    const unsigned z0 = sp.lo[2] >> s3 & 0x09249u, z1 = sp.hi[2] >> s3 & 0x09249u;
-    const bool dx = x1 != x0, dy = y1 != y0, dz = z1 != z0;
-    f(x0 | y0 | z0);
-    if (dz) f(x0 | y0 | z1);
-    if (dy) { f(x0 | y1 | z0); if (dz) f(x0 | y1 | z1); }
-    if (dx) {
-        f(x1 | y0 | z0);
-        if (dz) f(x1 | y0 | z1);
-        if (dy) { f(x1 | y1 | z0); if (dz) f(x1 | y1 | z1); }
+__device__ __forceinline__ void top_for_cells(const TopCells& c, F&& f) {
+    f(c.x0 | c.y0 | c.z0);
+    if (c.dz) f(c.x0 | c.y0 | c.z1);
+    if (c.dy) { f(c.x0 | c.y1 | c.z0); if (c.dz) f(c.x0 | c.y1 | c.z1); }
+    if (c.dx) {
+        f(c.x1 | c.y0 | c.z0);
+        if (c.dz) f(c.x1 | c.y0 | c.z1);
+        if (c.dy) { f(c.x1 | c.y1 | c.z0); if (c.dz) f(c.x1 | c.y1 | c.z1); }
+    }
+}
+// Warp-aggregated "+1 per (lane, cell)": the lanes of a warp that name the same cell in the same slot send ONE atomic. All 32 lanes
+// call this together; `on` = this lane takes part. With the triangles processed along a space-filling curve (TopJob::perm) a warp's
+// 32 triangles fall into a handful of cells, so the number of atomics drops by an order of magnitude.
+template <typename F>
+__device__ __forceinline__ void top_warp_add(bool on, const TopCells& c, F&& add /* (cell, count) by the group's leader */) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int slot = 0; slot < 8; ++slot) {
+        unsigned cell;
+        const bool has = on && top_slot(c, slot, cell);
+        const unsigned any = __ballot_sync(0xffffffffu, has);
+        if (any == 0u) continue;   // warp-uniform
+        if (has) {
+            const unsigned grp = __match_any_sync(any, cell);
+            if ((int)__ffs(grp) - 1 == lane) add(cell, __popc(grp));
+        }
     }
 }
 
-__global__ void __launch_bounds__(256) k_top_count(const TopJob* __restrict__ jobs, unsigned* __restrict__ cnt, long long cells_per_mesh) {
+__global__ void __launch_bounds__(256) k_top_count(const TopJob* __restrict__ jobs, unsigned* __restrict__ cnt, long long cells_per_mesh, int agg) {
     __shared__ unsigned s_cnt[8 + 64 + 512];   // depths 1..3
     const TopJob job = jobs[blockIdx.y];
     const int t0 = blockIdx.x * kTopTrisPerBlock;
@@ -766,29 +812,54 @@ __global__ void __launch_bounds__(256) k_top_count(const TopJob* __restrict__ jo
     for (int i = threadIdx.x; i < 8 + 64 + 512; i += blockDim.x) s_cnt[i] = 0u;
     __syncthreads();
     unsigned* g = cnt + (size_t)blockIdx.y * cells_per_mesh;
-    for (int t = t0 + threadIdx.x; t < min(t0 + kTopTrisPerBlock, job.nt); t += blockDim.x) {
-        const TopBox b = top_unpack(__ldg(job.qbox + t));
-        const TopSpan sp = top_span(b, job.d0);
-        if (sp.empty) continue;   // outside the root cube: only the root holds it
-        if (sp.narrow) {
-            for (int d = job.d0; d >= 1; --d) {
-                const int base = (int)top_cells_before(d);
-                if (d <= 3) top_for_cells(sp, job.d0 - d, [&](unsigned cell) { atomicAdd(&s_cnt[base - 1 + cell], 1u); });
-                else top_for_cells(sp, job.d0 - d, [&](unsigned cell) { atomicAdd(g + base + cell, 1u); });
-            }
-            continue;
-        }
-        for (int d = 1; d <= job.d0; ++d) {   // a triangle wider than a cell of depth d0 (coarse meshes at a forced depth)
-            int lo[3], hi[3];
-#pragma unroll
-            for (int a = 0; a < 3; ++a) top_range(b, a, d, lo[a], hi[a]);
-            for (int ix = lo[0]; ix <= hi[0]; ++ix)
-                for (int iy = lo[1]; iy <= hi[1]; ++iy)
-                    for (int iz = lo[2]; iz <= hi[2]; ++iz) {
-                        const unsigned cell = top_cell(ix, iy, iz);
-                        if (d <= 3) atomicAdd(&s_cnt[top_cells_before(d) - 1 + cell], 1u);
-                        else atomicAdd(g + top_cells_before(d) + cell, 1u);
+    for (int k0 = t0; k0 < min(t0 + kTopTrisPerBlock, job.nt); k0 += blockDim.x) {   // (uniform trip count: the warp stays converged)
+        const int k = k0 + threadIdx.x;
+        const bool valid = k < min(t0 + kTopTrisPerBlock, job.nt);
+        const int t = valid ? (job.perm ? __ldg(job.perm + k) : k) : 0;
+        TopBox b{};
+        TopSpan sp{};
+        sp.empty = true; sp.narrow = true;
+        if (valid) { b = top_unpack(__ldg(job.qbox + t)); sp = top_span(b, job.d0); }
+        const bool fast = valid && !sp.empty && sp.narrow;   // (an empty span lies outside the root cube: only the root holds it)
+        for (int d = job.d0; d >= 1; --d) {
+            const int base = (int)top_cells_before(d);
+            const TopCells c = top_cells(sp, job.d0 - d);
+            if (!agg) {
+                if (fast) {
+                    if (d <= 3) top_for_cells(c, [&](unsigned cell) { atomicAdd(&s_cnt[base - 1 + cell], 1u); });
+                    else top_for_cells(c, [&](unsigned cell) { atomicAdd(g + base + cell, 1u); });
+                }
+            } else if (agg == 2) {   // the lower-corner cell (every lane has one) aggregated over the warp, the straddlers' other cells one by one
+                const unsigned on = __ballot_sync(0xffffffffu, fast);
+                if (fast) {
+                    const unsigned c0 = c.x0 | c.y0 | c.z0;
+                    const unsigned grp = __match_any_sync(on, c0);
+                    if ((int)__ffs(grp) - 1 == (int)(threadIdx.x & 31)) {
+                        if (d <= 3) atomicAdd(&s_cnt[base - 1 + c0], (unsigned)__popc(grp));
+                        else atomicAdd(g + base + c0, (unsigned)__popc(grp));
                     }
+                    if (c.dx | c.dy | c.dz) {
+                        bool first = true;
+                        if (d <= 3) top_for_cells(c, [&](unsigned cell) { if (!first) atomicAdd(&s_cnt[base - 1 + cell], 1u); first = false; });
+                        else top_for_cells(c, [&](unsigned cell) { if (!first) atomicAdd(g + base + cell, 1u); first = false; });
+                    }
+                }
+            } else if (d <= 3) top_warp_add(fast, c, [&](unsigned cell, int n) { atomicAdd(&s_cnt[base - 1 + cell], (unsigned)n); });
+            else top_warp_add(fast, c, [&](unsigned cell, int n) { atomicAdd(g + base + cell, (unsigned)n); });
+        }
+        if (valid && !sp.empty && !sp.narrow) {
+            for (int d = 1; d <= job.d0; ++d) {   // a triangle wider than a cell of depth d0 (coarse meshes at a forced depth)
+                int lo[3], hi[3];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) top_range(b, a, d, lo[a], hi[a]);
+                for (int ix = lo[0]; ix <= hi[0]; ++ix)
+                    for (int iy = lo[1]; iy <= hi[1]; ++iy)
+                        for (int iz = lo[2]; iz <= hi[2]; ++iz) {
+                            const unsigned cell = top_cell(ix, iy, iz);
+                            if (d <= 3) atomicAdd(&s_cnt[top_cells_before(d) - 1 + cell], 1u);
+                            else atomicAdd(g + top_cells_before(d) + cell, 1u);
+                        }
+            }
         }
     }
     __syncthreads();
@@ -964,24 +1035,74 @@ __global__ void __launch_bounds__(256) k_top_children(int n, int d, const TopJob
 }
 
 __global__ void __launch_bounds__(256) k_top_fill(const TopJob* __restrict__ jobs, int* __restrict__ nid, long long cells_per_mesh,
-                                                  int* __restrict__ fillc, long long fillc_per_mesh, int* __restrict__ pairs) {
+                                                  int* __restrict__ fillc, long long fillc_per_mesh, int* __restrict__ pairs, int agg) {
     const TopJob job = jobs[blockIdx.y];
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= job.nt || job.d0 <= 0) return;
+    if ((long long)blockIdx.x * blockDim.x >= job.nt || job.d0 <= 0) return;   // whole CTA beyond this mesh
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = k < job.nt;
+    const int t = valid ? (job.perm ? __ldg(job.perm + k) : k) : 0;
     int* __restrict__ ids = nid + (size_t)blockIdx.y * cells_per_mesh;
-    const TopBox b = top_unpack(__ldg(job.qbox + t));
-    // the common case first: every touched cell of depth D0 exists (all its ancestors were split); its nid entry is the write cursor
+    TopBox b{};
+    TopSpan sp{};
+    sp.empty = true; sp.narrow = true;
+    if (valid) { b = top_unpack(__ldg(job.qbox + t)); sp = top_span(b, job.d0); }
+    if (!valid || sp.empty) sp.empty = true;   // outside the root cube: no cell below the root holds it
+    // the common case first: every touched cell of depth D0 exists (all its ancestors were split); its nid entry is the list's write
+    // cursor. The lanes of a warp that append to the same list reserve their places with one atomic (slot by slot, top_warp_add).
     bool missing = false;
-    const TopSpan sp = top_span(b, job.d0);
-    if (sp.empty) return;   // outside the root cube: no cell below the root holds it
     int* __restrict__ cur0 = ids + top_cells_before(job.d0);
-    if (sp.narrow) {
-        top_for_cells(sp, 0, [&](unsigned cell) {
-            const int pos = atomicAdd(cur0 + cell, 1);
-            if (pos >= 0) pairs[pos] = t;
-            else missing = true;   // (the entry of a cell without node stays far below zero)
-        });
-    } else {
+    const int lane = threadIdx.x & 31;
+    {
+        const bool fast = valid && !sp.empty && sp.narrow;
+        const TopCells c = top_cells(sp, 0);
+        if (!agg) {
+            if (fast) top_for_cells(c, [&](unsigned cell) {
+                const int pos = atomicAdd(cur0 + cell, 1);
+                if (pos >= 0) pairs[pos] = t;
+                else missing = true;
+            });
+        } else if (agg == 2) {
+            const unsigned on = __ballot_sync(0xffffffffu, fast);
+            if (fast) {
+                const unsigned c0 = c.x0 | c.y0 | c.z0;
+                const unsigned grp = __match_any_sync(on, c0);
+                const int leader = (int)__ffs(grp) - 1;
+                int pos = 0;
+                if (lane == leader) pos = atomicAdd(cur0 + c0, __popc(grp));
+                pos = __shfl_sync(grp, pos, leader);
+                if (pos >= 0) pairs[pos + __popc(grp & ((1u << lane) - 1u))] = t;
+                else missing = true;
+                if (c.dx | c.dy | c.dz) {
+                    bool first = true;
+                    top_for_cells(c, [&](unsigned cell) {
+                        if (!first) {
+                            const int p2 = atomicAdd(cur0 + cell, 1);
+                            if (p2 >= 0) pairs[p2] = t;
+                            else missing = true;
+                        }
+                        first = false;
+                    });
+                }
+            }
+        } else
+#pragma unroll
+        for (int slot = 0; slot < 8; ++slot) {
+            unsigned cell;
+            const bool has = fast && top_slot(c, slot, cell);
+            const unsigned any = __ballot_sync(0xffffffffu, has);
+            if (any == 0u) continue;   // warp-uniform
+            if (has) {
+                const unsigned grp = __match_any_sync(any, cell);
+                const int leader = (int)__ffs(grp) - 1;
+                int pos = 0;
+                if (lane == leader) pos = atomicAdd(cur0 + cell, __popc(grp));
+                pos = __shfl_sync(grp, pos, leader);
+                if (pos >= 0) pairs[pos + __popc(grp & ((1u << lane) - 1u))] = t;
+                else missing = true;   // (the entry of a cell without node stays far below zero)
+            }
+        }
+    }
+    if (valid && !sp.empty && !sp.narrow) {
         int lo[3], hi[3];
 #pragma unroll
         for (int a = 0; a < 3; ++a) top_range(b, a, job.d0, lo[a], hi[a]);
@@ -1089,6 +1210,13 @@ __global__ void __launch_bounds__(256) k_top_sort_block(int first_node, int n_no
         }
     for (int i = threadIdx.x; i < nd.z; i += blockDim.x) pairs[nd.y + i] = buf[i];
 }
+__global__ void k_tri_points(int nt, const double* __restrict__ xyz, const int* __restrict__ tri, double* __restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nt) return;
+    const int v = tri[3 * (size_t)t];   // the first corner stands for the triangle: only coherence of the order matters
+#pragma unroll
+    for (int a = 0; a < 3; ++a) out[3 * (size_t)t + a] = xyz[3 * (size_t)v + a];
+}
 __global__ void k_iota(int n, int* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = i;
@@ -1170,8 +1298,33 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
         {
             const int knob = top_disabled ? 0 : tuning_get("build_top", "MSMGPU_BUILD_TOP", -1);
             for (int i = 0; i < n; ++i) {
-                top_jobs[i] = TopJob{h_qbox[i], h_nt[i], top_depth_for(h_nt[i], knob)};
+                top_jobs[i] = TopJob{h_qbox[i], h_nt[i], top_depth_for(h_nt[i], knob), nullptr};
                 top_dmax = std::max(top_dmax, top_jobs[i].d0);
+            }
+        }
+        // Optional processing order of the triangles (knob "build_top_order", off by default; results do not depend on it: the lists
+        // are sorted afterwards). Meshes that share one topology share nearly the same geometry, so one Morton order of the first
+        // mesh's triangles makes the 32 triangles of a warp land in a handful of lattice cells. MEASURED (profiles/t4_top_phase.md):
+        // slower — the box reads become gathers and the full 8-slot warp aggregation (knob "build_top_agg" = 1) costs more
+        // instructions than the atomics it saves; what pays is aggregating the lower-corner cell only (= 2, the default), in id order.
+        std::vector<DevBuf<int>> top_perms;
+        const int top_agg = tuning_get("build_top_agg", "MSMGPU_BUILD_TOP_AGG", 2);
+        if (top_dmax > 0 && tuning_get("build_top_order", "MSMGPU_BUILD_TOP_ORDER", 0) != 0) {
+            std::vector<char> done(n, 0);
+            for (int i = 0; i < n; ++i) {
+                if (done[i] || top_jobs[i].d0 <= 0) continue;
+                std::vector<int> same;
+                for (int j = i; j < n; ++j)
+                    if (!done[j] && top_jobs[j].d0 > 0 && meshes[j]->tri.p == meshes[i]->tri.p && h_nt[j] == h_nt[i] && meshes[j]->nv == meshes[i]->nv) same.push_back(j);
+                for (int j : same) done[j] = 1;
+                if ((int)same.size() < 4) continue;   // the sort costs more than it saves on a few meshes
+                DevBuf<double> pts;
+                MSM_CUDA(pts.alloc(3 * (size_t)h_nt[i], s));
+                k_tri_points<<<(h_nt[i] + 255) / 256, 256, 0, s>>>(h_nt[i], meshes[i]->xyz.p, meshes[i]->tri.p, pts.p);
+                MSM_LAUNCH_CHECK();
+                top_perms.emplace_back();
+                MSM_TRY(morton_order(pts.p, h_nt[i], top_perms.back(), s));
+                for (int j : same) top_jobs[j].perm = top_perms.back().p;
             }
         }
         bool top_done = false;
@@ -1199,7 +1352,7 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
             TopCursors h_cur{};
             h_cur.nodes = n;   // the roots are nodes 0 .. n-1
             MSM_CUDA(cudaMemcpyAsync(cur.p, &h_cur, sizeof(TopCursors), cudaMemcpyHostToDevice, s));
-            k_top_count<<<dim3((unsigned)((max_nt + kTopTrisPerBlock - 1) / kTopTrisPerBlock), (unsigned)n), 256, 0, s>>>(d_jobs.p, cnt.p, cells_per_mesh);
+            k_top_count<<<dim3((unsigned)((max_nt + kTopTrisPerBlock - 1) / kTopTrisPerBlock), (unsigned)n), 256, 0, s>>>(d_jobs.p, cnt.p, cells_per_mesh, top_agg);
             MSM_LAUNCH_CHECK();
             {
                 const long long threads = (long long)n * top_cells_before(top_dmax);
@@ -1223,7 +1376,7 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
             // roots that keep their list (meshes too small to split, D0 = 0, or undecided): the identity, octree.cpp:42-61
             k_top_root_lists<<<dim3((unsigned)std::min((max_nt + 255) / 256, 64), (unsigned)n), 256, 0, s>>>(nid.p, cells_per_mesh, F->nodes.p, F->pairs.p);
             MSM_LAUNCH_CHECK();
-            k_top_fill<<<dim3((unsigned)((max_nt + 255) / 256), (unsigned)n), 256, 0, s>>>(d_jobs.p, nid.p, cells_per_mesh, fillc.p, fillc_per_mesh, F->pairs.p);
+            k_top_fill<<<dim3((unsigned)((max_nt + 255) / 256), (unsigned)n), 256, 0, s>>>(d_jobs.p, nid.p, cells_per_mesh, fillc.p, fillc_per_mesh, F->pairs.p, top_agg);
             MSM_LAUNCH_CHECK();
             if (r.nodes > n) {
                 k_top_sort_warp<<<(unsigned)((r.nodes - n + 7) / 8), 256, 0, s>>>(n, r.nodes, F->nodes.p, F->pairs.p);
@@ -1287,6 +1440,12 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
             MSM_CUDA(stats.alloc((size_t)n_level * max_chunks * kStatInts, s));
             if (max_chunks > 65535) return fail(MSMGPU_ERR_CAPACITY, "forest_build: list too long for the chunk grid");
             const dim3 g_cta((unsigned)std::max(n_live, 1), (unsigned)max_chunks), g_warp((unsigned)((std::max(n_live, 1) + 7) / 8), (unsigned)max_chunks);
+            if (depth > kGridMaxDepth) {   // below the lattice k_chunk_stats rebuilds the FP64 boxes from the records: deferred ones are needed now
+                bool changed = false;
+                for (int i = 0; i < n; ++i)
+                    if (!meshes[i]->rec.p && meshes[i]->nt > 0) { MSM_TRY(ensure_records(meshes[i])); h_rec[i] = meshes[i]->rec.p; changed = true; }
+                if (changed) MSM_CUDA(cudaMemcpyAsync(d_rec.p, h_rec.data(), n * sizeof(TriRec*), cudaMemcpyHostToDevice, s));
+            }
             mark();
             if (n_live == 0) {}   // nothing can split: k_node_combine clears the flags and the loop ends
             else if (K == 8192)
@@ -1374,3 +1533,9 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
 } // namespace msm
 
 msmgpu_mesh::~msmgpu_mesh() { delete own_tree; }
+
+msm::TreeView msmgpu_octree::view() const {
+    if (!mesh->rec.p && mesh->nt > 0 && msm::ensure_records(mesh) != MSMGPU_OK)
+        fprintf(stderr, "[msmgpu] could not materialise the triangle records of a mesh: %s\n", msmgpu_last_error());
+    return view_lazy();
+}

@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256) k_bary_weights(TreeView T, int n, const d
 }
 
 // the same for a batch of jobs (blockIdx.y = job): different trees and/or different point sets, outputs concatenated
-template <int G, int MINB>
+template <int G, int MINB, bool LAZY = false>
 __global__ void __launch_bounds__(256, MINB) k_bary_weights_batch(const QueryJob* __restrict__ jobs, int* __restrict__ out_idx, double* __restrict__ out_w,
                                                             int* __restrict__ out_ne, int* __restrict__ out_status) {
     const QueryJob job = jobs[blockIdx.y];
@@ -82,12 +82,12 @@ __global__ void __launch_bounds__(256, MINB) k_bary_weights_batch(const QueryJob
     const int q = (active && job.perm) ? __ldg(job.perm + k) : k;   // processing order only; outputs are indexed by the point
     const V3 pt = active ? load_pt(job.pts, q) : V3{0, 0, 0};
     int st;
-    const int t = nearest_triangle<G>(job.tree, pt, active, gl, st);
+    const int t = nearest_triangle<G, LAZY>(job.tree, pt, active, gl, st);
     if (!active || gl != 0) return;
     int idx[3] = {-1, -1, -1};
     double w[3] = {0, 0, 0};
     int ne = 0;
-    if (t >= 0) ne = sorted_weights(job.tree, t, pt, idx, w);
+    if (t >= 0) ne = sorted_weights<LAZY>(job.tree, t, pt, idx, w);
     const size_t o = (size_t)job.out_off + q;
 #pragma unroll
     for (int j = 0; j < 3; ++j) { out_idx[3 * o + j] = idx[j]; out_w[3 * o + j] = w[j]; }
@@ -328,11 +328,22 @@ msmgpu_status launch_bary_weights(const TreeView& t, int n, const double* d_pts,
     return MSMGPU_OK;
 }
 
-msmgpu_status launch_bary_weights_batch(const QueryJob* d_jobs, int n_jobs, int max_n, int* d_idx, double* d_w, int* d_ne, int* d_status, cudaStream_t s) {
+msmgpu_status launch_bary_weights_batch(const QueryJob* d_jobs, int n_jobs, int max_n, int* d_idx, double* d_w, int* d_ne, int* d_status, cudaStream_t s,
+                                        bool lazy) {
     if (n_jobs <= 0 || max_n <= 0) return MSMGPU_OK;
     const int g = query_group_width();
     const int minb = tuning_get("weights_minb", "MSMGPU_WEIGHTS_MINB", 4);   // tuning knob: resident CTAs per SM (4: 64 registers, measured best)
     const dim3 grid(query_blocks(max_n, g), (unsigned)n_jobs);
+    if (lazy) {   // trees without stored records (subjects of a batch job): the record values come from the corners
+        const int minb_lazy = tuning_get("weights_minb_lazy", "MSMGPU_WEIGHTS_MINB_LAZY", 4);
+        switch (minb_lazy) {
+            case 2: MSM_DISPATCH_G(g, (k_bary_weights_batch<G, 2, true><<<grid, 256, 0, s>>>(d_jobs, d_idx, d_w, d_ne, d_status))); break;
+            case 3: MSM_DISPATCH_G(g, (k_bary_weights_batch<G, 3, true><<<grid, 256, 0, s>>>(d_jobs, d_idx, d_w, d_ne, d_status))); break;
+            default: MSM_DISPATCH_G(g, (k_bary_weights_batch<G, 4, true><<<grid, 256, 0, s>>>(d_jobs, d_idx, d_w, d_ne, d_status))); break;
+        }
+        MSM_LAUNCH_CHECK();
+        return MSMGPU_OK;
+    }
     switch (minb) {
         case 2: MSM_DISPATCH_G(g, (k_bary_weights_batch<G, 2><<<grid, 256, 0, s>>>(d_jobs, d_idx, d_w, d_ne, d_status))); break;
         case 3: MSM_DISPATCH_G(g, (k_bary_weights_batch<G, 3><<<grid, 256, 0, s>>>(d_jobs, d_idx, d_w, d_ne, d_status))); break;

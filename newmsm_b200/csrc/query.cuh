@@ -20,10 +20,46 @@ __device__ __forceinline__ void group_argmin(double& d, int& pos, int& t) {
     }
 }
 
+// A triangle's query record, stored (TriRec) or, LAZY, built from its corners with the expressions make_trirec stores
+// (project_to_plane / boundary_distance of geom.cuh are those expressions; --fmad=false: same bits)
+template <bool LAZY>
+__device__ __forceinline__ void tri_corners(const TreeView& T, int t, V3& v1, V3& v2, V3& v3) {
+    if (LAZY) {
+        const int i0 = __ldg(T.tri + 3 * (size_t)t), i1 = __ldg(T.tri + 3 * (size_t)t + 1), i2 = __ldg(T.tri + 3 * (size_t)t + 2);
+        v1 = V3{__ldg(T.xyz + 3 * (size_t)i0), __ldg(T.xyz + 3 * (size_t)i0 + 1), __ldg(T.xyz + 3 * (size_t)i0 + 2)};
+        v2 = V3{__ldg(T.xyz + 3 * (size_t)i1), __ldg(T.xyz + 3 * (size_t)i1 + 1), __ldg(T.xyz + 3 * (size_t)i1 + 2)};
+        v3 = V3{__ldg(T.xyz + 3 * (size_t)i2), __ldg(T.xyz + 3 * (size_t)i2 + 1), __ldg(T.xyz + 3 * (size_t)i2 + 2)};
+    } else {
+        const double* v = T.rec[t].v;
+        v1 = V3{v[0], v[1], v[2]}; v2 = V3{v[3], v[4], v[5]}; v3 = V3{v[6], v[7], v[8]};
+    }
+}
+template <bool LAZY>
+__device__ __forceinline__ bool tri_inside(const TreeView& T, const V3& pt, int t) {
+    if (!LAZY) return rec_inside(pt, T.rec + t);
+    V3 v1, v2, v3;
+    tri_corners<true>(T, t, v1, v2, v3);
+    return in_triangle(project_to_plane(pt, v1, v2, v3), v1, v2, v3);
+}
+template <bool LAZY>
+__device__ __forceinline__ double tri_distance_inside(const TreeView& T, const V3& pt, int t) {
+    if (!LAZY) return rec_distance_inside(pt, T.rec + t);
+    V3 v1, v2, v3;
+    tri_corners<true>(T, t, v1, v2, v3);
+    return boundary_distance(project_to_plane(pt, v1, v2, v3), v1, v2, v3);
+}
+template <bool LAZY>
+__device__ __forceinline__ double tri_distance(const TreeView& T, const V3& pt, int t) {
+    if (!LAZY) return rec_distance(pt, T.rec + t);
+    V3 v1, v2, v3;
+    tri_corners<true>(T, t, v1, v2, v3);
+    return distance_to_triangle(pt, v1, v2, v3);
+}
+
 // All 32 lanes of the warp must call this together (inactive queries pass active = false);
 // the G lanes of a group pass the same point. `gl` = lane index inside the group.
 // Returns the triangle id (same value in all lanes of the group) or -1; status as msmgpu_status.
-template <int G>
+template <int G, bool LAZY = false>
 __device__ __forceinline__ int nearest_triangle(const TreeView& T, const V3& pt, bool active, int gl, int& status) {
     status = MSMGPU_OK;
     if (active) {   // node.cpp:67-77 on the root cube [-101,101]^3 (octree.cpp:157-158)
@@ -111,21 +147,21 @@ __device__ __forceinline__ int nearest_triangle(const TreeView& T, const V3& pt,
         while (keep) {
             const int j = __ffsll((long long)keep) - 1;
             keep &= keep - 1;
-            if (rec_inside(pt, T.rec + __ldg(list + gl + j * G))) inside |= 1ull << j;
+            if (tri_inside<LAZY>(T, pt, __ldg(list + gl + j * G))) inside |= 1ull << j;
         }
         while (inside) {
             const int j = __ffsll((long long)inside) - 1;
             inside &= inside - 1;
             const int i = gl + j * G;
             const int t = __ldg(list + i);
-            const double d = rec_distance_inside(pt, T.rec + t);
+            const double d = tri_distance_inside<LAZY>(T, pt, t);
             if (d > kNotInTriangle && d < best_d) { best_d = d; best_pos = i; best_t = t; }
         }
         for (int j = 64; j < mine; ++j) {                     // oversized leaves (split refused, octree.cpp:102): no mask
             const int i = gl + j * G;
             const int t = __ldg(list + i);
             if (!cull_keep_f4(__ldg(T.cull + t), pt, pp)) continue;
-            const double d = rec_distance(pt, T.rec + t);
+            const double d = tri_distance<LAZY>(T, pt, t);
             if (d > kNotInTriangle && d < best_d) { best_d = d; best_pos = i; best_t = t; }
         }
     }
@@ -142,7 +178,7 @@ __device__ __forceinline__ int nearest_triangle(const TreeView& T, const V3& pt,
                 for (int i = gl; i < ch.z; i += G) {
                     const int t = __ldg(T.pairs + ch.y + i);
                     if (!cull_keep_f4(__ldg(T.cull + t), pt, vdot(pt, pt))) continue;
-                    const double d = rec_distance(pt, T.rec + t);
+                    const double d = tri_distance<LAZY>(T, pt, t);
                     if (d > kNotInTriangle && d < best_d) { best_d = d; best_pos = base + i; best_t = t; }
                 }
                 base += ch.z;
@@ -160,10 +196,11 @@ __device__ __forceinline__ int nearest_triangle(const TreeView& T, const V3& pt,
                     const int4 ch = __ldg(T.nodes + first_child + c);
                     for (int i = gl; i < ch.z; i += G) {
                         const int t = __ldg(T.pairs + ch.y + i);
-                        const double* v = T.rec[t].v;
+                        V3 cv[3];
+                        tri_corners<LAZY>(T, t, cv[0], cv[1], cv[2]);
 #pragma unroll
                         for (int k = 0; k < 3; ++k) {
-                            const double d = vnorm(vsub(V3{v[3 * k], v[3 * k + 1], v[3 * k + 2]}, pt));
+                            const double d = vnorm(vsub(cv[k], pt));
                             // a chord longer than the diameter makes the reference's asin NaN and its `<` false: corner skipped
                             if (d <= 2.0 * kRad && d < best_d) { best_d = d; best_pos = 3 * (base + i) + k; best_t = t; }
                         }
@@ -189,11 +226,17 @@ __device__ __forceinline__ void rec_corners(const TriRec* __restrict__ r, V3& v1
 
 // calc_barycentric_weights (triangle.cpp:124-143) -> std::map<int,double> semantics: entries in
 // ascending vertex id, a repeated id keeps the LAST value assigned. Returns the entry count.
+template <bool LAZY = false>
 __device__ __forceinline__ int sorted_weights(const TreeView& T, int t, const V3& pt, int* idx, double* w) {
-    const TriRec* r = T.rec + t;
-    V3 v1, v2, v3;
-    rec_corners(r, v1, v2, v3);
-    const V3 PP = rec_project(pt, V3{r->s3[0], r->s3[1], r->s3[2]}, r->d);
+    V3 v1, v2, v3, PP;
+    if (LAZY) {
+        tri_corners<true>(T, t, v1, v2, v3);
+        PP = project_to_plane(pt, v1, v2, v3);
+    } else {
+        const TriRec* r = T.rec + t;
+        rec_corners(r, v1, v2, v3);
+        PP = rec_project(pt, V3{r->s3[0], r->s3[1], r->s3[2]}, r->d);
+    }
     const double Aa = tri_area(PP, v2, v3);
     const double Ab = tri_area(PP, v1, v3);
     const double Ac = tri_area(PP, v1, v2);

@@ -306,6 +306,7 @@ static msmgpu_status vertex_areas_batch(msmgpu_ctx* ctx, int S, msmgpu_mesh* con
         h_tri[i] = meshes[i]->tri.p;
         h_rec[i] = meshes[i]->rec.p;
         h_area[i] = meshes[i]->tri_area.p ? meshes[i]->tri_area.p : meshes[i]->area_tab.p;   // explicit cached values, else the table of the current geometry
+        if (!h_area[i] && !meshes[i]->rec.p) { MSM_TRY(ensure_records(meshes[i])); h_rec[i] = meshes[i]->rec.p; }
         h_toff[i + 1] = h_toff[i] + meshes[i]->nt;
     }
     DevBuf<const int*> d_tri;
@@ -512,8 +513,10 @@ msmgpu_status adaptive_weights_build_batch(msmgpu_ctx* ctx, int S, msmgpu_mesh* 
     if (ordered >= 1) MSM_TRY(morton_order(in_meshes[0]->xyz.p, in_meshes[0]->nv, perm_rev, s));
     if (ordered >= 2 && !fwd) MSM_TRY(morton_order(low_mesh->xyz.p, n_low, perm_fwd, s));
     std::vector<QueryJob> jobs(2 * (size_t)S);
+    bool lazy_fwd = !fwd;   // forward queries in trees without stored records -> the LAZY query kernel (a mixed batch materialises them)
+    for (int i = 0; lazy_fwd && i < S; ++i) lazy_fwd = !in_trees[i]->mesh->rec.p;
     for (int i = 0; i < S; ++i) {
-        jobs[i] = QueryJob{in_trees[i]->view(), low_mesh->xyz.p, n_low, i * n_low, perm_fwd.p};
+        jobs[i] = QueryJob{(fwd || lazy_fwd) ? in_trees[i]->view_lazy() : in_trees[i]->view(), low_mesh->xyz.p, n_low, i * n_low, perm_fwd.p};
         jobs[S + i] = QueryJob{low_tree->view(), in_meshes[i]->xyz.p, in_meshes[i]->nv, in_off[i],
                                in_meshes[i]->nv == in_meshes[0]->nv ? perm_rev.p : nullptr};
     }
@@ -541,7 +544,7 @@ msmgpu_status adaptive_weights_build_batch(msmgpu_ctx* ctx, int S, msmgpu_mesh* 
     MSM_CUDA(rne.alloc((size_t)NV, s));
     MSM_CUDA(st.alloc((size_t)(NL + NV), s));
     if (fwd) MSM_CUDA(cudaMemsetAsync(st.p, 0, (size_t)NL * sizeof(int), s));   // the fused kernel already reported the forward statuses
-    else MSM_TRY(launch_bary_weights_batch(d_jobs.p, S, n_low, fidx_own.p, fw_own.p, fne_own.p, st.p, s));
+    else MSM_TRY(launch_bary_weights_batch(d_jobs.p, S, n_low, fidx_own.p, fw_own.p, fne_own.p, st.p, s, lazy_fwd));
     MSM_TRY(launch_bary_weights_batch(d_jobs.p + S, S, max_nv, ridx.p, rw.p, rne.p, st.p + NL, s));
     int code = 0;
     MSM_TRY(first_error(st.p, (size_t)(NL + NV), s, &code));   // synchronises: `jobs` / `in_off` may now go

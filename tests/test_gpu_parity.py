@@ -1269,3 +1269,64 @@ def test_octree_top_phase_matches_level_passes(R, oracle_built, meshes, top):
         assert list(kinds) == [1] and list(counts) == [2] and list(tris) == [0, 1]
     finally:
         capi.check(L.msmgpu_set_tuning(b"build_top", -1))
+        capi.check(L.msmgpu_set_tuning(b"lazy_records", 1))
+
+
+@pytest.mark.parametrize("top", [-1, 3, 6])
+def test_octree_top_phase_shared_topology_order(R, oracle_built, meshes, top):
+    """Five subjects that share one topology (device views): the top phase processes their triangles along one Morton order of the
+    first subject's triangles and aggregates its atomics per warp — the forests must equal the exact level passes (knob 0) and the
+    oracle, and the barycentric weight maps of queries in those trees (records deferred: built from the corners) must be the
+    per-mesh ones bit for bit."""
+    import torch
+    L = capi.lib()
+    ctx = R.Context(0)
+    dev = torch.device("cuda", 0)
+    S = 5
+    tri = np.ascontiguousarray(meshes[5][1], dtype=np.int32)
+    xyz = [synth.jitter_sphere(meshes[5][0], tri, frac=0.3, seed=70 + s) for s in range(S)]
+    d_xyz = [torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in xyz]
+    d_tri = torch.from_numpy(tri).to(dev)
+    torch.cuda.synchronize()
+    q = np.concatenate([synth.rotate_sphere(meshes[4][0], 0.02, -0.01, 0.03), adversarial_points(xyz[0], tri)[:2000]])
+    try:
+        capi.check(L.msmgpu_set_tuning(b"build_top", 0))
+        want = [R.Octree(R.Mesh(x, tri, ctx=ctx)) for x in xyz]
+        want_dump = [t.dump() for t in want]
+        assert all(np.array_equal(a, b) for a, b in zip(want_dump[0], oracle_built.OracleOctree(xyz[0], tri).dump()))
+        capi.check(L.msmgpu_set_tuning(b"build_top", top))
+        views = R.Mesh.views_from_device(ctx, len(xyz[0]), d_xyz, len(tri), d_tri)
+        trees = R.Octree.build_batch(views)
+        for s in range(S):
+            assert all(np.array_equal(a, b) for a, b in zip(want_dump[s], trees[s].dump())), f"subject {s}"
+        # batched resample in the view trees with deferred records (values built from the corners) against the same call on views that
+        # store their records, and the statuses against the per-mesh queries
+        d_q = torch.from_numpy(np.ascontiguousarray(q)).to(dev)
+        n = len(q)
+        rng = np.random.default_rng(5)
+        d_feat = [torch.from_numpy(rng.normal(size=(len(xyz[0]), 4)).astype(np.float32)).to(dev) for _ in range(S)]
+
+        def run(tree_list):
+            d_out = [torch.zeros((n, 4), dtype=torch.float32, device=dev) for _ in range(S)]
+            d_st = torch.zeros(S * n, dtype=torch.int32, device=dev)
+            fwd = capi.C.c_void_p()
+            capi.check(L.msmgpu_fwd_create(ctx.h, S, n, capi.C.byref(fwd)))
+            tp = (capi.C.c_void_p * S)(*[t.h.value for t in tree_list])
+            fp = (capi.C.c_void_p * S)(*[f.data_ptr() for f in d_feat])
+            op = (capi.C.c_void_p * S)(*[o.data_ptr() for o in d_out])
+            capi.check(L.msmgpu_bary_resample_batch_f32_dev_keep(ctx.h, S, tp, n, d_q.data_ptr(), 4, fp, op, d_st.data_ptr(), fwd))
+            capi.check(L.msmgpu_ctx_sync(ctx.h))
+            L.msmgpu_fwd_destroy(fwd)
+            return [o.cpu().numpy() for o in d_out], d_st.cpu().numpy().reshape(S, n)
+        got, st = run(trees)
+        capi.check(L.msmgpu_set_tuning(b"lazy_records", 0))
+        views2 = R.Mesh.views_from_device(ctx, len(xyz[0]), d_xyz, len(tri), d_tri)
+        ref, st2 = run(R.Octree.build_batch(views2))
+        assert np.array_equal(st, st2)
+        for s in range(S):
+            ok = st[s] == 0
+            assert np.array_equal(got[s][ok], ref[s][ok]), f"resampled values, subject {s}"
+            assert np.array_equal(st[s], want[s].query(q)[2]), f"statuses, subject {s}"
+    finally:
+        capi.check(L.msmgpu_set_tuning(b"build_top", -1))
+        capi.check(L.msmgpu_set_tuning(b"lazy_records", 1))
