@@ -392,18 +392,23 @@ __global__ void k_row_lengths(int n_rows, const int* __restrict__ fne, const int
     len[n] = r <= fne[n] ? fne[n] : r;
 }
 // rows in ascending column order, multiplied by the target vertex area (resampler.cpp:111-113)
-__global__ void k_fill_rows(int n_rows, int n_low, const int* __restrict__ rowptr, const int* __restrict__ fidx, const double* __restrict__ fw,
-                            const int* __restrict__ fne, const int* __restrict__ rr_ptr, const int* __restrict__ rr_id,
-                            const double* __restrict__ rr_val, const double* __restrict__ new_area, int* __restrict__ col, double* __restrict__ val) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) k_fill_rows(int n_rows, int n_low, const int* __restrict__ rowptr, const int* __restrict__ fidx,
+                                                   const double* __restrict__ fw, const int* __restrict__ fne, const int* __restrict__ rr_ptr,
+                                                   const int* __restrict__ rr_id, const double* __restrict__ rr_val,
+                                                   const double* __restrict__ new_area, int* __restrict__ col, double* __restrict__ val) {
+    // half a warp per row (rows hold ~15 entries): consecutive lanes copy consecutive entries, so the reads of the transposed
+    // reverse lists and the writes of the row are contiguous (one thread per row walked its row with a stride of the row length)
+    const int n = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4);
+    const int hl = threadIdx.x & 15;
     if (n >= n_rows) return;
     const int rb = rr_ptr[n], r = rr_ptr[n + 1] - rb;
     const int o = rowptr[n];
     const double a = new_area[n % n_low];
-    if (r <= fne[n]) {
-        for (int j = 0; j < fne[n]; ++j) { col[o + j] = fidx[3 * (size_t)n + j]; val[o + j] = fw[3 * (size_t)n + j] * a; }
+    const int nf = fne[n];
+    if (r <= nf) {
+        if (hl < nf) { col[o + hl] = fidx[3 * (size_t)n + hl]; val[o + hl] = fw[3 * (size_t)n + hl] * a; }
     } else {
-        for (int j = 0; j < r; ++j) { col[o + j] = rr_id[rb + j]; val[o + j] = rr_val[rb + j] * a; }
+        for (int j = hl; j < r; j += 16) { col[o + j] = rr_id[rb + j]; val[o + j] = rr_val[rb + j] * a; }
     }
 }
 // correction[src] = sum over the targets whose row holds src, in ascending target order, of the area-scaled weight
@@ -582,7 +587,7 @@ msmgpu_status adaptive_weights_build_batch(msmgpu_ctx* ctx, int S, msmgpu_mesh* 
     const size_t cap = 3 * (size_t)(NL + NV);
     MSM_CUDA(store->col.alloc(cap, s));
     MSM_CUDA(store->val.alloc(cap, s));
-    k_fill_rows<<<gl, 256, 0, s>>>((int)NL, n_low, store->rowptr.p, fidx.p, fw.p, fne.p, rr.ptr.p, rr.id.p, rr.val.p, new_area.p, store->col.p,
+    k_fill_rows<<<(unsigned)((16 * NL + 255) / 256), 256, 0, s>>>((int)NL, n_low, store->rowptr.p, fidx.p, fw.p, fne.p, rr.ptr.p, rr.id.p, rr.val.p, new_area.p, store->col.p,
                                    store->val.p);
     MSM_LAUNCH_CHECK();
 
