@@ -1,6 +1,7 @@
 // Internal declarations shared by the kernels and the C-ABI layer (include/msmgpu.h).
 #pragma once
 #include <cuda_runtime.h>
+#include <climits>
 #include <cstdint>
 #include <atomic>
 #include <cstdio>
@@ -220,6 +221,38 @@ struct ResampleJob {      // one subject of a batched fused resample
 };
 
 msmgpu_status launch_bary_resample_f32(const ResampleJob* d_jobs, int n_jobs, int n, const double* d_pts, int D, int* d_status, cudaStream_t s);
+
+// Bitonic sort of 16 * E keys held by the 16 lanes of a half-warp (element e = r * 16 + lane16; ascending): exchanges at distance
+// >= 16 stay inside the lane, shorter ones are one shuffle. `mask` names the 16 lanes of the group; both halves of a warp may run
+// different E (divergent), each with its own mask.
+template <int E>
+__device__ __forceinline__ void half_warp_bitonic(int (&v)[E], unsigned mask) {
+    const int hl = threadIdx.x & 15;
+#pragma unroll
+    for (int k = 2; k <= 16 * E; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 16) {
+                const int rj = j >> 4;
+#pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    if (r & rj) continue;
+                    const bool asc = (((r << 4) | hl) & k) == 0;
+                    const int x = v[r], y = v[r | rj];
+                    if ((x > y) == asc) { v[r] = y; v[r | rj] = x; }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    const int o = __shfl_xor_sync(mask, v[r], j, 16);
+                    const bool asc = (((r << 4) | hl) & k) == 0;
+                    const bool lower = (hl & j) == 0;
+                    v[r] = (lower == asc) ? min(v[r], o) : max(v[r], o);
+                }
+            }
+        }
+    }
+}
 
 msmgpu_status exclusive_scan_i32(const int* d_in, int* d_out, int n, int* d_total, cudaStream_t s);
 

@@ -821,8 +821,8 @@ __global__ void __launch_bounds__(256) k_top_count(const TopJob* __restrict__ jo
         sp.empty = true; sp.narrow = true;
         if (valid) { b = top_unpack(__ldg(job.qbox + t)); sp = top_span(b, job.d0); }
         const bool fast = valid && !sp.empty && sp.narrow;   // (an empty span lies outside the root cube: only the root holds it)
-        for (int d = job.d0; d >= 1; --d) {
-            const int base = (int)top_cells_before(d);
+        int base = (int)top_cells_before(job.d0);
+        for (int d = job.d0; d >= 1; base = (base - 1) >> 3, --d) {   // (8^d - 1) / 7 -> (8^(d-1) - 1) / 7
             const TopCells c = top_cells(sp, job.d0 - d);
             if (!agg) {
                 if (fast) {
@@ -1135,56 +1135,29 @@ __global__ void __launch_bounds__(256) k_top_fill(const TopJob* __restrict__ job
 }
 
 // ascending id order inside every list the top phase filled = the order the reference's sequential insertion produces.
-// One warp per node, bitonic network on E registers per lane (element e = r * 32 + lane): exchanges at distance >= 32 stay inside the
-// lane, shorter ones are one shuffle.
+// Half a warp per node (lists hold ~20 ids), shuffle network of common.cuh on E registers per lane.
 template <int E>
-__device__ __forceinline__ void warp_bitonic(int (&v)[E]) {
-    const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int k = 2; k <= 32 * E; k <<= 1) {
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            if (j >= 32) {
-                const int rj = j >> 5;
-#pragma unroll
-                for (int r = 0; r < E; ++r) {
-                    if (r & rj) continue;
-                    const bool asc = (((r << 5) | lane) & k) == 0;
-                    const int x = v[r], y = v[r | rj];
-                    if ((x > y) == asc) { v[r] = y; v[r | rj] = x; }
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < E; ++r) {
-                    const int o = __shfl_xor_sync(0xffffffffu, v[r], j);
-                    const bool asc = (((r << 5) | lane) & k) == 0;
-                    const bool lower = (lane & j) == 0;
-                    v[r] = (lower == asc) ? min(v[r], o) : max(v[r], o);
-                }
-            }
-        }
-    }
-}
-template <int E>
-__device__ __forceinline__ void warp_sort_list(int* __restrict__ list, int cnt) {
-    const int lane = threadIdx.x & 31;
+__device__ __forceinline__ void half_warp_sort_list(int* __restrict__ list, int cnt, unsigned mask) {
+    const int hl = threadIdx.x & 15;
     int v[E];
 #pragma unroll
-    for (int r = 0; r < E; ++r) { const int e = (r << 5) | lane; v[r] = e < cnt ? list[e] : INT_MAX; }
-    warp_bitonic<E>(v);
+    for (int r = 0; r < E; ++r) { const int e = (r << 4) | hl; v[r] = e < cnt ? list[e] : INT_MAX; }
+    half_warp_bitonic<E>(v, mask);
 #pragma unroll
-    for (int r = 0; r < E; ++r) { const int e = (r << 5) | lane; if (e < cnt) list[e] = v[r]; }
+    for (int r = 0; r < E; ++r) { const int e = (r << 4) | hl; if (e < cnt) list[e] = v[r]; }
 }
 __global__ void __launch_bounds__(256) k_top_sort_warp(int first_node, int n_nodes, const int4* __restrict__ nodes, int* __restrict__ pairs) {
-    const int id = first_node + blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (id >= n_nodes) return;
+    const int id = first_node + blockIdx.x * 16 + (threadIdx.x >> 4);
+    const unsigned mask = 0xffffu << (threadIdx.x & 16);
+    if (id >= n_nodes) return;       // (whole half-warps leave together)
     const int4 nd = nodes[id];
     if (nd.x != -1 || nd.z <= 1 || nd.z > 256) return;
     int* list = pairs + nd.y;
-    if (nd.z <= 32) warp_sort_list<1>(list, nd.z);
-    else if (nd.z <= 64) warp_sort_list<2>(list, nd.z);
-    else if (nd.z <= 128) warp_sort_list<4>(list, nd.z);
-    else warp_sort_list<8>(list, nd.z);
+    if (nd.z <= 16) half_warp_sort_list<1>(list, nd.z, mask);
+    else if (nd.z <= 32) half_warp_sort_list<2>(list, nd.z, mask);
+    else if (nd.z <= 64) half_warp_sort_list<4>(list, nd.z, mask);
+    else if (nd.z <= 128) half_warp_sort_list<8>(list, nd.z, mask);
+    else half_warp_sort_list<16>(list, nd.z, mask);
 }
 constexpr int kTopSortCap = 4096;
 __global__ void __launch_bounds__(256) k_top_sort_block(int first_node, int n_nodes, const int4* __restrict__ nodes, int* __restrict__ pairs) {
@@ -1379,7 +1352,7 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
             k_top_fill<<<dim3((unsigned)((max_nt + 255) / 256), (unsigned)n), 256, 0, s>>>(d_jobs.p, nid.p, cells_per_mesh, fillc.p, fillc_per_mesh, F->pairs.p, top_agg);
             MSM_LAUNCH_CHECK();
             if (r.nodes > n) {
-                k_top_sort_warp<<<(unsigned)((r.nodes - n + 7) / 8), 256, 0, s>>>(n, r.nodes, F->nodes.p, F->pairs.p);
+                k_top_sort_warp<<<(unsigned)((r.nodes - n + 15) / 16), 256, 0, s>>>(n, r.nodes, F->nodes.p, F->pairs.p);
                 MSM_LAUNCH_CHECK();
                 if (r.max_list > 256) {
                     k_top_sort_block<<<(unsigned)(r.nodes - n), 256, 0, s>>>(n, r.nodes, F->nodes.p, F->pairs.p);
