@@ -8,10 +8,13 @@ metric_resample builds its trees per call, resampler.cpp:74-78). Metric: resampl
 2 * S * 32 492 output vertices (x100 channels each) per step time.
 
   value : inputs (meshes, targets, features) already resident in HBM; CUDA events, max over ranks
-  e2e   : the same work through the host-buffer C ABI a reference-side adapter calls
-          (msmgpu_mesh_create / msmgpu_mesh_set_features_f32 / msmgpu_mesh_bary_resample_f32 /
-          msmgpu_mesh_metric_resample_f32), pinned host
-          buffers, H2D and D2H copies inside the timed region, 4 worker streams
+  e2e   : the same work through the host-buffer C ABI a reference-side loop calls: ONE msmgpu_resample_batch_host_f32 per step
+          (chunks of subjects pipelined over copy-in / compute / copy-out streams inside the library), pinned host buffers,
+          H2D and D2H copies inside the timed region; the per-subject calls on 8 worker streams beside it ("per_subject_calls")
+  secondary legs of the same line (rank 0; skippable): "parity" (subject 0 at full size against the compiled reference),
+          "e2e_adapter" (the C++ adapter on reference Mesh objects), "gmsm" (BASELINE configs[4], all ranks, NCCL all-gather),
+          "unary_costs" (BASELINE metric ii: unary cost tables, costs/s), "newmsm_wall_time" (BASELINE metric iii on a bounded case:
+          the reference's own program with the library bound in vs the same program on the host cores)
   --impl reference : the reference's own CPU implementation (oracle/_ref, compiled from the
           unmodified sources) on the host cores, one subject per step
 
@@ -56,6 +59,8 @@ def parse():
     ap.add_argument("--e2e-workers", type=int, default=8)
     ap.add_argument("--e2e-chunk", type=int, default=0, help="subjects per pipeline stage of the batch host call (0: the library's default)")
     ap.add_argument("--no-adapter-e2e", action="store_true", help="skip the C++ adapter leg (Mesh in / Mesh out, pageable FP64)")
+    ap.add_argument("--no-newmsm", action="store_true", help="skip the secondary `newmsm` wall-time leg (BASELINE metric iii, ~45 s)")
+    ap.add_argument("--no-unary", action="store_true", help="skip the secondary unary-cost-table leg (BASELINE metric ii)")
     ap.add_argument("--no-gmsm", action="store_true", help="skip the secondary groupwise (gMSM, BASELINE configs[4]) leg")
     ap.add_argument("--gmsm-subjects", type=int, default=int(os.environ.get("BENCH_GMSM_SUBJECTS", 64)))
     ap.add_argument("--gmsm-data-level", type=int, default=6)
@@ -577,6 +582,25 @@ def run_ours(a):
         except Exception as ex:
             adapter = {"error": f"{type(ex).__name__}: {ex}"}
 
+    # BASELINE.json's second quantity, "unary costs/s": one unary cost table N_cp x L (control grid ico4 on data grid ico6, 19 labels)
+    # through msmgpu_costfn_unary_table, univariate and multivariate; the oracle port on the host cores beside it, compared bit for bit
+    unary = None
+    if rank == 0 and world == 1 and not a.no_unary:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import bench_unary
+            unary = {"cases": bench_unary.run_cases(4, 6, 10, cpu=not a.no_cpu_baseline),
+                     "api": "msmgpu_costfn_unary_table: host rotation matrices + upload + k_unary_table + table download, median of 10"}
+        except Exception as ex:
+            unary = {"error": f"{type(ex).__name__}: {ex}"}
+
+    newmsm = None
+    if rank == 0 and world == 1 and not a.no_newmsm:
+        try:
+            newmsm = run_newmsm_leg()
+        except Exception as ex:
+            newmsm = {"error": f"{type(ex).__name__}: {ex}"}
+
     if rank == 0:
         cfg = workload_config(a, nv, nt, n_low)
         detail = {"query_group_lanes": int(L.msmgpu_get_query_group()), "breakdown_ms_per_step": breakdown, "value_streams": NW,
@@ -593,6 +617,10 @@ def run_ours(a):
             line["e2e"] = e2e
         if adapter is not None:
             line["e2e_adapter"] = adapter
+        if unary is not None:
+            line["unary_costs"] = unary
+        if newmsm is not None:
+            line["newmsm_wall_time"] = newmsm
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
         print(json.dumps(line), flush=True)
@@ -867,6 +895,32 @@ def run_e2e(a, torch, R, capi, L, local, S, D, host_xyz, tri, low_xyz, low_tri, 
                    "out; chunks of subjects pipelined over copy-in / compute / copy-out streams inside the library), pinned host buffers",
             "h2d_GBs": h2d_batch * a.steps / dt_batch / 1e9,
             "per_subject_calls": per_subject}
+
+
+def run_newmsm_leg():
+    """BASELINE.json's third quantity, "`newmsm` wall-time vs CPU cores", on a bounded case: the reference's own program — CLI, config
+    parsing, drivers, FastPD solver, unmodified — with libmsmgpu.so bound in at link time (integration/_build/newmsm_gpu) against the
+    same program on the host cores (oracle/_ref/newmsm_ref_trace, all threads), on `basic_configs/config_standard_MSMpair` semantics
+    (three DISCRETE levels, 19 iterations) at ico5. Parity: the labeling and every traced mesh of every iteration against the
+    single-thread reference trace recorded by tests/newmsm_e2e.py --cpu-trace-out (the multi-threaded reference races).
+    Full-size cases (ico6, cfg1 / cfg3 / cfg4, gMSM) take minutes per arm: profiles/*newmsm_e2e*, DESIGN §6b."""
+    trace = os.path.join(ROOT, "tests", "golden", "newmsm_cfg1_MSMpair_ico5_single_thread_trace.txt")
+    for need in (trace, os.path.join(ROOT, "integration", "_build", "newmsm_gpu"), os.path.join(ROOT, "oracle", "_ref", "newmsm_ref_trace")):
+        if not os.path.exists(need):
+            return {"unavailable": "missing " + os.path.relpath(need, ROOT)}
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    with tempfile.TemporaryDirectory() as td:
+        out = os.path.join(td, "res.json")
+        subprocess.run([sys.executable, os.path.join(ROOT, "tests", "newmsm_e2e.py"), "--level", "5", "--config", "MSMpair", "--D", "1",
+                        "--threads", str(threads), "--cpu-trace-in", trace, "--out", out],
+                       check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=900)
+        r = json.load(open(out))
+    return {"workload": "newmsm, config_standard_MSMpair semantics (3 DISCRETE levels, FastPD, D = 1), ico5 input / reference meshes, synthetic warp",
+            "gpu_wall_s": r["gpu_wall_s"], "cpu_wall_s": r["cpu_wall_s"], "cpu_threads": r["cpu_threads"], "speedup": r["speedup"],
+            "discrete_iterations": r["discrete_iterations"], "labels_bit_exact": r.get("labels_bit_exact"),
+            "all_meshes_bit_exact": r.get("all_meshes_bit_exact"), "parity_against": "single-thread reference trace " + r.get("cpu_parity_trace", "?"),
+            "gpu_split": r["gpu_split"][-1] if r.get("gpu_split") else None,
+            "note": "process wall clock of both programs incl. file I/O and CUDA start-up; the GPU run's remainder is the reference's host solver"}
 
 
 def main():

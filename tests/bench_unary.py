@@ -31,16 +31,11 @@ def label_grid(spacing):
     return np.array(pts)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--cp", type=int, default=4)
-    ap.add_argument("--data", type=int, default=6)
-    ap.add_argument("--reps", type=int, default=10)
-    ap.add_argument("--no-cpu", action="store_true")
-    a = ap.parse_args()
-    from oracle import bindings as O
-    cp, cp_tri = synth.icosphere(a.cp)
-    xyz, tri = synth.icosphere(a.data)
+def run_cases(cp_level=4, data_level=6, reps=10, cpu=True):
+    """One JSON-able dict per case (univariate D = 1, multivariate D = 40). cpu: also time the oracle port on the same table and
+    compare bit for bit (the only place this module touches oracle/)."""
+    cp, cp_tri = synth.icosphere(cp_level)
+    xyz, tri = synth.icosphere(data_level)
     src = synth.smooth_warp(xyz, max_disp=4.0, seed=2024)
     e = np.zeros(len(cp))
     for i, j in ((0, 1), (1, 2), (0, 2)):
@@ -52,6 +47,7 @@ def main():
     rot = R.estimate_rotation_matrix(np.tile(centre, (len(cp), 1)), cp).reshape(-1, 9)
     target = R.Mesh(xyz, tri)
     tree = R.Octree(target)
+    out = []
     for name, cls, kind, D in (("univariate corr, D=1", DC.UnivariateNonLinearSRegDiscreteCostFunction, 0, 1),
                                ("multivariate corr, D=40", DC.MultivariateNonLinearSRegDiscreteCostFunction, 1, 40)):
         ref_feat = synth.smooth_fields(xyz, D)
@@ -64,24 +60,37 @@ def main():
         prow, pmem = cf.get_source_data()
         cf.computeUnaryCosts(labels, rot)
         ts = []
-        for _ in range(a.reps):
+        for _ in range(reps):
             t0 = time.perf_counter()
             costs = cf.computeUnaryCosts(labels, rot)
             ts.append(time.perf_counter() - t0)
         t = float(np.median(ts))
         n_costs = costs.size
-        line = {"metric": "unary costs/s", "case": name, "cp_grid": f"ico{a.cp}", "data_grid": f"ico{a.data}", "labels": len(labels),
+        line = {"metric": "unary costs/s", "case": name, "cp_grid": f"ico{cp_level}", "data_grid": f"ico{data_level}", "labels": len(labels),
                 "costs": int(n_costs), "patch_points": int(prow[-1]), "queries_per_table": int(prow[-1]) * len(labels),
                 "value": n_costs / t, "unit": "costs/s", "ms_per_table": 1e3 * t, "resampled_verts_per_s": int(prow[-1]) * len(labels) / t,
                 "patch_membership_ms": 1e3 * t_patch, "query_group_lanes": int(capi.lib().msmgpu_get_query_group())}
-        if not a.no_cpu:
+        if cpu:
+            from oracle import bindings as O
             ot = O.OracleOctree(xyz, tri)
-            threads = os.cpu_count() or 1
+            threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
             t0 = time.perf_counter()
             ref = O.oracle_unary_costs(kind, 2, ot, cp, rot, labels, src, prow, pmem, src_feat, ref_feat, None, np.ones(len(cp)), nthreads=threads)
             tc = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": n_costs / tc, "unit": "costs/s", "cores": threads, "kind": "port", "sample": "the same full table, one pass"}
             line["bit_exact_vs_cpu"] = bool(np.array_equal(ref, costs))
+        out.append(line)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cp", type=int, default=4)
+    ap.add_argument("--data", type=int, default=6)
+    ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    for line in run_cases(a.cp, a.data, a.reps, not a.no_cpu):
         print(json.dumps(line), flush=True)
 
 
