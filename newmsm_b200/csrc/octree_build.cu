@@ -696,12 +696,6 @@ __global__ void k_init_roots(int n, int4* nodes, BuildNode* bn, unsigned char* n
 // triangle count (cells of depth D0-1 hold >= 64 triangles on average on a sphere); knob "build_top" (MSMGPU_BUILD_TOP): -1 auto,
 // 0 off, k force D0 = k.
 // ------------------------------------------------------------------------------------------
-#ifndef TOPC_MINB
-#define TOPC_MINB 6
-#endif
-#ifndef TOPF_MINB
-#define TOPF_MINB 8
-#endif
 constexpr int kTopMaxDepth = 6;
 constexpr int kTopTrisPerBlock = 1024;   // k_top_count: 256 threads x 4 triangles
 constexpr int kTopNone = -0x40000000;    // nid entries at or below this: the cell has no node
@@ -810,7 +804,7 @@ __device__ __forceinline__ void top_warp_add(bool on, const TopCells& c, F&& add
     }
 }
 
-__global__ void __launch_bounds__(256, TOPC_MINB) k_top_count(const TopJob* __restrict__ jobs, unsigned* __restrict__ cnt, long long cells_per_mesh, int agg) {
+__global__ void __launch_bounds__(256) k_top_count(const TopJob* __restrict__ jobs, unsigned* __restrict__ cnt, long long cells_per_mesh, int agg) {
     __shared__ unsigned s_cnt[8 + 64 + 512];   // depths 1..3
     const TopJob job = jobs[blockIdx.y];
     const int t0 = blockIdx.x * kTopTrisPerBlock;
@@ -1040,7 +1034,7 @@ __global__ void __launch_bounds__(256) k_top_children(int n, int d, const TopJob
     }
 }
 
-__global__ void __launch_bounds__(256, TOPF_MINB) k_top_fill(const TopJob* __restrict__ jobs, int* __restrict__ nid, long long cells_per_mesh,
+__global__ void __launch_bounds__(256) k_top_fill(const TopJob* __restrict__ jobs, int* __restrict__ nid, long long cells_per_mesh,
                                                   int* __restrict__ fillc, long long fillc_per_mesh, int* __restrict__ pairs, int agg) {
     const TopJob job = jobs[blockIdx.y];
     if ((long long)blockIdx.x * blockDim.x >= job.nt || job.d0 <= 0) return;   // whole CTA beyond this mesh
