@@ -210,6 +210,9 @@ msmgpu_status morton_order(const double* d_xyz, int n, DevBuf<int>& perm, cudaSt
 msmgpu_status launch_bary_weights_batch(const QueryJob* d_jobs, int n_jobs, int max_n, int* d_idx, double* d_w, int* d_ne, int* d_status, cudaStream_t s,
                                         bool lazy = false);   // lazy: every job's tree comes without records
 msmgpu_status ensure_records(msmgpu_mesh* m);
+// jobs that share one tree, one point count and one processing order, the subject on the lanes (query.cu: k_bary_weights_across)
+msmgpu_status launch_bary_weights_across(const TreeView& t, const int* d_perm, const double* const* d_pts, const int* d_out_off, int n_jobs, int n,
+                                         int* d_idx, double* d_w, int* d_ne, int* d_status, cudaStream_t s);
 
 struct ResampleJob {      // one subject of a batched fused resample
     TreeView tree;

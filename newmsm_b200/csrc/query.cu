@@ -95,6 +95,35 @@ __global__ void __launch_bounds__(256, MINB) k_bary_weights_batch(const QueryJob
     out_status[o] = st;
 }
 
+// The same for jobs that share ONE tree and one point count (the reverse queries of a batch: every subject's vertices located in the
+// target sphere's tree), with the SUBJECT on the lanes: thread g handles point perm[g / n_jobs] of subject g % n_jobs. Subjects of a
+// batch share one topology and nearly the same geometry, so the 32 lanes of a warp descend to the same leaf and test the same
+// candidates: node, list, cull-sphere and record loads become broadcasts (one L1 wavefront per request instead of ~2.8,
+// profiles/r2_gather_summary.md: the kernel is bound by L1 wavefronts). Outputs are written at the point's own slot: same results.
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) k_bary_weights_across(TreeView T, const int* __restrict__ perm, const double* const* __restrict__ pts,
+                                                                   const int* __restrict__ out_off, int n_jobs, int n, int* __restrict__ out_idx,
+                                                                   double* __restrict__ out_w, int* __restrict__ out_ne, int* __restrict__ out_status) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = g < (long long)n * n_jobs;
+    const int j = active ? (int)(g % n_jobs) : 0;
+    const int k = active ? (int)(g / n_jobs) : 0;
+    const int q = perm ? __ldg(perm + k) : k;
+    const V3 pt = active ? load_pt(pts[j], q) : V3{0, 0, 0};
+    int st;
+    const int t = nearest_triangle<1>(T, pt, active, 0, st);
+    if (!active) return;
+    int idx[3] = {-1, -1, -1};
+    double w[3] = {0, 0, 0};
+    int ne = 0;
+    if (t >= 0) ne = sorted_weights(T, t, pt, idx, w);
+    const size_t o = (size_t)__ldg(out_off + j) + q;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { out_idx[3 * o + i] = idx[i]; out_w[3 * o + i] = w[i]; }
+    out_ne[o] = ne;
+    out_status[o] = st;
+}
+
 // sphere_project_warp (resampler.cpp:311-328, reproject = 1) / surface_resample (284-302, reproject = 0):
 // newPt = sum over the weight map (ascending id) of payload[id] * w, optionally normalised * 100.
 template <int G>
@@ -350,6 +379,18 @@ msmgpu_status launch_bary_weights_batch(const QueryJob* d_jobs, int n_jobs, int 
         case 5: MSM_DISPATCH_G(g, (k_bary_weights_batch<G, 5><<<grid, 256, 0, s>>>(d_jobs, d_idx, d_w, d_ne, d_status))); break;
         default: MSM_DISPATCH_G(g, (k_bary_weights_batch<G, 4><<<grid, 256, 0, s>>>(d_jobs, d_idx, d_w, d_ne, d_status))); break;
     }
+    MSM_LAUNCH_CHECK();
+    return MSMGPU_OK;
+}
+
+msmgpu_status launch_bary_weights_across(const TreeView& t, const int* d_perm, const double* const* d_pts, const int* d_out_off, int n_jobs, int n,
+                                         int* d_idx, double* d_w, int* d_ne, int* d_status, cudaStream_t s) {
+    if (n_jobs <= 0 || n <= 0) return MSMGPU_OK;
+    const unsigned blocks = (unsigned)(((long long)n * n_jobs + 255) / 256);
+    if (tuning_get("weights_minb", "MSMGPU_WEIGHTS_MINB", 4) == 3)
+        k_bary_weights_across<3><<<blocks, 256, 0, s>>>(t, d_perm, d_pts, d_out_off, n_jobs, n, d_idx, d_w, d_ne, d_status);
+    else
+        k_bary_weights_across<4><<<blocks, 256, 0, s>>>(t, d_perm, d_pts, d_out_off, n_jobs, n, d_idx, d_w, d_ne, d_status);
     MSM_LAUNCH_CHECK();
     return MSMGPU_OK;
 }

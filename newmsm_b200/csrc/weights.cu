@@ -550,7 +550,18 @@ msmgpu_status adaptive_weights_build_batch(msmgpu_ctx* ctx, int S, msmgpu_mesh* 
     MSM_CUDA(st.alloc((size_t)(NL + NV), s));
     if (fwd) MSM_CUDA(cudaMemsetAsync(st.p, 0, (size_t)NL * sizeof(int), s));   // the fused kernel already reported the forward statuses
     else MSM_TRY(launch_bary_weights_batch(d_jobs.p, S, n_low, fidx_own.p, fw_own.p, fne_own.p, st.p, s, lazy_fwd));
-    MSM_TRY(launch_bary_weights_batch(d_jobs.p + S, S, max_nv, ridx.p, rw.p, rne.p, st.p + NL, s));
+    // reverse queries: with enough subjects of one size (one topology, nearly one geometry) the subject goes on the lanes
+    bool across = S >= 8 && tuning_get("reverse_across", "MSMGPU_REVERSE_ACROSS", 1) != 0;
+    for (int i = 0; across && i < S; ++i) across = in_meshes[i]->nv == in_meshes[0]->nv;
+    if (across) {
+        std::vector<const double*> h_pts(S);
+        for (int i = 0; i < S; ++i) h_pts[i] = in_meshes[i]->xyz.p;
+        DevBuf<const double*> d_pts;
+        MSM_CUDA(d_pts.alloc(S, s));
+        MSM_CUDA(cudaMemcpyAsync(d_pts.p, h_pts.data(), S * sizeof(double*), cudaMemcpyHostToDevice, s));   // pageable: staged before return
+        MSM_TRY(launch_bary_weights_across(low_tree->view(), perm_rev.p, d_pts.p, d_in_off.p, S, in_meshes[0]->nv, ridx.p, rw.p, rne.p, st.p + NL, s));
+    } else
+        MSM_TRY(launch_bary_weights_batch(d_jobs.p + S, S, max_nv, ridx.p, rw.p, rne.p, st.p + NL, s));
     int code = 0;
     MSM_TRY(first_error(st.p, (size_t)(NL + NV), s, &code));   // synchronises: `jobs` / `in_off` may now go
     if (code) return status_to_error(code);
