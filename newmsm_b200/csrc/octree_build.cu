@@ -94,6 +94,33 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_tiles(const int* __restri
     if (total_out && blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) *total_out = off;
 }
 
+// second kernel of the two-launch form: every CTA first adds up the sums of the tiles before its own (at most kScanTile of them,
+// kScanItems per thread) instead of reading them from a third, recursive launch
+__global__ void __launch_bounds__(kScanThreads) k_scan_tiles_from_sums(const int* __restrict__ in, int* __restrict__ out, int n,
+                                                                       const int* __restrict__ tile_sums, int* __restrict__ total_out) {
+    __shared__ int sw[33];
+    int before = 0;
+    for (int t = threadIdx.x; t < (int)blockIdx.x; t += kScanThreads) before += tile_sums[t];
+    int tile_off;
+    block_exclusive_scan(before, sw, tile_off);   // tile_off = block total = sum of the sums of tiles 0 .. blockIdx.x - 1
+    const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    int v[kScanItems];
+    int acc = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        v[k] = (base + k < n) ? in[base + k] : 0;
+        acc += v[k];
+    }
+    int total;
+    int off = block_exclusive_scan(acc, sw, total) + tile_off;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        if (base + k < n) out[base + k] = off;
+        off += v[k];
+    }
+    if (total_out && blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) *total_out = off;
+}
+
 msmgpu_status exclusive_scan_i32(const int* d_in, int* d_out, int n, int* d_total, cudaStream_t s) {
     if (n <= 0) {
         if (d_total) MSM_CUDA(cudaMemsetAsync(d_total, 0, sizeof(int), s));
@@ -107,9 +134,14 @@ msmgpu_status exclusive_scan_i32(const int* d_in, int* d_out, int n, int* d_tota
     }
     DevBuf<int> sums, offs;
     MSM_CUDA(sums.alloc(tiles, s));
-    MSM_CUDA(offs.alloc(tiles, s));
     k_scan_tile_sums<<<tiles, kScanThreads, 0, s>>>(d_in, n, sums.p);
     MSM_LAUNCH_CHECK();
+    if (tiles <= kScanTile) {   // up to 4 M elements: two launches
+        k_scan_tiles_from_sums<<<tiles, kScanThreads, 0, s>>>(d_in, d_out, n, sums.p, d_total);
+        MSM_LAUNCH_CHECK();
+        return MSMGPU_OK;
+    }
+    MSM_CUDA(offs.alloc(tiles, s));
     MSM_TRY(exclusive_scan_i32(sums.p, offs.p, tiles, nullptr, s));
     k_scan_tiles<<<tiles, kScanThreads, 0, s>>>(d_in, d_out, n, offs.p, d_total);
     MSM_LAUNCH_CHECK();
