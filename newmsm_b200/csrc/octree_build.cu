@@ -191,7 +191,8 @@ struct TableJob {
     const double* xyz; const int* tri; TriRec* rec; double* area; float4* cull; uint4* qbox; int nt;
 };
 
-__global__ void __launch_bounds__(256) k_mesh_tables(const TableJob* __restrict__ jobs) {
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) k_mesh_tables(const TableJob* __restrict__ jobs) {
     // the 128-byte records of a warp's 32 triangles are contiguous (4 KB): they are transposed through shared memory so that every
     // store instruction of the warp writes 256 consecutive bytes instead of 32 lines at a 128-byte stride
     __shared__ double s_rec[8][32 * 17];
@@ -261,7 +262,12 @@ msmgpu_status ensure_tables(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes) 
     DevBuf<TableJob> d_jobs;
     MSM_CUDA(d_jobs.alloc(jobs.size(), s));
     MSM_CUDA(cudaMemcpyAsync(d_jobs.p, jobs.data(), jobs.size() * sizeof(TableJob), cudaMemcpyHostToDevice, s));   // pageable: staged before return
-    k_mesh_tables<<<dim3((unsigned)((max_nt + 255) / 256), (unsigned)jobs.size()), 256, 0, s>>>(d_jobs.p);
+    switch (tuning_get("tables_minb", "MSMGPU_TABLES_MINB", 5)) {   // resident CTAs per SM; measured 3 / 4 / 5 / 6: tables + forest 3.44 / 3.35 / 3.32 / 3.56 ms (ncu: FP64 pipe 51 % at 35 % occupancy with the compiler's 72 registers)
+        case 4: k_mesh_tables<4><<<dim3((unsigned)((max_nt + 255) / 256), (unsigned)jobs.size()), 256, 0, s>>>(d_jobs.p); break;
+        case 3: k_mesh_tables<3><<<dim3((unsigned)((max_nt + 255) / 256), (unsigned)jobs.size()), 256, 0, s>>>(d_jobs.p); break;
+        case 6: k_mesh_tables<6><<<dim3((unsigned)((max_nt + 255) / 256), (unsigned)jobs.size()), 256, 0, s>>>(d_jobs.p); break;
+        default: k_mesh_tables<5><<<dim3((unsigned)((max_nt + 255) / 256), (unsigned)jobs.size()), 256, 0, s>>>(d_jobs.p); break;
+    }
     MSM_LAUNCH_CHECK();
     return MSMGPU_OK;
 }
@@ -275,7 +281,7 @@ msmgpu_status ensure_records(msmgpu_mesh* m) {
     DevBuf<TableJob> d_job;
     MSM_CUDA(d_job.alloc(1, s));
     MSM_CUDA(cudaMemcpyAsync(d_job.p, &job, sizeof(TableJob), cudaMemcpyHostToDevice, s));   // pageable: staged before return
-    k_mesh_tables<<<dim3((unsigned)((m->nt + 255) / 256), 1u), 256, 0, s>>>(d_job.p);
+    k_mesh_tables<5><<<dim3((unsigned)((m->nt + 255) / 256), 1u), 256, 0, s>>>(d_job.p);
     MSM_LAUNCH_CHECK();
     return MSMGPU_OK;
 }
