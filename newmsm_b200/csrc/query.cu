@@ -387,10 +387,11 @@ msmgpu_status launch_bary_weights_across(const TreeView& t, const int* d_perm, c
                                          int* d_idx, double* d_w, int* d_ne, int* d_status, cudaStream_t s) {
     if (n_jobs <= 0 || n <= 0) return MSMGPU_OK;
     const unsigned blocks = (unsigned)(((long long)n * n_jobs + 255) / 256);
-    if (tuning_get("weights_minb", "MSMGPU_WEIGHTS_MINB", 4) == 3)
-        k_bary_weights_across<3><<<blocks, 256, 0, s>>>(t, d_perm, d_pts, d_out_off, n_jobs, n, d_idx, d_w, d_ne, d_status);
-    else
-        k_bary_weights_across<4><<<blocks, 256, 0, s>>>(t, d_perm, d_pts, d_out_off, n_jobs, n, d_idx, d_w, d_ne, d_status);
+    switch (tuning_get("across_minb", "MSMGPU_ACROSS_MINB", 4)) {   // resident CTAs per SM
+        case 3: k_bary_weights_across<3><<<blocks, 256, 0, s>>>(t, d_perm, d_pts, d_out_off, n_jobs, n, d_idx, d_w, d_ne, d_status); break;
+        case 5: k_bary_weights_across<5><<<blocks, 256, 0, s>>>(t, d_perm, d_pts, d_out_off, n_jobs, n, d_idx, d_w, d_ne, d_status); break;
+        default: k_bary_weights_across<4><<<blocks, 256, 0, s>>>(t, d_perm, d_pts, d_out_off, n_jobs, n, d_idx, d_w, d_ne, d_status); break;
+    }
     MSM_LAUNCH_CHECK();
     return MSMGPU_OK;
 }
