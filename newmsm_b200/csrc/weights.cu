@@ -643,7 +643,8 @@ struct ApplyJob {
     const double* excl;  // optional [n_cols]: entries whose source vertex has excl == 0 are skipped (resampler.cpp:46-47, 62-63)
 };
 
-__global__ void __launch_bounds__(256) k_csr_apply_f32x4(const ApplyJob* __restrict__ jobs, int n_rows, const int* __restrict__ col,
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) k_csr_apply_f32x4(const ApplyJob* __restrict__ jobs, int n_rows, const int* __restrict__ col,
                                                          const double* __restrict__ val, int D4) {
     const ApplyJob job = jobs[blockIdx.y];
     const long long slot = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -730,7 +731,12 @@ static msmgpu_status csr_apply_batch(msmgpu_ctx* ctx, int n, msmgpu_weights* con
     if (vec) {
         const int D4 = D >> 2;
         const long long slots = (long long)n_rows * D4;
-        k_csr_apply_f32x4<<<dim3((unsigned)((slots + 255) / 256), (unsigned)n), 256, 0, s>>>(d_jobs.p, n_rows, store->col.p, store->val.p, D4);
+        const dim3 grid((unsigned)((slots + 255) / 256), (unsigned)n);
+        switch (tuning_get("apply_minb", "MSMGPU_APPLY_MINB", 5)) {   // resident CTAs per SM (5 = the compiler's 48 registers)
+            case 6: k_csr_apply_f32x4<6><<<grid, 256, 0, s>>>(d_jobs.p, n_rows, store->col.p, store->val.p, D4); break;
+            case 8: k_csr_apply_f32x4<8><<<grid, 256, 0, s>>>(d_jobs.p, n_rows, store->col.p, store->val.p, D4); break;
+            default: k_csr_apply_f32x4<5><<<grid, 256, 0, s>>>(d_jobs.p, n_rows, store->col.p, store->val.p, D4); break;
+        }
     } else {
         const long long slots = (long long)n_rows * D;
         k_csr_apply<T><<<dim3((unsigned)((slots + 255) / 256), (unsigned)n), 256, 0, s>>>(d_jobs.p, n_rows, store->col.p, store->val.p, D);
