@@ -1269,15 +1269,16 @@ def test_octree_top_phase_matches_level_passes(R, oracle_built, meshes, top):
         assert list(kinds) == [1] and list(counts) == [2] and list(tris) == [0, 1]
     finally:
         capi.check(L.msmgpu_set_tuning(b"build_top", -1))
+        capi.check(L.msmgpu_set_tuning(b"build_top_order", 0))
         capi.check(L.msmgpu_set_tuning(b"lazy_records", 1))
 
 
 @pytest.mark.parametrize("top", [-1, 3, 6])
 def test_octree_top_phase_shared_topology_order(R, oracle_built, meshes, top):
-    """Five subjects that share one topology (device views): the top phase processes their triangles along one Morton order of the
-    first subject's triangles and aggregates its atomics per warp — the forests must equal the exact level passes (knob 0) and the
-    oracle, and the barycentric weight maps of queries in those trees (records deferred: built from the corners) must be the
-    per-mesh ones bit for bit."""
+    """Five subjects that share one topology (device views, as a batch job creates them): the forests of the top phase must equal the
+    exact level passes (knob 0) and the oracle — also with the optional Morton processing order of the triangles, which shared
+    topologies enable (knob build_top_order) — and the batched resample in those trees (records deferred: record values built from
+    the corners) must give the values of the stored-record path bit for bit."""
     import torch
     L = capi.lib()
     ctx = R.Context(0)
@@ -1295,10 +1296,12 @@ def test_octree_top_phase_shared_topology_order(R, oracle_built, meshes, top):
         want_dump = [t.dump() for t in want]
         assert all(np.array_equal(a, b) for a, b in zip(want_dump[0], oracle_built.OracleOctree(xyz[0], tri).dump()))
         capi.check(L.msmgpu_set_tuning(b"build_top", top))
-        views = R.Mesh.views_from_device(ctx, len(xyz[0]), d_xyz, len(tri), d_tri)
-        trees = R.Octree.build_batch(views)
-        for s in range(S):
-            assert all(np.array_equal(a, b) for a, b in zip(want_dump[s], trees[s].dump())), f"subject {s}"
+        for order in (1, 0):
+            capi.check(L.msmgpu_set_tuning(b"build_top_order", order))
+            views = R.Mesh.views_from_device(ctx, len(xyz[0]), d_xyz, len(tri), d_tri)
+            trees = R.Octree.build_batch(views)
+            for s in range(S):
+                assert all(np.array_equal(a, b) for a, b in zip(want_dump[s], trees[s].dump())), f"subject {s}, order {order}"
         # batched resample in the view trees with deferred records (values built from the corners) against the same call on views that
         # store their records, and the statuses against the per-mesh queries
         d_q = torch.from_numpy(np.ascontiguousarray(q)).to(dev)
@@ -1329,4 +1332,5 @@ def test_octree_top_phase_shared_topology_order(R, oracle_built, meshes, top):
             assert np.array_equal(st[s], want[s].query(q)[2]), f"statuses, subject {s}"
     finally:
         capi.check(L.msmgpu_set_tuning(b"build_top", -1))
+        capi.check(L.msmgpu_set_tuning(b"build_top_order", 0))
         capi.check(L.msmgpu_set_tuning(b"lazy_records", 1))
