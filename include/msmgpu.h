@@ -60,7 +60,7 @@ int msmgpu_get_query_group(void);
 /* Other tuning knobs with no effect on results (launch variants that profiles/ compares): "gather" (1 = bulk-copy row gather for
  * rows >= 128 bytes, 0 = register-path kernels), "gather_variant", "gather_variant_bary", "resample_variant", "weights_minb",
  * "query_order", "build_top" (-1 auto / 0 off / k: depth of the one-pass construction of the first octree levels), "build_top_order",
- * "build_top_agg", "lazy_records" (1: view-batch meshes defer their 128-byte records), "reverse_across" (1: reverse queries of a batch
+ * "build_top_agg", "build_fused_levels", "lazy_records" (1: view-batch meshes defer their 128-byte records), "reverse_across" (1: reverse queries of a batch
  * with the subject on the lanes), "tables_minb", "across_minb", "apply_minb", "batch_chunk" ... Each starts from its MSMGPU_<NAME>
  * environment variable. */
 msmgpu_status msmgpu_set_tuning(const char* name, int value);

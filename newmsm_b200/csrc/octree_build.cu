@@ -1233,6 +1233,118 @@ __global__ void k_iota(int n, int* __restrict__ out) {
     if (i < n) out[i] = i;
 }
 
+// ------------------------------------------------------------------------------------------
+// One level pass in ONE kernel, for levels whose lists are short (the levels below the top phase: <= a few hundred triangles per
+// node): a warp owns a node, walks its list in chunks of 32 — lattice classification, running sum of a = split_size - 3 by warp
+// scan, the reference's prefix rule (some prefix of length >= 50 with a negative sum, octree.cpp:69-102), per-child counts by
+// ballots — and, if the node splits, takes 8 node records and the children's list space from atomic cursors and scatters the ids
+// in list order (ballot rank). That replaces k_chunk_stats, k_node_combine, two device scans, k_save_lists, k_make_children and
+// k_scatter_chunk (12 launches and their buffers) of the chunked level pass, which stays for long lists and for levels below the
+// lattice. Same decisions, same lists; node numbering by cursor.
+// ------------------------------------------------------------------------------------------
+struct FuseCursors { unsigned long long pairs; int nodes, live, max_cnt, overflow; };
+constexpr int kFuseMaxList = 2048;
+
+__global__ void __launch_bounds__(256) k_level_fused(int node_begin, const int* __restrict__ live, int n_live, const int* __restrict__ node_map,
+                                                     int4* __restrict__ nodes, BuildNode* __restrict__ bn, unsigned char* __restrict__ node_depth,
+                                                     int* __restrict__ pairs, const uint4* const* __restrict__ mesh_qbox,
+                                                     unsigned char* __restrict__ pmask, int level_base, double root_half, FuseCursors* __restrict__ cur,
+                                                     int* __restrict__ next_nodes, int next_cap, int node_cap, long long pair_cap) {
+    const int slot = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (slot >= n_live) return;                         // warp-uniform
+    const int li = live ? live[slot] : slot;
+    const int g = level_node(node_map, node_begin, li);
+    const int4 nd = nodes[g];
+    const int cnt = nd.z;
+    if (nd.x >= 0 || cnt < kMaxTriangles) return;       // octree.cpp:69: the test only runs from 50 triangles on
+    const BuildNode b = bn[g];
+    const uint4* __restrict__ qbox = mesh_qbox[b.mesh];
+    int L0[3];
+    const double h = 2.0 * kBounds / (double)(1 << kGridBits);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) L0[d] = (int)((b.lo[d] + kBounds) / h);   // exact: the corner is a lattice line
+    const int Hh = 1 << (kGridMaxDepth - b.depth);
+    unsigned char* __restrict__ pm = pmask + (size_t)(nd.y - level_base);
+    int run = 0, ccnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool split = false;
+    for (int p0 = 0; p0 < cnt; p0 += 32) {
+        const int p = p0 + lane;
+        int a = 0;
+        unsigned mask = 0;
+        if (p < cnt) {
+            classify_q(__ldg(qbox + __ldg(pairs + nd.y + p)), L0, Hh, a, mask);
+            pm[p] = (unsigned char)mask;
+        }
+        int inc = a;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (p < cnt && p + 1 >= kMaxTriangles && run + inc < 0) split = true;
+        run += __shfl_sync(0xffffffffu, inc, 31);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) ccnt[c] += __popc(__ballot_sync(0xffffffffu, (mask >> c) & 1u));
+    }
+    if (!__any_sync(0xffffffffu, split)) return;
+    int total = 0, n_next = 0, cmax = 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { total += ccnt[c]; n_next += ccnt[c] >= kMaxTriangles; cmax = max(cmax, ccnt[c]); }
+    int first = 0, lslot = 0;
+    unsigned long long off = 0;
+    if (lane == 0) {
+        first = atomicAdd(&cur->nodes, 8);
+        off = atomicAdd(&cur->pairs, (unsigned long long)total);
+        if (n_next) lslot = atomicAdd(&cur->live, n_next);
+        atomicMax(&cur->max_cnt, cmax);
+        if (first + 8 > node_cap || off + (unsigned long long)total > (unsigned long long)pair_cap || lslot + n_next > next_cap) cur->overflow = 1;
+    }
+    first = __shfl_sync(0xffffffffu, first, 0);
+    off = __shfl_sync(0xffffffffu, off, 0);
+    lslot = __shfl_sync(0xffffffffu, lslot, 0);
+    if (first + 8 > node_cap || off + (unsigned long long)total > (unsigned long long)pair_cap || lslot + n_next > next_cap) return;
+    int coff[8];
+    {
+        int acc = (int)off;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { coff[c] = acc; acc += ccnt[c]; }
+    }
+    if (lane == 0) nodes[g] = make_int4(first, nd.y, 0, nd.w);   // clear_triangles(), octree.cpp:129
+    {
+        const double half = ldexp(root_half, -b.depth);
+        int ls = lslot;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            if (lane == c) {
+                BuildNode cb;
+                cb.lo[0] = b.lo[0] + ((c & 4) ? half : 0.0);   // node.cpp:99-106
+                cb.lo[1] = b.lo[1] + ((c & 2) ? half : 0.0);
+                cb.lo[2] = b.lo[2] + ((c & 1) ? half : 0.0);
+                cb.mesh = b.mesh;
+                cb.depth = b.depth + 1;
+                bn[first + c] = cb;
+                node_depth[first + c] = (unsigned char)(b.depth + 1);
+                nodes[first + c] = make_int4(-1, coff[c], ccnt[c], g);
+                if (ccnt[c] >= kMaxTriangles) next_nodes[ls] = first + c;
+            }
+            ls += ccnt[c] >= kMaxTriangles;
+        }
+    }
+    const unsigned lt = (1u << lane) - 1u;
+    for (int p0 = 0; p0 < cnt; p0 += 32) {
+        const int p = p0 + lane;
+        const unsigned mask = p < cnt ? pm[p] : 0u;
+        const int tid = p < cnt ? pairs[nd.y + p] : 0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const unsigned bal = __ballot_sync(0xffffffffu, (mask >> c) & 1u);
+            if ((mask >> c) & 1u) pairs[coff[c] + __popc(bal & lt)] = tid;
+            coff[c] += __popc(bal);
+        }
+    }
+}
+
 static int top_depth_for(int nt, int knob) {
     if (knob == 0) return 0;
     if (knob > 0) return std::min(knob, kTopMaxDepth);
@@ -1430,7 +1542,56 @@ msmgpu_status forest_build(msmgpu_ctx* ctx, int n, msmgpu_mesh* const* meshes, s
         double t_enq = 0, t_wait = 0, t_alloc = 0;
         std::vector<cudaEvent_t> evs;
         auto mark = [&] { if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); evs.push_back(e); } };
+        DevBuf<int> fuse_nodes[2];
+        DevBuf<FuseCursors> fuse_cur;
+        int fuse_flip = 0;
+        bool live_valid = true;          // `live` holds the work list of the current level (false: the level is node_map[0 .. n_live) itself)
+        const bool fuse_knob = tuning_get("build_fused_levels", "MSMGPU_BUILD_FUSED_LEVELS", 1) != 0;
         while (n_level > 0) {
+            if (fuse_knob && n_live > 0 && level_max_cnt <= kFuseMaxList && depth + 1 <= kGridMaxDepth) {
+                // short lists: the whole level pass in one kernel (k_level_fused)
+                if (n_pairs > pmask_cap) {
+                    pmask_cap = n_pairs + n_pairs / 4;
+                    MSM_CUDA(pmask.alloc((size_t)pmask_cap, s));
+                }
+                const int pm_base = node_map ? 0 : level_base;   // (after the top phase / a fused level the lists lie anywhere in `pairs`)
+                if (!fuse_cur.p) MSM_CUDA(fuse_cur.alloc(1, s));
+                const int next_cap = (int)std::min<long long>((pair_cap - n_pairs) / kMaxTriangles + 8, 0x3fffffffll);
+                DevBuf<int>& nxt = fuse_nodes[fuse_flip];
+                MSM_CUDA(nxt.alloc((size_t)std::max(next_cap, 1), s));
+                FuseCursors hc{};
+                hc.pairs = (unsigned long long)n_pairs;
+                hc.nodes = n_nodes;
+                MSM_CUDA(cudaMemcpyAsync(fuse_cur.p, &hc, sizeof(FuseCursors), cudaMemcpyHostToDevice, s));   // pageable: staged before return
+                k_level_fused<<<(unsigned)((n_live + 7) / 8), 256, 0, s>>>(node_begin, live_valid ? live.p : nullptr, n_live, node_map, F->nodes.p, bn.p,
+                                                                          F->node_depth.p, F->pairs.p, d_qbox.p, pmask.p, pm_base, root_half, fuse_cur.p,
+                                                                          nxt.p, next_cap, (int)node_cap, pair_cap);
+                MSM_LAUNCH_CHECK();
+                FuseCursors* hr = reinterpret_cast<FuseCursors*>(ctx->pinned ? (void*)ctx->pinned : (void*)&hc);
+                MSM_CUDA(cudaMemcpyAsync(hr, fuse_cur.p, sizeof(FuseCursors), cudaMemcpyDeviceToHost, s));
+                MSM_CUDA(cudaStreamSynchronize(s));
+                const FuseCursors r = *hr;
+                if (r.overflow) { overflow = true; break; }
+                if (r.nodes == n_nodes) break;            // nothing split: done
+                n_nodes = r.nodes;
+                n_pairs = (long long)r.pairs;
+                node_map = nxt.p;                         // the next level = the children that still hold >= 50 triangles
+                fuse_flip ^= 1;
+                live_valid = false;
+                node_begin = 0;
+                n_level = n_live = r.live;
+                level_base = 0;
+                level_entries = n_pairs;
+                level_max_cnt = std::max(1, r.max_cnt);
+                ++depth;
+                if (depth > 40) return fail(MSMGPU_ERR_CAPACITY, "forest_build: depth limit (degenerate mesh?)");
+                continue;
+            }
+            if (!live_valid) {   // back to the chunked pass after fused levels: its work list is the identity over node_map
+                MSM_CUDA(live.alloc((size_t)std::max(n_live, 1), s));
+                if (n_live > 0) { k_iota<<<(n_live + 255) / 256, 256, 0, s>>>(n_live, live.p); MSM_LAUNCH_CHECK(); }
+                live_valid = true;
+            }
             const double t0 = timing ? now() : 0;
             MSM_CUDA(split_flag.alloc(n_level, s));
             MSM_CUDA(split_rank.alloc(n_level, s));

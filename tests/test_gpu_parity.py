@@ -1249,7 +1249,12 @@ def test_octree_top_phase_matches_level_passes(R, oracle_built, meshes, top):
     keys = [2, 4, "j5", 5, 6]
     try:
         capi.check(L.msmgpu_set_tuning(b"build_top", 0))
+        capi.check(L.msmgpu_set_tuning(b"build_fused_levels", 0))      # the chunked level passes alone ...
         want = {k: R.Octree(R.Mesh(*meshes[k])).dump() for k in keys}
+        capi.check(L.msmgpu_set_tuning(b"build_fused_levels", 1))      # ... then also the one-kernel pass for levels with short lists
+        for k in keys:
+            got = R.Octree(R.Mesh(*meshes[k])).dump()
+            assert all(np.array_equal(a, b) for a, b in zip(want[k], got)), f"fused level passes, mesh {k}"
         for k in (3, "j5"):
             ref = oracle_built.OracleOctree(*meshes[k]).dump()
             got = want[k] if k in want else R.Octree(R.Mesh(*meshes[k])).dump()
@@ -1269,6 +1274,7 @@ def test_octree_top_phase_matches_level_passes(R, oracle_built, meshes, top):
         assert list(kinds) == [1] and list(counts) == [2] and list(tris) == [0, 1]
     finally:
         capi.check(L.msmgpu_set_tuning(b"build_top", -1))
+        capi.check(L.msmgpu_set_tuning(b"build_fused_levels", 1))
         capi.check(L.msmgpu_set_tuning(b"build_top_order", 0))
         capi.check(L.msmgpu_set_tuning(b"lazy_records", 1))
 
