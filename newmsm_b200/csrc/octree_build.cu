@@ -16,6 +16,13 @@
 // of those counts a second pass scatters the ids with a stable (order-preserving) ballot rank.
 // Node boxes are dyadic fractions of [-101,101] and are exact in FP64, so midpoints equal the
 // reference's (lo+hi)/2 bit for bit.
+//
+// Three constructions share those invariants and give the same tree (tests/test_gpu_parity.py: test_octree_top_phase_*):
+//   * the TOP PHASE (k_top_*): the first D0 levels of a dense mesh in one pass over its triangles, from the number of triangles that
+//     touch each cell of the 8^d lattices — a sufficient form of the split rule that needs no list order (note above k_top_count);
+//   * k_level_fused: one kernel per level for levels with short lists (a warp per node, the prefix rule by warp scan);
+//   * the chunked level pass (k_chunk_stats / k_node_combine / k_scatter_chunk): teams of threads per list chunk, for long lists
+//     and for levels below the depth-18 lattice.
 #include "common.cuh"
 
 #include <algorithm>
